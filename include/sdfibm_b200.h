@@ -1,0 +1,189 @@
+/*
+ * sdfibm_b200.h — C ABI of the B200-native solid–fluid coupling path.
+ *
+ * This is the drop-in boundary for the ONE hot path of ChenguangZhang/sdfibm that this
+ * repository re-implements on sm_100a: SolidCloud::interact (reference
+ * src/solidcloud.cpp:435-464) with solidFluidInteract (:361-433), CellEnumerator
+ * (src/cellenumerator.cpp:6-78), GeometricTools (src/geometrictools.cpp:6-116), the shape
+ * SDFs (src/libshape/), checkAlpha (:564-570), fixInternal (:288-301) and the collision
+ * step (:477-519, src/libcollision/).
+ *
+ * The reference has no FFI for this path: the seam is the C++ class sdfibm::SolidCloud
+ * (src/solidcloud.h:89-123).  The host façade in sdfibm_b200/host/ keeps that class shape
+ * and calls only the entry points below.  Plain pointers and sizes, no C++/torch types.
+ *
+ * Conventions
+ *   - scalar = double, label = int32_t (reference CMakeLists.txt:20: -DWM_DP -DWM_LABEL_SIZE=32)
+ *   - every entry returns 0 on success, non-zero on error; sdfibm_last_error() gives the
+ *     thread-local message.  The library never calls exit().
+ *   - there is NO CPU fallback: every compute entry fails if no CUDA device is usable.
+ */
+#ifndef SDFIBM_B200_H
+#define SDFIBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFIBM_OK 0
+#define SDFIBM_ERR_ARG 1
+#define SDFIBM_ERR_CUDA 2
+#define SDFIBM_ERR_STATE 3
+#define SDFIBM_ERR_CAPACITY 4
+#define SDFIBM_ERR_UNSUPPORTED 5
+
+/* Shape tags of the device tagged union.  0..2 follow SHAPE2ID (src/libcollision/collision.h:11-15). */
+enum sdfibm_shape_tag {
+    SDFIBM_SHAPE_PLANE = 0,          /* src/libshape/plane.h:13-28 */
+    SDFIBM_SHAPE_CIRCLE = 1,         /* src/libshape/circle.h:15-46 */
+    SDFIBM_SHAPE_SPHERE = 2,         /* src/libshape/sphere.h:14-45 */
+    SDFIBM_SHAPE_ELLIPSE = 3,        /* src/libshape/ellipse.h:14-54 */
+    SDFIBM_SHAPE_ELLIPSOID = 4,      /* src/libshape/ellipsoid.h:15-54 */
+    SDFIBM_SHAPE_RECTANGLE = 5,      /* src/libshape/rectangle.h:16-58 */
+    SDFIBM_SHAPE_BOX = 6,            /* src/libshape/box.h:14-57 */
+    SDFIBM_SHAPE_CIRCLE_TAIL = 7,    /* src/libshape/circle_tail.h:18-61 */
+    SDFIBM_SHAPE_CIRCLE_TWOTAIL = 8, /* src/libshape/circle_twotail.h:18-66 */
+    SDFIBM_SHAPE_NTAGS = 9
+};
+
+/* Cell classification, same numbering as CellEnumerator::CELL_TYPE (src/cellenumerator.h:23). */
+enum sdfibm_cell_type {
+    SDFIBM_CELL_UNVISITED = 0,
+    SDFIBM_CELL_ALL_INSIDE = 1,
+    SDFIBM_CELL_CENTER_INSIDE = 2,
+    SDFIBM_CELL_CENTER_OUTSIDE = 3,
+    SDFIBM_CELL_ALL_OUTSIDE = 4
+};
+
+/*
+ * One registered shape, lowered to a POD record (what IShape subclasses keep as members).
+ * p[] holds the members each reference class derives in its constructor:
+ *   PLANE           -
+ *   CIRCLE, SPHERE  p0 = radius, p1 = radius*radius
+ *   ELLIPSE         p0 = a, p1 = b, p2 = 1/(a*a), p3 = 1/(b*b)
+ *   ELLIPSOID       p0..2 = a,b,c, p3..5 = 1/(a*a), 1/(b*b), 1/(c*c)      (ignores com)
+ *   RECTANGLE       p0 = a, p1 = b (half widths)
+ *   BOX             p0..2 = a,b,c
+ *   CIRCLE_TAIL     p0 = radius, p1 = radius^2, p2 = (ratio+1)*0.5*radius, p3 = thickness
+ *   CIRCLE_TWOTAIL  p0 = radius, p1 = radius^2, p2 = (ratio+1)*0.5*radius, p3 = thickness*0.5
+ */
+typedef struct sdfibm_shape {
+    int32_t tag;      /* enum sdfibm_shape_tag */
+    int32_t finite;   /* IShape::finite (src/libshape/ishape.h:38) */
+    double radiusB;   /* IShape::m_radiusB — used by the narrow phase (collision.cpp:12-13) */
+    double com[3];    /* IShape::m_com, ADDED to the local point (circle.h:40) */
+    double p[8];
+} sdfibm_shape_t;
+
+/* Rigid-body state the path reads (src/solid.h:17-28).  quat = (w, x, y, z). */
+typedef struct sdfibm_solid {
+    double pos[3];
+    double quat[4];
+    double vel[3];
+    double omega[3];
+    int32_t shape; /* index into the shape table */
+    int32_t pad_;
+} sdfibm_solid_t;
+
+/*
+ * The mesh arrays MeshInfo binds (src/meshinfo.h:20-29) plus mesh.cells()/mesh.faces()
+ * (src/geometrictools.cpp:61,66), in CSR form, local (per-rank) numbering.
+ */
+typedef struct sdfibm_mesh {
+    int32_t n_cells, n_points, n_faces, n_internal_faces;
+    const double *points;        /* [n_points*3]  mesh.points()      */
+    const double *cell_centres;  /* [n_cells*3]   mesh.cellCentres() */
+    const double *cell_volumes;  /* [n_cells]     mesh.V()           */
+    const double *face_centres;  /* [n_faces*3]   mesh.faceCentres() */
+    const double *face_areas;    /* [n_faces*3]   mesh.faceAreas()   */
+    const int32_t *cell_points_off; /* [n_cells+1] */
+    const int32_t *cell_points;     /* cellPoints(): ascending point label per cell */
+    const int32_t *cell_faces_off;  /* [n_cells+1] */
+    const int32_t *cell_faces;      /* cells(): owned faces ascending, then neighbour faces */
+    const int32_t *face_points_off; /* [n_faces+1] */
+    const int32_t *face_points;     /* faces(): vertex loop as stored */
+    const int32_t *cell_cells_off;  /* [n_cells+1] */
+    const int32_t *cell_cells;      /* cellCells(): ascending internal-face order */
+    double bounds_min[3], bounds_max[3]; /* mesh.bounds() */
+} sdfibm_mesh_t;
+
+typedef struct sdfibm_context sdfibm_context;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+int sdfibm_version(void);
+const char *sdfibm_last_error(void);
+int sdfibm_device_count(int *count);
+/* One context per rank/GPU; owns one CUDA stream.  replaces SolidCloud ctor device part (solidcloud.cpp:209-217). */
+int sdfibm_create(int device, sdfibm_context **ctx);
+int sdfibm_destroy(sdfibm_context *ctx);
+/* max solids that may touch one mesh cell (default 4); call before sdfibm_set_mesh */
+int sdfibm_set_cell_slots(sdfibm_context *ctx, int slots);
+
+/* ---- one-time uploads ------------------------------------------------------------- */
+/* replaces GeometricTools(mesh)/MeshInfo(mesh) binding (solidcloud.cpp:216, meshinfo.h:20-29) */
+int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *mesh, int two_d);
+/* replaces EntityLibrary<IShape> lookup by pointer (solidcloud.cpp:59, solid.h:47-50) */
+int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n_shapes);
+
+/* ---- SolidCloud::interact (solidcloud.cpp:435-464), host buffers --------------------
+ * U[3*n_cells] in;  As[n_cells], Fs[3*n_cells], Ts[n_cells], Ct[n_cells] out (cell values of
+ * the registered volFields);  force_torque[6*n_solids] out = per-solid (F, T) already
+ * multiplied by rhof (solidcloud.cpp:424-425), BEFORE any cross-rank reduction. */
+int sdfibm_interact(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids,
+                    const double *U, double dt, double rhof,
+                    double *As, double *Fs, double *Ts, double *Ct, double *force_torque);
+/* Same with DEVICE pointers on the context's device, enqueued on the context stream and
+ * synchronised before return (the per-step status word needs one 4-byte read-back). */
+int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids,
+                           const double *dU, double dt, double rhof,
+                           double *dAs, double *dFs, double *dTs, double *dCt,
+                           double *d_force_torque);
+
+/* ---- SolidCloud::fixInternal (solidcloud.cpp:288-301) -------------------------------
+ * Uses Ct of the last interact on this context and the CURRENT solid states. */
+int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *U);
+int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids,
+                               double *dU, const double *dCt);
+
+/* ---- candidate lists of the last interact (CellEnumerator::intersect result) --------
+ * counts[3] = total ALL_INSIDE, CENTER_INSIDE, CENTER_OUTSIDE pairs. */
+int sdfibm_candidate_counts(sdfibm_context *ctx, int64_t counts[3]);
+/* offsets[3*n_solids+1]: segment (3*s + type-1) of cells[] holds the ascending cell ids of
+ * solid s and type (1,2,3) — std::set order (cellenumerator.h:25, solidcloud.cpp:367-374). */
+int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells, int64_t capacity);
+/* diagnostics of the last interact: [0] solids whose vertex-inside cell set was not one
+ * face-connected component (exact flood-fill replay was run), [1] launches enqueued. */
+int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]);
+
+/* ---- collision step (solidcloud.cpp:477-519, libcollision/) -------------------------
+ * delta = UGrid cell size.  HEAD passes 2*m_radiusB = -2 (solidcloud.cpp:74-75,245) which yields
+ * no pairs; pass a positive delta for the intended behaviour.  pairs[2*cap] receives (p<q)
+ * pairs in UGrid::generateCollisionPairs order; force_torque[6*n_solids] is ACCUMULATED into. */
+int sdfibm_collide(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double delta,
+                   int32_t *pairs, int64_t pair_capacity, int64_t *n_pairs, double *force_torque);
+
+/* ---- device-resident access for the multi-GPU host (allreduce by the caller's NCCL) -- */
+int sdfibm_stream(sdfibm_context *ctx, void **cuda_stream);
+int sdfibm_synchronize(sdfibm_context *ctx);
+
+/* ---- Foam-free mesh helpers (stand-alone harness; OpenFOAM supplies these in the drop-in) */
+/* derived geometry + connectivity from polyMesh primitives (points/faces/owner/neighbour) */
+typedef struct sdfibm_mesh_storage sdfibm_mesh_storage;
+int sdfibm_mesh_from_polymesh(int32_t n_points, const double *points, int32_t n_faces,
+                              const int32_t *face_off, const int32_t *face_pts,
+                              const int32_t *owner, int32_t n_internal, const int32_t *neighbour,
+                              sdfibm_mesh_storage **out);
+/* single blockMesh-numbered hex block: nx*ny*nz cells, origin x0, spacing dx */
+int sdfibm_mesh_hex_block(int32_t nx, int32_t ny, int32_t nz, const double x0[3], const double dx[3],
+                          sdfibm_mesh_storage **out);
+int sdfibm_mesh_view(const sdfibm_mesh_storage *st, sdfibm_mesh_t *view);
+/* polyMesh owner[n_faces] / neighbour[n_internal_faces] of the stored mesh */
+int sdfibm_mesh_owner_neighbour(const sdfibm_mesh_storage *st, const int32_t **owner, const int32_t **neighbour);
+int sdfibm_mesh_free(sdfibm_mesh_storage *st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFIBM_B200_H */

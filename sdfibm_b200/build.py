@@ -1,0 +1,64 @@
+"""In-tree build of the CUDA library (sm_100a) — `python -m sdfibm_b200.build`."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "libsdfibm_b200.so")
+SOURCES = [os.path.join(HERE, "csrc", "sdfibm_cuda.cu"), os.path.join(HERE, "csrc", "mesh_host.cpp")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", "device_math.cuh"), os.path.join(ROOT, "include", "sdfibm_b200.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-fmad=false",               # strict predicates: no FMA contraction
+    "-Xcompiler", "-fPIC,-ffp-contract=off",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB
+
+
+def build_oracle(force: bool = False) -> str:
+    d = os.path.join(ROOT, "oracle")
+    lib = os.path.join(d, "liboracle.so")
+    src = os.path.join(d, "oracle.cpp")
+    hdr = os.path.join(ROOT, "include", "sdfibm_b200.h")
+    if force or not os.path.exists(lib) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(lib):
+        r = subprocess.run(["make", "-C", d, "-B", "liboracle.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_oracle(force="--force" in sys.argv))

@@ -1,0 +1,116 @@
+"""ctypes binding of include/sdfibm_b200.h (the C-ABI drop-in boundary).
+
+The library is loaded from the in-tree build (sdfibm_b200/libsdfibm_b200.so).  There is no CPU
+fallback: if the library is missing, loading raises; if no CUDA device is usable, every compute
+entry returns an error that is raised as SdfibmError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsdfibm_b200.so")
+
+SHAPE_TAGS = {
+    "Plane": 0, "Circle": 1, "Sphere": 2, "Ellipse": 3, "Ellipsoid": 4,
+    "Rectangle": 5, "Box": 6, "Circle_Tail": 7, "Circle_TwoTail": 8,
+}
+
+# numpy dtypes that mirror the POD records (sdfibm_shape_t, sdfibm_solid_t)
+SHAPE_DTYPE = np.dtype(
+    [("tag", "<i4"), ("finite", "<i4"), ("radiusB", "<f8"), ("com", "<f8", 3), ("p", "<f8", 8)], align=True
+)
+SOLID_DTYPE = np.dtype(
+    [("pos", "<f8", 3), ("quat", "<f8", 4), ("vel", "<f8", 3), ("omega", "<f8", 3), ("shape", "<i4"), ("pad_", "<i4")],
+    align=True,
+)
+assert SHAPE_DTYPE.itemsize == 104 and SOLID_DTYPE.itemsize == 112
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class MeshT(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_int32), ("n_points", C.c_int32), ("n_faces", C.c_int32), ("n_internal_faces", C.c_int32),
+        ("points", c_double_p), ("cell_centres", c_double_p), ("cell_volumes", c_double_p),
+        ("face_centres", c_double_p), ("face_areas", c_double_p),
+        ("cell_points_off", c_int32_p), ("cell_points", c_int32_p),
+        ("cell_faces_off", c_int32_p), ("cell_faces", c_int32_p),
+        ("face_points_off", c_int32_p), ("face_points", c_int32_p),
+        ("cell_cells_off", c_int32_p), ("cell_cells", c_int32_p),
+        ("bounds_min", C.c_double * 3), ("bounds_max", C.c_double * 3),
+    ]
+
+
+class SdfibmError(RuntimeError):
+    pass
+
+
+# every symbol include/sdfibm_b200.h declares: name -> (restype, argtypes)
+_VP = C.c_void_p
+SYMBOLS = {
+    "sdfibm_version": (C.c_int, []),
+    "sdfibm_last_error": (C.c_char_p, []),
+    "sdfibm_device_count": (C.c_int, [c_int32_p]),
+    "sdfibm_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "sdfibm_destroy": (C.c_int, [_VP]),
+    "sdfibm_set_cell_slots": (C.c_int, [_VP, C.c_int]),
+    "sdfibm_set_mesh": (C.c_int, [_VP, C.POINTER(MeshT), C.c_int]),
+    "sdfibm_set_shapes": (C.c_int, [_VP, _VP, C.c_int]),
+    "sdfibm_interact": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
+    "sdfibm_interact_device": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
+    "sdfibm_fix_internal": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "sdfibm_fix_internal_device": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
+    "sdfibm_candidate_counts": (C.c_int, [_VP, c_int64_p]),
+    "sdfibm_candidate_lists": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
+    "sdfibm_last_stats": (C.c_int, [_VP, c_int64_p]),
+    "sdfibm_collide": (C.c_int, [_VP, _VP, C.c_int, C.c_double, _VP, C.c_int64, c_int64_p, _VP]),
+    "sdfibm_stream": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "sdfibm_synchronize": (C.c_int, [_VP]),
+    "sdfibm_mesh_from_polymesh": (C.c_int, [C.c_int32, _VP, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP, C.POINTER(_VP)]),
+    "sdfibm_mesh_hex_block": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p, C.POINTER(_VP)]),
+    "sdfibm_mesh_view": (C.c_int, [_VP, C.POINTER(MeshT)]),
+    "sdfibm_mesh_owner_neighbour": (C.c_int, [_VP, C.POINTER(c_int32_p), C.POINTER(c_int32_p)]),
+    "sdfibm_mesh_free": (C.c_int, [_VP]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsdfibm_b200.so (building is the caller's job: `python -m sdfibm_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SdfibmError(
+            f"{LIB_PATH} is missing: build it with `python -m sdfibm_b200.build` (there is no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().sdfibm_last_error()
+        raise SdfibmError(f"sdfibm error {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(a):
+    """void* of a numpy array (must be C-contiguous) or a raw integer device pointer."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)

@@ -1,0 +1,123 @@
+"""Thin Python host over the C ABI (one Context per rank/GPU).
+
+Mirrors the per-step surface of sdfibm::SolidCloud that main.cpp uses (reference src/solidcloud.h:98-116):
+``interact`` / ``fix_internal`` plus the collision step, on numpy host arrays or raw device pointers.
+All compute happens in libsdfibm_b200.so; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class Context:
+    def __init__(self, device: int = 0, cell_slots: int | None = None):
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        capi.check(self._lib.sdfibm_create(int(device), C.byref(self._h)))
+        if cell_slots is not None:
+            capi.check(self._lib.sdfibm_set_cell_slots(self._h, int(cell_slots)))
+        self.mesh = None
+        self.n_cells = 0
+        self.n_solids = 0
+
+    def close(self):
+        if self._h:
+            self._lib.sdfibm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- one-time uploads ----
+    def set_mesh(self, mesh, two_d: bool):
+        capi.check(self._lib.sdfibm_set_mesh(self._h, C.byref(mesh.view), int(bool(two_d))))
+        self.mesh = mesh
+        self.n_cells = mesh.n_cells
+
+    def set_shapes(self, shapes: np.ndarray):
+        shapes = np.ascontiguousarray(shapes, dtype=capi.SHAPE_DTYPE)
+        capi.check(self._lib.sdfibm_set_shapes(self._h, capi.ptr(shapes), len(shapes)))
+
+    # ---- SolidCloud::interact ----
+    def interact(self, solids: np.ndarray, U: np.ndarray, dt: float, rhof: float, out=None):
+        """Host-buffer interact.  Returns dict(As, Fs, Ts, Ct, FT)."""
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        nC, n = self.n_cells, len(solids)
+        assert U.size == 3 * nC
+        if out is None:
+            out = dict(As=np.empty(nC), Fs=np.empty((nC, 3)), Ts=np.empty(nC), Ct=np.empty(nC), FT=np.empty((n, 6)))
+        capi.check(self._lib.sdfibm_interact(self._h, capi.ptr(solids), n, capi.ptr(U), float(dt), float(rhof),
+                                             capi.ptr(out["As"]), capi.ptr(out["Fs"]), capi.ptr(out["Ts"]),
+                                             capi.ptr(out["Ct"]), capi.ptr(out["FT"])))
+        self.n_solids = n
+        return out
+
+    def interact_device(self, solids: np.ndarray, dU: int, dt: float, rhof: float, dAs: int, dFs: int, dTs: int,
+                        dCt: int, dFT: int):
+        """Device-pointer interact (pointers as ints, e.g. torch.Tensor.data_ptr())."""
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        capi.check(self._lib.sdfibm_interact_device(self._h, capi.ptr(solids), len(solids), capi.ptr(dU), float(dt),
+                                                    float(rhof), capi.ptr(dAs), capi.ptr(dFs), capi.ptr(dTs),
+                                                    capi.ptr(dCt), capi.ptr(dFT)))
+        self.n_solids = len(solids)
+
+    # ---- SolidCloud::fixInternal ----
+    def fix_internal(self, solids: np.ndarray, U: np.ndarray) -> np.ndarray:
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        U = np.array(U, dtype=np.float64, copy=True, order="C")
+        capi.check(self._lib.sdfibm_fix_internal(self._h, capi.ptr(solids), len(solids), capi.ptr(U)))
+        return U
+
+    def fix_internal_device(self, solids: np.ndarray, dU: int, dCt: int | None = None):
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        capi.check(self._lib.sdfibm_fix_internal_device(self._h, capi.ptr(solids), len(solids), capi.ptr(dU),
+                                                        capi.ptr(dCt) if dCt else None))
+
+    # ---- candidate lists / diagnostics of the last interact ----
+    def candidate_counts(self):
+        c = (C.c_int64 * 3)()
+        capi.check(self._lib.sdfibm_candidate_counts(self._h, c))
+        return [int(x) for x in c]
+
+    def candidate_lists(self):
+        n = self.n_solids
+        off = np.zeros(3 * n + 1, dtype=np.int32)
+        capi.check(self._lib.sdfibm_candidate_lists(self._h, capi.ptr(off), None, 0))
+        cells = np.empty(max(int(off[-1]), 1), dtype=np.int32)
+        capi.check(self._lib.sdfibm_candidate_lists(self._h, capi.ptr(off), capi.ptr(cells), len(cells)))
+        return off, cells[: off[-1]]
+
+    def last_stats(self):
+        s = (C.c_int64 * 4)()
+        capi.check(self._lib.sdfibm_last_stats(self._h, s))
+        return dict(flagged_solids=int(s[0]), launches=int(s[1]), bin_entries=int(s[2]), global_solids=int(s[3]))
+
+    # ---- collision step ----
+    def collide(self, solids: np.ndarray, delta: float, force_torque: np.ndarray | None = None):
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        n = len(solids)
+        ft = np.zeros((n, 6)) if force_torque is None else np.array(force_torque, dtype=np.float64, order="C")
+        npairs = C.c_int64(0)
+        cap = 1 << 16
+        while True:
+            pairs = np.empty((cap, 2), dtype=np.int32)
+            ft_try = ft.copy()
+            rc = self._lib.sdfibm_collide(self._h, capi.ptr(solids), n, float(delta), capi.ptr(pairs), cap,
+                                          C.byref(npairs), capi.ptr(ft_try))
+            if rc == 4 and npairs.value > cap:
+                cap = int(npairs.value) + 16
+                continue
+            capi.check(rc)
+            break
+        return pairs[: npairs.value].copy(), ft_try
+
+    def synchronize(self):
+        capi.check(self._lib.sdfibm_synchronize(self._h))
