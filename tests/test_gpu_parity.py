@@ -1,0 +1,151 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): candidate lists and collision pair sets bit-exact; As / Fs (and Ts, Ct)
+within 1e-12 relative; per-solid force / torque within 1e-10 relative to the sum of |terms|.
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle_py import Oracle
+from sdfibm_b200 import cases
+from sdfibm_b200.context import Context
+
+pytestmark = pytest.mark.gpu
+
+REL_FIELD = 1e-12
+REL_FORCE = 1e-10
+
+
+def _term_scale(case, off, cells):
+    """Per-solid upper bound of sum |terms| of the force/torque sums (alpha <= 1)."""
+    m, S = case["mesh"], case["solids"]
+    n = len(S)
+    scale = np.zeros((n, 6))
+    for s in range(n):
+        cs = cells[off[3 * s]:off[3 * s + 3]]
+        if len(cs) == 0:
+            continue
+        r = m.cc[cs] - S[s]["pos"]
+        us = S[s]["vel"] + np.cross(S[s]["omega"], r)
+        f = np.abs(case["U"][cs] - us) * m.V[cs, None] / case["dt"] * case["rhof"]
+        scale[s, :3] = f.sum(axis=0)
+        scale[s, 3:] = (np.linalg.norm(r, axis=1)[:, None] * np.linalg.norm(f, axis=1)[:, None]).sum()
+    return scale
+
+
+def run_both(case, cell_slots=None):
+    o = Oracle(case["mesh"], case["two_d"])
+    ref = o.interact(case["shapes"], case["solids"], case["U"], case["dt"], case["rhof"])
+    ctx = Context(0, cell_slots=cell_slots)
+    ctx.set_mesh(case["mesh"], case["two_d"])
+    ctx.set_shapes(case["shapes"])
+    got = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
+    return o, ref, ctx, got
+
+
+def check_parity(case, o, ref, ctx, got):
+    off, cells = ctx.candidate_lists()
+    assert np.array_equal(off, ref["list_off"]), "candidate list sizes differ"
+    assert np.array_equal(cells, ref["list_cells"]), "candidate lists differ"
+    counts = ctx.candidate_counts()
+    n = len(case["solids"])
+    assert counts == [int((off[1::3][:n] - off[0::3][:n]).sum()), int((off[2::3][:n] - off[1::3][:n]).sum()),
+                      int((off[3::3][:n] - off[2::3][:n]).sum())]
+    assert np.array_equal(got["Ct"], ref["Ct"])
+    for k in ("As", "Ts", "Fs"):
+        a, b = got[k], ref[k]
+        tol = REL_FIELD * np.maximum(np.abs(b), np.abs(b).max() * 1e-3 + 1e-300)
+        assert (np.abs(a - b) <= tol).all(), (k, np.abs(a - b).max())
+    scale = _term_scale(case, ref["list_off"], ref["list_cells"])
+    err = np.abs(got["FT"] - ref["FT"])
+    assert (err <= REL_FORCE * np.maximum(scale, np.abs(ref["FT"])) + 1e-300).all(), err.max()
+    # fixInternal with moved solids (solid state AFTER evolve, Ct of the last interact)
+    S2 = case["solids"].copy()
+    S2["vel"] += 0.05
+    S2["omega"] *= 1.1
+    S2["pos"] += 0.01
+    U2 = case["U"] * 0.9
+    assert np.array_equal(ctx.fix_internal(S2, U2), o.fix_internal(case["shapes"], S2, ref["Ct"], U2))
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c2_walls", "skewed2d", "mixed3d", "prism2d", "c4_small"])
+def test_parity_synthetic(name):
+    case = {
+        "c1": cases.case_c1,
+        "c2": cases.case_c2,
+        "c2_walls": lambda: cases.case_c2(with_walls=True),
+        "skewed2d": cases.case_skewed_2d,
+        "mixed3d": cases.case_mixed3d,
+        "prism2d": cases.case_prism2d,
+        "c4_small": lambda: cases.case_c4(n=48, n_solids=50, n_side=4),
+    }[name]()
+    o, ref, ctx, got = run_both(case, cell_slots=8 if name == "mixed3d" else None)
+    check_parity(case, o, ref, ctx, got)
+    assert sum(ctx.candidate_counts()) > 0
+
+
+def test_parity_g1_and_golden(m1_points, g1_alpha):
+    case = cases.case_g1(m1_points)
+    o, ref, ctx, got = run_both(case)
+    check_parity(case, o, ref, ctx, got)
+    assert np.abs(got["As"] - g1_alpha).max() <= 1e-15      # the GPU itself against the reference's golden
+
+
+def test_parity_c3_shipped_mesh(m2_points):
+    case = cases.case_c3(m2_points)
+    check_parity(case, *run_both(case))
+
+
+def test_parity_disconnected_component_replay():
+    """a vertex-inside set that is not face connected must be cut to the seed's component."""
+    case = cases.case_disconnected()
+    o, ref, ctx, got = run_both(case)
+    assert ctx.last_stats()["flagged_solids"] >= 1
+    check_parity(case, o, ref, ctx, got)
+
+
+def test_empty_and_outside_solids():
+    """Solids that touch no cell of this (sub)mesh yield empty lists and zero force (cellenumerator.cpp:52-65)."""
+    case = cases.case_c4(n=32, n_solids=6, n_side=2)
+    case["solids"]["pos"][0] = (-40.0, 5.0, 5.0)
+    case["solids"]["pos"][1] = (16.0, 16.0, 90.0)
+    o, ref, ctx, got = run_both(case)
+    check_parity(case, o, ref, ctx, got)
+    assert not got["FT"][:2].any()
+
+
+def test_slot_overflow_is_reported():
+    from sdfibm_b200.capi import SdfibmError
+    case = cases.case_c4(n=16, n_solids=3, n_side=1)
+    case["solids"]["pos"][:] = (8.0, 8.0, 8.0)
+    ctx = Context(0, cell_slots=2)
+    ctx.set_mesh(case["mesh"], False)
+    ctx.set_shapes(case["shapes"])
+    with pytest.raises(SdfibmError, match="slot"):
+        ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
+
+
+def test_collision_parity():
+    case = cases.case_c2(with_walls=True)
+    rng = np.random.RandomState(11)
+    S = case["solids"].copy()
+    S["pos"][:100, :2] += rng.uniform(-0.12, 0.12, size=(100, 2))   # create overlaps, keep planes in place
+    o = Oracle(case["mesh"], True)
+    ctx = Context(0)
+    ctx.set_mesh(case["mesh"], True)
+    ctx.set_shapes(case["shapes"])
+    for delta in (-2.0, 0.3, 0.45):
+        pr, fr = o.collide(case["shapes"], S, delta)
+        pg, fg = ctx.collide(S, delta)
+        assert np.array_equal(pr, pg), delta
+        assert np.abs(fr - fg).max() <= REL_FORCE * max(1.0, np.abs(fr).max())
+    assert len(pr) > 0 and np.abs(fr).max() > 0
+    # 3-D spheres + a plane
+    c3 = cases.case_mixed3d()
+    pr, fr = o.__class__(c3["mesh"], False).collide(c3["shapes"], c3["solids"], 7.0)
+    ctx3 = Context(0)
+    ctx3.set_mesh(c3["mesh"], False)
+    ctx3.set_shapes(c3["shapes"])
+    pg, fg = ctx3.collide(c3["solids"], 7.0)
+    assert np.array_equal(pr, pg) and len(pr) > 0
+    assert np.abs(fr - fg).max() <= REL_FORCE * max(1.0, np.abs(fr).max())
