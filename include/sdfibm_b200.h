@@ -156,6 +156,9 @@ int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells
 /* diagnostics of the last interact: [0] solids whose vertex-inside cell set was not one
  * face-connected component (exact flood-fill replay was run), [1] launches enqueued. */
 int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]);
+/* device time (CUDA events on the context stream) of the last interact, in ms:
+ * [0] solid preparation + binning, [1] the fused interact kernel, [2] connectivity + finalise, [3] whole pipeline */
+int sdfibm_last_timings(sdfibm_context *ctx, double ms[4]);
 
 /* ---- collision step (solidcloud.cpp:477-519, libcollision/) -------------------------
  * delta = UGrid cell size.  HEAD passes 2*m_radiusB = -2 (solidcloud.cpp:74-75,245) which yields

@@ -69,6 +69,7 @@ SYMBOLS = {
     "sdfibm_candidate_counts": (C.c_int, [_VP, c_int64_p]),
     "sdfibm_candidate_lists": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "sdfibm_last_stats": (C.c_int, [_VP, c_int64_p]),
+    "sdfibm_last_timings": (C.c_int, [_VP, c_double_p]),
     "sdfibm_collide": (C.c_int, [_VP, _VP, C.c_int, C.c_double, _VP, C.c_int64, c_int64_p, _VP]),
     "sdfibm_stream": (C.c_int, [_VP, C.POINTER(_VP)]),
     "sdfibm_synchronize": (C.c_int, [_VP]),

@@ -100,6 +100,16 @@ class Context:
         capi.check(self._lib.sdfibm_last_stats(self._h, s))
         return dict(flagged_solids=int(s[0]), launches=int(s[1]), bin_entries=int(s[2]), global_solids=int(s[3]))
 
+    def last_timings(self):
+        t = (C.c_double * 4)()
+        capi.check(self._lib.sdfibm_last_timings(self._h, t))
+        return dict(binning_ms=t[0], interact_kernel_ms=t[1], connectivity_ms=t[2], pipeline_ms=t[3])
+
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        capi.check(self._lib.sdfibm_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
     # ---- collision step ----
     def collide(self, solids: np.ndarray, delta: float, force_torque: np.ndarray | None = None):
         solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)

@@ -943,6 +943,8 @@ struct sdfibm_context {
     bool last_used_replay = false;
     // stats
     StepStatus last{};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double t_ms[4] = {0, 0, 0, 0}; // binning, k_interact, connectivity+finalize, whole pipeline (device time, last call)
     int64_t launches = 0;
     int64_t flagged_last = 0;
 };
@@ -1009,6 +1011,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(StepStatus)));
     CUDA_TRY(ctx->status.ensure(1));
+    for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     *out = ctx;
     return SDFIBM_OK;
 }
@@ -1027,6 +1030,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
+    for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_solids) cudaFreeHost(ctx->h_solids);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1256,6 +1260,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         const BinGrid &g = ctx->grid;
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
         CUDA_TRY(cudaMemsetAsync(ctx->status.p, 0, sizeof(StepStatus), st));
         CUDA_TRY(cudaMemsetAsync(ctx->root_count.p, 0, sizeof(int) * n_solids, st));
         CUDA_TRY(cudaMemsetAsync(ctx->pair_counts.p, 0, sizeof(unsigned) * 3 * n_solids, st));
@@ -1296,7 +1301,9 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         I.dtINV = 1.0 / dt; I.rhof = rhof; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
         I.pair_counts = ctx->pair_counts.p; I.slots = ctx->slots.p; I.K = ctx->K;
         I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status.p;
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
         k_interact<<<grid_for(nC, 128), 128, 0, st>>>(I);
+        CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
         ++ctx->launches;
         if (replay) { k_fix_ct<<<grid_for(nC, 256), 256, 0, st>>>(dCt, nC); ++ctx->launches; }
         else {
@@ -1308,9 +1315,22 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts.p, ctx->root_count.p, n_solids, ctx->status.p);
         k_scale_ft<<<grid_for(6LL * n_solids, 256), 256, 0, st>>>(dFT, 6 * n_solids, rhof);
         ctx->launches += 2;
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status.p, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+            cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+            cudaEventElapsedTime(&d, ctx->ev[0], ctx->ev[3]);
+            const double add = replay ? 1.0 : 0.0; // a replay pass adds to the first pass of the same call
+            ctx->t_ms[0] = add * ctx->t_ms[0] + a;
+            ctx->t_ms[1] = add * ctx->t_ms[1] + b;
+            ctx->t_ms[2] = add * ctx->t_ms[2] + c;
+            ctx->t_ms[3] = add * ctx->t_ms[3] + d;
+        }
         ctx->last = *ctx->h_status;
         if (replay) ctx->last.n_flagged = (int)ctx->flagged_last;
         if (ctx->last.bin_overflow && !replay && attempt == 0) {
@@ -1399,6 +1419,12 @@ int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]) {
     stats[1] = ctx->launches;
     stats[2] = ctx->last.bin_total;
     stats[3] = ctx->last.n_global;
+    return SDFIBM_OK;
+}
+
+int sdfibm_last_timings(sdfibm_context *ctx, double ms[4]) {
+    if (!ctx || !ms) return fail(SDFIBM_ERR_ARG, "null argument");
+    for (int k = 0; k < 4; ++k) ms[k] = ctx->t_ms[k];
     return SDFIBM_OK;
 }
 
