@@ -232,6 +232,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    split = []
+
     def timed(fn, steps, warmup):
         with torch.cuda.stream(ext):
             for _ in range(warmup):
@@ -239,11 +241,13 @@ def main():
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             kern_ms, pipe_ms = [], []
+            split.clear()
             e0.record(ext)
             for _ in range(steps):
                 fn()
                 t = ctx.last_timings()
-                kern_ms.append(t["interact_kernel_ms"])
+                kern_ms.append(t["interact_kernels_ms"])
+                split.append((t["classify_ms"], t["heavy_ms"], t["accumulate_ms"], t["connectivity_ms"], t["binning_ms"]))
                 pipe_ms.append(t["pipeline_ms"])
             e1.record(ext)
             barrier()
@@ -259,6 +263,7 @@ def main():
         sampler.start()
     ms, kern_ms, pipe_ms = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    split_mean = [float(x) for x in np.mean(np.array(split), axis=0)]
     counts = ctx.candidate_counts()
     stats = ctx.last_stats()
     launches_per_step = stats["launches"]
@@ -312,8 +317,11 @@ def main():
                            l2="inputs larger than L2 (fields + mesh arrays of one step >> 126 MB); no explicit flush"),
             "clocks": clocks,
             "gpu_launches": int(launches_per_step * args.steps),
-            "kernel_ms": {"k_interact": kern_ms, "pipeline_device": pipe_ms, "step_wall_on_stream": ms_per_step},
-            "roofline": {"bound": "hbm", "kernel": "k_interact", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "kernel_ms": {"k_classify": split_mean[0], "k_heavy": split_mean[1], "k_accumulate": split_mean[2],
+                          "k_connectivity+finalise": split_mean[3], "solid_binning": split_mean[4],
+                          "interact_kernels": kern_ms, "pipeline_device": pipe_ms, "step_wall_on_stream": ms_per_step,
+                          "heavy_items": stats["heavy_items"]},
+            "roofline": {"bound": "hbm", "kernel": "k_classify+k_heavy+k_accumulate (the interact kernels; k_heavy dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg),
                          "formula": "48*nCells + 112*P + 216*P_b + 176*N (SURVEY.md 8d), rank 0"},

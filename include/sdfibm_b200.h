@@ -154,11 +154,13 @@ int sdfibm_candidate_counts(sdfibm_context *ctx, int64_t counts[3]);
  * solid s and type (1,2,3) — std::set order (cellenumerator.h:25, solidcloud.cpp:367-374). */
 int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells, int64_t capacity);
 /* diagnostics of the last interact: [0] solids whose vertex-inside cell set was not one
- * face-connected component (exact flood-fill replay was run), [1] launches enqueued. */
+ * face-connected component (exact flood-fill replay was run), [1] launches enqueued, [2] solid-bin
+ * entries, [3] (cell, solid) items that needed exact vertex evaluation. */
 int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]);
 /* device time (CUDA events on the context stream) of the last interact, in ms:
- * [0] solid preparation + binning, [1] the fused interact kernel, [2] connectivity + finalise, [3] whole pipeline */
-int sdfibm_last_timings(sdfibm_context *ctx, double ms[4]);
+ * [0] solid preparation + binning, [1] k_classify, [2] k_heavy, [3] k_accumulate, [4] connectivity + finalise,
+ * [5] whole pipeline */
+int sdfibm_last_timings(sdfibm_context *ctx, double ms[6]);
 
 /* ---- collision step (solidcloud.cpp:477-519, libcollision/) -------------------------
  * delta = UGrid cell size.  HEAD passes 2*m_radiusB = -2 (solidcloud.cpp:74-75,245) which yields

@@ -98,12 +98,13 @@ class Context:
     def last_stats(self):
         s = (C.c_int64 * 4)()
         capi.check(self._lib.sdfibm_last_stats(self._h, s))
-        return dict(flagged_solids=int(s[0]), launches=int(s[1]), bin_entries=int(s[2]), global_solids=int(s[3]))
+        return dict(flagged_solids=int(s[0]), launches=int(s[1]), bin_entries=int(s[2]), heavy_items=int(s[3]))
 
     def last_timings(self):
-        t = (C.c_double * 4)()
+        t = (C.c_double * 6)()
         capi.check(self._lib.sdfibm_last_timings(self._h, t))
-        return dict(binning_ms=t[0], interact_kernel_ms=t[1], connectivity_ms=t[2], pipeline_ms=t[3])
+        return dict(binning_ms=t[0], classify_ms=t[1], heavy_ms=t[2], accumulate_ms=t[3], connectivity_ms=t[4],
+                    pipeline_ms=t[5], interact_kernels_ms=t[1] + t[2] + t[3])
 
     def stream_ptr(self) -> int:
         p = C.c_void_p()

@@ -77,6 +77,11 @@ struct DevMesh {
     const double *points, *cc, *V, *Cf, *Sf;
     const int *cp_off, *cp, *cf_off, *cf, *fp_off, *fp, *nb_off, *nb;
     const float2 *cell_rad; // (3-D radius, xy radius) of the vertex cloud about the centre, rounded up
+    const double *magSf;    // |Sf| per face (same expression as Foam::mag, evaluated once at upload)
+    const unsigned *hex_topo; // hex meshes: 3 words per cell, 4-bit cell-local vertex slot of every face vertex
+    float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
+    int rad_uniform;
+    int is_hex;             // every cell has 8 points / 6 faces and every face 4 points
     int two_d;
 };
 
@@ -95,6 +100,7 @@ struct StepStatus {
     int bad_cell;                 // a cell/face exceeded MAX_CELL_VERTS / MAX_FACE_VERTS
     int bin_total;
     int n_global;
+    unsigned long long heavy_total; // (cell, solid) items that needed exact evaluation
 };
 
 __device__ __forceinline__ D3 ld3(const double *__restrict__ p, long long i) {
@@ -110,6 +116,35 @@ __device__ __forceinline__ int bin_coord(const BinGrid &g, double x, int d) {
 // ------------------------------------------------------------------------------------------------
 // K0  per-cell vertex-cloud radii (once per mesh)
 // ------------------------------------------------------------------------------------------------
+__global__ void k_face_mag(const double *Sf, int n_faces, double *magSf) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n_faces) magSf[f] = mag3(ld3(Sf, f));
+}
+
+// hex meshes: for face k (cells() order) of cell c and its j-th vertex (faces() order), the position of that
+// vertex in the cell's cellPoints() list, packed 4 bits each: word k/2, bit 16*(k&1) + 4*j.
+__global__ void k_hex_topo(DevMesh m, unsigned *topo, int *bad) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    int vid[8];
+    for (int k = 0; k < 8; ++k) vid[k] = m.cp[8 * (long long)c + k];
+    unsigned w[3] = {0u, 0u, 0u};
+    for (int k = 0; k < 6; ++k) {
+        const int f = m.cf[6 * (long long)c + k];
+        for (int j = 0; j < 4; ++j) {
+            const int g = m.fp[4 * (long long)f + j];
+            int l = -1;
+            for (int t = 0; t < 8; ++t) if (vid[t] == g) l = t;
+            if (l < 0) { atomicExch(bad, 1); l = 0; }
+            w[k >> 1] |= (unsigned)l << (16 * (k & 1) + 4 * j);
+        }
+    }
+    topo[3 * (long long)c] = w[0];
+    topo[3 * (long long)c + 1] = w[1];
+    topo[3 * (long long)c + 2] = w[2];
+}
+
+// rmax[0..1] = max of the (3-D, xy) radii, rmax[2..3] = min
 __global__ void k_cell_radius(DevMesh m, float2 *rad, int *bad, float *rmax) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     float r3f = 0.f, rxyf = 0.f;
@@ -133,21 +168,27 @@ __global__ void k_cell_radius(DevMesh m, float2 *rad, int *bad, float *rmax) {
         rxyf = nextafterf(rxyf, INFINITY);
         rad[c] = make_float2(r3f, rxyf);
     }
-    // block max -> global max (floats are non-negative: int compare is order preserving)
-    __shared__ float s3[256], sxy[256];
+    // block max/min -> global (floats are non-negative: int compare is order preserving)
+    __shared__ float s3[256], sxy[256], m3[256], mxy[256];
     s3[threadIdx.x] = r3f;
     sxy[threadIdx.x] = rxyf;
+    m3[threadIdx.x] = (c < m.n_cells) ? r3f : 3.0e38f;
+    mxy[threadIdx.x] = (c < m.n_cells) ? rxyf : 3.0e38f;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             s3[threadIdx.x] = fmaxf(s3[threadIdx.x], s3[threadIdx.x + o]);
             sxy[threadIdx.x] = fmaxf(sxy[threadIdx.x], sxy[threadIdx.x + o]);
+            m3[threadIdx.x] = fminf(m3[threadIdx.x], m3[threadIdx.x + o]);
+            mxy[threadIdx.x] = fminf(mxy[threadIdx.x], mxy[threadIdx.x + o]);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         atomicMax((int *)&rmax[0], __float_as_int(s3[0]));
         atomicMax((int *)&rmax[1], __float_as_int(sxy[0]));
+        atomicMin((int *)&rmax[2], __float_as_int(m3[0]));
+        atomicMin((int *)&rmax[3], __float_as_int(mxy[0]));
     }
 }
 
@@ -335,9 +376,11 @@ __device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad)
     const D3 r = cc - D3{S.pos[0], S.pos[1], S.pos[2]};
     const double d2 = dot3(r, r);
     if (S.kind == KIND_3D) {
-        const double d = sqrt(d2);
-        if (d - rad.x > S.r_out) return 0;
-        if (d + rad.x < S.r_in) return 1;
+        // d - rad > r_out  <=>  d^2 > (r_out + rad)^2 ;  d + rad < r_in  <=>  d^2 < (r_in - rad)^2 with r_in > rad
+        // (the 1e-6 relative margins inside r_out / r_in / rad dwarf the rounding of the squares)
+        const double ro = S.r_out + (double)rad.x, ri = S.r_in - (double)rad.x;
+        if (d2 > ro * ro) return 0;
+        if (ri > 0.0 && d2 < ri * ri) return 1;
         return 2;
     }
     if (S.kind == KIND_2D) {
@@ -359,7 +402,7 @@ __device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2  the fused interact kernel: classification + As + forcing + Ts + Ct + per-solid force/torque
+// K2  interact: parameters shared by the classify / heavy / accumulate kernels
 // ------------------------------------------------------------------------------------------------
 struct InteractParams {
     DevMesh m;
@@ -376,10 +419,18 @@ struct InteractParams {
     double *force_torque; // [6*n_solids], zeroed
     unsigned *pair_counts; // [3*n_solids], zeroed
     int *slots;            // [n_cells*K]: (solid<<2 | type) of every member pair of the cell, -1 terminated
+    double *vols;          // [n_cells*K]: solid volume of the pair's cell (boundary types)
+    unsigned char *n_item; // [n_cells]: slots in use after k_classify
+    int2 *heavy;           // queue of (cell, slot) needing exact evaluation
+    unsigned long long *heavy_count;
+    long long heavy_cap;
+    int n_global;
     int K;
     const unsigned char *excluded; // replay mode: [n_cells*K] 1 = pair is outside the seed's component
     StepStatus *status;
 };
+
+#define TPB 128
 
 // warp-level aggregation of one member pair per lane: lanes with the same solid are reduced with a
 // butterfly and the group leader issues the 6 fp64 + 1 counter reductions.
@@ -415,122 +466,285 @@ __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, cons
     }
 }
 
-__global__ void __launch_bounds__(128) k_interact(InteractParams P) {
+// Exact evaluation of one (cell, solid) item: number of vertices inside, cell type, solid volume.
+// General polyhedra: cell-local arrays in local memory, CSR connectivity.
+__device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out) {
     const DevMesh &m = P.m;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = c < m.n_cells;
-
-    D3 cc = {0, 0, 0};
-    float2 rad = make_float2(0.f, 0.f);
-    int bi = 0, be = 0, gi = 0, ge = 0;
-    if (live) {
-        cc = ld3(m.cc, c);
-        rad = __ldg(m.cell_rad + c);
-        const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] +
-                      bin_coord(P.grid, cc.x, 0);
-        bi = __ldg(P.bin_off + b);
-        be = __ldg(P.bin_off + b + 1);
-        ge = P.status->n_global;
-    }
-    double as = 0.0, ts = 0.0, ct = 0.0;
-    D3 fs = {0.0, 0.0, 0.0};
-    int nslot = 0;
-    bool have_cell_data = false;
-    int nv = 0;
+    const DevSolid &S = P.solids[s];
+    const DevShape &sh = P.shapes[S.shape];
+    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
     int vid[MAX_CELL_VERTS];
     D3 pts[MAX_CELL_VERTS];
     double phi[MAX_CELL_VERTS];
-    D3 uf = {0, 0, 0};
-    double vol = 0.0;
-    bool have_uv = false;
+    const int pb = __ldg(m.cp_off + c);
+    int nv = __ldg(m.cp_off + c + 1) - pb;
+    if (nv > MAX_CELL_VERTS) { nv = MAX_CELL_VERTS; P.status->bad_cell = 1; }
+    int n_in = 0;
+    for (int k = 0; k < nv; ++k) {
+        vid[k] = __ldg(m.cp + pb + k);
+        pts[k] = ld3(m.points, vid[k]);
+        double ph;
+        n_in += shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph) ? 1 : 0;
+        phi[k] = ph;
+    }
+    type_out = 0;
+    vol_out = 0.0;
+    if (n_in == 0) return;
+    if (n_in == nv) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
+    double dummy;
+    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+    vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
+}
 
-    for (;;) {
-        // ---- divergent part: advance to this cell's next member pair -------------------------
-        bool have = false;
-        int s = -1, type = 0;
-        double contrib[6] = {0, 0, 0, 0, 0, 0};
+// Hexahedral fast path: fixed 8/6/4 strides, per-cell face->vertex-slot nibbles precomputed at upload,
+// vertex coordinates and phi staged in transposed shared memory (column = executing thread) so that the
+// data-dependent slot indexing is bank-conflict free.
+__device__ __forceinline__ void heavy_eval_hex(const InteractParams &P, int c, int s, int col, double *s_px, double *s_py,
+                                               double *s_pz, double *s_phi, int &type_out, double &vol_out) {
+    const DevMesh &m = P.m;
+    const DevSolid &S = P.solids[s];
+    const DevShape &sh = P.shapes[S.shape];
+    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+    const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
+    const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
+    const int vid[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    int n_in = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const D3 p = ld3(m.points, vid[k]);
+        double ph;
+        n_in += shape_eval<true>(sh.s, world2local(q, t, p), ph) ? 1 : 0;
+        s_px[k * TPB + col] = p.x;
+        s_py[k * TPB + col] = p.y;
+        s_pz[k * TPB + col] = p.z;
+        s_phi[k * TPB + col] = ph;
+    }
+    type_out = 0;
+    vol_out = 0.0;
+    if (n_in == 0) return;
+    if (n_in == 8) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
+    double dummy;
+    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+
+    auto PT = [&](int l) { return D3{s_px[l * TPB + col], s_py[l * TPB + col], s_pz[l * TPB + col]}; };
+    auto PH = [&](int l) { return s_phi[l * TPB + col]; };
+    // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
+    D3 apex;
+    {
+        const D3 A = PT(0);
+        const double phiA = PH(0);
+        D3 B = {0.0, 0.0, 0.0};
+        double phiB = 0.0;
+        for (int i = 1; i < 8; ++i) {
+            B = PT(i);
+            phiB = PH(i);
+            if (phiA * phiB <= 0) break;
+        }
+        apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
+        if (m.two_d) apex.z = 0.0;
+    }
+    const unsigned tw0 = __ldg(m.hex_topo + 3 * (long long)c), tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1),
+                   tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
+    const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
+    const int2 f01 = __ldg(cf2), f23 = __ldg(cf2 + 1), f45 = __ldg(cf2 + 2);
+    double volume = 0.0;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
+        const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
+        const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
+        const int l[4] = {(int)(nib & 0xf), (int)((nib >> 4) & 0xf), (int)((nib >> 8) & 0xf), (int)((nib >> 12) & 0xf)};
+        const double ph[4] = {PH(l[0]), PH(l[1]), PH(l[2]), PH(l[3])};
+        const int npos = (ph[0] > 0) + (ph[1] > 0) + (ph[2] > 0) + (ph[3] > 0);
+        if (npos == 4) continue;                                                // eps_f = 0: adds +0.0 (:107-108)
+        double eps_f = 1.0;                                                     // all phi <= 0 (:109-110)
+        if (npos != 0) {
+            const D3 A = PT(l[0]);                                              // calcFaceArea (:74-96)
+            D3 B = PT(l[1]);
+            double phiB = ph[1];
+            if (!(ph[0] * ph[1] <= 0)) {
+                B = PT(l[2]);
+                phiB = ph[2];
+                if (!(ph[0] * ph[2] <= 0)) { B = PT(l[3]); phiB = ph[3]; }
+            }
+            const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - B);
+            double area = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
+                if (lf != 0.0) {                                                // a zero fraction adds +0.0
+                    const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
+                    area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;
+                }
+            }
+            eps_f = area / __ldg(m.magSf + face);
+        }
+        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - ld3(m.Cf, face), ld3(m.Sf, face)));
+    }
+    vol_out = volume;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a  k_classify (thread per cell): walk the cell's candidate solids in ascending id; every candidate that
+//      may be a member becomes a slot of the cell (certain ALL_INSIDE -> final; otherwise "heavy": appended
+//      to a global queue for exact evaluation).
+// K2b  k_heavy (thread per heavy item, persistent grid): exact vertex predicates + SDF, cell type,
+//      apex/pyramid volume.  Dense: no barriers, no idle lanes waiting on light cells.
+// K2c  k_accumulate (thread per cell): consume the cell's slots in ascending solid order — As/Fs/Ts/Ct
+//      accumulation exactly in the reference's += order, every field written once and coalesced, per-solid
+//      force/torque warp-aggregated before the atomics.
+// ------------------------------------------------------------------------------------------------
+template <bool HEX>
+__global__ void __launch_bounds__(TPB) k_heavy(InteractParams P) {
+    __shared__ double s_px[HEX ? 8 * TPB : 1], s_py[HEX ? 8 * TPB : 1], s_pz[HEX ? 8 * TPB : 1], s_phi[HEX ? 8 * TPB : 1];
+    const int tid = threadIdx.x;
+    const long long n = min((long long)*P.heavy_count, (long long)P.heavy_cap);
+    for (long long k = (long long)blockIdx.x * TPB + tid; k < n; k += (long long)gridDim.x * TPB) {
+        const int2 it = __ldg(P.heavy + k);           // (cell, slot index)
+        const int c = it.x;
+        const long long si = (long long)c * P.K + it.y;
+        const int s = P.slots[si] >> 2;
+        int type;
+        double v;
+        if (HEX) heavy_eval_hex(P, c, s, tid, s_px, s_py, s_pz, s_phi, type, v);
+        else heavy_eval_general(P, c, s, type, v);
+        P.slots[si] = (s << 2) | type;                // type 0: no vertex inside -> not a member
+        P.vols[si] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_classify(InteractParams P) {
+    const DevMesh &m = P.m;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < m.n_cells;
+    int n_item = 0, n_heavy = 0;
+    unsigned heavy_mask = 0;
+    if (live) {
+        const D3 cc = ld3(m.cc, c);
+        const float2 rad = m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c);
+        const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] +
+                      bin_coord(P.grid, cc.x, 0);
+        int bi = __ldg(P.bin_off + b);
+        const int be = __ldg(P.bin_off + b + 1);
+        int gi = 0;
+        const int ge = P.status->n_global;
         while (bi < be || gi < ge) {
             // merge the bin list and the global list in ascending solid id
-            int sb = (bi < be) ? __ldg(P.bin_list + bi) : 0x7fffffff;
-            int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
+            int s;
+            const int sb = (bi < be) ? __ldg(P.bin_list + bi) : 0x7fffffff;
+            const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
             if (sb <= sg) { s = sb; ++bi; if (sb == sg) ++gi; }
             else { s = sg; ++gi; }
-            const DevSolid &S = P.solids[s];
-            const int qc = quick_class(S, cc, rad);
+            const int qc = quick_class(P.solids[s], cc, rad);
             if (qc == 0) continue;
-            const DevShape &sh = P.shapes[S.shape];
-            const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-            const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-            if (!have_cell_data) {
-                const int pb = __ldg(m.cp_off + c);
-                nv = __ldg(m.cp_off + c + 1) - pb;
-                if (nv > MAX_CELL_VERTS) { nv = MAX_CELL_VERTS; P.status->bad_cell = 1; }
-                for (int k = 0; k < nv; ++k) vid[k] = __ldg(m.cp + pb + k);
-                have_cell_data = true;
-            }
-            int n_in = nv;
-            if (qc == 2) {
-                n_in = 0;
-                for (int k = 0; k < nv; ++k) {
-                    pts[k] = ld3(m.points, vid[k]);
-                    double ph;
-                    n_in += shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph) ? 1 : 0;
-                    phi[k] = ph;
-                }
-                if (n_in == 0) continue;
-            }
-            if (n_in == nv) type = SDFIBM_CELL_ALL_INSIDE;
-            else {
-                double dummy;
-                type = shape_eval<false>(sh.s, world2local(q, t, cc), dummy) ? SDFIBM_CELL_CENTER_INSIDE
-                                                                               : SDFIBM_CELL_CENTER_OUTSIDE;
-            }
-            // replay mode: pairs outside the seed's component are not part of the flood fill
-            if (P.excluded && nslot < P.K && P.excluded[(long long)c * P.K + nslot]) {
-                if (nslot < P.K) P.slots[(long long)c * P.K + nslot] = (s << 2) | type;
-                ++nslot;
-                continue;
-            }
-            if (!have_uv) {
-                uf = ld3(P.U, c);
-                vol = __ldg(m.V + c);
-                have_uv = true;
-            }
-            double alpha = 1.0;
-            if (type != SDFIBM_CELL_ALL_INSIDE) alpha = cell_solid_volume(m, c, vid, pts, phi, nv) / vol;
-            // solidcloud.cpp:384-390,411-421
-            const D3 om = {S.omega[0], S.omega[1], S.omega[2]};
-            const D3 us = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(om, cc - t);
-            const D3 f_ = alpha * (uf - us);
-            const D3 t_ = cross3(cc - t, f_);
-            const D3 fo = f_ * vol * P.dtINV;
-            const D3 to = t_ * vol * P.dtINV;
-            contrib[0] = fo.x; contrib[1] = fo.y; contrib[2] = fo.z;
-            contrib[3] = to.x; contrib[4] = to.y; contrib[5] = to.z;
-            as += alpha;
-            fs = fs + f_ * P.dtINV;
-            ts += alpha;
-            ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;   // :376-382, last writer wins
-            if (nslot < P.K) P.slots[(long long)c * P.K + nslot] = (s << 2) | type;
-            else P.status->slot_overflow = 1;
-            ++nslot;
-            have = true;
-            break;
+            if (n_item < P.K) {
+                P.slots[(long long)c * P.K + n_item] = (s << 2) | qc;   // 1 = certain ALL_INSIDE, 2 = heavy (pending)
+                if (qc == 2) { heavy_mask |= 1u << n_item; ++n_heavy; }
+                ++n_item;
+            } else P.status->slot_overflow = 1;
         }
-        // ---- converged part ------------------------------------------------------------------
-        if (!__any_sync(0xffffffffu, have)) break;
-        warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
+        P.n_item[c] = (unsigned char)n_item;
+    }
+    // warp-aggregated append of the heavy items to the global queue
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int incl = n_heavy;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(P.heavy_count, (unsigned long long)total);
+    base = __shfl_sync(FULL, base, 31);
+    long long pos = (long long)base + incl - n_heavy;
+    while (heavy_mask) {
+        const int j = __ffs(heavy_mask) - 1;
+        heavy_mask &= heavy_mask - 1;
+        if (pos < P.heavy_cap) P.heavy[pos] = make_int2(c, j);
+        ++pos;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_accumulate(InteractParams P) {
+    const DevMesh &m = P.m;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < m.n_cells;
+    const int n = live ? (int)P.n_item[c] : 0;
+    const unsigned FULL = 0xffffffffu;
+    int nmax = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+
+    double as = 0.0, ts = 0.0, ct = 0.0;
+    D3 fs = {0.0, 0.0, 0.0};
+    if (nmax > 0) {
+        D3 cc = {0, 0, 0}, uf = {0, 0, 0};
+        double vol = 1.0;
+        if (n > 0) {
+            cc = ld3(m.cc, c);
+            uf = ld3(P.U, c);
+            vol = __ldg(m.V + c);
+        }
+        int nslot = 0;
+        bool ended = false;
+        for (int j = 0; j < nmax; ++j) {
+            bool have = false;
+            int s = -1, type = 0;
+            double contrib[6] = {0, 0, 0, 0, 0, 0};
+            if (j < n && !ended) {
+                const long long si = (long long)c * P.K + j;
+                const int e = P.slots[si];
+                if (e < 0) ended = true;                                   // terminator of an earlier (compacting) pass
+                else if ((e & 3) != 0) {
+                    type = e & 3;
+                    s = e >> 2;
+                    const double v = (type == SDFIBM_CELL_ALL_INSIDE) ? 0.0 : P.vols[si];
+                    const long long so = (long long)c * P.K + nslot;       // compact the members to the front
+                    if (nslot != j) { P.slots[so] = e; P.vols[so] = v; }
+                    const bool skip = P.excluded && P.excluded[so];        // replay: outside the seed's component
+                    ++nslot;
+                    if (!skip) {
+                        const DevSolid &S = P.solids[s];
+                        const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+                        const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol;   // solidcloud.cpp:408-410
+                        // solidcloud.cpp:384-390,411-421
+                        const D3 om = {S.omega[0], S.omega[1], S.omega[2]};
+                        const D3 us = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(om, cc - t);
+                        const D3 f_ = alpha * (uf - us);
+                        const D3 t_ = cross3(cc - t, f_);
+                        const D3 fo = f_ * vol * P.dtINV;
+                        const D3 to = t_ * vol * P.dtINV;
+                        contrib[0] = fo.x; contrib[1] = fo.y; contrib[2] = fo.z;
+                        contrib[3] = to.x; contrib[4] = to.y; contrib[5] = to.z;
+                        as += alpha;
+                        fs = fs + f_ * P.dtINV;
+                        ts += alpha;
+                        ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;   // :376-382, last writer wins
+                        have = true;
+                    }
+                }
+            }
+            if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
+        }
+        if (n > 0 && nslot < P.K) P.slots[(long long)c * P.K + nslot] = -1;
+        if (live && nslot == 0) ct = 0.0;
+        if (live && nslot > 0 && ct == 0.0) ct = -1.0;   // only excluded pairs (replay): slots stay valid for the list extraction
     }
     if (live) {
-        if (nslot < P.K && nslot > 0) P.slots[(long long)c * P.K + nslot] = -1;
         P.As[c] = (as < 1.0) ? as : 1.0;                                           // checkAlpha, :564-570 (std::min(As,1))
         P.Fs[3 * (long long)c] = fs.x;
         P.Fs[3 * (long long)c + 1] = fs.y;
         P.Fs[3 * (long long)c + 2] = fs.z;
         P.Ts[c] = ts;
-        P.Ct[c] = (nslot > 0 && ct == 0.0) ? -1.0 : ct; // -1: only excluded pairs (replay); fixed up below
+        P.Ct[c] = ct;
     }
 }
+
 
 // replay mode leaves Ct = -1 on cells whose only pairs were excluded; they are untouched cells.
 __global__ void k_fix_ct(double *Ct, int n) {
@@ -915,6 +1129,8 @@ struct sdfibm_context {
     DevBuf<double> points, cc, V, Cf, Sf;
     DevBuf<int> cp_off, cp, cf_off, cf, fp_off, fp, nb_off, nb;
     DevBuf<float2> cell_rad;
+    DevBuf<double> magSf;
+    DevBuf<unsigned> hex_topo;
     double bmin[3], bmax[3];
     float rad3_max = 0.f, radxy_max = 0.f;
     // shapes
@@ -924,6 +1140,9 @@ struct sdfibm_context {
     DevBuf<sdfibm_solid_t> solids_in;
     DevBuf<DevSolid> solids;
     DevBuf<int> bin_count, bin_off, bin_cursor, bin_list, global_list, root_count, slots;
+    DevBuf<double> vols;
+    DevBuf<unsigned char> n_item;
+    DevBuf<int2> heavy;
     DevBuf<unsigned> pair_counts;
     DevBuf<double> ft_internal;
     DevBuf<StepStatus> status;
@@ -943,8 +1162,9 @@ struct sdfibm_context {
     bool last_used_replay = false;
     // stats
     StepStatus last{};
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    double t_ms[4] = {0, 0, 0, 0}; // binning, k_interact, connectivity+finalize, whole pipeline (device time, last call)
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double t_ms[6] = {0, 0, 0, 0, 0, 0}; // binning, k_classify, k_heavy, k_accumulate, connectivity+finalise, whole pipeline
+    int n_sm = 148;
     int64_t launches = 0;
     int64_t flagged_last = 0;
 };
@@ -1011,7 +1231,8 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(StepStatus)));
     CUDA_TRY(ctx->status.ensure(1));
-    for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    CUDA_TRY(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device));
     *out = ctx;
     return SDFIBM_OK;
 }
@@ -1023,14 +1244,15 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->points.release(); ctx->cc.release(); ctx->V.release(); ctx->Cf.release(); ctx->Sf.release();
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
-    ctx->cell_rad.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    ctx->cell_rad.release(); ctx->magSf.release(); ctx->hex_topo.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
     ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
+    ctx->vols.release(); ctx->n_item.release(); ctx->heavy.release();
     ctx->ft_internal.release(); ctx->status.release(); ctx->scan_tmp.release();
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
-    for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_solids) cudaFreeHost(ctx->h_solids);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1082,6 +1304,9 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     if ((rc = upload(ctx->nb, m->cell_cells, (size_t)m->cell_cells_off[nC], st))) return rc;
     CUDA_TRY(ctx->cell_rad.ensure(nC));
     CUDA_TRY(ctx->slots.ensure(nC * ctx->K));
+    CUDA_TRY(ctx->vols.ensure(nC * ctx->K));
+    CUDA_TRY(ctx->n_item.ensure(nC));
+    CUDA_TRY(ctx->heavy.ensure(std::max<size_t>(1 << 20, nC / 2)));
     DevMesh &d = ctx->dm;
     d.n_cells = m->n_cells; d.n_points = m->n_points; d.n_faces = m->n_faces;
     d.points = ctx->points.p; d.cc = ctx->cc.p; d.V = ctx->V.p; d.Cf = ctx->Cf.p; d.Sf = ctx->Sf.p;
@@ -1089,26 +1314,50 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     d.fp_off = ctx->fp_off.p; d.fp = ctx->fp.p; d.nb_off = ctx->nb_off.p; d.nb = ctx->nb.p;
     d.cell_rad = ctx->cell_rad.p;
     d.two_d = two_d ? 1 : 0;
+    // hexahedral fast path?
+    bool is_hex = true;
+    for (size_t c = 0; c < nC && is_hex; ++c)
+        is_hex = (m->cell_points_off[c + 1] - m->cell_points_off[c] == 8) && (m->cell_faces_off[c + 1] - m->cell_faces_off[c] == 6);
+    for (size_t f = 0; f < nF && is_hex; ++f) is_hex = (m->face_points_off[f + 1] - m->face_points_off[f] == 4);
+    is_hex = is_hex && m->cell_points_off[0] == 0 && m->cell_faces_off[0] == 0 && m->face_points_off[0] == 0;
+    d.is_hex = is_hex ? 1 : 0;
+    CUDA_TRY(ctx->magSf.ensure(nF));
+    d.magSf = ctx->magSf.p;
+    d.hex_topo = nullptr;
+    k_face_mag<<<grid_for(nF, 256), 256, 0, st>>>(d.Sf, (int)nF, ctx->magSf.p);
     for (int k = 0; k < 3; ++k) { ctx->bmin[k] = m->bounds_min[k]; ctx->bmax[k] = m->bounds_max[k]; }
     // per-cell radii + maxima
     DevBuf<int> bad;
     DevBuf<float> rmax;
     CUDA_TRY(bad.ensure(1));
-    CUDA_TRY(rmax.ensure(2));
+    CUDA_TRY(rmax.ensure(4));
     CUDA_TRY(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(rmax.p, 0, 2 * sizeof(float), st));
+    {
+        const float init[4] = {0.f, 0.f, 3.0e38f, 3.0e38f};
+        CUDA_TRY(cudaMemcpyAsync(rmax.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     k_cell_radius<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->cell_rad.p, bad.p, rmax.p);
+    if (is_hex) {
+        CUDA_TRY(ctx->hex_topo.ensure(3 * nC));
+        d.hex_topo = ctx->hex_topo.p;
+        k_hex_topo<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->hex_topo.p, bad.p);
+    }
     CUDA_TRY(cudaGetLastError());
     int h_bad = 0;
-    float h_rmax[2];
+    float h_rmax[4];
     CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h_rmax, rmax.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_rmax, rmax.p, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     bad.release();
     rmax.release();
-    if (h_bad) return fail(SDFIBM_ERR_UNSUPPORTED, "sdfibm_set_mesh: a cell has more than 32 vertices or a face more than 16");
+    if (h_bad) return fail(SDFIBM_ERR_UNSUPPORTED, "sdfibm_set_mesh: a cell has more than 32 vertices, a face more than 16, or inconsistent cell/face point lists");
     ctx->rad3_max = h_rmax[0];
     ctx->radxy_max = h_rmax[1];
+    // near-uniform cell sizes: the mesh-wide upper bound serves every cell (always conservative) and the
+    // per-cell radius array is not read by the interact kernel
+    d.rad_const = make_float2(h_rmax[0], h_rmax[1]);
+    d.rad_uniform = (h_rmax[0] <= 1.05f * h_rmax[2] && h_rmax[1] <= 1.05f * h_rmax[3]) ? 1 : 0;
     ctx->has_mesh = true;
     ctx->last_Ct = nullptr;
     return SDFIBM_OK;
@@ -1292,6 +1541,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             StepStatus keep{};
             keep.n_global = ctx->last.n_global;
             keep.bin_total = ctx->last.bin_total;
+            keep.heavy_total = ctx->last.heavy_total;
             CUDA_TRY(cudaMemcpyAsync(ctx->status.p, &keep, sizeof(StepStatus), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         }
@@ -1300,10 +1550,23 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.global_list = ctx->global_list.p; I.U = dU;
         I.dtINV = 1.0 / dt; I.rhof = rhof; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
         I.pair_counts = ctx->pair_counts.p; I.slots = ctx->slots.p; I.K = ctx->K;
+        I.vols = ctx->vols.p; I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p;
+        I.heavy_count = &ctx->status.p->heavy_total; I.heavy_cap = (long long)ctx->heavy.n; I.n_global = 0;
         I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status.p;
         CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        k_interact<<<grid_for(nC, 128), 128, 0, st>>>(I);
-        CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        if (!replay) {
+            k_classify<<<grid_for(nC, 256), 256, 0, st>>>(I);
+            CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+            const int hgrid = ctx->n_sm * 4;
+            if (ctx->dm.is_hex) k_heavy<true><<<hgrid, TPB, 0, st>>>(I);
+            else k_heavy<false><<<hgrid, TPB, 0, st>>>(I);
+            ctx->launches += 2;
+        } else {
+            CUDA_TRY(cudaEventRecord(ctx->ev[2], st));   // replay re-uses the classified and evaluated slots
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+        k_accumulate<<<grid_for(nC, 256), 256, 0, st>>>(I);
+        CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         ++ctx->launches;
         if (replay) { k_fix_ct<<<grid_for(nC, 256), 256, 0, st>>>(dCt, nC); ++ctx->launches; }
         else {
@@ -1315,24 +1578,30 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts.p, ctx->root_count.p, n_solids, ctx->status.p);
         k_scale_ft<<<grid_for(6LL * n_solids, 256), 256, 0, st>>>(dFT, 6 * n_solids, rhof);
         ctx->launches += 2;
-        CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+        CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status.p, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         {
-            float a = 0, b = 0, c = 0, d = 0;
-            cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-            cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
-            cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
-            cudaEventElapsedTime(&d, ctx->ev[0], ctx->ev[3]);
             const double add = replay ? 1.0 : 0.0; // a replay pass adds to the first pass of the same call
-            ctx->t_ms[0] = add * ctx->t_ms[0] + a;
-            ctx->t_ms[1] = add * ctx->t_ms[1] + b;
-            ctx->t_ms[2] = add * ctx->t_ms[2] + c;
-            ctx->t_ms[3] = add * ctx->t_ms[3] + d;
+            for (int k = 0; k < 5; ++k) {
+                float x = 0;
+                cudaEventElapsedTime(&x, ctx->ev[k], ctx->ev[k + 1]);
+                ctx->t_ms[k] = add * ctx->t_ms[k] + x;
+            }
+            float d = 0;
+            cudaEventElapsedTime(&d, ctx->ev[0], ctx->ev[5]);
+            ctx->t_ms[5] = add * ctx->t_ms[5] + d;
         }
-        ctx->last = *ctx->h_status;
-        if (replay) ctx->last.n_flagged = (int)ctx->flagged_last;
+        {
+            const StepStatus prev = ctx->last;
+            ctx->last = *ctx->h_status;
+            if (replay) { ctx->last.n_flagged = (int)ctx->flagged_last; ctx->last.heavy_total = prev.heavy_total; }
+        }
+        if (!replay && ctx->last.heavy_total > (unsigned long long)ctx->heavy.n && attempt == 0) {
+            CUDA_TRY(ctx->heavy.ensure((size_t)(ctx->last.heavy_total + ctx->last.heavy_total / 4 + 1024)));
+            continue;
+        }
         if (ctx->last.bin_overflow && !replay && attempt == 0) {
             CUDA_TRY(ctx->bin_list.ensure((size_t)ctx->last.bin_total + (size_t)ctx->last.bin_total / 4 + 1024));
             continue;
@@ -1418,13 +1687,13 @@ int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]) {
     stats[0] = ctx->flagged_last;
     stats[1] = ctx->launches;
     stats[2] = ctx->last.bin_total;
-    stats[3] = ctx->last.n_global;
+    stats[3] = (int64_t)ctx->last.heavy_total;
     return SDFIBM_OK;
 }
 
-int sdfibm_last_timings(sdfibm_context *ctx, double ms[4]) {
+int sdfibm_last_timings(sdfibm_context *ctx, double ms[6]) {
     if (!ctx || !ms) return fail(SDFIBM_ERR_ARG, "null argument");
-    for (int k = 0; k < 4; ++k) ms[k] = ctx->t_ms[k];
+    for (int k = 0; k < 6; ++k) ms[k] = ctx->t_ms[k];
     return SDFIBM_OK;
 }
 
