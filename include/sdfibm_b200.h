@@ -118,7 +118,7 @@ int sdfibm_device_count(int *count);
 /* One context per rank/GPU; owns one CUDA stream.  replaces SolidCloud ctor device part (solidcloud.cpp:209-217). */
 int sdfibm_create(int device, sdfibm_context **ctx);
 int sdfibm_destroy(sdfibm_context *ctx);
-/* max solids that may touch one mesh cell (default 4); call before sdfibm_set_mesh */
+/* max solids that may touch one mesh cell (default 3); call before sdfibm_set_mesh */
 int sdfibm_set_cell_slots(sdfibm_context *ctx, int slots);
 
 /* ---- one-time uploads ------------------------------------------------------------- */

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libsdfibm_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "sdfibm_cuda.cu"), os.path.join(HERE, "csrc", "mesh_host.cpp")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "device_math.cuh"), os.path.join(ROOT, "include", "sdfibm_b200.h")]
+DEPS = SOURCES + [os.path.join(HERE, "csrc", "device_math.cuh"), os.path.join(HERE, "csrc", "interact_kernels.cuh"), os.path.join(ROOT, "include", "sdfibm_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -1,0 +1,703 @@
+// interact_kernels.cuh — the sm_100a kernels of SolidCloud::interact / fixInternal.
+// Included by sdfibm_cuda.cu after the device records (DevMesh, DevSolid, DevShape, BinGrid, StepStatus).
+//
+//   k_classify      thread per cell   candidate solids (ascending id) -> per-cell slot record; pairs whose
+//                                     vertices must be evaluated exactly are appended to a global queue
+//   k_heavy         thread per item   exact vertex predicates + SDF, cell type, apex/pyramid volume (dense, no barriers)
+//   k_accumulate    thread per cell   As/Fs/Ts/Ct in the reference's += order, written once and coalesced;
+//                                     per-solid force/torque warp-aggregated before the atomics
+//   k_connectivity  thread per cell   certificate that each solid's cell set is one face-connected component
+//   k_replay_*                        exact flood-fill component selection for solids that fail it (rare)
+//   k_fix_internal  thread per cell   SolidCloud::fixInternal
+//   k_list_*                          candidate-list extraction for parity (off the timed path)
+//
+// Slot record of cell c: KS = K+1 ints at slots + c*KS.  [0] = index of the cell's first heavy item in the
+// queue; [1+j] = (solid << 3) | (heavy ? 4 : 0) | type, j < n_item[c].  type is the CELL_TYPE (1,2,3) or 0
+// (no vertex inside: not a member).  Heavy items of a cell are consecutive in the queue, in slot order.
+#pragma once
+
+#define TPB 128
+#define SLOT_HEAVY 4
+
+// ------------------------------------------------------------------------------------------------
+// geometry: apex / pyramid volume fraction (reference src/geometrictools.cpp:13-116)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double line_fraction(double a, double b) {          // :13-23
+    if (a > 0 && b > 0) return 0.0;
+    if (a <= 0 && b <= 0) return 1.0;
+    if (a > 0) return -b / (a - b);
+    return -a / (b - a);
+}
+
+// calcApex over an indexed vertex list (:25-45).  pts/phi are the cell-local arrays, idx maps the
+// list position to the cell-local slot (identity for the cell's own vertex list).
+template <typename IDX>
+__device__ __forceinline__ D3 calc_apex(const D3 *pts, const double *phi, IDX idx, int n) {
+    const int i0 = idx(0);
+    D3 A = pts[i0];
+    double phiA = phi[i0];
+    D3 B = {0.0, 0.0, 0.0};
+    double phiB = 0.0;
+    for (int i = 1; i < n; ++i) {
+        int ii = idx(i);
+        B = pts[ii];
+        phiB = phi[ii];
+        if (phiA * phiB <= 0) break;
+    }
+    return A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
+}
+
+// calcCellVolume (:47-72) for cell c with cell-local vertex coordinates and phi already evaluated (general polyhedra).
+__device__ double cell_solid_volume(const DevMesh &m, int c, const int *vid, const D3 *pts, const double *phi, int nv) {
+    D3 apex = calc_apex(pts, phi, [](int i) { return i; }, nv);
+    if (m.two_d) apex.z = 0.0;
+    double volume = 0.0;
+    const int fb = __ldg(m.cf_off + c), fe = __ldg(m.cf_off + c + 1);
+    for (int k = fb; k < fe; ++k) {
+        const int f = __ldg(m.cf + k);
+        const int pb = __ldg(m.fp_off + f), nf = __ldg(m.fp_off + f + 1) - pb;
+        int loc[MAX_FACE_VERTS];
+        int sign_sum = 0;
+        for (int i = 0; i < nf; ++i) {
+            const int g = __ldg(m.fp + pb + i);
+            int l = 0;
+            while (l < nv - 1 && vid[l] != g) ++l;
+            loc[i] = l;
+            if (phi[l] > 0) ++sign_sum;
+            else --sign_sum;
+        }
+        double eps_f;
+        const D3 Sf = ld3(m.Sf, f);
+        if (sign_sum == nf) eps_f = 0.0;                                        // :98-116
+        else if (sign_sum == -nf) eps_f = 1.0;
+        else {
+            D3 fap = calc_apex(pts, phi, [&](int i) { return loc[i]; }, nf);    // calcFaceArea :74-96
+            double area = 0.0;
+            for (int i = 0; i < nf; ++i) {
+                const int lo = loc[i], la = loc[(i + 1) % nf];
+                const D3 O = pts[lo], A = pts[la];
+                area += fabs(0.5 * mag3(cross3(A - O, fap - O))) * line_fraction(phi[lo], phi[la]);
+            }
+            eps_f = area / __ldg(m.magSf + f);
+        }
+        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - ld3(m.Cf, f), Sf));
+    }
+    return volume;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conservative pre-classification of (cell, solid): 0 = no vertex can be inside, 1 = every vertex is
+// certainly inside, 2 = evaluate the vertices exactly.  Margins (REL_MARGIN) dwarf fp64 rounding, so
+// the exact predicate's outcome is never changed — only skipped when it is certain.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad) {
+    const D3 r = cc - D3{S.pos[0], S.pos[1], S.pos[2]};
+    const double d2 = dot3(r, r);
+    if (S.kind == KIND_3D) {
+        // d - rad > r_out  <=>  d^2 > (r_out + rad)^2 ;  d + rad < r_in  <=>  d^2 < (r_in - rad)^2 with r_in > rad
+        // (the 1e-6 relative margins inside r_out / r_in / rad dwarf the rounding of the squares)
+        const double ro = S.r_out + (double)rad.x, ri = S.r_in - (double)rad.x;
+        if (d2 > ro * ro) return 0;
+        if (ri > 0.0 && d2 < ri * ri) return 1;
+        return 2;
+    }
+    if (S.kind == KIND_2D) {
+        const double t = r.x * S.axis[0] + r.y * S.axis[1] + r.z * S.axis[2];
+        const double dax = sqrt(fmax(0.0, d2 - t * t));
+        const double rr = S.axis_is_z ? (double)rad.y : (double)rad.x;
+        const double slack = 1e-9 * (sqrt(d2) + 1.0);
+        if (dax - rr - slack > S.r_out) return 0;
+        if (dax + rr + slack < S.r_in) return 1;
+        return 2;
+    }
+    // plane: body-frame y of the centre
+    DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+    const double yl = world2local(q, D3{S.pos[0], S.pos[1], S.pos[2]}, cc).y;
+    const double m = (double)rad.x + 1e-11 * (sqrt(d2) + 1.0);
+    if (yl > m) return 0;
+    if (yl < -m) return 1;
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameters shared by the classify / heavy / accumulate kernels
+// ------------------------------------------------------------------------------------------------
+struct InteractParams {
+    DevMesh m;
+    const DevSolid *solids;
+    const DevShape *shapes;
+    int n_solids;
+    BinGrid grid;
+    const int *bin_off;
+    const int *bin_list;
+    const int *global_list;
+    const double *U;
+    double dtINV, rhof;
+    double *As, *Fs, *Ts, *Ct;
+    double *force_torque;   // [6*n_solids], zeroed
+    unsigned *pair_counts;  // [3*n_solids], zeroed
+    int *slots;             // [n_cells*(K+1)] slot records (see file header)
+    unsigned char *n_item;  // [n_cells] slots in use
+    int2 *heavy;            // queue of (cell, solid) needing exact evaluation
+    double *heavy_vol;      // [queue] solid volume inside the cell (boundary types)
+    unsigned char *heavy_type; // [queue] resulting CELL_TYPE or 0
+    unsigned long long *heavy_count;
+    long long heavy_cap;
+    int K;
+    int final_slots;        // replay pass: slot types are already final
+    const unsigned char *excluded; // replay pass: [n_cells*K] 1 = pair is outside the seed's component
+    StepStatus *status;
+};
+
+// ------------------------------------------------------------------------------------------------
+// k_classify
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_classify(InteractParams P) {
+    const DevMesh &m = P.m;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < m.n_cells;
+    const int KS = P.K + 1;
+    int n_item = 0, n_heavy = 0;
+    if (live) {
+        const D3 cc = ld3(m.cc, c);
+        const float2 rad = m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c);
+        const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] +
+                      bin_coord(P.grid, cc.x, 0);
+        int bi = __ldg(P.bin_off + b);
+        const int be = __ldg(P.bin_off + b + 1);
+        int gi = 0;
+        const int ge = P.status->n_global;
+        int *rec = P.slots + (long long)c * KS;
+        while (bi < be || gi < ge) {
+            // merge the bin list and the global list in ascending solid id
+            int s;
+            const int sb = (bi < be) ? __ldg(P.bin_list + bi) : 0x7fffffff;
+            const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
+            if (sb <= sg) { s = sb; ++bi; if (sb == sg) ++gi; }
+            else { s = sg; ++gi; }
+            const int qc = quick_class(P.solids[s], cc, rad);
+            if (qc == 0) continue;
+            if (n_item < P.K) {
+                rec[1 + n_item] = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
+                n_heavy += (qc == 2);
+                ++n_item;
+            } else P.status->slot_overflow = 1;
+        }
+        P.n_item[c] = (unsigned char)n_item;
+    }
+    // warp-aggregated append of the heavy items to the global queue (one atomic per warp)
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int incl = n_heavy;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(P.heavy_count, (unsigned long long)total);
+    base = __shfl_sync(FULL, base, 31);
+    if (n_heavy == 0) return;
+    long long pos = (long long)base + incl - n_heavy;
+    int *rec = P.slots + (long long)c * KS;
+    rec[0] = (int)pos;
+    for (int j = 0; j < n_item; ++j) {
+        const int e = rec[1 + j];
+        if (e & SLOT_HEAVY) {
+            if (pos < P.heavy_cap) P.heavy[pos] = make_int2(c, e >> 3);
+            ++pos;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_heavy: exact evaluation of one (cell, solid) item
+// ------------------------------------------------------------------------------------------------
+// General polyhedra: cell-local arrays in local memory, CSR connectivity.
+__device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out) {
+    const DevMesh &m = P.m;
+    const DevSolid &S = P.solids[s];
+    const DevShape &sh = P.shapes[S.shape];
+    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+    int vid[MAX_CELL_VERTS];
+    D3 pts[MAX_CELL_VERTS];
+    double phi[MAX_CELL_VERTS];
+    const int pb = __ldg(m.cp_off + c);
+    int nv = __ldg(m.cp_off + c + 1) - pb;
+    if (nv > MAX_CELL_VERTS) { nv = MAX_CELL_VERTS; P.status->bad_cell = 1; }
+    int n_in = 0;
+    for (int k = 0; k < nv; ++k) {
+        vid[k] = __ldg(m.cp + pb + k);
+        pts[k] = ld3(m.points, vid[k]);
+        double ph;
+        n_in += shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph) ? 1 : 0;
+        phi[k] = ph;
+    }
+    type_out = 0;
+    vol_out = 0.0;
+    if (n_in == 0) return;
+    if (n_in == nv) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
+    double dummy;
+    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+    vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
+}
+
+// Hexahedral fast path: fixed 8/6/4 strides, per-cell face->vertex-slot nibbles precomputed at upload,
+// vertex coordinates and phi staged in transposed shared memory (column = executing thread) so that the
+// data-dependent slot indexing is bank-conflict free.
+__device__ __forceinline__ void heavy_eval_hex(const InteractParams &P, int c, int s, int col, double *s_px, double *s_py,
+                                               double *s_pz, double *s_phi, int &type_out, double &vol_out) {
+    const DevMesh &m = P.m;
+    const DevSolid &S = P.solids[s];
+    const DevShape &sh = P.shapes[S.shape];
+    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+    const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
+    const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
+    const int vid[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    int n_in = 0;
+#pragma unroll 2
+    for (int k = 0; k < 8; ++k) {
+        const D3 p = ld3(m.points, vid[k]);
+        double ph;
+        n_in += shape_eval<true>(sh.s, world2local(q, t, p), ph) ? 1 : 0;
+        s_px[k * TPB + col] = p.x;
+        s_py[k * TPB + col] = p.y;
+        s_pz[k * TPB + col] = p.z;
+        s_phi[k * TPB + col] = ph;
+    }
+    type_out = 0;
+    vol_out = 0.0;
+    if (n_in == 0) return;
+    if (n_in == 8) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
+    double dummy;
+    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+
+    auto PT = [&](int l) { return D3{s_px[l * TPB + col], s_py[l * TPB + col], s_pz[l * TPB + col]}; };
+    auto PH = [&](int l) { return s_phi[l * TPB + col]; };
+    // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
+    D3 apex;
+    {
+        const D3 A = PT(0);
+        const double phiA = PH(0);
+        D3 B = {0.0, 0.0, 0.0};
+        double phiB = 0.0;
+        for (int i = 1; i < 8; ++i) {
+            B = PT(i);
+            phiB = PH(i);
+            if (phiA * phiB <= 0) break;
+        }
+        apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
+        if (m.two_d) apex.z = 0.0;
+    }
+    const unsigned *topo = m.hex_topo + 3 * (long long)c;
+    const int *cfp = m.cf + 6 * (long long)c;
+    double volume = 0.0;
+#pragma unroll 1
+    for (int f = 0; f < 6; ++f) {
+        const unsigned nib = (__ldg(topo + (f >> 1)) >> (16 * (f & 1))) & 0xffffu;
+        const int l[4] = {(int)(nib & 0xf), (int)((nib >> 4) & 0xf), (int)((nib >> 8) & 0xf), (int)((nib >> 12) & 0xf)};
+        const double ph[4] = {PH(l[0]), PH(l[1]), PH(l[2]), PH(l[3])};
+        const int npos = (ph[0] > 0) + (ph[1] > 0) + (ph[2] > 0) + (ph[3] > 0);
+        if (npos == 4) continue;                                                // eps_f = 0: adds +0.0 (:107-108)
+        const int face = __ldg(cfp + f);
+        double eps_f = 1.0;                                                     // all phi <= 0 (:109-110)
+        if (npos != 0) {
+            const D3 A = PT(l[0]);                                              // calcFaceArea (:74-96)
+            D3 B = PT(l[1]);
+            double phiB = ph[1];
+            if (!(ph[0] * ph[1] <= 0)) {
+                B = PT(l[2]);
+                phiB = ph[2];
+                if (!(ph[0] * ph[2] <= 0)) { B = PT(l[3]); phiB = ph[3]; }
+            }
+            const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - B);
+            double area = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
+                if (lf != 0.0) {                                                // a zero fraction adds +0.0
+                    const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
+                    area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;
+                }
+            }
+            eps_f = area / __ldg(m.magSf + face);
+        }
+        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - ld3(m.Cf, face), ld3(m.Sf, face)));
+    }
+    vol_out = volume;
+}
+
+#define HEAVY_CTAS_PER_SM 6
+template <bool HEX>
+__global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy(InteractParams P) {
+    __shared__ double s_px[HEX ? 8 * TPB : 1], s_py[HEX ? 8 * TPB : 1], s_pz[HEX ? 8 * TPB : 1], s_phi[HEX ? 8 * TPB : 1];
+    const int tid = threadIdx.x;
+    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
+    for (long long k = (long long)blockIdx.x * TPB + tid; k < n; k += (long long)gridDim.x * TPB) {
+        const int2 it = __ldg(P.heavy + k); // (cell, solid)
+        int type;
+        double v;
+        if (HEX) heavy_eval_hex(P, it.x, it.y, tid, s_px, s_py, s_pz, s_phi, type, v);
+        else heavy_eval_general(P, it.x, it.y, type, v);
+        P.heavy_type[k] = (unsigned char)type; // 0: no vertex inside -> not a member
+        P.heavy_vol[k] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_accumulate
+// ------------------------------------------------------------------------------------------------
+// warp-level aggregation of one member pair per lane: lanes with the same solid are reduced with a
+// butterfly and the group leader issues the 6 fp64 + counter reductions.
+__device__ __forceinline__ void warp_accumulate(bool have, int s, int type, const double v[6], double *force_torque,
+                                                unsigned *pair_counts) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned pending = __ballot_sync(FULL, have);
+    const int lane = threadIdx.x & 31;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int s0 = __shfl_sync(FULL, s, leader);
+        const bool mine = have && (s == s0);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        double w[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = mine ? v[k] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) w[k] += __shfl_xor_sync(FULL, w[k], o);
+        }
+        const unsigned c1 = __popc(__ballot_sync(FULL, mine && type == 1));
+        const unsigned c2 = __popc(__ballot_sync(FULL, mine && type == 2));
+        const unsigned c3 = __popc(__ballot_sync(FULL, mine && type == 3));
+        if (lane == leader) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(force_torque + 6 * (long long)s0 + k, w[k]);
+            if (c1) atomicAdd(pair_counts + 3 * (long long)s0 + 0, c1);
+            if (c2) atomicAdd(pair_counts + 3 * (long long)s0 + 1, c2);
+            if (c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
+        }
+        pending &= ~grp;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_accumulate(InteractParams P) {
+    const DevMesh &m = P.m;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < m.n_cells;
+    const int n = live ? (int)P.n_item[c] : 0;
+    const unsigned FULL = 0xffffffffu;
+    const int KS = P.K + 1;
+    int nmax = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+
+    double as = 0.0, ts = 0.0, ct = 0.0;
+    D3 fs = {0.0, 0.0, 0.0};
+    if (nmax > 0) {
+        D3 cc = {0, 0, 0}, uf = {0, 0, 0};
+        double vol = 1.0;
+        int *rec = P.slots + (long long)c * KS;
+        long long hk = 0;
+        if (n > 0) {
+            cc = ld3(m.cc, c);
+            uf = ld3(P.U, c);
+            vol = __ldg(m.V + c);
+            hk = rec[0];
+        }
+        for (int j = 0; j < nmax; ++j) {
+            bool have = false;
+            int s = -1, type = 0;
+            double contrib[6] = {0, 0, 0, 0, 0, 0};
+            if (j < n) {
+                const int e = rec[1 + j];
+                s = e >> 3;
+                type = e & 3;
+                double v = 0.0;
+                if (e & SLOT_HEAVY) {
+                    if (!P.final_slots) {
+                        type = P.heavy_type[hk];
+                        rec[1 + j] = (e & ~3) | type;                       // the slot now carries the final type
+                    }
+                    if (type > SDFIBM_CELL_ALL_INSIDE) v = P.heavy_vol[hk];
+                    ++hk;
+                }
+                const bool skip = P.excluded && P.excluded[(long long)c * P.K + j]; // replay: outside the seed's component
+                if (type != 0 && !skip) {
+                    const DevSolid &S = P.solids[s];
+                    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+                    const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol;   // solidcloud.cpp:408-410
+                    // solidcloud.cpp:384-390,411-421
+                    const D3 om = {S.omega[0], S.omega[1], S.omega[2]};
+                    const D3 us = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(om, cc - t);
+                    const D3 f_ = alpha * (uf - us);
+                    const D3 t_ = cross3(cc - t, f_);
+                    const D3 fo = f_ * vol * P.dtINV;
+                    const D3 to = t_ * vol * P.dtINV;
+                    contrib[0] = fo.x; contrib[1] = fo.y; contrib[2] = fo.z;
+                    contrib[3] = to.x; contrib[4] = to.y; contrib[5] = to.z;
+                    as += alpha;
+                    fs = fs + f_ * P.dtINV;
+                    ts += alpha;
+                    ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;   // :376-382, last writer wins
+                    have = true;
+                }
+            }
+            if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
+        }
+    }
+    if (live) {
+        P.As[c] = (as < 1.0) ? as : 1.0;                                           // checkAlpha, :564-570 (std::min(As,1))
+        P.Fs[3 * (long long)c] = fs.x;
+        P.Fs[3 * (long long)c + 1] = fs.y;
+        P.Fs[3 * (long long)c + 2] = fs.z;
+        P.Ts[c] = ts;
+        P.Ct[c] = ct;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_connectivity: a member pair is a "root" when no face neighbour that is a member of the same solid has a
+// smaller (distance-to-centre, cell id) key.  Exactly one root  =>  the solid's vertex-inside cell set is
+// face connected  =>  it equals the reference's flood fill from any seed.
+// ------------------------------------------------------------------------------------------------
+struct ConnParams {
+    DevMesh m;
+    const DevSolid *solids;
+    const unsigned char *n_item;
+    const int *slots;
+    int K;
+    int *root_count; // [n_solids] zeroed
+};
+
+__device__ __forceinline__ bool key_less(double ka, int ca, double kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
+
+// slot index of solid s among the members of cell nb, or -1
+__device__ __forceinline__ int find_member(const unsigned char *n_item, const int *slots, int KS, int nb, int s) {
+    const int nn = n_item[nb];
+    const int *rec = slots + (long long)nb * KS;
+    for (int jj = 0; jj < nn; ++jj) {
+        const int e = rec[1 + jj];
+        if ((e >> 3) == s) return (e & 3) ? jj : -1;
+    }
+    return -1;
+}
+
+__global__ void k_connectivity(ConnParams P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.m.n_cells) return;
+    const int n = P.n_item[c];
+    if (n == 0) return;
+    const int KS = P.K + 1;
+    const D3 cc = ld3(P.m.cc, c);
+    const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
+    const int *rec = P.slots + (long long)c * KS;
+    for (int j = 0; j < n; ++j) {
+        const int e = rec[1 + j];
+        if ((e & 3) == 0) continue;
+        const int s = e >> 3;
+        const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
+        const double kc = magSqr3(cc - x);
+        bool has_parent = false;
+        for (int k = nb0; k < nb1 && !has_parent; ++k) {
+            const int nb = __ldg(P.m.nb + k);
+            if (find_member(P.n_item, P.slots, KS, nb, s) >= 0) {
+                const double kn = magSqr3(ld3(P.m.cc, nb) - x);
+                if (key_less(kn, nb, kc, c)) has_parent = true;
+            }
+        }
+        if (!has_parent) atomicAdd(P.root_count + s, 1);
+    }
+}
+
+__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status) {
+    unsigned long long c0 = 0, c1 = 0, c2 = 0;
+    int nf = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_solids; s += gridDim.x * blockDim.x) {
+        c0 += pair_counts[3 * s];
+        c1 += pair_counts[3 * s + 1];
+        c2 += pair_counts[3 * s + 2];
+        nf += root_count[s] > 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        nf += __shfl_xor_sync(0xffffffffu, nf, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c0) atomicAdd(&status->counts[0], c0);
+        if (c1) atomicAdd(&status->counts[1], c1);
+        if (c2) atomicAdd(&status->counts[2], c2);
+        if (nf) atomicAdd(&status->n_flagged, nf);
+    }
+}
+
+// rhof scaling of the per-solid sums (solidcloud.cpp:424-425)
+__global__ void k_scale_ft(double *ft, int n, double rhof) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ft[i] = ft[i] * rhof;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact flood-fill replay for solids that failed the certificate (rare path, all on the GPU)
+// ------------------------------------------------------------------------------------------------
+struct ReplayParams {
+    DevMesh m;
+    const DevSolid *solids;
+    const unsigned char *n_item;
+    const int *slots;
+    int K;
+    const int *root_count;
+    int *labels;                    // [n_cells*K] component label (min cell id) of flagged pairs
+    int *changed;
+    unsigned long long *seed_key;   // [n_solids] min dist^2 bits over candidate cells
+    int *seed_cell;                 // [n_solids]
+    int *min_label;                 // [n_solids]
+    int *chosen;                    // [n_solids]
+    unsigned char *excluded;        // [n_cells*K]
+    BinGrid grid;
+    const int *bin_off, *bin_list, *global_list;
+    int n_global, n_solids;
+};
+
+__global__ void k_replay_init(ReplayParams P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.m.n_cells) return;
+    for (int j = 0; j < P.K; ++j) { P.labels[(long long)c * P.K + j] = -1; P.excluded[(long long)c * P.K + j] = 0; }
+    const int n = P.n_item[c];
+    const int *rec = P.slots + (long long)c * (P.K + 1);
+    for (int j = 0; j < n; ++j) {
+        const int e = rec[1 + j];
+        if ((e & 3) != 0 && P.root_count[e >> 3] > 1) P.labels[(long long)c * P.K + j] = c;
+    }
+}
+
+__global__ void k_replay_propagate(ReplayParams P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.m.n_cells) return;
+    const int n = P.n_item[c];
+    if (n == 0) return;
+    const int KS = P.K + 1;
+    const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
+    const int *rec = P.slots + (long long)c * KS;
+    for (int j = 0; j < n; ++j) {
+        int lab = P.labels[(long long)c * P.K + j];
+        if (lab < 0) continue;
+        const int s = rec[1 + j] >> 3;
+        int best = lab;
+        for (int k = nb0; k < nb1; ++k) {
+            const int nb = __ldg(P.m.nb + k);
+            const int jj = find_member(P.n_item, P.slots, KS, nb, s);
+            if (jj >= 0) {
+                const int l2 = ((volatile int *)P.labels)[(long long)nb * P.K + jj];
+                if (l2 >= 0 && l2 < best) best = l2;
+            }
+        }
+        if (best < lab) { P.labels[(long long)c * P.K + j] = best; *P.changed = 1; }
+    }
+}
+
+// nearest cell centre to each flagged solid's centre, restricted to the cells that list the solid as
+// a candidate (sufficient: any member cell is within the binned bounding volume).
+__global__ void k_replay_seed(ReplayParams P, int pass) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.m.n_cells) return;
+    const D3 cc = ld3(P.m.cc, c);
+    const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] + bin_coord(P.grid, cc.x, 0);
+    const int b0 = P.bin_off[b], b1 = P.bin_off[b + 1];
+    for (int t = 0; t < (b1 - b0) + P.n_global; ++t) {
+        const int s = (t < b1 - b0) ? P.bin_list[b0 + t] : P.global_list[t - (b1 - b0)];
+        if (P.root_count[s] <= 1) continue;
+        const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
+        const unsigned long long key = (unsigned long long)__double_as_longlong(magSqr3(cc - x));
+        if (pass == 0) atomicMin(P.seed_key + s, key);
+        else if (key == P.seed_key[s]) atomicMin(P.seed_cell + s, c);
+    }
+    if (pass == 1) {
+        const int n = P.n_item[c];
+        const int *rec = P.slots + (long long)c * (P.K + 1);
+        for (int j = 0; j < n; ++j) {
+            const int lab = P.labels[(long long)c * P.K + j];
+            if (lab >= 0) atomicMin(P.min_label + (rec[1 + j] >> 3), lab);
+        }
+    }
+}
+
+__global__ void k_replay_choose(ReplayParams P) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_solids) return;
+    if (P.root_count[s] <= 1) { P.chosen[s] = -1; return; }
+    int chosen = P.min_label[s]; // component of the first member cell in index order (cellenumerator.cpp:52-63)
+    const int g = P.seed_cell[s];
+    if (g >= 0 && g < P.m.n_cells) {
+        const int jj = find_member(P.n_item, P.slots, P.K + 1, g, s);
+        if (jj >= 0) chosen = P.labels[(long long)g * P.K + jj]; // the nearest cell is a member: it is the seed
+    }
+    P.chosen[s] = chosen;
+}
+
+__global__ void k_replay_mark(ReplayParams P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.m.n_cells) return;
+    const int n = P.n_item[c];
+    const int *rec = P.slots + (long long)c * (P.K + 1);
+    for (int j = 0; j < n; ++j) {
+        const int lab = P.labels[(long long)c * P.K + j];
+        if (lab >= 0 && lab != P.chosen[rec[1 + j] >> 3]) P.excluded[(long long)c * P.K + j] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixInternal (solidcloud.cpp:288-301)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fix_internal(DevMesh m, const sdfibm_solid_t *solids, int n_solids, const double *Ct, double *U) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    const double ct = Ct[c];
+    if (ct >= 4) {
+        const int id = (int)(ct - 4);
+        if (id < n_solids) {
+            const sdfibm_solid_t &S = solids[id];
+            const D3 x = {S.pos[0], S.pos[1], S.pos[2]};
+            const D3 u = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(D3{S.omega[0], S.omega[1], S.omega[2]}, ld3(m.cc, c) - x);
+            U[3 * (long long)c] = u.x;
+            U[3 * (long long)c + 1] = u.y;
+            U[3 * (long long)c + 2] = u.z;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// candidate list extraction (parity output, off the timed path): pairs in cell order, then a stable
+// radix sort by (solid, type) gives ascending cell ids inside every segment (std::set order).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_list_count(const unsigned char *n_item, const int *slots, const unsigned char *excluded, int K, int n_cells, int *cnt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    int n = 0;
+    const int ni = n_item[c];
+    const int *rec = slots + (long long)c * (K + 1);
+    for (int j = 0; j < ni; ++j)
+        if ((rec[1 + j] & 3) != 0 && !(excluded && excluded[(long long)c * K + j])) ++n;
+    cnt[c] = n;
+}
+__global__ void k_list_emit(const unsigned char *n_item, const int *slots, const unsigned char *excluded, int K, int n_cells,
+                            const int *off, unsigned *keys, int *vals) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    int o = off[c];
+    const int ni = n_item[c];
+    const int *rec = slots + (long long)c * (K + 1);
+    for (int j = 0; j < ni; ++j) {
+        const int e = rec[1 + j];
+        if ((e & 3) == 0 || (excluded && excluded[(long long)c * K + j])) continue;
+        keys[o] = (unsigned)(3 * (e >> 3) + ((e & 3) - 1));
+        vals[o] = c;
+        ++o;
+    }
+}

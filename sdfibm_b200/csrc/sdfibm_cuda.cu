@@ -301,696 +301,7 @@ __global__ void k_bin_sort(const int *bin_off, int *bin_list, int n_bins, int bi
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// geometry: apex / pyramid volume fraction (reference src/geometrictools.cpp:13-116)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double line_fraction(double a, double b) {          // :13-23
-    if (a > 0 && b > 0) return 0.0;
-    if (a <= 0 && b <= 0) return 1.0;
-    if (a > 0) return -b / (a - b);
-    return -a / (b - a);
-}
-
-// calcApex over an indexed vertex list (:25-45).  pts/phi are the cell-local arrays, idx maps the
-// list position to the cell-local slot (identity for the cell's own vertex list).
-template <typename IDX>
-__device__ __forceinline__ D3 calc_apex(const D3 *pts, const double *phi, IDX idx, int n) {
-    const int i0 = idx(0);
-    D3 A = pts[i0];
-    double phiA = phi[i0];
-    D3 B = {0.0, 0.0, 0.0};
-    double phiB = 0.0;
-    for (int i = 1; i < n; ++i) {
-        int ii = idx(i);
-        B = pts[ii];
-        phiB = phi[ii];
-        if (phiA * phiB <= 0) break;
-    }
-    return A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
-}
-
-// calcCellVolume (:47-72) for cell c with cell-local vertex coordinates and phi already evaluated.
-__device__ double cell_solid_volume(const DevMesh &m, int c, const int *vid, const D3 *pts, const double *phi, int nv) {
-    D3 apex = calc_apex(pts, phi, [](int i) { return i; }, nv);
-    if (m.two_d) apex.z = 0.0;
-    double volume = 0.0;
-    const int fb = __ldg(m.cf_off + c), fe = __ldg(m.cf_off + c + 1);
-    for (int k = fb; k < fe; ++k) {
-        const int f = __ldg(m.cf + k);
-        const int pb = __ldg(m.fp_off + f), nf = __ldg(m.fp_off + f + 1) - pb;
-        int loc[MAX_FACE_VERTS];
-        int sign_sum = 0;
-        for (int i = 0; i < nf; ++i) {
-            const int g = __ldg(m.fp + pb + i);
-            int l = 0;
-            while (l < nv - 1 && vid[l] != g) ++l;
-            loc[i] = l;
-            if (phi[l] > 0) ++sign_sum;
-            else --sign_sum;
-        }
-        double eps_f;
-        const D3 Sf = ld3(m.Sf, f);
-        if (sign_sum == nf) eps_f = 0.0;                                        // :98-116
-        else if (sign_sum == -nf) eps_f = 1.0;
-        else {
-            D3 fap = calc_apex(pts, phi, [&](int i) { return loc[i]; }, nf);    // calcFaceArea :74-96
-            double area = 0.0;
-            for (int i = 0; i < nf; ++i) {
-                const int lo = loc[i], la = loc[(i + 1) % nf];
-                const D3 O = pts[lo], A = pts[la];
-                area += fabs(0.5 * mag3(cross3(A - O, fap - O))) * line_fraction(phi[lo], phi[la]);
-            }
-            eps_f = area / mag3(Sf);
-        }
-        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - ld3(m.Cf, f), Sf));
-    }
-    return volume;
-}
-
-// ------------------------------------------------------------------------------------------------
-// conservative pre-classification of (cell, solid): 0 = no vertex can be inside, 1 = every vertex is
-// certainly inside, 2 = evaluate the vertices exactly.  Margins (REL_MARGIN) dwarf fp64 rounding, so
-// the exact predicate's outcome is never changed — only skipped when it is certain.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad) {
-    const D3 r = cc - D3{S.pos[0], S.pos[1], S.pos[2]};
-    const double d2 = dot3(r, r);
-    if (S.kind == KIND_3D) {
-        // d - rad > r_out  <=>  d^2 > (r_out + rad)^2 ;  d + rad < r_in  <=>  d^2 < (r_in - rad)^2 with r_in > rad
-        // (the 1e-6 relative margins inside r_out / r_in / rad dwarf the rounding of the squares)
-        const double ro = S.r_out + (double)rad.x, ri = S.r_in - (double)rad.x;
-        if (d2 > ro * ro) return 0;
-        if (ri > 0.0 && d2 < ri * ri) return 1;
-        return 2;
-    }
-    if (S.kind == KIND_2D) {
-        const double t = r.x * S.axis[0] + r.y * S.axis[1] + r.z * S.axis[2];
-        const double dax = sqrt(fmax(0.0, d2 - t * t));
-        const double rr = S.axis_is_z ? (double)rad.y : (double)rad.x;
-        const double slack = 1e-9 * (sqrt(d2) + 1.0);
-        if (dax - rr - slack > S.r_out) return 0;
-        if (dax + rr + slack < S.r_in) return 1;
-        return 2;
-    }
-    // plane: body-frame y of the centre
-    DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-    const double yl = world2local(q, D3{S.pos[0], S.pos[1], S.pos[2]}, cc).y;
-    const double m = (double)rad.x + 1e-11 * (sqrt(d2) + 1.0);
-    if (yl > m) return 0;
-    if (yl < -m) return 1;
-    return 2;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2  interact: parameters shared by the classify / heavy / accumulate kernels
-// ------------------------------------------------------------------------------------------------
-struct InteractParams {
-    DevMesh m;
-    const DevSolid *solids;
-    const DevShape *shapes;
-    int n_solids;
-    BinGrid grid;
-    const int *bin_off;
-    const int *bin_list;
-    const int *global_list;
-    const double *U;
-    double dtINV, rhof;
-    double *As, *Fs, *Ts, *Ct;
-    double *force_torque; // [6*n_solids], zeroed
-    unsigned *pair_counts; // [3*n_solids], zeroed
-    int *slots;            // [n_cells*K]: (solid<<2 | type) of every member pair of the cell, -1 terminated
-    double *vols;          // [n_cells*K]: solid volume of the pair's cell (boundary types)
-    unsigned char *n_item; // [n_cells]: slots in use after k_classify
-    int2 *heavy;           // queue of (cell, slot) needing exact evaluation
-    unsigned long long *heavy_count;
-    long long heavy_cap;
-    int n_global;
-    int K;
-    const unsigned char *excluded; // replay mode: [n_cells*K] 1 = pair is outside the seed's component
-    StepStatus *status;
-};
-
-#define TPB 128
-
-// warp-level aggregation of one member pair per lane: lanes with the same solid are reduced with a
-// butterfly and the group leader issues the 6 fp64 + 1 counter reductions.
-__device__ __forceinline__ void warp_accumulate(bool have, int s, int type, const double v[6], double *force_torque,
-                                                unsigned *pair_counts) {
-    const unsigned FULL = 0xffffffffu;
-    unsigned pending = __ballot_sync(FULL, have);
-    const int lane = threadIdx.x & 31;
-    while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const int s0 = __shfl_sync(FULL, s, leader);
-        const bool mine = have && (s == s0);
-        const unsigned grp = __ballot_sync(FULL, mine);
-        double w[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) w[k] = mine ? v[k] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) w[k] += __shfl_xor_sync(FULL, w[k], o);
-        }
-        const unsigned c1 = __popc(__ballot_sync(FULL, mine && type == 1));
-        const unsigned c2 = __popc(__ballot_sync(FULL, mine && type == 2));
-        const unsigned c3 = __popc(__ballot_sync(FULL, mine && type == 3));
-        if (lane == leader) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) atomicAdd(force_torque + 6 * (long long)s0 + k, w[k]);
-            if (c1) atomicAdd(pair_counts + 3 * (long long)s0 + 0, c1);
-            if (c2) atomicAdd(pair_counts + 3 * (long long)s0 + 1, c2);
-            if (c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
-        }
-        pending &= ~grp;
-    }
-}
-
-// Exact evaluation of one (cell, solid) item: number of vertices inside, cell type, solid volume.
-// General polyhedra: cell-local arrays in local memory, CSR connectivity.
-__device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out) {
-    const DevMesh &m = P.m;
-    const DevSolid &S = P.solids[s];
-    const DevShape &sh = P.shapes[S.shape];
-    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-    int vid[MAX_CELL_VERTS];
-    D3 pts[MAX_CELL_VERTS];
-    double phi[MAX_CELL_VERTS];
-    const int pb = __ldg(m.cp_off + c);
-    int nv = __ldg(m.cp_off + c + 1) - pb;
-    if (nv > MAX_CELL_VERTS) { nv = MAX_CELL_VERTS; P.status->bad_cell = 1; }
-    int n_in = 0;
-    for (int k = 0; k < nv; ++k) {
-        vid[k] = __ldg(m.cp + pb + k);
-        pts[k] = ld3(m.points, vid[k]);
-        double ph;
-        n_in += shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph) ? 1 : 0;
-        phi[k] = ph;
-    }
-    type_out = 0;
-    vol_out = 0.0;
-    if (n_in == 0) return;
-    if (n_in == nv) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
-    double dummy;
-    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
-    vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
-}
-
-// Hexahedral fast path: fixed 8/6/4 strides, per-cell face->vertex-slot nibbles precomputed at upload,
-// vertex coordinates and phi staged in transposed shared memory (column = executing thread) so that the
-// data-dependent slot indexing is bank-conflict free.
-__device__ __forceinline__ void heavy_eval_hex(const InteractParams &P, int c, int s, int col, double *s_px, double *s_py,
-                                               double *s_pz, double *s_phi, int &type_out, double &vol_out) {
-    const DevMesh &m = P.m;
-    const DevSolid &S = P.solids[s];
-    const DevShape &sh = P.shapes[S.shape];
-    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-    const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
-    const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
-    const int vid[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-    int n_in = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const D3 p = ld3(m.points, vid[k]);
-        double ph;
-        n_in += shape_eval<true>(sh.s, world2local(q, t, p), ph) ? 1 : 0;
-        s_px[k * TPB + col] = p.x;
-        s_py[k * TPB + col] = p.y;
-        s_pz[k * TPB + col] = p.z;
-        s_phi[k * TPB + col] = ph;
-    }
-    type_out = 0;
-    vol_out = 0.0;
-    if (n_in == 0) return;
-    if (n_in == 8) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
-    double dummy;
-    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
-
-    auto PT = [&](int l) { return D3{s_px[l * TPB + col], s_py[l * TPB + col], s_pz[l * TPB + col]}; };
-    auto PH = [&](int l) { return s_phi[l * TPB + col]; };
-    // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
-    D3 apex;
-    {
-        const D3 A = PT(0);
-        const double phiA = PH(0);
-        D3 B = {0.0, 0.0, 0.0};
-        double phiB = 0.0;
-        for (int i = 1; i < 8; ++i) {
-            B = PT(i);
-            phiB = PH(i);
-            if (phiA * phiB <= 0) break;
-        }
-        apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
-        if (m.two_d) apex.z = 0.0;
-    }
-    const unsigned tw0 = __ldg(m.hex_topo + 3 * (long long)c), tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1),
-                   tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
-    const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
-    const int2 f01 = __ldg(cf2), f23 = __ldg(cf2 + 1), f45 = __ldg(cf2 + 2);
-    double volume = 0.0;
-#pragma unroll
-    for (int f = 0; f < 6; ++f) {
-        const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
-        const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
-        const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
-        const int l[4] = {(int)(nib & 0xf), (int)((nib >> 4) & 0xf), (int)((nib >> 8) & 0xf), (int)((nib >> 12) & 0xf)};
-        const double ph[4] = {PH(l[0]), PH(l[1]), PH(l[2]), PH(l[3])};
-        const int npos = (ph[0] > 0) + (ph[1] > 0) + (ph[2] > 0) + (ph[3] > 0);
-        if (npos == 4) continue;                                                // eps_f = 0: adds +0.0 (:107-108)
-        double eps_f = 1.0;                                                     // all phi <= 0 (:109-110)
-        if (npos != 0) {
-            const D3 A = PT(l[0]);                                              // calcFaceArea (:74-96)
-            D3 B = PT(l[1]);
-            double phiB = ph[1];
-            if (!(ph[0] * ph[1] <= 0)) {
-                B = PT(l[2]);
-                phiB = ph[2];
-                if (!(ph[0] * ph[2] <= 0)) { B = PT(l[3]); phiB = ph[3]; }
-            }
-            const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - B);
-            double area = 0.0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
-                if (lf != 0.0) {                                                // a zero fraction adds +0.0
-                    const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
-                    area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;
-                }
-            }
-            eps_f = area / __ldg(m.magSf + face);
-        }
-        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - ld3(m.Cf, face), ld3(m.Sf, face)));
-    }
-    vol_out = volume;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2a  k_classify (thread per cell): walk the cell's candidate solids in ascending id; every candidate that
-//      may be a member becomes a slot of the cell (certain ALL_INSIDE -> final; otherwise "heavy": appended
-//      to a global queue for exact evaluation).
-// K2b  k_heavy (thread per heavy item, persistent grid): exact vertex predicates + SDF, cell type,
-//      apex/pyramid volume.  Dense: no barriers, no idle lanes waiting on light cells.
-// K2c  k_accumulate (thread per cell): consume the cell's slots in ascending solid order — As/Fs/Ts/Ct
-//      accumulation exactly in the reference's += order, every field written once and coalesced, per-solid
-//      force/torque warp-aggregated before the atomics.
-// ------------------------------------------------------------------------------------------------
-template <bool HEX>
-__global__ void __launch_bounds__(TPB) k_heavy(InteractParams P) {
-    __shared__ double s_px[HEX ? 8 * TPB : 1], s_py[HEX ? 8 * TPB : 1], s_pz[HEX ? 8 * TPB : 1], s_phi[HEX ? 8 * TPB : 1];
-    const int tid = threadIdx.x;
-    const long long n = min((long long)*P.heavy_count, (long long)P.heavy_cap);
-    for (long long k = (long long)blockIdx.x * TPB + tid; k < n; k += (long long)gridDim.x * TPB) {
-        const int2 it = __ldg(P.heavy + k);           // (cell, slot index)
-        const int c = it.x;
-        const long long si = (long long)c * P.K + it.y;
-        const int s = P.slots[si] >> 2;
-        int type;
-        double v;
-        if (HEX) heavy_eval_hex(P, c, s, tid, s_px, s_py, s_pz, s_phi, type, v);
-        else heavy_eval_general(P, c, s, type, v);
-        P.slots[si] = (s << 2) | type;                // type 0: no vertex inside -> not a member
-        P.vols[si] = v;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_classify(InteractParams P) {
-    const DevMesh &m = P.m;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = c < m.n_cells;
-    int n_item = 0, n_heavy = 0;
-    unsigned heavy_mask = 0;
-    if (live) {
-        const D3 cc = ld3(m.cc, c);
-        const float2 rad = m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c);
-        const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] +
-                      bin_coord(P.grid, cc.x, 0);
-        int bi = __ldg(P.bin_off + b);
-        const int be = __ldg(P.bin_off + b + 1);
-        int gi = 0;
-        const int ge = P.status->n_global;
-        while (bi < be || gi < ge) {
-            // merge the bin list and the global list in ascending solid id
-            int s;
-            const int sb = (bi < be) ? __ldg(P.bin_list + bi) : 0x7fffffff;
-            const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
-            if (sb <= sg) { s = sb; ++bi; if (sb == sg) ++gi; }
-            else { s = sg; ++gi; }
-            const int qc = quick_class(P.solids[s], cc, rad);
-            if (qc == 0) continue;
-            if (n_item < P.K) {
-                P.slots[(long long)c * P.K + n_item] = (s << 2) | qc;   // 1 = certain ALL_INSIDE, 2 = heavy (pending)
-                if (qc == 2) { heavy_mask |= 1u << n_item; ++n_heavy; }
-                ++n_item;
-            } else P.status->slot_overflow = 1;
-        }
-        P.n_item[c] = (unsigned char)n_item;
-    }
-    // warp-aggregated append of the heavy items to the global queue
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    int incl = n_heavy;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (total == 0) return;
-    unsigned long long base = 0;
-    if (lane == 31) base = atomicAdd(P.heavy_count, (unsigned long long)total);
-    base = __shfl_sync(FULL, base, 31);
-    long long pos = (long long)base + incl - n_heavy;
-    while (heavy_mask) {
-        const int j = __ffs(heavy_mask) - 1;
-        heavy_mask &= heavy_mask - 1;
-        if (pos < P.heavy_cap) P.heavy[pos] = make_int2(c, j);
-        ++pos;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_accumulate(InteractParams P) {
-    const DevMesh &m = P.m;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = c < m.n_cells;
-    const int n = live ? (int)P.n_item[c] : 0;
-    const unsigned FULL = 0xffffffffu;
-    int nmax = n;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-
-    double as = 0.0, ts = 0.0, ct = 0.0;
-    D3 fs = {0.0, 0.0, 0.0};
-    if (nmax > 0) {
-        D3 cc = {0, 0, 0}, uf = {0, 0, 0};
-        double vol = 1.0;
-        if (n > 0) {
-            cc = ld3(m.cc, c);
-            uf = ld3(P.U, c);
-            vol = __ldg(m.V + c);
-        }
-        int nslot = 0;
-        bool ended = false;
-        for (int j = 0; j < nmax; ++j) {
-            bool have = false;
-            int s = -1, type = 0;
-            double contrib[6] = {0, 0, 0, 0, 0, 0};
-            if (j < n && !ended) {
-                const long long si = (long long)c * P.K + j;
-                const int e = P.slots[si];
-                if (e < 0) ended = true;                                   // terminator of an earlier (compacting) pass
-                else if ((e & 3) != 0) {
-                    type = e & 3;
-                    s = e >> 2;
-                    const double v = (type == SDFIBM_CELL_ALL_INSIDE) ? 0.0 : P.vols[si];
-                    const long long so = (long long)c * P.K + nslot;       // compact the members to the front
-                    if (nslot != j) { P.slots[so] = e; P.vols[so] = v; }
-                    const bool skip = P.excluded && P.excluded[so];        // replay: outside the seed's component
-                    ++nslot;
-                    if (!skip) {
-                        const DevSolid &S = P.solids[s];
-                        const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-                        const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol;   // solidcloud.cpp:408-410
-                        // solidcloud.cpp:384-390,411-421
-                        const D3 om = {S.omega[0], S.omega[1], S.omega[2]};
-                        const D3 us = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(om, cc - t);
-                        const D3 f_ = alpha * (uf - us);
-                        const D3 t_ = cross3(cc - t, f_);
-                        const D3 fo = f_ * vol * P.dtINV;
-                        const D3 to = t_ * vol * P.dtINV;
-                        contrib[0] = fo.x; contrib[1] = fo.y; contrib[2] = fo.z;
-                        contrib[3] = to.x; contrib[4] = to.y; contrib[5] = to.z;
-                        as += alpha;
-                        fs = fs + f_ * P.dtINV;
-                        ts += alpha;
-                        ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;   // :376-382, last writer wins
-                        have = true;
-                    }
-                }
-            }
-            if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
-        }
-        if (n > 0 && nslot < P.K) P.slots[(long long)c * P.K + nslot] = -1;
-        if (live && nslot == 0) ct = 0.0;
-        if (live && nslot > 0 && ct == 0.0) ct = -1.0;   // only excluded pairs (replay): slots stay valid for the list extraction
-    }
-    if (live) {
-        P.As[c] = (as < 1.0) ? as : 1.0;                                           // checkAlpha, :564-570 (std::min(As,1))
-        P.Fs[3 * (long long)c] = fs.x;
-        P.Fs[3 * (long long)c + 1] = fs.y;
-        P.Fs[3 * (long long)c + 2] = fs.z;
-        P.Ts[c] = ts;
-        P.Ct[c] = ct;
-    }
-}
-
-
-// replay mode leaves Ct = -1 on cells whose only pairs were excluded; they are untouched cells.
-__global__ void k_fix_ct(double *Ct, int n) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n && Ct[c] < 0.0) Ct[c] = 0.0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3  connectivity certificate: a member pair is a "root" when no face neighbour that is a member of
-// the same solid has a smaller (distance-to-centre, cell id) key.  Exactly one root  =>  the solid's
-// vertex-inside cell set is face connected  =>  it equals the reference's flood fill from any seed.
-// ------------------------------------------------------------------------------------------------
-struct ConnParams {
-    DevMesh m;
-    const DevSolid *solids;
-    const double *Ct;
-    const int *slots;
-    int K;
-    int *root_count; // [n_solids] zeroed
-};
-
-__device__ __forceinline__ bool key_less(double ka, int ca, double kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
-
-__global__ void k_connectivity(ConnParams P) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.m.n_cells) return;
-    if (P.Ct[c] == 0.0) return;
-    const D3 cc = ld3(P.m.cc, c);
-    const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
-    for (int j = 0; j < P.K; ++j) {
-        const int e = P.slots[(long long)c * P.K + j];
-        if (e < 0) break;
-        const int s = e >> 2;
-        const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
-        const double kc = magSqr3(cc - x);
-        bool has_parent = false;
-        for (int k = nb0; k < nb1 && !has_parent; ++k) {
-            const int nb = __ldg(P.m.nb + k);
-            if (P.Ct[nb] == 0.0) continue;
-            for (int jj = 0; jj < P.K; ++jj) {
-                const int e2 = P.slots[(long long)nb * P.K + jj];
-                if (e2 < 0) break;
-                if ((e2 >> 2) == s) {
-                    const double kn = magSqr3(ld3(P.m.cc, nb) - x);
-                    if (key_less(kn, nb, kc, c)) has_parent = true;
-                    break;
-                }
-            }
-        }
-        if (!has_parent) atomicAdd(P.root_count + s, 1);
-    }
-}
-
-__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status) {
-    unsigned long long c0 = 0, c1 = 0, c2 = 0;
-    int nf = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_solids; s += gridDim.x * blockDim.x) {
-        c0 += pair_counts[3 * s];
-        c1 += pair_counts[3 * s + 1];
-        c2 += pair_counts[3 * s + 2];
-        nf += root_count[s] > 1;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-        nf += __shfl_xor_sync(0xffffffffu, nf, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (c0) atomicAdd(&status->counts[0], c0);
-        if (c1) atomicAdd(&status->counts[1], c1);
-        if (c2) atomicAdd(&status->counts[2], c2);
-        if (nf) atomicAdd(&status->n_flagged, nf);
-    }
-}
-
-// rhof scaling of the per-solid sums (solidcloud.cpp:424-425)
-__global__ void k_scale_ft(double *ft, int n, double rhof) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ft[i] = ft[i] * rhof;
-}
-
-// ------------------------------------------------------------------------------------------------
-// exact flood-fill replay for solids that failed the certificate (rare path, all on the GPU)
-// ------------------------------------------------------------------------------------------------
-struct ReplayParams {
-    DevMesh m;
-    const DevSolid *solids;
-    const double *Ct;
-    const int *slots;
-    int K;
-    const int *root_count;
-    int *labels;                    // [n_cells*K] component label (min cell id) of flagged pairs
-    int *changed;
-    unsigned long long *seed_key;   // [n_solids] min dist^2 bits over candidate cells
-    int *seed_cell;                 // [n_solids]
-    int *min_label;                 // [n_solids]
-    int *chosen;                    // [n_solids]
-    unsigned char *excluded;        // [n_cells*K]
-    BinGrid grid;
-    const int *bin_off, *bin_list, *global_list;
-    int n_global, n_solids;
-};
-
-__global__ void k_replay_init(ReplayParams P) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.m.n_cells) return;
-    for (int j = 0; j < P.K; ++j) { P.labels[(long long)c * P.K + j] = -1; P.excluded[(long long)c * P.K + j] = 0; }
-    if (P.Ct[c] == 0.0) return;
-    for (int j = 0; j < P.K; ++j) {
-        const int e = P.slots[(long long)c * P.K + j];
-        if (e < 0) break;
-        if (P.root_count[e >> 2] > 1) P.labels[(long long)c * P.K + j] = c;
-    }
-}
-
-__global__ void k_replay_propagate(ReplayParams P) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.m.n_cells || P.Ct[c] == 0.0) return;
-    const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
-    for (int j = 0; j < P.K; ++j) {
-        const int e = P.slots[(long long)c * P.K + j];
-        if (e < 0) break;
-        int lab = P.labels[(long long)c * P.K + j];
-        if (lab < 0) continue;
-        const int s = e >> 2;
-        int best = lab;
-        for (int k = nb0; k < nb1; ++k) {
-            const int nb = __ldg(P.m.nb + k);
-            if (P.Ct[nb] == 0.0) continue;
-            for (int jj = 0; jj < P.K; ++jj) {
-                const int e2 = P.slots[(long long)nb * P.K + jj];
-                if (e2 < 0) break;
-                if ((e2 >> 2) == s) {
-                    const int l2 = ((volatile int *)P.labels)[(long long)nb * P.K + jj];
-                    if (l2 >= 0 && l2 < best) best = l2;
-                    break;
-                }
-            }
-        }
-        if (best < lab) { P.labels[(long long)c * P.K + j] = best; *P.changed = 1; }
-    }
-}
-
-// nearest cell centre to each flagged solid's centre, restricted to the cells that list the solid as
-// a candidate (sufficient: any member cell is within the binned bounding volume).
-__global__ void k_replay_seed(ReplayParams P, int pass) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.m.n_cells) return;
-    const D3 cc = ld3(P.m.cc, c);
-    const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] + bin_coord(P.grid, cc.x, 0);
-    const int b0 = P.bin_off[b], b1 = P.bin_off[b + 1];
-    for (int t = 0; t < (b1 - b0) + P.n_global; ++t) {
-        const int s = (t < b1 - b0) ? P.bin_list[b0 + t] : P.global_list[t - (b1 - b0)];
-        if (P.root_count[s] <= 1) continue;
-        const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
-        const unsigned long long key = (unsigned long long)__double_as_longlong(magSqr3(cc - x));
-        if (pass == 0) atomicMin(P.seed_key + s, key);
-        else if (key == P.seed_key[s]) atomicMin(P.seed_cell + s, c);
-    }
-    if (pass == 1 && P.Ct[c] != 0.0) {
-        for (int j = 0; j < P.K; ++j) {
-            const int e = P.slots[(long long)c * P.K + j];
-            if (e < 0) break;
-            const int lab = P.labels[(long long)c * P.K + j];
-            if (lab >= 0) atomicMin(P.min_label + (e >> 2), lab);
-        }
-    }
-}
-
-__global__ void k_replay_choose(ReplayParams P) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.n_solids) return;
-    if (P.root_count[s] <= 1) { P.chosen[s] = -1; return; }
-    int chosen = P.min_label[s]; // component of the first member cell in index order (cellenumerator.cpp:52-63)
-    const int g = P.seed_cell[s];
-    if (g >= 0 && g < P.m.n_cells && P.Ct[g] != 0.0) {
-        for (int j = 0; j < P.K; ++j) {
-            const int e = P.slots[(long long)g * P.K + j];
-            if (e < 0) break;
-            if ((e >> 2) == s) { chosen = P.labels[(long long)g * P.K + j]; break; } // nearest cell is a member: it is the seed
-        }
-    }
-    P.chosen[s] = chosen;
-}
-
-__global__ void k_replay_mark(ReplayParams P) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.m.n_cells || P.Ct[c] == 0.0) return;
-    for (int j = 0; j < P.K; ++j) {
-        const int e = P.slots[(long long)c * P.K + j];
-        if (e < 0) break;
-        const int lab = P.labels[(long long)c * P.K + j];
-        if (lab >= 0 && lab != P.chosen[e >> 2]) P.excluded[(long long)c * P.K + j] = 1;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4  fixInternal (solidcloud.cpp:288-301)
-// ------------------------------------------------------------------------------------------------
-__global__ void k_fix_internal(DevMesh m, const sdfibm_solid_t *solids, int n_solids, const double *Ct, double *U) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.n_cells) return;
-    const double ct = Ct[c];
-    if (ct >= 4) {
-        const int id = (int)(ct - 4);
-        if (id < n_solids) {
-            const sdfibm_solid_t &S = solids[id];
-            const D3 x = {S.pos[0], S.pos[1], S.pos[2]};
-            const D3 u = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(D3{S.omega[0], S.omega[1], S.omega[2]}, ld3(m.cc, c) - x);
-            U[3 * (long long)c] = u.x;
-            U[3 * (long long)c + 1] = u.y;
-            U[3 * (long long)c + 2] = u.z;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// candidate list extraction (parity output, off the timed path): pairs in cell order, then a stable
-// radix sort by (solid, type) gives ascending cell ids inside every segment (std::set order).
-// ------------------------------------------------------------------------------------------------
-__global__ void k_list_count(const double *Ct, const int *slots, const unsigned char *excluded, int K, int n_cells, int *cnt) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
-    int n = 0;
-    if (Ct[c] != 0.0)
-        for (int j = 0; j < K; ++j) {
-            if (slots[(long long)c * K + j] < 0) break;
-            if (!(excluded && excluded[(long long)c * K + j])) ++n;
-        }
-    cnt[c] = n;
-}
-__global__ void k_list_emit(const double *Ct, const int *slots, const unsigned char *excluded, int K, int n_cells,
-                            const int *off, unsigned *keys, int *vals) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells || Ct[c] == 0.0) return;
-    int o = off[c];
-    for (int j = 0; j < K; ++j) {
-        const int e = slots[(long long)c * K + j];
-        if (e < 0) break;
-        if (excluded && excluded[(long long)c * K + j]) continue;
-        keys[o] = (unsigned)(3 * (e >> 2) + ((e & 3) - 1));
-        vals[o] = c;
-        ++o;
-    }
-}
+#include "interact_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // collision step (solidcloud.cpp:477-519, libcollision/): centres hashed on the UGrid, pairs
@@ -1122,7 +433,7 @@ struct DevBuf {
 struct sdfibm_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    int K = 4;
+    int K = 3;
     // mesh
     bool has_mesh = false;
     DevMesh dm{};
@@ -1140,8 +451,8 @@ struct sdfibm_context {
     DevBuf<sdfibm_solid_t> solids_in;
     DevBuf<DevSolid> solids;
     DevBuf<int> bin_count, bin_off, bin_cursor, bin_list, global_list, root_count, slots;
-    DevBuf<double> vols;
-    DevBuf<unsigned char> n_item;
+    DevBuf<double> heavy_vol;
+    DevBuf<unsigned char> n_item, heavy_type;
     DevBuf<int2> heavy;
     DevBuf<unsigned> pair_counts;
     DevBuf<double> ft_internal;
@@ -1247,7 +558,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cell_rad.release(); ctx->magSf.release(); ctx->hex_topo.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
     ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
-    ctx->vols.release(); ctx->n_item.release(); ctx->heavy.release();
+    ctx->heavy_vol.release(); ctx->heavy_type.release(); ctx->n_item.release(); ctx->heavy.release();
     ctx->ft_internal.release(); ctx->status.release(); ctx->scan_tmp.release();
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
@@ -1303,10 +614,14 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     if ((rc = upload(ctx->nb_off, m->cell_cells_off, nC + 1, st))) return rc;
     if ((rc = upload(ctx->nb, m->cell_cells, (size_t)m->cell_cells_off[nC], st))) return rc;
     CUDA_TRY(ctx->cell_rad.ensure(nC));
-    CUDA_TRY(ctx->slots.ensure(nC * ctx->K));
-    CUDA_TRY(ctx->vols.ensure(nC * ctx->K));
+    CUDA_TRY(ctx->slots.ensure(nC * (ctx->K + 1)));
     CUDA_TRY(ctx->n_item.ensure(nC));
-    CUDA_TRY(ctx->heavy.ensure(std::max<size_t>(1 << 20, nC / 2)));
+    {
+        const size_t cap = std::max<size_t>(1 << 20, nC / 2);
+        CUDA_TRY(ctx->heavy.ensure(cap));
+        CUDA_TRY(ctx->heavy_vol.ensure(cap));
+        CUDA_TRY(ctx->heavy_type.ensure(cap));
+    }
     DevMesh &d = ctx->dm;
     d.n_cells = m->n_cells; d.n_points = m->n_points; d.n_faces = m->n_faces;
     d.points = ctx->points.p; d.cc = ctx->cc.p; d.V = ctx->V.p; d.Cf = ctx->Cf.p; d.Sf = ctx->Sf.p;
@@ -1456,7 +771,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         CUDA_TRY(ctx->chosen.ensure(n_solids));
         CUDA_TRY(ctx->changed.ensure(1));
         ReplayParams R;
-        R.m = ctx->dm; R.solids = ctx->solids.p; R.Ct = dCt; R.slots = ctx->slots.p; R.K = ctx->K;
+        R.m = ctx->dm; R.solids = ctx->solids.p; R.n_item = ctx->n_item.p; R.slots = ctx->slots.p; R.K = ctx->K;
         R.root_count = ctx->root_count.p; R.labels = ctx->labels.p; R.changed = ctx->changed.p;
         R.seed_key = ctx->seed_key.p; R.seed_cell = ctx->seed_cell.p; R.min_label = ctx->min_label.p;
         R.chosen = ctx->chosen.p; R.excluded = ctx->excluded.p; R.grid = ctx->grid; R.bin_off = ctx->bin_off.p;
@@ -1550,14 +865,14 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.global_list = ctx->global_list.p; I.U = dU;
         I.dtINV = 1.0 / dt; I.rhof = rhof; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
         I.pair_counts = ctx->pair_counts.p; I.slots = ctx->slots.p; I.K = ctx->K;
-        I.vols = ctx->vols.p; I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p;
-        I.heavy_count = &ctx->status.p->heavy_total; I.heavy_cap = (long long)ctx->heavy.n; I.n_global = 0;
+        I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_vol = ctx->heavy_vol.p; I.heavy_type = ctx->heavy_type.p;
+        I.heavy_count = &ctx->status.p->heavy_total; I.heavy_cap = (long long)ctx->heavy.n; I.final_slots = replay ? 1 : 0;
         I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status.p;
         CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
         if (!replay) {
             k_classify<<<grid_for(nC, 256), 256, 0, st>>>(I);
             CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-            const int hgrid = ctx->n_sm * 4;
+            const int hgrid = ctx->n_sm * HEAVY_CTAS_PER_SM;
             if (ctx->dm.is_hex) k_heavy<true><<<hgrid, TPB, 0, st>>>(I);
             else k_heavy<false><<<hgrid, TPB, 0, st>>>(I);
             ctx->launches += 2;
@@ -1568,10 +883,9 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         k_accumulate<<<grid_for(nC, 256), 256, 0, st>>>(I);
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         ++ctx->launches;
-        if (replay) { k_fix_ct<<<grid_for(nC, 256), 256, 0, st>>>(dCt, nC); ++ctx->launches; }
-        else {
+        if (!replay) {
             ConnParams C;
-            C.m = ctx->dm; C.solids = ctx->solids.p; C.Ct = dCt; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count.p;
+            C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count.p;
             k_connectivity<<<grid_for(nC, 256), 256, 0, st>>>(C);
             ++ctx->launches;
         }
@@ -1599,7 +913,10 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             if (replay) { ctx->last.n_flagged = (int)ctx->flagged_last; ctx->last.heavy_total = prev.heavy_total; }
         }
         if (!replay && ctx->last.heavy_total > (unsigned long long)ctx->heavy.n && attempt == 0) {
-            CUDA_TRY(ctx->heavy.ensure((size_t)(ctx->last.heavy_total + ctx->last.heavy_total / 4 + 1024)));
+            const size_t cap = (size_t)(ctx->last.heavy_total + ctx->last.heavy_total / 4 + 1024);
+            CUDA_TRY(ctx->heavy.ensure(cap));
+            CUDA_TRY(ctx->heavy_vol.ensure(cap));
+            CUDA_TRY(ctx->heavy_type.ensure(cap));
             continue;
         }
         if (ctx->last.bin_overflow && !replay && attempt == 0) {
@@ -1721,12 +1038,12 @@ int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells
     CUDA_TRY(off.ensure((size_t)nC + 1));
     CUDA_TRY(keys.ensure(total)); CUDA_TRY(keys2.ensure(total)); CUDA_TRY(vals.ensure(total)); CUDA_TRY(vals2.ensure(total));
     CUDA_TRY(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)nC + 1), st));
-    k_list_count<<<grid_for(nC, 256), 256, 0, st>>>(ctx->last_Ct, ctx->slots.p, excl, ctx->K, nC, cnt.p);
+    k_list_count<<<grid_for(nC, 256), 256, 0, st>>>(ctx->n_item.p, ctx->slots.p, excl, ctx->K, nC, cnt.p);
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, nC + 1, st);
     CUDA_TRY(tmp.ensure(tb));
     cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, nC + 1, st);
-    k_list_emit<<<grid_for(nC, 256), 256, 0, st>>>(ctx->last_Ct, ctx->slots.p, excl, ctx->K, nC, off.p, keys.p, vals.p);
+    k_list_emit<<<grid_for(nC, 256), 256, 0, st>>>(ctx->n_item.p, ctx->slots.p, excl, ctx->K, nC, off.p, keys.p, vals.p);
     size_t sb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sb, keys.p, keys2.p, vals.p, vals2.p, (int)total, 0, 32, st);
     CUDA_TRY(tmp.ensure(sb));
