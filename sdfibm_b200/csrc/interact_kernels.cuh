@@ -245,105 +245,190 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
     vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
 }
 
-// Hexahedral fast path: fixed 8/6/4 strides, per-cell face->vertex-slot nibbles precomputed at upload,
-// vertex coordinates and phi staged in transposed shared memory (column = executing thread) so that the
-// data-dependent slot indexing is bank-conflict free.
-__device__ __forceinline__ void heavy_eval_hex(const InteractParams &P, int c, int s, int col, double *s_px, double *s_py,
-                                               double *s_pz, double *s_phi, int &type_out, double &vol_out) {
-    const DevMesh &m = P.m;
-    const DevSolid &S = P.solids[s];
-    const DevShape &sh = P.shapes[S.shape];
-    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-    const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
-    const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
-    const int vid[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-    int n_in = 0;
-#pragma unroll 2
-    for (int k = 0; k < 8; ++k) {
-        const D3 p = ld3(m.points, vid[k]);
-        double ph;
-        n_in += shape_eval<true>(sh.s, world2local(q, t, p), ph) ? 1 : 0;
-        s_px[k * TPB + col] = p.x;
-        s_py[k * TPB + col] = p.y;
-        s_pz[k * TPB + col] = p.z;
-        s_phi[k * TPB + col] = ph;
-    }
-    type_out = 0;
-    vol_out = 0.0;
-    if (n_in == 0) return;
-    if (n_in == 8) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
-    double dummy;
-    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+// Hexahedral fast path, warp-cooperative.  Lane = one (cell, solid) item; consecutive lanes are mostly
+// consecutive cells of one solid along a mesh line, whose "low" vertex quad {0,2,4,6} (cellPoints order)
+// is the previous lane's "high" quad {1,3,5,7}.  Every lane evaluates its own high quad (4 rounds); the low
+// quads are evaluated only for run starts, spread over all lanes in extra rounds.  A vertex shared by two
+// lanes is therefore transformed and evaluated once — the SAME operation sequence either lane would run, so
+// results are bit-identical to the per-cell evaluation.  Coordinates, phi and inside flags are staged in
+// transposed shared memory (column = lane's thread) so that the data-dependent face->slot indexing of the
+// volume phase is bank-conflict free.
+struct HeavySmem {
+    double px[8 * TPB], py[8 * TPB], pz[8 * TPB], phi[8 * TPB];
+    int vid[8 * TPB];
+    unsigned char in[8 * TPB];
+};
 
-    auto PT = [&](int l) { return D3{s_px[l * TPB + col], s_py[l * TPB + col], s_pz[l * TPB + col]}; };
-    auto PH = [&](int l) { return s_phi[l * TPB + col]; };
-    // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
-    D3 apex;
-    {
-        const D3 A = PT(0);
-        const double phiA = PH(0);
-        D3 B = {0.0, 0.0, 0.0};
-        double phiB = 0.0;
-        for (int i = 1; i < 8; ++i) {
-            B = PT(i);
-            phiB = PH(i);
-            if (phiA * phiB <= 0) break;
-        }
-        apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
-        if (m.two_d) apex.z = 0.0;
+__device__ __forceinline__ void eval_vertex_to_smem(HeavySmem &sm, const DevMesh &m, const DevShape &sh, DQ q, D3 t, int v,
+                                                    int slot_a, int col_a, bool dup, int slot_b, int col_b) {
+    const D3 p = ld3(m.points, v);
+    double ph;
+    const bool in = shape_eval<true>(sh.s, world2local(q, t, p), ph);
+    sm.px[slot_a * TPB + col_a] = p.x;
+    sm.py[slot_a * TPB + col_a] = p.y;
+    sm.pz[slot_a * TPB + col_a] = p.z;
+    sm.phi[slot_a * TPB + col_a] = ph;
+    sm.in[slot_a * TPB + col_a] = in ? 1 : 0;
+    if (dup) {
+        sm.px[slot_b * TPB + col_b] = p.x;
+        sm.py[slot_b * TPB + col_b] = p.y;
+        sm.pz[slot_b * TPB + col_b] = p.z;
+        sm.phi[slot_b * TPB + col_b] = ph;
+        sm.in[slot_b * TPB + col_b] = in ? 1 : 0;
     }
-    const unsigned *topo = m.hex_topo + 3 * (long long)c;
-    const int *cfp = m.cf + 6 * (long long)c;
-    double volume = 0.0;
-#pragma unroll 1
-    for (int f = 0; f < 6; ++f) {
-        const unsigned nib = (__ldg(topo + (f >> 1)) >> (16 * (f & 1))) & 0xffffu;
-        const int l[4] = {(int)(nib & 0xf), (int)((nib >> 4) & 0xf), (int)((nib >> 8) & 0xf), (int)((nib >> 12) & 0xf)};
-        const double ph[4] = {PH(l[0]), PH(l[1]), PH(l[2]), PH(l[3])};
-        const int npos = (ph[0] > 0) + (ph[1] > 0) + (ph[2] > 0) + (ph[3] > 0);
-        if (npos == 4) continue;                                                // eps_f = 0: adds +0.0 (:107-108)
-        const int face = __ldg(cfp + f);
-        double eps_f = 1.0;                                                     // all phi <= 0 (:109-110)
-        if (npos != 0) {
-            const D3 A = PT(l[0]);                                              // calcFaceArea (:74-96)
-            D3 B = PT(l[1]);
-            double phiB = ph[1];
-            if (!(ph[0] * ph[1] <= 0)) {
-                B = PT(l[2]);
-                phiB = ph[2];
-                if (!(ph[0] * ph[2] <= 0)) { B = PT(l[3]); phiB = ph[3]; }
-            }
-            const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - B);
-            double area = 0.0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
-                if (lf != 0.0) {                                                // a zero fraction adds +0.0
-                    const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
-                    area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;
-                }
-            }
-            eps_f = area / __ldg(m.magSf + face);
-        }
-        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - ld3(m.Cf, face), ld3(m.Sf, face)));
-    }
-    vol_out = volume;
 }
 
-#define HEAVY_CTAS_PER_SM 6
-template <bool HEX>
-__global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy(InteractParams P) {
-    __shared__ double s_px[HEX ? 8 * TPB : 1], s_py[HEX ? 8 * TPB : 1], s_pz[HEX ? 8 * TPB : 1], s_phi[HEX ? 8 * TPB : 1];
-    const int tid = threadIdx.x;
+#define HEAVY_CTAS_PER_SM 5
+__global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractParams P) {
+    __shared__ HeavySmem sm;
+    const DevMesh &m = P.m;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
-    for (long long k = (long long)blockIdx.x * TPB + tid; k < n; k += (long long)gridDim.x * TPB) {
+    for (long long k0 = (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
+        const long long k = k0 + lane;
+        const bool valid = k < n;
+        int c = -1, s = -1;
+        int vid[8] = {-1, -2, -3, -4, -5, -6, -7, -8};
+        DQ q = {1.0, {0.0, 0.0, 0.0}};
+        D3 t = {0.0, 0.0, 0.0};
+        int shape_idx = 0;
+        unsigned tw0 = 0, tw1 = 0, tw2 = 0;
+        int2 f01 = {0, 0}, f23 = {0, 0}, f45 = {0, 0};
+        if (valid) {
+            const int2 it = __ldg(P.heavy + k);
+            c = it.x;
+            s = it.y;
+            const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
+            const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
+            vid[0] = va.x; vid[1] = va.y; vid[2] = va.z; vid[3] = va.w;
+            vid[4] = vb.x; vid[5] = vb.y; vid[6] = vb.z; vid[7] = vb.w;
+            const DevSolid &S = P.solids[s];
+            q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+            t = {S.pos[0], S.pos[1], S.pos[2]};
+            shape_idx = S.shape;
+            // issued early: consumed by the volume phase
+            tw0 = __ldg(m.hex_topo + 3 * (long long)c);
+            tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1);
+            tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
+            const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
+            f01 = __ldg(cf2); f23 = __ldg(cf2 + 1); f45 = __ldg(cf2 + 2);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm.vid[j * TPB + tid] = vid[j];
+        __syncwarp();
+        // does my low quad coincide with the previous lane's high quad (same solid)?
+        const int ls = __shfl_up_sync(FULL, s, 1);
+        const int l1 = __shfl_up_sync(FULL, vid[1], 1), l3 = __shfl_up_sync(FULL, vid[3], 1);
+        const int l5 = __shfl_up_sync(FULL, vid[5], 1), l7 = __shfl_up_sync(FULL, vid[7], 1);
+        const bool shared_left = valid && lane > 0 && ls == s && l1 == vid[0] && l3 == vid[2] && l5 == vid[4] && l7 == vid[6];
+        const unsigned sharedmask = __ballot_sync(FULL, shared_left);
+        const unsigned startmask = __ballot_sync(FULL, valid) & ~sharedmask;
+        const bool right_shares = lane < 31 && ((sharedmask >> (lane + 1)) & 1u);
+        const DevShape &sh = P.shapes[shape_idx];
+        // rounds 0..3: my own high quad (also the next lane's low quad when it shares)
+        if (valid) {
+#pragma unroll 2
+            for (int v = 0; v < 4; ++v)
+                eval_vertex_to_smem(sm, m, sh, q, t, vid[2 * v + 1], 2 * v + 1, tid, right_shares, 2 * v, tid + 1);
+        }
+        // extra rounds: low quads of the run starts, 4 vertices each, spread over all lanes
+        const int nwork = 4 * __popc(startmask);
+        for (int base = 0; base < nwork; base += 32) {
+            const int u = base + lane;
+            const bool work = u < nwork;
+            const int src = work ? (int)__fns(startmask, 0, (u >> 2) + 1) : 0;
+            if (work) {
+                const int kk = 2 * (u & 3);
+                const int col = wbase + src;
+                const int s_src = __ldg(&P.heavy[k0 + src].y);
+                const DevSolid &S2 = P.solids[s_src];
+                const DQ q2 = {S2.q[0], {S2.q[1], S2.q[2], S2.q[3]}};
+                const D3 t2 = {S2.pos[0], S2.pos[1], S2.pos[2]};
+                eval_vertex_to_smem(sm, m, P.shapes[S2.shape], q2, t2, sm.vid[kk * TPB + col], kk, col, false, 0, 0);
+            }
+        }
+        __syncwarp();
+        if (valid) {
+            int type = 0;
+            double volume = 0.0;
+            int n_in = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) n_in += sm.in[j * TPB + tid];
+            if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
+            else if (n_in != 0) {
+                double dummy;
+                type = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                auto PT = [&](int l) { return D3{sm.px[l * TPB + tid], sm.py[l * TPB + tid], sm.pz[l * TPB + tid]}; };
+                auto PH = [&](int l) { return sm.phi[l * TPB + tid]; };
+                // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
+                D3 apex;
+                {
+                    const D3 A = PT(0);
+                    const double phiA = PH(0);
+                    D3 B = {0.0, 0.0, 0.0};
+                    double phiB = 0.0;
+                    for (int i = 1; i < 8; ++i) {
+                        B = PT(i);
+                        phiB = PH(i);
+                        if (phiA * phiB <= 0) break;
+                    }
+                    apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
+                    if (m.two_d) apex.z = 0.0;
+                }
+#pragma unroll 1
+                for (int f = 0; f < 6; ++f) {
+                    const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
+                    const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
+                    const int l[4] = {(int)(nib & 0xf), (int)((nib >> 4) & 0xf), (int)((nib >> 8) & 0xf), (int)((nib >> 12) & 0xf)};
+                    const double ph[4] = {PH(l[0]), PH(l[1]), PH(l[2]), PH(l[3])};
+                    const int npos = (ph[0] > 0) + (ph[1] > 0) + (ph[2] > 0) + (ph[3] > 0);
+                    if (npos == 4) continue;                                        // eps_f = 0: adds +0.0 (:107-108)
+                    const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
+                    // face record: Cf.xyz, Sf.xyz, |Sf|, pad — four 16-byte loads issued before the area math
+                    const double2 *fr = m.face_rec + 4 * (long long)face;
+                    const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2), r3 = __ldg(fr + 3);
+                    double eps_f = 1.0;                                             // all phi <= 0 (:109-110)
+                    if (npos != 0) {
+                        const D3 A = PT(l[0]);                                      // calcFaceArea (:74-96)
+                        D3 B = PT(l[1]);
+                        double phiB = ph[1];
+                        if (!(ph[0] * ph[1] <= 0)) {
+                            B = PT(l[2]);
+                            phiB = ph[2];
+                            if (!(ph[0] * ph[2] <= 0)) { B = PT(l[3]); phiB = ph[3]; }
+                        }
+                        const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - B);
+                        double area = 0.0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
+                            if (lf != 0.0) {                                        // a zero fraction adds +0.0
+                                const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
+                                area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;
+                            }
+                        }
+                        eps_f = area / r3.x;
+                    }
+                    const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
+                    volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
+                }
+            }
+            P.heavy_type[k] = (unsigned char)type; // 0: no vertex inside -> not a member
+            P.heavy_vol[k] = volume;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
+    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
+    for (long long k = (long long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long long)gridDim.x * TPB) {
         const int2 it = __ldg(P.heavy + k); // (cell, solid)
         int type;
         double v;
-        if (HEX) heavy_eval_hex(P, it.x, it.y, tid, s_px, s_py, s_pz, s_phi, type, v);
-        else heavy_eval_general(P, it.x, it.y, type, v);
-        P.heavy_type[k] = (unsigned char)type; // 0: no vertex inside -> not a member
+        heavy_eval_general(P, it.x, it.y, type, v);
+        P.heavy_type[k] = (unsigned char)type;
         P.heavy_vol[k] = v;
     }
 }

@@ -78,6 +78,7 @@ struct DevMesh {
     const int *cp_off, *cp, *cf_off, *cf, *fp_off, *fp, *nb_off, *nb;
     const float2 *cell_rad; // (3-D radius, xy radius) of the vertex cloud about the centre, rounded up
     const double *magSf;    // |Sf| per face (same expression as Foam::mag, evaluated once at upload)
+    const double2 *face_rec; // hex path: 64-byte record per face: Cf.xyz, Sf.xyz, |Sf|, pad
     const unsigned *hex_topo; // hex meshes: 3 words per cell, 4-bit cell-local vertex slot of every face vertex
     float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
     int rad_uniform;
@@ -116,9 +117,19 @@ __device__ __forceinline__ int bin_coord(const BinGrid &g, double x, int d) {
 // ------------------------------------------------------------------------------------------------
 // K0  per-cell vertex-cloud radii (once per mesh)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_face_mag(const double *Sf, int n_faces, double *magSf) {
+__global__ void k_face_mag(const double *Cf, const double *Sf, int n_faces, double *magSf, double2 *face_rec) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < n_faces) magSf[f] = mag3(ld3(Sf, f));
+    if (f >= n_faces) return;
+    const D3 S = ld3(Sf, f);
+    const double mg = mag3(S);
+    magSf[f] = mg;
+    if (face_rec) {
+        const D3 C = ld3(Cf, f);
+        face_rec[4 * (long long)f] = make_double2(C.x, C.y);
+        face_rec[4 * (long long)f + 1] = make_double2(C.z, S.x);
+        face_rec[4 * (long long)f + 2] = make_double2(S.y, S.z);
+        face_rec[4 * (long long)f + 3] = make_double2(mg, 0.0);
+    }
 }
 
 // hex meshes: for face k (cells() order) of cell c and its j-th vertex (faces() order), the position of that
@@ -441,6 +452,7 @@ struct sdfibm_context {
     DevBuf<int> cp_off, cp, cf_off, cf, fp_off, fp, nb_off, nb;
     DevBuf<float2> cell_rad;
     DevBuf<double> magSf;
+    DevBuf<double2> face_rec;
     DevBuf<unsigned> hex_topo;
     double bmin[3], bmax[3];
     float rad3_max = 0.f, radxy_max = 0.f;
@@ -555,7 +567,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->points.release(); ctx->cc.release(); ctx->V.release(); ctx->Cf.release(); ctx->Sf.release();
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
-    ctx->cell_rad.release(); ctx->magSf.release(); ctx->hex_topo.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
     ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
     ctx->heavy_vol.release(); ctx->heavy_type.release(); ctx->n_item.release(); ctx->heavy.release();
@@ -639,7 +651,12 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     CUDA_TRY(ctx->magSf.ensure(nF));
     d.magSf = ctx->magSf.p;
     d.hex_topo = nullptr;
-    k_face_mag<<<grid_for(nF, 256), 256, 0, st>>>(d.Sf, (int)nF, ctx->magSf.p);
+    d.face_rec = nullptr;
+    if (is_hex) {
+        CUDA_TRY(ctx->face_rec.ensure(4 * nF));
+        d.face_rec = ctx->face_rec.p;
+    }
+    k_face_mag<<<grid_for(nF, 256), 256, 0, st>>>(d.Cf, d.Sf, (int)nF, ctx->magSf.p, ctx->face_rec.p);
     for (int k = 0; k < 3; ++k) { ctx->bmin[k] = m->bounds_min[k]; ctx->bmax[k] = m->bounds_max[k]; }
     // per-cell radii + maxima
     DevBuf<int> bad;
@@ -873,8 +890,8 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             k_classify<<<grid_for(nC, 256), 256, 0, st>>>(I);
             CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
             const int hgrid = ctx->n_sm * HEAVY_CTAS_PER_SM;
-            if (ctx->dm.is_hex) k_heavy<true><<<hgrid, TPB, 0, st>>>(I);
-            else k_heavy<false><<<hgrid, TPB, 0, st>>>(I);
+            if (ctx->dm.is_hex) k_heavy_hex<<<hgrid, TPB, 0, st>>>(I);
+            else k_heavy_general<<<hgrid, TPB, 0, st>>>(I);
             ctx->launches += 2;
         } else {
             CUDA_TRY(cudaEventRecord(ctx->ev[2], st));   // replay re-uses the classified and evaluated slots
