@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c4", "c5"])
-    ap.add_argument("--n", type=int, default=0, help="cells per side (scaled-down runs)")
+    ap.add_argument("--cells-per-side", dest="n", type=int, default=0, help="cells per side (scaled-down runs)")
     ap.add_argument("--solids", type=int, default=0)
     ap.add_argument("--cpu-solids", type=int, default=48, help="solids per CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -341,9 +341,15 @@ def main():
                 "wall_s": time.time() - t0,
             }
         print(json.dumps(line), flush=True)
+    # orderly teardown: our context (own CUDA stream / events) before torch's NCCL communicator and allocator
+    torch.cuda.synchronize()
+    del ext
+    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)  # skip interpreter-exit destructors of two CUDA runtimes (torch's and the library's static cudart)
 
 
 if __name__ == "__main__":

@@ -122,6 +122,14 @@ __device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad)
 // ------------------------------------------------------------------------------------------------
 // parameters shared by the classify / heavy / accumulate kernels
 // ------------------------------------------------------------------------------------------------
+// one candidate of a solid bin: what the sphere-type pre-classification needs, inline
+struct BinEntry {
+    double x, y, z;    // solid centre
+    double r_out, r_in;
+    int s;             // solid id
+    int kind;
+};
+
 struct InteractParams {
     DevMesh m;
     const DevSolid *solids;
@@ -130,6 +138,7 @@ struct InteractParams {
     BinGrid grid;
     const int *bin_off;
     const int *bin_list;
+    const BinEntry *bin_entries; // bin_list materialised after the per-bin sort
     const int *global_list;
     const double *U;
     double dtINV, rhof;
@@ -170,12 +179,25 @@ __global__ void __launch_bounds__(256) k_classify(InteractParams P) {
         int *rec = P.slots + (long long)c * KS;
         while (bi < be || gi < ge) {
             // merge the bin list and the global list in ascending solid id
-            int s;
-            const int sb = (bi < be) ? __ldg(P.bin_list + bi) : 0x7fffffff;
+            int s, qc;
+            const int sb = (bi < be) ? __ldg(&P.bin_entries[bi].s) : 0x7fffffff;
             const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
-            if (sb <= sg) { s = sb; ++bi; if (sb == sg) ++gi; }
-            else { s = sg; ++gi; }
-            const int qc = quick_class(P.solids[s], cc, rad);
+            if (sb <= sg) {
+                // binned candidates carry the data of the sphere-type pre-classification inline (one dependent load less)
+                const BinEntry &e = P.bin_entries[bi];
+                s = sb;
+                ++bi;
+                if (__ldg(&e.kind) == KIND_3D) {
+                    const double rx = cc.x - __ldg(&e.x), ry = cc.y - __ldg(&e.y), rz = cc.z - __ldg(&e.z);
+                    const double d2 = rx * rx + ry * ry + rz * rz;
+                    const double ro = __ldg(&e.r_out) + (double)rad.x, ri = __ldg(&e.r_in) - (double)rad.x;
+                    qc = (d2 > ro * ro) ? 0 : ((ri > 0.0 && d2 < ri * ri) ? 1 : 2);
+                } else qc = quick_class(P.solids[s], cc, rad);
+            } else {
+                s = sg;
+                ++gi;
+                qc = quick_class(P.solids[s], cc, rad);
+            }
             if (qc == 0) continue;
             if (n_item < P.K) {
                 rec[1 + n_item] = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
@@ -436,8 +458,9 @@ __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
 // ------------------------------------------------------------------------------------------------
 // k_accumulate
 // ------------------------------------------------------------------------------------------------
-// warp-level aggregation of one member pair per lane: lanes with the same solid are reduced with a
-// butterfly and the group leader issues the 6 fp64 + counter reductions.
+// warp-level aggregation of one member pair per lane: lanes with the same solid are reduced together and
+// the 6 force/torque sums + 2 of the 3 type counters leave the warp as 8 parallel reductions.  The 8 values
+// are folded (16 -> 8 -> 4 lanes keep half of the values each) so the butterfly costs 7 shuffles, not 30+.
 __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, const double v[6], double *force_torque,
                                                 unsigned *pair_counts) {
     const unsigned FULL = 0xffffffffu;
@@ -448,24 +471,27 @@ __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, cons
         const int s0 = __shfl_sync(FULL, s, leader);
         const bool mine = have && (s == s0);
         const unsigned grp = __ballot_sync(FULL, mine);
-        double w[6];
+        double w[8];
 #pragma unroll
         for (int k = 0; k < 6; ++k) w[k] = mine ? v[k] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) w[k] += __shfl_xor_sync(FULL, w[k], o);
-        }
-        const unsigned c1 = __popc(__ballot_sync(FULL, mine && type == 1));
-        const unsigned c2 = __popc(__ballot_sync(FULL, mine && type == 2));
+        w[6] = (mine && type == 1) ? 1.0 : 0.0;
+        w[7] = (mine && type == 2) ? 1.0 : 0.0;
         const unsigned c3 = __popc(__ballot_sync(FULL, mine && type == 3));
-        if (lane == leader) {
+        double a[4], b[2], c;
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) atomicAdd(force_torque + 6 * (long long)s0 + k, w[k]);
-            if (c1) atomicAdd(pair_counts + 3 * (long long)s0 + 0, c1);
-            if (c2) atomicAdd(pair_counts + 3 * (long long)s0 + 1, c2);
-            if (c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
+        for (int i = 0; i < 4; ++i) a[i] = (h16 ? w[i + 4] : w[i]) + __shfl_xor_sync(FULL, h16 ? w[i] : w[i + 4], 16);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(FULL, h8 ? a[i] : a[i + 2], 8);
+        c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(FULL, h4 ? b[0] : b[1], 4);
+        c += __shfl_xor_sync(FULL, c, 2);
+        c += __shfl_xor_sync(FULL, c, 1);
+        if ((lane & 3) == 0) {
+            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if (idx < 6) atomicAdd(force_torque + 6 * (long long)s0 + idx, c);
+            else if (c != 0.0) atomicAdd(pair_counts + 3 * (long long)s0 + (idx - 6), (unsigned)c);
         }
+        if (lane == leader && c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
         pending &= ~grp;
     }
 }

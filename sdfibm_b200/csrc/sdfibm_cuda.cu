@@ -109,9 +109,9 @@ __device__ __forceinline__ D3 ld3(const double *__restrict__ p, long long i) {
 }
 
 __device__ __forceinline__ int bin_coord(const BinGrid &g, double x, int d) {
-    double t = floor((x - g.lo[d]) * g.inv_b);
-    int i = (t < 0.0) ? 0 : ((t > (double)(g.n[d] - 1)) ? g.n[d] - 1 : (int)t);
-    return i;
+    // monotone in x (the same expression maps cells and solid boxes); __double2int_rd saturates, so +-1e300 is safe
+    const int i = __double2int_rd((x - g.lo[d]) * g.inv_b);
+    return min(max(i, 0), g.n[d] - 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -237,8 +237,11 @@ struct PrepParams {
     StepStatus *status;
 };
 
+// SUB threads per solid share the loop over the bins its bounding box covers
+#define BIN_SUB 8
 __global__ void k_solid_prepare(PrepParams P) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = gid / BIN_SUB, sub = gid % BIN_SUB;
     if (s >= P.n_solids) return;
     const sdfibm_solid_t in = P.solids[s];
     DevSolid S;
@@ -254,17 +257,21 @@ __global__ void k_solid_prepare(PrepParams P) {
     S.axis[0] = ax.x; S.axis[1] = ax.y; S.axis[2] = ax.z;
     S.axis_is_z = (fabs(ax.x) <= 1e-12 && fabs(ax.y) <= 1e-12) ? 1 : 0;
     S.global = (S.kind == KIND_PLANE || (S.kind == KIND_2D && !S.axis_is_z)) ? 1 : 0;
-    P.out[s] = S;
+    if (sub == 0) P.out[s] = S;
     if (S.global) {
-        int k = atomicAdd(&P.status->n_global, 1);
-        P.global_list[k] = s;
+        if (sub == 0) {
+            int k = atomicAdd(&P.status->n_global, 1);
+            P.global_list[k] = s;
+        }
         return;
     }
     int lo[3], hi[3];
     if (!solid_bin_range(S, P.grid, P.rad3_max, P.radxy_max, P.mesh_lo, P.mesh_hi, lo, hi)) return;
-    for (int k = lo[2]; k <= hi[2]; ++k)
-        for (int j = lo[1]; j <= hi[1]; ++j)
-            for (int i = lo[0]; i <= hi[0]; ++i) atomicAdd(&P.bin_count[(k * P.grid.n[1] + j) * P.grid.n[0] + i], 1);
+    const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+    for (int t = sub; t < nx * ny * nz; t += BIN_SUB) {
+        const int i = lo[0] + t % nx, j = lo[1] + (t / nx) % ny, k = lo[2] + t / (nx * ny);
+        atomicAdd(&P.bin_count[(k * P.grid.n[1] + j) * P.grid.n[0] + i], 1);
+    }
 }
 
 struct FillParams {
@@ -281,20 +288,21 @@ struct FillParams {
 };
 
 __global__ void k_bin_fill(FillParams P) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = gid / BIN_SUB, sub = gid % BIN_SUB;
     if (s >= P.n_solids) return;
-    const DevSolid S = P.solids[s];
+    const DevSolid &S = P.solids[s];
     if (S.global) return;
     int lo[3], hi[3];
     if (!solid_bin_range(S, P.grid, P.rad3_max, P.radxy_max, P.mesh_lo, P.mesh_hi, lo, hi)) return;
-    for (int k = lo[2]; k <= hi[2]; ++k)
-        for (int j = lo[1]; j <= hi[1]; ++j)
-            for (int i = lo[0]; i <= hi[0]; ++i) {
-                int b = (k * P.grid.n[1] + j) * P.grid.n[0] + i;
-                int pos = P.bin_off[b] + atomicAdd(&P.bin_cursor[b], 1);
-                if (pos < P.bin_cap) P.bin_list[pos] = s;
-                else P.status->bin_overflow = 1;
-            }
+    const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+    for (int t = sub; t < nx * ny * nz; t += BIN_SUB) {
+        const int i = lo[0] + t % nx, j = lo[1] + (t / nx) % ny, k = lo[2] + t / (nx * ny);
+        const int b = (k * P.grid.n[1] + j) * P.grid.n[0] + i;
+        const int pos = P.bin_off[b] + atomicAdd(&P.bin_cursor[b], 1);
+        if (pos < P.bin_cap) P.bin_list[pos] = s;
+        else P.status->bin_overflow = 1;
+    }
 }
 
 // ascending solid id inside every bin (and the global list): the per-cell accumulation order
@@ -313,6 +321,21 @@ __global__ void k_bin_sort(const int *bin_off, int *bin_list, int n_bins, int bi
 }
 
 #include "interact_kernels.cuh"
+
+// bin_list (sorted per bin) -> inline candidate records read by k_classify
+__global__ void k_bin_entries(const int *bin_off, const int *bin_list, int n_bins, int bin_cap, const DevSolid *solids, BinEntry *out) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = min(bin_off[n_bins], bin_cap);
+    if (pos >= total) return;
+    const int s = bin_list[pos];
+    const DevSolid &S = solids[s];
+    BinEntry e;
+    e.x = S.pos[0]; e.y = S.pos[1]; e.z = S.pos[2];
+    e.r_out = S.r_out; e.r_in = S.r_in;
+    e.s = s;
+    e.kind = S.kind;
+    out[pos] = e;
+}
 
 // ------------------------------------------------------------------------------------------------
 // collision step (solidcloud.cpp:477-519, libcollision/): centres hashed on the UGrid, pairs
@@ -463,6 +486,7 @@ struct sdfibm_context {
     DevBuf<sdfibm_solid_t> solids_in;
     DevBuf<DevSolid> solids;
     DevBuf<int> bin_count, bin_off, bin_cursor, bin_list, global_list, root_count, slots;
+    DevBuf<BinEntry> bin_entries;
     DevBuf<double> heavy_vol;
     DevBuf<unsigned char> n_item, heavy_type;
     DevBuf<int2> heavy;
@@ -570,7 +594,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
     ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
-    ctx->heavy_vol.release(); ctx->heavy_type.release(); ctx->n_item.release(); ctx->heavy.release();
+    ctx->bin_entries.release(); ctx->heavy_vol.release(); ctx->heavy_type.release(); ctx->n_item.release(); ctx->heavy.release();
     ctx->ft_internal.release(); ctx->status.release(); ctx->scan_tmp.release();
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
@@ -854,7 +878,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             P.out = ctx->solids.p; P.grid = g; P.rad3_max = ctx->rad3_max; P.radxy_max = ctx->radxy_max;
             for (int d = 0; d < 3; ++d) { P.mesh_lo[d] = ctx->bmin[d]; P.mesh_hi[d] = ctx->bmax[d]; }
             P.bin_count = ctx->bin_count.p; P.global_list = ctx->global_list.p; P.status = ctx->status.p;
-            k_solid_prepare<<<grid_for(n_solids, 128), 128, 0, st>>>(P);
+            k_solid_prepare<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(P);
             size_t tmp_bytes = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->bin_count.p, ctx->bin_off.p, g.n_bins + 1, st);
             CUDA_TRY(ctx->scan_tmp.ensure(tmp_bytes));
@@ -864,10 +888,13 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             for (int d = 0; d < 3; ++d) { F.mesh_lo[d] = ctx->bmin[d]; F.mesh_hi[d] = ctx->bmax[d]; }
             F.bin_off = ctx->bin_off.p; F.bin_cursor = ctx->bin_cursor.p; F.bin_list = ctx->bin_list.p;
             F.bin_cap = (int)std::min<size_t>(ctx->bin_list.n, 0x7fffffff); F.status = ctx->status.p;
-            k_bin_fill<<<grid_for(n_solids, 128), 128, 0, st>>>(F);
+            k_bin_fill<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(F);
             k_bin_sort<<<grid_for((long long)g.n_bins + 1, 128), 128, 0, st>>>(ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap,
                                                                               ctx->global_list.p, ctx->status.p);
-            ctx->launches += 4;
+            CUDA_TRY(ctx->bin_entries.ensure(ctx->bin_list.n));
+            k_bin_entries<<<grid_for((long long)F.bin_cap, 256), 256, 0, st>>>(ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap,
+                                                                            ctx->solids.p, ctx->bin_entries.p);
+            ctx->launches += 5;
         } else {
             // keep the binning of the first pass; restore the counters the status word carries
             StepStatus keep{};
@@ -879,7 +906,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         }
         InteractParams I;
         I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.n_solids = n_solids; I.grid = g;
-        I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.global_list = ctx->global_list.p; I.U = dU;
+        I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.bin_entries = ctx->bin_entries.p; I.global_list = ctx->global_list.p; I.U = dU;
         I.dtINV = 1.0 / dt; I.rhof = rhof; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
         I.pair_counts = ctx->pair_counts.p; I.slots = ctx->slots.p; I.K = ctx->K;
         I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_vol = ctx->heavy_vol.p; I.heavy_type = ctx->heavy_type.p;

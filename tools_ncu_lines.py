@@ -2,7 +2,8 @@
 """Top source lines of a kernel in an .ncu-rep by thread-instructions and stall samples (cuda,sass view)."""
 import csv, io, subprocess, sys
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kf = (["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else [])
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kf, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur = None; hdr = None; agg = []
 for r in rows:
