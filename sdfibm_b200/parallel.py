@@ -1,0 +1,39 @@
+"""Multi-rank plumbing: one subdomain (decomposePar `simple` block) per rank/GPU, solids replicated on every
+rank, ONE all-reduce of the per-solid force/torque per step replacing the reference's 2N Foam::reduce calls
+(reference src/solidcloud.cpp:427-431).  No halo exchange: every per-cell result depends only on the cell's
+own geometry and U."""
+from __future__ import annotations
+
+import numpy as np
+
+from .cases import decompose_simple
+
+
+def block_extent(rank: int, world: int, n):
+    """(lo_index[3], size[3]) of rank's block of an n[0] x n[1] x n[2] cell box under the `simple` split
+    (x fastest, like OpenFOAM's simpleGeomDecomp)."""
+    px, py, pz = decompose_simple(world)
+    n = (n, n, n) if np.isscalar(n) else tuple(n)
+    ix, iy, iz = rank % px, (rank // px) % py, rank // (px * py)
+    size = (n[0] // px, n[1] // py, n[2] // pz)
+    return (ix * size[0], iy * size[1], iz * size[2]), size
+
+
+def local_to_global_cells(rank: int, world: int, n) -> np.ndarray:
+    """cellProcAddressing of the block: global cell id of every local cell (blockMesh numbering on both sides)."""
+    n = (n, n, n) if np.isscalar(n) else tuple(n)
+    lo, sz = block_extent(rank, world, n)
+    i = np.arange(sz[0])[None, None, :] + lo[0]
+    j = np.arange(sz[1])[None, :, None] + lo[1]
+    k = np.arange(sz[2])[:, None, None] + lo[2]
+    return (i + n[0] * (j + n[1] * k)).reshape(-1)
+
+
+def allreduce_force_torque(ft):
+    """Sum the per-rank partial (F, T)[n_solids, 6] over all ranks, in place.  `ft` is a torch tensor on the
+    rank's device (NCCL) or on the CPU (gloo)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(ft, op=dist.ReduceOp.SUM)
+    return ft
