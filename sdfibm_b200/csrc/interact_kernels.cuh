@@ -1,23 +1,28 @@
 // interact_kernels.cuh — the sm_100a kernels of SolidCloud::interact / fixInternal.
 // Included by sdfibm_cuda.cu after the device records (DevMesh, DevSolid, DevShape, BinGrid, StepStatus).
 //
-//   k_classify      thread per cell   candidate solids (ascending id) -> per-cell slot record; pairs whose
-//                                     vertices must be evaluated exactly are appended to a global queue
-//   k_heavy         thread per item   exact vertex predicates + SDF, cell type, apex/pyramid volume (dense, no barriers)
-//   k_accumulate    thread per cell   As/Fs/Ts/Ct in the reference's += order, written once and coalesced;
-//                                     per-solid force/torque warp-aggregated before the atomics
-//   k_connectivity  thread per cell   certificate that each solid's cell set is one face-connected component
+//   k_cells         thread per cell   candidate solids (ascending id) -> per-cell slot record.  Cells whose members are all
+//                                     certainly ALL_INSIDE (or that have none) are FINAL here: As/Fs/Ts/Ct written once,
+//                                     coalesced, in the reference's += order.  Pairs whose vertices must be evaluated
+//                                     exactly are appended to a dense global queue.
+//   k_heavy         lane per item     exact vertex predicates + SDF, cell type, apex/pyramid volume; a cell whose only slot is
+//                                     this item is FINAL here (forcing fused into the evaluation kernel)
+//   k_multi         thread per cell   the few cells touched by several solids with a queued item: summed in slot order
+//   (all three)                       per-solid force/torque warp-aggregated before the atomics; connectivity certificate
+//   k_connectivity  thread per cell   exact connectivity check, only when the fused certificate leaves a solid undecided
 //   k_replay_*                        exact flood-fill component selection for solids that fail it (rare)
 //   k_fix_internal  thread per cell   SolidCloud::fixInternal
 //   k_list_*                          candidate-list extraction for parity (off the timed path)
 //
-// Slot record of cell c: KS = K+1 ints at slots + c*KS.  [0] = index of the cell's first heavy item in the
-// queue; [1+j] = (solid << 3) | (heavy ? 4 : 0) | type, j < n_item[c].  type is the CELL_TYPE (1,2,3) or 0
-// (no vertex inside: not a member).  Heavy items of a cell are consecutive in the queue, in slot order.
+// Slot records: slots[j * n_cells + c], j < n_item[c] <= K, = (solid << 3) | (queued ? 4 : 0) | type.  type is the
+// CELL_TYPE (1,2,3) or 0 (no vertex inside: not a member; queued slots carry 0 until their item is evaluated).  Queue
+// items of a cell are consecutive, in slot (= ascending solid id) order.
 #pragma once
 
 #define TPB 128
 #define SLOT_HEAVY 4
+#define ITEM_MULTI 0x40000000
+#define ENT_STAGE 48   // candidate records staged per warp in k_cells
 
 // ------------------------------------------------------------------------------------------------
 // geometry: apex / pyramid volume fraction (reference src/geometrictools.cpp:13-116)
@@ -120,7 +125,7 @@ __device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad)
 }
 
 // ------------------------------------------------------------------------------------------------
-// parameters shared by the classify / heavy / accumulate kernels
+// parameters shared by the cells / heavy / multi kernels
 // ------------------------------------------------------------------------------------------------
 // one candidate of a solid bin: what the sphere-type pre-classification needs, inline
 struct BinEntry {
@@ -145,52 +150,178 @@ struct InteractParams {
     double *As, *Fs, *Ts, *Ct;
     double *force_torque;   // [6*n_solids], zeroed
     unsigned *pair_counts;  // [3*n_solids], zeroed
-    int *slots;             // [n_cells*(K+1)] slot records (see file header)
+    int *unproven;          // [n_solids], zeroed: members for which no smaller-key member neighbour was proven
+    int *slots;             // [K][n_cells] slot records (see file header)
     unsigned char *n_item;  // [n_cells] slots in use
-    int2 *heavy;            // queue of (cell, solid) needing exact evaluation
-    double *heavy_vol;      // [queue] solid volume inside the cell (boundary types)
-    unsigned char *heavy_type; // [queue] resulting CELL_TYPE or 0
+    int2 *heavy;            // queue of (cell, solid | ITEM_MULTI) needing exact evaluation
+    double2 *heavy_res;     // [queue] per item: (solid volume inside the cell, bits: CELL_TYPE | vertex-inside mask << 8)
+    int2 *multi;            // queue of (cell, first heavy item) for cells with a heavy item and more than one slot
     unsigned long long *heavy_count;
     long long heavy_cap;
     int K;
-    int final_slots;        // replay pass: slot types are already final
     const unsigned char *excluded; // replay pass: [n_cells*K] 1 = pair is outside the seed's component
     StepStatus *status;
+    int debug;              // timing experiments only (SDFIBM_DEBUG): skip parts of the work
 };
 
+__device__ __forceinline__ float2 cell_radius(const DevMesh &m, int c) { return m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c); }
+
+// One member pair (solidcloud.cpp:384-390,411-421): the increments of the cell's fields and of the solid's sums.
+__device__ __forceinline__ void pair_terms(const DevSolid &S, D3 cc, D3 uf, double vol, double alpha, double dtINV,
+                                           D3 &fs_inc, double contrib[6]) {
+    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+    const D3 om = {S.omega[0], S.omega[1], S.omega[2]};
+    const D3 us = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(om, cc - t);
+    const D3 f_ = alpha * (uf - us);
+    const D3 t_ = cross3(cc - t, f_);
+    const D3 fo = f_ * vol * dtINV;
+    const D3 to = t_ * vol * dtINV;
+    contrib[0] = fo.x; contrib[1] = fo.y; contrib[2] = fo.z;
+    contrib[3] = to.x; contrib[4] = to.y; contrib[5] = to.z;
+    fs_inc = f_ * dtINV;
+}
+
+__device__ __forceinline__ void store_cell(const InteractParams &P, int c, double as, D3 fs, double ts, double ct) {
+    P.As[c] = (as < 1.0) ? as : 1.0;                                               // checkAlpha, :564-570 (std::min(As,1))
+    P.Fs[3 * (long long)c] = fs.x;
+    P.Fs[3 * (long long)c + 1] = fs.y;
+    P.Fs[3 * (long long)c + 2] = fs.z;
+    P.Ts[c] = ts;
+    P.Ct[c] = ct;
+}
+
+// warp-level aggregation of one member pair per lane: lanes with the same solid are reduced together and
+// the 6 force/torque sums + 2 of the 3 type counters leave the warp as 8 parallel reductions.  The 8 values
+// are folded (16 -> 8 -> 4 lanes keep half of the values each) so the butterfly costs 7 shuffles, not 30+.
+__device__ __forceinline__ void warp_accumulate(bool have, int s, int type, const double v[6], double *force_torque,
+                                                unsigned *pair_counts) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned pending = __ballot_sync(FULL, have);
+    const int lane = threadIdx.x & 31;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int s0 = __shfl_sync(FULL, s, leader);
+        const bool mine = have && (s == s0);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        double w[8];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = mine ? v[k] : 0.0;
+        w[6] = (mine && type == 1) ? 1.0 : 0.0;
+        w[7] = (mine && type == 2) ? 1.0 : 0.0;
+        const unsigned c3 = __popc(__ballot_sync(FULL, mine && type == 3));
+        double a[4], b[2], c;
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = (h16 ? w[i + 4] : w[i]) + __shfl_xor_sync(FULL, h16 ? w[i] : w[i + 4], 16);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(FULL, h8 ? a[i] : a[i + 2], 8);
+        c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(FULL, h4 ? b[0] : b[1], 4);
+        c += __shfl_xor_sync(FULL, c, 2);
+        c += __shfl_xor_sync(FULL, c, 1);
+        if ((lane & 3) == 0) {
+            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if (idx < 6) atomicAdd(force_torque + 6 * (long long)s0 + idx, c);
+            else if (c != 0.0) atomicAdd(pair_counts + 3 * (long long)s0 + (idx - 6), (unsigned)c);
+        }
+        if (lane == leader && c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
+        pending &= ~grp;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// k_classify
+// connectivity certificate.  A member pair (c, s) is "proven" when one face neighbour with a smaller
+// (distance-to-centre, cell id) key is CERTAINLY a member of s.  If at most one member of a solid is
+// unproven, its vertex-inside cell set is one face-connected component (follow the proven parents: keys
+// strictly decrease, so every chain ends in the single unproven cell)  =>  it equals the reference's flood
+// fill from any seed.  Solids with more unproven members go through the exact check
+// (k_connectivity) and, if that fails too, the flood-fill replay.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_classify(InteractParams P) {
+__device__ __forceinline__ bool key_less(double ka, int ca, double kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
+
+// neighbour certainly ALL_INSIDE (its whole vertex cloud lies inside the certified inner radius)
+__device__ __forceinline__ bool proven_by_inner_neighbour(const DevMesh &m, const DevSolid &S, int c, D3 cc) {
+    const D3 x = {S.pos[0], S.pos[1], S.pos[2]};
+    const double kc = magSqr3(cc - x);
+    const int nb0 = __ldg(m.nb_off + c), nb1 = __ldg(m.nb_off + c + 1);
+    for (int k = nb0; k < nb1; ++k) {
+        const int nb = __ldg(m.nb + k);
+        const D3 ccn = ld3(m.cc, nb);
+        if (!key_less(magSqr3(ccn - x), nb, kc, c)) continue;
+        if (quick_class(S, ccn, cell_radius(m, nb)) == 1) return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_cells: thread per mesh cell
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cells(InteractParams P) {
     const DevMesh &m = P.m;
+    const unsigned FULL = 0xffffffffu;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = c < m.n_cells;
-    const int KS = P.K + 1;
+    const long long nC = m.n_cells;
+    const int lane = threadIdx.x & 31;
     int n_item = 0, n_heavy = 0;
+    D3 cc = {0.0, 0.0, 0.0};
+    float2 rad = m.rad_const;
+    int b = -1;
     if (live) {
-        const D3 cc = ld3(m.cc, c);
-        const float2 rad = m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c);
-        const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] +
-                      bin_coord(P.grid, cc.x, 0);
-        int bi = __ldg(P.bin_off + b);
-        const int be = __ldg(P.bin_off + b + 1);
+        cc = ld3(m.cc, c);
+        rad = cell_radius(m, c);
+        b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] + bin_coord(P.grid, cc.x, 0);
+    }
+    // The cells of a warp usually fall into a short run of consecutive bins, whose candidate records are
+    // contiguous: fetch the offsets with one load per lane and the records with coalesced 16-byte loads into
+    // shared memory, so the per-cell loop below has no dependent global loads.
+    __shared__ __align__(16) BinEntry s_ent[8][ENT_STAGE];
+    const int bmin = __reduce_min_sync(FULL, live ? b : 0x7fffffff), bmax = __reduce_max_sync(FULL, b);
+    int bi = 0, be = 0;
+    const BinEntry *E = P.bin_entries;
+    if (bmax >= 0) {
+        const int span = bmax - bmin + 1;
+        bool staged = span <= 31;
+        int off_l = 0, e0 = 0;
+        if (staged) {
+            off_l = (lane <= span) ? __ldg(P.bin_off + bmin + lane) : 0;
+            e0 = __shfl_sync(FULL, off_l, 0);
+            const int ne = __shfl_sync(FULL, off_l, span) - e0;
+            staged = ne <= ENT_STAGE;
+            if (staged) {
+                const int4 *src = reinterpret_cast<const int4 *>(P.bin_entries + e0);
+                int4 *dst = reinterpret_cast<int4 *>(s_ent[threadIdx.x >> 5]);
+                for (int i = lane; i < 3 * ne; i += 32) dst[i] = __ldg(src + i);
+                __syncwarp();
+                E = s_ent[threadIdx.x >> 5] - e0;
+            }
+        }
+        if (staged) {
+            const int rel = live ? b - bmin : 0;
+            bi = __shfl_sync(FULL, off_l, rel);
+            be = __shfl_sync(FULL, off_l, rel + 1);
+            if (!live) be = bi;
+        } else if (live) {
+            bi = __ldg(P.bin_off + b);
+            be = __ldg(P.bin_off + b + 1);
+        }
+    }
+    if (live) {
         int gi = 0;
         const int ge = P.status->n_global;
-        int *rec = P.slots + (long long)c * KS;
         while (bi < be || gi < ge) {
             // merge the bin list and the global list in ascending solid id
             int s, qc;
-            const int sb = (bi < be) ? __ldg(&P.bin_entries[bi].s) : 0x7fffffff;
+            const int sb = (bi < be) ? E[bi].s : 0x7fffffff;
             const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
             if (sb <= sg) {
-                // binned candidates carry the data of the sphere-type pre-classification inline (one dependent load less)
-                const BinEntry &e = P.bin_entries[bi];
+                // binned candidates carry the data of the sphere-type pre-classification inline
+                const BinEntry &e = E[bi];
                 s = sb;
                 ++bi;
-                if (__ldg(&e.kind) == KIND_3D) {
-                    const double rx = cc.x - __ldg(&e.x), ry = cc.y - __ldg(&e.y), rz = cc.z - __ldg(&e.z);
+                if (e.kind == KIND_3D) {
+                    const double rx = cc.x - e.x, ry = cc.y - e.y, rz = cc.z - e.z;
                     const double d2 = rx * rx + ry * ry + rz * rz;
-                    const double ro = __ldg(&e.r_out) + (double)rad.x, ri = __ldg(&e.r_in) - (double)rad.x;
+                    const double ro = e.r_out + (double)rad.x, ri = e.r_in - (double)rad.x;
                     qc = (d2 > ro * ro) ? 0 : ((ri > 0.0 && d2 < ri * ri) ? 1 : 2);
                 } else qc = quick_class(P.solids[s], cc, rad);
             } else {
@@ -200,37 +331,86 @@ __global__ void __launch_bounds__(256) k_classify(InteractParams P) {
             }
             if (qc == 0) continue;
             if (n_item < P.K) {
-                rec[1 + n_item] = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
+                P.slots[(long long)n_item * nC + c] = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
                 n_heavy += (qc == 2);
                 ++n_item;
             } else P.status->slot_overflow = 1;
         }
         P.n_item[c] = (unsigned char)n_item;
     }
-    // warp-aggregated append of the heavy items to the global queue (one atomic per warp)
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    int incl = n_heavy;
+    // ---- warp-aggregated append of the heavy items to the global queue (one atomic per warp) ----
+    const bool is_multi = n_heavy > 0 && n_item > 1;
+    {
+        int incl = n_heavy;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (total == 0) return;
-    unsigned long long base = 0;
-    if (lane == 31) base = atomicAdd(P.heavy_count, (unsigned long long)total);
-    base = __shfl_sync(FULL, base, 31);
-    if (n_heavy == 0) return;
-    long long pos = (long long)base + incl - n_heavy;
-    int *rec = P.slots + (long long)c * KS;
-    rec[0] = (int)pos;
-    for (int j = 0; j < n_item; ++j) {
-        const int e = rec[1 + j];
-        if (e & SLOT_HEAVY) {
-            if (pos < P.heavy_cap) P.heavy[pos] = make_int2(c, e >> 3);
-            ++pos;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
         }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total > 0) {
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(P.heavy_count, (unsigned long long)total);
+            base = __shfl_sync(FULL, base, 31);
+            long long pos = (long long)base + incl - n_heavy;
+            const unsigned mm = __ballot_sync(FULL, is_multi);
+            if (mm) {
+                unsigned mbase = 0;
+                const int mlead = __ffs(mm) - 1;
+                if (lane == mlead) mbase = atomicAdd(&P.status->multi_total, (unsigned)__popc(mm));
+                mbase = __shfl_sync(FULL, mbase, mlead);
+                const long long mpos = (long long)mbase + __popc(mm & ((1u << lane) - 1u));
+                if (is_multi && mpos < P.heavy_cap) P.multi[mpos] = make_int2(c, (int)pos);
+            }
+            for (int j = 0; j < n_item && n_heavy > 0; ++j) {
+                const int e = P.slots[(long long)j * nC + c];
+                if (e & SLOT_HEAVY) {
+                    if (pos < P.heavy_cap) P.heavy[pos] = make_int2(c, (e >> 3) | (is_multi ? ITEM_MULTI : 0));
+                    ++pos;
+                }
+            }
+        }
+    }
+    // ---- cells without a heavy item are final here: every member is ALL_INSIDE with alpha = 1 ----
+    const bool fin = live && n_heavy == 0;
+    const int nl = (fin && !(P.debug & 2)) ? n_item : 0;
+    int nmax = nl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+    double as = 0.0, ts = 0.0, ct = 0.0;
+    D3 fs = {0.0, 0.0, 0.0};
+    if (nmax > 0) {
+        D3 uf = {0.0, 0.0, 0.0};
+        double vol = 1.0;
+        if (nl > 0) {
+            uf = ld3(P.U, c);
+            vol = __ldg(m.V + c);
+        }
+        for (int j = 0; j < nmax; ++j) {
+            bool have = false;
+            int s = -1;
+            double contrib[6] = {0, 0, 0, 0, 0, 0};
+            if (j < nl && !(P.excluded && P.excluded[(long long)c * P.K + j])) {
+                s = P.slots[(long long)j * nC + c] >> 3;
+                D3 fi;
+                pair_terms(P.solids[s], cc, uf, vol, 1.0, P.dtINV, fi, contrib);     // solidcloud.cpp:408-421, alpha = 1
+                as += 1.0;
+                fs = fs + fi;
+                ts += 1.0;
+                ct = (double)(s + 4);                                                // :376-382, last writer wins
+                have = true;
+            }
+            if (__any_sync(FULL, have)) warp_accumulate(have, s, SDFIBM_CELL_ALL_INSIDE, contrib, P.force_torque, P.pair_counts);
+        }
+    }
+    if (fin) store_cell(P, c, as, fs, ts, ct);
+    // ---- connectivity certificate of the ALL_INSIDE members found by the pre-classification ----
+    for (int j = 0; j < n_item; ++j) {
+        const int e = P.slots[(long long)j * nC + c];
+        if (e & SLOT_HEAVY) continue;
+        if (P.excluded || (P.debug & 1)) continue;   // replay pass: the certificate is not consulted
+        const int s = e >> 3;
+        if (!proven_by_inner_neighbour(m, P.solids[s], c, cc)) atomicAdd(P.unproven + s, 1);
     }
 }
 
@@ -238,7 +418,7 @@ __global__ void __launch_bounds__(256) k_classify(InteractParams P) {
 // k_heavy: exact evaluation of one (cell, solid) item
 // ------------------------------------------------------------------------------------------------
 // General polyhedra: cell-local arrays in local memory, CSR connectivity.
-__device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out) {
+__device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out, unsigned &inmask) {
     const DevMesh &m = P.m;
     const DevSolid &S = P.solids[s];
     const DevShape &sh = P.shapes[S.shape];
@@ -251,19 +431,21 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
     int nv = __ldg(m.cp_off + c + 1) - pb;
     if (nv > MAX_CELL_VERTS) { nv = MAX_CELL_VERTS; P.status->bad_cell = 1; }
     int n_in = 0;
+    inmask = 0;
     for (int k = 0; k < nv; ++k) {
         vid[k] = __ldg(m.cp + pb + k);
         pts[k] = ld3(m.points, vid[k]);
         double ph;
-        n_in += shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph) ? 1 : 0;
+        if (shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph)) { ++n_in; inmask |= 1u << k; }
         phi[k] = ph;
     }
     type_out = 0;
     vol_out = 0.0;
     if (n_in == 0) return;
+    const D3 cc = ld3(m.cc, c);
     if (n_in == nv) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
     double dummy;
-    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+    type_out = shape_eval<false>(sh.s, world2local(q, t, cc), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
     vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
 }
 
@@ -310,7 +492,7 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
     for (long long k0 = (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
         const long long k = k0 + lane;
         const bool valid = k < n;
-        int c = -1, s = -1;
+        int c = -1, s = -1, s_raw = 0;
         int vid[8] = {-1, -2, -3, -4, -5, -6, -7, -8};
         DQ q = {1.0, {0.0, 0.0, 0.0}};
         D3 t = {0.0, 0.0, 0.0};
@@ -320,7 +502,8 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
         if (valid) {
             const int2 it = __ldg(P.heavy + k);
             c = it.x;
-            s = it.y;
+            s_raw = it.y;
+            s = s_raw & ~ITEM_MULTI;
             const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
             const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
             vid[0] = va.x; vid[1] = va.y; vid[2] = va.z; vid[3] = va.w;
@@ -363,7 +546,7 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
             if (work) {
                 const int kk = 2 * (u & 3);
                 const int col = wbase + src;
-                const int s_src = __ldg(&P.heavy[k0 + src].y);
+                const int s_src = __ldg(&P.heavy[k0 + src].y) & ~ITEM_MULTI;
                 const DevSolid &S2 = P.solids[s_src];
                 const DQ q2 = {S2.q[0], {S2.q[1], S2.q[2], S2.q[3]}};
                 const D3 t2 = {S2.pos[0], S2.pos[1], S2.pos[2]};
@@ -375,8 +558,13 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
             int type = 0;
             double volume = 0.0;
             int n_in = 0;
+            unsigned inmask = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) n_in += sm.in[j * TPB + tid];
+            for (int j = 0; j < 8; ++j) {
+                const unsigned b = sm.in[j * TPB + tid];
+                n_in += b;
+                inmask |= b << j;
+            }
             if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
             else if (n_in != 0) {
                 double dummy;
@@ -436,8 +624,7 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
                     volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
                 }
             }
-            P.heavy_type[k] = (unsigned char)type; // 0: no vertex inside -> not a member
-            P.heavy_vol[k] = volume;
+            P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (inmask << 8))));
         }
         __syncwarp();
     }
@@ -446,135 +633,158 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
 __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
     for (long long k = (long long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long long)gridDim.x * TPB) {
-        const int2 it = __ldg(P.heavy + k); // (cell, solid)
+        const int2 it = __ldg(P.heavy + k); // (cell, solid | ITEM_MULTI)
         int type;
         double v;
-        heavy_eval_general(P, it.x, it.y, type, v);
-        P.heavy_type[k] = (unsigned char)type;
-        P.heavy_vol[k] = v;
+        unsigned inmask;
+        heavy_eval_general(P, it.x, it.y & ~ITEM_MULTI, type, v, inmask);
+        P.heavy_res[k] = make_double2(v, __longlong_as_double((long long)type | ((long long)inmask << 8)));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_accumulate
+// k_finish: thread per evaluated item, full occupancy.  A cell whose only slot is this item is FINAL here
+// (forcing fused with the hand-over of the evaluation result); every member item gets its connectivity
+// certificate: a smaller-key face neighbour that is certainly ALL_INSIDE, or that shares a vertex the exact
+// predicate found inside (such a neighbour has >= 1 vertex inside, i.e. it is a member).
 // ------------------------------------------------------------------------------------------------
-// warp-level aggregation of one member pair per lane: lanes with the same solid are reduced together and
-// the 6 force/torque sums + 2 of the 3 type counters leave the warp as 8 parallel reductions.  The 8 values
-// are folded (16 -> 8 -> 4 lanes keep half of the values each) so the butterfly costs 7 shuffles, not 30+.
-__device__ __forceinline__ void warp_accumulate(bool have, int s, int type, const double v[6], double *force_torque,
-                                                unsigned *pair_counts) {
-    const unsigned FULL = 0xffffffffu;
-    unsigned pending = __ballot_sync(FULL, have);
-    const int lane = threadIdx.x & 31;
-    while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const int s0 = __shfl_sync(FULL, s, leader);
-        const bool mine = have && (s == s0);
-        const unsigned grp = __ballot_sync(FULL, mine);
-        double w[8];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) w[k] = mine ? v[k] : 0.0;
-        w[6] = (mine && type == 1) ? 1.0 : 0.0;
-        w[7] = (mine && type == 2) ? 1.0 : 0.0;
-        const unsigned c3 = __popc(__ballot_sync(FULL, mine && type == 3));
-        double a[4], b[2], c;
-        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = (h16 ? w[i + 4] : w[i]) + __shfl_xor_sync(FULL, h16 ? w[i] : w[i + 4], 16);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(FULL, h8 ? a[i] : a[i + 2], 8);
-        c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(FULL, h4 ? b[0] : b[1], 4);
-        c += __shfl_xor_sync(FULL, c, 2);
-        c += __shfl_xor_sync(FULL, c, 1);
-        if ((lane & 3) == 0) {
-            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            if (idx < 6) atomicAdd(force_torque + 6 * (long long)s0 + idx, c);
-            else if (c != 0.0) atomicAdd(pair_counts + 3 * (long long)s0 + (idx - 6), (unsigned)c);
+template <bool HEX>
+__device__ __forceinline__ bool proven_by_shared_vertex(const DevMesh &m, const DevSolid &S, int c, D3 cc, unsigned inmask) {
+    const D3 x = {S.pos[0], S.pos[1], S.pos[2]};
+    const double kc = magSqr3(cc - x);
+    const int nb0 = __ldg(m.nb_off + c), nb1 = __ldg(m.nb_off + c + 1);
+    const int pc = HEX ? 8 * c : __ldg(m.cp_off + c);
+    const int nvc = HEX ? 8 : __ldg(m.cp_off + c + 1) - pc;
+    for (int k = nb0; k < nb1; ++k) {
+        const int nb = __ldg(m.nb + k);
+        const D3 ccn = ld3(m.cc, nb);
+        if (!key_less(magSqr3(ccn - x), nb, kc, c)) continue;
+        if (quick_class(S, ccn, cell_radius(m, nb)) == 1) return true;
+        const int pb = HEX ? 8 * nb : __ldg(m.cp_off + nb);
+        const int nvn = HEX ? 8 : __ldg(m.cp_off + nb + 1) - pb;
+        for (int j = 0; j < nvc; ++j) {
+            if (!((inmask >> j) & 1u)) continue;
+            const int v = __ldg(m.cp + pc + j);
+            for (int i = 0; i < nvn; ++i)
+                if (__ldg(m.cp + pb + i) == v) return true;
         }
-        if (lane == leader && c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
-        pending &= ~grp;
+    }
+    return false;
+}
+
+template <bool HEX>
+__global__ void __launch_bounds__(256) k_finish(InteractParams P) {
+    const DevMesh &m = P.m;
+    const unsigned FULL = 0xffffffffu;
+    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
+    for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < n; k0 += (long long)gridDim.x * blockDim.x) {
+        const long long k = k0 + threadIdx.x;
+        bool have = false;
+        int type = 0, s = -1;
+        double contrib[6] = {0, 0, 0, 0, 0, 0};
+        if (k < n) {
+            const int2 it = __ldg(P.heavy + k);
+            const int c = it.x;
+            s = it.y & ~ITEM_MULTI;
+            const double2 r = P.heavy_res[k];
+            const long long bits = __double_as_longlong(r.y);
+            type = (int)(bits & 3);
+            const unsigned inmask = (unsigned)(bits >> 8);
+            D3 cc = {0.0, 0.0, 0.0};
+            if (type != 0) cc = ld3(m.cc, c);
+            if (!(it.y & ITEM_MULTI)) {      // otherwise k_multi sums the cell's slots in order
+                double as = 0.0, ts = 0.0, ct = 0.0;
+                D3 fs = {0.0, 0.0, 0.0};
+                const bool skip = P.excluded && P.excluded[(long long)c * P.K];
+                if (type != 0 && !skip) {
+                    const double vol = __ldg(m.V + c);
+                    const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : r.x / vol;     // solidcloud.cpp:408-410
+                    D3 fi;
+                    pair_terms(P.solids[s], cc, ld3(P.U, c), vol, alpha, P.dtINV, fi, contrib);
+                    as += alpha;
+                    fs = fs + fi;
+                    ts += alpha;
+                    ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;      // :376-382
+                    have = true;
+                }
+                store_cell(P, c, as, fs, ts, ct);
+                P.slots[c] = (s << 3) | SLOT_HEAVY | type;                                       // slot 0 now carries the final type
+            }
+            if (type != 0 && !P.excluded && !(P.debug & 4) && !proven_by_shared_vertex<HEX>(m, P.solids[s], c, cc, inmask))
+                atomicAdd(P.unproven + s, 1);
+        }
+        if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
     }
 }
 
-__global__ void __launch_bounds__(256) k_accumulate(InteractParams P) {
+// ------------------------------------------------------------------------------------------------
+// k_multi: cells touched by several solids of which at least one needed exact evaluation — the per-cell
+// sums are taken in slot (= ascending solid = the reference's `+=`) order, one thread per such cell.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_multi(InteractParams P) {
     const DevMesh &m = P.m;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = c < m.n_cells;
-    const int n = live ? (int)P.n_item[c] : 0;
     const unsigned FULL = 0xffffffffu;
-    const int KS = P.K + 1;
-    int nmax = n;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-
-    double as = 0.0, ts = 0.0, ct = 0.0;
-    D3 fs = {0.0, 0.0, 0.0};
-    if (nmax > 0) {
+    const long long nC = m.n_cells;
+    const long long n = min((long long)P.status->multi_total, P.heavy_cap);
+    for (long long i0 = (long long)blockIdx.x * TPB; i0 < n; i0 += (long long)gridDim.x * TPB) {
+        const long long i = i0 + threadIdx.x;
+        const bool valid = i < n;
+        int c = 0, nI = 0;
+        long long hk = 0;
         D3 cc = {0, 0, 0}, uf = {0, 0, 0};
         double vol = 1.0;
-        int *rec = P.slots + (long long)c * KS;
-        long long hk = 0;
-        if (n > 0) {
+        if (valid) {
+            const int2 e = __ldg(P.multi + i);
+            c = e.x;
+            hk = e.y;
+            nI = P.n_item[c];
             cc = ld3(m.cc, c);
             uf = ld3(P.U, c);
             vol = __ldg(m.V + c);
-            hk = rec[0];
         }
+        int nmax = nI;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+        double as = 0.0, ts = 0.0, ct = 0.0;
+        D3 fs = {0.0, 0.0, 0.0};
         for (int j = 0; j < nmax; ++j) {
             bool have = false;
             int s = -1, type = 0;
             double contrib[6] = {0, 0, 0, 0, 0, 0};
-            if (j < n) {
-                const int e = rec[1 + j];
+            if (j < nI) {
+                const int e = P.slots[(long long)j * nC + c];
                 s = e >> 3;
                 type = e & 3;
                 double v = 0.0;
                 if (e & SLOT_HEAVY) {
-                    if (!P.final_slots) {
-                        type = P.heavy_type[hk];
-                        rec[1 + j] = (e & ~3) | type;                       // the slot now carries the final type
-                    }
-                    if (type > SDFIBM_CELL_ALL_INSIDE) v = P.heavy_vol[hk];
+                    const double2 r = P.heavy_res[hk];
+                    type = (int)(__double_as_longlong(r.y) & 3);
+                    P.slots[(long long)j * nC + c] = (e & ~3) | type;               // the slot now carries the final type
+                    if (type > SDFIBM_CELL_ALL_INSIDE) v = r.x;
                     ++hk;
                 }
                 const bool skip = P.excluded && P.excluded[(long long)c * P.K + j]; // replay: outside the seed's component
                 if (type != 0 && !skip) {
-                    const DevSolid &S = P.solids[s];
-                    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
                     const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol;   // solidcloud.cpp:408-410
-                    // solidcloud.cpp:384-390,411-421
-                    const D3 om = {S.omega[0], S.omega[1], S.omega[2]};
-                    const D3 us = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(om, cc - t);
-                    const D3 f_ = alpha * (uf - us);
-                    const D3 t_ = cross3(cc - t, f_);
-                    const D3 fo = f_ * vol * P.dtINV;
-                    const D3 to = t_ * vol * P.dtINV;
-                    contrib[0] = fo.x; contrib[1] = fo.y; contrib[2] = fo.z;
-                    contrib[3] = to.x; contrib[4] = to.y; contrib[5] = to.z;
+                    D3 fi;
+                    pair_terms(P.solids[s], cc, uf, vol, alpha, P.dtINV, fi, contrib);
                     as += alpha;
-                    fs = fs + f_ * P.dtINV;
+                    fs = fs + fi;
                     ts += alpha;
-                    ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;   // :376-382, last writer wins
+                    ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;  // :376-382, last writer wins
                     have = true;
                 }
             }
             if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
         }
-    }
-    if (live) {
-        P.As[c] = (as < 1.0) ? as : 1.0;                                           // checkAlpha, :564-570 (std::min(As,1))
-        P.Fs[3 * (long long)c] = fs.x;
-        P.Fs[3 * (long long)c + 1] = fs.y;
-        P.Fs[3 * (long long)c + 2] = fs.z;
-        P.Ts[c] = ts;
-        P.Ct[c] = ct;
+        if (valid) store_cell(P, c, as, fs, ts, ct);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_connectivity: a member pair is a "root" when no face neighbour that is a member of the same solid has a
-// smaller (distance-to-centre, cell id) key.  Exactly one root  =>  the solid's vertex-inside cell set is
-// face connected  =>  it equals the reference's flood fill from any seed.
+// k_connectivity (exact check, only launched when a solid has more than one unproven member): a member pair
+// is a "root" when no face neighbour that is a member of the same solid has a smaller key.  Exactly one
+// root  =>  the solid's vertex-inside cell set is face connected.
 // ------------------------------------------------------------------------------------------------
 struct ConnParams {
     DevMesh m;
@@ -582,17 +792,15 @@ struct ConnParams {
     const unsigned char *n_item;
     const int *slots;
     int K;
+    const int *unproven;
     int *root_count; // [n_solids] zeroed
 };
 
-__device__ __forceinline__ bool key_less(double ka, int ca, double kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
-
 // slot index of solid s among the members of cell nb, or -1
-__device__ __forceinline__ int find_member(const unsigned char *n_item, const int *slots, int KS, int nb, int s) {
+__device__ __forceinline__ int find_member(const unsigned char *n_item, const int *slots, long long nC, int nb, int s) {
     const int nn = n_item[nb];
-    const int *rec = slots + (long long)nb * KS;
     for (int jj = 0; jj < nn; ++jj) {
-        const int e = rec[1 + jj];
+        const int e = slots[(long long)jj * nC + nb];
         if ((e >> 3) == s) return (e & 3) ? jj : -1;
     }
     return -1;
@@ -603,20 +811,20 @@ __global__ void k_connectivity(ConnParams P) {
     if (c >= P.m.n_cells) return;
     const int n = P.n_item[c];
     if (n == 0) return;
-    const int KS = P.K + 1;
+    const long long nC = P.m.n_cells;
     const D3 cc = ld3(P.m.cc, c);
     const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
-    const int *rec = P.slots + (long long)c * KS;
     for (int j = 0; j < n; ++j) {
-        const int e = rec[1 + j];
+        const int e = P.slots[(long long)j * nC + c];
         if ((e & 3) == 0) continue;
         const int s = e >> 3;
+        if (P.unproven[s] <= 1) continue;          // already certified
         const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
         const double kc = magSqr3(cc - x);
         bool has_parent = false;
         for (int k = nb0; k < nb1 && !has_parent; ++k) {
             const int nb = __ldg(P.m.nb + k);
-            if (find_member(P.n_item, P.slots, KS, nb, s) >= 0) {
+            if (find_member(P.n_item, P.slots, nC, nb, s) >= 0) {
                 const double kn = magSqr3(ld3(P.m.cc, nb) - x);
                 if (key_less(kn, nb, kc, c)) has_parent = true;
             }
@@ -625,14 +833,18 @@ __global__ void k_connectivity(ConnParams P) {
     }
 }
 
-__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status) {
+// totals of the per-solid counters; mode 0: pair counts + solids with more than one unproven member,
+// mode 1: solids with more than one root (after the exact check)
+__global__ void k_finalize(const unsigned *pair_counts, const int *per_solid, int n_solids, StepStatus *status, int mode) {
     unsigned long long c0 = 0, c1 = 0, c2 = 0;
     int nf = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_solids; s += gridDim.x * blockDim.x) {
-        c0 += pair_counts[3 * s];
-        c1 += pair_counts[3 * s + 1];
-        c2 += pair_counts[3 * s + 2];
-        nf += root_count[s] > 1;
+        if (mode == 0) {
+            c0 += pair_counts[3 * s];
+            c1 += pair_counts[3 * s + 1];
+            c2 += pair_counts[3 * s + 2];
+        }
+        nf += per_solid[s] > 1;
     }
     for (int o = 16; o > 0; o >>= 1) {
         c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -644,7 +856,7 @@ __global__ void k_finalize(const unsigned *pair_counts, const int *root_count, i
         if (c0) atomicAdd(&status->counts[0], c0);
         if (c1) atomicAdd(&status->counts[1], c1);
         if (c2) atomicAdd(&status->counts[2], c2);
-        if (nf) atomicAdd(&status->n_flagged, nf);
+        if (nf) atomicAdd(mode == 0 ? &status->n_suspect : &status->n_flagged, nf);
     }
 }
 
@@ -681,9 +893,8 @@ __global__ void k_replay_init(ReplayParams P) {
     if (c >= P.m.n_cells) return;
     for (int j = 0; j < P.K; ++j) { P.labels[(long long)c * P.K + j] = -1; P.excluded[(long long)c * P.K + j] = 0; }
     const int n = P.n_item[c];
-    const int *rec = P.slots + (long long)c * (P.K + 1);
-    for (int j = 0; j < n; ++j) {
-        const int e = rec[1 + j];
+        for (int j = 0; j < n; ++j) {
+        const int e = P.slots[(long long)j * P.m.n_cells + c];
         if ((e & 3) != 0 && P.root_count[e >> 3] > 1) P.labels[(long long)c * P.K + j] = c;
     }
 }
@@ -693,17 +904,15 @@ __global__ void k_replay_propagate(ReplayParams P) {
     if (c >= P.m.n_cells) return;
     const int n = P.n_item[c];
     if (n == 0) return;
-    const int KS = P.K + 1;
-    const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
-    const int *rec = P.slots + (long long)c * KS;
-    for (int j = 0; j < n; ++j) {
+        const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
+        for (int j = 0; j < n; ++j) {
         int lab = P.labels[(long long)c * P.K + j];
         if (lab < 0) continue;
-        const int s = rec[1 + j] >> 3;
+        const int s = P.slots[(long long)j * P.m.n_cells + c] >> 3;
         int best = lab;
         for (int k = nb0; k < nb1; ++k) {
             const int nb = __ldg(P.m.nb + k);
-            const int jj = find_member(P.n_item, P.slots, KS, nb, s);
+            const int jj = find_member(P.n_item, P.slots, P.m.n_cells, nb, s);
             if (jj >= 0) {
                 const int l2 = ((volatile int *)P.labels)[(long long)nb * P.K + jj];
                 if (l2 >= 0 && l2 < best) best = l2;
@@ -731,10 +940,9 @@ __global__ void k_replay_seed(ReplayParams P, int pass) {
     }
     if (pass == 1) {
         const int n = P.n_item[c];
-        const int *rec = P.slots + (long long)c * (P.K + 1);
-        for (int j = 0; j < n; ++j) {
+                for (int j = 0; j < n; ++j) {
             const int lab = P.labels[(long long)c * P.K + j];
-            if (lab >= 0) atomicMin(P.min_label + (rec[1 + j] >> 3), lab);
+            if (lab >= 0) atomicMin(P.min_label + (P.slots[(long long)j * P.m.n_cells + c] >> 3), lab);
         }
     }
 }
@@ -746,7 +954,7 @@ __global__ void k_replay_choose(ReplayParams P) {
     int chosen = P.min_label[s]; // component of the first member cell in index order (cellenumerator.cpp:52-63)
     const int g = P.seed_cell[s];
     if (g >= 0 && g < P.m.n_cells) {
-        const int jj = find_member(P.n_item, P.slots, P.K + 1, g, s);
+        const int jj = find_member(P.n_item, P.slots, P.m.n_cells, g, s);
         if (jj >= 0) chosen = P.labels[(long long)g * P.K + jj]; // the nearest cell is a member: it is the seed
     }
     P.chosen[s] = chosen;
@@ -756,10 +964,9 @@ __global__ void k_replay_mark(ReplayParams P) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.m.n_cells) return;
     const int n = P.n_item[c];
-    const int *rec = P.slots + (long long)c * (P.K + 1);
-    for (int j = 0; j < n; ++j) {
+        for (int j = 0; j < n; ++j) {
         const int lab = P.labels[(long long)c * P.K + j];
-        if (lab >= 0 && lab != P.chosen[rec[1 + j] >> 3]) P.excluded[(long long)c * P.K + j] = 1;
+        if (lab >= 0 && lab != P.chosen[P.slots[(long long)j * P.m.n_cells + c] >> 3]) P.excluded[(long long)c * P.K + j] = 1;
     }
 }
 
@@ -792,9 +999,8 @@ __global__ void k_list_count(const unsigned char *n_item, const int *slots, cons
     if (c >= n_cells) return;
     int n = 0;
     const int ni = n_item[c];
-    const int *rec = slots + (long long)c * (K + 1);
     for (int j = 0; j < ni; ++j)
-        if ((rec[1 + j] & 3) != 0 && !(excluded && excluded[(long long)c * K + j])) ++n;
+        if ((slots[(long long)j * n_cells + c] & 3) != 0 && !(excluded && excluded[(long long)c * K + j])) ++n;
     cnt[c] = n;
 }
 __global__ void k_list_emit(const unsigned char *n_item, const int *slots, const unsigned char *excluded, int K, int n_cells,
@@ -803,9 +1009,8 @@ __global__ void k_list_emit(const unsigned char *n_item, const int *slots, const
     if (c >= n_cells) return;
     int o = off[c];
     const int ni = n_item[c];
-    const int *rec = slots + (long long)c * (K + 1);
     for (int j = 0; j < ni; ++j) {
-        const int e = rec[1 + j];
+        const int e = slots[(long long)j * n_cells + c];
         if ((e & 3) == 0 || (excluded && excluded[(long long)c * K + j])) continue;
         keys[o] = (unsigned)(3 * (e >> 3) + ((e & 3) - 1));
         vals[o] = c;

@@ -7,8 +7,8 @@
 // then written exactly once per cell, fully coalesced, with the per-cell sums taken in ascending
 // solid order exactly like the reference's `+=` over its solid loop — no field memsets, no field
 // atomics.  The flood fill's "face-connected component of the seed" semantics is
-// restored by a connectivity certificate kernel and, only for solids that fail it, an exact
-// label-propagation replay (all on the GPU).
+// restored by a connectivity certificate fused into the kernels and, only for solids that fail it, an
+// exact check plus label-propagation replay (all on the GPU).
 //
 // Compiled with -fmad=false: predicates are strict `<` on un-contracted fp64.
 #include <cuda_runtime.h>
@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -95,7 +96,9 @@ struct BinGrid {
 
 struct StepStatus {
     unsigned long long counts[3]; // ALL_INSIDE, CENTER_INSIDE, CENTER_OUTSIDE pairs
-    int n_flagged;                // solids with >1 certificate roots
+    int n_flagged;                // solids with >1 roots in the exact connectivity check
+    int n_suspect;                // solids with >1 members the fused certificate could not prove
+    unsigned multi_total;         // cells with a queued item and more than one slot
     int slot_overflow;            // a cell was touched by more than K solids
     int bin_overflow;             // bin list capacity exceeded
     int bad_cell;                 // a cell/face exceeded MAX_CELL_VERTS / MAX_FACE_VERTS
@@ -485,11 +488,11 @@ struct sdfibm_context {
     // per step
     DevBuf<sdfibm_solid_t> solids_in;
     DevBuf<DevSolid> solids;
-    DevBuf<int> bin_count, bin_off, bin_cursor, bin_list, global_list, root_count, slots;
+    DevBuf<int> bin_count, bin_off, bin_cursor, bin_list, global_list, root_count, unproven, slots;
     DevBuf<BinEntry> bin_entries;
-    DevBuf<double> heavy_vol;
-    DevBuf<unsigned char> n_item, heavy_type;
-    DevBuf<int2> heavy;
+    DevBuf<double2> heavy_res;
+    DevBuf<unsigned char> n_item;
+    DevBuf<int2> heavy, multi;
     DevBuf<unsigned> pair_counts;
     DevBuf<double> ft_internal;
     DevBuf<StepStatus> status;
@@ -593,8 +596,8 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
     ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
-    ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
-    ctx->bin_entries.release(); ctx->heavy_vol.release(); ctx->heavy_type.release(); ctx->n_item.release(); ctx->heavy.release();
+    ctx->global_list.release(); ctx->root_count.release(); ctx->unproven.release(); ctx->multi.release(); ctx->slots.release(); ctx->pair_counts.release();
+    ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
     ctx->ft_internal.release(); ctx->status.release(); ctx->scan_tmp.release();
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
@@ -650,13 +653,13 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     if ((rc = upload(ctx->nb_off, m->cell_cells_off, nC + 1, st))) return rc;
     if ((rc = upload(ctx->nb, m->cell_cells, (size_t)m->cell_cells_off[nC], st))) return rc;
     CUDA_TRY(ctx->cell_rad.ensure(nC));
-    CUDA_TRY(ctx->slots.ensure(nC * (ctx->K + 1)));
+    CUDA_TRY(ctx->slots.ensure(nC * ctx->K));
     CUDA_TRY(ctx->n_item.ensure(nC));
     {
         const size_t cap = std::max<size_t>(1 << 20, nC / 2);
         CUDA_TRY(ctx->heavy.ensure(cap));
-        CUDA_TRY(ctx->heavy_vol.ensure(cap));
-        CUDA_TRY(ctx->heavy_type.ensure(cap));
+        CUDA_TRY(ctx->multi.ensure(cap));
+        CUDA_TRY(ctx->heavy_res.ensure(cap));
     }
     DevMesh &d = ctx->dm;
     d.n_cells = m->n_cells; d.n_points = m->n_points; d.n_faces = m->n_faces;
@@ -791,19 +794,35 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     if (!ctx || !solids || n_solids <= 0 || !dU || !dAs || !dFs || !dTs || !dCt || !dFT)
         return fail(SDFIBM_ERR_ARG, "sdfibm_interact: null argument");
     if (!ctx->has_mesh || ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
-    if (n_solids > (1 << 29) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
+    if (n_solids > (1 << 28) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
     CUDA_TRY(cudaSetDevice(ctx->device));
     int rc = stage_solids(ctx, solids, n_solids);
     if (rc) return rc;
     ctx->launches = 0;
     rc = run_pipeline(ctx, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT, false);
     if (rc) return rc;
-    ctx->flagged_last = ctx->last.n_flagged;
+    ctx->flagged_last = 0;
     ctx->last_used_replay = false;
+    cudaStream_t st = ctx->stream;
+    const size_t nC = ctx->dm.n_cells;
+    if (ctx->last.n_suspect > 0) {
+        // the fused certificate left some solids undecided: exact root count on the final slot records
+        ConnParams C;
+        C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K;
+        C.unproven = ctx->unproven.p; C.root_count = ctx->root_count.p;
+        CUDA_TRY(cudaMemsetAsync(ctx->root_count.p, 0, sizeof(int) * n_solids, st));
+        k_connectivity<<<grid_for(nC, 256), 256, 0, st>>>(C);
+        k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts.p, ctx->root_count.p, n_solids, ctx->status.p, 1);
+        ctx->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status.p, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->last.n_flagged = ctx->h_status->n_flagged;
+        ctx->flagged_last = ctx->last.n_flagged;
+    }
     if (ctx->last.n_flagged > 0) {
         // exact flood-fill replay for the flagged solids
-        const size_t nC = ctx->dm.n_cells, K = ctx->K;
-        cudaStream_t st = ctx->stream;
+        const size_t K = ctx->K;
         CUDA_TRY(ctx->labels.ensure(nC * K));
         CUDA_TRY(ctx->excluded.ensure(nC * K));
         CUDA_TRY(ctx->seed_key.ensure(n_solids));
@@ -838,6 +857,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         k_replay_mark<<<g, 256, 0, st>>>(R);
         CUDA_TRY(cudaGetLastError());
         ctx->launches += 5;
+        // second pass of the same kernels with the pairs outside the seed's component masked out
         rc = run_pipeline(ctx, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT, true);
         if (rc) return rc;
         ctx->last_used_replay = true;
@@ -860,6 +880,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         CUDA_TRY(ctx->bin_cursor.ensure((size_t)g.n_bins));
         CUDA_TRY(ctx->global_list.ensure(n_solids));
         CUDA_TRY(ctx->root_count.ensure(n_solids));
+        CUDA_TRY(ctx->unproven.ensure(n_solids));
         CUDA_TRY(ctx->pair_counts.ensure(3 * (size_t)n_solids));
         if (ctx->bin_list.n == 0) CUDA_TRY(ctx->bin_list.ensure(std::max<size_t>(1 << 20, 128 * (size_t)n_solids)));
     }
@@ -867,7 +888,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         const BinGrid &g = ctx->grid;
         CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
         CUDA_TRY(cudaMemsetAsync(ctx->status.p, 0, sizeof(StepStatus), st));
-        CUDA_TRY(cudaMemsetAsync(ctx->root_count.p, 0, sizeof(int) * n_solids, st));
+        CUDA_TRY(cudaMemsetAsync(ctx->unproven.p, 0, sizeof(int) * n_solids, st));
         CUDA_TRY(cudaMemsetAsync(ctx->pair_counts.p, 0, sizeof(unsigned) * 3 * n_solids, st));
         CUDA_TRY(cudaMemsetAsync(dFT, 0, sizeof(double) * 6 * n_solids, st));
         if (!replay) {
@@ -900,7 +921,6 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             StepStatus keep{};
             keep.n_global = ctx->last.n_global;
             keep.bin_total = ctx->last.bin_total;
-            keep.heavy_total = ctx->last.heavy_total;
             CUDA_TRY(cudaMemcpyAsync(ctx->status.p, &keep, sizeof(StepStatus), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         }
@@ -908,34 +928,26 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.n_solids = n_solids; I.grid = g;
         I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.bin_entries = ctx->bin_entries.p; I.global_list = ctx->global_list.p; I.U = dU;
         I.dtINV = 1.0 / dt; I.rhof = rhof; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
-        I.pair_counts = ctx->pair_counts.p; I.slots = ctx->slots.p; I.K = ctx->K;
-        I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_vol = ctx->heavy_vol.p; I.heavy_type = ctx->heavy_type.p;
-        I.heavy_count = &ctx->status.p->heavy_total; I.heavy_cap = (long long)ctx->heavy.n; I.final_slots = replay ? 1 : 0;
+        I.pair_counts = ctx->pair_counts.p; I.unproven = ctx->unproven.p; I.slots = ctx->slots.p; I.K = ctx->K;
+        I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_res = ctx->heavy_res.p;
+        I.multi = ctx->multi.p;
+        I.heavy_count = &ctx->status.p->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
         I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status.p;
+        I.debug = getenv("SDFIBM_DEBUG") ? atoi(getenv("SDFIBM_DEBUG")) : 0;
         CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        if (!replay) {
-            k_classify<<<grid_for(nC, 256), 256, 0, st>>>(I);
-            CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-            const int hgrid = ctx->n_sm * HEAVY_CTAS_PER_SM;
-            if (ctx->dm.is_hex) k_heavy_hex<<<hgrid, TPB, 0, st>>>(I);
-            else k_heavy_general<<<hgrid, TPB, 0, st>>>(I);
-            ctx->launches += 2;
-        } else {
-            CUDA_TRY(cudaEventRecord(ctx->ev[2], st));   // replay re-uses the classified and evaluated slots
-        }
+        k_cells<<<grid_for(nC, 256), 256, 0, st>>>(I);
+        CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        const int hgrid = ctx->n_sm * HEAVY_CTAS_PER_SM;
+        if (ctx->dm.is_hex) k_heavy_hex<<<hgrid, TPB, 0, st>>>(I);
+        else k_heavy_general<<<hgrid, TPB, 0, st>>>(I);
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
-        k_accumulate<<<grid_for(nC, 256), 256, 0, st>>>(I);
+        if (ctx->dm.is_hex) k_finish<true><<<ctx->n_sm * 8, 256, 0, st>>>(I);
+        else k_finish<false><<<ctx->n_sm * 8, 256, 0, st>>>(I);
+        k_multi<<<ctx->n_sm * 2, TPB, 0, st>>>(I);
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
-        ++ctx->launches;
-        if (!replay) {
-            ConnParams C;
-            C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count.p;
-            k_connectivity<<<grid_for(nC, 256), 256, 0, st>>>(C);
-            ++ctx->launches;
-        }
-        k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts.p, ctx->root_count.p, n_solids, ctx->status.p);
+        k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts.p, ctx->unproven.p, n_solids, ctx->status.p, 0);
         k_scale_ft<<<grid_for(6LL * n_solids, 256), 256, 0, st>>>(dFT, 6 * n_solids, rhof);
-        ctx->launches += 2;
+        ctx->launches += 6;
         CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status.p, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
@@ -952,15 +964,14 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             ctx->t_ms[5] = add * ctx->t_ms[5] + d;
         }
         {
-            const StepStatus prev = ctx->last;
             ctx->last = *ctx->h_status;
-            if (replay) { ctx->last.n_flagged = (int)ctx->flagged_last; ctx->last.heavy_total = prev.heavy_total; }
+            if (replay) { ctx->last.n_flagged = (int)ctx->flagged_last; ctx->last.n_suspect = 0; }
         }
-        if (!replay && ctx->last.heavy_total > (unsigned long long)ctx->heavy.n && attempt == 0) {
+        if (ctx->last.heavy_total > (unsigned long long)ctx->heavy.n && attempt == 0) {
             const size_t cap = (size_t)(ctx->last.heavy_total + ctx->last.heavy_total / 4 + 1024);
             CUDA_TRY(ctx->heavy.ensure(cap));
-            CUDA_TRY(ctx->heavy_vol.ensure(cap));
-            CUDA_TRY(ctx->heavy_type.ensure(cap));
+            CUDA_TRY(ctx->multi.ensure(cap));
+            CUDA_TRY(ctx->heavy_res.ensure(cap));
             continue;
         }
         if (ctx->last.bin_overflow && !replay && attempt == 0) {
@@ -973,6 +984,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
     if (ctx->last.bad_cell) return fail(SDFIBM_ERR_UNSUPPORTED, "cell with more than 32 vertices");
     if (ctx->last.slot_overflow)
         return fail(SDFIBM_ERR_CAPACITY, "more solids touch one cell than the slot count; raise it with sdfibm_set_cell_slots");
+    if (ctx->last.heavy_total > (unsigned long long)ctx->heavy.n) return fail(SDFIBM_ERR_CAPACITY, "exact-evaluation queue overflow");
     return SDFIBM_OK;
 }
 
