@@ -247,7 +247,7 @@ def main():
                 fn()
                 t = ctx.last_timings()
                 kern_ms.append(t["interact_kernels_ms"])
-                split.append((t["cells_ms"], t["heavy_ms"], t["multi_ms"], t["finalize_ms"], t["binning_ms"]))
+                split.append((t["classify_ms"], t["heavy_ms"], t["final_ms"], t["connectivity_ms"], t["binning_ms"]))
                 pipe_ms.append(t["pipeline_ms"])
             e1.record(ext)
             barrier()
@@ -317,11 +317,11 @@ def main():
                            l2="inputs larger than L2 (fields + mesh arrays of one step >> 126 MB); no explicit flush"),
             "clocks": clocks,
             "gpu_launches": int(launches_per_step * args.steps),
-            "kernel_ms": {"k_cells": split_mean[0], "k_heavy": split_mean[1], "k_multi": split_mean[2],
-                          "finalise": split_mean[3], "solid_binning": split_mean[4],
+            "kernel_ms": {"k_classify": split_mean[0], "k_heavy": split_mean[1], "k_final": split_mean[2],
+                          "k_connectivity+finalise": split_mean[3], "solid_binning": split_mean[4],
                           "interact_kernels": kern_ms, "pipeline_device": pipe_ms, "step_wall_on_stream": ms_per_step,
                           "heavy_items": stats["heavy_items"]},
-            "roofline": {"bound": "hbm", "kernel": "k_cells+k_heavy+k_multi (the interact kernels; k_heavy dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_classify+k_heavy+k_final (the interact kernels; k_heavy dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg),
                          "formula": "48*nCells + 112*P + 216*P_b + 176*N (SURVEY.md 8d), rank 0"},

@@ -158,7 +158,8 @@ int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells
  * entries, [3] (cell, solid) items that needed exact vertex evaluation. */
 int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]);
 /* device time (CUDA events on the context stream) of the last interact, in ms:
- * [0] solid preparation + binning, [1] k_cells, [2] k_heavy, [3] k_multi, [4] finalise, [5] whole pipeline */
+ * [0] solid preparation + binning, [1] k_classify, [2] k_heavy, [3] k_final, [4] connectivity + finalise,
+ * [5] whole pipeline */
 int sdfibm_last_timings(sdfibm_context *ctx, double ms[6]);
 
 /* ---- collision step (solidcloud.cpp:477-519, libcollision/) -------------------------

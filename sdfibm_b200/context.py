@@ -103,7 +103,7 @@ class Context:
     def last_timings(self):
         t = (C.c_double * 6)()
         capi.check(self._lib.sdfibm_last_timings(self._h, t))
-        return dict(binning_ms=t[0], cells_ms=t[1], heavy_ms=t[2], multi_ms=t[3], finalize_ms=t[4],
+        return dict(binning_ms=t[0], classify_ms=t[1], heavy_ms=t[2], final_ms=t[3], connectivity_ms=t[4],
                     pipeline_ms=t[5], interact_kernels_ms=t[1] + t[2] + t[3])
 
     def stream_ptr(self) -> int:

@@ -1,28 +1,24 @@
 // interact_kernels.cuh — the sm_100a kernels of SolidCloud::interact / fixInternal.
 // Included by sdfibm_cuda.cu after the device records (DevMesh, DevSolid, DevShape, BinGrid, StepStatus).
 //
-//   k_cells         thread per cell   candidate solids (ascending id) -> per-cell slot record.  Cells whose members are all
-//                                     certainly ALL_INSIDE (or that have none) are FINAL here: As/Fs/Ts/Ct written once,
-//                                     coalesced, in the reference's += order.  Pairs whose vertices must be evaluated
-//                                     exactly are appended to a dense global queue.
-//   k_heavy         lane per item     exact vertex predicates + SDF, cell type, apex/pyramid volume; a cell whose only slot is
-//                                     this item is FINAL here (forcing fused into the evaluation kernel)
-//   k_multi         thread per cell   the few cells touched by several solids with a queued item: summed in slot order
-//   (all three)                       per-solid force/torque warp-aggregated before the atomics; connectivity certificate
-//   k_connectivity  thread per cell   exact connectivity check, only when the fused certificate leaves a solid undecided
+//   k_classify      thread per cell   candidate solids (ascending id) -> per-cell slot record; pairs whose vertices must be
+//                                     evaluated exactly are appended to a dense global queue (block-aggregated: one atomic per CTA)
+//   k_heavy         lane per item     exact vertex predicates + SDF, cell type, apex/pyramid volume (dense, no barriers)
+//   k_final         thread per cell   As/Fs/Ts/Ct in the reference's += order, every cell written exactly once in full,
+//                                     coalesced sectors; per-solid force/torque warp-aggregated before the atomics
+//   k_connectivity  thread per cell   certificate that each solid's cell set is one face-connected component
 //   k_replay_*                        exact flood-fill component selection for solids that fail it (rare)
 //   k_fix_internal  thread per cell   SolidCloud::fixInternal
 //   k_list_*                          candidate-list extraction for parity (off the timed path)
 //
-// Slot records: slots[j * n_cells + c], j < n_item[c] <= K, = (solid << 3) | (queued ? 4 : 0) | type.  type is the
-// CELL_TYPE (1,2,3) or 0 (no vertex inside: not a member; queued slots carry 0 until their item is evaluated).  Queue
-// items of a cell are consecutive, in slot (= ascending solid id) order.
+// Slot records: slots[j * n_cells + c], j < n_item[c] <= K.  After k_classify a slot is (solid << 3) | ALL_INSIDE for a
+// pair the pre-classification proved inside, or (queue index << 3) | 4 for a queued pair.  k_final rewrites every slot
+// as (solid << 3) | (queued ? 4 : 0) | type with the final CELL_TYPE (1,2,3) or 0 (no vertex inside: not a member).
 #pragma once
 
 #define TPB 128
 #define SLOT_HEAVY 4
-#define ITEM_MULTI 0x40000000
-#define ENT_STAGE 48   // candidate records staged per warp in k_cells
+#define ENT_STAGE 48   // candidate records staged per warp in k_classify
 
 // ------------------------------------------------------------------------------------------------
 // geometry: apex / pyramid volume fraction (reference src/geometrictools.cpp:13-116)
@@ -125,7 +121,7 @@ __device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad)
 }
 
 // ------------------------------------------------------------------------------------------------
-// parameters shared by the cells / heavy / multi kernels
+// parameters shared by the classify / heavy / final kernels
 // ------------------------------------------------------------------------------------------------
 // one candidate of a solid bin: what the sphere-type pre-classification needs, inline
 struct BinEntry {
@@ -150,18 +146,15 @@ struct InteractParams {
     double *As, *Fs, *Ts, *Ct;
     double *force_torque;   // [6*n_solids], zeroed
     unsigned *pair_counts;  // [3*n_solids], zeroed
-    int *unproven;          // [n_solids], zeroed: members for which no smaller-key member neighbour was proven
     int *slots;             // [K][n_cells] slot records (see file header)
     unsigned char *n_item;  // [n_cells] slots in use
-    int2 *heavy;            // queue of (cell, solid | ITEM_MULTI) needing exact evaluation
-    double2 *heavy_res;     // [queue] per item: (solid volume inside the cell, bits: CELL_TYPE | vertex-inside mask << 8)
-    int2 *multi;            // queue of (cell, first heavy item) for cells with a heavy item and more than one slot
+    int2 *heavy;            // queue of (cell, solid) needing exact evaluation
+    double2 *heavy_res;     // [queue] per item: (solid volume inside the cell, bits: CELL_TYPE | solid << 2)
     unsigned long long *heavy_count;
     long long heavy_cap;
     int K;
     const unsigned char *excluded; // replay pass: [n_cells*K] 1 = pair is outside the seed's component
     StepStatus *status;
-    int debug;              // timing experiments only (SDFIBM_DEBUG): skip parts of the work
 };
 
 __device__ __forceinline__ float2 cell_radius(const DevMesh &m, int c) { return m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c); }
@@ -229,33 +222,10 @@ __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// connectivity certificate.  A member pair (c, s) is "proven" when one face neighbour with a smaller
-// (distance-to-centre, cell id) key is CERTAINLY a member of s.  If at most one member of a solid is
-// unproven, its vertex-inside cell set is one face-connected component (follow the proven parents: keys
-// strictly decrease, so every chain ends in the single unproven cell)  =>  it equals the reference's flood
-// fill from any seed.  Solids with more unproven members go through the exact check
-// (k_connectivity) and, if that fails too, the flood-fill replay.
+// k_classify: thread per mesh cell
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool key_less(double ka, int ca, double kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
-
-// neighbour certainly ALL_INSIDE (its whole vertex cloud lies inside the certified inner radius)
-__device__ __forceinline__ bool proven_by_inner_neighbour(const DevMesh &m, const DevSolid &S, int c, D3 cc) {
-    const D3 x = {S.pos[0], S.pos[1], S.pos[2]};
-    const double kc = magSqr3(cc - x);
-    const int nb0 = __ldg(m.nb_off + c), nb1 = __ldg(m.nb_off + c + 1);
-    for (int k = nb0; k < nb1; ++k) {
-        const int nb = __ldg(m.nb + k);
-        const D3 ccn = ld3(m.cc, nb);
-        if (!key_less(magSqr3(ccn - x), nb, kc, c)) continue;
-        if (quick_class(S, ccn, cell_radius(m, nb)) == 1) return true;
-    }
-    return false;
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_cells: thread per mesh cell
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cells(InteractParams P) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_classify(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,79 +308,37 @@ __global__ void __launch_bounds__(256) k_cells(InteractParams P) {
         }
         P.n_item[c] = (unsigned char)n_item;
     }
-    // ---- warp-aggregated append of the heavy items to the global queue (one atomic per warp) ----
-    const bool is_multi = n_heavy > 0 && n_item > 1;
-    {
-        int incl = n_heavy;
+    // ---- block-aggregated append of the queued pairs to the global queue: ONE atomic on the queue counter per CTA
+    //      (a per-warp atomic serialises ~3e5 same-address operations at C4 and bounds the whole kernel) ----
+    int incl = n_heavy;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(FULL, incl, 31);
-        if (total > 0) {
-            unsigned long long base = 0;
-            if (lane == 31) base = atomicAdd(P.heavy_count, (unsigned long long)total);
-            base = __shfl_sync(FULL, base, 31);
-            long long pos = (long long)base + incl - n_heavy;
-            const unsigned mm = __ballot_sync(FULL, is_multi);
-            if (mm) {
-                unsigned mbase = 0;
-                const int mlead = __ffs(mm) - 1;
-                if (lane == mlead) mbase = atomicAdd(&P.status->multi_total, (unsigned)__popc(mm));
-                mbase = __shfl_sync(FULL, mbase, mlead);
-                const long long mpos = (long long)mbase + __popc(mm & ((1u << lane) - 1u));
-                if (is_multi && mpos < P.heavy_cap) P.multi[mpos] = make_int2(c, (int)pos);
-            }
-            for (int j = 0; j < n_item && n_heavy > 0; ++j) {
-                const int e = P.slots[(long long)j * nC + c];
-                if (e & SLOT_HEAVY) {
-                    if (pos < P.heavy_cap) P.heavy[pos] = make_int2(c, (e >> 3) | (is_multi ? ITEM_MULTI : 0));
-                    ++pos;
-                }
-            }
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
     }
-    // ---- cells without a heavy item are final here: every member is ALL_INSIDE with alpha = 1 ----
-    const bool fin = live && n_heavy == 0;
-    const int nl = (fin && !(P.debug & 2)) ? n_item : 0;
-    int nmax = nl;
+    __shared__ int s_wtot[8];
+    __shared__ unsigned long long s_base;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-    double as = 0.0, ts = 0.0, ct = 0.0;
-    D3 fs = {0.0, 0.0, 0.0};
-    if (nmax > 0) {
-        D3 uf = {0.0, 0.0, 0.0};
-        double vol = 1.0;
-        if (nl > 0) {
-            uf = ld3(P.U, c);
-            vol = __ldg(m.V + c);
-        }
-        for (int j = 0; j < nmax; ++j) {
-            bool have = false;
-            int s = -1;
-            double contrib[6] = {0, 0, 0, 0, 0, 0};
-            if (j < nl && !(P.excluded && P.excluded[(long long)c * P.K + j])) {
-                s = P.slots[(long long)j * nC + c] >> 3;
-                D3 fi;
-                pair_terms(P.solids[s], cc, uf, vol, 1.0, P.dtINV, fi, contrib);     // solidcloud.cpp:408-421, alpha = 1
-                as += 1.0;
-                fs = fs + fi;
-                ts += 1.0;
-                ct = (double)(s + 4);                                                // :376-382, last writer wins
-                have = true;
-            }
-            if (__any_sync(FULL, have)) warp_accumulate(have, s, SDFIBM_CELL_ALL_INSIDE, contrib, P.force_torque, P.pair_counts);
-        }
+        for (int w = 0; w < 8; ++w) { const int t = s_wtot[w]; s_wtot[w] = tot; tot += t; }
+        s_base = tot ? atomicAdd(P.heavy_count, (unsigned long long)tot) : 0ull;
     }
-    if (fin) store_cell(P, c, as, fs, ts, ct);
-    // ---- connectivity certificate of the ALL_INSIDE members found by the pre-classification ----
+    __syncthreads();
+    if (n_heavy == 0) return;
+    long long pos = (long long)s_base + s_wtot[warp] + incl - n_heavy;
     for (int j = 0; j < n_item; ++j) {
         const int e = P.slots[(long long)j * nC + c];
-        if (e & SLOT_HEAVY) continue;
-        if (P.excluded || (P.debug & 1)) continue;   // replay pass: the certificate is not consulted
-        const int s = e >> 3;
-        if (!proven_by_inner_neighbour(m, P.solids[s], c, cc)) atomicAdd(P.unproven + s, 1);
+        if (e & SLOT_HEAVY) {
+            if (pos < P.heavy_cap) {
+                P.heavy[pos] = make_int2(c, e >> 3);
+                P.slots[(long long)j * nC + c] = ((int)pos << 3) | SLOT_HEAVY;     // the slot now points at its queue item
+            }
+            ++pos;
+        }
     }
 }
 
@@ -418,7 +346,7 @@ __global__ void __launch_bounds__(256) k_cells(InteractParams P) {
 // k_heavy: exact evaluation of one (cell, solid) item
 // ------------------------------------------------------------------------------------------------
 // General polyhedra: cell-local arrays in local memory, CSR connectivity.
-__device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out, unsigned &inmask) {
+__device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out) {
     const DevMesh &m = P.m;
     const DevSolid &S = P.solids[s];
     const DevShape &sh = P.shapes[S.shape];
@@ -431,21 +359,19 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
     int nv = __ldg(m.cp_off + c + 1) - pb;
     if (nv > MAX_CELL_VERTS) { nv = MAX_CELL_VERTS; P.status->bad_cell = 1; }
     int n_in = 0;
-    inmask = 0;
     for (int k = 0; k < nv; ++k) {
         vid[k] = __ldg(m.cp + pb + k);
         pts[k] = ld3(m.points, vid[k]);
         double ph;
-        if (shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph)) { ++n_in; inmask |= 1u << k; }
+        n_in += shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph) ? 1 : 0;
         phi[k] = ph;
     }
     type_out = 0;
     vol_out = 0.0;
     if (n_in == 0) return;
-    const D3 cc = ld3(m.cc, c);
     if (n_in == nv) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
     double dummy;
-    type_out = shape_eval<false>(sh.s, world2local(q, t, cc), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
     vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
 }
 
@@ -483,7 +409,8 @@ __device__ __forceinline__ void eval_vertex_to_smem(HeavySmem &sm, const DevMesh
 }
 
 #define HEAVY_CTAS_PER_SM 5
-__global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractParams P) {
+template <int CTAS, bool PREFETCH>
+__global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     __shared__ HeavySmem sm;
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
@@ -492,7 +419,7 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
     for (long long k0 = (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
         const long long k = k0 + lane;
         const bool valid = k < n;
-        int c = -1, s = -1, s_raw = 0;
+        int c = -1, s = -1;
         int vid[8] = {-1, -2, -3, -4, -5, -6, -7, -8};
         DQ q = {1.0, {0.0, 0.0, 0.0}};
         D3 t = {0.0, 0.0, 0.0};
@@ -502,8 +429,7 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
         if (valid) {
             const int2 it = __ldg(P.heavy + k);
             c = it.x;
-            s_raw = it.y;
-            s = s_raw & ~ITEM_MULTI;
+            s = it.y;
             const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
             const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
             vid[0] = va.x; vid[1] = va.y; vid[2] = va.z; vid[3] = va.w;
@@ -518,6 +444,16 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
             tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
             const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
             f01 = __ldg(cf2); f23 = __ldg(cf2 + 1); f45 = __ldg(cf2 + 2);
+            if (PREFETCH) {   // face records are consumed by the volume phase, long after the vertex phase: pull them into L2 now
+                const int fid[6] = {f01.x, f01.y, f23.x, f23.y, f45.x, f45.y};
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    const char *ptr = reinterpret_cast<const char *>(m.face_rec + 4 * (long long)fid[f]);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 32));
+                }
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(m.cc + 3 * (long long)c));
+            }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) sm.vid[j * TPB + tid] = vid[j];
@@ -546,7 +482,7 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
             if (work) {
                 const int kk = 2 * (u & 3);
                 const int col = wbase + src;
-                const int s_src = __ldg(&P.heavy[k0 + src].y) & ~ITEM_MULTI;
+                const int s_src = __ldg(&P.heavy[k0 + src].y);
                 const DevSolid &S2 = P.solids[s_src];
                 const DQ q2 = {S2.q[0], {S2.q[1], S2.q[2], S2.q[3]}};
                 const D3 t2 = {S2.pos[0], S2.pos[1], S2.pos[2]};
@@ -558,13 +494,8 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
             int type = 0;
             double volume = 0.0;
             int n_in = 0;
-            unsigned inmask = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const unsigned b = sm.in[j * TPB + tid];
-                n_in += b;
-                inmask |= b << j;
-            }
+            for (int j = 0; j < 8; ++j) n_in += sm.in[j * TPB + tid];
             if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
             else if (n_in != 0) {
                 double dummy;
@@ -624,7 +555,7 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
                     volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
                 }
             }
-            P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (inmask << 8))));
+            P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));   // type 0: no vertex inside -> not a member
         }
         __syncwarp();
     }
@@ -633,157 +564,77 @@ __global__ void __launch_bounds__(TPB, HEAVY_CTAS_PER_SM) k_heavy_hex(InteractPa
 __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
     for (long long k = (long long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long long)gridDim.x * TPB) {
-        const int2 it = __ldg(P.heavy + k); // (cell, solid | ITEM_MULTI)
+        const int2 it = __ldg(P.heavy + k); // (cell, solid)
         int type;
         double v;
-        unsigned inmask;
-        heavy_eval_general(P, it.x, it.y & ~ITEM_MULTI, type, v, inmask);
-        P.heavy_res[k] = make_double2(v, __longlong_as_double((long long)type | ((long long)inmask << 8)));
+        heavy_eval_general(P, it.x, it.y, type, v);
+        P.heavy_res[k] = make_double2(v, __longlong_as_double((long long)(type | (it.y << 2))));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_finish: thread per evaluated item, full occupancy.  A cell whose only slot is this item is FINAL here
-// (forcing fused with the hand-over of the evaluation result); every member item gets its connectivity
-// certificate: a smaller-key face neighbour that is certainly ALL_INSIDE, or that shares a vertex the exact
-// predicate found inside (such a neighbour has >= 1 vertex inside, i.e. it is a member).
+// k_final: thread per cell, every output sector written exactly once and in full.
 // ------------------------------------------------------------------------------------------------
-template <bool HEX>
-__device__ __forceinline__ bool proven_by_shared_vertex(const DevMesh &m, const DevSolid &S, int c, D3 cc, unsigned inmask) {
-    const D3 x = {S.pos[0], S.pos[1], S.pos[2]};
-    const double kc = magSqr3(cc - x);
-    const int nb0 = __ldg(m.nb_off + c), nb1 = __ldg(m.nb_off + c + 1);
-    const int pc = HEX ? 8 * c : __ldg(m.cp_off + c);
-    const int nvc = HEX ? 8 : __ldg(m.cp_off + c + 1) - pc;
-    for (int k = nb0; k < nb1; ++k) {
-        const int nb = __ldg(m.nb + k);
-        const D3 ccn = ld3(m.cc, nb);
-        if (!key_less(magSqr3(ccn - x), nb, kc, c)) continue;
-        if (quick_class(S, ccn, cell_radius(m, nb)) == 1) return true;
-        const int pb = HEX ? 8 * nb : __ldg(m.cp_off + nb);
-        const int nvn = HEX ? 8 : __ldg(m.cp_off + nb + 1) - pb;
-        for (int j = 0; j < nvc; ++j) {
-            if (!((inmask >> j) & 1u)) continue;
-            const int v = __ldg(m.cp + pc + j);
-            for (int i = 0; i < nvn; ++i)
-                if (__ldg(m.cp + pb + i) == v) return true;
-        }
-    }
-    return false;
-}
-
-template <bool HEX>
-__global__ void __launch_bounds__(256) k_finish(InteractParams P) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
     const DevMesh &m = P.m;
-    const unsigned FULL = 0xffffffffu;
-    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
-    for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < n; k0 += (long long)gridDim.x * blockDim.x) {
-        const long long k = k0 + threadIdx.x;
-        bool have = false;
-        int type = 0, s = -1;
-        double contrib[6] = {0, 0, 0, 0, 0, 0};
-        if (k < n) {
-            const int2 it = __ldg(P.heavy + k);
-            const int c = it.x;
-            s = it.y & ~ITEM_MULTI;
-            const double2 r = P.heavy_res[k];
-            const long long bits = __double_as_longlong(r.y);
-            type = (int)(bits & 3);
-            const unsigned inmask = (unsigned)(bits >> 8);
-            D3 cc = {0.0, 0.0, 0.0};
-            if (type != 0) cc = ld3(m.cc, c);
-            if (!(it.y & ITEM_MULTI)) {      // otherwise k_multi sums the cell's slots in order
-                double as = 0.0, ts = 0.0, ct = 0.0;
-                D3 fs = {0.0, 0.0, 0.0};
-                const bool skip = P.excluded && P.excluded[(long long)c * P.K];
-                if (type != 0 && !skip) {
-                    const double vol = __ldg(m.V + c);
-                    const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : r.x / vol;     // solidcloud.cpp:408-410
-                    D3 fi;
-                    pair_terms(P.solids[s], cc, ld3(P.U, c), vol, alpha, P.dtINV, fi, contrib);
-                    as += alpha;
-                    fs = fs + fi;
-                    ts += alpha;
-                    ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;      // :376-382
-                    have = true;
-                }
-                store_cell(P, c, as, fs, ts, ct);
-                P.slots[c] = (s << 3) | SLOT_HEAVY | type;                                       // slot 0 now carries the final type
-            }
-            if (type != 0 && !P.excluded && !(P.debug & 4) && !proven_by_shared_vertex<HEX>(m, P.solids[s], c, cc, inmask))
-                atomicAdd(P.unproven + s, 1);
-        }
-        if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_multi: cells touched by several solids of which at least one needed exact evaluation — the per-cell
-// sums are taken in slot (= ascending solid = the reference's `+=`) order, one thread per such cell.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_multi(InteractParams P) {
-    const DevMesh &m = P.m;
-    const unsigned FULL = 0xffffffffu;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < m.n_cells;
     const long long nC = m.n_cells;
-    const long long n = min((long long)P.status->multi_total, P.heavy_cap);
-    for (long long i0 = (long long)blockIdx.x * TPB; i0 < n; i0 += (long long)gridDim.x * TPB) {
-        const long long i = i0 + threadIdx.x;
-        const bool valid = i < n;
-        int c = 0, nI = 0;
-        long long hk = 0;
+    const int n = live ? (int)P.n_item[c] : 0;
+    const int e0 = live ? P.slots[c] : 0;       // slot 0, fetched together with n_item (meaningless when n == 0)
+    const unsigned FULL = 0xffffffffu;
+    int nmax = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+
+    double as = 0.0, ts = 0.0, ct = 0.0;
+    D3 fs = {0.0, 0.0, 0.0};
+    if (nmax > 0) {
         D3 cc = {0, 0, 0}, uf = {0, 0, 0};
         double vol = 1.0;
-        if (valid) {
-            const int2 e = __ldg(P.multi + i);
-            c = e.x;
-            hk = e.y;
-            nI = P.n_item[c];
+        if (n > 0) {
             cc = ld3(m.cc, c);
             uf = ld3(P.U, c);
             vol = __ldg(m.V + c);
         }
-        int nmax = nI;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-        double as = 0.0, ts = 0.0, ct = 0.0;
-        D3 fs = {0.0, 0.0, 0.0};
         for (int j = 0; j < nmax; ++j) {
             bool have = false;
             int s = -1, type = 0;
             double contrib[6] = {0, 0, 0, 0, 0, 0};
-            if (j < nI) {
-                const int e = P.slots[(long long)j * nC + c];
+            if (j < n) {
+                const int e = (j == 0) ? e0 : P.slots[(long long)j * nC + c];
                 s = e >> 3;
                 type = e & 3;
                 double v = 0.0;
-                if (e & SLOT_HEAVY) {
-                    const double2 r = P.heavy_res[hk];
-                    type = (int)(__double_as_longlong(r.y) & 3);
-                    P.slots[(long long)j * nC + c] = (e & ~3) | type;               // the slot now carries the final type
-                    if (type > SDFIBM_CELL_ALL_INSIDE) v = r.x;
-                    ++hk;
+                if (e & SLOT_HEAVY) {                                           // the slot points at its queue item
+                    const double2 r = P.heavy_res[e >> 3];
+                    const int bits = (int)__double_as_longlong(r.y);
+                    type = bits & 3;
+                    s = bits >> 2;
+                    v = r.x;
+                    P.slots[(long long)j * nC + c] = (s << 3) | SLOT_HEAVY | type;   // final record
                 }
                 const bool skip = P.excluded && P.excluded[(long long)c * P.K + j]; // replay: outside the seed's component
                 if (type != 0 && !skip) {
                     const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol;   // solidcloud.cpp:408-410
                     D3 fi;
-                    pair_terms(P.solids[s], cc, uf, vol, alpha, P.dtINV, fi, contrib);
+                    pair_terms(P.solids[s], cc, uf, vol, alpha, P.dtINV, fi, contrib);   // :384-390,411-421
                     as += alpha;
                     fs = fs + fi;
                     ts += alpha;
-                    ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;  // :376-382, last writer wins
+                    ct = (type == SDFIBM_CELL_ALL_INSIDE) ? (double)(s + 4) : (double)type;   // :376-382, last writer wins
                     have = true;
                 }
             }
             if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
         }
-        if (valid) store_cell(P, c, as, fs, ts, ct);
     }
+    if (live) store_cell(P, c, as, fs, ts, ct);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_connectivity (exact check, only launched when a solid has more than one unproven member): a member pair
-// is a "root" when no face neighbour that is a member of the same solid has a smaller key.  Exactly one
+// k_connectivity: a member pair is a "root" when no face neighbour that is a member of the same solid has a smaller key.  Exactly one
 // root  =>  the solid's vertex-inside cell set is face connected.
 // ------------------------------------------------------------------------------------------------
 struct ConnParams {
@@ -792,9 +643,10 @@ struct ConnParams {
     const unsigned char *n_item;
     const int *slots;
     int K;
-    const int *unproven;
     int *root_count; // [n_solids] zeroed
 };
+
+__device__ __forceinline__ bool key_less(double ka, int ca, double kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
 
 // slot index of solid s among the members of cell nb, or -1
 __device__ __forceinline__ int find_member(const unsigned char *n_item, const int *slots, long long nC, int nb, int s) {
@@ -818,7 +670,6 @@ __global__ void k_connectivity(ConnParams P) {
         const int e = P.slots[(long long)j * nC + c];
         if ((e & 3) == 0) continue;
         const int s = e >> 3;
-        if (P.unproven[s] <= 1) continue;          // already certified
         const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
         const double kc = magSqr3(cc - x);
         bool has_parent = false;
@@ -833,18 +684,14 @@ __global__ void k_connectivity(ConnParams P) {
     }
 }
 
-// totals of the per-solid counters; mode 0: pair counts + solids with more than one unproven member,
-// mode 1: solids with more than one root (after the exact check)
-__global__ void k_finalize(const unsigned *pair_counts, const int *per_solid, int n_solids, StepStatus *status, int mode) {
+__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status) {
     unsigned long long c0 = 0, c1 = 0, c2 = 0;
     int nf = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_solids; s += gridDim.x * blockDim.x) {
-        if (mode == 0) {
-            c0 += pair_counts[3 * s];
-            c1 += pair_counts[3 * s + 1];
-            c2 += pair_counts[3 * s + 2];
-        }
-        nf += per_solid[s] > 1;
+        c0 += pair_counts[3 * s];
+        c1 += pair_counts[3 * s + 1];
+        c2 += pair_counts[3 * s + 2];
+        nf += root_count[s] > 1;
     }
     for (int o = 16; o > 0; o >>= 1) {
         c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -856,7 +703,7 @@ __global__ void k_finalize(const unsigned *pair_counts, const int *per_solid, in
         if (c0) atomicAdd(&status->counts[0], c0);
         if (c1) atomicAdd(&status->counts[1], c1);
         if (c2) atomicAdd(&status->counts[2], c2);
-        if (nf) atomicAdd(mode == 0 ? &status->n_suspect : &status->n_flagged, nf);
+        if (nf) atomicAdd(&status->n_flagged, nf);
     }
 }
 
