@@ -47,6 +47,37 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libsdfibm_host.so")
+HOST_DIR = os.path.join(HERE, "host")
+HOST_SOURCES = [os.path.join(HOST_DIR, "solidcloud.cpp"), os.path.join(HOST_DIR, "capi_host.cpp")]
+RUNNER = os.path.join(HERE, "sdfibm_b200_run")
+
+
+def _host_deps():
+    deps = [os.path.join(ROOT, "include", "sdfibm_b200_host.h"), os.path.join(ROOT, "include", "sdfibm_b200.h"),
+            os.path.join(HERE, "csrc", "device_math.cuh"), LIB]
+    for d, _, files in os.walk(HOST_DIR):
+        deps += [os.path.join(d, f) for f in files if f.endswith((".h", ".cpp", ".H"))]
+    return deps
+
+
+def build_host(force: bool = False) -> str:
+    """Host façade (C++17, g++): libsdfibm_host.so + the stand-alone runner, linked against the CUDA library."""
+    outs = [HOST_LIB, RUNNER]
+    if not force and all(os.path.exists(o) for o in outs):
+        t = min(os.path.getmtime(o) for o in outs)
+        if all(os.path.getmtime(d) <= t for d in _host_deps()):
+            return HOST_LIB
+    common = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-Wall"]
+    link = ["-L" + HERE, "-lsdfibm_b200", "-Wl,-rpath,$ORIGIN"]
+    for cmd in (common + ["-shared", "-o", HOST_LIB] + HOST_SOURCES + link,
+                common + ["-o", RUNNER, os.path.join(HOST_DIR, "standalone_main.cpp")] + HOST_SOURCES + link):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return HOST_LIB
+
+
 def build_oracle(force: bool = False) -> str:
     d = os.path.join(ROOT, "oracle")
     lib = os.path.join(d, "liboracle.so")
@@ -61,4 +92,5 @@ def build_oracle(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))
     print(build_oracle(force="--force" in sys.argv))

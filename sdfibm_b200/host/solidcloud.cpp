@@ -1,0 +1,342 @@
+// solidcloud.cpp — host façade over the C ABI (see solidcloud.h).  Statement order follows the reference's
+// src/solidcloud.cpp so the two read side by side; line numbers in comments refer to it.
+#define SDFIBM_REGISTER_BUILTINS
+#include "solidcloud.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <ctime>
+#include <iomanip>
+#include <sstream>
+#include <stdexcept>
+
+#include "../../include/sdfibm_b200.h"
+#include "libmotion/motions.h"
+#include "libshape/shapefactory.h"
+
+namespace sdfibm {
+
+label SolidCloud::N_SUBITER = 20;
+
+namespace {
+void check(int rc, const char *what) {
+    if (rc != SDFIBM_OK) throw std::runtime_error(std::string(what) + ": " + sdfibm_last_error());
+}
+#ifndef SDFIBM_WITH_OPENFOAM
+// Foam-free field / mesh access; foam_adapter.H provides the same four functions for OpenFOAM objects
+inline double *cellData(Foam::volScalarField &f) { return f.data(); }
+inline double *cellData(Foam::volVectorField &f) { return f.data(); }
+inline const sdfibm_mesh_t &meshView(const Foam::fvMesh &m) { return m.view(); }
+inline scalar transportRho(const Foam::fvMesh &m) { return m.transportRho(); }
+inline scalar meshTime(const Foam::fvMesh &m) { return m.timeValue(); }
+inline std::string casePath(const Foam::fvMesh &m, const std::string &f) { return m.caseDir() + "/" + f; }
+inline bool isMaster() { return true; }
+#endif
+} // namespace
+
+void SolidCloud::log(const std::string &msg) {
+    if (isMaster() && logfile) logfile << msg << std::endl;
+}
+
+void SolidCloud::initFromDictionary(const Foam::word &dictfile) {   // :14-206
+    dictionary root = dictionary::fromFile(dictfile);
+    root.remove("FoamFile");   // OpenFOAM drops the header entry when reading a dictionary file
+    log("Init from " + dictfile);
+
+    const dictionary &meta = root.subDict("meta");
+    m_ON_FLUID = Foam::readBool(meta.lookup("on_fluid"));
+    m_ON_TWOD = Foam::readBool(meta.lookup("on_twod"));
+    if (meta.found("on_meanfield") || meta.found("sampler"))
+        log("note: the mean-field sampler (src/solidcloud.cpp:303-359) is outside the GPU path and is ignored");
+    m_gravity = meta.lookup("gravity");
+    m_writeFrequency = (unsigned)meta.lookupOrDefault("writeFrequency", (label)1);
+    if (meta.found("collision_delta")) m_collisionDelta = Foam::readScalar(meta.lookup("collision_delta"));
+    {
+        std::ostringstream msg;
+        msg << "Summary: " << (m_ON_TWOD ? "2D" : "3D") << ' ' << (m_ON_FLUID ? "FSI" : "DEM (fluid disabled)") << ", g = ("
+            << m_gravity[0] << ' ' << m_gravity[1] << ' ' << m_gravity[2] << ").";
+        log(msg.str());
+    }
+
+    // shapes, forces, motions, materials: any failure is fatal, as in the reference (:146-154) — but reported by
+    // exception, never exit(), so an embedding application decides
+    m_libshape = EntityLibrary<IShape>(root.subDict("shapes"));
+    m_radiusB = -1.0;   // :74-75
+    if (root.found("forces")) m_libforcer = EntityLibrary<forcer::IForcer>(root.subDict("forces"));
+
+    const dictionary &motions = root.subDict("motions");
+    for (const auto &key : motions.toc()) {
+        const dictionary &para = motions.subDict(key);
+        const std::string type = Foam::word(para.lookup("type"));
+        const std::string name = Foam::word(para.lookup("name"));
+        m_libmotion[name] = MotionFactory::create(type, para);
+        if (m_libmotion[name] == nullptr) throw std::runtime_error("Unrecognized motion type " + type + '\n');
+    }
+    const dictionary &materials = root.subDict("materials");
+    for (const auto &key : materials.toc()) {
+        const dictionary &para = materials.subDict(key);
+        const std::string type = Foam::word(para.lookup("type"));
+        if (type != "General") throw std::runtime_error("Unrecognizable material parameter!");
+        const scalar rho = Foam::readScalar(para.lookup("rho"));
+        m_libmat[Foam::word(para.lookup("name"))] = new IMaterial(rho);
+    }
+
+    const dictionary &solids = root.subDict("solids");
+    const auto names = solids.toc();
+    for (size_t i = 0; i < names.size(); ++i) {
+        const dictionary &solid = solids.subDict(names[i]);
+        const vector pos = solid.lookup("pos");
+        if (m_ON_TWOD && pos.z() != 0)
+            throw std::runtime_error("Solid must has z=0 in 2D simulation, violated by solid # " + std::to_string(i));
+        Solid s((label)i, pos, quaternion::I);
+        s.setVelocity(solid.lookupOrDefault("vel", vector::zero));
+        s.setOrientation(solid.lookupOrDefault("euler", vector::zero) * M_PI / 180.0);
+        s.setOmega(solid.lookupOrDefault("omega", vector::zero));
+
+        const std::string mot_name = Foam::word(solid.lookup("mot_name"));
+        const std::string mat_name = Foam::word(solid.lookup("mat_name"));
+        const std::string shp_name = Foam::word(solid.lookup("shp_name"));
+        if (mot_name != "free") {
+            // the reference's operator[] silently inserts a null motion for an unknown name (:186); report it instead
+            const auto it = m_libmotion.find(mot_name);
+            if (it == m_libmotion.end()) throw std::runtime_error("Unrecognized motion name " + mot_name);
+            s.setMotion(it->second);
+        }
+        const auto shp = m_libshape.find(shp_name);
+        if (shp == m_libshape.end()) throw std::runtime_error("Unrecognized shape name " + shp_name);
+        s.setShape(shp->second.get());
+        if (solid.found("for_name")) {
+            const std::string for_name = Foam::word(solid.lookup("for_name"));
+            const auto f = m_libforcer.find(for_name);
+            if (f == m_libforcer.end()) throw std::runtime_error("Unrecognized force name " + for_name);
+            s.setForcer(f->second.get());
+        }
+        const auto mat = m_libmat.find(mat_name);
+        if (mat == m_libmat.end()) throw std::runtime_error("Unrecognized material name " + mat_name);   // null deref in the reference (:198)
+        s.setMaterial(mat->second);
+        this->addSolid(std::move(s));
+    }
+    m_solidDict = root;
+}
+
+void SolidCloud::buildShapeTable() {
+    // shape table in solidDict order; a registered type with no device tag is a hard error (no CPU fallback)
+    const dictionary &shapes = m_solidDict.subDict("shapes");
+    std::vector<sdfibm_shape_t> &table = m_shapeTable;
+    table.clear();
+    std::map<const IShape *, int> index;
+    for (const auto &key : shapes.toc()) {
+        const std::string name = Foam::word(shapes.subDict(key).lookup("name"));
+        const IShape *sh = m_libshape.at(name).get();
+        if (index.count(sh)) continue;
+        sdfibm_shape_t rec;
+        if (!sh->lower(rec))
+            throw std::runtime_error("shape type '" + sh->getTypeName() + "' has no device tag: implement IShape::lower() "
+                                     "(the coupling path has no CPU fallback)");
+        index[sh] = (int)table.size();
+        table.push_back(rec);
+    }
+    if (table.empty()) throw std::runtime_error("solidDict defines no shapes");
+    m_shapeIndex.resize(m_solids.size());
+    for (size_t i = 0; i < m_solids.size(); ++i) m_shapeIndex[i] = index.at(m_solids[i].getShape());
+}
+
+// device context: one per rank, on the GPU given by SDFIBM_DEVICE (default 0).  Created at the first device call; the
+// static mesh and the shape table are uploaded exactly once.
+void SolidCloud::ensureDevice() {
+    if (m_ctx) return;
+    int device = 0;
+    if (const char *d = std::getenv("SDFIBM_DEVICE")) device = std::atoi(d);
+    sdfibm_context *ctx = nullptr;
+    check(sdfibm_create(device, &ctx), "sdfibm_create");
+    m_ctx = ctx;
+    if (const char *k = std::getenv("SDFIBM_CELL_SLOTS")) check(sdfibm_set_cell_slots(m_ctx, std::atoi(k)), "sdfibm_set_cell_slots");
+    check(sdfibm_set_mesh(m_ctx, &meshView(m_mesh), m_ON_TWOD ? 1 : 0), "sdfibm_set_mesh");
+    check(sdfibm_set_shapes(m_ctx, m_shapeTable.data(), (int)m_shapeTable.size()), "sdfibm_set_shapes");
+}
+
+void SolidCloud::stageRecords() {
+    m_records.resize(m_solids.size());
+    for (size_t i = 0; i < m_solids.size(); ++i) m_solids[i].toRecord(m_records[i], m_shapeIndex[i]);
+}
+
+SolidCloud::SolidCloud(const Foam::word &dictfile, Foam::volVectorField &U, scalar time)   // :209-274
+    : m_mesh(U.mesh()),
+      m_Uf(U),
+      m_ct(const_cast<Foam::volScalarField &>(m_mesh.lookupObject<Foam::volScalarField>("Ct"))),
+      m_As(const_cast<Foam::volScalarField &>(m_mesh.lookupObject<Foam::volScalarField>("As"))),
+      m_Fs(const_cast<Foam::volVectorField &>(m_mesh.lookupObject<Foam::volVectorField>("Fs"))),
+      m_Ts(const_cast<Foam::volScalarField &>(m_mesh.lookupObject<Foam::volScalarField>("Ts"))) {
+    m_time = time;
+    m_solids.reserve(10);
+    if (isMaster()) logfile.open(casePath(m_mesh, "cloud.log"), std::fstream::out);
+
+    initFromDictionary(Foam::word(dictfile));
+    log("Totally [" + std::to_string(m_solids.size()) + "] solids.");
+
+    if (isMaster()) {
+        statefile.open(casePath(m_mesh, "cloud.out"), std::fstream::out);
+        statefile << std::scientific;
+    }
+
+    buildShapeTable();
+    m_forceTorque.assign(6 * m_solids.size(), 0.0);
+
+    m_rhof = transportRho(m_mesh);   // :247-251
+    if (!m_ON_FLUID) m_rhof = 0.0;
+
+    m_ON_RESTART = meshTime(m_mesh) > 0;   // :254-258
+    if (!m_ON_RESTART) initialCorrect();
+    log("END OF INIT");
+}
+
+SolidCloud::~SolidCloud() {
+    log("Simulation finished! Congratulations!");
+    if (m_ctx) sdfibm_destroy(m_ctx);
+    for (auto &kv : m_libmotion) delete kv.second;
+    for (auto &kv : m_libmat) delete kv.second;
+}
+
+void SolidCloud::initialCorrect() {   // :276-286
+    this->interact(0, 1);
+    m_As.write();
+    log("Initial As written to 0 directory");
+    for (Solid &solid : m_solids) solid.clearForceAndTorque();
+}
+
+void SolidCloud::fixInternal(scalar) {   // :288-301 — Ct of the last interact, solid state AFTER evolve
+    if (m_solids.empty()) return;
+    ensureDevice();
+    stageRecords();
+    check(sdfibm_fix_internal(m_ctx, m_records.data(), (int)m_records.size(), cellData(m_Uf)), "sdfibm_fix_internal");
+    m_Uf.correctBoundaryConditions();
+}
+
+void SolidCloud::interact(scalar time, scalar dt) {   // :435-464
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    // the four fields are rewritten for every cell by the kernels (the reference zeroes them first, :438-441)
+    if (!m_solids.empty()) {
+        ensureDevice();
+        stageRecords();
+        check(sdfibm_interact(m_ctx, m_records.data(), (int)m_records.size(), cellData(m_Uf), dt, m_rhof, cellData(m_As), cellData(m_Fs),
+                              cellData(m_Ts), cellData(m_ct), m_forceTorque.data()),
+              "sdfibm_interact");
+        if (m_reduce) m_reduce(m_forceTorque.data(), (int)m_forceTorque.size());   // :427-431, one sum instead of 2N
+        for (size_t i = 0; i < m_solids.size(); ++i) {
+            const double *ft = &m_forceTorque[6 * i];
+            m_solids[i].setFluidForceAndTorque(vector(ft[0], ft[1], ft[2]), vector(ft[3], ft[4], ft[5]));   // :432
+        }
+    } else {
+        m_ct = 0.0; m_As = 0.0; m_Fs = vector::zero; m_Ts = 0.0;
+    }
+    const auto t2 = std::chrono::high_resolution_clock::now();
+    m_lastInteractMs = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    {
+        std::ostringstream msg;   // :453-459, the origin of the "interact() ms/step" metric
+        msg << "t = " << time << " [FSI took " << m_lastInteractMs << " ms]";
+        log(msg.str());
+    }
+    m_As.correctBoundaryConditions();
+    m_Fs.correctBoundaryConditions();
+    m_Ts.correctBoundaryConditions();
+}
+
+void SolidCloud::addMidEnvironment() {   // :466-475
+    for (Solid &solid : m_solids) {
+        const scalar rhos = solid.getMaterial()->getRho();
+        const vector gprime = ((rhos - m_rhof) / rhos) * m_gravity;
+        solid.addAcceleration(gprime);
+    }
+}
+
+void SolidCloud::solidSolidInteract() {   // :477-519 — broad phase, narrow phase and force law on the device
+    // HEAD constructs its UGrid with cell size 2*m_radiusB = -2, which has no cells and never yields a pair
+    // (SURVEY Q7): nothing to do for delta <= 0.
+    if (m_solids.empty() || !(m_collisionDelta > 0)) return;
+    ensureDevice();
+    stageRecords();
+    std::vector<double> ft(6 * m_solids.size(), 0.0);
+    int64_t n_pairs = 0;
+    check(sdfibm_collide(m_ctx, m_records.data(), (int)m_records.size(), m_collisionDelta, nullptr, 0, &n_pairs, ft.data()), "sdfibm_collide");
+    if (n_pairs == 0) return;
+    for (size_t i = 0; i < m_solids.size(); ++i)
+        m_solids[i].addForceAndTorque(vector(ft[6 * i], ft[6 * i + 1], ft[6 * i + 2]), vector(ft[6 * i + 3], ft[6 * i + 4], ft[6 * i + 5]));
+}
+
+void SolidCloud::evolve(scalar time, scalar dt) {   // :521-562
+    m_time = time;
+    if (m_solids.size() == 1) N_SUBITER = 1;   // sticky, like the reference's function-static
+    const scalar dt_sub = dt / N_SUBITER;
+    for (int i = 0; i < N_SUBITER; ++i) {
+        for (Solid &solid : m_solids) solid.clearForceAndTorque();
+        for (Solid &solid : m_solids) solid.applyForcer(time);
+        for (Solid &solid : m_solids) solid.addMidFluidForceAndTorque();
+        this->addMidEnvironment();
+        this->solidSolidInteract();
+        for (Solid &solid : m_solids) solid.move(time, dt_sub);   // `time` is not advanced across sub-iterations (Q8)
+    }
+    for (Solid &solid : m_solids) solid.storeOldForce();
+}
+
+scalar SolidCloud::totalSolidVolume() const {   // :572-576
+    const sdfibm_mesh_t &mv = meshView(m_mesh);
+    const double *as = cellData(const_cast<Foam::volScalarField &>(m_As));
+    scalar sum = 0;
+    for (label c = 0; c < mv.n_cells; ++c) sum += as[c] * mv.cell_volumes[c];
+    return sum;
+}
+
+void SolidCloud::saveState() {   // :578-593
+    if (!isMaster()) return;
+    if (m_timeStepCounter % m_writeFrequency == 0) {
+        statefile << (*this);
+        statefile.flush();
+    }
+    ++m_timeStepCounter;
+}
+
+std::ostream &operator<<(std::ostream &os, const SolidCloud &sc) {   // :595-614
+    if (sc.m_ON_TWOD) {
+        for (const Solid &solid : sc.m_solids) {
+            os << sc.m_time << ' ';
+            write2D(os, solid);
+            os << '\n';
+        }
+    } else {
+        for (const Solid &solid : sc.m_solids) os << sc.m_time << ' ' << solid << '\n';
+    }
+    return os;
+}
+
+void SolidCloud::saveRestart(const std::string &filename) {   // :616-665
+    dictionary &solids = m_solidDict.subDict("solids");
+    const auto names = solids.toc();
+    for (size_t i = 0; i < names.size(); ++i) {
+        const Solid &s = m_solids[i];
+        dictionary &solid = solids.subDict(names[i]);
+        vector tmp = s.getCenter();
+        if (m_ON_TWOD) tmp.z() = 0.0;
+        solid.set("pos", tmp);
+        tmp = s.getVelocity();
+        if (m_ON_TWOD) tmp.z() = 0.0;
+        solid.set("vel", tmp);
+        solid.set("euler", s.getOrientation().eulerAngles(quaternion::XYZ) * 180.0 / M_PI);   // degrees
+        tmp = s.getOmega();
+        if (m_ON_TWOD) {
+            tmp.x() = 0.0;
+            tmp.y() = 0.0;
+        }
+        solid.set("omega", tmp);
+    }
+    std::ofstream os(filename);
+    if (!os) throw std::runtime_error("cannot write restart dictionary " + filename);
+    os << "FoamFile\n{\n    version     2.0;\n    format      ascii;\n    class       dictionary;\n    object      solidDict;\n}\n";
+    m_solidDict.write(os, false);
+    const std::time_t now = std::time(nullptr);
+    char stamp[64];
+    std::strftime(stamp, sizeof stamp, "%Y-%m-%d %H:%M:%S", std::localtime(&now));
+    os << "\n// " << stamp << "\n";
+}
+
+} // namespace sdfibm

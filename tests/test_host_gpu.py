@@ -1,0 +1,107 @@
+"""Host façade on the GPU: the whole per-step sequence main.cpp runs on SolidCloud (interact -> U -= Fs dt -> evolve ->
+saveState -> fixInternal, reference src/main.cpp:66-88) through the C++ SolidCloud, against the oracle chain
+(oracle interact / collide / fixInternal + the Python restatement of evolve) on the same solidDict."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import host_cases as hc
+from oracle import host_oracle as ho
+from oracle.oracle_py import Oracle
+from sdfibm_b200 import cases, hostapi
+from sdfibm_b200.mesh import Mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def _sedimentation(n_side=5):
+    """Scaled-down examples/sedimentation: circles r = 0.15 on a lattice in a box closed by four plane walls."""
+    solids = []
+    for j in range(n_side):
+        for i in range(n_side):
+            solids.append(dict(shp_name="circ", mot_name="free", mat_name="heavy", pos=(-0.8 + 0.4 * i + 0.03 * ((i + j) % 3), 2.2 + 0.36 * j, 0.0),
+                               vel=(0.05 * (i - 2), -0.1 * j, 0.0), omega=(0.0, 0.0, 0.3 * (i - j))))
+    walls = [((0.0, 0.0, 0.0), 0.0), ((0.0, 4.0, 0.0), 180.0), ((-2.0, 2.0, 0.0), -90.0), ((2.0, 2.0, 0.0), 90.0)]
+    for p, ez in walls:
+        solids.append(dict(shp_name="plane", mot_name="fixed", mat_name="heavy", pos=p, euler=(0.0, 0.0, ez)))
+    return solids
+
+
+def test_coupled_steps_match_oracle_chain(tmp_path):
+    solids = _sedimentation()
+    motions = dict(hc.MOTIONS, fixed=dict(type="Motion01Mask", mask="b000000"))
+    meta = dict(on_fluid=1, on_twod=1, gravity=(0.0, -10.0, 0.0), collision_delta=0.33)
+    path = hc.write_case(tmp_path, meta, solids, motions=motions)
+    mesh = Mesh.hex_block((200, 200, 1), (-2.0, 0.0, -0.5), (0.02, 0.02, 1.0))
+    U0 = cases.taylor_green(mesh.cc, 4.0)
+    rhof, dt = 1.0, 5e-4
+    hostapi.load().sdfibm_host_reset_subiterations()
+    cloud = hostapi.HostCloud(path, str(tmp_path), mesh, rhof, start_time=0.0, U_init=U0)
+    assert os.path.exists(os.path.join(str(tmp_path), "0_As"))            # initialCorrect wrote As (src/solidcloud.cpp:276-281)
+
+    table, index = hc.shape_table(solids)
+    ref = hc.oracle_solids(solids, motions=motions)
+    o = Oracle(mesh, True)
+    U = U0.copy()
+    # initialCorrect: interact(0, dt = 1) — only As survives, the fluid force is overwritten before the first evolve
+    r0 = o.interact(table, ho.records(ref, index), U, 1.0, rhof)
+    assert np.abs(cloud.field("As") - r0["As"]).max() <= 1e-12
+
+    def collide(ss):
+        pairs, ft = o.collide(table, ho.records(ss, index), meta["collision_delta"])
+        return ft if len(pairs) else None
+
+    t = 0.0
+    n_pairs_seen = 0
+    for step in range(3):
+        t += dt
+        cloud.interact(t, dt)
+        r = o.interact(table, ho.records(ref, index), U, dt, rhof)
+        for k in ("As", "Ts", "Ct"):
+            assert np.abs(cloud.field(k) - r[k]).max() <= 1e-9 * max(1.0, np.abs(r[k]).max()), (step, k)
+        assert np.abs(cloud.field("Fs") - r["Fs"]).max() <= 1e-9 * np.abs(r["Fs"]).max(), step
+        _, fluid = cloud.forces()
+        assert np.abs(fluid - r["FT"]).max() <= 1e-9 * np.abs(r["FT"]).max(), step
+        for i, s in enumerate(ref):
+            s.ff, s.ft = tuple(r["FT"][i, :3]), tuple(r["FT"][i, 3:])
+        # main.cpp:70
+        cloud.field("U")[:] = cloud.field("U") - cloud.field("Fs") * dt
+        U = U - r["Fs"] * dt
+        cloud.evolve(t, dt)
+        n_pairs_seen += len(o.collide(table, ho.records(ref, index), meta["collision_delta"])[0])
+        ho.evolve(ref, t, dt, 20, meta["gravity"], rhof, collide=collide)
+        cloud.save_state()
+        cloud.fix_internal(dt)
+        U = o.fix_internal(table, ho.records(ref, index), r["Ct"], U)
+        x, q, v, om = hc.state_arrays(ref)
+        got = cloud.solids()
+        for a, b in ((got["pos"], x), (got["quat"], q), (got["vel"], v), (got["omega"], om)):
+            assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(b).max()), step
+        assert np.abs(cloud.field("U") - U).max() <= 1e-8 * np.abs(U).max(), step
+    assert n_pairs_seen > 0                                                  # the collision step was exercised
+    # planes are held by their motion mask
+    assert np.array_equal(got["pos"][-4:], [s["pos"] for s in solids[-4:]])
+
+
+def test_standalone_runner_3d(tmp_path):
+    """sdfibm_b200_run: the main.cpp-shaped loop without OpenFOAM on a small 3-D case."""
+    solids = [dict(shp_name="sph", mot_name="free", mat_name="heavy", pos=(1.6, 1.7, 1.5), omega=(0.0, 0.0, 0.5)),
+              dict(shp_name="elo", mot_name="free", mat_name="light", pos=(3.1, 2.2, 2.6), euler=(10.0, 20.0, 30.0))]
+    hc.write_case(tmp_path, dict(on_fluid=1, on_twod=0, gravity=(0.0, 0.0, -9.81)), solids)
+    with open(os.path.join(str(tmp_path), "runDict"), "w") as f:
+        f.write("mesh { cells (48 48 48); origin (0 0 0); spacing (0.1 0.1 0.1); }\n"
+                "fluid { rho 1.0; U (0.1 0 0); }\ntime { deltaT 1e-3; nSteps 3; startTime 0; }\n")
+    hostapi.load()
+    r = subprocess.run([hostapi.RUNNER_PATH, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "ran 3 steps, 2 solids" in r.stdout
+    rows = open(os.path.join(str(tmp_path), "cloud.out")).read().strip().split("\n")
+    assert len(rows) == 2 * 4 and all(len(x.split()) == 19 for x in rows)
+    vol = float(r.stdout.split("solid volume")[1])
+    exact = 4.0 / 3.0 * np.pi * (0.3 ** 3 + 0.5 * 0.45 * 0.4)
+    assert -0.05 < vol / exact - 1.0 < 0.0                                   # the algorithm's known negative bias
+    assert os.path.exists(os.path.join(str(tmp_path), "solidDict.restart"))
+    log = open(os.path.join(str(tmp_path), "cloud.log")).read()
+    assert "FSI took" in log
