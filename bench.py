@@ -90,6 +90,19 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the interact kernels from the committed ncu capture (profiles/r01_traffic.json); None when the
+    capture is of another workload."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("workload", "").lower() == workload:
+            return int(sum(d["kernels"].values())), d
+    except Exception:
+        pass
+    return None, None
+
+
 def algorithmic_bytes(n_cells, counts, n_solids):
     """B = 48 nCells + 112 P + 216 P_b + 176 N  (hex mesh)."""
     P = sum(counts)
@@ -308,6 +321,7 @@ def main():
         peak, peak_src = measured_hbm_peak()
         alg = algorithmic_bytes(nC, counts, nS)            # rank 0's kernel launch
         achieved = alg / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(wl if world == 1 and not args.n else "-")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -322,7 +336,9 @@ def main():
                           "interact_kernels": kern_ms, "pipeline_device": pipe_ms, "step_wall_on_stream": ms_per_step,
                           "heavy_items": stats["heavy_items"]},
             "roofline": {"bound": "hbm", "kernel": "k_classify+k_heavy+k_final (the interact kernels; k_heavy dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src["source"] if traffic_src else None,
+                         "traffic_per_kernel": traffic_src["kernels"] if traffic_src else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg),
                          "formula": "48*nCells + 112*P + 216*P_b + 176*N (SURVEY.md 8d), rank 0"},
             "e2e": e2e,

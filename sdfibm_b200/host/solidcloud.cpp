@@ -14,6 +14,9 @@
 #include "../../include/sdfibm_b200.h"
 #include "libmotion/motions.h"
 #include "libshape/shapefactory.h"
+#ifdef SDFIBM_WITH_OPENFOAM
+#include "IFstream.H"
+#endif
 
 namespace sdfibm {
 
@@ -32,6 +35,16 @@ inline scalar transportRho(const Foam::fvMesh &m) { return m.transportRho(); }
 inline scalar meshTime(const Foam::fvMesh &m) { return m.timeValue(); }
 inline std::string casePath(const Foam::fvMesh &m, const std::string &f) { return m.caseDir() + "/" + f; }
 inline bool isMaster() { return true; }
+inline dictionary readDictionaryFile(const std::string &path) {
+    dictionary d = dictionary::fromFile(path);
+    d.remove("FoamFile");   // OpenFOAM drops the header entry when reading a dictionary file
+    return d;
+}
+#else
+inline dictionary readDictionaryFile(const std::string &path) {
+    Foam::IFstream is(path);
+    return dictionary(is());
+}
 #endif
 } // namespace
 
@@ -40,8 +53,7 @@ void SolidCloud::log(const std::string &msg) {
 }
 
 void SolidCloud::initFromDictionary(const Foam::word &dictfile) {   // :14-206
-    dictionary root = dictionary::fromFile(dictfile);
-    root.remove("FoamFile");   // OpenFOAM drops the header entry when reading a dictionary file
+    dictionary root = readDictionaryFile(dictfile);
     log("Init from " + dictfile);
 
     const dictionary &meta = root.subDict("meta");
