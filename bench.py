@@ -315,7 +315,8 @@ def main():
         d2h = int(sum(v.nbytes for v in out.values()))
         e2e = {"value": pairs_all / (e_ms_step * 1e-3), "unit": UNIT, "ms_per_step": e_ms_step,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
-               "note": "sdfibm_interact (host-buffer C ABI): pinned U H2D, kernels, As/Fs/Ts/Ct/forceTorque D2H every step"}
+               "note": "sdfibm_interact (host-buffer C ABI): pinned U H2D, kernels, As/Fs/Ts/Ct/forceTorque D2H every step; "
+                       "the copies stream in 8 cell chunks on two copy streams, overlapped with the kernels and with each other"}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()

@@ -24,10 +24,12 @@
 // geometry: apex / pyramid volume fraction (reference src/geometrictools.cpp:13-116)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double line_fraction(double a, double b) {          // :13-23
-    if (a > 0 && b > 0) return 0.0;
-    if (a <= 0 && b <= 0) return 1.0;
-    if (a > 0) return -b / (a - b);
-    return -a / (b - a);
+    // branch-free: ONE division per call for the whole warp.  in = the phi <= 0 end, out = the phi > 0 end; the quotient is
+    // the reference's -phi_in / (phi_out - phi_in) and is discarded when both ends lie on the same side.
+    const bool ap = a > 0, bp = b > 0;
+    const double in = ap ? b : a, out = ap ? a : b;
+    const double q = -in / (out - in);
+    return (ap && bp) ? 0.0 : ((ap || bp) ? q : 1.0);
 }
 
 // calcApex over an indexed vertex list (:25-45).  pts/phi are the cell-local arrays, idx maps the
@@ -155,6 +157,7 @@ struct InteractParams {
     int K;
     const unsigned char *excluded; // replay pass: [n_cells*K] 1 = pair is outside the seed's component
     StepStatus *status;
+    int c_begin, c_end;     // k_final: cell range of this launch
 };
 
 __device__ __forceinline__ float2 cell_radius(const DevMesh &m, int c) { return m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c); }
@@ -544,10 +547,8 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
-                            if (lf != 0.0) {                                        // a zero fraction adds +0.0
-                                const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
-                                area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;
-                            }
+                            const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
+                            area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
                         }
                         eps_f = area / r3.x;
                     }
@@ -578,8 +579,8 @@ __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
     const DevMesh &m = P.m;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = c < m.n_cells;
+    const int c = P.c_begin + blockIdx.x * blockDim.x + threadIdx.x;   // [c_begin, c_end): one chunk of the cell range
+    const bool live = c < P.c_end;
     const long long nC = m.n_cells;
     const int n = live ? (int)P.n_item[c] : 0;
     const int e0 = live ? P.slots[c] : 0;       // slot 0, fetched together with n_item (meaningless when n == 0)
@@ -666,14 +667,26 @@ __global__ void k_connectivity(ConnParams P) {
     const long long nC = P.m.n_cells;
     const D3 cc = ld3(P.m.cc, c);
     const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
+    const unsigned hint = __ldg(P.m.nb_hint + c);
     for (int j = 0; j < n; ++j) {
         const int e = P.slots[(long long)j * nC + c];
         if ((e & 3) == 0) continue;
         const int s = e >> 3;
         const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
-        const double kc = magSqr3(cc - x);
+        const D3 r = cc - x;
+        const double kc = magSqr3(r);
+        // try the face neighbour that lies towards the solid centre first: almost always a member with a smaller key
+        const double ax = fabs(r.x), ay = fabs(r.y), az = fabs(r.z);
+        const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+        const double comp = axis == 0 ? r.x : axis == 1 ? r.y : r.z;
+        const int first = (int)((hint >> (3 * (2 * axis + (comp > 0 ? 0 : 1)))) & 7u);
         bool has_parent = false;
+        if (first < nb1 - nb0) {
+            const int nb = __ldg(P.m.nb + nb0 + first);
+            if (find_member(P.n_item, P.slots, nC, nb, s) >= 0 && key_less(magSqr3(ld3(P.m.cc, nb) - x), nb, kc, c)) has_parent = true;
+        }
         for (int k = nb0; k < nb1 && !has_parent; ++k) {
+            if (k - nb0 == first) continue;
             const int nb = __ldg(P.m.nb + k);
             if (find_member(P.n_item, P.slots, nC, nb, s) >= 0) {
                 const double kn = magSqr3(ld3(P.m.cc, nb) - x);
@@ -820,9 +833,9 @@ __global__ void k_replay_mark(ReplayParams P) {
 // ------------------------------------------------------------------------------------------------
 // fixInternal (solidcloud.cpp:288-301)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_fix_internal(DevMesh m, const sdfibm_solid_t *solids, int n_solids, const double *Ct, double *U) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.n_cells) return;
+__global__ void k_fix_internal(DevMesh m, const sdfibm_solid_t *solids, int n_solids, const double *Ct, double *U, int c_begin, int c_end) {
+    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_end) return;
     const double ct = Ct[c];
     if (ct >= 4) {
         const int id = (int)(ct - 4);

@@ -81,6 +81,8 @@ struct DevMesh {
     const double *magSf;    // |Sf| per face (same expression as Foam::mag, evaluated once at upload)
     const double2 *face_rec; // hex path: 64-byte record per face: Cf.xyz, Sf.xyz, |Sf|, pad
     const unsigned *hex_topo; // hex meshes: 3 words per cell, 4-bit cell-local vertex slot of every face vertex
+    const unsigned *nb_hint;  // per cell: for each signed axis direction (-x,+x,-y,+y,-z,+z) the position in cellCells[c] of
+                              // the best-aligned face neighbour, 3 bits each (7 = none)
     float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
     int rad_uniform;
     int is_hex;             // every cell has 8 points / 6 faces and every face 4 points
@@ -154,6 +156,27 @@ __global__ void k_hex_topo(DevMesh m, unsigned *topo, int *bad) {
     topo[3 * (long long)c] = w[0];
     topo[3 * (long long)c + 1] = w[1];
     topo[3 * (long long)c + 2] = w[2];
+}
+
+// direction hints for the connectivity certificate: which face neighbour lies towards -x, +x, -y, ...
+__global__ void k_nb_hint(DevMesh m, unsigned *hint) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    const D3 cc = ld3(m.cc, c);
+    const int b = m.nb_off[c], e = m.nb_off[c + 1];
+    unsigned w = 0;
+    for (int d = 0; d < 6; ++d) {
+        int best = 7;
+        double best_cos = 0.0;
+        for (int k = b; k < e && k - b < 7; ++k) {
+            const D3 r = ld3(m.cc, m.nb[k]) - cc;
+            const double comp = (d >> 1) == 0 ? r.x : (d >> 1) == 1 ? r.y : r.z;
+            const double cs = ((d & 1) ? comp : -comp) / (mag3(r) + 1e-300);
+            if (cs > best_cos) { best_cos = cs; best = k - b; }
+        }
+        w |= (unsigned)best << (3 * d);
+    }
+    hint[c] = w;
 }
 
 // rmax[0..1] = max of the (3-D, xy) radii, rmax[2..3] = min
@@ -477,7 +500,7 @@ struct sdfibm_context {
     DevBuf<float2> cell_rad;
     DevBuf<double> magSf;
     DevBuf<double2> face_rec;
-    DevBuf<unsigned> hex_topo;
+    DevBuf<unsigned> hex_topo, nb_hint;
     double bmin[3], bmax[3];
     float rad3_max = 0.f, radxy_max = 0.f;
     // shapes
@@ -511,6 +534,11 @@ struct sdfibm_context {
     // stats
     StepStatus last{};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // host-buffer entry: U arrives and the fields leave in cell chunks on two copy streams, overlapped with the kernels
+    static const int N_CHUNK = 8;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[N_CHUNK] = {}, ev_fin[N_CHUNK] = {};
+    struct { bool active = false, stale = false; double *As = nullptr, *Fs = nullptr, *Ts = nullptr, *Ct = nullptr; const double *U = nullptr; } pipe;
     double t_ms[6] = {0, 0, 0, 0, 0, 0}; // binning, k_classify, k_heavy, k_accumulate, connectivity+finalise, whole pipeline
     int n_sm = 148;
     int64_t launches = 0;
@@ -580,6 +608,12 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(StepStatus)));
     CUDA_TRY(ctx->status.ensure(1));
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fin[i], cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device));
     *out = ctx;
     return SDFIBM_OK;
@@ -592,7 +626,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->points.release(); ctx->cc.release(); ctx->V.release(); ctx->Cf.release(); ctx->Sf.release();
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
-    ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb_hint.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
     ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
     ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
@@ -601,6 +635,9 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_fin[i]) cudaEventDestroy(ctx->ev_fin[i]); }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_solids) cudaFreeHost(ctx->h_solids);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -699,6 +736,9 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         d.hex_topo = ctx->hex_topo.p;
         k_hex_topo<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->hex_topo.p, bad.p);
     }
+    CUDA_TRY(ctx->nb_hint.ensure(nC));
+    d.nb_hint = ctx->nb_hint.p;
+    k_nb_hint<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->nb_hint.p);
     CUDA_TRY(cudaGetLastError());
     int h_bad = 0;
     float h_rmax[4];
@@ -793,7 +833,8 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     if (!ctx->has_mesh || ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
     if (n_solids > (1 << 28) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    int rc = stage_solids(ctx, solids, n_solids);
+    int rc = SDFIBM_OK;
+    if (!ctx->pipe.active) rc = stage_solids(ctx, solids, n_solids);   // the host-buffer entry stages them ahead of its U copies
     if (rc) return rc;
     ctx->launches = 0;
     rc = run_pipeline(ctx, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT, false);
@@ -919,7 +960,39 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
         else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
-        k_final<4><<<grid_for(nC, 256), 256, 0, st>>>(I);
+        if (ctx->pipe.active && !replay && attempt == 0) {
+            // chunked: k_final of chunk i waits for its slice of U and releases its slice of the fields to the copy-out stream.
+            // The copy engines are FIFO across streams, so the U chunks are enqueued only now — after every small upload /
+            // memset the preceding kernels depend on — and still start at t ~ 0 because enqueueing is asynchronous.
+            for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
+                const size_t c0 = (size_t)nC * i / sdfibm_context::N_CHUNK, c1 = (size_t)nC * (i + 1) / sdfibm_context::N_CHUNK;
+                if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(dU) + 3 * c0, ctx->pipe.U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
+                CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+            }
+            for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
+                const long long c0 = (long long)nC * i / sdfibm_context::N_CHUNK, c1 = (long long)nC * (i + 1) / sdfibm_context::N_CHUNK;
+                if (c1 <= c0) continue;
+                I.c_begin = (int)c0; I.c_end = (int)c1;
+                CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[i], 0));
+                k_final<4><<<grid_for(c1 - c0, 256), 256, 0, st>>>(I);
+                CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
+                CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
+                const size_t n = (size_t)(c1 - c0);
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.As + c0, dAs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Fs + 3 * c0, dFs + 3 * c0, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ts + c0, dTs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ct + c0, dCt + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+            ctx->launches += sdfibm_context::N_CHUNK - 1;
+        } else {
+            if (ctx->pipe.active) {   // a retry / replay pass rewrites the fields: copy them out again at the end
+                ctx->pipe.stale = true;
+                CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
+                CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+            }
+            I.c_begin = 0; I.c_end = nC;
+            k_final<4><<<grid_for(nC, 256), 256, 0, st>>>(I);
+        }
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         ctx->launches += 3;
         if (!replay) {
@@ -991,14 +1064,24 @@ int sdfibm_interact(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_sol
     if (rc) return rc;
     const size_t nC = ctx->dm.n_cells;
     cudaStream_t st = ctx->stream;
-    CUDA_TRY(cudaMemcpyAsync(ctx->dU.p, U, sizeof(double) * 3 * nC, cudaMemcpyHostToDevice, st));
-    rc = sdfibm_interact_device(ctx, solids, n_solids, ctx->dU.p, dt, rhof, ctx->dAs.p, ctx->dFs.p, ctx->dTs.p, ctx->dCt.p, ctx->dFT.p);
+    // the copy engines are FIFO across streams: the small solid upload the kernels depend on goes first
+    rc = stage_solids(ctx, solids, n_solids);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(As, ctx->dAs.p, sizeof(double) * nC, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(Fs, ctx->dFs.p, sizeof(double) * 3 * nC, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(Ts, ctx->dTs.p, sizeof(double) * nC, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(Ct, ctx->dCt.p, sizeof(double) * nC, cudaMemcpyDeviceToHost, st));
+    // U is not needed before k_final: its chunks stream in on s_in while binning / k_classify / k_heavy run; each chunk of the
+    // fields leaves on s_out as soon as its k_final launch is done (PCIe is full duplex: copy-in and copy-out overlap too).
+    ctx->pipe.active = true; ctx->pipe.stale = false;
+    ctx->pipe.As = As; ctx->pipe.Fs = Fs; ctx->pipe.Ts = Ts; ctx->pipe.Ct = Ct; ctx->pipe.U = U;
+    rc = sdfibm_interact_device(ctx, solids, n_solids, ctx->dU.p, dt, rhof, ctx->dAs.p, ctx->dFs.p, ctx->dTs.p, ctx->dCt.p, ctx->dFT.p);
+    ctx->pipe.active = false;
+    if (rc) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out); return rc; }
     CUDA_TRY(cudaMemcpyAsync(force_torque, ctx->dFT.p, sizeof(double) * 6 * n_solids, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+    if (ctx->pipe.stale) {
+        CUDA_TRY(cudaMemcpyAsync(As, ctx->dAs.p, sizeof(double) * nC, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(Fs, ctx->dFs.p, sizeof(double) * 3 * nC, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(Ts, ctx->dTs.p, sizeof(double) * nC, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(Ct, ctx->dCt.p, sizeof(double) * nC, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return SDFIBM_OK;
 }
@@ -1011,23 +1094,39 @@ int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids
     CUDA_TRY(cudaSetDevice(ctx->device));
     int rc = stage_solids(ctx, solids, n_solids);
     if (rc) return rc;
-    k_fix_internal<<<grid_for(ctx->dm.n_cells, 256), 256, 0, ctx->stream>>>(ctx->dm, ctx->solids_in.p, n_solids, dCt, dU);
+    k_fix_internal<<<grid_for(ctx->dm.n_cells, 256), 256, 0, ctx->stream>>>(ctx->dm, ctx->solids_in.p, n_solids, dCt, dU, 0, ctx->dm.n_cells);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SDFIBM_OK;
 }
 
 int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *U) {
-    if (!ctx || !U) return fail(SDFIBM_ERR_ARG, "sdfibm_fix_internal: null argument");
+    if (!ctx || !U || !solids || n_solids <= 0) return fail(SDFIBM_ERR_ARG, "sdfibm_fix_internal: null argument");
     if (!ctx->has_mesh || !ctx->dCt.p || ctx->last_Ct != ctx->dCt.p)
         return fail(SDFIBM_ERR_STATE, "sdfibm_fix_internal: call sdfibm_interact (host buffers) first");
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t nC = ctx->dm.n_cells;
-    CUDA_TRY(cudaMemcpyAsync(ctx->dU.p, U, sizeof(double) * 3 * nC, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = sdfibm_fix_internal_device(ctx, solids, n_solids, ctx->dU.p, ctx->dCt.p);
+    cudaStream_t st = ctx->stream;
+    int rc = stage_solids(ctx, solids, n_solids);   // first on the copy engine, ahead of the U chunks
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(U, ctx->dU.p, sizeof(double) * 3 * nC, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // U in / kernel / U out per cell chunk: the two copy directions overlap (full-duplex PCIe)
+    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
+        const size_t c0 = nC * i / sdfibm_context::N_CHUNK, c1 = nC * (i + 1) / sdfibm_context::N_CHUNK;
+        if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(ctx->dU.p + 3 * c0, U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+    }
+    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
+        const size_t c0 = nC * i / sdfibm_context::N_CHUNK, c1 = nC * (i + 1) / sdfibm_context::N_CHUNK;
+        if (c1 <= c0) continue;
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[i], 0));
+        k_fix_internal<<<grid_for((long long)(c1 - c0), 256), 256, 0, st>>>(ctx->dm, ctx->solids_in.p, n_solids, ctx->dCt.p, ctx->dU.p, (int)c0, (int)c1);
+        CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
+        CUDA_TRY(cudaMemcpyAsync(U + 3 * c0, ctx->dU.p + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return SDFIBM_OK;
 }
 
