@@ -147,6 +147,15 @@ int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
 int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids,
                                double *dU, const double *dCt);
 
+/* ---- mean-field sampler: SolidCloud::calcMeanField (solidcloud.cpp:315-359) ------------
+ * For every solid (placed with the SUBSTITUTE shape its record names) the volume-weighted mean of a cell field over
+ * the shape's candidate cells: mean[3*s..] = sum(alpha V field) / sum(alpha V); sum_alpha_v[s] = the denominator
+ * (before any cross-rank reduction; pass NULL if not wanted).  field[3*n_cells] is a host array.  Runs the interact
+ * kernels on scratch outputs: the fields and Ct of the last sdfibm_interact stay valid for sdfibm_fix_internal
+ * (the reference's sampler overwrites Ct as a side effect, SURVEY Q11 — not reproduced). */
+int sdfibm_mean_field(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field,
+                      double *mean, double *sum_alpha_v);
+
 /* ---- candidate lists of the last interact (CellEnumerator::intersect result) --------
  * counts[3] = total ALL_INSIDE, CENTER_INSIDE, CENTER_OUTSIDE pairs. */
 int sdfibm_candidate_counts(sdfibm_context *ctx, int64_t counts[3]);

@@ -45,6 +45,9 @@ int sdfibm_host_get_solids(sdfibm_host_cloud *h, sdfibm_solid_t *out);
 int sdfibm_host_get_forces(sdfibm_host_cloud *h, double *force_torque, double *fluid_force_torque);
 int sdfibm_host_get_masses(sdfibm_host_cloud *h, double *mass);
 
+/* SolidCloud::calcMeanField with the sampler shape of meta.sampler: mean[3N] (src/solidcloud.cpp:315-359) */
+int sdfibm_host_mean_field(sdfibm_host_cloud *h, double *mean);
+
 /* UGrid cell size of the collision step (HEAD: -2 => no pairs) and the process-wide sub-iteration count reset */
 int sdfibm_host_set_collision_delta(sdfibm_host_cloud *h, double delta);
 int sdfibm_host_reset_subiterations(void);

@@ -53,7 +53,7 @@ class Context:
         nC, n = self.n_cells, len(solids)
         assert U.size == 3 * nC
         if out is None:
-            out = dict(As=np.empty(nC), Fs=np.empty((nC, 3)), Ts=np.empty(nC), Ct=np.empty(nC), FT=np.empty((n, 6)))
+            out = dict(As=np.empty(nC), Fs=np.empty((nC, 3)), Ts=np.empty(nC), Ct=np.empty(nC), FT=np.empty((max(n, 0), 6)))
         capi.check(self._lib.sdfibm_interact(self._h, capi.ptr(solids), n, capi.ptr(U), float(dt), float(rhof),
                                              capi.ptr(out["As"]), capi.ptr(out["Fs"]), capi.ptr(out["Ts"]),
                                              capi.ptr(out["Ct"]), capi.ptr(out["FT"])))
@@ -80,6 +80,16 @@ class Context:
         solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
         capi.check(self._lib.sdfibm_fix_internal_device(self._h, capi.ptr(solids), len(solids), capi.ptr(dU),
                                                         capi.ptr(dCt) if dCt else None))
+
+    # ---- SolidCloud::calcMeanField ----
+    def mean_field(self, solids: np.ndarray, field: np.ndarray):
+        """Volume-weighted mean of `field` over each solid's (substitute) shape; returns (mean[N,3], sum_alpha_V[N])."""
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        field = np.ascontiguousarray(field, dtype=np.float64)
+        n = len(solids)
+        mean, den = np.empty((n, 3)), np.empty(n)
+        capi.check(self._lib.sdfibm_mean_field(self._h, capi.ptr(solids), n, capi.ptr(field), capi.ptr(mean), capi.ptr(den)))
+        return mean, den
 
     # ---- candidate lists / diagnostics of the last interact ----
     def candidate_counts(self):

@@ -227,8 +227,8 @@ __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, cons
 // ------------------------------------------------------------------------------------------------
 // k_classify: thread per mesh cell
 // ------------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) k_classify(InteractParams P) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256, MINB) k_classify(InteractParams P) {
     // The cells of a warp usually fall into a short run of consecutive bins, whose candidate records are
     // contiguous: fetch the offsets with one load per lane and the records with coalesced 16-byte loads into
     // shared memory, so the per-cell loop below has no dependent global loads.
-    __shared__ __align__(16) BinEntry s_ent[8][ENT_STAGE];
+    __shared__ __align__(16) BinEntry s_ent[NT / 32][ENT_STAGE];
     const int bmin = __reduce_min_sync(FULL, live ? b : 0x7fffffff), bmax = __reduce_max_sync(FULL, b);
     int bi = 0, be = 0;
     const BinEntry *E = P.bin_entries;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256, MINB) k_classify(InteractParams P) {
         const int v = __shfl_up_sync(FULL, incl, o);
         if (lane >= o) incl += v;
     }
-    __shared__ int s_wtot[8];
+    __shared__ int s_wtot[NT / 32];
     __shared__ unsigned long long s_base;
     const int warp = threadIdx.x >> 5;
     if (lane == 31) s_wtot[warp] = incl;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256, MINB) k_classify(InteractParams P) {
     if (threadIdx.x == 0) {
         int tot = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { const int t = s_wtot[w]; s_wtot[w] = tot; tot += t; }
+        for (int w = 0; w < NT / 32; ++w) { const int t = s_wtot[w]; s_wtot[w] = tot; tot += t; }
         s_base = tot ? atomicAdd(P.heavy_count, (unsigned long long)tot) : 0ull;
     }
     __syncthreads();
@@ -388,7 +388,6 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
 // volume phase is bank-conflict free.
 struct HeavySmem {
     double px[8 * TPB], py[8 * TPB], pz[8 * TPB], phi[8 * TPB];
-    int vid[8 * TPB];
     unsigned char in[8 * TPB];
 };
 
@@ -458,9 +457,6 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(m.cc + 3 * (long long)c));
             }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sm.vid[j * TPB + tid] = vid[j];
-        __syncwarp();
         // does my low quad coincide with the previous lane's high quad (same solid)?
         const int ls = __shfl_up_sync(FULL, s, 1);
         const int l1 = __shfl_up_sync(FULL, vid[1], 1), l3 = __shfl_up_sync(FULL, vid[3], 1);
@@ -482,14 +478,18 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             const int u = base + lane;
             const bool work = u < nwork;
             const int src = work ? (int)__fns(startmask, 0, (u >> 2) + 1) : 0;
+            // the low-quad vertex (slot 0, 2, 4 or 6) and the solid of the run start `src`, fetched by shuffle
+            const int v0 = __shfl_sync(FULL, vid[0], src), v2 = __shfl_sync(FULL, vid[2], src);
+            const int v4 = __shfl_sync(FULL, vid[4], src), v6 = __shfl_sync(FULL, vid[6], src);
+            const int s_src = __shfl_sync(FULL, s, src);
             if (work) {
-                const int kk = 2 * (u & 3);
+                const int q4 = u & 3, kk = 2 * q4;
+                const int vv = (q4 == 0) ? v0 : (q4 == 1) ? v2 : (q4 == 2) ? v4 : v6;
                 const int col = wbase + src;
-                const int s_src = __ldg(&P.heavy[k0 + src].y);
                 const DevSolid &S2 = P.solids[s_src];
                 const DQ q2 = {S2.q[0], {S2.q[1], S2.q[2], S2.q[3]}};
                 const D3 t2 = {S2.pos[0], S2.pos[1], S2.pos[2]};
-                eval_vertex_to_smem(sm, m, P.shapes[S2.shape], q2, t2, sm.vid[kk * TPB + col], kk, col, false, 0, 0);
+                eval_vertex_to_smem(sm, m, P.shapes[S2.shape], q2, t2, vv, kk, col, false, 0, 0);
             }
         }
         __syncwarp();

@@ -525,6 +525,7 @@ struct sdfibm_context {
     int n_solids_last = 0;
     // fields kept on device for the host-buffer API and fixInternal
     DevBuf<double> dU, dAs, dFs, dTs, dCt, dFT;
+    DevBuf<double> sU, sOut, sFT; // mean-field sampler scratch
     const double *last_Ct = nullptr;
     // replay
     DevBuf<int> labels, seed_cell, min_label, chosen, changed;
@@ -631,7 +632,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
     ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
     ctx->ft_internal.release(); ctx->status.release(); ctx->scan_tmp.release();
-    ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release();
+    ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release(); ctx->sU.release(); ctx->sOut.release(); ctx->sFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -828,11 +829,25 @@ static int stage_solids(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
 
 int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *dU, double dt,
                            double rhof, double *dAs, double *dFs, double *dTs, double *dCt, double *dFT) {
-    if (!ctx || !solids || n_solids <= 0 || !dU || !dAs || !dFs || !dTs || !dCt || !dFT)
+    if (!ctx || n_solids < 0 || (n_solids > 0 && (!solids || !dFT)) || !dU || !dAs || !dFs || !dTs || !dCt)
         return fail(SDFIBM_ERR_ARG, "sdfibm_interact: null argument");
-    if (!ctx->has_mesh || ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
-    if (n_solids > (1 << 28) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
+    if (!ctx->has_mesh) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n_solids == 0) {   // an empty cloud: the four fields are reset and nothing else happens (solidcloud.cpp:438-441)
+        const size_t nC0 = ctx->dm.n_cells;
+        CUDA_TRY(cudaMemsetAsync(dAs, 0, sizeof(double) * nC0, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(dFs, 0, sizeof(double) * 3 * nC0, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(dTs, 0, sizeof(double) * nC0, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(dCt, 0, sizeof(double) * nC0, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->n_item.p, 0, nC0, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->last = StepStatus{};
+        ctx->last_Ct = dCt;
+        ctx->n_solids_last = 0;
+        return SDFIBM_OK;
+    }
+    if (ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
+    if (n_solids > (1 << 28) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
     int rc = SDFIBM_OK;
     if (!ctx->pipe.active) rc = stage_solids(ctx, solids, n_solids);   // the host-buffer entry stages them ahead of its U copies
     if (rc) return rc;
@@ -955,7 +970,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         I.heavy_count = &ctx->status.p->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
         I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status.p;
         CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        k_classify<4><<<grid_for(nC, 256), 256, 0, st>>>(I);
+        k_classify<256, 4><<<grid_for(nC, 256), 256, 0, st>>>(I);
         CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
         if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
         else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
@@ -1056,14 +1071,21 @@ static int ensure_fields(sdfibm_context *ctx, int n_solids) {
 
 int sdfibm_interact(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *U, double dt, double rhof,
                     double *As, double *Fs, double *Ts, double *Ct, double *force_torque) {
-    if (!ctx || !solids || n_solids <= 0 || !U || !As || !Fs || !Ts || !Ct || !force_torque)
+    if (!ctx || n_solids < 0 || (n_solids > 0 && (!solids || !force_torque)) || !U || !As || !Fs || !Ts || !Ct)
         return fail(SDFIBM_ERR_ARG, "sdfibm_interact: null argument");
-    if (!ctx->has_mesh || ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
+    if (!ctx->has_mesh || (n_solids > 0 && ctx->h_shapes.empty())) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    int rc = ensure_fields(ctx, n_solids);
+    int rc = ensure_fields(ctx, std::max(n_solids, 1));
     if (rc) return rc;
     const size_t nC = ctx->dm.n_cells;
     cudaStream_t st = ctx->stream;
+    if (n_solids == 0) {
+        rc = sdfibm_interact_device(ctx, nullptr, 0, ctx->dU.p, dt, rhof, ctx->dAs.p, ctx->dFs.p, ctx->dTs.p, ctx->dCt.p, nullptr);
+        if (rc) return rc;
+        memset(As, 0, sizeof(double) * nC); memset(Fs, 0, sizeof(double) * 3 * nC);
+        memset(Ts, 0, sizeof(double) * nC); memset(Ct, 0, sizeof(double) * nC);
+        return SDFIBM_OK;
+    }
     // the copy engines are FIFO across streams: the small solid upload the kernels depend on goes first
     rc = stage_solids(ctx, solids, n_solids);
     if (rc) return rc;
@@ -1087,7 +1109,8 @@ int sdfibm_interact(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_sol
 }
 
 int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *dU, const double *dCt) {
-    if (!ctx || !solids || n_solids <= 0 || !dU) return fail(SDFIBM_ERR_ARG, "sdfibm_fix_internal: null argument");
+    if (!ctx || n_solids < 0 || (n_solids > 0 && !solids) || !dU) return fail(SDFIBM_ERR_ARG, "sdfibm_fix_internal: null argument");
+    if (n_solids == 0) return SDFIBM_OK;   // Ct >= 4 nowhere
     if (!ctx->has_mesh) return fail(SDFIBM_ERR_STATE, "sdfibm_fix_internal: set mesh first");
     if (!dCt) dCt = ctx->last_Ct;
     if (!dCt) return fail(SDFIBM_ERR_STATE, "sdfibm_fix_internal: no Ct available (call interact first)");
@@ -1101,7 +1124,8 @@ int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids
 }
 
 int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *U) {
-    if (!ctx || !U || !solids || n_solids <= 0) return fail(SDFIBM_ERR_ARG, "sdfibm_fix_internal: null argument");
+    if (!ctx || !U || n_solids < 0 || (n_solids > 0 && !solids)) return fail(SDFIBM_ERR_ARG, "sdfibm_fix_internal: null argument");
+    if (n_solids == 0) return SDFIBM_OK;
     if (!ctx->has_mesh || !ctx->dCt.p || ctx->last_Ct != ctx->dCt.p)
         return fail(SDFIBM_ERR_STATE, "sdfibm_fix_internal: call sdfibm_interact (host buffers) first");
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1127,6 +1151,49 @@ int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return SDFIBM_OK;
+}
+
+__global__ void k_fill_unit_x(double *U, long long n_cells) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    U[3 * c] = 1.0; U[3 * c + 1] = 0.0; U[3 * c + 2] = 0.0;
+}
+
+int sdfibm_mean_field(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field, double *mean,
+                      double *sum_alpha_v) {
+    if (!ctx || !solids || n_solids <= 0 || !field || !mean) return fail(SDFIBM_ERR_ARG, "sdfibm_mean_field: null argument");
+    if (!ctx->has_mesh || ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_mean_field: set mesh and shapes first");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t nC = ctx->dm.n_cells;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx->sU.ensure(3 * nC));
+    CUDA_TRY(ctx->sOut.ensure(6 * nC));
+    CUDA_TRY(ctx->sFT.ensure(12 * (size_t)n_solids));
+    // solids at rest, dt = 1, rhof = 1: interact's per-solid "force" is sum(alpha V U) (solidcloud.cpp:414-416)
+    std::vector<sdfibm_solid_t> rest(solids, solids + n_solids);
+    for (auto &r : rest)
+        for (int d = 0; d < 3; ++d) r.vel[d] = r.omega[d] = 0.0;
+    double *tAs = ctx->sOut.p, *tFs = tAs + nC, *tTs = tFs + 3 * nC, *tCt = tTs + nC;
+    const double *keep_Ct = ctx->last_Ct;
+    const int keep_n = ctx->n_solids_last;
+    CUDA_TRY(cudaMemcpyAsync(ctx->sU.p, field, sizeof(double) * 3 * nC, cudaMemcpyHostToDevice, st));
+    int rc = sdfibm_interact_device(ctx, rest.data(), n_solids, ctx->sU.p, 1.0, 1.0, tAs, tFs, tTs, tCt, ctx->sFT.p);
+    if (!rc) {
+        k_fill_unit_x<<<grid_for((long long)nC, 256), 256, 0, st>>>(ctx->sU.p, (long long)nC);
+        rc = sdfibm_interact_device(ctx, rest.data(), n_solids, ctx->sU.p, 1.0, 1.0, tAs, tFs, tTs, tCt, ctx->sFT.p + 6 * (size_t)n_solids);
+    }
+    ctx->last_Ct = keep_Ct;   // the sampler leaves the coupling state of the last interact alone (its candidate lists are replaced)
+    ctx->n_solids_last = keep_n;
+    if (rc) return rc;
+    std::vector<double> ft(12 * (size_t)n_solids);
+    CUDA_TRY(cudaMemcpyAsync(ft.data(), ctx->sFT.p, sizeof(double) * ft.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int s = 0; s < n_solids; ++s) {
+        const double den = ft[6 * ((size_t)n_solids + s)];
+        for (int d = 0; d < 3; ++d) mean[3 * s + d] = ft[6 * (size_t)s + d] / den;
+        if (sum_alpha_v) sum_alpha_v[s] = den;
+    }
     return SDFIBM_OK;
 }
 

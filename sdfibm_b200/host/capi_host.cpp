@@ -4,6 +4,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "libmotion/motions.h"
 #include "libshape/shapefactory.h"
@@ -119,6 +120,13 @@ int sdfibm_host_get_forces(sdfibm_host_cloud *h, double *ft, double *fluid_ft) {
 }
 int sdfibm_host_get_masses(sdfibm_host_cloud *h, double *mass) {
     HOST_TRY({ for (label i = 0; i < h->cloud->size(); ++i) mass[i] = (*h->cloud)[i].getMass(); })
+}
+int sdfibm_host_mean_field(sdfibm_host_cloud *h, double *mean) {
+    HOST_TRY({
+        std::vector<double> m;
+        h->cloud->calcMeanField(m);
+        std::memcpy(mean, m.data(), sizeof(double) * m.size());
+    })
 }
 int sdfibm_host_set_collision_delta(sdfibm_host_cloud *h, double delta) { HOST_TRY(h->cloud->setCollisionDelta(delta)) }
 int sdfibm_host_reset_subiterations(void) { HOST_TRY(SolidCloud::resetSubIterations()) }

@@ -59,8 +59,14 @@ void SolidCloud::initFromDictionary(const Foam::word &dictfile) {   // :14-206
     const dictionary &meta = root.subDict("meta");
     m_ON_FLUID = Foam::readBool(meta.lookup("on_fluid"));
     m_ON_TWOD = Foam::readBool(meta.lookup("on_twod"));
-    if (meta.found("on_meanfield") || meta.found("sampler"))
-        log("note: the mean-field sampler (src/solidcloud.cpp:303-359) is outside the GPU path and is ignored");
+    if (meta.found("on_meanfield")) {   // :29-34
+        m_ON_MEANFIELD = true;
+        if (isMaster()) {
+            meanFieldFile.open(casePath(m_mesh, "meanfield.out"), std::fstream::out);
+            meanFieldFile << std::scientific;
+        }
+    }
+    if (meta.found("sampler")) m_sampler = Foam::word(meta.lookup("sampler"));
     m_gravity = meta.lookup("gravity");
     m_writeFrequency = (unsigned)meta.lookupOrDefault("writeFrequency", (label)1);
     if (meta.found("collision_delta")) m_collisionDelta = Foam::readScalar(meta.lookup("collision_delta"));
@@ -305,7 +311,55 @@ void SolidCloud::saveState() {   // :578-593
         statefile << (*this);
         statefile.flush();
     }
+    if (m_ON_MEANFIELD) this->writeMeanField();
     ++m_timeStepCounter;
+}
+
+// Mean-field sampler (:303-359): for every solid, the average of U over a SUBSTITUTE shape placed at the solid,
+// sum(alpha V U) / sum(alpha V) over that shape's candidate cells.  It is the interact path with other inputs: with the
+// solids at rest, dt = 1 and rhof = 1 the per-solid "force" of interact IS sum(alpha V U), and with U = (1,0,0) its x
+// component is sum(alpha V) — sdfibm_mean_field runs the same kernels twice on scratch outputs.  Unlike the reference this
+// does not overwrite Ct as a side effect and, in parallel, reduces on every rank instead of hanging on the master.
+void SolidCloud::calcMeanField(std::vector<double> &out) {
+    out.assign(3 * m_solids.size(), 0.0);
+    if (m_solids.empty() || m_sampler.empty()) return;
+    const auto sh = m_libshape.find(m_sampler);
+    if (sh == m_libshape.end()) throw std::runtime_error("Unrecognized sampler shape name " + m_sampler);
+    int sampler_index = -1;
+    {
+        const dictionary &shapes = m_solidDict.subDict("shapes");
+        int i = 0;
+        for (const auto &key : shapes.toc()) {
+            if (std::string(Foam::word(shapes.subDict(key).lookup("name"))) == m_sampler) sampler_index = i;
+            ++i;
+        }
+    }
+    ensureDevice();
+    const size_t n = m_solids.size();
+    std::vector<sdfibm_solid_t> recs(n);
+    for (size_t i = 0; i < n; ++i) m_solids[i].toRecord(recs[i], sampler_index);
+    std::vector<double> den(n);
+    check(sdfibm_mean_field(m_ctx, recs.data(), (int)n, cellData(m_Uf), out.data(), den.data()), "sdfibm_mean_field");
+    if (m_reduce) {   // :353-357 — reduce numerator and denominator, then divide
+        std::vector<double> nd(4 * n);
+        for (size_t i = 0; i < n; ++i) {
+            for (int d = 0; d < 3; ++d) nd[4 * i + d] = out[3 * i + d] * den[i];
+            nd[4 * i + 3] = den[i];
+        }
+        m_reduce(nd.data(), (int)nd.size());
+        for (size_t i = 0; i < n; ++i)
+            for (int d = 0; d < 3; ++d) out[3 * i + d] = nd[4 * i + d] / nd[4 * i + 3];
+    }
+}
+
+void SolidCloud::writeMeanField() {   // :303-313
+    if (m_sampler.empty()) return;
+    std::vector<double> mean;
+    calcMeanField(mean);
+    if (!isMaster()) return;
+    for (size_t i = 0; i < m_solids.size(); ++i) meanFieldFile << mean[3 * i] << ' ' << mean[3 * i + 1] << ' ' << mean[3 * i + 2] << ' ';
+    meanFieldFile << '\n';
+    meanFieldFile.flush();
 }
 
 std::ostream &operator<<(std::ostream &os, const SolidCloud &sc) {   // :595-614

@@ -31,6 +31,8 @@ private:
     bool m_ON_FLUID{true};
     bool m_ON_TWOD{false};
     bool m_ON_RESTART{false};
+    bool m_ON_MEANFIELD{false};
+    std::string m_sampler;           // name of the substitute shape of the mean-field sampler (meta.sampler)
     unsigned int m_timeStepCounter{0};
     unsigned int m_writeFrequency{1};
     scalar m_time{0};
@@ -54,6 +56,7 @@ private:
     EntityLibrary<forcer::IForcer> m_libforcer;
     std::ofstream statefile;
     std::ofstream logfile;
+    std::ofstream meanFieldFile;
 
     // device side
     sdfibm_context *m_ctx{nullptr};
@@ -93,6 +96,9 @@ public:
     void addMidEnvironment();
     void fixInternal(scalar dt);
     void initialCorrect();
+    void writeMeanField();
+    // mean of U over each solid's sampler shape, Σ αV·U / Σ αV (src/solidcloud.cpp:315-359); out[3 N]
+    void calcMeanField(std::vector<double> &out);
 
     // ---- additions of this implementation ----
     // cross-rank sum of the per-solid (F, T) array, replacing the 2N Foam::reduce calls (src/solidcloud.cpp:427-431)

@@ -33,6 +33,7 @@ SYMBOLS = {
     "sdfibm_host_get_solids": (C.c_int, [_VP, _VP]),
     "sdfibm_host_get_forces": (C.c_int, [_VP, _VP, _VP]),
     "sdfibm_host_get_masses": (C.c_int, [_VP, _VP]),
+    "sdfibm_host_mean_field": (C.c_int, [_VP, _VP]),
     "sdfibm_host_set_collision_delta": (C.c_int, [_VP, C.c_double]),
     "sdfibm_host_reset_subiterations": (C.c_int, []),
     "sdfibm_host_factory_has": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]),
@@ -151,6 +152,11 @@ class HostCloud:
         ft, fl = np.zeros((n, 6)), np.zeros((n, 6))
         check(self._lib.sdfibm_host_get_forces(self._h, capi.ptr(ft), capi.ptr(fl)))
         return ft, fl
+
+    def mean_field(self):
+        m = np.zeros((self.n_solids, 3))
+        check(self._lib.sdfibm_host_mean_field(self._h, capi.ptr(m)))
+        return m
 
     def masses(self):
         m = np.zeros(self.n_solids)

@@ -206,3 +206,47 @@ def test_full_size_properties_c4():
     assert np.array_equal(ref["list_cells"], cells[:off[120]])
     scale = np.abs(ref["FT"][:40]).max()
     assert np.abs(got["FT"][:40] - ref["FT"][:40]).max() <= REL_FORCE * scale * 100
+
+
+def test_empty_cloud_resets_the_fields():
+    """No solids: interact only zeroes As/Fs/Ts/Ct (reference src/solidcloud.cpp:438-441); fixInternal changes nothing."""
+    case = cases.case_c4(n=16, n_solids=2, n_side=1)
+    ctx = Context(0)
+    ctx.set_mesh(case["mesh"], False)
+    ctx.set_shapes(case["shapes"])
+    first = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
+    assert first["As"].max() > 0
+    out = ctx.interact(case["solids"][:0], case["U"], case["dt"], case["rhof"])
+    for k in ("As", "Fs", "Ts", "Ct"):
+        assert not out[k].any(), k
+    assert ctx.candidate_counts() == [0, 0, 0]
+    assert np.array_equal(ctx.fix_internal(case["solids"][:0], case["U"]), case["U"])
+
+
+def test_mean_field_sampler():
+    """SolidCloud::calcMeanField (src/solidcloud.cpp:315-359): sum(alpha V U) / sum(alpha V) over a substitute shape per
+    solid, against the same sums formed from the oracle's per-solid alpha (one solid at a time, so As == alpha)."""
+    case = cases.case_mixed3d(n=24, n_solids=6)
+    S = case["solids"][:6].copy()
+    S["shape"] = [0, 1, 2, 3, 4, 0]          # substitute shapes: Sphere, Ellipsoid, Box, Sphere+com, Box+com, Sphere
+    ctx = Context(0, cell_slots=8)
+    ctx.set_mesh(case["mesh"], False)
+    ctx.set_shapes(case["shapes"])
+    before = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
+    mean, den = ctx.mean_field(S, case["U"])
+    o = Oracle(case["mesh"], False)
+    V = case["mesh"].V
+    for i in range(len(S)):
+        one = S[i:i + 1].copy()
+        one["vel"] = 0
+        one["omega"] = 0
+        a = o.interact(case["shapes"], one, case["U"], 1.0, 1.0)["Ts"]       # unclamped alpha of this solid alone
+        if a.sum() == 0:
+            continue
+        ref_den = float((a * V).sum())
+        ref_mean = (a * V) @ case["U"] / ref_den
+        assert abs(den[i] - ref_den) <= 1e-10 * ref_den
+        assert np.abs(mean[i] - ref_mean).max() <= 1e-10 * max(1.0, np.abs(ref_mean).max())
+    # the sampler must not disturb the coupling state: fixInternal still uses the Ct of the last interact
+    assert np.array_equal(ctx.fix_internal(case["solids"], case["U"]),
+                          o.fix_internal(case["shapes"], case["solids"], before["Ct"], case["U"]))

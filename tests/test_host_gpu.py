@@ -105,3 +105,33 @@ def test_standalone_runner_3d(tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "solidDict.restart"))
     log = open(os.path.join(str(tmp_path), "cloud.log")).read()
     assert "FSI took" in log
+
+
+def test_mean_field_output(tmp_path):
+    """meta { on_meanfield 1; sampler <shape>; }: saveState appends one row of 3 N means to meanfield.out
+    (reference src/solidcloud.cpp:29-34,303-313,587-590) and leaves Ct / fixInternal alone."""
+    solids = [dict(shp_name="sph", mot_name="free", mat_name="heavy", pos=(1.6, 1.7, 1.5)),
+              dict(shp_name="box", mot_name="free", mat_name="light", pos=(3.1, 2.2, 2.6), euler=(10.0, 20.0, 30.0))]
+    meta = dict(on_fluid=1, on_twod=0, gravity=(0.0, 0.0, -9.81), on_meanfield=1, sampler="elo")
+    path = hc.write_case(tmp_path, meta, solids)
+    mesh = Mesh.hex_block((48, 48, 48), (0, 0, 0), (0.1, 0.1, 0.1))
+    U0 = cases.taylor_green(mesh.cc, 4.8)
+    hostapi.load().sdfibm_host_reset_subiterations()
+    cloud = hostapi.HostCloud(path, str(tmp_path), mesh, 1.0, start_time=0.0, U_init=U0)
+    cloud.interact(1e-3, 1e-3)
+    ct = cloud.field("Ct").copy()
+    cloud.save_state()
+    rows = open(os.path.join(str(tmp_path), "meanfield.out")).read().strip().split("\n")
+    assert len(rows) == 1 and len(rows[0].split()) == 6
+    got = np.array(rows[0].split(), dtype=float).reshape(2, 3)
+    assert np.allclose(got, cloud.mean_field(), rtol=1e-6)
+    # against the oracle: alpha of the sampler ellipsoid placed at each solid
+    table, index = hc.shape_table(solids)
+    o = Oracle(mesh, False)
+    ref = hc.oracle_solids(solids)
+    recs = ho.records(ref, [list(hc.SHAPES).index("elo")] * 2)
+    for i in range(2):
+        a = o.interact(table, recs[i:i + 1], U0, 1.0, 1.0)["Ts"]
+        w = a * mesh.V
+        assert np.abs(cloud.mean_field()[i] - w @ U0 / w.sum()).max() <= 1e-10
+    assert np.array_equal(cloud.field("Ct"), ct)
