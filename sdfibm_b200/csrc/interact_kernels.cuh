@@ -18,7 +18,6 @@
 
 #define TPB 128
 #define SLOT_HEAVY 4
-#define ENT_STAGE 48   // candidate records staged per warp in k_classify
 
 // ------------------------------------------------------------------------------------------------
 // geometry: apex / pyramid volume fraction (reference src/geometrictools.cpp:13-116)
@@ -125,12 +124,14 @@ __device__ __forceinline__ int quick_class(const DevSolid &S, D3 cc, float2 rad)
 // ------------------------------------------------------------------------------------------------
 // parameters shared by the classify / heavy / final kernels
 // ------------------------------------------------------------------------------------------------
-// one candidate of a solid bin: what the sphere-type pre-classification needs, inline
-struct BinEntry {
-    double x, y, z;    // solid centre
-    double r_out, r_in;
+// one candidate of a tile: what the fp32 sphere-type pre-classification needs, inline (32 bytes, two 16-byte loads)
+struct __align__(16) BinEntry {
+    float x, y, z;     // solid centre relative to the mesh origin
+    float r_out;       // certified outer radius + fp32 slack, rounded up
+    float r_in;        // certified inner radius - fp32 slack, rounded down
     int s;             // solid id
     int kind;
+    int pad;
 };
 
 struct InteractParams {
@@ -177,6 +178,7 @@ __device__ __forceinline__ void pair_terms(const DevSolid &S, D3 cc, D3 uf, doub
     fs_inc = f_ * dtINV;
 }
 
+// c = the caller's cell label (orig[position])
 __device__ __forceinline__ void store_cell(const InteractParams &P, int c, double as, D3 fs, double ts, double ct) {
     P.As[c] = (as < 1.0) ? as : 1.0;                                               // checkAlpha, :564-570 (std::min(As,1))
     P.Fs[3 * (long long)c] = fs.x;
@@ -225,81 +227,55 @@ __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_classify: thread per mesh cell
+// k_classify: thread per mesh cell (tile order).  The candidates of a cell are the solids binned on its tile —
+// one contiguous, id-sorted run of 32-byte records that the whole warp reads at the same address (broadcast) —
+// tested in fp32 against the fp32 centre copy: 16 bytes of HBM traffic per cell and no fp64 instruction
+// unless a plane / tilted 2-D solid (global list) is present.
 // ------------------------------------------------------------------------------------------------
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * NT + threadIdx.x;
     const bool live = c < m.n_cells;
     const long long nC = m.n_cells;
     const int lane = threadIdx.x & 31;
     int n_item = 0, n_heavy = 0;
-    D3 cc = {0.0, 0.0, 0.0};
-    float2 rad = m.rad_const;
-    int b = -1;
     if (live) {
-        cc = ld3(m.cc, c);
-        rad = cell_radius(m, c);
-        b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] + bin_coord(P.grid, cc.x, 0);
-    }
-    // The cells of a warp usually fall into a short run of consecutive bins, whose candidate records are
-    // contiguous: fetch the offsets with one load per lane and the records with coalesced 16-byte loads into
-    // shared memory, so the per-cell loop below has no dependent global loads.
-    __shared__ __align__(16) BinEntry s_ent[NT / 32][ENT_STAGE];
-    const int bmin = __reduce_min_sync(FULL, live ? b : 0x7fffffff), bmax = __reduce_max_sync(FULL, b);
-    int bi = 0, be = 0;
-    const BinEntry *E = P.bin_entries;
-    if (bmax >= 0) {
-        const int span = bmax - bmin + 1;
-        bool staged = span <= 31;
-        int off_l = 0, e0 = 0;
-        if (staged) {
-            off_l = (lane <= span) ? __ldg(P.bin_off + bmin + lane) : 0;
-            e0 = __shfl_sync(FULL, off_l, 0);
-            const int ne = __shfl_sync(FULL, off_l, span) - e0;
-            staged = ne <= ENT_STAGE;
-            if (staged) {
-                const int4 *src = reinterpret_cast<const int4 *>(P.bin_entries + e0);
-                int4 *dst = reinterpret_cast<int4 *>(s_ent[threadIdx.x >> 5]);
-                for (int i = lane; i < 3 * ne; i += 32) dst[i] = __ldg(src + i);
-                __syncwarp();
-                E = s_ent[threadIdx.x >> 5] - e0;
-            }
-        }
-        if (staged) {
-            const int rel = live ? b - bmin : 0;
-            bi = __shfl_sync(FULL, off_l, rel);
-            be = __shfl_sync(FULL, off_l, rel + 1);
-            if (!live) be = bi;
-        } else if (live) {
-            bi = __ldg(P.bin_off + b);
-            be = __ldg(P.bin_off + b + 1);
-        }
-    }
-    if (live) {
+        const float4 p = __ldg(m.cc32 + c);
+        const unsigned t = __ldg(m.tile_key + c);
+        int bi = __ldg(P.bin_off + t);
+        const int be = __ldg(P.bin_off + t + 1);
         int gi = 0;
         const int ge = P.status->n_global;
+        const float4 *E = reinterpret_cast<const float4 *>(P.bin_entries);
+        D3 cc = {0.0, 0.0, 0.0};
+        float2 rad = m.rad_const;
+        bool have_cc = false;
         while (bi < be || gi < ge) {
-            // merge the bin list and the global list in ascending solid id
+            // merge the tile list and the global list in ascending solid id
             int s, qc;
-            const int sb = (bi < be) ? E[bi].s : 0x7fffffff;
+            float4 e0 = {0.f, 0.f, 0.f, 0.f}, e1 = {0.f, 0.f, 0.f, 0.f};
+            int sb = 0x7fffffff;
+            if (bi < be) {
+                e0 = __ldg(E + 2 * (long long)bi);
+                e1 = __ldg(E + 2 * (long long)bi + 1);
+                sb = __float_as_int(e1.y);
+            }
             const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
             if (sb <= sg) {
-                // binned candidates carry the data of the sphere-type pre-classification inline
-                const BinEntry &e = E[bi];
                 s = sb;
                 ++bi;
-                if (e.kind == KIND_3D) {
-                    const double rx = cc.x - e.x, ry = cc.y - e.y, rz = cc.z - e.z;
-                    const double d2 = rx * rx + ry * ry + rz * rz;
-                    const double ro = e.r_out + (double)rad.x, ri = e.r_in - (double)rad.x;
-                    qc = (d2 > ro * ro) ? 0 : ((ri > 0.0 && d2 < ri * ri) ? 1 : 2);
-                } else qc = quick_class(P.solids[s], cc, rad);
+                const int kind = __float_as_int(e1.z);
+                const float dx = p.x - e0.x, dy = p.y - e0.y, dz = (kind == KIND_3D) ? p.z - e0.z : 0.f;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                const float r = (kind == KIND_3D) ? p.w : (m.rad_uniform ? m.rad_const.y : __ldg(&m.cell_rad[c].y));
+                const float ro = e0.w + r, ri = e1.x - r;
+                qc = (d2 > ro * ro) ? 0 : ((ri > 0.f && d2 < ri * ri) ? 1 : 2);
             } else {
                 s = sg;
                 ++gi;
+                if (!have_cc) { cc = ld3(m.cc, c); rad = cell_radius(m, c); have_cc = true; }
                 qc = quick_class(P.solids[s], cc, rad);
             }
             if (qc == 0) continue;
@@ -582,6 +558,7 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
     const int c = P.c_begin + blockIdx.x * blockDim.x + threadIdx.x;   // [c_begin, c_end): one chunk of the cell range
     const bool live = c < P.c_end;
     const long long nC = m.n_cells;
+    const int oc = live ? __ldg(m.orig + c) : 0;   // caller's cell label: U is read and the fields are written there
     const int n = live ? (int)P.n_item[c] : 0;
     const int e0 = live ? P.slots[c] : 0;       // slot 0, fetched together with n_item (meaningless when n == 0)
     const unsigned FULL = 0xffffffffu;
@@ -596,7 +573,7 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
         double vol = 1.0;
         if (n > 0) {
             cc = ld3(m.cc, c);
-            uf = ld3(P.U, c);
+            uf = ld3(P.U, oc);
             vol = __ldg(m.V + c);
         }
         for (int j = 0; j < nmax; ++j) {
@@ -631,7 +608,7 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
             if (__any_sync(FULL, have)) warp_accumulate(have, s, type, contrib, P.force_torque, P.pair_counts);
         }
     }
-    if (live) store_cell(P, c, as, fs, ts, ct);
+    if (live) store_cell(P, oc, as, fs, ts, ct);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -736,7 +713,8 @@ struct ReplayParams {
     const int *slots;
     int K;
     const int *root_count;
-    int *labels;                    // [n_cells*K] component label (min cell id) of flagged pairs
+    int *labels;                    // [n_cells*K] component label (min caller cell label) of flagged pairs
+    const int *inv;                 // caller's cell label -> position
     int *changed;
     unsigned long long *seed_key;   // [n_solids] min dist^2 bits over candidate cells
     int *seed_cell;                 // [n_solids]
@@ -755,7 +733,7 @@ __global__ void k_replay_init(ReplayParams P) {
     const int n = P.n_item[c];
         for (int j = 0; j < n; ++j) {
         const int e = P.slots[(long long)j * P.m.n_cells + c];
-        if ((e & 3) != 0 && P.root_count[e >> 3] > 1) P.labels[(long long)c * P.K + j] = c;
+        if ((e & 3) != 0 && P.root_count[e >> 3] > 1) P.labels[(long long)c * P.K + j] = __ldg(P.m.orig + c);
     }
 }
 
@@ -788,7 +766,7 @@ __global__ void k_replay_seed(ReplayParams P, int pass) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.m.n_cells) return;
     const D3 cc = ld3(P.m.cc, c);
-    const int b = (bin_coord(P.grid, cc.z, 2) * P.grid.n[1] + bin_coord(P.grid, cc.y, 1)) * P.grid.n[0] + bin_coord(P.grid, cc.x, 0);
+    const int b = (int)__ldg(P.m.tile_key + c);
     const int b0 = P.bin_off[b], b1 = P.bin_off[b + 1];
     for (int t = 0; t < (b1 - b0) + P.n_global; ++t) {
         const int s = (t < b1 - b0) ? P.bin_list[b0 + t] : P.global_list[t - (b1 - b0)];
@@ -796,7 +774,7 @@ __global__ void k_replay_seed(ReplayParams P, int pass) {
         const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
         const unsigned long long key = (unsigned long long)__double_as_longlong(magSqr3(cc - x));
         if (pass == 0) atomicMin(P.seed_key + s, key);
-        else if (key == P.seed_key[s]) atomicMin(P.seed_cell + s, c);
+        else if (key == P.seed_key[s]) atomicMin(P.seed_cell + s, __ldg(P.m.orig + c));
     }
     if (pass == 1) {
         const int n = P.n_item[c];
@@ -812,8 +790,9 @@ __global__ void k_replay_choose(ReplayParams P) {
     if (s >= P.n_solids) return;
     if (P.root_count[s] <= 1) { P.chosen[s] = -1; return; }
     int chosen = P.min_label[s]; // component of the first member cell in index order (cellenumerator.cpp:52-63)
-    const int g = P.seed_cell[s];
-    if (g >= 0 && g < P.m.n_cells) {
+    const int go = P.seed_cell[s];   // caller's label of the nearest cell centre (ties: lowest label)
+    if (go >= 0 && go < P.m.n_cells) {
+        const int g = P.inv[go];
         const int jj = find_member(P.n_item, P.slots, P.m.n_cells, g, s);
         if (jj >= 0) chosen = P.labels[(long long)g * P.K + jj]; // the nearest cell is a member: it is the seed
     }
@@ -833,7 +812,7 @@ __global__ void k_replay_mark(ReplayParams P) {
 // ------------------------------------------------------------------------------------------------
 // fixInternal (solidcloud.cpp:288-301)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_fix_internal(DevMesh m, const sdfibm_solid_t *solids, int n_solids, const double *Ct, double *U, int c_begin, int c_end) {
+__global__ void k_fix_internal(const double *cc, const sdfibm_solid_t *solids, int n_solids, const double *Ct, double *U, int c_begin, int c_end) {
     const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c_end) return;
     const double ct = Ct[c];
@@ -842,7 +821,7 @@ __global__ void k_fix_internal(DevMesh m, const sdfibm_solid_t *solids, int n_so
         if (id < n_solids) {
             const sdfibm_solid_t &S = solids[id];
             const D3 x = {S.pos[0], S.pos[1], S.pos[2]};
-            const D3 u = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(D3{S.omega[0], S.omega[1], S.omega[2]}, ld3(m.cc, c) - x);
+            const D3 u = D3{S.vel[0], S.vel[1], S.vel[2]} + cross3(D3{S.omega[0], S.omega[1], S.omega[2]}, ld3(cc, c) - x);
             U[3 * (long long)c] = u.x;
             U[3 * (long long)c + 1] = u.y;
             U[3 * (long long)c + 2] = u.z;
@@ -851,8 +830,8 @@ __global__ void k_fix_internal(DevMesh m, const sdfibm_solid_t *solids, int n_so
 }
 
 // ------------------------------------------------------------------------------------------------
-// candidate list extraction (parity output, off the timed path): pairs in cell order, then a stable
-// radix sort by (solid, type) gives ascending cell ids inside every segment (std::set order).
+// candidate list extraction (parity output, off the timed path): pairs in position order, a stable radix sort by the
+// caller's cell label, then a stable radix sort by (solid, type): ascending cell ids inside every segment (std::set order).
 // ------------------------------------------------------------------------------------------------
 __global__ void k_list_count(const unsigned char *n_item, const int *slots, const unsigned char *excluded, int K, int n_cells, int *cnt) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -864,7 +843,7 @@ __global__ void k_list_count(const unsigned char *n_item, const int *slots, cons
     cnt[c] = n;
 }
 __global__ void k_list_emit(const unsigned char *n_item, const int *slots, const unsigned char *excluded, int K, int n_cells,
-                            const int *off, unsigned *keys, int *vals) {
+                            const int *off, const int *orig, unsigned *keys, int *vals) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     int o = off[c];
@@ -873,7 +852,7 @@ __global__ void k_list_emit(const unsigned char *n_item, const int *slots, const
         const int e = slots[(long long)j * n_cells + c];
         if ((e & 3) == 0 || (excluded && excluded[(long long)c * K + j])) continue;
         keys[o] = (unsigned)(3 * (e >> 3) + ((e & 3) - 1));
-        vals[o] = c;
+        vals[o] = orig[c];   // caller's cell label
         ++o;
     }
 }

@@ -83,15 +83,23 @@ struct DevMesh {
     const unsigned *hex_topo; // hex meshes: 3 words per cell, 4-bit cell-local vertex slot of every face vertex
     const unsigned *nb_hint;  // per cell: for each signed axis direction (-x,+x,-y,+y,-z,+z) the position in cellCells[c] of
                               // the best-aligned face neighbour, 3 bits each (7 = none)
+    // Cells are renumbered at upload into TILE ORDER (position i = rank of the cell in a stable sort by the key of the
+    // spatial tile holding its centre; ~256 cells per tile).  Every per-cell array above/below is stored in position
+    // order; orig[i] is the caller's cell label of position i (U is read and As/Fs/Ts/Ct are written through it).
+    const int *orig;          // position -> caller's cell label
+    const float4 *cc32;       // per position: fp32 (centre - origin, vertex-cloud radius rounded up): conservative pre-classification
+    const unsigned *tile_key; // per position: linear index of its tile in the tile grid (= solid-bin index)
+    double origin[3];         // centre of the mesh bounds
     float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
     int rad_uniform;
     int is_hex;             // every cell has 8 points / 6 faces and every face 4 points
     int two_d;
 };
 
+// the tile grid: static per mesh; solids are binned on it every step
 struct BinGrid {
     double lo[3];
-    double inv_b;
+    double inv[3];
     int n[3];
     int n_bins;
 };
@@ -113,7 +121,7 @@ __device__ __forceinline__ D3 ld3(const double *__restrict__ p, long long i) {
 
 __device__ __forceinline__ int bin_coord(const BinGrid &g, double x, int d) {
     // monotone in x (the same expression maps cells and solid boxes); __double2int_rd saturates, so +-1e300 is safe
-    const int i = __double2int_rd((x - g.lo[d]) * g.inv_b);
+    const int i = __double2int_rd((x - g.lo[d]) * g.inv[d]);
     return min(max(i, 0), g.n[d] - 1);
 }
 
@@ -225,6 +233,63 @@ __global__ void k_cell_radius(DevMesh m, float2 *rad, int *bad, float *rmax) {
         atomicMin((int *)&rmax[2], __float_as_int(m3[0]));
         atomicMin((int *)&rmax[3], __float_as_int(mxy[0]));
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0b  tile-order renumbering of the cells (once per mesh)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_tile_keys(const double *cc, int n_cells, BinGrid g, unsigned *keys, int *ids) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const D3 x = ld3(cc, c);
+    keys[c] = (unsigned)((bin_coord(g, x.z, 2) * g.n[1] + bin_coord(g, x.y, 1)) * g.n[0] + bin_coord(g, x.x, 0));
+    ids[c] = c;
+}
+__global__ void k_perm_inverse(const int *orig, int n_cells, int *inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_cells) inv[orig[i]] = i;
+}
+__global__ void k_perm_counts(const int *off, const int *orig, int n_cells, int *cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_cells) return;
+    cnt[i] = (i < n_cells) ? off[orig[i] + 1] - off[orig[i]] : 0;
+}
+// vals_p[off_p[i] + k] = map(vals[off[orig[i]] + k])
+__global__ void k_perm_csr(const int *off, const int *vals, const int *orig, const int *off_p, const int *map, int n_cells, int *vals_p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const int b = off[orig[i]], n = off[orig[i] + 1] - b, o = off_p[i];
+    for (int k = 0; k < n; ++k) {
+        const int v = vals[b + k];
+        vals_p[o + k] = map ? map[v] : v;
+    }
+}
+__global__ void k_perm_cells(const double *cc, const double *V, const int *orig, int n_cells, double *cc_p, double *V_p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const int c = orig[i];
+    cc_p[3 * (long long)i] = cc[3 * (long long)c];
+    cc_p[3 * (long long)i + 1] = cc[3 * (long long)c + 1];
+    cc_p[3 * (long long)i + 2] = cc[3 * (long long)c + 2];
+    V_p[i] = V[c];
+}
+// fp32 copy of the centres relative to the mesh origin + the per-cell vertex-cloud radius (already rounded up)
+__global__ void k_cc32(const double *cc_p, const float2 *rad, int n_cells, double ox, double oy, double oz, float4 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    out[i] = make_float4((float)(cc_p[3 * (long long)i] - ox), (float)(cc_p[3 * (long long)i + 1] - oy),
+                         (float)(cc_p[3 * (long long)i + 2] - oz), rad[i].x);
+}
+// [cmin, cmax] of the caller's cell labels over each chunk of positions (host-buffer pipeline)
+__global__ void k_chunk_ranges(const int *orig, int n_cells, int n_chunk, int *cmin, int *cmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    // chunk k covers positions [n*k/n_chunk, n*(k+1)/n_chunk)
+    int k = (int)(((long long)i * n_chunk) / n_cells);
+    while ((long long)n_cells * k / n_chunk > i) --k;
+    while ((long long)n_cells * (k + 1) / n_chunk <= i) ++k;
+    atomicMin(cmin + k, orig[i]);
+    atomicMax(cmax + k, orig[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -346,18 +411,24 @@ __global__ void k_bin_sort(const int *bin_off, int *bin_list, int n_bins, int bi
 
 #include "interact_kernels.cuh"
 
-// bin_list (sorted per bin) -> inline candidate records read by k_classify
-__global__ void k_bin_entries(const int *bin_off, const int *bin_list, int n_bins, int bin_cap, const DevSolid *solids, BinEntry *out) {
+// bin_list (sorted per bin) -> inline fp32 candidate records read by k_classify.  The radii carry the fp32 slack:
+// coordinates relative to the mesh origin are bounded by M = half extent + r_out + rad, so the fp32 distance is off by
+// < 1e-6 M; slack = 4e-6 M keeps the three-way test conservative (the exact fp64 predicates decide everything it does not).
+__global__ void k_bin_entries(const int *bin_off, const int *bin_list, int n_bins, int bin_cap, const DevSolid *solids, BinEntry *out,
+                              double ox, double oy, double oz, double half_ext, double rad_max) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = min(bin_off[n_bins], bin_cap);
     if (pos >= total) return;
     const int s = bin_list[pos];
     const DevSolid &S = solids[s];
+    const double slack = 4e-6 * (half_ext + S.r_out + rad_max);
     BinEntry e;
-    e.x = S.pos[0]; e.y = S.pos[1]; e.z = S.pos[2];
-    e.r_out = S.r_out; e.r_in = S.r_in;
+    e.x = (float)(S.pos[0] - ox); e.y = (float)(S.pos[1] - oy); e.z = (float)(S.pos[2] - oz);
+    e.r_out = __double2float_ru(S.r_out + slack);
+    e.r_in = __double2float_rd(S.r_in - slack);
     e.s = s;
     e.kind = S.kind;
+    e.pad = 0;
     out[pos] = e;
 }
 
@@ -500,7 +571,12 @@ struct sdfibm_context {
     DevBuf<float2> cell_rad;
     DevBuf<double> magSf;
     DevBuf<double2> face_rec;
-    DevBuf<unsigned> hex_topo, nb_hint;
+    DevBuf<unsigned> hex_topo, nb_hint, tile_key;
+    DevBuf<int> orig, inv;      // tile-order renumbering: position -> caller's label and back
+    DevBuf<double> cc_orig;     // cell centres in the caller's order (fixInternal)
+    DevBuf<float4> cc32;
+    int chunk_cmin[8] = {0}, chunk_cmax[8] = {0};   // caller-label range of every position chunk (host-buffer pipeline)
+    double half_ext = 0.0;
     double bmin[3], bmax[3];
     float rad3_max = 0.f, radxy_max = 0.f;
     // shapes
@@ -627,6 +703,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->points.release(); ctx->cc.release(); ctx->V.release(); ctx->Cf.release(); ctx->Sf.release();
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
+    ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
     ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb_hint.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
     ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
@@ -675,20 +752,107 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     cudaStream_t st = ctx->stream;
     const size_t nC = m->n_cells, nP = m->n_points, nF = m->n_faces;
     int rc;
+    // ---- the tile grid: ~256 cells per tile (8x8x4 mean cell sizes; 16x16 columns for one-cell-thick 2-D meshes) ----
+    {
+        BinGrid &g = ctx->grid;
+        double ext[3], T[3];
+        for (int k = 0; k < 3; ++k) ext[k] = std::max(m->bounds_max[k] - m->bounds_min[k], 1e-300);
+        if (two_d) {
+            const double h = std::sqrt(ext[0] * ext[1] / (double)nC);
+            T[0] = T[1] = 16.0 * h; T[2] = 2.0 * ext[2];
+        } else {
+            const double h = std::cbrt(ext[0] * ext[1] * ext[2] / (double)nC);
+            T[0] = T[1] = 8.0 * h; T[2] = 4.0 * h;
+        }
+        for (;;) {
+            double nt = 1;
+            for (int k = 0; k < 3; ++k) nt *= std::max(1.0, std::ceil(ext[k] / T[k]));
+            if (nt <= 6.4e7) break;
+            for (int k = 0; k < 3; ++k) T[k] *= 1.26;
+        }
+        g.n_bins = 1;
+        ctx->half_ext = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            g.lo[k] = m->bounds_min[k];
+            g.inv[k] = 1.0 / T[k];
+            g.n[k] = (int)std::max(1.0, std::ceil(ext[k] / T[k]));
+            g.n_bins *= g.n[k];
+            ctx->half_ext = std::max(ctx->half_ext, 0.5 * ext[k]);
+        }
+    }
+    DevMesh &d = ctx->dm;
+    for (int k = 0; k < 3; ++k) d.origin[k] = 0.5 * (m->bounds_min[k] + m->bounds_max[k]);
     if ((rc = upload(ctx->points, m->points, 3 * nP, st))) return rc;
-    if ((rc = upload(ctx->cc, m->cell_centres, 3 * nC, st))) return rc;
-    if ((rc = upload(ctx->V, m->cell_volumes, nC, st))) return rc;
     if ((rc = upload(ctx->Cf, m->face_centres, 3 * nF, st))) return rc;
     if ((rc = upload(ctx->Sf, m->face_areas, 3 * nF, st))) return rc;
-    if ((rc = upload(ctx->cp_off, m->cell_points_off, nC + 1, st))) return rc;
-    if ((rc = upload(ctx->cp, m->cell_points, (size_t)m->cell_points_off[nC], st))) return rc;
-    if ((rc = upload(ctx->cf_off, m->cell_faces_off, nC + 1, st))) return rc;
-    if ((rc = upload(ctx->cf, m->cell_faces, (size_t)m->cell_faces_off[nC], st))) return rc;
     if ((rc = upload(ctx->fp_off, m->face_points_off, nF + 1, st))) return rc;
     if ((rc = upload(ctx->fp, m->face_points, (size_t)m->face_points_off[nF], st))) return rc;
-    if ((rc = upload(ctx->nb_off, m->cell_cells_off, nC + 1, st))) return rc;
-    if ((rc = upload(ctx->nb, m->cell_cells, (size_t)m->cell_cells_off[nC], st))) return rc;
+    if ((rc = upload(ctx->cc_orig, m->cell_centres, 3 * nC, st))) return rc;
+    // ---- renumber the cells into tile order: stable sort of the cell labels by tile key ----
+    CUDA_TRY(ctx->orig.ensure(nC));
+    CUDA_TRY(ctx->inv.ensure(nC));
+    CUDA_TRY(ctx->tile_key.ensure(nC));
+    {
+        DevBuf<unsigned> keys;
+        DevBuf<int> ids;
+        DevBuf<unsigned char> tmp;
+        CUDA_TRY(keys.ensure(nC));
+        CUDA_TRY(ids.ensure(nC));
+        k_tile_keys<<<grid_for(nC, 256), 256, 0, st>>>(ctx->cc_orig.p, (int)nC, ctx->grid, keys.p, ids.p);
+        size_t sb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sb, keys.p, ctx->tile_key.p, ids.p, ctx->orig.p, (int)nC, 0, 32, st);
+        CUDA_TRY(tmp.ensure(sb));
+        cub::DeviceRadixSort::SortPairs(tmp.p, sb, keys.p, ctx->tile_key.p, ids.p, ctx->orig.p, (int)nC, 0, 32, st);
+        k_perm_inverse<<<grid_for(nC, 256), 256, 0, st>>>(ctx->orig.p, (int)nC, ctx->inv.p);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(st));
+        keys.release(); ids.release(); tmp.release();
+    }
+    {
+        // per-cell arrays and CSR connectivity, permuted; cellCells values are mapped to positions
+        DevBuf<double> o_V;
+        DevBuf<int> o_off, o_val, cnt;
+        DevBuf<unsigned char> tmp;
+        if ((rc = upload(o_V, m->cell_volumes, nC, st))) return rc;
+        CUDA_TRY(ctx->cc.ensure(3 * nC));
+        CUDA_TRY(ctx->V.ensure(nC));
+        k_perm_cells<<<grid_for(nC, 256), 256, 0, st>>>(ctx->cc_orig.p, o_V.p, ctx->orig.p, (int)nC, ctx->cc.p, ctx->V.p);
+        CUDA_TRY(cnt.ensure(nC + 1));
+        struct Csr { const int32_t *off, *val; DevBuf<int> *d_off, *d_val; const int *map; };
+        Csr csr[3] = {{m->cell_points_off, m->cell_points, &ctx->cp_off, &ctx->cp, nullptr},
+                      {m->cell_faces_off, m->cell_faces, &ctx->cf_off, &ctx->cf, nullptr},
+                      {m->cell_cells_off, m->cell_cells, &ctx->nb_off, &ctx->nb, ctx->inv.p}};
+        for (auto &a : csr) {
+            const size_t nv = (size_t)a.off[nC];
+            if ((rc = upload(o_off, a.off, nC + 1, st))) return rc;
+            if ((rc = upload(o_val, a.val, nv, st))) return rc;
+            CUDA_TRY(a.d_off->ensure(nC + 1));
+            CUDA_TRY(a.d_val->ensure(nv));
+            k_perm_counts<<<grid_for(nC + 1, 256), 256, 0, st>>>(o_off.p, ctx->orig.p, (int)nC, cnt.p);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, a.d_off->p, (int)nC + 1, st);
+            CUDA_TRY(tmp.ensure(tb));
+            cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, a.d_off->p, (int)nC + 1, st);
+            k_perm_csr<<<grid_for(nC, 256), 256, 0, st>>>(o_off.p, o_val.p, ctx->orig.p, a.d_off->p, a.map, (int)nC, a.d_val->p);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(st));   // the host arrays of this pass are consumed; o_off / o_val are reused
+        }
+        o_V.release(); o_off.release(); o_val.release(); cnt.release(); tmp.release();
+    }
+    {
+        DevBuf<int> rng;
+        CUDA_TRY(rng.ensure(16));
+        int init[16];
+        for (int k = 0; k < 8; ++k) { init[k] = 0x7fffffff; init[8 + k] = -1; }
+        CUDA_TRY(cudaMemcpyAsync(rng.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        k_chunk_ranges<<<grid_for(nC, 256), 256, 0, st>>>(ctx->orig.p, (int)nC, sdfibm_context::N_CHUNK, rng.p, rng.p + 8);
+        CUDA_TRY(cudaMemcpyAsync(init, rng.p, sizeof(init), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int k = 0; k < 8; ++k) { ctx->chunk_cmin[k] = init[k]; ctx->chunk_cmax[k] = init[8 + k]; }
+        rng.release();
+    }
     CUDA_TRY(ctx->cell_rad.ensure(nC));
+    CUDA_TRY(ctx->cc32.ensure(nC));
     CUDA_TRY(ctx->slots.ensure(nC * ctx->K));
     CUDA_TRY(ctx->n_item.ensure(nC));
     {
@@ -696,12 +860,12 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         CUDA_TRY(ctx->heavy.ensure(cap));
         CUDA_TRY(ctx->heavy_res.ensure(cap));
     }
-    DevMesh &d = ctx->dm;
     d.n_cells = m->n_cells; d.n_points = m->n_points; d.n_faces = m->n_faces;
     d.points = ctx->points.p; d.cc = ctx->cc.p; d.V = ctx->V.p; d.Cf = ctx->Cf.p; d.Sf = ctx->Sf.p;
     d.cp_off = ctx->cp_off.p; d.cp = ctx->cp.p; d.cf_off = ctx->cf_off.p; d.cf = ctx->cf.p;
     d.fp_off = ctx->fp_off.p; d.fp = ctx->fp.p; d.nb_off = ctx->nb_off.p; d.nb = ctx->nb.p;
     d.cell_rad = ctx->cell_rad.p;
+    d.orig = ctx->orig.p; d.cc32 = ctx->cc32.p; d.tile_key = ctx->tile_key.p;
     d.two_d = two_d ? 1 : 0;
     // hexahedral fast path?
     bool is_hex = true;
@@ -740,6 +904,7 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     CUDA_TRY(ctx->nb_hint.ensure(nC));
     d.nb_hint = ctx->nb_hint.p;
     k_nb_hint<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->nb_hint.p);
+    k_cc32<<<grid_for(nC, 256), 256, 0, st>>>(ctx->cc.p, ctx->cell_rad.p, (int)nC, d.origin[0], d.origin[1], d.origin[2], ctx->cc32.p);
     CUDA_TRY(cudaGetLastError());
     int h_bad = 0;
     float h_rmax[4];
@@ -773,38 +938,6 @@ int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) 
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SDFIBM_OK;
-}
-
-// choose the solid-binning grid for this step
-static void choose_grid(sdfibm_context *ctx) {
-    double rmax = 0.0;
-    for (auto &s : ctx->h_shapes)
-        if (s.kind != KIND_PLANE) rmax = std::max(rmax, s.r_out);
-    double ext[3], vol = 1.0;
-    int nd = 0;
-    for (int d = 0; d < 3; ++d) {
-        ext[d] = std::max(ctx->bmax[d] - ctx->bmin[d], 1e-300);
-        vol *= ext[d];
-    }
-    double b = std::max(0.75 * rmax, 1e-300);
-    // never more than ~4M bins and never finer than the cells
-    double bmin_cells = std::cbrt(vol / std::max(1.0, (double)ctx->dm.n_cells)) * 2.0;
-    b = std::max(b, bmin_cells);
-    for (;;) {
-        double nb = 1;
-        for (int d = 0; d < 3; ++d) nb *= std::max(1.0, std::ceil(ext[d] / b));
-        if (nb <= 4.0e6) break;
-        b *= 1.26;
-    }
-    (void)nd;
-    BinGrid &g = ctx->grid;
-    g.inv_b = 1.0 / b;
-    g.n_bins = 1;
-    for (int d = 0; d < 3; ++d) {
-        g.lo[d] = ctx->bmin[d];
-        g.n[d] = (int)std::max(1.0, std::ceil(ext[d] / b));
-        g.n_bins *= g.n[d];
-    }
 }
 
 static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, double dt, double rhof, double *dAs,
@@ -872,7 +1005,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         R.m = ctx->dm; R.solids = ctx->solids.p; R.n_item = ctx->n_item.p; R.slots = ctx->slots.p; R.K = ctx->K;
         R.root_count = ctx->root_count.p; R.labels = ctx->labels.p; R.changed = ctx->changed.p;
         R.seed_key = ctx->seed_key.p; R.seed_cell = ctx->seed_cell.p; R.min_label = ctx->min_label.p;
-        R.chosen = ctx->chosen.p; R.excluded = ctx->excluded.p; R.grid = ctx->grid; R.bin_off = ctx->bin_off.p;
+        R.chosen = ctx->chosen.p; R.excluded = ctx->excluded.p; R.inv = ctx->inv.p; R.grid = ctx->grid; R.bin_off = ctx->bin_off.p;
         R.bin_list = ctx->bin_list.p; R.global_list = ctx->global_list.p; R.n_global = ctx->last.n_global;
         R.n_solids = n_solids;
         const int g = grid_for(nC, 256);
@@ -910,8 +1043,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
     cudaStream_t st = ctx->stream;
     const int nC = ctx->dm.n_cells;
     if (!replay) {
-        choose_grid(ctx);
-        const BinGrid &g = ctx->grid;
+        const BinGrid &g = ctx->grid;   // the static tile grid
         CUDA_TRY(ctx->solids.ensure(n_solids));
         CUDA_TRY(ctx->bin_count.ensure((size_t)g.n_bins + 1));
         CUDA_TRY(ctx->bin_off.ensure((size_t)g.n_bins + 1));
@@ -951,7 +1083,8 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
                                                                               ctx->global_list.p, ctx->status.p);
             CUDA_TRY(ctx->bin_entries.ensure(ctx->bin_list.n));
             k_bin_entries<<<grid_for((long long)F.bin_cap, 256), 256, 0, st>>>(ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap,
-                                                                            ctx->solids.p, ctx->bin_entries.p);
+                                                                            ctx->solids.p, ctx->bin_entries.p, ctx->dm.origin[0], ctx->dm.origin[1],
+                                                                            ctx->dm.origin[2], ctx->half_ext, (double)std::max(ctx->rad3_max, ctx->radxy_max));
             ctx->launches += 5;
         } else {
             // keep the binning of the first pass; restore the counters the status word carries
@@ -984,19 +1117,38 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
                 if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(dU) + 3 * c0, ctx->pipe.U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
                 CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
             }
-            for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
-                const long long c0 = (long long)nC * i / sdfibm_context::N_CHUNK, c1 = (long long)nC * (i + 1) / sdfibm_context::N_CHUNK;
-                if (c1 <= c0) continue;
-                I.c_begin = (int)c0; I.c_end = (int)c1;
-                CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[i], 0));
-                k_final<4><<<grid_for(c1 - c0, 256), 256, 0, st>>>(I);
+            // Position chunk i touches the caller's cells [chunk_cmin[i], chunk_cmax[i]] (tile order follows the mesh in slabs, so
+            // for block-structured numberings chunk i == cell range i): it waits for the U range holding its largest label, and
+            // cell range j leaves once the last position chunk that intersects it is done.
+            const int NCH = sdfibm_context::N_CHUNK;
+            auto range_of = [&](int c) { int j = (int)(((long long)c * NCH) / nC); while ((long long)nC * j / NCH > c) --j; while ((long long)nC * (j + 1) / NCH <= c) ++j; return j; };
+            int i_last[sdfibm_context::N_CHUNK];
+            for (int j = 0; j < NCH; ++j) i_last[j] = -1;
+            for (int i = 0; i < NCH; ++i) {
+                if (ctx->chunk_cmax[i] < 0) continue;
+                for (int j = range_of(ctx->chunk_cmin[i]); j <= range_of(ctx->chunk_cmax[i]); ++j) i_last[j] = i;
+            }
+            int last_pos_chunk = 0;
+            for (int i = 0; i < NCH; ++i) if (ctx->chunk_cmax[i] >= 0) last_pos_chunk = i;
+            for (int i = 0; i < NCH; ++i) {
+                const long long p0 = (long long)nC * i / NCH, p1 = (long long)nC * (i + 1) / NCH;
+                if (p1 > p0) {
+                    I.c_begin = (int)p0; I.c_end = (int)p1;
+                    CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
+                    k_final<4><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
+                }
                 CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
-                CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
-                const size_t n = (size_t)(c1 - c0);
-                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.As + c0, dAs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
-                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Fs + 3 * c0, dFs + 3 * c0, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->s_out));
-                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ts + c0, dTs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
-                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ct + c0, dCt + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                for (int j = 0; j < NCH; ++j) {
+                    if (!(i_last[j] == i || (i_last[j] < 0 && i == last_pos_chunk))) continue;
+                    const size_t c0 = (size_t)nC * j / NCH, c1 = (size_t)nC * (j + 1) / NCH;
+                    if (c1 <= c0) continue;
+                    const size_t n = c1 - c0;
+                    CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
+                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.As + c0, dAs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Fs + 3 * c0, dFs + 3 * c0, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ts + c0, dTs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ct + c0, dCt + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                }
             }
             ctx->launches += sdfibm_context::N_CHUNK - 1;
         } else {
@@ -1117,7 +1269,7 @@ int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids
     CUDA_TRY(cudaSetDevice(ctx->device));
     int rc = stage_solids(ctx, solids, n_solids);
     if (rc) return rc;
-    k_fix_internal<<<grid_for(ctx->dm.n_cells, 256), 256, 0, ctx->stream>>>(ctx->dm, ctx->solids_in.p, n_solids, dCt, dU, 0, ctx->dm.n_cells);
+    k_fix_internal<<<grid_for(ctx->dm.n_cells, 256), 256, 0, ctx->stream>>>(ctx->cc_orig.p, ctx->solids_in.p, n_solids, dCt, dU, 0, ctx->dm.n_cells);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SDFIBM_OK;
@@ -1143,7 +1295,7 @@ int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
         const size_t c0 = nC * i / sdfibm_context::N_CHUNK, c1 = nC * (i + 1) / sdfibm_context::N_CHUNK;
         if (c1 <= c0) continue;
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[i], 0));
-        k_fix_internal<<<grid_for((long long)(c1 - c0), 256), 256, 0, st>>>(ctx->dm, ctx->solids_in.p, n_solids, ctx->dCt.p, ctx->dU.p, (int)c0, (int)c1);
+        k_fix_internal<<<grid_for((long long)(c1 - c0), 256), 256, 0, st>>>(ctx->cc_orig.p, ctx->solids_in.p, n_solids, ctx->dCt.p, ctx->dU.p, (int)c0, (int)c1);
         CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
         CUDA_TRY(cudaMemcpyAsync(U + 3 * c0, ctx->dU.p + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyDeviceToHost, ctx->s_out));
@@ -1247,13 +1399,16 @@ int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells
     cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, nC + 1, st);
     CUDA_TRY(tmp.ensure(tb));
     cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, nC + 1, st);
-    k_list_emit<<<grid_for(nC, 256), 256, 0, st>>>(ctx->n_item.p, ctx->slots.p, excl, ctx->K, nC, off.p, keys.p, vals.p);
-    size_t sb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sb, keys.p, keys2.p, vals.p, vals2.p, (int)total, 0, 32, st);
-    CUDA_TRY(tmp.ensure(sb));
-    cub::DeviceRadixSort::SortPairs(tmp.p, sb, keys.p, keys2.p, vals.p, vals2.p, (int)total, 0, 32, st);
+    k_list_emit<<<grid_for(nC, 256), 256, 0, st>>>(ctx->n_item.p, ctx->slots.p, excl, ctx->K, nC, off.p, ctx->orig.p, keys.p, vals.p);
+    size_t sb = 0, sb2 = 0;
+    // stable sort by the caller's cell label, then stable sort by (solid, type)
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, (unsigned *)vals.p, (unsigned *)vals2.p, keys.p, keys2.p, (int)total, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, sb2, keys2.p, keys.p, vals2.p, vals.p, (int)total, 0, 32, st);
+    CUDA_TRY(tmp.ensure(std::max(sb, sb2)));
+    cub::DeviceRadixSort::SortPairs(tmp.p, sb, (unsigned *)vals.p, (unsigned *)vals2.p, keys.p, keys2.p, (int)total, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(tmp.p, sb2, keys2.p, keys.p, vals2.p, vals.p, (int)total, 0, 32, st);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(cells, vals2.p, sizeof(int) * total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(cells, vals.p, sizeof(int) * total, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     cnt.release(); off.release(); vals.release(); vals2.release(); keys.release(); keys2.release(); tmp.release();
     return SDFIBM_OK;
