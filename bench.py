@@ -234,8 +234,11 @@ def main():
     dFT = torch.empty(nS, 6, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 
+    from sdfibm_b200 import capi
+    solids_pinned = capi.pinned_like(np.ascontiguousarray(case["solids"], dtype=capi.SOLID_DTYPE))   # the host side's own solid array
+
     def step_device():
-        ctx.interact_device(case["solids"], dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(), dFs.data_ptr(),
+        ctx.interact_device(solids_pinned, dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(), dFs.data_ptr(),
                             dTs.data_ptr(), dCt.data_ptr(), dFT.data_ptr())
         if world > 1:
             dist.all_reduce(dFT)  # replaces the 2N Foam::reduce calls of solidcloud.cpp:427-431
@@ -246,6 +249,7 @@ def main():
         torch.cuda.synchronize()
 
     split = []
+    host_us = []
 
     def timed(fn, steps, warmup):
         with torch.cuda.stream(ext):
@@ -255,6 +259,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             kern_ms, pipe_ms = [], []
             split.clear()
+            host_us.clear()
             e0.record(ext)
             for _ in range(steps):
                 fn()
@@ -262,6 +267,7 @@ def main():
                 kern_ms.append(t["interact_kernels_ms"])
                 split.append((t["classify_ms"], t["heavy_ms"], t["final_ms"], t["connectivity_ms"], t["binning_ms"]))
                 pipe_ms.append(t["pipeline_ms"])
+                host_us.append(list(ctx.last_host_timings().values()))
             e1.record(ext)
             barrier()
             ms = e0.elapsed_time(e1)
@@ -335,7 +341,8 @@ def main():
             "kernel_ms": {"k_classify": split_mean[0], "k_heavy": split_mean[1], "k_final": split_mean[2],
                           "k_connectivity+finalise": split_mean[3], "solid_binning": split_mean[4],
                           "interact_kernels": kern_ms, "pipeline_device": pipe_ms, "step_wall_on_stream": ms_per_step,
-                          "heavy_items": stats["heavy_items"]},
+                          "heavy_items": stats["heavy_items"],
+                          "host_us": dict(zip(("stage_solids", "enqueue", "wait_gpu", "call"), [float(x) for x in np.mean(np.array(host_us), axis=0)]))},
             "roofline": {"bound": "hbm", "kernel": "k_classify+k_heavy+k_final (the interact kernels; k_heavy dominates)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src["source"] if traffic_src else None,

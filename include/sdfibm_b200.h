@@ -21,6 +21,7 @@
 #ifndef SDFIBM_B200_H
 #define SDFIBM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -118,6 +119,10 @@ int sdfibm_device_count(int *count);
 /* One context per rank/GPU; owns one CUDA stream.  replaces SolidCloud ctor device part (solidcloud.cpp:209-217). */
 int sdfibm_create(int device, sdfibm_context **ctx);
 int sdfibm_destroy(sdfibm_context *ctx);
+/* Page-locked host memory for the per-step arrays the host side owns (solid states, U, the four fields): copies from / to
+ * such memory are asynchronous and skip the library's staging copy.  Optional — any host pointer is accepted everywhere. */
+int sdfibm_alloc_pinned(size_t bytes, void **out);
+int sdfibm_free_pinned(void *p);
 /* max solids that may touch one mesh cell (default 3); call before sdfibm_set_mesh */
 int sdfibm_set_cell_slots(sdfibm_context *ctx, int slots);
 
@@ -170,6 +175,9 @@ int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]);
  * [0] solid preparation + binning, [1] k_classify, [2] k_heavy, [3] k_final, [4] connectivity + finalise,
  * [5] whole pipeline */
 int sdfibm_last_timings(sdfibm_context *ctx, double ms[6]);
+/* host wall time of the last interact, in microseconds: [0] staging the solid states, [1] enqueue / graph launch,
+ * [2] waiting for the GPU, [3] the whole call */
+int sdfibm_last_host_timings(sdfibm_context *ctx, double us[4]);
 
 /* ---- collision step (solidcloud.cpp:477-519, libcollision/) -------------------------
  * delta = UGrid cell size.  HEAD passes 2*m_radiusB = -2 (solidcloud.cpp:74-75,245) which yields

@@ -70,7 +70,10 @@ SYMBOLS = {
     "sdfibm_candidate_counts": (C.c_int, [_VP, c_int64_p]),
     "sdfibm_candidate_lists": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "sdfibm_last_stats": (C.c_int, [_VP, c_int64_p]),
+    "sdfibm_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "sdfibm_free_pinned": (C.c_int, [_VP]),
     "sdfibm_last_timings": (C.c_int, [_VP, c_double_p]),
+    "sdfibm_last_host_timings": (C.c_int, [_VP, c_double_p]),
     "sdfibm_collide": (C.c_int, [_VP, _VP, C.c_int, C.c_double, _VP, C.c_int64, c_int64_p, _VP]),
     "sdfibm_stream": (C.c_int, [_VP, C.POINTER(_VP)]),
     "sdfibm_synchronize": (C.c_int, [_VP]),
@@ -116,3 +119,16 @@ def ptr(a):
         return C.c_void_p(a)
     assert a.flags["C_CONTIGUOUS"]
     return C.c_void_p(a.ctypes.data)
+
+
+def pinned_like(a):
+    """Copy of `a` in page-locked host memory from sdfibm_alloc_pinned (never freed: meant for long-lived per-step buffers)."""
+    import numpy as np
+
+    a = np.ascontiguousarray(a)
+    p = C.c_void_p()
+    check(load().sdfibm_alloc_pinned(max(a.nbytes, 1), C.byref(p)))
+    buf = (C.c_char * max(a.nbytes, 1)).from_address(p.value)
+    out = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+    out[...] = a
+    return out

@@ -110,6 +110,11 @@ class Context:
         capi.check(self._lib.sdfibm_last_stats(self._h, s))
         return dict(flagged_solids=int(s[0]), launches=int(s[1]), bin_entries=int(s[2]), heavy_items=int(s[3]))
 
+    def last_host_timings(self):
+        t = (C.c_double * 4)()
+        capi.check(self._lib.sdfibm_last_host_timings(self._h, t))
+        return {"stage_us": t[0], "enqueue_us": t[1], "wait_us": t[2], "call_us": t[3]}
+
     def last_timings(self):
         t = (C.c_double * 6)()
         capi.check(self._lib.sdfibm_last_timings(self._h, t))

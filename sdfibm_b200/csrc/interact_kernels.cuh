@@ -145,7 +145,7 @@ struct InteractParams {
     const BinEntry *bin_entries; // bin_list materialised after the per-bin sort
     const int *global_list;
     const double *U;
-    double dtINV, rhof;
+    const double *scal;     // device: {1/dt, rhof} of this step (uploaded per step so that a captured graph stays valid)
     double *As, *Fs, *Ts, *Ct;
     double *force_torque;   // [6*n_solids], zeroed
     unsigned *pair_counts;  // [3*n_solids], zeroed
@@ -232,7 +232,7 @@ __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, cons
 // tested in fp32 against the fp32 centre copy: 16 bytes of HBM traffic per cell and no fp64 instruction
 // unless a plane / tilted 2-D solid (global list) is present.
 // ------------------------------------------------------------------------------------------------
-template <int NT, int MINB>
+template <int NT, int MINB, bool HAS_GLOBAL>
 __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
@@ -246,44 +246,48 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
         const unsigned t = __ldg(m.tile_key + c);
         int bi = __ldg(P.bin_off + t);
         const int be = __ldg(P.bin_off + t + 1);
-        int gi = 0;
-        const int ge = P.status->n_global;
         const float4 *E = reinterpret_cast<const float4 *>(P.bin_entries);
-        D3 cc = {0.0, 0.0, 0.0};
-        float2 rad = m.rad_const;
-        bool have_cc = false;
-        while (bi < be || gi < ge) {
-            // merge the tile list and the global list in ascending solid id
-            int s, qc;
-            float4 e0 = {0.f, 0.f, 0.f, 0.f}, e1 = {0.f, 0.f, 0.f, 0.f};
-            int sb = 0x7fffffff;
-            if (bi < be) {
-                e0 = __ldg(E + 2 * (long long)bi);
-                e1 = __ldg(E + 2 * (long long)bi + 1);
-                sb = __float_as_int(e1.y);
-            }
-            const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
-            if (sb <= sg) {
-                s = sb;
-                ++bi;
-                const int kind = __float_as_int(e1.z);
-                const float dx = p.x - e0.x, dy = p.y - e0.y, dz = (kind == KIND_3D) ? p.z - e0.z : 0.f;
-                const float d2 = dx * dx + dy * dy + dz * dz;
-                const float r = (kind == KIND_3D) ? p.w : (m.rad_uniform ? m.rad_const.y : __ldg(&m.cell_rad[c].y));
-                const float ro = e0.w + r, ri = e1.x - r;
-                qc = (d2 > ro * ro) ? 0 : ((ri > 0.f && d2 < ri * ri) ? 1 : 2);
-            } else {
-                s = sg;
-                ++gi;
-                if (!have_cc) { cc = ld3(m.cc, c); rad = cell_radius(m, c); have_cc = true; }
-                qc = quick_class(P.solids[s], cc, rad);
-            }
-            if (qc == 0) continue;
+        // one pre-classified candidate -> slot record
+        auto emit = [&](int s, int qc) {
+            if (qc == 0) return;
             if (n_item < P.K) {
                 P.slots[(long long)n_item * nC + c] = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
                 n_heavy += (qc == 2);
                 ++n_item;
             } else P.status->slot_overflow = 1;
+        };
+        // fp32 three-way test of a binned candidate (two 16-byte records)
+        auto test32 = [&](float4 e0, float4 e1) {
+            const int kind = __float_as_int(e1.z);
+            const float dx = p.x - e0.x, dy = p.y - e0.y, dz = (kind == KIND_3D) ? p.z - e0.z : 0.f;
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            const float r = (kind == KIND_3D) ? p.w : (m.rad_uniform ? m.rad_const.y : __ldg(&m.cell_rad[c].y));
+            const float ro = e0.w + r, ri = e1.x - r;
+            return (d2 > ro * ro) ? 0 : ((ri > 0.f && d2 < ri * ri) ? 1 : 2);
+        };
+        if (!HAS_GLOBAL) {
+            for (; bi < be; ++bi) {
+                const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
+                emit(__float_as_int(e1.y), test32(e0, e1));
+            }
+        } else {
+            // planes / tilted 2-D solids are tested by every cell: merge the tile list and the global list in ascending solid id
+            int gi = 0;
+            const int ge = P.status->n_global;
+            const D3 cc = ld3(m.cc, c);
+            const float2 rad = cell_radius(m, c);
+            while (bi < be || gi < ge) {
+                float4 e0 = {0.f, 0.f, 0.f, 0.f}, e1 = {0.f, 0.f, 0.f, 0.f};
+                int sb = 0x7fffffff;
+                if (bi < be) {
+                    e0 = __ldg(E + 2 * (long long)bi);
+                    e1 = __ldg(E + 2 * (long long)bi + 1);
+                    sb = __float_as_int(e1.y);
+                }
+                const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
+                if (sb <= sg) { ++bi; emit(sb, test32(e0, e1)); }
+                else { ++gi; emit(sg, quick_class(P.solids[sg], cc, rad)); }
+            }
         }
         P.n_item[c] = (unsigned char)n_item;
     }
@@ -387,9 +391,18 @@ __device__ __forceinline__ void eval_vertex_to_smem(HeavySmem &sm, const DevMesh
 }
 
 #define HEAVY_CTAS_PER_SM 5
-template <int CTAS, bool PREFETCH>
+// BAL: the cut faces of the warp's 32 cells are pooled and dealt out evenly to the lanes (a lane's own cell has 0..6 cut
+// faces, so the per-lane loop leaves most lanes idle behind the slowest one); a face is still evaluated by the same
+// instruction sequence on the same inputs, so nothing changes bit-wise.
+struct HeavyTask {
+    unsigned short nib;      // cell-local slots of the face's four vertices (face order), 4 bits each
+    unsigned char lane, f;   // owner lane and face index
+};
+template <int CTAS, bool PREFETCH, bool BAL>
 __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     __shared__ HeavySmem sm;
+    __shared__ double s_farea[BAL ? 6 * TPB : 1];
+    __shared__ HeavyTask s_task[BAL ? 6 * TPB : 1];
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
@@ -469,6 +482,117 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             }
         }
         __syncwarp();
+        if (BAL) {
+            auto PT = [&](int col, int l) { return D3{sm.px[l * TPB + col], sm.py[l * TPB + col], sm.pz[l * TPB + col]}; };
+            auto PH = [&](int col, int l) { return sm.phi[l * TPB + col]; };
+            // ---- A: cell type and the class of each face: 0 = entirely outside, 1 = entirely inside, 2 = cut ----
+            int type = 0;
+            unsigned fcls = 0;
+            int ncut = 0;
+            if (valid) {
+                int n_in = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) n_in += sm.in[j * TPB + tid];
+                if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
+                else if (n_in != 0) {
+                    type = 4;
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) {
+                        const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
+                        const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
+                        const int npos = (PH(tid, nib & 0xf) > 0) + (PH(tid, (nib >> 4) & 0xf) > 0) + (PH(tid, (nib >> 8) & 0xf) > 0) + (PH(tid, (nib >> 12) & 0xf) > 0);
+                        const unsigned cls = (npos == 4) ? 0u : (npos == 0) ? 1u : 2u;
+                        fcls |= cls << (2 * f);
+                        ncut += (cls == 2u);
+                        if (cls != 0u) {   // the face record is consumed in phase D, after the pooled area math: start fetching it now
+                            const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(m.face_rec + 4 * (long long)face));
+                        }
+                    }
+                }
+            }
+            if (type == 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.cc + 3 * (long long)c));
+            // ---- B: pool the cut faces of the warp, face-index major: consecutive tasks belong to different cells, so the
+            //      lanes of a round read different shared-memory columns (the layout is conflict free per column) ----
+            int total = 0;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+                const bool cut = ((fcls >> (2 * f)) & 3u) == 2u;
+                const unsigned bal = __ballot_sync(FULL, cut);
+                if (cut) {
+                    const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
+                    HeavyTask t;
+                    t.nib = (unsigned short)((w >> (16 * (f & 1))) & 0xffffu);
+                    t.lane = (unsigned char)lane;
+                    t.f = (unsigned char)f;
+                    s_task[wbase * 6 + total + __popc(bal & ((1u << lane) - 1u))] = t;
+                }
+                total += __popc(bal);
+            }
+            (void)ncut;
+            __syncwarp();
+            // ---- C: one pooled face per lane per round: calcFaceArea (:74-96) ----
+            for (int u = lane; u < total; u += 32) {
+                const HeavyTask t = s_task[wbase * 6 + u];
+                const int col = wbase + t.lane;
+                const int l[4] = {t.nib & 0xf, (t.nib >> 4) & 0xf, (t.nib >> 8) & 0xf, (t.nib >> 12) & 0xf};
+                const double ph[4] = {PH(col, l[0]), PH(col, l[1]), PH(col, l[2]), PH(col, l[3])};
+                const D3 A = PT(col, l[0]);
+                D3 B = PT(col, l[1]);
+                double phiB = ph[1];
+                if (!(ph[0] * ph[1] <= 0)) {
+                    B = PT(col, l[2]);
+                    phiB = ph[2];
+                    if (!(ph[0] * ph[2] <= 0)) { B = PT(col, l[3]); phiB = ph[3]; }
+                }
+                const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - B);
+                double area = 0.0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
+                    const D3 O = PT(col, l[e]), A2 = PT(col, l[(e + 1) & 3]);
+                    area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
+                }
+                s_farea[t.f * TPB + col] = area;
+            }
+            __syncwarp();
+            // ---- D: combine ----
+            if (valid) {
+                double volume = 0.0;
+                if (type == 4) {
+                    double dummy;
+                    type = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                    D3 apex;
+                    {
+                        const D3 A = PT(tid, 0);
+                        const double phiA = PH(tid, 0);
+                        D3 B = {0.0, 0.0, 0.0};
+                        double phiB = 0.0;
+                        for (int i = 1; i < 8; ++i) {
+                            B = PT(tid, i);
+                            phiB = PH(tid, i);
+                            if (phiA * phiB <= 0) break;
+                        }
+                        apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
+                        if (m.two_d) apex.z = 0.0;
+                    }
+#pragma unroll
+                    for (int f = 0; f < 6; ++f) {
+                        const unsigned cls = (fcls >> (2 * f)) & 3u;
+                        if (cls == 0u) continue;                                    // eps_f = 0: adds +0.0 (:107-108)
+                        const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
+                        const double2 *fr = m.face_rec + 4 * (long long)face;
+                        const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2), r3 = __ldg(fr + 3);
+                        const double eps_f = (cls == 1u) ? 1.0 : s_farea[f * TPB + tid] / r3.x;   // :109-116
+                        const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
+                        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
+                    }
+                }
+                P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));
+            }
+            __syncwarp();
+            continue;
+        }
         if (valid) {
             int type = 0;
             double volume = 0.0;
@@ -538,6 +662,243 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_heavy_dedupe: hexahedral path, CTA-cooperative.  A batch of B consecutive queue items is a spatially
+// compact patch of one or a few solids' boundary shells (the queue is filled tile by tile), so its cells share
+// most of their vertices and every cut face is shared by exactly two of its cells.  The batch is processed in
+// phases with the work re-distributed over the CTA between phases:
+//   1  every (solid, vertex) reference is inserted into a shared-memory hash set -> dense list of UNIQUE vertices
+//   2  the unique vertices are evaluated (world2local + predicate + filtered SDF), one per thread per round
+//   3  every item classifies its cell and its six faces; cut faces are inserted into the (re-used) hash set
+//   4  the unique cut faces are evaluated (calcFaceAreaFraction), one per thread per round
+//   5  every boundary item combines its faces: apex, centre test, sum of pyramid volumes
+// A vertex or face is evaluated by the SAME instruction sequence whichever cell asks for it, so sharing the result
+// is bit-identical to per-cell evaluation.  Items that do not fit the fixed-capacity lists (pathological queue
+// order) fall back to the self-contained per-item evaluation.
+// ------------------------------------------------------------------------------------------------
+#define HD_EMPTY 0xffffffffffffffffull
+#define HD_NONE 0xffffu
+#define HD_EPS0 0xfffeu    // face entirely outside: contributes +0.0 (:107-108)
+#define HD_EPS1 0xfffdu    // face entirely inside: eps_f = 1 (:109-110)
+
+template <int B>
+struct HeavyDedupeSmem {
+    static constexpr int NV = 4 * B;   // unique vertices of a batch
+    static constexpr int NF = 3 * B;   // unique cut faces of a batch
+    static constexpr int HT = 8 * B;   // hash slots: >= every insert of a phase (8 B vertex / 6 B face references)
+    unsigned long long key[HT];
+    double vx[NV], vy[NV], vz[NV], vphi[NV];
+    double feps[NF];
+    int2 ulist[NV];                    // unique vertex work list: (point label, solid)
+    int fface[NF];                     // unique face work list: face label ...
+    ushort4 fvi[NF];                   // ... and the dense indices of its four vertices, in the face's own order
+    unsigned short val[HT];
+    unsigned char vflag[NV];           // bit 0: strictly inside (isInside), bit 1: filtered phi > 0
+    int n_uv, n_uf;
+};
+
+template <int HT>
+__device__ __forceinline__ unsigned hd_hash(unsigned a, unsigned b) {
+    return ((a * 2654435761u) ^ (b * 0x9E3779B1u + 0x7F4A7C15u)) * 0x85EBCA6Bu >> 7 & (unsigned)(HT - 1);
+}
+
+// calcFaceAreaFraction of a cut quadrilateral face (geometrictools.cpp:74-116); vertices in the face's own order
+__device__ __forceinline__ double cut_face_eps(const D3 p[4], const double ph[4], double magSf) {
+    const D3 A = p[0];
+    D3 Bp = p[1];
+    double phiB = ph[1];
+    if (!(ph[0] * ph[1] <= 0)) {
+        Bp = p[2];
+        phiB = ph[2];
+        if (!(ph[0] * ph[2] <= 0)) { Bp = p[3]; phiB = ph[3]; }
+    }
+    const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - Bp);
+    double area = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
+        const D3 O = p[e], A2 = p[(e + 1) & 3];
+        area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
+    }
+    return area / magSf;
+}
+
+template <int B, int CTAS>
+__global__ void __launch_bounds__(B, CTAS) k_heavy_dedupe(InteractParams P) {
+    using SM = HeavyDedupeSmem<B>;
+    extern __shared__ __align__(16) unsigned char hd_raw[];
+    SM &sm = *reinterpret_cast<SM *>(hd_raw);
+    const DevMesh &m = P.m;
+    const int tid = threadIdx.x;
+    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
+    for (int i = tid; i < SM::HT; i += B) sm.key[i] = HD_EMPTY;
+    if (tid == 0) { sm.n_uv = 0; sm.n_uf = 0; }
+    __syncthreads();
+    for (long long k0 = (long long)blockIdx.x * B; k0 < n; k0 += (long long)gridDim.x * B) {
+        const long long k = k0 + tid;
+        const bool valid = k < n;
+        int c = 0, s = 0;
+        unsigned tw0 = 0, tw1 = 0, tw2 = 0;
+        int fid[6] = {0, 0, 0, 0, 0, 0};
+        unsigned short hv[8];
+        // ---- phase 1: unique (solid, vertex) references ----
+        if (valid) {
+            const int2 it = __ldg(P.heavy + k);
+            c = it.x;
+            s = it.y;
+            const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
+            const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
+            const int vid[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+            tw0 = __ldg(m.hex_topo + 3 * (long long)c);
+            tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1);
+            tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
+            const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
+            const int2 f01 = __ldg(cf2), f23 = __ldg(cf2 + 1), f45 = __ldg(cf2 + 2);
+            fid[0] = f01.x; fid[1] = f01.y; fid[2] = f23.x; fid[3] = f23.y; fid[4] = f45.x; fid[5] = f45.y;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const unsigned long long key = ((unsigned long long)(unsigned)s << 32) | (unsigned)vid[v];
+                unsigned h = hd_hash<SM::HT>((unsigned)vid[v], (unsigned)s);
+                for (;;) {
+                    const unsigned long long old = atomicCAS(&sm.key[h], HD_EMPTY, key);
+                    if (old == HD_EMPTY) {
+                        const int idx = atomicAdd(&sm.n_uv, 1);
+                        if (idx < SM::NV) { sm.val[h] = (unsigned short)idx; sm.ulist[idx] = make_int2(vid[v], s); }
+                        else sm.val[h] = HD_NONE;
+                        break;
+                    }
+                    if (old == key) break;
+                    h = (h + 1) & (unsigned)(SM::HT - 1);
+                }
+                hv[v] = (unsigned short)h;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: evaluate the unique vertices; the hash set is recycled for the faces ----
+        // dense indices of the cell's 8 vertices, 16 bits each (packed: indexed dynamically by the face topology below)
+        unsigned long long vlo = 0, vhi = 0;
+        bool slow = false;
+        if (valid) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const unsigned short x = sm.val[hv[v]];
+                slow = slow || (x == HD_NONE);
+                if (v < 4) vlo |= (unsigned long long)x << (16 * v);
+                else vhi |= (unsigned long long)x << (16 * (v - 4));
+            }
+        }
+        auto VI = [&](unsigned l) -> unsigned { return (unsigned)(((l & 4u) ? vhi : vlo) >> (16 * (l & 3u))) & 0xffffu; };
+        const int nuv = min(sm.n_uv, SM::NV);
+        __syncthreads();                       // every val[] of the vertex phase has been read
+        for (int i = tid; i < SM::HT; i += B) sm.key[i] = HD_EMPTY;
+        for (int u = tid; u < nuv; u += B) {
+            const int2 w = sm.ulist[u];
+            const DevSolid &S = P.solids[w.y];
+            const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+            const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+            const D3 p = ld3(m.points, w.x);
+            double ph;
+            const bool in = shape_eval<true>(P.shapes[S.shape].s, world2local(q, t, p), ph);
+            sm.vx[u] = p.x; sm.vy[u] = p.y; sm.vz[u] = p.z; sm.vphi[u] = ph;
+            sm.vflag[u] = (unsigned char)((in ? 1 : 0) | (ph > 0 ? 2 : 0));
+        }
+        __syncthreads();
+        // ---- phase 3: cell type; unique cut faces ----
+        int type = 0;
+        unsigned short fh[6] = {HD_EPS0, HD_EPS0, HD_EPS0, HD_EPS0, HD_EPS0, HD_EPS0};
+        if (valid && !slow) {
+            int n_in = 0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) n_in += sm.vflag[VI(v)] & 1;
+            if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
+            else if (n_in != 0) {
+                type = 4;   // boundary cell; centre test in phase 5
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
+                    const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
+                    ushort4 fv;
+                    fv.x = (unsigned short)VI(nib & 0xf); fv.y = (unsigned short)VI((nib >> 4) & 0xf); fv.z = (unsigned short)VI((nib >> 8) & 0xf); fv.w = (unsigned short)VI((nib >> 12) & 0xf);
+                    const int npos = ((sm.vflag[fv.x] >> 1) & 1) + ((sm.vflag[fv.y] >> 1) & 1) + ((sm.vflag[fv.z] >> 1) & 1) + ((sm.vflag[fv.w] >> 1) & 1);
+                    if (npos == 4) continue;
+                    if (npos == 0) { fh[f] = HD_EPS1; continue; }
+                    const unsigned long long key = ((unsigned long long)(unsigned)s << 32) | (unsigned)fid[f];
+                    unsigned h = hd_hash<SM::HT>((unsigned)fid[f], (unsigned)s);
+                    for (;;) {
+                        const unsigned long long old = atomicCAS(&sm.key[h], HD_EMPTY, key);
+                        if (old == HD_EMPTY) {
+                            const int idx = atomicAdd(&sm.n_uf, 1);
+                            if (idx < SM::NF) { sm.val[h] = (unsigned short)idx; sm.fface[idx] = fid[f]; sm.fvi[idx] = fv; }
+                            else sm.val[h] = HD_NONE;
+                            break;
+                        }
+                        if (old == key) break;
+                        h = (h + 1) & (unsigned)(SM::HT - 1);
+                    }
+                    fh[f] = (unsigned short)h;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 4: evaluate the unique cut faces ----
+        if (type == 4) {
+#pragma unroll
+            for (int f = 0; f < 6; ++f)
+                if (fh[f] < HD_EPS1) { fh[f] = sm.val[fh[f]]; slow = slow || (fh[f] == HD_NONE); }
+        }
+        const int nuf = min(sm.n_uf, SM::NF);
+        __syncthreads();                       // every val[] of the face phase has been read
+        for (int i = tid; i < SM::HT; i += B) sm.key[i] = HD_EMPTY;   // ready for the next batch
+        if (tid == 0) { sm.n_uv = 0; sm.n_uf = 0; }
+        for (int w = tid; w < nuf; w += B) {
+            const ushort4 fv = sm.fvi[w];
+            const D3 p[4] = {{sm.vx[fv.x], sm.vy[fv.x], sm.vz[fv.x]}, {sm.vx[fv.y], sm.vy[fv.y], sm.vz[fv.y]},
+                             {sm.vx[fv.z], sm.vy[fv.z], sm.vz[fv.z]}, {sm.vx[fv.w], sm.vy[fv.w], sm.vz[fv.w]}};
+            const double ph[4] = {sm.vphi[fv.x], sm.vphi[fv.y], sm.vphi[fv.z], sm.vphi[fv.w]};
+            const double magSf = __ldg(&m.face_rec[4 * (long long)sm.fface[w] + 3].x);
+            sm.feps[w] = cut_face_eps(p, ph, magSf);
+        }
+        __syncthreads();
+        // ---- phase 5: combine ----
+        if (valid) {
+            double volume = 0.0;
+            if (slow) heavy_eval_general(P, c, s, type, volume);
+            else if (type == 4) {
+                const DevSolid &S = P.solids[s];
+                const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+                const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
+                double dummy;
+                type = shape_eval<false>(P.shapes[S.shape].s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
+                D3 apex;
+                {
+                    const unsigned i0 = VI(0);
+                    const D3 A = {sm.vx[i0], sm.vy[i0], sm.vz[i0]};
+                    const double phiA = sm.vphi[i0];
+                    unsigned ib = VI(7);             // the FIRST i >= 1 with phiA * phi_i <= 0, else the last vertex
+#pragma unroll
+                    for (int i = 6; i >= 1; --i) { const unsigned ii = VI(i); if (phiA * sm.vphi[ii] <= 0) ib = ii; }
+                    const D3 Bp = {sm.vx[ib], sm.vy[ib], sm.vz[ib]};
+                    const double phiB = sm.vphi[ib];
+                    apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - Bp);
+                    if (m.two_d) apex.z = 0.0;
+                }
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                    if (fh[f] == HD_EPS0) continue;
+                    const double eps_f = (fh[f] == HD_EPS1) ? 1.0 : sm.feps[fh[f]];
+                    const double2 *fr = m.face_rec + 4 * (long long)fid[f];
+                    const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2);
+                    const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
+                    volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
+                }
+            }
+            P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));   // type 0: no vertex inside -> not a member
+        }
+        // the next batch's phase 1 touches key/val/ulist/n_uv only; vx..vflag/feps are rewritten after its first barrier
+    }
+}
+
 __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
     for (long long k = (long long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long long)gridDim.x * TPB) {
@@ -569,6 +930,7 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
     double as = 0.0, ts = 0.0, ct = 0.0;
     D3 fs = {0.0, 0.0, 0.0};
     if (nmax > 0) {
+        const double dtINV = __ldg(P.scal);
         D3 cc = {0, 0, 0}, uf = {0, 0, 0};
         double vol = 1.0;
         if (n > 0) {
@@ -597,7 +959,7 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
                 if (type != 0 && !skip) {
                     const double alpha = (type == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol;   // solidcloud.cpp:408-410
                     D3 fi;
-                    pair_terms(P.solids[s], cc, uf, vol, alpha, P.dtINV, fi, contrib);   // :384-390,411-421
+                    pair_terms(P.solids[s], cc, uf, vol, alpha, dtINV, fi, contrib);   // :384-390,411-421
                     as += alpha;
                     fs = fs + fi;
                     ts += alpha;
@@ -624,7 +986,14 @@ struct ConnParams {
     int *root_count; // [n_solids] zeroed
 };
 
-__device__ __forceinline__ bool key_less(double ka, int ca, double kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
+// The key of a (cell, solid) pair is the fp32 squared distance between the fp32 copies of the cell centre and the solid
+// centre, ties broken by the cell position: any strict total order certifies connectivity, this one is cheap and mostly
+// decreases towards the solid centre.
+__device__ __forceinline__ bool key_less(float ka, int ca, float kb, int cb) { return ka < kb || (ka == kb && ca < cb); }
+__device__ __forceinline__ float conn_key(float4 p, const float *x) {
+    const float dx = p.x - x[0], dy = p.y - x[1], dz = p.z - x[2];
+    return dx * dx + dy * dy + dz * dz;
+}
 
 // slot index of solid s among the members of cell nb, or -1
 __device__ __forceinline__ int find_member(const unsigned char *n_item, const int *slots, long long nC, int nb, int s) {
@@ -642,46 +1011,45 @@ __global__ void k_connectivity(ConnParams P) {
     const int n = P.n_item[c];
     if (n == 0) return;
     const long long nC = P.m.n_cells;
-    const D3 cc = ld3(P.m.cc, c);
-    const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
-    const unsigned hint = __ldg(P.m.nb_hint + c);
+    const float4 p = __ldg(P.m.cc32 + c);
     for (int j = 0; j < n; ++j) {
         const int e = P.slots[(long long)j * nC + c];
         if ((e & 3) == 0) continue;
         const int s = e >> 3;
-        const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
-        const D3 r = cc - x;
-        const double kc = magSqr3(r);
+        const float *x = P.solids[s].pos32;
+        const float kc = conn_key(p, x);
         // try the face neighbour that lies towards the solid centre first: almost always a member with a smaller key
-        const double ax = fabs(r.x), ay = fabs(r.y), az = fabs(r.z);
+        const float rx = p.x - x[0], ry = p.y - x[1], rz = p.z - x[2];
+        const float ax = fabsf(rx), ay = fabsf(ry), az = fabsf(rz);
         const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
-        const double comp = axis == 0 ? r.x : axis == 1 ? r.y : r.z;
-        const int first = (int)((hint >> (3 * (2 * axis + (comp > 0 ? 0 : 1)))) & 7u);
-        bool has_parent = false;
-        if (first < nb1 - nb0) {
-            const int nb = __ldg(P.m.nb + nb0 + first);
-            if (find_member(P.n_item, P.slots, nC, nb, s) >= 0 && key_less(magSqr3(ld3(P.m.cc, nb) - x), nb, kc, c)) has_parent = true;
-        }
-        for (int k = nb0; k < nb1 && !has_parent; ++k) {
-            if (k - nb0 == first) continue;
-            const int nb = __ldg(P.m.nb + k);
-            if (find_member(P.n_item, P.slots, nC, nb, s) >= 0) {
-                const double kn = magSqr3(ld3(P.m.cc, nb) - x);
-                if (key_less(kn, nb, kc, c)) has_parent = true;
+        const float comp = axis == 0 ? rx : axis == 1 ? ry : rz;
+        const int first = __ldg(P.m.nb6 + 6 * (long long)c + 2 * axis + (comp > 0 ? 0 : 1));
+        bool has_parent = first >= 0 && find_member(P.n_item, P.slots, nC, first, s) >= 0 &&
+                          key_less(conn_key(__ldg(P.m.cc32 + first), x), first, kc, c);
+        if (!has_parent) {
+            const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
+            for (int k = nb0; k < nb1 && !has_parent; ++k) {
+                const int nb = __ldg(P.m.nb + k);
+                if (nb == first) continue;
+                if (find_member(P.n_item, P.slots, nC, nb, s) >= 0 && key_less(conn_key(__ldg(P.m.cc32 + nb), x), nb, kc, c)) has_parent = true;
             }
         }
         if (!has_parent) atomicAdd(P.root_count + s, 1);
     }
 }
 
-__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status) {
+// per-step totals for the status word + rhof scaling of the per-solid sums (solidcloud.cpp:424-425)
+__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status, double *ft, const double *scal) {
     unsigned long long c0 = 0, c1 = 0, c2 = 0;
     int nf = 0;
+    const double rhof = __ldg(scal + 1);
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_solids; s += gridDim.x * blockDim.x) {
         c0 += pair_counts[3 * s];
         c1 += pair_counts[3 * s + 1];
         c2 += pair_counts[3 * s + 2];
         nf += root_count[s] > 1;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ft[6 * (long long)s + k] = ft[6 * (long long)s + k] * rhof;
     }
     for (int o = 16; o > 0; o >>= 1) {
         c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -695,12 +1063,6 @@ __global__ void k_finalize(const unsigned *pair_counts, const int *root_count, i
         if (c2) atomicAdd(&status->counts[2], c2);
         if (nf) atomicAdd(&status->n_flagged, nf);
     }
-}
-
-// rhof scaling of the per-solid sums (solidcloud.cpp:424-425)
-__global__ void k_scale_ft(double *ft, int n, double rhof) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ft[i] = ft[i] * rhof;
 }
 
 // ------------------------------------------------------------------------------------------------

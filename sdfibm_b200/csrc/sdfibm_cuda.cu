@@ -16,6 +16,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -67,6 +68,7 @@ struct DevSolid {
     double omega[3];
     double axis[3]; // world direction of the body z axis
     double r_out, r_in;
+    float pos32[3]; // centre relative to the mesh origin (keys of the connectivity certificate)
     int shape;
     int kind;
     int axis_is_z; // body z axis coincides with world z (2-D cases)
@@ -81,8 +83,7 @@ struct DevMesh {
     const double *magSf;    // |Sf| per face (same expression as Foam::mag, evaluated once at upload)
     const double2 *face_rec; // hex path: 64-byte record per face: Cf.xyz, Sf.xyz, |Sf|, pad
     const unsigned *hex_topo; // hex meshes: 3 words per cell, 4-bit cell-local vertex slot of every face vertex
-    const unsigned *nb_hint;  // per cell: for each signed axis direction (-x,+x,-y,+y,-z,+z) the position in cellCells[c] of
-                              // the best-aligned face neighbour, 3 bits each (7 = none)
+    const int *nb6;           // per cell: for each signed axis direction (-x,+x,-y,+y,-z,+z) the best-aligned face neighbour (-1 = none)
     // Cells are renumbered at upload into TILE ORDER (position i = rank of the cell in a stable sort by the key of the
     // spatial tile holding its centre; ~256 cells per tile).  Every per-cell array above/below is stored in position
     // order; orig[i] is the caller's cell label of position i (U is read and As/Fs/Ts/Ct are written through it).
@@ -166,25 +167,23 @@ __global__ void k_hex_topo(DevMesh m, unsigned *topo, int *bad) {
     topo[3 * (long long)c + 2] = w[2];
 }
 
-// direction hints for the connectivity certificate: which face neighbour lies towards -x, +x, -y, ...
-__global__ void k_nb_hint(DevMesh m, unsigned *hint) {
+// direction table for the connectivity certificate: which face neighbour lies towards -x, +x, -y, ...
+__global__ void k_nb6(DevMesh m, int *nb6) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m.n_cells) return;
     const D3 cc = ld3(m.cc, c);
     const int b = m.nb_off[c], e = m.nb_off[c + 1];
-    unsigned w = 0;
     for (int d = 0; d < 6; ++d) {
-        int best = 7;
+        int best = -1;
         double best_cos = 0.0;
-        for (int k = b; k < e && k - b < 7; ++k) {
+        for (int k = b; k < e; ++k) {
             const D3 r = ld3(m.cc, m.nb[k]) - cc;
             const double comp = (d >> 1) == 0 ? r.x : (d >> 1) == 1 ? r.y : r.z;
             const double cs = ((d & 1) ? comp : -comp) / (mag3(r) + 1e-300);
-            if (cs > best_cos) { best_cos = cs; best = k - b; }
+            if (cs > best_cos) { best_cos = cs; best = m.nb[k]; }
         }
-        w |= (unsigned)best << (3 * d);
+        nb6[6 * (long long)c + d] = best;
     }
-    hint[c] = w;
 }
 
 // rmax[0..1] = max of the (3-D, xy) radii, rmax[2..3] = min
@@ -321,6 +320,7 @@ struct PrepParams {
     BinGrid grid;
     double rad3_max, radxy_max;
     double mesh_lo[3], mesh_hi[3];
+    double origin[3];
     int *bin_count;   // [n_bins+1]
     int *global_list; // [n_solids]
     StepStatus *status;
@@ -336,6 +336,7 @@ __global__ void k_solid_prepare(PrepParams P) {
     DevSolid S;
     for (int d = 0; d < 3; ++d) { S.pos[d] = in.pos[d]; S.vel[d] = in.vel[d]; S.omega[d] = in.omega[d]; }
     for (int d = 0; d < 4; ++d) S.q[d] = in.quat[d];
+    for (int d = 0; d < 3; ++d) S.pos32[d] = (float)(in.pos[d] - P.origin[d]);
     S.shape = in.shape;
     const DevShape &sh = P.shapes[in.shape];
     S.kind = sh.kind;
@@ -395,13 +396,7 @@ __global__ void k_bin_fill(FillParams P) {
 }
 
 // ascending solid id inside every bin (and the global list): the per-cell accumulation order
-__global__ void k_bin_sort(const int *bin_off, int *bin_list, int n_bins, int bin_cap, int *global_list, StepStatus *status) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    int beg, end;
-    int *lst;
-    if (b < n_bins) { beg = bin_off[b]; end = bin_off[b + 1]; lst = bin_list; if (end > bin_cap) return; }
-    else if (b == n_bins) { beg = 0; end = status->n_global; lst = global_list; status->bin_total = bin_off[n_bins]; }
-    else return;
+__device__ __forceinline__ void bin_insertion_sort(int *lst, int beg, int end) {
     for (int i = beg + 1; i < end; ++i) {
         int v = lst[i], j = i - 1;
         while (j >= beg && lst[j] > v) { lst[j + 1] = lst[j]; --j; }
@@ -411,25 +406,30 @@ __global__ void k_bin_sort(const int *bin_off, int *bin_list, int n_bins, int bi
 
 #include "interact_kernels.cuh"
 
-// bin_list (sorted per bin) -> inline fp32 candidate records read by k_classify.  The radii carry the fp32 slack:
-// coordinates relative to the mesh origin are bounded by M = half extent + r_out + rad, so the fp32 distance is off by
-// < 1e-6 M; slack = 4e-6 M keeps the three-way test conservative (the exact fp64 predicates decide everything it does not).
-__global__ void k_bin_entries(const int *bin_off, const int *bin_list, int n_bins, int bin_cap, const DevSolid *solids, BinEntry *out,
-                              double ox, double oy, double oz, double half_ext, double rad_max) {
-    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = min(bin_off[n_bins], bin_cap);
-    if (pos >= total) return;
-    const int s = bin_list[pos];
-    const DevSolid &S = solids[s];
-    const double slack = 4e-6 * (half_ext + S.r_out + rad_max);
-    BinEntry e;
-    e.x = (float)(S.pos[0] - ox); e.y = (float)(S.pos[1] - oy); e.z = (float)(S.pos[2] - oz);
-    e.r_out = __double2float_ru(S.r_out + slack);
-    e.r_in = __double2float_rd(S.r_in - slack);
-    e.s = s;
-    e.kind = S.kind;
-    e.pad = 0;
-    out[pos] = e;
+// Thread per bin: sort the bin's solids by id, then write the inline fp32 candidate records k_classify reads.  The radii carry
+// the fp32 slack: coordinates relative to the mesh origin are bounded by M = half extent + r_out + rad, so the fp32 distance is
+// off by < 1e-6 M; slack = 4e-6 M keeps the three-way test conservative (the exact fp64 predicates decide everything it does not).
+__global__ void k_bin_sort_entries(const int *bin_off, int *bin_list, int n_bins, int bin_cap, int *global_list, StepStatus *status,
+                                   const DevSolid *solids, BinEntry *out, double ox, double oy, double oz, double half_ext, double rad_max) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == n_bins) { bin_insertion_sort(global_list, 0, status->n_global); status->bin_total = bin_off[n_bins]; return; }
+    if (b > n_bins) return;
+    const int beg = bin_off[b], end = bin_off[b + 1];
+    if (end > bin_cap) return;
+    bin_insertion_sort(bin_list, beg, end);
+    for (int pos = beg; pos < end; ++pos) {
+        const int s = bin_list[pos];
+        const DevSolid &S = solids[s];
+        const double slack = 4e-6 * (half_ext + S.r_out + rad_max);
+        BinEntry e;
+        e.x = (float)(S.pos[0] - ox); e.y = (float)(S.pos[1] - oy); e.z = (float)(S.pos[2] - oz);
+        e.r_out = __double2float_ru(S.r_out + slack);
+        e.r_in = __double2float_rd(S.r_in - slack);
+        e.s = s;
+        e.kind = S.kind;
+        e.pad = 0;
+        out[pos] = e;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,7 +571,8 @@ struct sdfibm_context {
     DevBuf<float2> cell_rad;
     DevBuf<double> magSf;
     DevBuf<double2> face_rec;
-    DevBuf<unsigned> hex_topo, nb_hint, tile_key;
+    DevBuf<unsigned> hex_topo, tile_key;
+    DevBuf<int> nb6;
     DevBuf<int> orig, inv;      // tile-order renumbering: position -> caller's label and back
     DevBuf<double> cc_orig;     // cell centres in the caller's order (fixInternal)
     DevBuf<float4> cc32;
@@ -585,14 +586,18 @@ struct sdfibm_context {
     // per step
     DevBuf<sdfibm_solid_t> solids_in;
     DevBuf<DevSolid> solids;
-    DevBuf<int> bin_count, bin_off, bin_cursor, bin_list, global_list, root_count, slots;
+    DevBuf<int> bin_off, bin_list, global_list, slots;
+    DevBuf<unsigned char> zero_block;   // [StepStatus | root_count | pair_counts | bin_count | bin_cursor]: zeroed by one memset per step
+    StepStatus *status = nullptr;       // the pointers below live in zero_block
+    int *root_count = nullptr, *bin_count = nullptr, *bin_cursor = nullptr;
+    unsigned *pair_counts = nullptr;
+    DevBuf<double> scal;                // {1/dt, rhof} of the step
+    double *h_scal = nullptr;           // pinned
     DevBuf<BinEntry> bin_entries;
     DevBuf<double2> heavy_res;
     DevBuf<unsigned char> n_item;
     DevBuf<int2> heavy;
-    DevBuf<unsigned> pair_counts;
     DevBuf<double> ft_internal;
-    DevBuf<StepStatus> status;
     DevBuf<unsigned char> scan_tmp;
     StepStatus *h_status = nullptr; // pinned
     sdfibm_solid_t *h_solids = nullptr; // pinned staging
@@ -616,9 +621,18 @@ struct sdfibm_context {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[N_CHUNK] = {}, ev_fin[N_CHUNK] = {};
     struct { bool active = false, stale = false; double *As = nullptr, *Fs = nullptr, *Ts = nullptr, *Ct = nullptr; const double *U = nullptr; } pipe;
+    double t_host_us[4] = {0, 0, 0, 0}; // host wall time of the last interact: solid staging, enqueue / graph launch, wait for the GPU, whole call
     double t_ms[6] = {0, 0, 0, 0, 0, 0}; // binning, k_classify, k_heavy, k_accumulate, connectivity+finalise, whole pipeline
     int n_sm = 148;
-    int64_t launches = 0;
+    int heavy_mode = 0;   // 0: warp-cooperative k_heavy_hex with pooled faces, 3: without pooling, 1/2: CTA-cooperative k_heavy_dedupe (B = 128 / 256)
+    int64_t launches = 0, graph_launches = 0;
+    // the device-resident entry replays one captured graph per step while its arguments stay the same
+    typedef uint64_t GraphKey[20];
+    GraphKey graph_key = {0};
+    cudaGraphExec_t graph_exec = nullptr;
+    bool use_graph = true;
+    int final_minb = 4;
+    int n_global_hint = 0;   // host-side: some solid may be on the global list (selects the k_classify variant)
     int64_t flagged_last = 0;
 };
 
@@ -683,7 +697,10 @@ int sdfibm_create(int device, sdfibm_context **out) {
     ctx->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(StepStatus)));
-    CUDA_TRY(ctx->status.ensure(1));
+    CUDA_TRY(cudaMallocHost(&ctx->h_scal, 2 * sizeof(double)));
+    CUDA_TRY(ctx->scal.ensure(2));
+    if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
+    if (const char *e = getenv("SDFIBM_FINAL_MINB")) ctx->final_minb = atoi(e);
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -692,6 +709,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fin[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device));
+    if (const char *e = getenv("SDFIBM_HEAVY")) ctx->heavy_mode = atoi(e);
     *out = ctx;
     return SDFIBM_OK;
 }
@@ -704,11 +722,12 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
-    ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb_hint.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
-    ctx->bin_count.release(); ctx->bin_off.release(); ctx->bin_cursor.release(); ctx->bin_list.release();
-    ctx->global_list.release(); ctx->root_count.release(); ctx->slots.release(); ctx->pair_counts.release();
+    ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release();
+    ctx->global_list.release(); ctx->slots.release();
     ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
-    ctx->ft_internal.release(); ctx->status.release(); ctx->scan_tmp.release();
+    ctx->ft_internal.release(); ctx->scan_tmp.release();
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release(); ctx->sU.release(); ctx->sOut.release(); ctx->sFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
@@ -717,9 +736,20 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->h_solids) cudaFreeHost(ctx->h_solids);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return SDFIBM_OK;
+}
+
+int sdfibm_alloc_pinned(size_t bytes, void **out) {
+    if (!out) return fail(SDFIBM_ERR_ARG, "sdfibm_alloc_pinned: null out");
+    CUDA_TRY(cudaMallocHost(out, std::max<size_t>(bytes, 1)));
+    return SDFIBM_OK;
+}
+int sdfibm_free_pinned(void *p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
     return SDFIBM_OK;
 }
 
@@ -901,9 +931,9 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         d.hex_topo = ctx->hex_topo.p;
         k_hex_topo<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->hex_topo.p, bad.p);
     }
-    CUDA_TRY(ctx->nb_hint.ensure(nC));
-    d.nb_hint = ctx->nb_hint.p;
-    k_nb_hint<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->nb_hint.p);
+    CUDA_TRY(ctx->nb6.ensure(6 * nC));
+    d.nb6 = ctx->nb6.p;
+    k_nb6<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->nb6.p);
     k_cc32<<<grid_for(nC, 256), 256, 0, st>>>(ctx->cc.p, ctx->cell_rad.p, (int)nC, d.origin[0], d.origin[1], d.origin[2], ctx->cc32.p);
     CUDA_TRY(cudaGetLastError());
     int h_bad = 0;
@@ -952,11 +982,25 @@ static int stage_solids(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
         ctx->h_solids_cap = n;
     }
     const int ns = (int)ctx->h_shapes.size();
-    for (int i = 0; i < n; ++i)
+    // may any solid be tested by every cell (plane, or a 2-D shape whose axis is not exactly world z)?  A superset of the device's
+    // decision in k_solid_prepare: it only selects the k_classify variant that merges the global list.
+    int hint = 0;
+    for (int i = 0; i < n; ++i) {
         if (solids[i].shape < 0 || solids[i].shape >= ns) return fail(SDFIBM_ERR_ARG, "solid refers to an unknown shape index");
-    memcpy(ctx->h_solids, solids, sizeof(sdfibm_solid_t) * (size_t)n);
+        const int kind = ctx->h_shapes[solids[i].shape].kind;
+        hint |= (kind == KIND_PLANE) || (kind == KIND_2D && (solids[i].quat[1] != 0.0 || solids[i].quat[2] != 0.0));
+    }
+    ctx->n_global_hint = hint;
     CUDA_TRY(ctx->solids_in.ensure(n));
-    CUDA_TRY(cudaMemcpyAsync(ctx->solids_in.p, ctx->h_solids, sizeof(sdfibm_solid_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    // page-locked caller memory (sdfibm_alloc_pinned, cudaHostRegister, ...) is copied from directly; anything else is staged
+    const void *src = solids;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, solids) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        memcpy(ctx->h_solids, solids, sizeof(sdfibm_solid_t) * (size_t)n);
+        src = ctx->h_solids;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->solids_in.p, src, sizeof(sdfibm_solid_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     return SDFIBM_OK;
 }
 
@@ -982,10 +1026,14 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     if (ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
     if (n_solids > (1 << 28) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
     int rc = SDFIBM_OK;
+    const auto h0 = std::chrono::steady_clock::now();
     if (!ctx->pipe.active) rc = stage_solids(ctx, solids, n_solids);   // the host-buffer entry stages them ahead of its U copies
     if (rc) return rc;
+    const auto h1 = std::chrono::steady_clock::now();
+    ctx->t_host_us[0] = std::chrono::duration<double, std::micro>(h1 - h0).count();
     ctx->launches = 0;
     rc = run_pipeline(ctx, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT, false);
+    ctx->t_host_us[3] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
     if (rc) return rc;
     ctx->flagged_last = ctx->last.n_flagged;
     ctx->last_used_replay = false;
@@ -1003,7 +1051,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         CUDA_TRY(ctx->changed.ensure(1));
         ReplayParams R;
         R.m = ctx->dm; R.solids = ctx->solids.p; R.n_item = ctx->n_item.p; R.slots = ctx->slots.p; R.K = ctx->K;
-        R.root_count = ctx->root_count.p; R.labels = ctx->labels.p; R.changed = ctx->changed.p;
+        R.root_count = ctx->root_count; R.labels = ctx->labels.p; R.changed = ctx->changed.p;
         R.seed_key = ctx->seed_key.p; R.seed_cell = ctx->seed_cell.p; R.min_label = ctx->min_label.p;
         R.chosen = ctx->chosen.p; R.excluded = ctx->excluded.p; R.inv = ctx->inv.p; R.grid = ctx->grid; R.bin_off = ctx->bin_off.p;
         R.bin_list = ctx->bin_list.p; R.global_list = ctx->global_list.p; R.n_global = ctx->last.n_global;
@@ -1038,143 +1086,219 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     return SDFIBM_OK;
 }
 
+static void launch_final(sdfibm_context *ctx, const InteractParams &I, int grid, cudaStream_t st) {
+    if (ctx->final_minb == 4) k_final<4><<<grid, 256, 0, st>>>(I);
+    else if (ctx->final_minb == 6) k_final<6><<<grid, 256, 0, st>>>(I);
+    else k_final<5><<<grid, 256, 0, st>>>(I);
+}
+
+// Everything one pass of the pipeline enqueues on the context stream (directly, or once into a CUDA graph that later steps
+// re-launch: ~20 dependent launches / memsets become one submission, which matters because every step starts on an idle GPU).
+static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, double *dAs, double *dFs, double *dTs, double *dCt,
+                            double *dFT, bool replay, bool chunked, bool capturing) {
+    cudaStream_t st = ctx->stream;
+    const int nC = ctx->dm.n_cells;
+    const BinGrid &g = ctx->grid;
+    auto rec = [&](cudaEvent_t e) { return capturing ? cudaEventRecordWithFlags(e, st, cudaEventRecordExternal) : cudaEventRecord(e, st); };
+    CUDA_TRY(rec(ctx->ev[0]));
+    CUDA_TRY(cudaMemcpyAsync(ctx->scal.p, ctx->h_scal, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(dFT, 0, sizeof(double) * 6 * n_solids, st));
+    if (!replay) {
+        // status word, root / pair counters, bin counters and cursors live in one block: one memset
+        CUDA_TRY(cudaMemsetAsync(ctx->zero_block.p, 0, ctx->zero_block.n, st));
+        PrepParams P;
+        P.solids = ctx->solids_in.p; P.shapes = ctx->shapes.p; P.n_solids = n_solids; P.n_shapes = (int)ctx->h_shapes.size();
+        P.out = ctx->solids.p; P.grid = g; P.rad3_max = ctx->rad3_max; P.radxy_max = ctx->radxy_max;
+        for (int d = 0; d < 3; ++d) { P.mesh_lo[d] = ctx->bmin[d]; P.mesh_hi[d] = ctx->bmax[d]; P.origin[d] = ctx->dm.origin[d]; }
+        P.bin_count = ctx->bin_count; P.global_list = ctx->global_list.p; P.status = ctx->status;
+        k_solid_prepare<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(P);
+        size_t tmp_bytes = ctx->scan_tmp.n;
+        cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, ctx->bin_count, ctx->bin_off.p, g.n_bins + 1, st);
+        FillParams F;
+        F.solids = ctx->solids.p; F.n_solids = n_solids; F.grid = g; F.rad3_max = ctx->rad3_max; F.radxy_max = ctx->radxy_max;
+        for (int d = 0; d < 3; ++d) { F.mesh_lo[d] = ctx->bmin[d]; F.mesh_hi[d] = ctx->bmax[d]; }
+        F.bin_off = ctx->bin_off.p; F.bin_cursor = ctx->bin_cursor; F.bin_list = ctx->bin_list.p;
+        F.bin_cap = (int)std::min<size_t>(ctx->bin_list.n, 0x7fffffff); F.status = ctx->status;
+        k_bin_fill<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(F);
+        k_bin_sort_entries<<<grid_for((long long)g.n_bins + 1, 128), 128, 0, st>>>(
+            ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap, ctx->global_list.p, ctx->status, ctx->solids.p, ctx->bin_entries.p,
+            ctx->dm.origin[0], ctx->dm.origin[1], ctx->dm.origin[2], ctx->half_ext, (double)std::max(ctx->rad3_max, ctx->radxy_max));
+        ctx->launches += 4;
+    } else {
+        // keep the binning of the first pass; restore the counters the status word carries
+        CUDA_TRY(cudaMemsetAsync(ctx->root_count, 0, sizeof(int) * n_solids, st));
+        CUDA_TRY(cudaMemsetAsync(ctx->pair_counts, 0, sizeof(unsigned) * 3 * n_solids, st));
+        StepStatus keep{};
+        keep.n_global = ctx->last.n_global;
+        keep.bin_total = ctx->last.bin_total;
+        CUDA_TRY(cudaMemcpyAsync(ctx->status, &keep, sizeof(StepStatus), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    InteractParams I;
+    I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.n_solids = n_solids; I.grid = g;
+    I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.bin_entries = ctx->bin_entries.p; I.global_list = ctx->global_list.p; I.U = dU;
+    I.scal = ctx->scal.p; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
+    I.pair_counts = ctx->pair_counts; I.slots = ctx->slots.p; I.K = ctx->K;
+    I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_res = ctx->heavy_res.p;
+    I.heavy_count = &ctx->status->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
+    I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status;
+    CUDA_TRY(rec(ctx->ev[1]));
+    if (ctx->n_global_hint) k_classify<256, 4, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
+    else k_classify<256, 6, false><<<grid_for(nC, 256), 256, 0, st>>>(I);
+    CUDA_TRY(rec(ctx->ev[2]));
+    if (ctx->dm.is_hex && ctx->heavy_mode == 1) {
+        constexpr int HB = 128, HC = 5;
+        const size_t smem = sizeof(HeavyDedupeSmem<HB>);
+        k_heavy_dedupe<HB, HC><<<ctx->n_sm * HC, HB, smem, st>>>(I);
+    } else if (ctx->dm.is_hex && ctx->heavy_mode == 2) {
+        constexpr int HB = 256, HC = 2;
+        const size_t smem = sizeof(HeavyDedupeSmem<HB>);
+        k_heavy_dedupe<HB, HC><<<ctx->n_sm * HC, HB, smem, st>>>(I);
+    } else if (ctx->dm.is_hex && ctx->heavy_mode == 3) k_heavy_hex<HEAVY_CTAS_PER_SM, false, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+    else if (ctx->dm.is_hex && ctx->heavy_mode == 4) k_heavy_hex<HEAVY_CTAS_PER_SM, true, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+    else if (ctx->dm.is_hex && ctx->heavy_mode == 5) k_heavy_hex<6, false, false><<<ctx->n_sm * 6, TPB, 0, st>>>(I);
+    else if (ctx->dm.is_hex && ctx->heavy_mode == 6) k_heavy_hex<6, true, false><<<ctx->n_sm * 6, TPB, 0, st>>>(I);
+    else if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM, false, true><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+    else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+    CUDA_TRY(rec(ctx->ev[3]));
+    if (chunked) {
+        // chunked: k_final of chunk i waits for its slice of U and releases its slice of the fields to the copy-out stream.
+        // The copy engines are FIFO across streams, so the U chunks are enqueued only now — after every small upload /
+        // memset the preceding kernels depend on — and still start at t ~ 0 because enqueueing is asynchronous.
+        for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
+            const size_t c0 = (size_t)nC * i / sdfibm_context::N_CHUNK, c1 = (size_t)nC * (i + 1) / sdfibm_context::N_CHUNK;
+            if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(dU) + 3 * c0, ctx->pipe.U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
+            CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
+        }
+        // Position chunk i touches the caller's cells [chunk_cmin[i], chunk_cmax[i]] (tile order follows the mesh in slabs, so
+        // for block-structured numberings chunk i == cell range i): it waits for the U range holding its largest label, and
+        // cell range j leaves once the last position chunk that intersects it is done.
+        const int NCH = sdfibm_context::N_CHUNK;
+        auto range_of = [&](int c) { int j = (int)(((long long)c * NCH) / nC); while ((long long)nC * j / NCH > c) --j; while ((long long)nC * (j + 1) / NCH <= c) ++j; return j; };
+        int i_last[sdfibm_context::N_CHUNK];
+        for (int j = 0; j < NCH; ++j) i_last[j] = -1;
+        for (int i = 0; i < NCH; ++i) {
+            if (ctx->chunk_cmax[i] < 0) continue;
+            for (int j = range_of(ctx->chunk_cmin[i]); j <= range_of(ctx->chunk_cmax[i]); ++j) i_last[j] = i;
+        }
+        int last_pos_chunk = 0;
+        for (int i = 0; i < NCH; ++i) if (ctx->chunk_cmax[i] >= 0) last_pos_chunk = i;
+        for (int i = 0; i < NCH; ++i) {
+            const long long p0 = (long long)nC * i / NCH, p1 = (long long)nC * (i + 1) / NCH;
+            if (p1 > p0) {
+                I.c_begin = (int)p0; I.c_end = (int)p1;
+                CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
+                launch_final(ctx, I, grid_for(p1 - p0, 256), st);
+            }
+            CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
+            for (int j = 0; j < NCH; ++j) {
+                if (!(i_last[j] == i || (i_last[j] < 0 && i == last_pos_chunk))) continue;
+                const size_t c0 = (size_t)nC * j / NCH, c1 = (size_t)nC * (j + 1) / NCH;
+                if (c1 <= c0) continue;
+                const size_t n = c1 - c0;
+                CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.As + c0, dAs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Fs + 3 * c0, dFs + 3 * c0, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ts + c0, dTs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+                CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ct + c0, dCt + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+        }
+        ctx->launches += sdfibm_context::N_CHUNK - 1;
+    } else {
+        I.c_begin = 0; I.c_end = nC;
+        launch_final(ctx, I, grid_for(nC, 256), st);
+    }
+    CUDA_TRY(rec(ctx->ev[4]));
+    ctx->launches += 3;
+    if (!replay) {
+        ConnParams C;
+        C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count;
+        k_connectivity<<<grid_for(nC, 256), 256, 0, st>>>(C);
+        ++ctx->launches;
+    }
+    k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts, ctx->root_count, n_solids, ctx->status, dFT, ctx->scal.p);
+    ++ctx->launches;
+    CUDA_TRY(rec(ctx->ev[5]));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
+    return SDFIBM_OK;
+}
+
+static void drop_graph(sdfibm_context *ctx) {
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr;
+}
+
 static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, double dt, double rhof, double *dAs,
                         double *dFs, double *dTs, double *dCt, double *dFT, bool replay) {
     cudaStream_t st = ctx->stream;
-    const int nC = ctx->dm.n_cells;
+    const BinGrid &g = ctx->grid;   // the static tile grid
     if (!replay) {
-        const BinGrid &g = ctx->grid;   // the static tile grid
         CUDA_TRY(ctx->solids.ensure(n_solids));
-        CUDA_TRY(ctx->bin_count.ensure((size_t)g.n_bins + 1));
         CUDA_TRY(ctx->bin_off.ensure((size_t)g.n_bins + 1));
-        CUDA_TRY(ctx->bin_cursor.ensure((size_t)g.n_bins));
         CUDA_TRY(ctx->global_list.ensure(n_solids));
-        CUDA_TRY(ctx->root_count.ensure(n_solids));
-        CUDA_TRY(ctx->pair_counts.ensure(3 * (size_t)n_solids));
         if (ctx->bin_list.n == 0) CUDA_TRY(ctx->bin_list.ensure(std::max<size_t>(1 << 20, 128 * (size_t)n_solids)));
+        // one zero-initialised block: [StepStatus | root_count n | pair_counts 3n | bin_count n_bins+1 | bin_cursor n_bins]
+        const size_t o_root = (sizeof(StepStatus) + 15) & ~size_t(15);
+        const size_t o_pair = o_root + ((sizeof(int) * (size_t)n_solids + 15) & ~size_t(15));
+        const size_t o_cnt = o_pair + ((sizeof(unsigned) * 3 * (size_t)n_solids + 15) & ~size_t(15));
+        const size_t o_cur = o_cnt + ((sizeof(int) * ((size_t)g.n_bins + 1) + 15) & ~size_t(15));
+        const size_t total = o_cur + sizeof(int) * (size_t)g.n_bins;
+        if (ctx->zero_block.n != total) { ctx->zero_block.release(); CUDA_TRY(ctx->zero_block.ensure(total)); }
+        unsigned char *zb = ctx->zero_block.p;
+        ctx->status = reinterpret_cast<StepStatus *>(zb);
+        ctx->root_count = reinterpret_cast<int *>(zb + o_root);
+        ctx->pair_counts = reinterpret_cast<unsigned *>(zb + o_pair);
+        ctx->bin_count = reinterpret_cast<int *>(zb + o_cnt);
+        ctx->bin_cursor = reinterpret_cast<int *>(zb + o_cur);
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->bin_count, ctx->bin_off.p, g.n_bins + 1, st);
+        CUDA_TRY(ctx->scan_tmp.ensure(tmp_bytes));
     }
+    ctx->h_scal[0] = 1.0 / dt;
+    ctx->h_scal[1] = rhof;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const BinGrid &g = ctx->grid;
-        CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
-        CUDA_TRY(cudaMemsetAsync(ctx->status.p, 0, sizeof(StepStatus), st));
-        CUDA_TRY(cudaMemsetAsync(ctx->root_count.p, 0, sizeof(int) * n_solids, st));
-        CUDA_TRY(cudaMemsetAsync(ctx->pair_counts.p, 0, sizeof(unsigned) * 3 * n_solids, st));
-        CUDA_TRY(cudaMemsetAsync(dFT, 0, sizeof(double) * 6 * n_solids, st));
-        if (!replay) {
-            CUDA_TRY(cudaMemsetAsync(ctx->bin_count.p, 0, sizeof(int) * ((size_t)g.n_bins + 1), st));
-            CUDA_TRY(cudaMemsetAsync(ctx->bin_cursor.p, 0, sizeof(int) * (size_t)g.n_bins, st));
-            PrepParams P;
-            P.solids = ctx->solids_in.p; P.shapes = ctx->shapes.p; P.n_solids = n_solids; P.n_shapes = (int)ctx->h_shapes.size();
-            P.out = ctx->solids.p; P.grid = g; P.rad3_max = ctx->rad3_max; P.radxy_max = ctx->radxy_max;
-            for (int d = 0; d < 3; ++d) { P.mesh_lo[d] = ctx->bmin[d]; P.mesh_hi[d] = ctx->bmax[d]; }
-            P.bin_count = ctx->bin_count.p; P.global_list = ctx->global_list.p; P.status = ctx->status.p;
-            k_solid_prepare<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(P);
-            size_t tmp_bytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->bin_count.p, ctx->bin_off.p, g.n_bins + 1, st);
-            CUDA_TRY(ctx->scan_tmp.ensure(tmp_bytes));
-            cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, ctx->bin_count.p, ctx->bin_off.p, g.n_bins + 1, st);
-            FillParams F;
-            F.solids = ctx->solids.p; F.n_solids = n_solids; F.grid = g; F.rad3_max = ctx->rad3_max; F.radxy_max = ctx->radxy_max;
-            for (int d = 0; d < 3; ++d) { F.mesh_lo[d] = ctx->bmin[d]; F.mesh_hi[d] = ctx->bmax[d]; }
-            F.bin_off = ctx->bin_off.p; F.bin_cursor = ctx->bin_cursor.p; F.bin_list = ctx->bin_list.p;
-            F.bin_cap = (int)std::min<size_t>(ctx->bin_list.n, 0x7fffffff); F.status = ctx->status.p;
-            k_bin_fill<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(F);
-            k_bin_sort<<<grid_for((long long)g.n_bins + 1, 128), 128, 0, st>>>(ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap,
-                                                                              ctx->global_list.p, ctx->status.p);
-            CUDA_TRY(ctx->bin_entries.ensure(ctx->bin_list.n));
-            k_bin_entries<<<grid_for((long long)F.bin_cap, 256), 256, 0, st>>>(ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap,
-                                                                            ctx->solids.p, ctx->bin_entries.p, ctx->dm.origin[0], ctx->dm.origin[1],
-                                                                            ctx->dm.origin[2], ctx->half_ext, (double)std::max(ctx->rad3_max, ctx->radxy_max));
-            ctx->launches += 5;
+        if (!replay) CUDA_TRY(ctx->bin_entries.ensure(ctx->bin_list.n));
+        const bool chunked = ctx->pipe.active && !replay && attempt == 0;
+        if (ctx->pipe.active && !chunked) {   // a retry / replay pass rewrites the fields: copy them out again at the end
+            ctx->pipe.stale = true;
+            CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
+            CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
+        }
+        const bool use_graph = ctx->use_graph && !replay && !ctx->pipe.active;
+        const auto q0 = std::chrono::steady_clock::now();
+        if (use_graph) {
+            const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
+                                      (uint64_t)ctx->solids_in.p, (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
+                                      (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
+                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)ctx->heavy_mode,
+                                      (uint64_t)ctx->n_global_hint};
+            if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
+                drop_graph(ctx);
+                cudaGraph_t graph = nullptr;
+                CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int64_t keep_launches = ctx->launches;
+                const int rc = enqueue_pipeline(ctx, n_solids, dU, dAs, dFs, dTs, dCt, dFT, false, false, true);
+                ctx->graph_launches = ctx->launches - keep_launches;
+                ctx->launches = keep_launches;
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (e != cudaSuccess) return fail(SDFIBM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+                const cudaError_t e2 = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e2 != cudaSuccess) { ctx->graph_exec = nullptr; return fail(SDFIBM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2)); }
+                memcpy(ctx->graph_key, key, sizeof(key));
+            }
+            CUDA_TRY(cudaGraphLaunch(ctx->graph_exec, st));
+            ctx->launches += ctx->graph_launches;
         } else {
-            // keep the binning of the first pass; restore the counters the status word carries
-            StepStatus keep{};
-            keep.n_global = ctx->last.n_global;
-            keep.bin_total = ctx->last.bin_total;
-            CUDA_TRY(cudaMemcpyAsync(ctx->status.p, &keep, sizeof(StepStatus), cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            const int rc = enqueue_pipeline(ctx, n_solids, dU, dAs, dFs, dTs, dCt, dFT, replay, chunked, false);
+            if (rc) return rc;
         }
-        InteractParams I;
-        I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.n_solids = n_solids; I.grid = g;
-        I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.bin_entries = ctx->bin_entries.p; I.global_list = ctx->global_list.p; I.U = dU;
-        I.dtINV = 1.0 / dt; I.rhof = rhof; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
-        I.pair_counts = ctx->pair_counts.p; I.slots = ctx->slots.p; I.K = ctx->K;
-        I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_res = ctx->heavy_res.p;
-        I.heavy_count = &ctx->status.p->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
-        I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status.p;
-        CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        k_classify<256, 4><<<grid_for(nC, 256), 256, 0, st>>>(I);
-        CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-        if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-        else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-        CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
-        if (ctx->pipe.active && !replay && attempt == 0) {
-            // chunked: k_final of chunk i waits for its slice of U and releases its slice of the fields to the copy-out stream.
-            // The copy engines are FIFO across streams, so the U chunks are enqueued only now — after every small upload /
-            // memset the preceding kernels depend on — and still start at t ~ 0 because enqueueing is asynchronous.
-            for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
-                const size_t c0 = (size_t)nC * i / sdfibm_context::N_CHUNK, c1 = (size_t)nC * (i + 1) / sdfibm_context::N_CHUNK;
-                if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(dU) + 3 * c0, ctx->pipe.U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
-                CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
-            }
-            // Position chunk i touches the caller's cells [chunk_cmin[i], chunk_cmax[i]] (tile order follows the mesh in slabs, so
-            // for block-structured numberings chunk i == cell range i): it waits for the U range holding its largest label, and
-            // cell range j leaves once the last position chunk that intersects it is done.
-            const int NCH = sdfibm_context::N_CHUNK;
-            auto range_of = [&](int c) { int j = (int)(((long long)c * NCH) / nC); while ((long long)nC * j / NCH > c) --j; while ((long long)nC * (j + 1) / NCH <= c) ++j; return j; };
-            int i_last[sdfibm_context::N_CHUNK];
-            for (int j = 0; j < NCH; ++j) i_last[j] = -1;
-            for (int i = 0; i < NCH; ++i) {
-                if (ctx->chunk_cmax[i] < 0) continue;
-                for (int j = range_of(ctx->chunk_cmin[i]); j <= range_of(ctx->chunk_cmax[i]); ++j) i_last[j] = i;
-            }
-            int last_pos_chunk = 0;
-            for (int i = 0; i < NCH; ++i) if (ctx->chunk_cmax[i] >= 0) last_pos_chunk = i;
-            for (int i = 0; i < NCH; ++i) {
-                const long long p0 = (long long)nC * i / NCH, p1 = (long long)nC * (i + 1) / NCH;
-                if (p1 > p0) {
-                    I.c_begin = (int)p0; I.c_end = (int)p1;
-                    CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
-                    k_final<4><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
-                }
-                CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
-                for (int j = 0; j < NCH; ++j) {
-                    if (!(i_last[j] == i || (i_last[j] < 0 && i == last_pos_chunk))) continue;
-                    const size_t c0 = (size_t)nC * j / NCH, c1 = (size_t)nC * (j + 1) / NCH;
-                    if (c1 <= c0) continue;
-                    const size_t n = c1 - c0;
-                    CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
-                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.As + c0, dAs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
-                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Fs + 3 * c0, dFs + 3 * c0, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->s_out));
-                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ts + c0, dTs + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
-                    CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ct + c0, dCt + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
-                }
-            }
-            ctx->launches += sdfibm_context::N_CHUNK - 1;
-        } else {
-            if (ctx->pipe.active) {   // a retry / replay pass rewrites the fields: copy them out again at the end
-                ctx->pipe.stale = true;
-                CUDA_TRY(cudaStreamSynchronize(ctx->s_in));
-                CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
-            }
-            I.c_begin = 0; I.c_end = nC;
-            k_final<4><<<grid_for(nC, 256), 256, 0, st>>>(I);
-        }
-        CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
-        ctx->launches += 3;
-        if (!replay) {
-            ConnParams C;
-            C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count.p;
-            k_connectivity<<<grid_for(nC, 256), 256, 0, st>>>(C);
-            ++ctx->launches;
-        }
-        k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts.p, ctx->root_count.p, n_solids, ctx->status.p);
-        k_scale_ft<<<grid_for(6LL * n_solids, 256), 256, 0, st>>>(dFT, 6 * n_solids, rhof);
-        ctx->launches += 2;
-        CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status.p, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
+        const auto w0 = std::chrono::steady_clock::now();
         CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->t_host_us[2] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+        ctx->t_host_us[1] = std::chrono::duration<double, std::micro>(w0 - q0).count();
         {
             const double add = replay ? 1.0 : 0.0; // a replay pass adds to the first pass of the same call
             for (int k = 0; k < 5; ++k) {
@@ -1193,7 +1317,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         if (ctx->last.heavy_total > (unsigned long long)ctx->heavy.n && attempt == 0) {
             const size_t cap = (size_t)(ctx->last.heavy_total + ctx->last.heavy_total / 4 + 1024);
             CUDA_TRY(ctx->heavy.ensure(cap));
-                CUDA_TRY(ctx->heavy_res.ensure(cap));
+            CUDA_TRY(ctx->heavy_res.ensure(cap));
             continue;
         }
         if (ctx->last.bin_overflow && !replay && attempt == 0) {
@@ -1370,6 +1494,12 @@ int sdfibm_last_timings(sdfibm_context *ctx, double ms[6]) {
     return SDFIBM_OK;
 }
 
+int sdfibm_last_host_timings(sdfibm_context *ctx, double us[4]) {
+    if (!ctx || !us) return fail(SDFIBM_ERR_ARG, "null argument");
+    for (int k = 0; k < 4; ++k) us[k] = ctx->t_host_us[k];
+    return SDFIBM_OK;
+}
+
 int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells, int64_t capacity) {
     if (!ctx || !offsets) return fail(SDFIBM_ERR_ARG, "null argument");
     if (!ctx->last_Ct) return fail(SDFIBM_ERR_STATE, "no interact has run on this context");
@@ -1379,7 +1509,7 @@ int sdfibm_candidate_lists(sdfibm_context *ctx, int32_t *offsets, int32_t *cells
     const unsigned char *excl = ctx->last_used_replay ? ctx->excluded.p : nullptr;
     // per (solid,type) sizes come from the pair counters of the last pass
     std::vector<unsigned> h_cnt(3 * (size_t)nS);
-    CUDA_TRY(cudaMemcpyAsync(h_cnt.data(), ctx->pair_counts.p, sizeof(unsigned) * 3 * nS, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_cnt.data(), ctx->pair_counts, sizeof(unsigned) * 3 * nS, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     int64_t total = 0;
     offsets[0] = 0;

@@ -3,7 +3,8 @@
 import csv, subprocess, sys, io, collections
 rep = sys.argv[1]
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+kfilt = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep] + kfilt + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
@@ -24,7 +25,7 @@ for i, h in enumerate(hdr):
             continue
         if v > 3:
             print(f"  stall {h.replace('smsp__warp_issue_stalled_','').replace('_per_warp_active.pct',''):40s} {v:.1f}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + kfilt + ["--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 if len(rows) > 2:
     h = rows[0]
