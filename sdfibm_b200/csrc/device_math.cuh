@@ -40,6 +40,13 @@ __host__ __device__ __forceinline__ D3 world2local(DQ q, D3 t, D3 p) {
     return qtransform(c, p - t);
 }
 
+// With the identity quaternion (w = 1, v = 0 — every solid that has not rotated yet) the sandwich above returns p - t
+// exactly: each product with a zero component is a signed zero, and x + (+-0) == x.  Only the SIGN of an exactly-zero
+// component can differ, which no predicate, distance or volume below can observe.  Callers test the quaternion once per
+// warp and skip the 42 multiply / adds per point.
+__host__ __device__ __forceinline__ bool quat_is_identity(DQ q) { return q.w == 1.0 && q.v.x == 0.0 && q.v.y == 0.0 && q.v.z == 0.0; }
+__host__ __device__ __forceinline__ D3 world2local_sel(DQ q, D3 t, D3 p, bool identity) { return identity ? p - t : world2local(q, t, p); }
+
 // std::max / std::min semantics ((a<b)?b:a, (b<a)?b:a)
 __host__ __device__ __forceinline__ double smax(double a, double b) { return (a < b) ? b : a; }
 __host__ __device__ __forceinline__ double smin(double a, double b) { return (b < a) ? b : a; }

@@ -342,11 +342,12 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
     int nv = __ldg(m.cp_off + c + 1) - pb;
     if (nv > MAX_CELL_VERTS) { nv = MAX_CELL_VERTS; P.status->bad_cell = 1; }
     int n_in = 0;
+    const bool ident = quat_is_identity(q);
     for (int k = 0; k < nv; ++k) {
         vid[k] = __ldg(m.cp + pb + k);
         pts[k] = ld3(m.points, vid[k]);
         double ph;
-        n_in += shape_eval<true>(sh.s, world2local(q, t, pts[k]), ph) ? 1 : 0;
+        n_in += shape_eval<true>(sh.s, world2local_sel(q, t, pts[k], ident), ph) ? 1 : 0;
         phi[k] = ph;
     }
     type_out = 0;
@@ -354,7 +355,7 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
     if (n_in == 0) return;
     if (n_in == nv) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
     double dummy;
-    type_out = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+    type_out = shape_eval<false>(sh.s, world2local_sel(q, t, ld3(m.cc, c), ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
     vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
 }
 
@@ -371,11 +372,11 @@ struct HeavySmem {
     unsigned char in[8 * TPB];
 };
 
-__device__ __forceinline__ void eval_vertex_to_smem(HeavySmem &sm, const DevMesh &m, const DevShape &sh, DQ q, D3 t, int v,
+__device__ __forceinline__ void eval_vertex_to_smem(HeavySmem &sm, const DevMesh &m, const DevShape &sh, DQ q, D3 t, bool ident, int v,
                                                     int slot_a, int col_a, bool dup, int slot_b, int col_b) {
     const D3 p = ld3(m.points, v);
     double ph;
-    const bool in = shape_eval<true>(sh.s, world2local(q, t, p), ph);
+    const bool in = shape_eval<true>(sh.s, world2local_sel(q, t, p, ident), ph);
     sm.px[slot_a * TPB + col_a] = p.x;
     sm.py[slot_a * TPB + col_a] = p.y;
     sm.pz[slot_a * TPB + col_a] = p.z;
@@ -391,18 +392,9 @@ __device__ __forceinline__ void eval_vertex_to_smem(HeavySmem &sm, const DevMesh
 }
 
 #define HEAVY_CTAS_PER_SM 5
-// BAL: the cut faces of the warp's 32 cells are pooled and dealt out evenly to the lanes (a lane's own cell has 0..6 cut
-// faces, so the per-lane loop leaves most lanes idle behind the slowest one); a face is still evaluated by the same
-// instruction sequence on the same inputs, so nothing changes bit-wise.
-struct HeavyTask {
-    unsigned short nib;      // cell-local slots of the face's four vertices (face order), 4 bits each
-    unsigned char lane, f;   // owner lane and face index
-};
-template <int CTAS, bool PREFETCH, bool BAL>
+template <int CTAS>
 __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     __shared__ HeavySmem sm;
-    __shared__ double s_farea[BAL ? 6 * TPB : 1];
-    __shared__ HeavyTask s_task[BAL ? 6 * TPB : 1];
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
@@ -435,16 +427,6 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
             const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
             f01 = __ldg(cf2); f23 = __ldg(cf2 + 1); f45 = __ldg(cf2 + 2);
-            if (PREFETCH) {   // face records are consumed by the volume phase, long after the vertex phase: pull them into L2 now
-                const int fid[6] = {f01.x, f01.y, f23.x, f23.y, f45.x, f45.y};
-#pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    const char *ptr = reinterpret_cast<const char *>(m.face_rec + 4 * (long long)fid[f]);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 32));
-                }
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(m.cc + 3 * (long long)c));
-            }
         }
         // does my low quad coincide with the previous lane's high quad (same solid)?
         const int ls = __shfl_up_sync(FULL, s, 1);
@@ -455,11 +437,13 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
         const unsigned startmask = __ballot_sync(FULL, valid) & ~sharedmask;
         const bool right_shares = lane < 31 && ((sharedmask >> (lane + 1)) & 1u);
         const DevShape &sh = P.shapes[shape_idx];
+        // warp-uniform: every solid of this warp's items still has the identity orientation (world2local == p - t)
+        const bool ident = __all_sync(FULL, !valid || quat_is_identity(q));
         // rounds 0..3: my own high quad (also the next lane's low quad when it shares)
         if (valid) {
 #pragma unroll 2
             for (int v = 0; v < 4; ++v)
-                eval_vertex_to_smem(sm, m, sh, q, t, vid[2 * v + 1], 2 * v + 1, tid, right_shares, 2 * v, tid + 1);
+                eval_vertex_to_smem(sm, m, sh, q, t, ident, vid[2 * v + 1], 2 * v + 1, tid, right_shares, 2 * v, tid + 1);
         }
         // extra rounds: low quads of the run starts, 4 vertices each, spread over all lanes
         const int nwork = 4 * __popc(startmask);
@@ -478,121 +462,10 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
                 const DevSolid &S2 = P.solids[s_src];
                 const DQ q2 = {S2.q[0], {S2.q[1], S2.q[2], S2.q[3]}};
                 const D3 t2 = {S2.pos[0], S2.pos[1], S2.pos[2]};
-                eval_vertex_to_smem(sm, m, P.shapes[S2.shape], q2, t2, vv, kk, col, false, 0, 0);
+                eval_vertex_to_smem(sm, m, P.shapes[S2.shape], q2, t2, ident, vv, kk, col, false, 0, 0);
             }
         }
         __syncwarp();
-        if (BAL) {
-            auto PT = [&](int col, int l) { return D3{sm.px[l * TPB + col], sm.py[l * TPB + col], sm.pz[l * TPB + col]}; };
-            auto PH = [&](int col, int l) { return sm.phi[l * TPB + col]; };
-            // ---- A: cell type and the class of each face: 0 = entirely outside, 1 = entirely inside, 2 = cut ----
-            int type = 0;
-            unsigned fcls = 0;
-            int ncut = 0;
-            if (valid) {
-                int n_in = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) n_in += sm.in[j * TPB + tid];
-                if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
-                else if (n_in != 0) {
-                    type = 4;
-#pragma unroll
-                    for (int f = 0; f < 6; ++f) {
-                        const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
-                        const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
-                        const int npos = (PH(tid, nib & 0xf) > 0) + (PH(tid, (nib >> 4) & 0xf) > 0) + (PH(tid, (nib >> 8) & 0xf) > 0) + (PH(tid, (nib >> 12) & 0xf) > 0);
-                        const unsigned cls = (npos == 4) ? 0u : (npos == 0) ? 1u : 2u;
-                        fcls |= cls << (2 * f);
-                        ncut += (cls == 2u);
-                        if (cls != 0u) {   // the face record is consumed in phase D, after the pooled area math: start fetching it now
-                            const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(m.face_rec + 4 * (long long)face));
-                        }
-                    }
-                }
-            }
-            if (type == 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(m.cc + 3 * (long long)c));
-            // ---- B: pool the cut faces of the warp, face-index major: consecutive tasks belong to different cells, so the
-            //      lanes of a round read different shared-memory columns (the layout is conflict free per column) ----
-            int total = 0;
-#pragma unroll
-            for (int f = 0; f < 6; ++f) {
-                const bool cut = ((fcls >> (2 * f)) & 3u) == 2u;
-                const unsigned bal = __ballot_sync(FULL, cut);
-                if (cut) {
-                    const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
-                    HeavyTask t;
-                    t.nib = (unsigned short)((w >> (16 * (f & 1))) & 0xffffu);
-                    t.lane = (unsigned char)lane;
-                    t.f = (unsigned char)f;
-                    s_task[wbase * 6 + total + __popc(bal & ((1u << lane) - 1u))] = t;
-                }
-                total += __popc(bal);
-            }
-            (void)ncut;
-            __syncwarp();
-            // ---- C: one pooled face per lane per round: calcFaceArea (:74-96) ----
-            for (int u = lane; u < total; u += 32) {
-                const HeavyTask t = s_task[wbase * 6 + u];
-                const int col = wbase + t.lane;
-                const int l[4] = {t.nib & 0xf, (t.nib >> 4) & 0xf, (t.nib >> 8) & 0xf, (t.nib >> 12) & 0xf};
-                const double ph[4] = {PH(col, l[0]), PH(col, l[1]), PH(col, l[2]), PH(col, l[3])};
-                const D3 A = PT(col, l[0]);
-                D3 B = PT(col, l[1]);
-                double phiB = ph[1];
-                if (!(ph[0] * ph[1] <= 0)) {
-                    B = PT(col, l[2]);
-                    phiB = ph[2];
-                    if (!(ph[0] * ph[2] <= 0)) { B = PT(col, l[3]); phiB = ph[3]; }
-                }
-                const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - B);
-                double area = 0.0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
-                    const D3 O = PT(col, l[e]), A2 = PT(col, l[(e + 1) & 3]);
-                    area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
-                }
-                s_farea[t.f * TPB + col] = area;
-            }
-            __syncwarp();
-            // ---- D: combine ----
-            if (valid) {
-                double volume = 0.0;
-                if (type == 4) {
-                    double dummy;
-                    type = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
-                    D3 apex;
-                    {
-                        const D3 A = PT(tid, 0);
-                        const double phiA = PH(tid, 0);
-                        D3 B = {0.0, 0.0, 0.0};
-                        double phiB = 0.0;
-                        for (int i = 1; i < 8; ++i) {
-                            B = PT(tid, i);
-                            phiB = PH(tid, i);
-                            if (phiA * phiB <= 0) break;
-                        }
-                        apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - B);
-                        if (m.two_d) apex.z = 0.0;
-                    }
-#pragma unroll
-                    for (int f = 0; f < 6; ++f) {
-                        const unsigned cls = (fcls >> (2 * f)) & 3u;
-                        if (cls == 0u) continue;                                    // eps_f = 0: adds +0.0 (:107-108)
-                        const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
-                        const double2 *fr = m.face_rec + 4 * (long long)face;
-                        const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2), r3 = __ldg(fr + 3);
-                        const double eps_f = (cls == 1u) ? 1.0 : s_farea[f * TPB + tid] / r3.x;   // :109-116
-                        const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
-                        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
-                    }
-                }
-                P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));
-            }
-            __syncwarp();
-            continue;
-        }
         if (valid) {
             int type = 0;
             double volume = 0.0;
@@ -602,7 +475,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
             else if (n_in != 0) {
                 double dummy;
-                type = shape_eval<false>(sh.s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                type = shape_eval<false>(sh.s, world2local_sel(q, t, ld3(m.cc, c), ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
                 auto PT = [&](int l) { return D3{sm.px[l * TPB + tid], sm.py[l * TPB + tid], sm.pz[l * TPB + tid]}; };
                 auto PH = [&](int l) { return sm.phi[l * TPB + tid]; };
                 // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
@@ -659,243 +532,6 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));   // type 0: no vertex inside -> not a member
         }
         __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_heavy_dedupe: hexahedral path, CTA-cooperative.  A batch of B consecutive queue items is a spatially
-// compact patch of one or a few solids' boundary shells (the queue is filled tile by tile), so its cells share
-// most of their vertices and every cut face is shared by exactly two of its cells.  The batch is processed in
-// phases with the work re-distributed over the CTA between phases:
-//   1  every (solid, vertex) reference is inserted into a shared-memory hash set -> dense list of UNIQUE vertices
-//   2  the unique vertices are evaluated (world2local + predicate + filtered SDF), one per thread per round
-//   3  every item classifies its cell and its six faces; cut faces are inserted into the (re-used) hash set
-//   4  the unique cut faces are evaluated (calcFaceAreaFraction), one per thread per round
-//   5  every boundary item combines its faces: apex, centre test, sum of pyramid volumes
-// A vertex or face is evaluated by the SAME instruction sequence whichever cell asks for it, so sharing the result
-// is bit-identical to per-cell evaluation.  Items that do not fit the fixed-capacity lists (pathological queue
-// order) fall back to the self-contained per-item evaluation.
-// ------------------------------------------------------------------------------------------------
-#define HD_EMPTY 0xffffffffffffffffull
-#define HD_NONE 0xffffu
-#define HD_EPS0 0xfffeu    // face entirely outside: contributes +0.0 (:107-108)
-#define HD_EPS1 0xfffdu    // face entirely inside: eps_f = 1 (:109-110)
-
-template <int B>
-struct HeavyDedupeSmem {
-    static constexpr int NV = 4 * B;   // unique vertices of a batch
-    static constexpr int NF = 3 * B;   // unique cut faces of a batch
-    static constexpr int HT = 8 * B;   // hash slots: >= every insert of a phase (8 B vertex / 6 B face references)
-    unsigned long long key[HT];
-    double vx[NV], vy[NV], vz[NV], vphi[NV];
-    double feps[NF];
-    int2 ulist[NV];                    // unique vertex work list: (point label, solid)
-    int fface[NF];                     // unique face work list: face label ...
-    ushort4 fvi[NF];                   // ... and the dense indices of its four vertices, in the face's own order
-    unsigned short val[HT];
-    unsigned char vflag[NV];           // bit 0: strictly inside (isInside), bit 1: filtered phi > 0
-    int n_uv, n_uf;
-};
-
-template <int HT>
-__device__ __forceinline__ unsigned hd_hash(unsigned a, unsigned b) {
-    return ((a * 2654435761u) ^ (b * 0x9E3779B1u + 0x7F4A7C15u)) * 0x85EBCA6Bu >> 7 & (unsigned)(HT - 1);
-}
-
-// calcFaceAreaFraction of a cut quadrilateral face (geometrictools.cpp:74-116); vertices in the face's own order
-__device__ __forceinline__ double cut_face_eps(const D3 p[4], const double ph[4], double magSf) {
-    const D3 A = p[0];
-    D3 Bp = p[1];
-    double phiB = ph[1];
-    if (!(ph[0] * ph[1] <= 0)) {
-        Bp = p[2];
-        phiB = ph[2];
-        if (!(ph[0] * ph[2] <= 0)) { Bp = p[3]; phiB = ph[3]; }
-    }
-    const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - Bp);
-    double area = 0.0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
-        const D3 O = p[e], A2 = p[(e + 1) & 3];
-        area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
-    }
-    return area / magSf;
-}
-
-template <int B, int CTAS>
-__global__ void __launch_bounds__(B, CTAS) k_heavy_dedupe(InteractParams P) {
-    using SM = HeavyDedupeSmem<B>;
-    extern __shared__ __align__(16) unsigned char hd_raw[];
-    SM &sm = *reinterpret_cast<SM *>(hd_raw);
-    const DevMesh &m = P.m;
-    const int tid = threadIdx.x;
-    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
-    for (int i = tid; i < SM::HT; i += B) sm.key[i] = HD_EMPTY;
-    if (tid == 0) { sm.n_uv = 0; sm.n_uf = 0; }
-    __syncthreads();
-    for (long long k0 = (long long)blockIdx.x * B; k0 < n; k0 += (long long)gridDim.x * B) {
-        const long long k = k0 + tid;
-        const bool valid = k < n;
-        int c = 0, s = 0;
-        unsigned tw0 = 0, tw1 = 0, tw2 = 0;
-        int fid[6] = {0, 0, 0, 0, 0, 0};
-        unsigned short hv[8];
-        // ---- phase 1: unique (solid, vertex) references ----
-        if (valid) {
-            const int2 it = __ldg(P.heavy + k);
-            c = it.x;
-            s = it.y;
-            const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
-            const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
-            const int vid[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-            tw0 = __ldg(m.hex_topo + 3 * (long long)c);
-            tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1);
-            tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
-            const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
-            const int2 f01 = __ldg(cf2), f23 = __ldg(cf2 + 1), f45 = __ldg(cf2 + 2);
-            fid[0] = f01.x; fid[1] = f01.y; fid[2] = f23.x; fid[3] = f23.y; fid[4] = f45.x; fid[5] = f45.y;
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const unsigned long long key = ((unsigned long long)(unsigned)s << 32) | (unsigned)vid[v];
-                unsigned h = hd_hash<SM::HT>((unsigned)vid[v], (unsigned)s);
-                for (;;) {
-                    const unsigned long long old = atomicCAS(&sm.key[h], HD_EMPTY, key);
-                    if (old == HD_EMPTY) {
-                        const int idx = atomicAdd(&sm.n_uv, 1);
-                        if (idx < SM::NV) { sm.val[h] = (unsigned short)idx; sm.ulist[idx] = make_int2(vid[v], s); }
-                        else sm.val[h] = HD_NONE;
-                        break;
-                    }
-                    if (old == key) break;
-                    h = (h + 1) & (unsigned)(SM::HT - 1);
-                }
-                hv[v] = (unsigned short)h;
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: evaluate the unique vertices; the hash set is recycled for the faces ----
-        // dense indices of the cell's 8 vertices, 16 bits each (packed: indexed dynamically by the face topology below)
-        unsigned long long vlo = 0, vhi = 0;
-        bool slow = false;
-        if (valid) {
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const unsigned short x = sm.val[hv[v]];
-                slow = slow || (x == HD_NONE);
-                if (v < 4) vlo |= (unsigned long long)x << (16 * v);
-                else vhi |= (unsigned long long)x << (16 * (v - 4));
-            }
-        }
-        auto VI = [&](unsigned l) -> unsigned { return (unsigned)(((l & 4u) ? vhi : vlo) >> (16 * (l & 3u))) & 0xffffu; };
-        const int nuv = min(sm.n_uv, SM::NV);
-        __syncthreads();                       // every val[] of the vertex phase has been read
-        for (int i = tid; i < SM::HT; i += B) sm.key[i] = HD_EMPTY;
-        for (int u = tid; u < nuv; u += B) {
-            const int2 w = sm.ulist[u];
-            const DevSolid &S = P.solids[w.y];
-            const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-            const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-            const D3 p = ld3(m.points, w.x);
-            double ph;
-            const bool in = shape_eval<true>(P.shapes[S.shape].s, world2local(q, t, p), ph);
-            sm.vx[u] = p.x; sm.vy[u] = p.y; sm.vz[u] = p.z; sm.vphi[u] = ph;
-            sm.vflag[u] = (unsigned char)((in ? 1 : 0) | (ph > 0 ? 2 : 0));
-        }
-        __syncthreads();
-        // ---- phase 3: cell type; unique cut faces ----
-        int type = 0;
-        unsigned short fh[6] = {HD_EPS0, HD_EPS0, HD_EPS0, HD_EPS0, HD_EPS0, HD_EPS0};
-        if (valid && !slow) {
-            int n_in = 0;
-#pragma unroll
-            for (int v = 0; v < 8; ++v) n_in += sm.vflag[VI(v)] & 1;
-            if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
-            else if (n_in != 0) {
-                type = 4;   // boundary cell; centre test in phase 5
-#pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
-                    const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
-                    ushort4 fv;
-                    fv.x = (unsigned short)VI(nib & 0xf); fv.y = (unsigned short)VI((nib >> 4) & 0xf); fv.z = (unsigned short)VI((nib >> 8) & 0xf); fv.w = (unsigned short)VI((nib >> 12) & 0xf);
-                    const int npos = ((sm.vflag[fv.x] >> 1) & 1) + ((sm.vflag[fv.y] >> 1) & 1) + ((sm.vflag[fv.z] >> 1) & 1) + ((sm.vflag[fv.w] >> 1) & 1);
-                    if (npos == 4) continue;
-                    if (npos == 0) { fh[f] = HD_EPS1; continue; }
-                    const unsigned long long key = ((unsigned long long)(unsigned)s << 32) | (unsigned)fid[f];
-                    unsigned h = hd_hash<SM::HT>((unsigned)fid[f], (unsigned)s);
-                    for (;;) {
-                        const unsigned long long old = atomicCAS(&sm.key[h], HD_EMPTY, key);
-                        if (old == HD_EMPTY) {
-                            const int idx = atomicAdd(&sm.n_uf, 1);
-                            if (idx < SM::NF) { sm.val[h] = (unsigned short)idx; sm.fface[idx] = fid[f]; sm.fvi[idx] = fv; }
-                            else sm.val[h] = HD_NONE;
-                            break;
-                        }
-                        if (old == key) break;
-                        h = (h + 1) & (unsigned)(SM::HT - 1);
-                    }
-                    fh[f] = (unsigned short)h;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- phase 4: evaluate the unique cut faces ----
-        if (type == 4) {
-#pragma unroll
-            for (int f = 0; f < 6; ++f)
-                if (fh[f] < HD_EPS1) { fh[f] = sm.val[fh[f]]; slow = slow || (fh[f] == HD_NONE); }
-        }
-        const int nuf = min(sm.n_uf, SM::NF);
-        __syncthreads();                       // every val[] of the face phase has been read
-        for (int i = tid; i < SM::HT; i += B) sm.key[i] = HD_EMPTY;   // ready for the next batch
-        if (tid == 0) { sm.n_uv = 0; sm.n_uf = 0; }
-        for (int w = tid; w < nuf; w += B) {
-            const ushort4 fv = sm.fvi[w];
-            const D3 p[4] = {{sm.vx[fv.x], sm.vy[fv.x], sm.vz[fv.x]}, {sm.vx[fv.y], sm.vy[fv.y], sm.vz[fv.y]},
-                             {sm.vx[fv.z], sm.vy[fv.z], sm.vz[fv.z]}, {sm.vx[fv.w], sm.vy[fv.w], sm.vz[fv.w]}};
-            const double ph[4] = {sm.vphi[fv.x], sm.vphi[fv.y], sm.vphi[fv.z], sm.vphi[fv.w]};
-            const double magSf = __ldg(&m.face_rec[4 * (long long)sm.fface[w] + 3].x);
-            sm.feps[w] = cut_face_eps(p, ph, magSf);
-        }
-        __syncthreads();
-        // ---- phase 5: combine ----
-        if (valid) {
-            double volume = 0.0;
-            if (slow) heavy_eval_general(P, c, s, type, volume);
-            else if (type == 4) {
-                const DevSolid &S = P.solids[s];
-                const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-                const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-                double dummy;
-                type = shape_eval<false>(P.shapes[S.shape].s, world2local(q, t, ld3(m.cc, c)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
-                // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
-                D3 apex;
-                {
-                    const unsigned i0 = VI(0);
-                    const D3 A = {sm.vx[i0], sm.vy[i0], sm.vz[i0]};
-                    const double phiA = sm.vphi[i0];
-                    unsigned ib = VI(7);             // the FIRST i >= 1 with phiA * phi_i <= 0, else the last vertex
-#pragma unroll
-                    for (int i = 6; i >= 1; --i) { const unsigned ii = VI(i); if (phiA * sm.vphi[ii] <= 0) ib = ii; }
-                    const D3 Bp = {sm.vx[ib], sm.vy[ib], sm.vz[ib]};
-                    const double phiB = sm.vphi[ib];
-                    apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - Bp);
-                    if (m.two_d) apex.z = 0.0;
-                }
-#pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    if (fh[f] == HD_EPS0) continue;
-                    const double eps_f = (fh[f] == HD_EPS1) ? 1.0 : sm.feps[fh[f]];
-                    const double2 *fr = m.face_rec + 4 * (long long)fid[f];
-                    const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2);
-                    const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
-                    volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
-                }
-            }
-            P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));   // type 0: no vertex inside -> not a member
-        }
-        // the next batch's phase 1 touches key/val/ulist/n_uv only; vx..vflag/feps are rewritten after its first barrier
     }
 }
 

@@ -624,7 +624,6 @@ struct sdfibm_context {
     double t_host_us[4] = {0, 0, 0, 0}; // host wall time of the last interact: solid staging, enqueue / graph launch, wait for the GPU, whole call
     double t_ms[6] = {0, 0, 0, 0, 0, 0}; // binning, k_classify, k_heavy, k_accumulate, connectivity+finalise, whole pipeline
     int n_sm = 148;
-    int heavy_mode = 0;   // 0: warp-cooperative k_heavy_hex with pooled faces, 3: without pooling, 1/2: CTA-cooperative k_heavy_dedupe (B = 128 / 256)
     int64_t launches = 0, graph_launches = 0;
     // the device-resident entry replays one captured graph per step while its arguments stay the same
     typedef uint64_t GraphKey[20];
@@ -709,7 +708,6 @@ int sdfibm_create(int device, sdfibm_context **out) {
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fin[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device));
-    if (const char *e = getenv("SDFIBM_HEAVY")) ctx->heavy_mode = atoi(e);
     *out = ctx;
     return SDFIBM_OK;
 }
@@ -1146,19 +1144,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     if (ctx->n_global_hint) k_classify<256, 4, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
     else k_classify<256, 6, false><<<grid_for(nC, 256), 256, 0, st>>>(I);
     CUDA_TRY(rec(ctx->ev[2]));
-    if (ctx->dm.is_hex && ctx->heavy_mode == 1) {
-        constexpr int HB = 128, HC = 5;
-        const size_t smem = sizeof(HeavyDedupeSmem<HB>);
-        k_heavy_dedupe<HB, HC><<<ctx->n_sm * HC, HB, smem, st>>>(I);
-    } else if (ctx->dm.is_hex && ctx->heavy_mode == 2) {
-        constexpr int HB = 256, HC = 2;
-        const size_t smem = sizeof(HeavyDedupeSmem<HB>);
-        k_heavy_dedupe<HB, HC><<<ctx->n_sm * HC, HB, smem, st>>>(I);
-    } else if (ctx->dm.is_hex && ctx->heavy_mode == 3) k_heavy_hex<HEAVY_CTAS_PER_SM, false, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-    else if (ctx->dm.is_hex && ctx->heavy_mode == 4) k_heavy_hex<HEAVY_CTAS_PER_SM, true, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-    else if (ctx->dm.is_hex && ctx->heavy_mode == 5) k_heavy_hex<6, false, false><<<ctx->n_sm * 6, TPB, 0, st>>>(I);
-    else if (ctx->dm.is_hex && ctx->heavy_mode == 6) k_heavy_hex<6, true, false><<<ctx->n_sm * 6, TPB, 0, st>>>(I);
-    else if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM, false, true><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+    if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     CUDA_TRY(rec(ctx->ev[3]));
     if (chunked) {
@@ -1271,7 +1257,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
                                       (uint64_t)ctx->solids_in.p, (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
-                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)ctx->heavy_mode,
+                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)ctx->final_minb,
                                       (uint64_t)ctx->n_global_hint};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
