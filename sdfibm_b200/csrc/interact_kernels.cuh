@@ -652,7 +652,8 @@ __global__ void k_connectivity(ConnParams P) {
         const int e = P.slots[(long long)j * nC + c];
         if ((e & 3) == 0) continue;
         const int s = e >> 3;
-        const float *x = P.solids[s].pos32;
+        const DevSolid &S = P.solids[s];
+        const float *x = S.pos32;
         const float kc = conn_key(p, x);
         // try the face neighbour that lies towards the solid centre first: almost always a member with a smaller key
         const float rx = p.x - x[0], ry = p.y - x[1], rz = p.z - x[2];
@@ -660,8 +661,16 @@ __global__ void k_connectivity(ConnParams P) {
         const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
         const float comp = axis == 0 ? rx : axis == 1 ? ry : rz;
         const int first = __ldg(P.m.nb6 + 6 * (long long)c + 2 * axis + (comp > 0 ? 0 : 1));
-        bool has_parent = first >= 0 && find_member(P.n_item, P.slots, nC, first, s) >= 0 &&
-                          key_less(conn_key(__ldg(P.m.cc32 + first), x), first, kc, c);
+        bool has_parent = false;
+        if (first >= 0) {
+            const float4 pn = __ldg(P.m.cc32 + first);
+            const float kn = conn_key(pn, x);
+            if (key_less(kn, first, kc, c)) {
+                // k_classify's own fp32 test: a neighbour certainly inside the solid is a member (ALL_INSIDE) without looking it up
+                const float ri = S.ri32 - pn.w;
+                has_parent = (ri > 0.f && kn < ri * ri) || find_member(P.n_item, P.slots, nC, first, s) >= 0;
+            }
+        }
         if (!has_parent) {
             const int nb0 = __ldg(P.m.nb_off + c), nb1 = __ldg(P.m.nb_off + c + 1);
             for (int k = nb0; k < nb1 && !has_parent; ++k) {

@@ -69,6 +69,7 @@ struct DevSolid {
     double axis[3]; // world direction of the body z axis
     double r_out, r_in;
     float pos32[3]; // centre relative to the mesh origin (keys of the connectivity certificate)
+    float ri32;     // KIND_3D: certified inner radius minus the fp32 slack, rounded down (<= 0: none): the same test as k_classify
     int shape;
     int kind;
     int axis_is_z; // body z axis coincides with world z (2-D cases)
@@ -111,6 +112,7 @@ struct StepStatus {
     int slot_overflow;            // a cell was touched by more than K solids
     int bin_overflow;             // bin list capacity exceeded
     int bad_cell;                 // a cell/face exceeded MAX_CELL_VERTS / MAX_FACE_VERTS
+    int bad_shape;                // a solid refers to a shape index outside the table
     int bin_total;
     int n_global;
     unsigned long long heavy_total; // (cell, solid) items that needed exact evaluation
@@ -321,6 +323,7 @@ struct PrepParams {
     double rad3_max, radxy_max;
     double mesh_lo[3], mesh_hi[3];
     double origin[3];
+    double half_ext, rad_max;   // fp32 slack of the conservative tests: 4e-6 (half_ext + r_out + rad_max)
     int *bin_count;   // [n_bins+1]
     int *global_list; // [n_solids]
     StepStatus *status;
@@ -328,15 +331,18 @@ struct PrepParams {
 
 // SUB threads per solid share the loop over the bins its bounding box covers
 #define BIN_SUB 8
+__device__ __forceinline__ int sh_kind_of(const DevShape &sh) { return sh.kind; }
 __global__ void k_solid_prepare(PrepParams P) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = gid / BIN_SUB, sub = gid % BIN_SUB;
     if (s >= P.n_solids) return;
-    const sdfibm_solid_t in = P.solids[s];
+    sdfibm_solid_t in = P.solids[s];
+    if (in.shape < 0 || in.shape >= P.n_shapes) { P.status->bad_shape = 1; in.shape = 0; }
     DevSolid S;
     for (int d = 0; d < 3; ++d) { S.pos[d] = in.pos[d]; S.vel[d] = in.vel[d]; S.omega[d] = in.omega[d]; }
     for (int d = 0; d < 4; ++d) S.q[d] = in.quat[d];
     for (int d = 0; d < 3; ++d) S.pos32[d] = (float)(in.pos[d] - P.origin[d]);
+    S.ri32 = (sh_kind_of(P.shapes[in.shape]) == KIND_3D) ? __double2float_rd(P.shapes[in.shape].r_in - 4e-6 * (P.half_ext + P.shapes[in.shape].r_out + P.rad_max)) : 0.f;
     S.shape = in.shape;
     const DevShape &sh = P.shapes[in.shape];
     S.kind = sh.kind;
@@ -576,7 +582,9 @@ struct sdfibm_context {
     DevBuf<int> orig, inv;      // tile-order renumbering: position -> caller's label and back
     DevBuf<double> cc_orig;     // cell centres in the caller's order (fixInternal)
     DevBuf<float4> cc32;
-    int chunk_cmin[8] = {0}, chunk_cmax[8] = {0};   // caller-label range of every position chunk (host-buffer pipeline)
+    static const int MAX_CHUNK = 64;
+    int n_chunk = 8;           // host-buffer pipeline: U arrives / the fields leave in this many cell chunks
+    int chunk_cmin[MAX_CHUNK] = {0}, chunk_cmax[MAX_CHUNK] = {0};   // caller-label range of every position chunk
     double half_ext = 0.0;
     double bmin[3], bmax[3];
     float rad3_max = 0.f, radxy_max = 0.f;
@@ -617,9 +625,8 @@ struct sdfibm_context {
     StepStatus last{};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // host-buffer entry: U arrives and the fields leave in cell chunks on two copy streams, overlapped with the kernels
-    static const int N_CHUNK = 8;
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[N_CHUNK] = {}, ev_fin[N_CHUNK] = {};
+    cudaEvent_t ev_in[MAX_CHUNK] = {}, ev_fin[MAX_CHUNK] = {};
     struct { bool active = false, stale = false; double *As = nullptr, *Fs = nullptr, *Ts = nullptr, *Ct = nullptr; const double *U = nullptr; } pipe;
     double t_host_us[4] = {0, 0, 0, 0}; // host wall time of the last interact: solid staging, enqueue / graph launch, wait for the GPU, whole call
     double t_ms[6] = {0, 0, 0, 0, 0, 0}; // binning, k_classify, k_heavy, k_accumulate, connectivity+finalise, whole pipeline
@@ -631,6 +638,7 @@ struct sdfibm_context {
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
     int final_minb = 4;
+    bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     int n_global_hint = 0;   // host-side: some solid may be on the global list (selects the k_classify variant)
     int64_t flagged_last = 0;
 };
@@ -703,7 +711,8 @@ int sdfibm_create(int device, sdfibm_context **out) {
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
+    if (const char *e = getenv("SDFIBM_CHUNKS")) ctx->n_chunk = std::min(std::max(atoi(e), 1), (int)sdfibm_context::MAX_CHUNK);
+    for (int i = 0; i < sdfibm_context::MAX_CHUNK; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fin[i], cudaEventDisableTiming));
     }
@@ -730,7 +739,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_fin[i]) cudaEventDestroy(ctx->ev_fin[i]); }
+    for (int i = 0; i < sdfibm_context::MAX_CHUNK; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_fin[i]) cudaEventDestroy(ctx->ev_fin[i]); }
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -869,14 +878,15 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     }
     {
         DevBuf<int> rng;
-        CUDA_TRY(rng.ensure(16));
-        int init[16];
-        for (int k = 0; k < 8; ++k) { init[k] = 0x7fffffff; init[8 + k] = -1; }
+        CUDA_TRY(rng.ensure(2 * sdfibm_context::MAX_CHUNK));
+        const int MC = sdfibm_context::MAX_CHUNK;
+        int init[2 * sdfibm_context::MAX_CHUNK];
+        for (int k = 0; k < MC; ++k) { init[k] = 0x7fffffff; init[MC + k] = -1; }
         CUDA_TRY(cudaMemcpyAsync(rng.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-        k_chunk_ranges<<<grid_for(nC, 256), 256, 0, st>>>(ctx->orig.p, (int)nC, sdfibm_context::N_CHUNK, rng.p, rng.p + 8);
+        k_chunk_ranges<<<grid_for(nC, 256), 256, 0, st>>>(ctx->orig.p, (int)nC, ctx->n_chunk, rng.p, rng.p + MC);
         CUDA_TRY(cudaMemcpyAsync(init, rng.p, sizeof(init), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        for (int k = 0; k < 8; ++k) { ctx->chunk_cmin[k] = init[k]; ctx->chunk_cmax[k] = init[8 + k]; }
+        for (int k = 0; k < MC; ++k) { ctx->chunk_cmin[k] = init[k]; ctx->chunk_cmax[k] = init[MC + k]; }
         rng.release();
     }
     CUDA_TRY(ctx->cell_rad.ensure(nC));
@@ -962,6 +972,8 @@ int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) 
             return fail(SDFIBM_ERR_UNSUPPORTED, "sdfibm_set_shapes: shape type has no device tag (no CPU fallback)");
         shape_bounds(shapes[i], ctx->h_shapes[i]);
     }
+    ctx->shapes_may_be_global = false;
+    for (auto &sh : ctx->h_shapes) ctx->shapes_may_be_global |= (sh.kind != KIND_3D);
     int rc = upload(ctx->shapes, ctx->h_shapes.data(), (size_t)n, ctx->stream);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -981,12 +993,15 @@ static int stage_solids(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
     }
     const int ns = (int)ctx->h_shapes.size();
     // may any solid be tested by every cell (plane, or a 2-D shape whose axis is not exactly world z)?  A superset of the device's
-    // decision in k_solid_prepare: it only selects the k_classify variant that merges the global list.
+    // decision in k_solid_prepare: it only selects the k_classify variant that merges the global list.  Shape tables without
+    // planes / 2-D shapes need no per-solid pass on the host at all (the shape index is range-checked on the device).
     int hint = 0;
-    for (int i = 0; i < n; ++i) {
-        if (solids[i].shape < 0 || solids[i].shape >= ns) return fail(SDFIBM_ERR_ARG, "solid refers to an unknown shape index");
-        const int kind = ctx->h_shapes[solids[i].shape].kind;
-        hint |= (kind == KIND_PLANE) || (kind == KIND_2D && (solids[i].quat[1] != 0.0 || solids[i].quat[2] != 0.0));
+    if (ctx->shapes_may_be_global) {
+        for (int i = 0; i < n; ++i) {
+            if (solids[i].shape < 0 || solids[i].shape >= ns) return fail(SDFIBM_ERR_ARG, "solid refers to an unknown shape index");
+            const int kind = ctx->h_shapes[solids[i].shape].kind;
+            hint |= (kind == KIND_PLANE) || (kind == KIND_2D && (solids[i].quat[1] != 0.0 || solids[i].quat[2] != 0.0));
+        }
     }
     ctx->n_global_hint = hint;
     CUDA_TRY(ctx->solids_in.ensure(n));
@@ -1108,6 +1123,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         P.solids = ctx->solids_in.p; P.shapes = ctx->shapes.p; P.n_solids = n_solids; P.n_shapes = (int)ctx->h_shapes.size();
         P.out = ctx->solids.p; P.grid = g; P.rad3_max = ctx->rad3_max; P.radxy_max = ctx->radxy_max;
         for (int d = 0; d < 3; ++d) { P.mesh_lo[d] = ctx->bmin[d]; P.mesh_hi[d] = ctx->bmax[d]; P.origin[d] = ctx->dm.origin[d]; }
+        P.half_ext = ctx->half_ext; P.rad_max = (double)std::max(ctx->rad3_max, ctx->radxy_max);
         P.bin_count = ctx->bin_count; P.global_list = ctx->global_list.p; P.status = ctx->status;
         k_solid_prepare<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(P);
         size_t tmp_bytes = ctx->scan_tmp.n;
@@ -1151,17 +1167,17 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         // chunked: k_final of chunk i waits for its slice of U and releases its slice of the fields to the copy-out stream.
         // The copy engines are FIFO across streams, so the U chunks are enqueued only now — after every small upload /
         // memset the preceding kernels depend on — and still start at t ~ 0 because enqueueing is asynchronous.
-        for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
-            const size_t c0 = (size_t)nC * i / sdfibm_context::N_CHUNK, c1 = (size_t)nC * (i + 1) / sdfibm_context::N_CHUNK;
+        for (int i = 0; i < ctx->n_chunk; ++i) {
+            const size_t c0 = (size_t)nC * i / ctx->n_chunk, c1 = (size_t)nC * (i + 1) / ctx->n_chunk;
             if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(dU) + 3 * c0, ctx->pipe.U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
             CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
         }
         // Position chunk i touches the caller's cells [chunk_cmin[i], chunk_cmax[i]] (tile order follows the mesh in slabs, so
         // for block-structured numberings chunk i == cell range i): it waits for the U range holding its largest label, and
         // cell range j leaves once the last position chunk that intersects it is done.
-        const int NCH = sdfibm_context::N_CHUNK;
+        const int NCH = ctx->n_chunk;
         auto range_of = [&](int c) { int j = (int)(((long long)c * NCH) / nC); while ((long long)nC * j / NCH > c) --j; while ((long long)nC * (j + 1) / NCH <= c) ++j; return j; };
-        int i_last[sdfibm_context::N_CHUNK];
+        int i_last[sdfibm_context::MAX_CHUNK];
         for (int j = 0; j < NCH; ++j) i_last[j] = -1;
         for (int i = 0; i < NCH; ++i) {
             if (ctx->chunk_cmax[i] < 0) continue;
@@ -1189,7 +1205,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
                 CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ct + c0, dCt + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
             }
         }
-        ctx->launches += sdfibm_context::N_CHUNK - 1;
+        ctx->launches += ctx->n_chunk - 1;
     } else {
         I.c_begin = 0; I.c_end = nC;
         launch_final(ctx, I, grid_for(nC, 256), st);
@@ -1314,6 +1330,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
     }
     if (ctx->last.bin_overflow) return fail(SDFIBM_ERR_CAPACITY, "solid bin list overflow");
     if (ctx->last.bad_cell) return fail(SDFIBM_ERR_UNSUPPORTED, "cell with more than 32 vertices");
+    if (ctx->last.bad_shape) return fail(SDFIBM_ERR_ARG, "solid refers to an unknown shape index");
     if (ctx->last.slot_overflow)
         return fail(SDFIBM_ERR_CAPACITY, "more solids touch one cell than the slot count; raise it with sdfibm_set_cell_slots");
     if (ctx->last.heavy_total > (unsigned long long)ctx->heavy.n) return fail(SDFIBM_ERR_CAPACITY, "exact-evaluation queue overflow");
@@ -1396,13 +1413,13 @@ int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
     int rc = stage_solids(ctx, solids, n_solids);   // first on the copy engine, ahead of the U chunks
     if (rc) return rc;
     // U in / kernel / U out per cell chunk: the two copy directions overlap (full-duplex PCIe)
-    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
-        const size_t c0 = nC * i / sdfibm_context::N_CHUNK, c1 = nC * (i + 1) / sdfibm_context::N_CHUNK;
+    for (int i = 0; i < ctx->n_chunk; ++i) {
+        const size_t c0 = nC * i / ctx->n_chunk, c1 = nC * (i + 1) / ctx->n_chunk;
         if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(ctx->dU.p + 3 * c0, U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
         CUDA_TRY(cudaEventRecord(ctx->ev_in[i], ctx->s_in));
     }
-    for (int i = 0; i < sdfibm_context::N_CHUNK; ++i) {
-        const size_t c0 = nC * i / sdfibm_context::N_CHUNK, c1 = nC * (i + 1) / sdfibm_context::N_CHUNK;
+    for (int i = 0; i < ctx->n_chunk; ++i) {
+        const size_t c0 = nC * i / ctx->n_chunk, c1 = nC * (i + 1) / ctx->n_chunk;
         if (c1 <= c0) continue;
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[i], 0));
         k_fix_internal<<<grid_for((long long)(c1 - c0), 256), 256, 0, st>>>(ctx->cc_orig.p, ctx->solids_in.p, n_solids, ctx->dCt.p, ctx->dU.p, (int)c0, (int)c1);
