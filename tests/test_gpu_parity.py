@@ -84,6 +84,78 @@ def test_parity_synthetic(name):
     assert sum(ctx.candidate_counts()) > 0
 
 
+def _renumber_cells(mesh, perm):
+    """The same polyMesh with cell c relabelled perm[c] (faces whose owner would exceed their neighbour are flipped)."""
+    from sdfibm_b200.mesh import Mesh
+
+    owner, neigh = perm[mesh.owner].astype(np.int32), perm[mesh.neighbour].astype(np.int32)
+    fp_off, fp = mesh.fp_off.copy(), mesh.fp.copy()
+    for f in np.nonzero(owner[: len(neigh)] > neigh)[0]:
+        owner[f], neigh[f] = neigh[f], owner[f]
+        fp[fp_off[f]:fp_off[f + 1]] = fp[fp_off[f]:fp_off[f + 1]][::-1].copy()
+    return Mesh.from_polymesh(mesh.points.copy(), fp_off, fp, owner, neigh)
+
+
+@pytest.mark.parametrize("name", ["c4_small", "mixed3d"])
+def test_parity_scrambled_cell_numbering(name):
+    """The library renumbers cells into tile order internally: results must not depend on the caller's numbering being
+    structured.  A random relabelling of the cells is the worst case for that mapping (every gather / scatter is scattered)."""
+    base = cases.case_c4(n=40, n_solids=27, n_side=3) if name == "c4_small" else cases.case_mixed3d()
+    rng = np.random.RandomState(7)
+    perm = rng.permutation(base["mesh"].n_cells).astype(np.int32)
+    mesh = _renumber_cells(base["mesh"], perm)
+    U = np.empty_like(base["U"])
+    U[perm] = base["U"]
+    assert np.allclose(mesh.cc[perm], base["mesh"].cc, rtol=0, atol=1e-12)
+    case = dict(base, mesh=mesh, U=U)
+    o, ref, ctx, got = run_both(case, cell_slots=8 if name == "mixed3d" else None)
+    check_parity(case, o, ref, ctx, got)
+    # and the relabelled result is the original one, cell by cell: the classification exactly; the fractions only roughly, because
+    # the reference's apex construction starts from a face's FIRST vertex (geometrictools.cpp:74-96) and flipped faces start elsewhere
+    o0 = Oracle(base["mesh"], base["two_d"]).interact(base["shapes"], base["solids"], base["U"], base["dt"], base["rhof"])
+    assert np.array_equal(got["Ct"][perm], o0["Ct"])
+    assert np.abs(got["As"][perm] - o0["As"]).max() <= 0.1
+
+
+def test_graph_replay_follows_changing_arguments():
+    """The device-resident entry replays a captured CUDA graph: dt, rhof, the solid states and the buffers may change between steps."""
+    import torch
+
+    case = cases.case_c4(n=32, n_solids=8, n_side=2)
+    o = Oracle(case["mesh"], case["two_d"])
+    ctx = Context(0)
+    ctx.set_mesh(case["mesh"], case["two_d"])
+    ctx.set_shapes(case["shapes"])
+    nC, nS = case["mesh"].n_cells, len(case["solids"])
+    dev = torch.device("cuda", 0)
+    for step, (dt, rhof, shift, fresh) in enumerate([(1e-3, 1.0, 0.0, False), (2e-3, 1.5, 0.3, False), (5e-4, 0.7, -0.2, True), (5e-4, 0.7, 0.1, False)]):
+        S = case["solids"].copy()
+        S["pos"] += shift
+        U = case["U"] * (1.0 + 0.1 * step)
+        if step == 0 or fresh:
+            buf = [torch.empty(nC * k, dtype=torch.float64, device=dev) for k in (3, 1, 3, 1, 1)] + [torch.empty(nS * 6, dtype=torch.float64, device=dev)]
+        buf[0].copy_(torch.from_numpy(U.reshape(-1)))
+        torch.cuda.synchronize()
+        ctx.interact_device(S, *[b.data_ptr() for b in buf[:1]], dt, rhof, *[b.data_ptr() for b in buf[1:]])
+        ref = o.interact(case["shapes"], S, U, dt, rhof)
+        As, Fs, Ct, FT = buf[1].cpu().numpy(), buf[2].cpu().numpy().reshape(-1, 3), buf[4].cpu().numpy(), buf[5].cpu().numpy().reshape(-1, 6)
+        assert np.array_equal(Ct, ref["Ct"])
+        assert np.abs(As - ref["As"]).max() <= 1e-12
+        assert np.abs(Fs - ref["Fs"]).max() <= 1e-12 * max(1.0, np.abs(ref["Fs"]).max())
+        assert np.abs(FT - ref["FT"]).max() <= 1e-10 * max(1.0, np.abs(ref["FT"]).max())
+
+
+def test_unknown_shape_index_is_an_error():
+    case = cases.case_c4(n=32, n_solids=4, n_side=2)
+    ctx = Context(0)
+    ctx.set_mesh(case["mesh"], case["two_d"])
+    ctx.set_shapes(case["shapes"])
+    S = case["solids"].copy()
+    S["shape"][2] = 7
+    with pytest.raises(Exception, match="unknown shape index"):
+        ctx.interact(S, case["U"], case["dt"], case["rhof"])
+
+
 def test_parity_g1_and_golden(m1_points, g1_alpha):
     case = cases.case_g1(m1_points)
     o, ref, ctx, got = run_both(case)
