@@ -369,23 +369,34 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
 // volume phase is bank-conflict free.
 struct HeavySmem {
     double px[8 * TPB], py[8 * TPB], pz[8 * TPB], phi[8 * TPB];
+    double cx[TPB], cy[TPB], cz[TPB];   // cell centre of the lane's item
     unsigned char in[8 * TPB];
 };
 
-__device__ __forceinline__ void eval_vertex_to_smem(HeavySmem &sm, const DevMesh &m, const DevShape &sh, DQ q, D3 t, bool ident, int v,
-                                                    int slot_a, int col_a, bool dup, int slot_b, int col_b) {
-    const D3 p = ld3(m.points, v);
+// 8-byte asynchronous global -> shared copy: the coordinates of a lane's 8 vertices (and its cell centre) are all in flight
+// at once without holding registers, and land directly in the transposed layout the evaluation reads.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void stage_point(HeavySmem &sm, const double *__restrict__ points, int v, int slot, int col) {
+    const double *g = points + 3 * (long long)v;
+    cp_async8(&sm.px[slot * TPB + col], g);
+    cp_async8(&sm.py[slot * TPB + col], g + 1);
+    cp_async8(&sm.pz[slot * TPB + col], g + 2);
+}
+
+// evaluate the staged vertex (slot_a, col_a); dup: the same vertex is slot_b of the neighbouring lane's cell
+__device__ __forceinline__ void eval_staged_vertex(HeavySmem &sm, const DevShape &sh, DQ q, D3 t, bool ident,
+                                                   int slot_a, int col_a, bool dup, int slot_b, int col_b) {
+    const D3 p = {sm.px[slot_a * TPB + col_a], sm.py[slot_a * TPB + col_a], sm.pz[slot_a * TPB + col_a]};
     double ph;
     const bool in = shape_eval<true>(sh.s, world2local_sel(q, t, p, ident), ph);
-    sm.px[slot_a * TPB + col_a] = p.x;
-    sm.py[slot_a * TPB + col_a] = p.y;
-    sm.pz[slot_a * TPB + col_a] = p.z;
     sm.phi[slot_a * TPB + col_a] = ph;
     sm.in[slot_a * TPB + col_a] = in ? 1 : 0;
     if (dup) {
-        sm.px[slot_b * TPB + col_b] = p.x;
-        sm.py[slot_b * TPB + col_b] = p.y;
-        sm.pz[slot_b * TPB + col_b] = p.z;
         sm.phi[slot_b * TPB + col_b] = ph;
         sm.in[slot_b * TPB + col_b] = in ? 1 : 0;
     }
@@ -439,11 +450,22 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
         const DevShape &sh = P.shapes[shape_idx];
         // warp-uniform: every solid of this warp's items still has the identity orientation (world2local == p - t)
         const bool ident = __all_sync(FULL, !valid || quat_is_identity(q));
+        // stage the coordinates of my 8 vertices and my cell centre: 27 asynchronous 8-byte copies, one memory latency
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) stage_point(sm, m.points, vid[j], j, tid);
+            const double *g = m.cc + 3 * (long long)c;
+            cp_async8(&sm.cx[tid], g);
+            cp_async8(&sm.cy[tid], g + 1);
+            cp_async8(&sm.cz[tid], g + 2);
+        }
+        cp_async_wait_all();
+        __syncwarp();
         // rounds 0..3: my own high quad (also the next lane's low quad when it shares)
         if (valid) {
-#pragma unroll 2
+#pragma unroll
             for (int v = 0; v < 4; ++v)
-                eval_vertex_to_smem(sm, m, sh, q, t, ident, vid[2 * v + 1], 2 * v + 1, tid, right_shares, 2 * v, tid + 1);
+                eval_staged_vertex(sm, sh, q, t, ident, 2 * v + 1, tid, right_shares, 2 * v, tid + 1);
         }
         // extra rounds: low quads of the run starts, 4 vertices each, spread over all lanes
         const int nwork = 4 * __popc(startmask);
@@ -451,18 +473,14 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             const int u = base + lane;
             const bool work = u < nwork;
             const int src = work ? (int)__fns(startmask, 0, (u >> 2) + 1) : 0;
-            // the low-quad vertex (slot 0, 2, 4 or 6) and the solid of the run start `src`, fetched by shuffle
-            const int v0 = __shfl_sync(FULL, vid[0], src), v2 = __shfl_sync(FULL, vid[2], src);
-            const int v4 = __shfl_sync(FULL, vid[4], src), v6 = __shfl_sync(FULL, vid[6], src);
             const int s_src = __shfl_sync(FULL, s, src);
             if (work) {
-                const int q4 = u & 3, kk = 2 * q4;
-                const int vv = (q4 == 0) ? v0 : (q4 == 1) ? v2 : (q4 == 2) ? v4 : v6;
+                const int kk = 2 * (u & 3);
                 const int col = wbase + src;
                 const DevSolid &S2 = P.solids[s_src];
                 const DQ q2 = {S2.q[0], {S2.q[1], S2.q[2], S2.q[3]}};
                 const D3 t2 = {S2.pos[0], S2.pos[1], S2.pos[2]};
-                eval_vertex_to_smem(sm, m, P.shapes[S2.shape], q2, t2, ident, vv, kk, col, false, 0, 0);
+                eval_staged_vertex(sm, P.shapes[S2.shape], q2, t2, ident, kk, col, false, 0, 0);
             }
         }
         __syncwarp();
@@ -475,7 +493,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
             else if (n_in != 0) {
                 double dummy;
-                type = shape_eval<false>(sh.s, world2local_sel(q, t, ld3(m.cc, c), ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                type = shape_eval<false>(sh.s, world2local_sel(q, t, D3{sm.cx[tid], sm.cy[tid], sm.cz[tid]}, ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
                 auto PT = [&](int l) { return D3{sm.px[l * TPB + tid], sm.py[l * TPB + tid], sm.pz[l * TPB + tid]}; };
                 auto PH = [&](int l) { return sm.phi[l * TPB + tid]; };
                 // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
