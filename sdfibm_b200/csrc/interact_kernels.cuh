@@ -256,14 +256,20 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
                 ++n_item;
             } else P.status->slot_overflow = 1;
         };
-        // fp32 three-way test of a binned candidate (two 16-byte records)
+        // fp32 three-way test of a binned candidate (two 16-byte records) against the cell's vertex-cloud box: N2 bounds the
+        // nearest vertex from below (for box cells it IS the nearest corner), F2 the farthest vertex from above; r_out / r_in
+        // carry the fp32 slack
+        const float4 hb = m.box_uniform ? m.box_const : __ldg(m.cell_box + c);
         auto test32 = [&](float4 e0, float4 e1) {
-            const int kind = __float_as_int(e1.z);
-            const float dx = p.x - e0.x, dy = p.y - e0.y, dz = (kind == KIND_3D) ? p.z - e0.z : 0.f;
-            const float d2 = dx * dx + dy * dy + dz * dz;
-            const float r = (kind == KIND_3D) ? p.w : (m.rad_uniform ? m.rad_const.y : __ldg(&m.cell_rad[c].y));
-            const float ro = e0.w + r, ri = e1.x - r;
-            return (d2 > ro * ro) ? 0 : ((ri > 0.f && d2 < ri * ri) ? 1 : 2);
+            const bool k3 = __float_as_int(e1.z) == KIND_3D;
+            const float ax = fabsf(p.x - e0.x), ay = fabsf(p.y - e0.y), az = k3 ? fabsf(p.z - e0.z) : 0.f;
+            const float hz = k3 ? hb.z : 0.f;
+            const float fx = ax + hb.x, fy = ay + hb.y, fz = az + hz;
+            float nx = ax - hb.x, ny = ay - hb.y, nz = az - hz;
+            if (hb.w == 0.f) { nx = fmaxf(nx, 0.f); ny = fmaxf(ny, 0.f); nz = fmaxf(nz, 0.f); }
+            const float N2 = nx * nx + ny * ny + nz * nz, F2 = fx * fx + fy * fy + fz * fz;
+            const float ro = e0.w, ri = e1.x;
+            return (N2 > ro * ro) ? 0 : ((ri > 0.f && F2 < ri * ri) ? 1 : 2);
         };
         if (!HAS_GLOBAL) {
             for (; bi < be; ++bi) {

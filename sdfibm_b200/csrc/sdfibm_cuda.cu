@@ -92,6 +92,12 @@ struct DevMesh {
     const float4 *cc32;       // per position: fp32 (centre - origin, vertex-cloud radius rounded up): conservative pre-classification
     const unsigned *tile_key; // per position: linear index of its tile in the tile grid (= solid-bin index)
     double origin[3];         // centre of the mesh bounds
+    // Bounding box of each cell's vertex cloud about its centre (half extents, rounded up; w = 1 when the cell IS that box: every
+    // vertex sits on a corner).  k_classify bounds the nearest / farthest vertex of a cell with it: for box cells the
+    // pre-classification is then exact up to the fp32 slack, so only cells that really have vertices on both sides are queued.
+    const float4 *cell_box;   // per position (nullptr when box_uniform)
+    float4 box_const;         // the one box of a uniform mesh
+    int box_uniform;
     float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
     int rad_uniform;
     int is_hex;             // every cell has 8 points / 6 faces and every face 4 points
@@ -234,6 +240,30 @@ __global__ void k_cell_radius(DevMesh m, float2 *rad, int *bad, float *rmax) {
         atomicMin((int *)&rmax[2], __float_as_int(m3[0]));
         atomicMin((int *)&rmax[3], __float_as_int(mxy[0]));
     }
+}
+
+// per-cell half extents of the vertex cloud + "is an axis-aligned box" flag; ext[0..2] = max, ext[3..5] = min over the mesh
+// (as int bits of non-negative floats), ext[6] = number of non-box cells
+__global__ void k_cell_box(DevMesh m, float4 *box, int *ext) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    const D3 cc = ld3(m.cc, c);
+    const int b = m.cp_off[c], e = m.cp_off[c + 1];
+    double hx = 0.0, hy = 0.0, hz = 0.0;
+    for (int k = b; k < e; ++k) {
+        const D3 d = ld3(m.points, m.cp[k]) - cc;
+        hx = fmax(hx, fabs(d.x)); hy = fmax(hy, fabs(d.y)); hz = fmax(hz, fabs(d.z));
+    }
+    bool is_box = (e - b == 8);
+    for (int k = b; k < e && is_box; ++k) {
+        const D3 d = ld3(m.points, m.cp[k]) - cc;
+        is_box = fabs(d.x) >= hx * (1.0 - 1e-9) && fabs(d.y) >= hy * (1.0 - 1e-9) && fabs(d.z) >= hz * (1.0 - 1e-9);
+    }
+    const float fx = __double2float_ru(hx * (1.0 + REL_MARGIN)), fy = __double2float_ru(hy * (1.0 + REL_MARGIN)), fz = __double2float_ru(hz * (1.0 + REL_MARGIN));
+    box[c] = make_float4(fx, fy, fz, is_box ? 1.f : 0.f);
+    atomicMax(ext + 0, __float_as_int(fx)); atomicMax(ext + 1, __float_as_int(fy)); atomicMax(ext + 2, __float_as_int(fz));
+    atomicMin(ext + 3, __float_as_int(fx)); atomicMin(ext + 4, __float_as_int(fy)); atomicMin(ext + 5, __float_as_int(fz));
+    if (!is_box) atomicAdd(ext + 6, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -575,6 +605,7 @@ struct sdfibm_context {
     DevBuf<double> points, cc, V, Cf, Sf;
     DevBuf<int> cp_off, cp, cf_off, cf, fp_off, fp, nb_off, nb;
     DevBuf<float2> cell_rad;
+    DevBuf<float4> cell_box;
     DevBuf<double> magSf;
     DevBuf<double2> face_rec;
     DevBuf<unsigned> hex_topo, tile_key;
@@ -729,7 +760,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
-    ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release();
     ctx->global_list.release(); ctx->slots.release();
@@ -942,6 +973,28 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     CUDA_TRY(ctx->nb6.ensure(6 * nC));
     d.nb6 = ctx->nb6.p;
     k_nb6<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->nb6.p);
+    {
+        // cell boxes; a mesh of identical boxes keeps one constant instead of 16 bytes per cell
+        DevBuf<int> ext;
+        CUDA_TRY(ctx->cell_box.ensure(nC));
+        CUDA_TRY(ext.ensure(7));
+        const int init[7] = {0, 0, 0, 0x7f7fffff, 0x7f7fffff, 0x7f7fffff, 0};
+        CUDA_TRY(cudaMemcpyAsync(ext.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        k_cell_box<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->cell_box.p, ext.p);
+        int h_ext[7];
+        CUDA_TRY(cudaMemcpyAsync(h_ext, ext.p, sizeof(h_ext), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ext.release();
+        float mx[3], mn[3];
+        memcpy(mx, h_ext, sizeof(mx));
+        memcpy(mn, h_ext + 3, sizeof(mn));
+        bool uniform = h_ext[6] == 0;
+        for (int k = 0; k < 3; ++k) uniform = uniform && (mx[k] - mn[k] <= 1e-6f * mx[k]);
+        d.box_uniform = uniform ? 1 : 0;
+        d.box_const = make_float4(mx[0], mx[1], mx[2], 1.f);
+        d.cell_box = ctx->cell_box.p;
+        if (uniform) { ctx->cell_box.release(); d.cell_box = nullptr; }
+    }
     k_cc32<<<grid_for(nC, 256), 256, 0, st>>>(ctx->cc.p, ctx->cell_rad.p, (int)nC, d.origin[0], d.origin[1], d.origin[2], ctx->cc32.p);
     CUDA_TRY(cudaGetLastError());
     int h_bad = 0;
