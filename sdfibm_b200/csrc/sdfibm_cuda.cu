@@ -668,7 +668,6 @@ struct sdfibm_context {
     GraphKey graph_key = {0};
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
-    int final_minb = 4;
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     int n_global_hint = 0;   // host-side: some solid may be on the global list (selects the k_classify variant)
     int64_t flagged_last = 0;
@@ -738,7 +737,6 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaMallocHost(&ctx->h_scal, 2 * sizeof(double)));
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
-    if (const char *e = getenv("SDFIBM_FINAL_MINB")) ctx->final_minb = atoi(e);
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -1152,12 +1150,6 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     return SDFIBM_OK;
 }
 
-static void launch_final(sdfibm_context *ctx, const InteractParams &I, int grid, cudaStream_t st) {
-    if (ctx->final_minb == 4) k_final<4><<<grid, 256, 0, st>>>(I);
-    else if (ctx->final_minb == 6) k_final<6><<<grid, 256, 0, st>>>(I);
-    else k_final<5><<<grid, 256, 0, st>>>(I);
-}
-
 // Everything one pass of the pipeline enqueues on the context stream (directly, or once into a CUDA graph that later steps
 // re-launch: ~20 dependent launches / memsets become one submission, which matters because every step starts on an idle GPU).
 static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, double *dAs, double *dFs, double *dTs, double *dCt,
@@ -1243,7 +1235,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
             if (p1 > p0) {
                 I.c_begin = (int)p0; I.c_end = (int)p1;
                 CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
-                launch_final(ctx, I, grid_for(p1 - p0, 256), st);
+                k_final<4><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
             }
             CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
             for (int j = 0; j < NCH; ++j) {
@@ -1261,7 +1253,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         ctx->launches += ctx->n_chunk - 1;
     } else {
         I.c_begin = 0; I.c_end = nC;
-        launch_final(ctx, I, grid_for(nC, 256), st);
+        k_final<4><<<grid_for(nC, 256), 256, 0, st>>>(I);
     }
     CUDA_TRY(rec(ctx->ev[4]));
     ctx->launches += 3;
@@ -1326,7 +1318,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
                                       (uint64_t)ctx->solids_in.p, (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
-                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)ctx->final_minb,
+                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)0,
                                       (uint64_t)ctx->n_global_hint};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
