@@ -154,7 +154,6 @@ struct InteractParams {
     int2 *heavy;            // queue of (cell, solid) needing exact evaluation
     double2 *heavy_res;     // [queue] per item: (solid volume inside the cell, bits: CELL_TYPE | solid << 2)
     unsigned long long *heavy_count;
-    int2 *chunk;            // [n_blocks] (first queue index, count) of the items each k_classify CTA appended (nullptr: not wanted)
     long long heavy_cap;
     int K;
     const unsigned char *excluded; // replay pass: [n_cells*K] 1 = pair is outside the seed's component
@@ -316,7 +315,6 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w) { const int t = s_wtot[w]; s_wtot[w] = tot; tot += t; }
         s_base = tot ? atomicAdd(P.heavy_count, (unsigned long long)tot) : 0ull;
-        if (P.chunk) P.chunk[blockIdx.x] = make_int2((int)s_base, tot);
     }
     __syncthreads();
     if (n_heavy == 0) return;
@@ -558,302 +556,6 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));   // type 0: no vertex inside -> not a member
         }
         __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_heavy_tile: hexahedral path on the static tile topology.  One WARP takes up to 64 consecutive queue items of one
-// 256-position block (a compact brick of cells, a few solids).  With the block-local vertex / face indices of the mesh
-// (DevMesh::lv, lf, bf_lv) a (solid ordinal, local index) pair is a bit position, so the unique vertices and the unique
-// cut faces of the unit are found with shared-memory bitmaps + population counts — no hashing, no block barriers — and
-// are evaluated in packed rounds of 32: every (solid, vertex) once instead of ~5x, every cut face once instead of twice,
-// with no lane idling behind a neighbour that has more cut faces.  A vertex or face is evaluated by the same instruction
-// sequence whichever cell needs it, so the results are bit-identical to the per-cell kernels.  Units that do not fit the
-// fixed capacities fall back to the self-contained per-item evaluation.
-// ------------------------------------------------------------------------------------------------
-#define HT_W 64       // queue items per unit (two per lane)
-#define HT_NS 8       // distinct solids per unit
-#define HT_VW 16      // vertex bitmap words per solid  (512 block-local vertices)
-#define HT_FW 32      // face bitmap words per solid    (1024 block-local faces)
-#define HT_VCAP 192   // unique (solid, vertex) pairs per unit
-#define HT_FCAP 192   // unique cut (solid, face) pairs per unit
-struct HeavyTileWarp {
-    double vx[HT_VCAP], vy[HT_VCAP], vz[HT_VCAP], vphi[HT_VCAP];
-    double feps[HT_FCAP];
-    unsigned vbm[HT_NS * HT_VW];
-    unsigned fbm[HT_NS * HT_FW];
-    unsigned short vpre[HT_NS * HT_VW];
-    unsigned short fpre[HT_NS * HT_FW];
-    unsigned short vlist[HT_VCAP];   // solid ordinal << 9 | local vertex
-    unsigned short flist[HT_FCAP];   // solid ordinal << 10 | local face
-    int solid[HT_NS];
-    unsigned char vflag[HT_VCAP];    // bit 0: strictly inside (isInside), bit 1: filtered phi > 0
-};
-
-// calcFaceAreaFraction of a cut quadrilateral face (geometrictools.cpp:74-116); vertices in the face's own order
-__device__ __forceinline__ double cut_face_eps(const D3 p[4], const double ph[4], double magSf) {
-    const D3 A = p[0];
-    D3 Bp = p[1];
-    double phiB = ph[1];
-    if (!(ph[0] * ph[1] <= 0)) {
-        Bp = p[2];
-        phiB = ph[2];
-        if (!(ph[0] * ph[2] <= 0)) { Bp = p[3]; phiB = ph[3]; }
-    }
-    const D3 fap = A - fabs(ph[0]) / (SDF_SMALL + fabs(ph[0]) + fabs(phiB)) * (A - Bp);
-    double area = 0.0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const double lf = line_fraction(ph[e], ph[(e + 1) & 3]);
-        const D3 O = p[e], A2 = p[(e + 1) & 3];
-        area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
-    }
-    return area / magSf;
-}
-
-template <int CTAS>
-__global__ void __launch_bounds__(128, CTAS) k_heavy_tile(InteractParams P) {
-    __shared__ HeavyTileWarp smw[4];
-    HeavyTileWarp &sm = smw[threadIdx.x >> 5];
-    const DevMesh &m = P.m;
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5), nw = gridDim.x * 4;
-    for (int i = lane; i < HT_NS * HT_VW; i += 32) sm.vbm[i] = 0u;
-    for (int i = lane; i < HT_NS * HT_FW; i += 32) sm.fbm[i] = 0u;
-    __syncwarp();
-    // rank of bit `l` of solid ordinal j among the set bits of a bitmap (= index of the pair in the unit's dense list)
-    auto vrank = [&](int j, unsigned l) -> unsigned { const int w = j * HT_VW + (int)(l >> 5); return sm.vpre[w] + __popc(sm.vbm[w] & ((1u << (l & 31u)) - 1u)); };
-    auto frank = [&](int j, unsigned l) -> unsigned { const int w = j * HT_FW + (int)(l >> 5); return sm.fpre[w] + __popc(sm.fbm[w] & ((1u << (l & 31u)) - 1u)); };
-    for (int b = gw; b < m.n_blocks; b += nw) {
-        const int2 ch = P.chunk[b];
-        if (ch.y == 0) continue;
-        const int bv0 = __ldg(m.bv_off + b), bf0 = __ldg(m.bf_off + b);
-        for (int i0 = 0; i0 < ch.y; i0 += HT_W) {
-            // ---- 0: my (up to) two items; ordinals of the unit's distinct solids ----
-            int c[2] = {0, 0}, s[2] = {0, 0}, jj[2] = {0, 0};
-            long long kq[2] = {0, 0};
-            bool val[2];
-            int ns = 0;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int idx = i0 + 32 * r + lane;
-                kq[r] = (long long)ch.x + idx;
-                val[r] = idx < ch.y && kq[r] < P.heavy_cap;
-                if (val[r]) { const int2 it = __ldg(P.heavy + kq[r]); c[r] = it.x; s[r] = it.y; }
-                unsigned rem = __ballot_sync(FULL, val[r]);
-                while (rem) {
-                    const int s0 = __shfl_sync(FULL, s[r], __ffs(rem) - 1);
-                    const unsigned found = __ballot_sync(FULL, lane < min(ns, HT_NS) && sm.solid[lane] == s0);
-                    int id;
-                    if (found) id = __ffs(found) - 1;
-                    else {
-                        id = ns;
-                        if (lane == 0 && ns < HT_NS) sm.solid[ns] = s0;
-                        ++ns;
-                        __syncwarp();
-                    }
-                    const bool mine = val[r] && s[r] == s0;
-                    if (mine) jj[r] = id;
-                    rem &= ~__ballot_sync(FULL, mine);
-                }
-            }
-            bool fallback = ns > HT_NS;
-            // ---- 1: mark the (solid, vertex) pairs the unit needs ----
-            uint4 lvp[2] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
-            auto LV = [&](const uint4 &q, int k) -> unsigned { const unsigned w = (k < 2) ? q.x : (k < 4) ? q.y : (k < 6) ? q.z : q.w; return (w >> (16 * (k & 1))) & 0xffffu; };
-            if (!fallback) {
-                bool big = false;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    if (!val[r]) continue;
-                    lvp[r] = __ldg(reinterpret_cast<const uint4 *>(m.lv + 8 * (long long)c[r]));
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const unsigned l = LV(lvp[r], k);
-                        if (l >= 32u * HT_VW) big = true;
-                        else atomicOr(&sm.vbm[jj[r] * HT_VW + (int)(l >> 5)], 1u << (l & 31u));
-                    }
-                }
-                fallback = __any_sync(FULL, big);
-            }
-            __syncwarp();
-            // ---- 2: dense list of the marked pairs (four bitmap words per lane) ----
-            int nv = 0;
-            if (!fallback) {
-                unsigned w4[4];
-                int cnt = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { w4[i] = sm.vbm[4 * lane + i]; cnt += __popc(w4[i]); }
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                nv = __shfl_sync(FULL, incl, 31);
-                fallback = nv > HT_VCAP;
-                if (!fallback) {
-                    int pos = incl - cnt;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int w = 4 * lane + i;
-                        sm.vpre[w] = (unsigned short)pos;
-                        unsigned bits = w4[i];
-                        while (bits) {
-                            const int bit = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            sm.vlist[pos++] = (unsigned short)(((w / HT_VW) << 9) | ((w % HT_VW) << 5) | bit);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            // ---- 3: evaluate every unique (solid, vertex) once ----
-            if (!fallback) {
-                for (int u = lane; u < nv; u += 32) {
-                    const unsigned e = sm.vlist[u];
-                    const DevSolid &S = P.solids[sm.solid[e >> 9]];
-                    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-                    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-                    const D3 p = ld3(m.points, __ldg(m.bv + bv0 + (int)(e & 511u)));
-                    double ph;
-                    const bool in = shape_eval<true>(P.shapes[S.shape].s, world2local_sel(q, t, p, quat_is_identity(q)), ph);
-                    sm.vx[u] = p.x; sm.vy[u] = p.y; sm.vz[u] = p.z; sm.vphi[u] = ph;
-                    sm.vflag[u] = (unsigned char)((in ? 1 : 0) | (ph > 0 ? 2 : 0));
-                }
-            }
-            __syncwarp();
-            // ---- 4: cell types; mark the cut faces ----
-            int type[2] = {0, 0};
-            unsigned ulo[2] = {0u, 0u}, uhi[2] = {0u, 0u}, fcls[2] = {0u, 0u};
-            unsigned lfp[2][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
-            if (!fallback) {
-                bool big = false;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    if (!val[r]) continue;
-                    int n_in = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const unsigned u = vrank(jj[r], LV(lvp[r], k));
-                        if (k < 4) ulo[r] |= u << (8 * k); else uhi[r] |= u << (8 * (k - 4));
-                        n_in += sm.vflag[u] & 1;
-                    }
-                    if (n_in == 8) type[r] = SDFIBM_CELL_ALL_INSIDE;
-                    else if (n_in != 0) {
-                        type[r] = 4;   // boundary cell; the centre test comes with the combine phase
-                        const unsigned tw0 = __ldg(m.hex_topo + 3 * (long long)c[r]), tw1 = __ldg(m.hex_topo + 3 * (long long)c[r] + 1), tw2 = __ldg(m.hex_topo + 3 * (long long)c[r] + 2);
-                        const unsigned *lfg = reinterpret_cast<const unsigned *>(m.lf + 6 * (long long)c[r]);
-                        lfp[r][0] = __ldg(lfg); lfp[r][1] = __ldg(lfg + 1); lfp[r][2] = __ldg(lfg + 2);
-                        auto U = [&](unsigned l) -> unsigned { return (((l & 4u) ? uhi[r] : ulo[r]) >> (8 * (l & 3u))) & 0xffu; };
-#pragma unroll
-                        for (int f = 0; f < 6; ++f) {
-                            const unsigned w = (f < 2) ? tw0 : (f < 4) ? tw1 : tw2;
-                            const unsigned nib = (w >> (16 * (f & 1))) & 0xffffu;
-                            const int npos = ((sm.vflag[U(nib & 0xf)] >> 1) & 1) + ((sm.vflag[U((nib >> 4) & 0xf)] >> 1) & 1) +
-                                             ((sm.vflag[U((nib >> 8) & 0xf)] >> 1) & 1) + ((sm.vflag[U((nib >> 12) & 0xf)] >> 1) & 1);
-                            const unsigned cls = (npos == 4) ? 0u : (npos == 0) ? 1u : 2u;   // entirely outside / inside / cut
-                            fcls[r] |= cls << (2 * f);
-                            if (cls == 2u) {
-                                const unsigned l = (lfp[r][f >> 1] >> (16 * (f & 1))) & 0xffffu;
-                                if (l >= 32u * HT_FW) big = true;
-                                else atomicOr(&sm.fbm[jj[r] * HT_FW + (int)(l >> 5)], 1u << (l & 31u));
-                            }
-                        }
-                    }
-                }
-                fallback = __any_sync(FULL, big);
-            }
-            __syncwarp();
-            // ---- 5: dense list of the cut faces (eight bitmap words per lane) ----
-            int nf = 0;
-            if (!fallback) {
-                unsigned w8[8];
-                int cnt = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { w8[i] = sm.fbm[8 * lane + i]; cnt += __popc(w8[i]); }
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-                nf = __shfl_sync(FULL, incl, 31);
-                fallback = nf > HT_FCAP;
-                if (!fallback) {
-                    int pos = incl - cnt;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int w = 8 * lane + i;
-                        sm.fpre[w] = (unsigned short)pos;
-                        unsigned bits = w8[i];
-                        while (bits) {
-                            const int bit = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            sm.flist[pos++] = (unsigned short)(((w / HT_FW) << 10) | ((w % HT_FW) << 5) | bit);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            // ---- 6: evaluate every unique cut face once ----
-            if (!fallback) {
-                for (int w = lane; w < nf; w += 32) {
-                    const unsigned e = sm.flist[w];
-                    const int j = (int)(e >> 10);
-                    const int fl = bf0 + (int)(e & 1023u);
-                    const uint2 fv = __ldg(reinterpret_cast<const uint2 *>(m.bf_lv + 4 * (long long)fl));
-                    const unsigned u0 = vrank(j, fv.x & 0xffffu), u1 = vrank(j, fv.x >> 16), u2 = vrank(j, fv.y & 0xffffu), u3 = vrank(j, fv.y >> 16);
-                    const D3 p[4] = {{sm.vx[u0], sm.vy[u0], sm.vz[u0]}, {sm.vx[u1], sm.vy[u1], sm.vz[u1]},
-                                     {sm.vx[u2], sm.vy[u2], sm.vz[u2]}, {sm.vx[u3], sm.vy[u3], sm.vz[u3]}};
-                    const double ph[4] = {sm.vphi[u0], sm.vphi[u1], sm.vphi[u2], sm.vphi[u3]};
-                    const double magSf = __ldg(&m.face_rec[4 * (long long)__ldg(m.bf + fl) + 3].x);
-                    sm.feps[w] = cut_face_eps(p, ph, magSf);
-                }
-            }
-            __syncwarp();
-            // ---- 7: combine (or the self-contained evaluation when the unit did not fit) ----
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (!val[r]) continue;
-                double volume = 0.0;
-                int ty = type[r];
-                if (fallback) heavy_eval_general(P, c[r], s[r], ty, volume);
-                else if (ty == 4) {
-                    const DevSolid &S = P.solids[s[r]];
-                    const DQ q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
-                    const D3 t = {S.pos[0], S.pos[1], S.pos[2]};
-                    double dummy;
-                    ty = shape_eval<false>(P.shapes[S.shape].s, world2local_sel(q, t, ld3(m.cc, c[r]), quat_is_identity(q)), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
-                    auto U = [&](int l) -> unsigned { return (((l & 4) ? uhi[r] : ulo[r]) >> (8 * (l & 3))) & 0xffu; };
-                    // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
-                    const unsigned i0v = U(0);
-                    const D3 A = {sm.vx[i0v], sm.vy[i0v], sm.vz[i0v]};
-                    const double phiA = sm.vphi[i0v];
-                    unsigned ib = U(7);              // the FIRST i >= 1 with phiA * phi_i <= 0, else the last vertex
-#pragma unroll
-                    for (int i = 6; i >= 1; --i) { const unsigned ii = U(i); if (phiA * sm.vphi[ii] <= 0) ib = ii; }
-                    const D3 Bp = {sm.vx[ib], sm.vy[ib], sm.vz[ib]};
-                    const double phiB = sm.vphi[ib];
-                    D3 apex = A - fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB)) * (A - Bp);
-                    if (m.two_d) apex.z = 0.0;
-                    const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c[r]);
-                    const int2 f01 = __ldg(cf2), f23 = __ldg(cf2 + 1), f45 = __ldg(cf2 + 2);
-                    const int fid[6] = {f01.x, f01.y, f23.x, f23.y, f45.x, f45.y};
-#pragma unroll
-                    for (int f = 0; f < 6; ++f) {
-                        const unsigned cls = (fcls[r] >> (2 * f)) & 3u;
-                        if (cls == 0u) continue;                                    // eps_f = 0: adds +0.0 (:107-108)
-                        const double eps_f = (cls == 1u) ? 1.0 : sm.feps[frank(jj[r], (lfp[r][f >> 1] >> (16 * (f & 1))) & 0xffffu)];
-                        const double2 *fr = m.face_rec + 4 * (long long)fid[f];
-                        const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2);
-                        const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
-                        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
-                    }
-                }
-                P.heavy_res[kq[r]] = make_double2(volume, __longlong_as_double((long long)(ty | (s[r] << 2))));   // type 0: no vertex inside -> not a member
-            }
-            __syncwarp();
-            for (int i = lane; i < HT_NS * HT_VW; i += 32) sm.vbm[i] = 0u;
-            for (int i = lane; i < HT_NS * HT_FW; i += 32) sm.fbm[i] = 0u;
-            __syncwarp();
-        }
     }
 }
 

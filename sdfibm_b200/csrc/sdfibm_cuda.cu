@@ -14,7 +14,6 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
-#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
 #include <chrono>
@@ -99,13 +98,6 @@ struct DevMesh {
     const float4 *cell_box;   // per position (nullptr when box_uniform)
     float4 box_const;         // the one box of a uniform mesh
     int box_uniform;
-    // Static tile topology (hex meshes): block b = positions [256 b, 256 b + 256).  bv / bf list the block's unique point / face
-    // labels (ascending); lv / lf give, for every cell vertex / face, its index in the block's list; bf_lv the block-local
-    // vertex indices of each listed face (faces() order).  A (block-local index, solid) pair is then a bitmap position, which
-    // is how k_heavy_tile de-duplicates the vertices and cut faces of a tile's queued cells without hashing.
-    const int *bv_off, *bv, *bf_off, *bf;
-    const unsigned short *lv, *lf, *bf_lv;
-    int n_blocks, has_tile_topo;
     float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
     int rad_uniform;
     int is_hex;             // every cell has 8 points / 6 faces and every face 4 points
@@ -272,51 +264,6 @@ __global__ void k_cell_box(DevMesh m, float4 *box, int *ext) {
     atomicMax(ext + 0, __float_as_int(fx)); atomicMax(ext + 1, __float_as_int(fy)); atomicMax(ext + 2, __float_as_int(fz));
     atomicMin(ext + 3, __float_as_int(fx)); atomicMin(ext + 4, __float_as_int(fy)); atomicMin(ext + 5, __float_as_int(fz));
     if (!is_box) atomicAdd(ext + 6, 1);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K0c  static tile topology (hex meshes): per 256-position block, unique point / face lists and local indices
-// ------------------------------------------------------------------------------------------------
-__global__ void k_seg_offsets(int n_blocks, int per_block, long long total, int *beg, int *end) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
-    beg[b] = b * per_block;
-    end[b] = (int)min((long long)(b + 1) * per_block, total);
-}
-// sorted[beg..end) of block b -> number of distinct values (pass 0) / the distinct values at out[off[b]..] (pass 1)
-__global__ void k_blk_unique(const int *sorted, const int *beg, const int *end, int n_blocks, int *cnt, const int *off, int *out) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
-    int n = 0;
-    for (int i = beg[b]; i < end[b]; ++i) {
-        if (i == beg[b] || sorted[i] != sorted[i - 1]) {
-            if (out) out[off[b] + n] = sorted[i];
-            ++n;
-        }
-    }
-    if (cnt) cnt[b] = n;
-}
-__device__ __forceinline__ int blk_find(const int *lst, int n, int key) {
-    int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-// local index of every cell vertex (per = 8) / face (per = 6) in its block's list
-__global__ void k_blk_local(const int *vals, long long total, int per, const int *off, const int *lst, unsigned short *loc) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int b = (int)((i / per) >> 8);
-    loc[i] = (unsigned short)blk_find(lst + off[b], off[b + 1] - off[b], vals[i]);
-}
-// block-local vertex indices of every listed face
-__global__ void k_blk_face_lv(const int *bf_off, const int *bf, const int *bv_off, const int *bv, const int *fp, int n_blocks, unsigned short *bf_lv) {
-    const int b = blockIdx.x;
-    if (b >= n_blocks) return;
-    const int f0 = bf_off[b], f1 = bf_off[b + 1], v0 = bv_off[b], nv = bv_off[b + 1] - v0;
-    for (int i = f0 + threadIdx.x; i < f1; i += blockDim.x) {
-        const int f = bf[i];
-        for (int j = 0; j < 4; ++j) bf_lv[4 * (long long)i + j] = (unsigned short)blk_find(bv + v0, nv, fp[4 * (long long)f + j]);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -659,9 +606,6 @@ struct sdfibm_context {
     DevBuf<int> cp_off, cp, cf_off, cf, fp_off, fp, nb_off, nb;
     DevBuf<float2> cell_rad;
     DevBuf<float4> cell_box;
-    DevBuf<int> bv_off, bv, bf_off, bf;
-    DevBuf<unsigned short> lv, lf, bf_lv;
-    DevBuf<int2> chunk;   // per block: (first queue index, count) of its items in the exact-evaluation queue
     DevBuf<double> magSf;
     DevBuf<double2> face_rec;
     DevBuf<unsigned> hex_topo, tile_key;
@@ -725,7 +669,6 @@ struct sdfibm_context {
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
-    int heavy_tile = 0;      // 1: k_heavy_tile (static tile topology) instead of k_heavy_hex
     int n_global_hint = 0;   // host-side: some solid may be on the global list (selects the k_classify variant)
     int64_t flagged_last = 0;
 };
@@ -794,7 +737,6 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaMallocHost(&ctx->h_scal, 2 * sizeof(double)));
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
-    if (const char *e = getenv("SDFIBM_HEAVY_TILE")) ctx->heavy_tile = atoi(e);
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -816,7 +758,6 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
-    ctx->bv_off.release(); ctx->bv.release(); ctx->bf_off.release(); ctx->bf.release(); ctx->lv.release(); ctx->lf.release(); ctx->bf_lv.release(); ctx->chunk.release();
     ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release();
@@ -1003,7 +944,6 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     CUDA_TRY(ctx->magSf.ensure(nF));
     d.magSf = ctx->magSf.p;
     d.hex_topo = nullptr;
-    d.has_tile_topo = 0; d.n_blocks = 0;
     d.face_rec = nullptr;
     if (is_hex) {
         CUDA_TRY(ctx->face_rec.ensure(4 * nF));
@@ -1027,50 +967,6 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         CUDA_TRY(ctx->hex_topo.ensure(3 * nC));
         d.hex_topo = ctx->hex_topo.p;
         k_hex_topo<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->hex_topo.p, bad.p);
-        // static tile topology
-        const int nB = (int)((nC + 255) / 256);
-        d.n_blocks = nB;
-        CUDA_TRY(ctx->chunk.ensure(nB));
-        DevBuf<int> seg_beg, seg_end, sorted, cnt;
-        DevBuf<unsigned char> tmp;
-        CUDA_TRY(seg_beg.ensure(nB)); CUDA_TRY(seg_end.ensure(nB)); CUDA_TRY(cnt.ensure((size_t)nB + 1));
-        struct Pass { const int *vals; int per; DevBuf<int> *off, *lst; DevBuf<unsigned short> *loc; };
-        Pass passes[2] = {{ctx->cp.p, 8, &ctx->bv_off, &ctx->bv, &ctx->lv}, {ctx->cf.p, 6, &ctx->bf_off, &ctx->bf, &ctx->lf}};
-        for (auto &ps : passes) {
-            const long long total = (long long)ps.per * (long long)nC;
-            if (total > 0x7fffffffLL) return fail(SDFIBM_ERR_CAPACITY, "sdfibm_set_mesh: mesh too large for 32-bit topology offsets");
-            CUDA_TRY(sorted.ensure((size_t)total));
-            k_seg_offsets<<<grid_for(nB, 256), 256, 0, st>>>(nB, 256 * ps.per, total, seg_beg.p, seg_end.p);
-            int bits = 1;
-            while (bits < 31 && (1LL << bits) <= std::max<long long>(ps.per == 8 ? (long long)nP : (long long)nF, 1)) ++bits;
-            size_t sb = 0;
-            cub::DeviceSegmentedRadixSort::SortKeys(nullptr, sb, ps.vals, sorted.p, (int)total, nB, seg_beg.p, seg_end.p, 0, bits, st);
-            CUDA_TRY(tmp.ensure(sb));
-            cub::DeviceSegmentedRadixSort::SortKeys(tmp.p, sb, ps.vals, sorted.p, (int)total, nB, seg_beg.p, seg_end.p, 0, bits, st);
-            CUDA_TRY(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)nB + 1), st));
-            k_blk_unique<<<grid_for(nB, 128), 128, 0, st>>>(sorted.p, seg_beg.p, seg_end.p, nB, cnt.p, nullptr, nullptr);
-            CUDA_TRY(ps.off->ensure((size_t)nB + 1));
-            size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, ps.off->p, nB + 1, st);
-            CUDA_TRY(tmp.ensure(tb));
-            cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, ps.off->p, nB + 1, st);
-            int n_unique = 0;
-            CUDA_TRY(cudaMemcpyAsync(&n_unique, ps.off->p + nB, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            CUDA_TRY(ps.lst->ensure((size_t)n_unique));
-            k_blk_unique<<<grid_for(nB, 128), 128, 0, st>>>(sorted.p, seg_beg.p, seg_end.p, nB, nullptr, ps.off->p, ps.lst->p);
-            CUDA_TRY(ps.loc->ensure((size_t)total));
-            k_blk_local<<<grid_for(total, 256), 256, 0, st>>>(ps.vals, total, ps.per, ps.off->p, ps.lst->p, ps.loc->p);
-            CUDA_TRY(cudaGetLastError());
-        }
-        CUDA_TRY(ctx->bf_lv.ensure(4 * ctx->bf.n));
-        k_blk_face_lv<<<nB, 128, 0, st>>>(ctx->bf_off.p, ctx->bf.p, ctx->bv_off.p, ctx->bv.p, ctx->fp.p, nB, ctx->bf_lv.p);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(st));
-        seg_beg.release(); seg_end.release(); sorted.release(); cnt.release(); tmp.release();
-        d.bv_off = ctx->bv_off.p; d.bv = ctx->bv.p; d.bf_off = ctx->bf_off.p; d.bf = ctx->bf.p;
-        d.lv = ctx->lv.p; d.lf = ctx->lf.p; d.bf_lv = ctx->bf_lv.p;
-        d.has_tile_topo = 1;
     }
     CUDA_TRY(ctx->nb6.ensure(6 * nC));
     d.nb6 = ctx->nb6.p;
@@ -1303,15 +1199,13 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     I.scal = ctx->scal.p; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
     I.pair_counts = ctx->pair_counts; I.slots = ctx->slots.p; I.K = ctx->K;
     I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_res = ctx->heavy_res.p;
-    I.chunk = (ctx->dm.has_tile_topo && ctx->heavy_tile) ? ctx->chunk.p : nullptr;
     I.heavy_count = &ctx->status->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
     I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status;
     CUDA_TRY(rec(ctx->ev[1]));
     if (ctx->n_global_hint) k_classify<256, 4, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
     else k_classify<256, 6, false><<<grid_for(nC, 256), 256, 0, st>>>(I);
     CUDA_TRY(rec(ctx->ev[2]));
-    if (ctx->dm.is_hex && ctx->dm.has_tile_topo && ctx->heavy_tile) k_heavy_tile<5><<<ctx->n_sm * 5, 128, 0, st>>>(I);
-    else if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+    if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     CUDA_TRY(rec(ctx->ev[3]));
     if (chunked) {
@@ -1424,7 +1318,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
                                       (uint64_t)ctx->solids_in.p, (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
-                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)ctx->heavy_tile,
+                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)0,
                                       (uint64_t)ctx->n_global_hint};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
