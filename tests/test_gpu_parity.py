@@ -117,6 +117,22 @@ def test_parity_scrambled_cell_numbering(name):
     assert np.abs(got["As"][perm] - o0["As"]).max() <= 0.1
 
 
+def test_parity_graded_box_cells():
+    """Axis-aligned cells of varying size (a graded blockMesh): k_classify's nearest / farthest-corner bounds use per-cell boxes."""
+    from sdfibm_b200.mesh import Mesh
+
+    base = cases.case_c4(n=40, n_solids=27, n_side=3)
+    pts = base["mesh"].points.copy()
+    for d, (a, w) in enumerate([(1.5, 0.31), (-1.1, 0.23), (0.9, 0.17)]):
+        pts[:, d] = pts[:, d] + a * np.sin(w * pts[:, d])          # monotone map: cells stay boxes, sizes vary by ~2x
+    mesh = Mesh.hex_block_with_points((40, 40, 40), pts)
+    assert (np.diff(np.sort(np.unique(pts[:, 0]))) > 0.3).all()
+    case = dict(base, mesh=mesh)
+    o, ref, ctx, got = run_both(case)
+    check_parity(case, o, ref, ctx, got)
+    assert sum(ctx.candidate_counts()) > 1000
+
+
 def test_graph_replay_follows_changing_arguments():
     """The device-resident entry replays a captured CUDA graph: dt, rhof, the solid states and the buffers may change between steps."""
     import torch
