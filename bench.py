@@ -237,7 +237,20 @@ def main():
     from sdfibm_b200 import capi
     solids_pinned = capi.pinned_like(np.ascontiguousarray(case["solids"], dtype=capi.SOLID_DTYPE))   # the host side's own solid array
 
+    rep = None
+    if world > 1:
+        from sdfibm_b200 import parallel
+        rep = parallel.ReplicatedSolids(nS, solids_pinned.dtype.itemsize, dev)
+
+    def step_device_gathered():
+        # the replicated solid states reach the GPUs as one 1/N PCIe upload per rank + an NCCL all-gather over NVLink
+        ctx.interact_device_solids(rep.refresh(solids_pinned), nS, dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(),
+                                   dFs.data_ptr(), dTs.data_ptr(), dCt.data_ptr(), dFT.data_ptr(), may_be_global=False)
+        dist.all_reduce(dFT)  # replaces the 2N Foam::reduce calls of solidcloud.cpp:427-431
+
     def step_device():
+        if rep is not None and not os.environ.get("SDFIBM_BENCH_FULL_UPLOAD"):
+            return step_device_gathered()
         ctx.interact_device(solids_pinned, dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(), dFs.data_ptr(),
                             dTs.data_ptr(), dCt.data_ptr(), dFT.data_ptr())
         if world > 1:

@@ -146,6 +146,15 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
                            double *dAs, double *dFs, double *dTs, double *dCt,
                            double *d_force_torque);
 
+/* Same, with the solid records ALREADY on the context's device (enqueued before this call on the context stream, e.g. one
+ * 1/N slice uploaded per rank and all-gathered over NVLink instead of N identical PCIe uploads of the replicated state).
+ * may_be_global = 0 promises that no solid is a plane or a 2-D shape whose axis is not exactly world z (only consulted when the
+ * shape table holds such shapes). */
+int sdfibm_interact_device_solids(sdfibm_context *ctx, const sdfibm_solid_t *d_solids, int n_solids, int may_be_global,
+                                  const double *dU, double dt, double rhof,
+                                  double *dAs, double *dFs, double *dTs, double *dCt,
+                                  double *d_force_torque);
+
 /* ---- SolidCloud::fixInternal (solidcloud.cpp:288-301) -------------------------------
  * Uses Ct of the last interact on this context and the CURRENT solid states. */
 int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *U);

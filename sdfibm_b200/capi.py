@@ -64,6 +64,7 @@ SYMBOLS = {
     "sdfibm_set_shapes": (C.c_int, [_VP, _VP, C.c_int]),
     "sdfibm_interact": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "sdfibm_interact_device": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
+    "sdfibm_interact_device_solids": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "sdfibm_fix_internal": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "sdfibm_fix_internal_device": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "sdfibm_mean_field": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),

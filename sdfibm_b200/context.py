@@ -69,6 +69,14 @@ class Context:
                                                     capi.ptr(dCt), capi.ptr(dFT)))
         self.n_solids = len(solids)
 
+    def interact_device_solids(self, d_solids: int, n_solids: int, dU: int, dt: float, rhof: float, dAs: int, dFs: int, dTs: int,
+                               dCt: int, dFT: int, may_be_global: bool = True):
+        """Device-pointer interact with the solid records already on the device (pointer as int)."""
+        capi.check(self._lib.sdfibm_interact_device_solids(self._h, capi.ptr(d_solids), int(n_solids), int(bool(may_be_global)),
+                                                           capi.ptr(dU), float(dt), float(rhof), capi.ptr(dAs), capi.ptr(dFs),
+                                                           capi.ptr(dTs), capi.ptr(dCt), capi.ptr(dFT)))
+        self.n_solids = int(n_solids)
+
     # ---- SolidCloud::fixInternal ----
     def fix_internal(self, solids: np.ndarray, U: np.ndarray) -> np.ndarray:
         solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)

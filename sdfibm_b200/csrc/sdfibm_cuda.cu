@@ -669,6 +669,7 @@ struct sdfibm_context {
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
+    const sdfibm_solid_t *ext_solids = nullptr;   // device-resident solid records supplied by the caller for the current call
     int n_global_hint = 0;   // host-side: some solid may be on the global list (selects the k_classify variant)
     int64_t flagged_last = 0;
 };
@@ -1070,7 +1071,7 @@ static int stage_solids(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
 
 int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *dU, double dt,
                            double rhof, double *dAs, double *dFs, double *dTs, double *dCt, double *dFT) {
-    if (!ctx || n_solids < 0 || (n_solids > 0 && (!solids || !dFT)) || !dU || !dAs || !dFs || !dTs || !dCt)
+    if (!ctx || n_solids < 0 || (n_solids > 0 && ((!solids && !ctx->ext_solids) || !dFT)) || !dU || !dAs || !dFs || !dTs || !dCt)
         return fail(SDFIBM_ERR_ARG, "sdfibm_interact: null argument");
     if (!ctx->has_mesh) return fail(SDFIBM_ERR_STATE, "sdfibm_interact: set mesh and shapes first");
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1091,7 +1092,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     if (n_solids > (1 << 28) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
     int rc = SDFIBM_OK;
     const auto h0 = std::chrono::steady_clock::now();
-    if (!ctx->pipe.active) rc = stage_solids(ctx, solids, n_solids);   // the host-buffer entry stages them ahead of its U copies
+    if (!ctx->pipe.active && !ctx->ext_solids) rc = stage_solids(ctx, solids, n_solids);   // the host-buffer entry stages them ahead of its U copies
     if (rc) return rc;
     const auto h1 = std::chrono::steady_clock::now();
     ctx->t_host_us[0] = std::chrono::duration<double, std::micro>(h1 - h0).count();
@@ -1165,7 +1166,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         // status word, root / pair counters, bin counters and cursors live in one block: one memset
         CUDA_TRY(cudaMemsetAsync(ctx->zero_block.p, 0, ctx->zero_block.n, st));
         PrepParams P;
-        P.solids = ctx->solids_in.p; P.shapes = ctx->shapes.p; P.n_solids = n_solids; P.n_shapes = (int)ctx->h_shapes.size();
+        P.solids = ctx->ext_solids ? ctx->ext_solids : ctx->solids_in.p; P.shapes = ctx->shapes.p; P.n_solids = n_solids; P.n_shapes = (int)ctx->h_shapes.size();
         P.out = ctx->solids.p; P.grid = g; P.rad3_max = ctx->rad3_max; P.radxy_max = ctx->radxy_max;
         for (int d = 0; d < 3; ++d) { P.mesh_lo[d] = ctx->bmin[d]; P.mesh_hi[d] = ctx->bmax[d]; P.origin[d] = ctx->dm.origin[d]; }
         P.half_ext = ctx->half_ext; P.rad_max = (double)std::max(ctx->rad3_max, ctx->radxy_max);
@@ -1316,7 +1317,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         const auto q0 = std::chrono::steady_clock::now();
         if (use_graph) {
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
-                                      (uint64_t)ctx->solids_in.p, (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
+                                      (uint64_t)(ctx->ext_solids ? ctx->ext_solids : ctx->solids_in.p), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
                                       (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)0,
                                       (uint64_t)ctx->n_global_hint};
@@ -1430,6 +1431,16 @@ int sdfibm_interact(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_sol
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     return SDFIBM_OK;
+}
+
+int sdfibm_interact_device_solids(sdfibm_context *ctx, const sdfibm_solid_t *d_solids, int n_solids, int may_be_global, const double *dU,
+                                  double dt, double rhof, double *dAs, double *dFs, double *dTs, double *dCt, double *dFT) {
+    if (!ctx || (n_solids > 0 && !d_solids)) return fail(SDFIBM_ERR_ARG, "sdfibm_interact_device_solids: null argument");
+    ctx->ext_solids = n_solids > 0 ? d_solids : nullptr;
+    ctx->n_global_hint = (may_be_global && ctx->shapes_may_be_global) ? 1 : 0;
+    const int rc = sdfibm_interact_device(ctx, nullptr, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT);
+    ctx->ext_solids = nullptr;
+    return rc;
 }
 
 int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *dU, const double *dCt) {

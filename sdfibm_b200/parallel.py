@@ -37,3 +37,34 @@ def allreduce_force_torque(ft):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(ft, op=dist.ReduceOp.SUM)
     return ft
+
+
+class ReplicatedSolids:
+    """The replicated solid states on this rank's GPU, refreshed per step by ONE 1/N PCIe upload per rank plus an NCCL
+    all-gather over NVLink, instead of N identical full uploads (every rank's host holds the same array, reference
+    src/solidcloud.cpp: every rank integrates every solid)."""
+
+    def __init__(self, n_solids: int, record_bytes: int, device):
+        import torch
+        import torch.distributed as dist
+
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.n, self.rb = int(n_solids), int(record_bytes)
+        self.per = (self.n + self.world - 1) // self.world            # records per rank slice (last slice padded)
+        self.full = torch.empty(self.per * self.world * self.rb, dtype=torch.uint8, device=device)
+        self.slice = torch.zeros(self.per * self.rb, dtype=torch.uint8, device=device)
+
+    def refresh(self, solids: np.ndarray) -> int:
+        """Upload this rank's slice of `solids` (the same array on every rank) and gather; returns the device pointer."""
+        import torch
+        import torch.distributed as dist
+
+        raw = np.ascontiguousarray(solids).view(np.uint8).reshape(-1)
+        lo, hi = self.rank * self.per * self.rb, min((self.rank + 1) * self.per, self.n) * self.rb
+        dst = self.full if self.world == 1 else self.slice
+        if hi > lo:   # asynchronous when `solids` lives in page-locked memory (capi.pinned_like), staged by torch otherwise
+            dst[: hi - lo].copy_(torch.from_numpy(raw[lo:hi]), non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.full, self.slice)
+        return self.full.data_ptr()

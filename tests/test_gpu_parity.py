@@ -161,6 +161,34 @@ def test_graph_replay_follows_changing_arguments():
         assert np.abs(FT - ref["FT"]).max() <= 1e-10 * max(1.0, np.abs(ref["FT"]).max())
 
 
+def test_device_resident_solids_entry():
+    """sdfibm_interact_device_solids: the solid records are already on the device (multi-GPU hosts gather them over NVLink)."""
+    import torch
+    from sdfibm_b200 import capi, parallel
+
+    case = cases.case_mixed3d()
+    o = Oracle(case["mesh"], case["two_d"])
+    ref = o.interact(case["shapes"], case["solids"], case["U"], case["dt"], case["rhof"])
+    ctx = Context(0, cell_slots=8)
+    ctx.set_mesh(case["mesh"], case["two_d"])
+    ctx.set_shapes(case["shapes"])
+    dev = torch.device("cuda", 0)
+    nC, nS = case["mesh"].n_cells, len(case["solids"])
+    solids = capi.pinned_like(np.ascontiguousarray(case["solids"], dtype=capi.SOLID_DTYPE))
+    rep = parallel.ReplicatedSolids(nS, solids.dtype.itemsize, dev)          # world size 1: a plain upload
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+    dU = torch.from_numpy(case["U"]).to(dev)
+    buf = [torch.empty(nC * k, dtype=torch.float64, device=dev) for k in (1, 3, 1, 1)] + [torch.empty(nS * 6, dtype=torch.float64, device=dev)]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(ext):
+        ctx.interact_device_solids(rep.refresh(solids), nS, dU.data_ptr(), case["dt"], case["rhof"], *[b.data_ptr() for b in buf])
+    assert np.array_equal(buf[3].cpu().numpy(), ref["Ct"])
+    assert np.abs(buf[0].cpu().numpy() - ref["As"]).max() <= 1e-12
+    assert np.abs(buf[4].cpu().numpy().reshape(-1, 6) - ref["FT"]).max() <= 1e-10 * max(1.0, np.abs(ref["FT"]).max())
+    off, cells = ctx.candidate_lists()
+    assert np.array_equal(off, ref["list_off"]) and np.array_equal(cells, ref["list_cells"])
+
+
 def test_unknown_shape_index_is_an_error():
     case = cases.case_c4(n=32, n_solids=4, n_side=2)
     ctx = Context(0)

@@ -41,6 +41,32 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdfibm_b200 import capi
+
+    _, solids = cases.c5_solids(L=float(N), n_solids=23, n_side=N_SIDE)          # 23: the last slice is padded
+    solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+    rep = parallel.ReplicatedSolids(len(solids), solids.dtype.itemsize, torch.device("cpu"))
+    rep.refresh(solids)
+    got = rep.full.numpy()[: solids.nbytes].copy()
+    np.save(os.path.join(out_dir, f"gather{rank}.npy"), got)
+    np.save(os.path.join(out_dir, "want.npy"), solids.view(np.uint8).reshape(-1))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicated_solids_slice_upload_and_all_gather(tmp_path):
+    """Each rank contributes its 1/N slice of the (identical) solid array; after the all-gather every rank holds all of it."""
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = np.load(tmp_path / "want.npy")
+    for rank in range(world):
+        assert np.array_equal(np.load(tmp_path / f"gather{rank}.npy"), want)
+
+
 @pytest.mark.parametrize("world", [2])
 def test_block_split_allreduce_matches_serial(tmp_path, world):
     port = _free_port()
