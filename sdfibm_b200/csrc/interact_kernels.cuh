@@ -131,7 +131,7 @@ struct __align__(16) BinEntry {
     float r_in;        // certified inner radius - fp32 slack, rounded down
     int s;             // solid id
     int kind;
-    int pad;
+    int refine;        // DevSolid::refine of the solid: 0 = no fp32 corner refinement for this shape
 };
 
 struct InteractParams {
@@ -232,7 +232,7 @@ __device__ __forceinline__ void warp_accumulate(bool have, int s, int type, cons
 // tested in fp32 against the fp32 centre copy: 16 bytes of HBM traffic per cell and no fp64 instruction
 // unless a plane / tilted 2-D solid (global list) is present.
 // ------------------------------------------------------------------------------------------------
-template <int NT, int MINB, bool HAS_GLOBAL>
+template <int NT, int MINB, bool HAS_GLOBAL, bool REFINE>
 __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
@@ -271,10 +271,44 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
             const float ro = e0.w, ri = e1.x;
             return (N2 > ro * ro) ? 0 : ((ri > 0.f && F2 < ri * ri) ? 1 : 2);
         };
+        // Second look at an undecided pair for convex analytic shapes: the shape's inside function at the 8 corners of the cell's
+        // box, in fp32 with a certified error bound.  Every corner inside => every vertex inside (the vertices lie in the box and
+        // the shape is convex); every corner outside a BOX cell => every vertex outside (its vertices are the corners).
+        auto refine32 = [&](int s, int qc, int mode) {
+            if (!REFINE || qc != 2 || mode == 0) return qc;
+            const DevSolid &S = P.solids[s];
+            const bool k3 = S.kind == KIND_3D;
+            const float dx = p.x - S.pos32[0], dy = p.y - S.pos32[1], dz = p.z - S.pos32[2];
+            const float hz = k3 ? hb.z : 0.f;
+            float gmax = -3.0e38f, gmin = 3.0e38f;
+            float bc[3], ex[3], ey[3], ez[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                bc[i] = S.M[3 * i] * dx + S.M[3 * i + 1] * dy + S.M[3 * i + 2] * dz + S.com32[i];
+                ex[i] = S.M[3 * i] * hb.x; ey[i] = S.M[3 * i + 1] * hb.y; ez[i] = S.M[3 * i + 2] * hz;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float g = (mode == 1) ? -1.f : -3.0e38f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float b = bc[i] + ((k & 1) ? ex[i] : -ex[i]) + ((k & 2) ? ey[i] : -ey[i]) + ((k & 4) ? ez[i] : -ez[i]);
+                    if (mode == 1) { const float t = b * S.rp[i]; g += t * t; }
+                    else g = fmaxf(g, fabsf(b) - S.rp[i]);
+                }
+                gmax = fmaxf(gmax, g);
+                gmin = fminf(gmin, g);
+            }
+            const float eps = S.eps_ref;
+            if (gmax < -eps) return 1;
+            if (hb.w != 0.f && gmin > ((mode == 1) ? 4.f * eps : eps)) return 0;
+            return 2;
+        };
         if (!HAS_GLOBAL) {
             for (; bi < be; ++bi) {
                 const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
-                emit(__float_as_int(e1.y), test32(e0, e1));
+                const int s = __float_as_int(e1.y);
+                emit(s, refine32(s, test32(e0, e1), __float_as_int(e1.w)));
             }
         } else {
             // planes / tilted 2-D solids are tested by every cell: merge the tile list and the global list in ascending solid id
@@ -291,7 +325,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
                     sb = __float_as_int(e1.y);
                 }
                 const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
-                if (sb <= sg) { ++bi; emit(sb, test32(e0, e1)); }
+                if (sb <= sg) { ++bi; emit(sb, refine32(sb, test32(e0, e1), __float_as_int(e1.w))); }
                 else { ++gi; emit(sg, quick_class(P.solids[sg], cc, rad)); }
             }
         }

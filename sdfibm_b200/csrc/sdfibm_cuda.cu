@@ -70,6 +70,12 @@ struct DevSolid {
     double r_out, r_in;
     float pos32[3]; // centre relative to the mesh origin (keys of the connectivity certificate)
     float ri32;     // KIND_3D: certified inner radius minus the fp32 slack, rounded down (<= 0: none): the same test as k_classify
+    // fp32 refinement of the pre-classification for convex analytic shapes (k_classify): body coordinates b = M (p - pos) + com;
+    // refine 1: inside <=> sum (b_i rp_i)^2 < 1 (ellipsoid, ellipse: rp = 1/radius, 0 for an ignored axis);
+    // refine 2: inside <=> |b_i| < rp_i for every i (box, rectangle: rp = half width, huge for an ignored axis); 0: none
+    float M[9], rp[3], com32[3];
+    float eps_ref;  // certified bound of the fp32 error of the refinement function near the surface
+    int refine;
     int shape;
     int kind;
     int axis_is_z; // body z axis coincides with world z (2-D cases)
@@ -375,6 +381,28 @@ __global__ void k_solid_prepare(PrepParams P) {
     S.ri32 = (sh_kind_of(P.shapes[in.shape]) == KIND_3D) ? __double2float_rd(P.shapes[in.shape].r_in - 4e-6 * (P.half_ext + P.shapes[in.shape].r_out + P.rad_max)) : 0.f;
     S.shape = in.shape;
     const DevShape &sh = P.shapes[in.shape];
+    {
+        const sdfibm_shape_t &sp = sh.s;
+        const double db = 4e-6 * (P.half_ext + sh.r_out + P.rad_max);   // bound of the fp32 error of a body coordinate (5x margin)
+        S.refine = 0;
+        S.eps_ref = 0.f;
+        for (int d = 0; d < 3; ++d) { S.rp[d] = 0.f; S.com32[d] = (float)sp.com[d]; }
+        double rmin = 0.0;
+        if (sp.tag == SDFIBM_SHAPE_ELLIPSOID) { S.refine = 1; for (int d = 0; d < 3; ++d) { S.rp[d] = (float)(1.0 / sp.p[d]); S.com32[d] = 0.f; } rmin = fmin(sp.p[0], fmin(sp.p[1], sp.p[2])); }
+        else if (sp.tag == SDFIBM_SHAPE_ELLIPSE) { S.refine = 1; S.rp[0] = (float)(1.0 / sp.p[0]); S.rp[1] = (float)(1.0 / sp.p[1]); rmin = fmin(sp.p[0], sp.p[1]); }
+        else if (sp.tag == SDFIBM_SHAPE_BOX) { S.refine = 2; for (int d = 0; d < 3; ++d) S.rp[d] = (float)sp.p[d]; }
+        else if (sp.tag == SDFIBM_SHAPE_RECTANGLE) { S.refine = 2; S.rp[0] = (float)sp.p[0]; S.rp[1] = (float)sp.p[1]; S.rp[2] = 3.0e38f; }
+        if (S.refine == 1) S.eps_ref = __double2float_ru(6.0 * db / rmin + 1e-5);
+        if (S.refine == 2) S.eps_ref = __double2float_ru(2.0 * db + 1e-6 * sh.r_out);
+        // rows of M: world2local of the unit vectors (the same quaternion sandwich the exact path uses, rounded to fp32)
+        const DQ qq = {in.quat[0], {in.quat[1], in.quat[2], in.quat[3]}};
+        const D3 zero = {0.0, 0.0, 0.0};
+        const D3 cx = world2local(qq, zero, D3{1.0, 0.0, 0.0}), cy = world2local(qq, zero, D3{0.0, 1.0, 0.0}), cz = world2local(qq, zero, D3{0.0, 0.0, 1.0});
+        S.M[0] = (float)cx.x; S.M[1] = (float)cy.x; S.M[2] = (float)cz.x;
+        S.M[3] = (float)cx.y; S.M[4] = (float)cy.y; S.M[5] = (float)cz.y;
+        S.M[6] = (float)cx.z; S.M[7] = (float)cy.z; S.M[8] = (float)cz.z;
+        if (!(fabs(magSqr3(cx) - 1.0) < 1e-9)) S.refine = 0;   // a non-unit quaternion scales the body frame: leave it to the exact path
+    }
     S.kind = sh.kind;
     S.r_out = sh.r_out;
     S.r_in = sh.r_in;
@@ -463,7 +491,7 @@ __global__ void k_bin_sort_entries(const int *bin_off, int *bin_list, int n_bins
         e.r_in = __double2float_rd(S.r_in - slack);
         e.s = s;
         e.kind = S.kind;
-        e.pad = 0;
+        e.refine = S.refine;
         out[pos] = e;
     }
 }
@@ -669,6 +697,7 @@ struct sdfibm_context {
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
+    bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
     const sdfibm_solid_t *ext_solids = nullptr;   // device-resident solid records supplied by the caller for the current call
     int n_global_hint = 0;   // host-side: some solid may be on the global list (selects the k_classify variant)
     int64_t flagged_last = 0;
@@ -1025,7 +1054,12 @@ int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) 
         shape_bounds(shapes[i], ctx->h_shapes[i]);
     }
     ctx->shapes_may_be_global = false;
-    for (auto &sh : ctx->h_shapes) ctx->shapes_may_be_global |= (sh.kind != KIND_3D);
+    ctx->shapes_refinable = false;
+    for (auto &sh : ctx->h_shapes) {
+        ctx->shapes_may_be_global |= (sh.kind != KIND_3D);
+        ctx->shapes_refinable |= (sh.s.tag == SDFIBM_SHAPE_ELLIPSOID || sh.s.tag == SDFIBM_SHAPE_ELLIPSE || sh.s.tag == SDFIBM_SHAPE_BOX || sh.s.tag == SDFIBM_SHAPE_RECTANGLE);
+    }
+    if (const char *e = getenv("SDFIBM_REFINE")) ctx->shapes_refinable = ctx->shapes_refinable && atoi(e) != 0;
     int rc = upload(ctx->shapes, ctx->h_shapes.data(), (size_t)n, ctx->stream);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1203,8 +1237,11 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     I.heavy_count = &ctx->status->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
     I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status;
     CUDA_TRY(rec(ctx->ev[1]));
-    if (ctx->n_global_hint) k_classify<256, 4, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
-    else k_classify<256, 6, false><<<grid_for(nC, 256), 256, 0, st>>>(I);
+    // variants: with / without the global-list merge (planes, tilted 2-D solids) and the fp32 corner refinement (shape tables
+    // holding ellipsoids, boxes, ellipses, rectangles); the plain one runs at 32 registers / full occupancy
+    if (ctx->n_global_hint) k_classify<256, 4, true, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
+    else if (ctx->shapes_refinable) k_classify<256, 6, false, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
+    else k_classify<256, 6, false, false><<<grid_for(nC, 256), 256, 0, st>>>(I);
     CUDA_TRY(rec(ctx->ev[2]));
     if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
@@ -1319,7 +1356,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
                                       (uint64_t)(ctx->ext_solids ? ctx->ext_solids : ctx->solids_in.p), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
-                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)0,
+                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
                                       (uint64_t)ctx->n_global_hint};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
