@@ -711,6 +711,7 @@ __global__ void k_connectivity(ConnParams P) {
         if ((e & 3) == 0) continue;
         const int s = e >> 3;
         const DevSolid &S = P.solids[s];
+        if (S.conn_proven) continue;   // connected by construction (k_solid_prepare)
         const float *x = S.pos32;
         const float kc = conn_key(p, x);
         // try the face neighbour that lies towards the solid centre first: almost always a member with a smaller key

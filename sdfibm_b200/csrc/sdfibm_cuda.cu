@@ -69,6 +69,7 @@ struct DevSolid {
     double axis[3]; // world direction of the body z axis
     double r_out, r_in;
     float pos32[3]; // centre relative to the mesh origin (keys of the connectivity certificate)
+    int conn_proven; // the vertex-inside cell set of this solid is provably face connected: no certificate needed
     float ri32;     // KIND_3D: certified inner radius minus the fp32 slack, rounded down (<= 0: none): the same test as k_classify
     // fp32 refinement of the pre-classification for convex analytic shapes (k_classify): body coordinates b = M (p - pos) + com;
     // refine 1: inside <=> sum (b_i rp_i)^2 < 1 (ellipsoid, ellipse: rp = 1/radius, 0 for an ignored axis);
@@ -104,6 +105,10 @@ struct DevMesh {
     const float4 *cell_box;   // per position (nullptr when box_uniform)
     float4 box_const;         // the one box of a uniform mesh
     int box_uniform;
+    // the mesh is a complete nx x ny x nz lattice of identical boxes whose lattice neighbours are all face neighbours: for such a
+    // mesh the vertex-inside cell set of a ball that lies inside the mesh is provably face connected (see k_solid_prepare)
+    int lattice_full;
+    double lattice_lo[3], lattice_hi[3];
     float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
     int rad_uniform;
     int is_hex;             // every cell has 8 points / 6 faces and every face 4 points
@@ -360,6 +365,8 @@ struct PrepParams {
     double mesh_lo[3], mesh_hi[3];
     double origin[3];
     double half_ext, rad_max;   // fp32 slack of the conservative tests: 4e-6 (half_ext + r_out + rad_max)
+    int lattice_full;
+    double box_h[3];            // half extents of the lattice cell
     int *bin_count;   // [n_bins+1]
     int *global_list; // [n_solids]
     StepStatus *status;
@@ -411,6 +418,27 @@ __global__ void k_solid_prepare(PrepParams P) {
     S.axis[0] = ax.x; S.axis[1] = ax.y; S.axis[2] = ax.z;
     S.axis_is_z = (fabs(ax.x) <= 1e-12 && fabs(ax.y) <= 1e-12) ? 1 : 0;
     S.global = (S.kind == KIND_PLANE || (S.kind == KIND_2D && !S.axis_is_z)) ? 1 : 0;
+    {
+        // A ball (disc) of radius r > the cell diagonal, lying with one cell of margin inside a complete lattice of identical boxes:
+        // every inside vertex v has, along an axis with |d_i| > h_i, a lattice neighbour strictly closer to the centre (hence
+        // inside); the walk ends at a corner of the cell that holds the centre, all of whose corners are inside (distance <= the
+        // cell diagonal < r).  So the inside vertices are lattice connected, and the member cells — the union of the 2x2x2
+        // stars of the inside vertices — are face connected: the flood fill returns all of them and the
+        // certificate pass can skip this solid.  A vertex within rounding of the surface is extremal: flipping it cannot cut the set.
+        const sdfibm_shape_t &sp = sh.s;
+        const bool ball = sp.tag == SDFIBM_SHAPE_SPHERE, disc = sp.tag == SDFIBM_SHAPE_CIRCLE && S.axis_is_z;
+        bool ok = P.lattice_full && (ball || disc) && sp.com[0] == 0.0 && sp.com[1] == 0.0 && sp.com[2] == 0.0;
+        if (ok) {
+            const double hz = ball ? P.box_h[2] : 0.0;
+            const double diag = 2.0 * sqrt(P.box_h[0] * P.box_h[0] + P.box_h[1] * P.box_h[1] + hz * hz);
+            ok = sp.p[0] > diag * (1.0 + 1e-5);
+            for (int d = 0; d < (ball ? 3 : 2); ++d) {
+                const double marg = sp.p[0] + 2.0 * P.box_h[d] * (1.0 + 1e-5);
+                ok = ok && in.pos[d] - marg > P.mesh_lo[d] && in.pos[d] + marg < P.mesh_hi[d];
+            }
+        }
+        S.conn_proven = ok ? 1 : 0;
+    }
     if (sub == 0) P.out[s] = S;
     if (S.global) {
         if (sub == 0) {
@@ -1020,6 +1048,20 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         for (int k = 0; k < 3; ++k) uniform = uniform && (mx[k] - mn[k] <= 1e-6f * mx[k]);
         d.box_uniform = uniform ? 1 : 0;
         d.box_const = make_float4(mx[0], mx[1], mx[2], 1.f);
+        d.lattice_full = 0;
+        if (uniform) {
+            long long n[3];
+            bool ok = true;
+            for (int k = 0; k < 3; ++k) {
+                const double sz = 2.0 * (double)mx[k] / (1.0 + REL_MARGIN), ext = m->bounds_max[k] - m->bounds_min[k];
+                n[k] = std::llround(ext / sz);
+                ok = ok && n[k] >= 1 && std::fabs((double)n[k] * sz - ext) <= 1e-4 * sz;
+                d.lattice_lo[k] = m->bounds_min[k]; d.lattice_hi[k] = m->bounds_max[k];
+            }
+            ok = ok && n[0] * n[1] * n[2] == (long long)nC &&
+                 (long long)m->n_internal_faces == 3 * n[0] * n[1] * n[2] - (n[0] * n[1] + n[1] * n[2] + n[0] * n[2]);
+            d.lattice_full = ok ? 1 : 0;
+        }
         d.cell_box = ctx->cell_box.p;
         if (uniform) { ctx->cell_box.release(); d.cell_box = nullptr; }
     }
@@ -1204,6 +1246,8 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         P.out = ctx->solids.p; P.grid = g; P.rad3_max = ctx->rad3_max; P.radxy_max = ctx->radxy_max;
         for (int d = 0; d < 3; ++d) { P.mesh_lo[d] = ctx->bmin[d]; P.mesh_hi[d] = ctx->bmax[d]; P.origin[d] = ctx->dm.origin[d]; }
         P.half_ext = ctx->half_ext; P.rad_max = (double)std::max(ctx->rad3_max, ctx->radxy_max);
+        P.lattice_full = ctx->dm.lattice_full;
+        P.box_h[0] = ctx->dm.box_const.x; P.box_h[1] = ctx->dm.box_const.y; P.box_h[2] = ctx->dm.box_const.z;
         P.bin_count = ctx->bin_count; P.global_list = ctx->global_list.p; P.status = ctx->status;
         k_solid_prepare<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(P);
         size_t tmp_bytes = ctx->scan_tmp.n;

@@ -133,6 +133,27 @@ def test_parity_graded_box_cells():
     assert sum(ctx.candidate_counts()) > 1000
 
 
+def test_small_balls_skip_the_connectivity_certificate():
+    """Balls barely larger than a cell diagonal, at random offsets: k_solid_prepare declares their cell sets connected without the
+    certificate pass; the oracle's real flood fill must agree cell for cell (a wrong proof would show up as missing cells)."""
+    from sdfibm_b200.mesh import Mesh
+    from sdfibm_b200.shapes import make_shape, make_solids
+
+    rng = np.random.RandomState(11)
+    n = 28
+    mesh = Mesh.hex_block((n, n, n))
+    shapes = np.array([make_shape("Sphere", radius=1.7321), make_shape("Sphere", radius=1.9), make_shape("Sphere", radius=1.0)])
+    S = make_solids(150)
+    S["pos"] = rng.uniform(4.0, n - 4.0, size=(150, 3))
+    S["pos"][:20] = np.round(S["pos"][:20] * 2) / 2          # centres on vertices / face centres: many exact ties
+    S["shape"] = rng.randint(0, 3, size=150).astype(np.int32)   # radius 1.0 is below the bound: certificate path
+    S["vel"] = 0.1 * rng.standard_normal((150, 3))
+    U = rng.standard_normal((mesh.n_cells, 3))
+    case = dict(name="small_balls", mesh=mesh, two_d=False, shapes=shapes, solids=S, U=U, dt=1e-3, rhof=1.0)
+    o, ref, ctx, got = run_both(case, cell_slots=24)
+    check_parity(case, o, ref, ctx, got)
+
+
 def test_graph_replay_follows_changing_arguments():
     """The device-resident entry replays a captured CUDA graph: dt, rhof, the solid states and the buffers may change between steps."""
     import torch
