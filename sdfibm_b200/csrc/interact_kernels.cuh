@@ -678,6 +678,8 @@ struct ConnParams {
     const int *slots;
     int K;
     int *root_count; // [n_solids] zeroed
+    const unsigned char *tile_proven;   // per tile: every binned candidate is provably connected
+    const StepStatus *status;
 };
 
 // The key of a (cell, solid) pair is the fp32 squared distance between the fp32 copies of the cell centre and the solid
@@ -702,6 +704,8 @@ __device__ __forceinline__ int find_member(const unsigned char *n_item, const in
 __global__ void k_connectivity(ConnParams P) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.m.n_cells) return;
+    // every candidate of the cell's tile is connected by construction and no plane / tilted 2-D solid is about: nothing to certify
+    if (P.tile_proven[__ldg(P.m.tile_key + c)] && P.status->n_global == 0) return;
     const int n = P.n_item[c];
     if (n == 0) return;
     const long long nC = P.m.n_cells;

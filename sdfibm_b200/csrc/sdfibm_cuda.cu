@@ -502,16 +502,19 @@ __device__ __forceinline__ void bin_insertion_sort(int *lst, int beg, int end) {
 // the fp32 slack: coordinates relative to the mesh origin are bounded by M = half extent + r_out + rad, so the fp32 distance is
 // off by < 1e-6 M; slack = 4e-6 M keeps the three-way test conservative (the exact fp64 predicates decide everything it does not).
 __global__ void k_bin_sort_entries(const int *bin_off, int *bin_list, int n_bins, int bin_cap, int *global_list, StepStatus *status,
-                                   const DevSolid *solids, BinEntry *out, double ox, double oy, double oz, double half_ext, double rad_max) {
+                                   const DevSolid *solids, BinEntry *out, double ox, double oy, double oz, double half_ext, double rad_max,
+                                   unsigned char *tile_proven) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == n_bins) { bin_insertion_sort(global_list, 0, status->n_global); status->bin_total = bin_off[n_bins]; return; }
     if (b > n_bins) return;
     const int beg = bin_off[b], end = bin_off[b + 1];
     if (end > bin_cap) return;
     bin_insertion_sort(bin_list, beg, end);
+    int proven = 1;   // every candidate of this tile has a provably connected cell set: its cells need no certificate pass
     for (int pos = beg; pos < end; ++pos) {
         const int s = bin_list[pos];
         const DevSolid &S = solids[s];
+        proven &= S.conn_proven;
         const double slack = 4e-6 * (half_ext + S.r_out + rad_max);
         BinEntry e;
         e.x = (float)(S.pos[0] - ox); e.y = (float)(S.pos[1] - oy); e.z = (float)(S.pos[2] - oz);
@@ -522,6 +525,7 @@ __global__ void k_bin_sort_entries(const int *bin_off, int *bin_list, int n_bins
         e.refine = S.refine;
         out[pos] = e;
     }
+    tile_proven[b] = (unsigned char)proven;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -662,6 +666,7 @@ struct sdfibm_context {
     DevBuf<int> cp_off, cp, cf_off, cf, fp_off, fp, nb_off, nb;
     DevBuf<float2> cell_rad;
     DevBuf<float4> cell_box;
+    DevBuf<unsigned char> tile_proven;   // per tile and step: all its candidate solids are provably connected
     DevBuf<double> magSf;
     DevBuf<double2> face_rec;
     DevBuf<unsigned> hex_topo, tile_key;
@@ -816,7 +821,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
-    ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    ctx->tile_proven.release(); ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release();
     ctx->global_list.release(); ctx->slots.release();
@@ -1260,7 +1265,8 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         k_bin_fill<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(F);
         k_bin_sort_entries<<<grid_for((long long)g.n_bins + 1, 128), 128, 0, st>>>(
             ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap, ctx->global_list.p, ctx->status, ctx->solids.p, ctx->bin_entries.p,
-            ctx->dm.origin[0], ctx->dm.origin[1], ctx->dm.origin[2], ctx->half_ext, (double)std::max(ctx->rad3_max, ctx->radxy_max));
+            ctx->dm.origin[0], ctx->dm.origin[1], ctx->dm.origin[2], ctx->half_ext, (double)std::max(ctx->rad3_max, ctx->radxy_max),
+            ctx->tile_proven.p);
         ctx->launches += 4;
     } else {
         // keep the binning of the first pass; restore the counters the status word carries
@@ -1341,7 +1347,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     ctx->launches += 3;
     if (!replay) {
         ConnParams C;
-        C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count;
+        C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count; C.tile_proven = ctx->tile_proven.p; C.status = ctx->status;
         k_connectivity<<<grid_for(nC, 256), 256, 0, st>>>(C);
         ++ctx->launches;
     }
@@ -1365,6 +1371,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
     if (!replay) {
         CUDA_TRY(ctx->solids.ensure(n_solids));
         CUDA_TRY(ctx->bin_off.ensure((size_t)g.n_bins + 1));
+        CUDA_TRY(ctx->tile_proven.ensure((size_t)g.n_bins + 1));
         CUDA_TRY(ctx->global_list.ensure(n_solids));
         if (ctx->bin_list.n == 0) CUDA_TRY(ctx->bin_list.ensure(std::max<size_t>(1 << 20, 128 * (size_t)n_solids)));
         // one zero-initialised block: [StepStatus | root_count n | pair_counts 3n | bin_count n_bins+1 | bin_cursor n_bins]
@@ -1400,7 +1407,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
                                       (uint64_t)(ctx->ext_solids ? ctx->ext_solids : ctx->solids_in.p), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
-                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p, (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
+                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p ^ ((uint64_t)ctx->tile_proven.p << 1), (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
                                       (uint64_t)ctx->n_global_hint};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
