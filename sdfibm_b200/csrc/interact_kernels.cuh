@@ -159,6 +159,8 @@ struct InteractParams {
     const unsigned char *excluded; // replay pass: [n_cells*K] 1 = pair is outside the seed's component
     StepStatus *status;
     int c_begin, c_end;     // k_final: cell range of this launch
+    int cls_begin, cls_end; // k_classify: position range of this launch (the host-buffer path works slab by slab)
+    const unsigned long long *heavy_start;   // k_heavy: first queue index of this launch (nullptr: 0)
 };
 
 __device__ __forceinline__ float2 cell_radius(const DevMesh &m, int c) { return m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c); }
@@ -236,8 +238,8 @@ template <int NT, int MINB, bool HAS_GLOBAL, bool REFINE>
 __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
-    const int c = blockIdx.x * NT + threadIdx.x;
-    const bool live = c < m.n_cells;
+    const int c = P.cls_begin + blockIdx.x * NT + threadIdx.x;
+    const bool live = c < P.cls_end;
     const long long nC = m.n_cells;
     const int lane = threadIdx.x & 31;
     int n_item = 0, n_heavy = 0;
@@ -450,7 +452,8 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
-    for (long long k0 = (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
+    const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
+    for (long long k0 = q0 + (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
         const long long k = k0 + lane;
         const bool valid = k < n;
         int c = -1, s = -1;
@@ -595,7 +598,8 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
 
 __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
-    for (long long k = (long long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long long)gridDim.x * TPB) {
+    const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
+    for (long long k = q0 + (long long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long long)gridDim.x * TPB) {
         const int2 it = __ldg(P.heavy + k); // (cell, solid)
         int type;
         double v;
@@ -745,6 +749,8 @@ __global__ void k_connectivity(ConnParams P) {
         if (!has_parent) atomicAdd(P.root_count + s, 1);
     }
 }
+
+__global__ void k_snapshot(const unsigned long long *src, unsigned long long *dst) { *dst = *src; }
 
 // per-step totals for the status word + rhof scaling of the per-solid sums (solidcloud.cpp:424-425)
 __global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status, double *ft, const double *scal) {

@@ -675,7 +675,8 @@ struct sdfibm_context {
     DevBuf<double> cc_orig;     // cell centres in the caller's order (fixInternal)
     DevBuf<float4> cc32;
     static const int MAX_CHUNK = 64;
-    int n_chunk = 8;           // host-buffer pipeline: U arrives / the fields leave in this many cell chunks
+    int n_chunk = 8;
+    int n_slab = 4;             // ... and the kernels run slab by slab (n_chunk / n_slab chunks each)           // host-buffer pipeline: U arrives / the fields leave in this many cell chunks
     int chunk_cmin[MAX_CHUNK] = {0}, chunk_cmax[MAX_CHUNK] = {0};   // caller-label range of every position chunk
     double half_ext = 0.0;
     double bmin[3], bmax[3];
@@ -692,6 +693,7 @@ struct sdfibm_context {
     int *root_count = nullptr, *bin_count = nullptr, *bin_cursor = nullptr;
     unsigned *pair_counts = nullptr;
     DevBuf<double> scal;                // {1/dt, rhof} of the step
+    DevBuf<unsigned long long> slab_start;   // queue length before the current slab (host-buffer path)
     double *h_scal = nullptr;           // pinned
     DevBuf<BinEntry> bin_entries;
     DevBuf<double2> heavy_res;
@@ -803,6 +805,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    if (const char *e = getenv("SDFIBM_SLABS")) ctx->n_slab = std::max(atoi(e), 1);
     if (const char *e = getenv("SDFIBM_CHUNKS")) ctx->n_chunk = std::min(std::max(atoi(e), 1), (int)sdfibm_context::MAX_CHUNK);
     for (int i = 0; i < sdfibm_context::MAX_CHUNK; ++i) {
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
@@ -823,7 +826,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
     ctx->tile_proven.release(); ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
-    ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release();
+    ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release(); ctx->slab_start.release();
     ctx->global_list.release(); ctx->slots.release();
     ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
     ctx->ft_internal.release(); ctx->scan_tmp.release();
@@ -1286,20 +1289,35 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_res = ctx->heavy_res.p;
     I.heavy_count = &ctx->status->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
     I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status;
+    auto launch_classify = [&](int p0, int p1) {
+        I.cls_begin = p0; I.cls_end = p1;
+        const int grid = grid_for(p1 - p0, 256);
+        // variants: with / without the global-list merge (planes, tilted 2-D solids) and the fp32 corner refinement (shape tables
+        // holding ellipsoids, boxes, ellipses, rectangles); the plain one runs at 32 registers / full occupancy
+        if (ctx->n_global_hint) k_classify<256, 4, true, true><<<grid, 256, 0, st>>>(I);
+        else if (ctx->shapes_refinable) k_classify<256, 6, false, true><<<grid, 256, 0, st>>>(I);
+        else k_classify<256, 6, false, false><<<grid, 256, 0, st>>>(I);
+    };
+    auto launch_heavy = [&]() {
+        if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+        else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+    };
+    I.heavy_start = nullptr;
     CUDA_TRY(rec(ctx->ev[1]));
-    // variants: with / without the global-list merge (planes, tilted 2-D solids) and the fp32 corner refinement (shape tables
-    // holding ellipsoids, boxes, ellipses, rectangles); the plain one runs at 32 registers / full occupancy
-    if (ctx->n_global_hint) k_classify<256, 4, true, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
-    else if (ctx->shapes_refinable) k_classify<256, 6, false, true><<<grid_for(nC, 256), 256, 0, st>>>(I);
-    else k_classify<256, 6, false, false><<<grid_for(nC, 256), 256, 0, st>>>(I);
-    CUDA_TRY(rec(ctx->ev[2]));
-    if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-    else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-    CUDA_TRY(rec(ctx->ev[3]));
+    if (!chunked) {
+        launch_classify(0, nC);
+        CUDA_TRY(rec(ctx->ev[2]));
+        launch_heavy();
+        CUDA_TRY(rec(ctx->ev[3]));
+    }
     if (chunked) {
-        // chunked: k_final of chunk i waits for its slice of U and releases its slice of the fields to the copy-out stream.
-        // The copy engines are FIFO across streams, so the U chunks are enqueued only now — after every small upload /
-        // memset the preceding kernels depend on — and still start at t ~ 0 because enqueueing is asynchronous.
+        CUDA_TRY(rec(ctx->ev[2]));   // (the per-kernel split is not resolved on this path: classify / heavy / final interleave)
+        CUDA_TRY(rec(ctx->ev[3]));
+        // Host-buffer path: the mesh is worked in N_SLAB position slabs (classify -> heavy -> final, chunk by chunk), so the first
+        // output chunk leaves after a quarter of the kernel time instead of after all of it; k_final of chunk i waits for its
+        // slice of U and releases its slice of the fields to the copy-out stream.  The copy engines are FIFO across streams, so
+        // the U chunks are enqueued only now — after every small upload / memset the preceding kernels depend on — and still
+        // start at t ~ 0 because enqueueing is asynchronous.
         for (int i = 0; i < ctx->n_chunk; ++i) {
             const size_t c0 = (size_t)nC * i / ctx->n_chunk, c1 = (size_t)nC * (i + 1) / ctx->n_chunk;
             if (c1 > c0) CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(dU) + 3 * c0, ctx->pipe.U + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyHostToDevice, ctx->s_in));
@@ -1318,8 +1336,19 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         }
         int last_pos_chunk = 0;
         for (int i = 0; i < NCH; ++i) if (ctx->chunk_cmax[i] >= 0) last_pos_chunk = i;
+        const int per_slab = std::max(1, NCH / ctx->n_slab);
+        CUDA_TRY(ctx->slab_start.ensure(1));
         for (int i = 0; i < NCH; ++i) {
             const long long p0 = (long long)nC * i / NCH, p1 = (long long)nC * (i + 1) / NCH;
+            if (i % per_slab == 0) {   // a new slab: classify its positions, evaluate the queue items they add
+                const int ie = std::min(NCH, i + per_slab);
+                const long long s0 = p0, s1 = (long long)nC * ie / NCH;
+                k_snapshot<<<1, 1, 0, st>>>(&ctx->status->heavy_total, ctx->slab_start.p);
+                I.heavy_start = ctx->slab_start.p;
+                if (s1 > s0) launch_classify((int)s0, (int)s1);
+                launch_heavy();
+                ctx->launches += 3;
+            }
             if (p1 > p0) {
                 I.c_begin = (int)p0; I.c_end = (int)p1;
                 CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
@@ -1338,7 +1367,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
                 CUDA_TRY(cudaMemcpyAsync(ctx->pipe.Ct + c0, dCt + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_out));
             }
         }
-        ctx->launches += ctx->n_chunk - 1;
+        ctx->launches += ctx->n_chunk - 3;
     } else {
         I.c_begin = 0; I.c_end = nC;
         k_final<4><<<grid_for(nC, 256), 256, 0, st>>>(I);
