@@ -331,6 +331,7 @@ struct Enumerator {
     int *ct;                   // cell type array in use
     int stamp_base;            // non-faithful: types are stored as stamp_base + type
     Predicate pred;
+    bool own_count = false;    // NOT the reference: compare with the neighbour's own vertex count (see next())
     std::queue<int> queue;
     std::set<size_t> sets[5];  // IntersectionSet (cellenumerator.h:25)
 
@@ -345,8 +346,8 @@ struct Enumerator {
     }
     int nverts(int c) const { return m.cell_points_off[c + 1] - m.cell_points_off[c]; }
 
-    Enumerator(const sdfibm_mesh_t &mesh, const Predicate &p, int seed, int *shared_ct, int stamp)
-        : m(mesh), pred(p) {                                                   // cellenumerator.cpp:47-78
+    Enumerator(const sdfibm_mesh_t &mesh, const Predicate &p, int seed, int *shared_ct, int stamp, bool own = false)
+        : m(mesh), pred(p), own_count(own) {                                                   // cellenumerator.cpp:47-78
         if (shared_ct) { ct = shared_ct; stamp_base = stamp; }
         else { own_ct.assign(m.n_cells, 0); ct = own_ct.data(); stamp_base = 0; }
         if (seed < 0 || count_vertex_inside(seed) == 0) {
@@ -377,7 +378,9 @@ struct Enumerator {
             }
             queue.push(inb);
             int t;
-            if (n_in == nverts(icur)) t = SDFIBM_CELL_ALL_INSIDE;             // (sic) vertex count of the CURRENT cell, :25
+            // (sic) the reference compares with the vertex count of the CURRENT cell, :25 — on meshes that mix cell types the
+            // outcome then depends on which neighbour discovered the cell first; own_count is the order-free variant
+            if (n_in == nverts(own_count ? inb : icur)) t = SDFIBM_CELL_ALL_INSIDE;
             else if (pred(ld3(m.cell_centres, inb))) t = SDFIBM_CELL_CENTER_INSIDE;
             else t = SDFIBM_CELL_CENTER_OUTSIDE;
             set(inb, t);
@@ -517,6 +520,8 @@ int oracle_interact(void *h, const sdfibm_shape_t *shapes, const sdfibm_solid_t 
     std::fill(Fs, Fs + 3 * nc, 0.0);
     std::fill(Ts, Ts + nc, 0.0);
     if (force_torque) std::fill(force_torque, force_torque + 6 * (int64_t)n_solids, 0.0);
+    const bool own_count = (faithful & 2) != 0;   // bit 1: order-free ALL_INSIDE test (not the reference's)
+    faithful &= 1;
     if (!faithful && (int64_t)o.stamp.size() != nc) { o.stamp.assign(nc, 0); o.stampv = 0; }
 
     GeoTools geo(m);
@@ -537,7 +542,7 @@ int oracle_interact(void *h, const sdfibm_shape_t *shapes, const sdfibm_solid_t 
             stamp = o.stampv;
             o.stampv += 8;
         }
-        Enumerator ce(m, pred, seed, shared, stamp);
+        Enumerator ce(m, pred, seed, shared, stamp, own_count);
         ce.intersect();
         const std::set<size_t> &sAI = ce.sets[SDFIBM_CELL_ALL_INSIDE];
         const std::set<size_t> &sCI = ce.sets[SDFIBM_CELL_CENTER_INSIDE];

@@ -61,7 +61,7 @@ class Oracle:
         p = np.ascontiguousarray(p, dtype=np.float64)
         return load().oracle_nearest_cell(self._h, _p(p))
 
-    def interact(self, shapes, solids, U, dt, rhof, faithful=False, want_lists=True, solid_range=None):
+    def interact(self, shapes, solids, U, dt, rhof, faithful=False, want_lists=True, solid_range=None, own_vertex_count=False):
         nC = self.mesh.n_cells
         n = len(solids)
         shapes = np.ascontiguousarray(shapes)
@@ -80,7 +80,7 @@ class Oracle:
             if want_lists:
                 cells = np.empty(cap, dtype=np.int32)
             rc = load().oracle_interact(self._h, _p(shapes), _p(solids), n, b, e, _p(U), float(dt), float(rhof),
-                                        int(faithful), _p(out["As"]), _p(out["Fs"]), _p(out["Ts"]), _p(out["Ct"]),
+                                        int(faithful) | (2 if own_vertex_count else 0), _p(out["As"]), _p(out["Fs"]), _p(out["Ts"]), _p(out["Ct"]),
                                         _p(out["FT"]), _p(off), _p(cells), cap, _p(timing))
             if rc == 4 and want_lists:
                 cap = int(off[-1]) + 16

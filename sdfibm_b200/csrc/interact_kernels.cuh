@@ -154,13 +154,14 @@ struct InteractParams {
     int2 *heavy;            // queue of (cell, solid) needing exact evaluation
     double2 *heavy_res;     // [queue] per item: (solid volume inside the cell, bits: CELL_TYPE | solid << 2)
     unsigned long long *heavy_count;
+    unsigned long long *heavy_gen;   // mixed meshes: count of the items queued from the back (non-hexahedral cells)
     long long heavy_cap;
     int K;
     const unsigned char *excluded; // replay pass: [n_cells*K] 1 = pair is outside the seed's component
     StepStatus *status;
     int c_begin, c_end;     // k_final: cell range of this launch
     int cls_begin, cls_end; // k_classify: position range of this launch (the host-buffer path works slab by slab)
-    const unsigned long long *heavy_start;   // k_heavy: first queue index of this launch (nullptr: 0)
+    const unsigned long long *heavy_start;   // k_heavy: [0] first front-queue index, [1] first back-queue item of this launch (nullptr: 0)
 };
 
 __device__ __forceinline__ float2 cell_radius(const DevMesh &m, int c) { return m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c); }
@@ -334,15 +335,19 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
         P.n_item[c] = (unsigned char)n_item;
     }
     // ---- block-aggregated append of the queued pairs to the global queue: ONE atomic on the queue counter per CTA
-    //      (a per-warp atomic serialises ~3e5 same-address operations at C4 and bounds the whole kernel) ----
-    int incl = n_heavy;
+    //      (a per-warp atomic serialises ~3e5 same-address operations at C4 and bounds the whole kernel).  Mixed meshes keep two
+    //      queues in the one buffer — hexahedral cells from the front, the others from the back — so the warp-cooperative hex
+    //      kernel sees only hexahedra; both counts ride one scan, 16 bits each ----
+    const bool gen_cell = m.mixed && n_heavy > 0 && __ldg(m.hex_topo + 3 * (long long)c) == HEX_NONE;
+    const int mine = gen_cell ? (n_heavy << 16) : n_heavy;
+    int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(FULL, incl, o);
         if (lane >= o) incl += v;
     }
     __shared__ int s_wtot[NT / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_base, s_base_gen;
     const int warp = threadIdx.x >> 5;
     if (lane == 31) s_wtot[warp] = incl;
     __syncthreads();
@@ -350,19 +355,24 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
         int tot = 0;
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w) { const int t = s_wtot[w]; s_wtot[w] = tot; tot += t; }
-        s_base = tot ? atomicAdd(P.heavy_count, (unsigned long long)tot) : 0ull;
+        const int tot_hex = tot & 0xffff, tot_gen = tot >> 16;
+        s_base = tot_hex ? atomicAdd(P.heavy_count, (unsigned long long)tot_hex) : 0ull;
+        s_base_gen = tot_gen ? atomicAdd(P.heavy_gen, (unsigned long long)tot_gen) : 0ull;
     }
     __syncthreads();
     if (n_heavy == 0) return;
-    long long pos = (long long)s_base + s_wtot[warp] + incl - n_heavy;
+    const int excl = s_wtot[warp] + incl - mine;
+    // front queue: ascending indices; back queue: item i lives at heavy_cap - 1 - i
+    long long pos = gen_cell ? P.heavy_cap - 1 - ((long long)s_base_gen + (excl >> 16)) : (long long)s_base + (excl & 0xffff);
+    const long long step = gen_cell ? -1 : 1;
     for (int j = 0; j < n_item; ++j) {
         const int e = P.slots[(long long)j * nC + c];
         if (e & SLOT_HEAVY) {
-            if (pos < P.heavy_cap) {
+            if (pos >= 0 && pos < P.heavy_cap) {
                 P.heavy[pos] = make_int2(c, e >> 3);
                 P.slots[(long long)j * nC + c] = ((int)pos << 3) | SLOT_HEAVY;     // the slot now points at its queue item
             }
-            ++pos;
+            pos += step;
         }
     }
 }
@@ -451,7 +461,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
+    const long long n = min((long long)*P.heavy_count, P.heavy_cap - (m.mixed ? (long long)*P.heavy_gen : 0));
     const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
     for (long long k0 = q0 + (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
         const long long k = k0 + lane;
@@ -467,10 +477,16 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             const int2 it = __ldg(P.heavy + k);
             c = it.x;
             s = it.y;
-            const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
-            const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
-            vid[0] = va.x; vid[1] = va.y; vid[2] = va.z; vid[3] = va.w;
-            vid[4] = vb.x; vid[5] = vb.y; vid[6] = vb.z; vid[7] = vb.w;
+            if (m.is_hex) {
+                const int4 *cp4 = reinterpret_cast<const int4 *>(m.cp + 8 * (long long)c);
+                const int4 va = __ldg(cp4), vb = __ldg(cp4 + 1);
+                vid[0] = va.x; vid[1] = va.y; vid[2] = va.z; vid[3] = va.w;
+                vid[4] = vb.x; vid[5] = vb.y; vid[6] = vb.z; vid[7] = vb.w;
+            } else {   // a hexahedron of a mixed mesh: CSR offsets, no alignment guarantee
+                const int *cpp = m.cp + __ldg(m.cp_off + c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vid[j] = __ldg(cpp + j);
+            }
             const DevSolid &S = P.solids[s];
             q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
             t = {S.pos[0], S.pos[1], S.pos[2]};
@@ -479,8 +495,13 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             tw0 = __ldg(m.hex_topo + 3 * (long long)c);
             tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1);
             tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
-            const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
-            f01 = __ldg(cf2); f23 = __ldg(cf2 + 1); f45 = __ldg(cf2 + 2);
+            if (m.is_hex) {
+                const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
+                f01 = __ldg(cf2); f23 = __ldg(cf2 + 1); f45 = __ldg(cf2 + 2);
+            } else {
+                const int *cfp = m.cf + __ldg(m.cf_off + c);
+                f01 = make_int2(__ldg(cfp), __ldg(cfp + 1)); f23 = make_int2(__ldg(cfp + 2), __ldg(cfp + 3)); f45 = make_int2(__ldg(cfp + 4), __ldg(cfp + 5));
+            }
         }
         // does my low quad coincide with the previous lane's high quad (same solid)?
         const int ls = __shfl_up_sync(FULL, s, 1);
@@ -597,9 +618,14 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
 }
 
 __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
-    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
-    const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
-    for (long long k = q0 + (long long)blockIdx.x * TPB + threadIdx.x; k < n; k += (long long)gridDim.x * TPB) {
+    // all-polyhedral meshes: the front queue; mixed meshes: the back queue (item i at heavy_cap - 1 - i)
+    const bool back = P.m.mixed != 0;
+    const long long n = back ? (long long)*P.heavy_gen : min((long long)*P.heavy_count, P.heavy_cap);
+    const long long q0 = P.heavy_start ? (long long)P.heavy_start[back ? 1 : 0] : 0;
+    const long long front = back ? (long long)*P.heavy_count : 0;   // the back queue may not run into the front one
+    for (long long i = q0 + (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+        const long long k = back ? P.heavy_cap - 1 - i : i;
+        if (k < front) continue;
         const int2 it = __ldg(P.heavy + k); // (cell, solid)
         int type;
         double v;
@@ -750,7 +776,7 @@ __global__ void k_connectivity(ConnParams P) {
     }
 }
 
-__global__ void k_snapshot(const unsigned long long *src, unsigned long long *dst) { *dst = *src; }
+__global__ void k_snapshot(const unsigned long long *a, const unsigned long long *b, unsigned long long *dst) { dst[0] = *a; dst[1] = *b; }
 
 // per-step totals for the status word + rhof scaling of the per-solid sums (solidcloud.cpp:424-425)
 __global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status, double *ft, const double *scal) {

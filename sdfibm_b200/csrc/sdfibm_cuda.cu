@@ -52,6 +52,7 @@ static int fail(int code, const std::string &msg) {
 #define MAX_CELL_VERTS 32
 #define MAX_FACE_VERTS 16
 #define REL_MARGIN 1e-6
+#define HEX_NONE 0xffffffffu
 
 struct DevShape {
     sdfibm_shape_t s;
@@ -112,6 +113,8 @@ struct DevMesh {
     float2 rad_const;       // upper bound of cell_rad over the mesh (used for every cell when the mesh is near uniform)
     int rad_uniform;
     int is_hex;             // every cell has 8 points / 6 faces and every face 4 points
+    int mixed;              // some cells are such hexahedra and some are not: hex_topo[3c] == HEX_NONE marks the others, which go
+                            // through the general-polyhedron kernel from a queue of their own
     int two_d;
 };
 
@@ -132,7 +135,8 @@ struct StepStatus {
     int bad_shape;                // a solid refers to a shape index outside the table
     int bin_total;
     int n_global;
-    unsigned long long heavy_total; // (cell, solid) items that needed exact evaluation
+    unsigned long long heavy_total; // (cell, solid) items that needed exact evaluation (mixed meshes: those of hexahedral cells)
+    unsigned long long heavy_gen;   // mixed meshes: items of non-hexahedral cells, queued from the back of the same buffer
 };
 
 __device__ __forceinline__ D3 ld3(const double *__restrict__ p, long long i) {
@@ -168,13 +172,20 @@ __global__ void k_face_mag(const double *Cf, const double *Sf, int n_faces, doub
 __global__ void k_hex_topo(DevMesh m, unsigned *topo, int *bad) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m.n_cells) return;
+    const int pb = m.cp_off[c], fb = m.cf_off[c];
+    bool hex = (m.cp_off[c + 1] - pb == 8) && (m.cf_off[c + 1] - fb == 6);
+    for (int k = 0; k < 6 && hex; ++k) { const int f = m.cf[fb + k]; hex = m.fp_off[f + 1] - m.fp_off[f] == 4; }
+    if (!hex) {   // not a hexahedron with quadrilateral faces: general path
+        topo[3 * (long long)c] = HEX_NONE; topo[3 * (long long)c + 1] = 0u; topo[3 * (long long)c + 2] = 0u;
+        return;
+    }
     int vid[8];
-    for (int k = 0; k < 8; ++k) vid[k] = m.cp[8 * (long long)c + k];
+    for (int k = 0; k < 8; ++k) vid[k] = m.cp[pb + k];
     unsigned w[3] = {0u, 0u, 0u};
     for (int k = 0; k < 6; ++k) {
-        const int f = m.cf[6 * (long long)c + k];
+        const int f = m.cf[fb + k];
         for (int j = 0; j < 4; ++j) {
-            const int g = m.fp[4 * (long long)f + j];
+            const int g = m.fp[m.fp_off[f] + j];
             int l = -1;
             for (int t = 0; t < 8; ++t) if (vid[t] == g) l = t;
             if (l < 0) { atomicExch(bad, 1); l = 0; }
@@ -1007,11 +1018,24 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     for (size_t f = 0; f < nF && is_hex; ++f) is_hex = (m->face_points_off[f + 1] - m->face_points_off[f] == 4);
     is_hex = is_hex && m->cell_points_off[0] == 0 && m->cell_faces_off[0] == 0 && m->face_points_off[0] == 0;
     d.is_hex = is_hex ? 1 : 0;
+    size_t n_hex_cells = 0;
+    if (!is_hex && m->cell_points_off[0] == 0 && m->cell_faces_off[0] == 0 && m->face_points_off[0] == 0) {
+        for (size_t c = 0; c < nC; ++c) {
+            bool h = (m->cell_points_off[c + 1] - m->cell_points_off[c] == 8) && (m->cell_faces_off[c + 1] - m->cell_faces_off[c] == 6);
+            for (int k = m->cell_faces_off[c]; k < m->cell_faces_off[c + 1] && h; ++k) {
+                const int f = m->cell_faces[k];
+                h = m->face_points_off[f + 1] - m->face_points_off[f] == 4;
+            }
+            n_hex_cells += h;
+        }
+    }
+    d.mixed = (!is_hex && n_hex_cells > 0) ? 1 : 0;
+    const bool hex_path = is_hex || d.mixed;
     CUDA_TRY(ctx->magSf.ensure(nF));
     d.magSf = ctx->magSf.p;
     d.hex_topo = nullptr;
     d.face_rec = nullptr;
-    if (is_hex) {
+    if (hex_path) {
         CUDA_TRY(ctx->face_rec.ensure(4 * nF));
         d.face_rec = ctx->face_rec.p;
     }
@@ -1029,7 +1053,7 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     k_cell_radius<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->cell_rad.p, bad.p, rmax.p);
-    if (is_hex) {
+    if (hex_path) {
         CUDA_TRY(ctx->hex_topo.ensure(3 * nC));
         d.hex_topo = ctx->hex_topo.p;
         k_hex_topo<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->hex_topo.p, bad.p);
@@ -1287,7 +1311,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     I.scal = ctx->scal.p; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
     I.pair_counts = ctx->pair_counts; I.slots = ctx->slots.p; I.K = ctx->K;
     I.n_item = ctx->n_item.p; I.heavy = ctx->heavy.p; I.heavy_res = ctx->heavy_res.p;
-    I.heavy_count = &ctx->status->heavy_total; I.heavy_cap = (long long)ctx->heavy.n;
+    I.heavy_count = &ctx->status->heavy_total; I.heavy_gen = &ctx->status->heavy_gen; I.heavy_cap = (long long)ctx->heavy.n;
     I.excluded = replay ? ctx->excluded.p : nullptr; I.status = ctx->status;
     auto launch_classify = [&](int p0, int p1) {
         I.cls_begin = p0; I.cls_end = p1;
@@ -1296,11 +1320,11 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         // holding ellipsoids, boxes, ellipses, rectangles); the plain one runs at 32 registers / full occupancy
         if (ctx->n_global_hint) k_classify<256, 4, true, true><<<grid, 256, 0, st>>>(I);
         else if (ctx->shapes_refinable) k_classify<256, 6, false, true><<<grid, 256, 0, st>>>(I);
-        else k_classify<256, 6, false, false><<<grid, 256, 0, st>>>(I);
+        else k_classify<256, 8, false, false><<<grid, 256, 0, st>>>(I);
     };
     auto launch_heavy = [&]() {
-        if (ctx->dm.is_hex) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-        else k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+        if (ctx->dm.is_hex || ctx->dm.mixed) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+        if (!ctx->dm.is_hex) k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     };
     I.heavy_start = nullptr;
     CUDA_TRY(rec(ctx->ev[1]));
@@ -1337,13 +1361,13 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         int last_pos_chunk = 0;
         for (int i = 0; i < NCH; ++i) if (ctx->chunk_cmax[i] >= 0) last_pos_chunk = i;
         const int per_slab = std::max(1, NCH / ctx->n_slab);
-        CUDA_TRY(ctx->slab_start.ensure(1));
+        CUDA_TRY(ctx->slab_start.ensure(2));
         for (int i = 0; i < NCH; ++i) {
             const long long p0 = (long long)nC * i / NCH, p1 = (long long)nC * (i + 1) / NCH;
             if (i % per_slab == 0) {   // a new slab: classify its positions, evaluate the queue items they add
                 const int ie = std::min(NCH, i + per_slab);
                 const long long s0 = p0, s1 = (long long)nC * ie / NCH;
-                k_snapshot<<<1, 1, 0, st>>>(&ctx->status->heavy_total, ctx->slab_start.p);
+                k_snapshot<<<1, 1, 0, st>>>(&ctx->status->heavy_total, &ctx->status->heavy_gen, ctx->slab_start.p);
                 I.heavy_start = ctx->slab_start.p;
                 if (s1 > s0) launch_classify((int)s0, (int)s1);
                 launch_heavy();
@@ -1479,8 +1503,9 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             ctx->last = *ctx->h_status;
             if (replay) ctx->last.n_flagged = (int)ctx->flagged_last;
         }
-        if (ctx->last.heavy_total > (unsigned long long)ctx->heavy.n && attempt == 0) {
-            const size_t cap = (size_t)(ctx->last.heavy_total + ctx->last.heavy_total / 4 + 1024);
+        if (ctx->last.heavy_total + ctx->last.heavy_gen > (unsigned long long)ctx->heavy.n && attempt == 0) {
+            const unsigned long long need = ctx->last.heavy_total + ctx->last.heavy_gen;
+            const size_t cap = (size_t)(need + need / 4 + 1024);
             CUDA_TRY(ctx->heavy.ensure(cap));
             CUDA_TRY(ctx->heavy_res.ensure(cap));
             continue;
@@ -1496,7 +1521,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
     if (ctx->last.bad_shape) return fail(SDFIBM_ERR_ARG, "solid refers to an unknown shape index");
     if (ctx->last.slot_overflow)
         return fail(SDFIBM_ERR_CAPACITY, "more solids touch one cell than the slot count; raise it with sdfibm_set_cell_slots");
-    if (ctx->last.heavy_total > (unsigned long long)ctx->heavy.n) return fail(SDFIBM_ERR_CAPACITY, "exact-evaluation queue overflow");
+    if (ctx->last.heavy_total + ctx->last.heavy_gen > (unsigned long long)ctx->heavy.n) return fail(SDFIBM_ERR_CAPACITY, "exact-evaluation queue overflow");
     return SDFIBM_OK;
 }
 
@@ -1660,7 +1685,7 @@ int sdfibm_last_stats(sdfibm_context *ctx, int64_t stats[4]) {
     stats[0] = ctx->flagged_last;
     stats[1] = ctx->launches;
     stats[2] = ctx->last.bin_total;
-    stats[3] = (int64_t)ctx->last.heavy_total;
+    stats[3] = (int64_t)(ctx->last.heavy_total + ctx->last.heavy_gen);
     return SDFIBM_OK;
 }
 

@@ -154,6 +154,46 @@ def test_small_balls_skip_the_connectivity_certificate():
     check_parity(case, o, ref, ctx, got)
 
 
+def test_parity_mixed_hex_prism_polyhedron_mesh():
+    """A mesh that is mostly hexahedra with some prisms and 7-faced polyhedra (what snappyHexMesh-like tools produce): the
+    hexahedra keep the warp-cooperative kernel, the rest are queued separately for the general-polyhedron kernel."""
+    from mixed_mesh import mixed_hex_prism_mesh
+    from sdfibm_b200.shapes import make_shape, make_solids, quat_from_euler_xyz_deg
+
+    mesh = mixed_hex_prism_mesh(14)
+    assert sorted(set(np.diff(mesh.cf_off))) == [5, 6, 7]
+    rng = np.random.RandomState(3)
+    shapes = np.array([make_shape("Sphere", radius=3.2), make_shape("Ellipsoid", radiusa=3.5, radiusb=2.5, radiusc=2.0),
+                       make_shape("Box", radiusa=2.2, radiusb=1.6, radiusc=2.7)])
+    S = make_solids(6)
+    S["pos"] = [(5.3, 6.1, 5.7), (9.9, 4.2, 8.7), (4.1, 10.2, 9.6), (10.4, 10.1, 4.3), (7.0, 7.0, 7.0), (12.5, 2.0, 12.0)]
+    S["shape"] = [0, 1, 2, 0, 1, 2]
+    for i, e in enumerate([(0, 0, 0), (20, 40, -15), (35, -10, 60), (0, 0, 0), (-70, 15, 5), (10, 20, 30)]):
+        S[i]["quat"] = quat_from_euler_xyz_deg(e)
+    S["vel"] = 0.1 * rng.standard_normal((6, 3))
+    S["omega"] = 0.05 * rng.standard_normal((6, 3))
+    U = rng.standard_normal((mesh.n_cells, 3))
+    case = dict(name="mixed_cells", mesh=mesh, two_d=False, shapes=shapes, solids=S, U=U, dt=1e-3, rhof=1.3)
+    # On a mesh that mixes cell types the reference's ALL_INSIDE test compares a cell's inside-vertex count with the vertex count
+    # of whichever neighbour discovered it first (SURVEY Q3, cellenumerator.cpp:25), i.e. with the flood fill's visiting order.
+    # The library uses the cell's own count; the oracle's order-free variant is the specification here, and the faithful run
+    # differs from it only in the TYPE of a few cells next to a cell of another kind.
+    o = Oracle(mesh, False)
+    ref = o.interact(shapes, S, U, 1e-3, 1.3, own_vertex_count=True)
+    ctx = Context(0, cell_slots=8)
+    ctx.set_mesh(mesh, False)
+    ctx.set_shapes(shapes)
+    got = ctx.interact(S, U, 1e-3, 1.3)
+    check_parity(case, o, ref, ctx, got)
+    assert sum(ctx.candidate_counts()) > 500
+    faithful = o.interact(shapes, S, U, 1e-3, 1.3)
+    assert faithful["list_off"][-1] == ref["list_off"][-1]                      # same member cells ...
+    differ = np.nonzero(faithful["Ct"] != ref["Ct"])[0]
+    assert 0 < len(differ) < 0.05 * ref["list_off"][-1]                         # ... a few of them typed differently
+    ok = np.isfinite(faithful["As"])       # (the faithful run divides by |grad f| = 0 at an ellipsoid centre that sits on a vertex)
+    assert np.abs(faithful["As"][ok] - ref["As"][ok]).max() < 1e-12             # a fully inside cell has fraction 1 either way
+
+
 def test_graph_replay_follows_changing_arguments():
     """The device-resident entry replays a captured CUDA graph: dt, rhof, the solid states and the buffers may change between steps."""
     import torch
