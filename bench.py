@@ -162,9 +162,15 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     wl, case, desc = build_case(args, 0, 1 if args.workload != "c5" and world == 1 else world)
-    n_sample = args.cpu_solids
+    # bounded sample: the per-solid cost of the faithful algorithm is O(nCells) (a fresh CELL_TYPE array per solid, a whole-mesh
+    # scan for every solid that has no vertex-inside cell on this rank), i.e. seconds per solid on a C5 block: probe two solids,
+    # then take as many per step as fit ~100 s for the whole run (at most --cpu-solids)
+    n_total = args.warmup + args.steps
+    _, probe_ms = cpu_baseline_sample(case, 2, faithful=True)
+    per_solid_s = max(probe_ms * 1e-3 / 2.0, 1e-4)
+    n_sample = int(max(1, min(args.cpu_solids, (100.0 / max(n_total, 1)) / per_solid_s)))
     vals = []
-    for i in range(args.warmup + args.steps):
+    for i in range(n_total):
         pairs, ms = cpu_baseline_sample(case, n_sample, faithful=True)
         if i >= args.warmup:
             vals.append((pairs, ms))
