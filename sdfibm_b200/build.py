@@ -90,7 +90,23 @@ def build_oracle(force: bool = False) -> str:
     return lib
 
 
+def build_reference_oracle(force: bool = False, reference: str = "/root/reference"):
+    """oracle/_ref/libsdfibm_ref.so: the reference's own hot-path translation units, compiled unmodified from where they lie
+    (only where the reference tree exists — this container, not the GPU box).  Test infrastructure; see oracle/Makefile."""
+    if not os.path.isdir(os.path.join(reference, "src")):
+        return None
+    d = os.path.join(ROOT, "oracle")
+    lib = os.path.join(d, "_ref", "libsdfibm_ref.so")
+    deps = [os.path.join(d, "refshim", f) for f in ("ref_bridge.cpp", "foam_shim.h")] + [os.path.join(HERE, "host", "foamlite.h")]
+    if force or not os.path.exists(lib) or max(os.path.getmtime(x) for x in deps) > os.path.getmtime(lib):
+        r = subprocess.run(["make", "-C", d, "-B", "ref", f"REFERENCE={reference}"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("reference oracle build failed:\n" + r.stdout + r.stderr)
+    return lib
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host(force="--force" in sys.argv))
     print(build_oracle(force="--force" in sys.argv))
+    print(build_reference_oracle(force="--force" in sys.argv))

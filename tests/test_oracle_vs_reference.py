@@ -1,0 +1,87 @@
+"""The oracle (oracle.cpp) against the reference's OWN code: src/cellenumerator.cpp, src/geometrictools.cpp, src/solid.h and the
+nine shape classes of src/libshape, compiled unmodified from /root/reference into oracle/_ref (oracle/Makefile, target `ref`).
+Candidate lists must be identical, the clipped volume-fraction field equal to the last bit or two.  Runs only where the
+reference tree exists (this container); the GPU box has neither the tree nor this library."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_py  # noqa: E402
+from oracle.oracle_py import Oracle  # noqa: E402
+from sdfibm_b200.mesh import Mesh  # noqa: E402
+from sdfibm_b200.shapes import make_shape, make_solids, quat_from_euler_xyz_deg  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from sdfibm_b200 import build
+
+    assert build.build_reference_oracle() is not None and ref_py.available()
+
+
+def _compare(mesh, two_d, specs, pos, euler):
+    """specs: list of (type name, kwargs) — one shape per solid."""
+    n = len(specs)
+    shapes = np.array([make_shape(t, **k) for t, k in specs])
+    S = make_solids(n)
+    S["pos"] = pos
+    S["shape"] = np.arange(n)
+    for i, e in enumerate(euler):
+        S[i]["quat"] = quat_from_euler_xyz_deg(e)
+    o = Oracle(mesh, two_d)
+    mine = o.interact(shapes, S, np.zeros((mesh.n_cells, 3)), 1.0, 1.0, faithful=True)
+    seeds = [o.nearest_cell(S[i]["pos"]) for i in range(n)]
+    texts = [ref_py.shape_dict_text(t, **k) for t, k in specs]
+    off, cells, As = ref_py.ref_interact(mesh, texts, S["pos"], S["quat"], seeds, two_d)
+    assert np.array_equal(off, mine["list_off"]), (off, mine["list_off"])
+    assert np.array_equal(cells, mine["list_cells"])
+    assert off[-1] > 50 * n
+    err = np.abs(As - mine["As"])
+    assert np.nanmax(err) <= 4e-16, np.nanmax(err)
+    assert np.array_equal(np.isnan(As), np.isnan(mine["As"]))
+    return off
+
+
+def test_three_d_shapes_on_a_hex_block():
+    mesh = Mesh.hex_block((24, 22, 20), x0=(-1.0, 0.5, 0.0), dx=(0.5, 0.55, 0.6))
+    specs = [("Sphere", dict(radius=2.3)), ("Ellipsoid", dict(radiusa=3.1, radiusb=2.0, radiusc=1.4)),
+             ("Box", dict(radiusa=1.9, radiusb=1.2, radiusc=2.4)), ("Sphere", dict(radius=1.7, com=(0.3, -0.2, 0.1))),
+             ("Ellipsoid", dict(radiusa=1.5, radiusb=2.5, radiusc=2.0))]
+    pos = [(4.1, 6.3, 5.2), (7.7, 5.9, 6.4), (3.9, 9.1, 7.7), (8.2, 9.0, 3.1), (5.0, 3.5, 9.0)]
+    euler = [(0, 0, 0), (25, -40, 70), (10, 20, 30), (0, 0, 0), (-60, 15, 5)]
+    _compare(mesh, False, specs, pos, euler)
+
+
+def test_two_d_shapes_on_a_one_cell_thick_block():
+    mesh = Mesh.hex_block((90, 80, 1), x0=(-2.0, -2.0, -0.5), dx=(0.05, 0.05, 1.0))
+    specs = [("Circle", dict(radius=0.6)), ("Ellipse", dict(radiusa=0.7, radiusb=0.35)), ("Rectangle", dict(radiusa=0.5, radiusb=0.3)),
+             ("Circle_Tail", dict(radius=0.3, ratio=2.0, thickness=0.08)), ("Circle_TwoTail", dict(radius=0.3, ratio=2.0, thickness=0.1)),
+             ("Circle", dict(radius=0.4, com=(0.1, 0.05, 0.0))), ("Plane", dict())]
+    pos = [(-1.0, -1.0, 0), (0.6, -0.9, 0), (1.6, 0.9, 0), (-0.9, 0.8, 0), (0.4, 0.9, 0), (1.7, -1.2, 0), (0.0, -1.8, 0)]
+    euler = [(0, 0, 0), (0, 0, -45), (0, 0, 30), (0, 0, 110), (0, 0, -20), (0, 0, 15), (0, 0, 4)]
+    _compare(mesh, True, specs, pos, euler)
+
+
+def test_vertices_exactly_on_the_surface():
+    """A unit circle centred on a vertex of a dx = 0.1 mesh (the flow_past_cylinder situation): strict `<` for the lists, the
+    filtered distance for the fractions."""
+    mesh = Mesh.hex_block((40, 40, 1), x0=(-2.0, -2.0, -0.5), dx=(0.1, 0.1, 1.0))
+    _compare(mesh, True, [("Circle", dict(radius=1.0))], [(0.0, 0.0, 0.0)], [(0, 0, 0)])
+
+
+def test_mixed_cell_types_reproduce_the_visiting_order_quirk():
+    """on a mesh of hexahedra, prisms and 7-faced polyhedra the ALL_INSIDE test depends on the flood fill's order; the
+    oracle's faithful mode must follow the reference cell for cell."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mixed_mesh import mixed_hex_prism_mesh
+
+    mesh = mixed_hex_prism_mesh(12)
+    specs = [("Sphere", dict(radius=3.2)), ("Box", dict(radiusa=2.2, radiusb=1.6, radiusc=2.7))]
+    _compare(mesh, False, specs, [(5.3, 6.1, 5.7), (7.9, 4.2, 7.7)], [(0, 0, 0), (35, -10, 60)])
