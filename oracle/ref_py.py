@@ -56,3 +56,24 @@ def ref_interact(mesh, dict_texts, pos, quat, seeds, two_d: bool):
     if rc < 0:
         raise RuntimeError(f"ref_interact failed ({rc})")
     return off, cells[:rc].copy(), As
+
+
+def ref_collide(bounds_min, bounds_max, delta, dict_texts, pos, quat):
+    """Pairs in UGrid::generateCollisionPairs order and the accumulated contact forces [n, 6] of the reference's libcollision."""
+    lib = C.CDLL(LIB_PATH)
+    lib.ref_collide.restype = C.c_int64
+    n = len(dict_texts)
+    texts = (C.c_char_p * n)(*[t.encode() for t in dict_texts])
+    bmin = np.ascontiguousarray(bounds_min, dtype=np.float64)
+    bmax = np.ascontiguousarray(bounds_max, dtype=np.float64)
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    quat = np.ascontiguousarray(quat, dtype=np.float64)
+    cap = 64 * n + 64
+    pairs = np.zeros((cap, 2), dtype=np.int32)
+    ft = np.zeros((n, 6))
+    rc = lib.ref_collide(C.c_void_p(bmin.ctypes.data), C.c_void_p(bmax.ctypes.data), C.c_double(delta), n, texts,
+                         C.c_void_p(pos.ctypes.data), C.c_void_p(quat.ctypes.data), C.c_void_p(pairs.ctypes.data), C.c_int64(cap),
+                         C.c_void_p(ft.ctypes.data))
+    if rc < 0:
+        raise RuntimeError(f"ref_collide failed ({rc})")
+    return pairs[:rc].copy(), ft

@@ -31,6 +31,9 @@ using cell = labelList;
 using faceList = List<face>;
 using cellList = List<cell>;
 
+// VectorSpaceI.H: vs / mag(vs), zero for a vanishing vector
+inline vector normalised(const vector &v) { const scalar m = mag(v); return m > 1e-300 ? v / m : vector::zero; }
+
 class fvMesh {
 public:
     labelListList c2c, c2p;

@@ -15,6 +15,8 @@
 #include "cellenumerator.h"
 #include "geometrictools.h"
 #include "solid.h"
+#include "libcollision/ugrid.h"
+#include "libcollision/collision.h"
 
 using namespace sdfibm;
 
@@ -85,6 +87,58 @@ int64_t ref_interact(const ref_mesh *m, int n_solids, const char *const *dict_te
         return n_out;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "ref_interact: %s\n", e.what());
+        return -2;
+    }
+}
+
+// The collision step: UGrid broad phase and the narrow-phase table are the reference's (src/libcollision/*, compiled unmodified);
+// the loop and the force law around them are the caller's lines, restated from src/solidcloud.cpp:477-519.
+// pairs[2*cap] receives the (first, second) pairs in generateCollisionPairs order; ft[6n] is accumulated into.
+int64_t ref_collide(const double *bmin, const double *bmax, double delta, int n_solids, const char *const *dict_text, const double *pos,
+                    const double *quat, int32_t *pairs, int64_t cap, double *ft) {
+    try {
+        static bool table = false;
+        if (!table) { InitCollisionFuncTable(); table = true; }                      // solidcloud.cpp:226
+        std::vector<std::unique_ptr<IShape>> shapes;
+        std::vector<Solid> solids;
+        for (int s = 0; s < n_solids; ++s) {
+            char tmpl[] = "/tmp/sdfibm_ref_dict_XXXXXX";
+            const int fd = mkstemp(tmpl);
+            if (fd < 0) return -3;
+            close(fd);
+            { std::ofstream os(tmpl); os << dict_text[s] << "\n"; }
+            Foam::dictionary d = Foam::dictionary::fromFile(tmpl);
+            std::remove(tmpl);
+            shapes.push_back(ShapeFactory::create(std::string(d.lookup("type")), d));
+            solids.emplace_back(s, Foam::vector(pos[3 * s], pos[3 * s + 1], pos[3 * s + 2]),
+                                Foam::quaternion(quat[4 * s], Foam::vector(quat[4 * s + 1], quat[4 * s + 2], quat[4 * s + 3])));
+            solids.back().setShape(shapes.back().get());
+        }
+        BBox bbox(bmin, bmax);
+        UGrid grid(bbox, delta);                                                     // solidcloud.cpp:245
+        grid.clear();
+        for (const Solid &s : solids) {                                             // :479-484
+            vector c = s.getCenter();
+            grid.insert(c.x(), c.y(), c.z(), s.getID());
+        }
+        std::vector<CollisionPair> cps;
+        grid.generateCollisionPairs(cps);
+        int64_t n = 0;
+        for (CollisionPair &cp : cps) {
+            if (n >= cap) return -1;
+            pairs[2 * n] = cp.first; pairs[2 * n + 1] = cp.second; ++n;
+            Solid &s1 = solids[cp.first], &s2 = solids[cp.second];                   // solidSolidCollision, :492-519
+            collisionFunc cfunc = getCollisionFunc(s1.getShape()->getTypeName(), s2.getShape()->getTypeName());
+            if (!cfunc) continue;
+            vector cP, cN;
+            const scalar cd = cfunc(s1, s2, cP, cN);
+            if (cd < 0) continue;
+            const vector force = 1e4 * cd * cN;
+            for (int k = 0; k < 3; ++k) { ft[6 * cp.first + k] -= force[k]; ft[6 * cp.second + k] += force[k]; }
+        }
+        return n;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "ref_collide: %s\n", e.what());
         return -2;
     }
 }

@@ -85,3 +85,30 @@ def test_mixed_cell_types_reproduce_the_visiting_order_quirk():
     mesh = mixed_hex_prism_mesh(12)
     specs = [("Sphere", dict(radius=3.2)), ("Box", dict(radiusa=2.2, radiusb=1.6, radiusc=2.7))]
     _compare(mesh, False, specs, [(5.3, 6.1, 5.7), (7.9, 4.2, 7.7)], [(0, 0, 0), (35, -10, 60)])
+
+
+def test_collision_step_against_libcollision():
+    """UGrid::generateCollisionPairs order and the sphere / circle / plane contact functions of src/libcollision (compiled
+    unmodified), with the caller's force law (solidcloud.cpp:509-518): the oracle's pairs and forces must be the same."""
+    rng = np.random.RandomState(5)
+    mesh = Mesh.hex_block((16, 16, 16), x0=(0.0, 0.0, 0.0), dx=(0.5, 0.5, 0.5))
+    n = 60
+    specs = [("Sphere", dict(radius=0.45))] * (n - 3) + [("Plane", dict()), ("Plane", dict()), ("Ellipsoid", dict(radiusa=0.5, radiusb=0.4, radiusc=0.3))]
+    shapes = np.array([make_shape(t, **k) for t, k in specs])
+    S = make_solids(n)
+    S["pos"] = rng.uniform(0.6, 7.4, size=(n, 3))
+    S["pos"][n - 3] = (4.0, 0.3, 4.0)        # a floor: half space y < 0 of the body frame
+    S["pos"][n - 2] = (7.7, 4.0, 4.0)        # a wall, rotated
+    S["shape"] = np.arange(n)
+    S[n - 2]["quat"] = quat_from_euler_xyz_deg((0, 0, 90))
+    texts = [ref_py.shape_dict_text(t, **k) for t, k in specs]
+    o = Oracle(mesh, False)
+    for delta in (0.9, 1.3, -2.0):           # -2 is what HEAD passes: a grid without cells, no pairs (SURVEY Q7)
+        pairs, ft = o.collide(shapes, S, delta)
+        rp, rft = ref_py.ref_collide(mesh.bounds_min, mesh.bounds_max, delta, texts, S["pos"], S["quat"])
+        assert np.array_equal(pairs, rp), delta
+        assert np.array_equal(ft, rft), delta
+        if delta > 0:
+            assert len(pairs) > 20 and np.abs(ft).max() > 0
+        else:
+            assert len(pairs) == 0
