@@ -77,3 +77,66 @@ def ref_collide(bounds_min, bounds_max, delta, dict_texts, pos, quat):
     if rc < 0:
         raise RuntimeError(f"ref_collide failed ({rc})")
     return pairs[:rc].copy(), ft
+
+
+def dict_text_from_record(rec) -> str:
+    """solidDict entries that make the reference's constructor rebuild a lowered sdfibm_shape_t record (sdfibm_b200/shapes.py)."""
+    names = {0: "Plane", 1: "Circle", 2: "Sphere", 3: "Ellipse", 4: "Ellipsoid", 5: "Rectangle", 6: "Box", 7: "Circle_Tail", 8: "Circle_TwoTail"}
+    t = names[int(rec["tag"])]
+    p = [float(x) for x in rec["p"]]
+    k = {}
+    if t in ("Circle", "Sphere"):
+        k = dict(radius=p[0])
+    elif t in ("Ellipse", "Rectangle"):
+        k = dict(radiusa=p[0], radiusb=p[1])
+    elif t in ("Ellipsoid", "Box"):
+        k = dict(radiusa=p[0], radiusb=p[1], radiusc=p[2])
+    elif t in ("Circle_Tail", "Circle_TwoTail"):
+        k = dict(radius=p[0], ratio=2.0 * p[2] / p[0] - 1.0, thickness=p[3] if t == "Circle_Tail" else 2.0 * p[3])
+    return shape_dict_text(t, com=tuple(float(x) for x in rec["com"]), **k)
+
+
+class Reference:
+    """interact() of the reference's own compiled classes on one mesh (the loop of src/solidcloud.cpp:361-464 around them)."""
+
+    def __init__(self, mesh):
+        self._lib = C.CDLL(LIB_PATH)
+        self._lib.ref_create.restype = C.c_void_p
+        self._lib.ref_interact_full.restype = C.c_int64
+        self._keep = [np.ascontiguousarray(a) for a in (mesh.points, mesh.cc, mesh.V, mesh.Cf, mesh.Sf, mesh.cp_off, mesh.cp, mesh.cf_off,
+                                                        mesh.cf, mesh.fp_off, mesh.fp, mesh.nb_off, mesh.nb)]
+        m = _RefMesh(mesh.n_cells, mesh.n_points, mesh.n_faces, *[a.ctypes.data for a in self._keep])
+        self.mesh = mesh
+        self._h = C.c_void_p(self._lib.ref_create(C.byref(m)))
+        if not self._h:
+            raise RuntimeError("ref_create failed")
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.ref_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def interact(self, dict_texts, solids, seeds, U, dt, rhof, two_d, solid_range=None, want_lists=True):
+        n, nC = len(solids), self.mesh.n_cells
+        b, e = (0, n) if solid_range is None else solid_range
+        texts = (C.c_char_p * n)(*[t.encode() for t in dict_texts])
+        arr = lambda a, dt_: np.ascontiguousarray(a, dtype=dt_)
+        pos, quat, vel, om = arr(solids["pos"], np.float64), arr(solids["quat"], np.float64), arr(solids["vel"], np.float64), arr(solids["omega"], np.float64)
+        seeds, U = arr(seeds, np.int32), arr(U, np.float64)
+        cap = 8 * nC + 64
+        out = dict(As=np.zeros(nC), Fs=np.zeros((nC, 3)), Ts=np.zeros(nC), Ct=np.zeros(nC), FT=np.zeros((n, 6)),
+                   list_off=np.zeros(3 * n + 1, dtype=np.int32), list_cells=np.zeros(cap if want_lists else 1, dtype=np.int32))
+        ms = C.c_double(0.0)
+        P = lambda a: C.c_void_p(a.ctypes.data)
+        rc = self._lib.ref_interact_full(self._h, n, texts, P(pos), P(quat), P(vel), P(om), P(seeds), P(U), C.c_double(dt), C.c_double(rhof),
+                                         int(bool(two_d)), int(b), int(e), P(out["list_off"]), P(out["list_cells"]) if want_lists else None,
+                                         C.c_int64(cap), P(out["As"]), P(out["Fs"]), P(out["Ts"]), P(out["Ct"]), P(out["FT"]), C.byref(ms))
+        if rc < 0:
+            raise RuntimeError(f"ref_interact_full failed ({rc})")
+        out["list_cells"] = out["list_cells"][:rc].copy() if want_lists else None
+        out["pairs"] = int(rc)
+        out["timing_ms"] = float(ms.value)
+        return out

@@ -15,21 +15,33 @@
 
 namespace Foam {
 
+// Non-owning views over the caller's flat arrays (the arrays of sdfibm_mesh_t): what the reference indexes as List<T> /
+// labelListList.  Nothing is copied, so binding a 16.7 M-cell mesh costs nothing and the timed region contains only the
+// reference's own work.
 template <class T>
-class List : public std::vector<T> {
-public:
-    using std::vector<T>::vector;
-    label size() const { return (label)std::vector<T>::size(); }
+struct UList {
+    const T *p = nullptr;
+    label n = 0;
+    label size() const { return n; }
+    const T &operator[](label i) const { return p[i]; }
 };
-using labelList = List<label>;
-using labelListList = List<labelList>;
-using pointField = List<vector>;
-using vectorField = List<vector>;
-using scalarField = List<scalar>;
+using labelList = UList<label>;
 using face = labelList;
 using cell = labelList;
-using faceList = List<face>;
-using cellList = List<cell>;
+struct CsrList {   // labelListList / cellList / faceList: row i is val[off[i] .. off[i+1])
+    const label *off = nullptr;
+    const label *val = nullptr;
+    label n = 0;
+    label size() const { return n; }
+    labelList operator[](label i) const { return labelList{val + off[i], off[i + 1] - off[i]}; }
+};
+using labelListList = CsrList;
+using cellList = CsrList;
+using faceList = CsrList;
+static_assert(sizeof(vector) == 3 * sizeof(scalar), "vector must be three packed scalars");
+using pointField = UList<vector>;
+using vectorField = UList<vector>;
+using scalarField = UList<scalar>;
 
 // VectorSpaceI.H: vs / mag(vs), zero for a vanishing vector
 inline vector normalised(const vector &v) { const scalar m = mag(v); return m > 1e-300 ? v / m : vector::zero; }

@@ -1,6 +1,7 @@
 // ref_bridge.cpp — TEST INFRASTRUCTURE.  A C entry over the reference's OWN CellEnumerator / GeometricTools / shape classes
 // (compiled unmodified from /root/reference/src through oracle/refshim): for each solid, the three candidate lists and the
 // clipped volume fraction field, following solidFluidInteract (reference src/solidcloud.cpp:361-410) up to alpha.
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,11 @@
 using namespace sdfibm;
 
 extern "C" {
+struct ref_mesh;
+}
+static void fill_mesh(Foam::fvMesh &mesh, const ref_mesh *m);
+
+extern "C" {
 
 struct ref_mesh {
     int32_t n_cells, n_points, n_faces;
@@ -35,22 +41,7 @@ int64_t ref_interact(const ref_mesh *m, int n_solids, const char *const *dict_te
                      const int32_t *seed, int two_d, int32_t *list_off, int32_t *list_cells, int64_t cap, double *As) {
     try {
         Foam::fvMesh mesh;
-        mesh.pts.resize(m->n_points);
-        for (int i = 0; i < m->n_points; ++i) mesh.pts[i] = Foam::vector(m->points[3 * i], m->points[3 * i + 1], m->points[3 * i + 2]);
-        mesh.cc.resize(m->n_cells); mesh.cv.resize(m->n_cells); mesh.c2c.resize(m->n_cells); mesh.c2p.resize(m->n_cells); mesh.cls.resize(m->n_cells);
-        for (int c = 0; c < m->n_cells; ++c) {
-            mesh.cc[c] = Foam::vector(m->cc[3 * c], m->cc[3 * c + 1], m->cc[3 * c + 2]);
-            mesh.cv[c] = m->V[c];
-            for (int k = m->nb_off[c]; k < m->nb_off[c + 1]; ++k) mesh.c2c[c].push_back(m->nb[k]);
-            for (int k = m->cp_off[c]; k < m->cp_off[c + 1]; ++k) mesh.c2p[c].push_back(m->cp[k]);
-            for (int k = m->cf_off[c]; k < m->cf_off[c + 1]; ++k) mesh.cls[c].push_back(m->cf[k]);
-        }
-        mesh.fc.resize(m->n_faces); mesh.fa.resize(m->n_faces); mesh.fcs.resize(m->n_faces);
-        for (int f = 0; f < m->n_faces; ++f) {
-            mesh.fc[f] = Foam::vector(m->Cf[3 * f], m->Cf[3 * f + 1], m->Cf[3 * f + 2]);
-            mesh.fa[f] = Foam::vector(m->Sf[3 * f], m->Sf[3 * f + 1], m->Sf[3 * f + 2]);
-            for (int k = m->fp_off[f]; k < m->fp_off[f + 1]; ++k) mesh.fcs[f].push_back(m->fp[k]);
-        }
+        fill_mesh(mesh, m);
         GeometricTools geo(mesh);
         for (int c = 0; c < m->n_cells; ++c) As[c] = 0.0;
         int64_t n_out = 0;
@@ -139,6 +130,138 @@ int64_t ref_collide(const double *bmin, const double *bmax, double delta, int n_
         return n;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "ref_collide: %s\n", e.what());
+        return -2;
+    }
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the whole of interact() (reference src/solidcloud.cpp:361-464) around the reference's compiled classes, on a persistent mesh
+// ---------------------------------------------------------------------------------------------------------------------
+struct RefCtx {
+    Foam::fvMesh mesh;
+    std::unique_ptr<GeometricTools> geo;
+};
+
+static void fill_mesh(Foam::fvMesh &mesh, const ref_mesh *m) {   // views over the caller's arrays (which must outlive the mesh)
+    const Foam::vector *P = reinterpret_cast<const Foam::vector *>(m->points);
+    mesh.pts = {P, m->n_points};
+    mesh.cc = {reinterpret_cast<const Foam::vector *>(m->cc), m->n_cells};
+    mesh.cv = {m->V, m->n_cells};
+    mesh.fc = {reinterpret_cast<const Foam::vector *>(m->Cf), m->n_faces};
+    mesh.fa = {reinterpret_cast<const Foam::vector *>(m->Sf), m->n_faces};
+    mesh.c2c = {m->nb_off, m->nb, m->n_cells};
+    mesh.c2p = {m->cp_off, m->cp, m->n_cells};
+    mesh.cls = {m->cf_off, m->cf, m->n_cells};
+    mesh.fcs = {m->fp_off, m->fp, m->n_faces};
+}
+
+static Foam::dictionary dict_of(const char *text) {
+    char tmpl[] = "/tmp/sdfibm_ref_dict_XXXXXX";
+    const int fd = mkstemp(tmpl);
+    if (fd < 0) throw std::runtime_error("mkstemp failed");
+    close(fd);
+    { std::ofstream os(tmpl); os << text << "\n"; }
+    Foam::dictionary d = Foam::dictionary::fromFile(tmpl);
+    std::remove(tmpl);
+    return d;
+}
+
+extern "C" {
+
+void *ref_create(const ref_mesh *m) {
+    try {
+        RefCtx *c = new RefCtx();
+        fill_mesh(c->mesh, m);
+        c->geo.reset(new GeometricTools(c->mesh));
+        return c;
+    } catch (...) { return nullptr; }
+}
+void ref_destroy(void *h) { delete static_cast<RefCtx *>(h); }
+
+// Solids [solid_begin, solid_end) of n_solids; fields are reset for all cells, results accumulated for those solids only.
+// timed_ms = the reference's own timed region (the solid loop + checkAlpha, :442-451).  Returns the number of list entries.
+int64_t ref_interact_full(void *h, int n_solids, const char *const *dict_text, const double *pos, const double *quat, const double *vel,
+                          const double *omega, const int32_t *seed, const double *U, double dt, double rhof, int two_d,
+                          int solid_begin, int solid_end, int32_t *list_off, int32_t *list_cells, int64_t cap, double *As, double *Fs,
+                          double *Ts, double *Ct, double *ft, double *timed_ms) {
+    try {
+        RefCtx &R = *static_cast<RefCtx *>(h);
+        const Foam::fvMesh &mesh = R.mesh;
+        GeometricTools &geo = *R.geo;
+        const int nC = mesh.nCells();
+        std::vector<std::unique_ptr<IShape>> shapes(n_solids);
+        std::vector<Solid> solids;
+        for (int s = 0; s < n_solids; ++s) {
+            if (s >= solid_begin && s < solid_end) {
+                Foam::dictionary d = dict_of(dict_text[s]);
+                shapes[s] = ShapeFactory::create(std::string(d.lookup("type")), d);
+            }
+            solids.emplace_back(s, Foam::vector(pos[3 * s], pos[3 * s + 1], pos[3 * s + 2]),
+                                Foam::quaternion(quat[4 * s], Foam::vector(quat[4 * s + 1], quat[4 * s + 2], quat[4 * s + 3])));
+            solids.back().setShape(shapes[s].get());
+            solids.back().setVelocity(Foam::vector(vel[3 * s], vel[3 * s + 1], vel[3 * s + 2]));
+            solids.back().setOmega(Foam::vector(omega[3 * s], omega[3 * s + 1], omega[3 * s + 2]));
+        }
+        // interact(): reset the four fields (:438-441)
+        std::vector<Foam::vector> mFs(nC, Foam::vector::zero);
+        for (int c = 0; c < nC; ++c) { As[c] = 0.0; Ts[c] = 0.0; Ct[c] = 0.0; }
+        for (int i = 0; i < 6 * n_solids; ++i) ft[i] = 0.0;
+        if (list_off) { list_off[0] = 0; for (int i = 0; i < 3 * n_solids; ++i) list_off[i + 1] = 0; }
+        int64_t n_out = 0;
+        const auto t1 = std::chrono::high_resolution_clock::now();
+        for (int sid = solid_begin; sid < solid_end; ++sid) {
+            // solidFluidInteract (:361-433); the seed is meshSearch::findNearestCell's (OpenFOAM's), supplied by the caller
+            Solid &solid = solids[sid];
+            CellEnumerator ce(mesh, [&](const vector &v) { return solid.phi01(v); }, seed[sid]);
+            auto is = ce.intersect();
+            using CT = CellEnumerator::CELL_TYPE;
+            size_t num_inside_cells = is[CT::ALL_INSIDE].size();
+            std::vector<size_t> cellids;
+            cellids.insert(cellids.end(), is[CT::ALL_INSIDE].begin(), is[CT::ALL_INSIDE].end());
+            cellids.insert(cellids.end(), is[CT::CENTER_INSIDE].begin(), is[CT::CENTER_INSIDE].end());
+            cellids.insert(cellids.end(), is[CT::CENTER_OUTSIDE].begin(), is[CT::CENTER_OUTSIDE].end());
+            const int insideType = solid.getID() + 4;
+            for (auto cellid : is[CT::ALL_INSIDE]) Ct[cellid] = insideType;
+            for (auto cellid : is[CT::CENTER_INSIDE]) Ct[cellid] = CT::CENTER_INSIDE;
+            for (auto cellid : is[CT::CENTER_OUTSIDE]) Ct[cellid] = CT::CENTER_OUTSIDE;
+            geo.clearCache();
+            const scalar dtINV = 1.0 / dt;
+            vector force = vector::zero, torque = vector::zero;
+            for (size_t counter = 0; counter < cellids.size(); ++counter) {
+                const auto cellid = cellids[counter];
+                scalar alpha = num_inside_cells > 0 ? 1.0 : 0.0;
+                if (counter >= num_inside_cells) alpha = geo.calcCellVolume(cellid, solid, two_d != 0) / mesh.cv[cellid];
+                As[cellid] += alpha;
+                const vector uf(U[3 * cellid], U[3 * cellid + 1], U[3 * cellid + 2]);
+                const vector us = solid.evalPointVelocity(mesh.cc[cellid]);
+                const vector f_ = alpha * (uf - us);
+                const vector t_ = (mesh.cc[cellid] - solid.getCenter()) ^ f_;
+                force += f_ * mesh.cv[cellid] * dtINV;
+                torque += t_ * mesh.cv[cellid] * dtINV;
+                mFs[cellid] += f_ * dtINV;
+                Ts[cellid] += alpha;
+            }
+            force *= rhof;
+            torque *= rhof;
+            for (int k = 0; k < 3; ++k) { ft[6 * sid + k] = force[k]; ft[6 * sid + 3 + k] = torque[k]; }
+            if (list_cells) {
+                const CT types[3] = {CT::ALL_INSIDE, CT::CENTER_INSIDE, CT::CENTER_OUTSIDE};
+                for (int t = 0; t < 3; ++t) {
+                    for (size_t icell : is[types[t]]) { if (n_out >= cap) return -1; list_cells[n_out++] = (int32_t)icell; }
+                    list_off[3 * sid + t + 1] = (int32_t)n_out;
+                }
+            } else n_out += (int64_t)cellids.size();
+        }
+        for (int c = 0; c < nC; ++c) As[c] = std::min(As[c], 1.0);   // checkAlpha (:564-570)
+        const auto t2 = std::chrono::high_resolution_clock::now();
+        if (timed_ms) *timed_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+        if (list_off) for (int i = 3 * solid_end; i < 3 * n_solids; ++i) list_off[i + 1] = (int32_t)n_out;
+        for (int c = 0; c < nC; ++c) { Fs[3 * c] = mFs[c].x(); Fs[3 * c + 1] = mFs[c].y(); Fs[3 * c + 2] = mFs[c].z(); }
+        return n_out;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "ref_interact_full: %s\n", e.what());
         return -2;
     }
 }

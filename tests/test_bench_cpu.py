@@ -24,7 +24,10 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(line)
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
     assert d["unit"] == "cell-solid updates/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_py
+
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_py.available() else "port")   # oracle/_ref: the reference's own compiled code
+    assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("C4")
 

@@ -46,6 +46,22 @@ def _compare(mesh, two_d, specs, pos, euler):
     err = np.abs(As - mine["As"])
     assert np.nanmax(err) <= 4e-16, np.nanmax(err)
     assert np.array_equal(np.isnan(As), np.isnan(mine["As"]))
+    # the whole of interact(): Fs, Ts, Ct and the per-solid force / torque, with moving solids and a non-trivial U
+    rng = np.random.RandomState(1)
+    S["vel"] = 0.3 * rng.standard_normal((n, 3))
+    S["omega"] = 0.2 * rng.standard_normal((n, 3))
+    U = rng.standard_normal((mesh.n_cells, 3))
+    mine = o.interact(shapes, S, U, 2.5e-3, 1.7, faithful=True)
+    ref = ref_py.Reference(mesh).interact([ref_py.dict_text_from_record(r) for r in shapes], S, seeds, U, 2.5e-3, 1.7, two_d)
+    assert np.array_equal(ref["list_off"], mine["list_off"]) and np.array_equal(ref["list_cells"], mine["list_cells"])
+    assert np.array_equal(ref["Ct"], mine["Ct"])
+    for k in ("As", "Ts", "Fs"):
+        ok = np.isfinite(ref[k])
+        assert np.array_equal(ok, np.isfinite(mine[k]))
+        scale = max(1.0, np.abs(mine[k][ok]).max())
+        assert np.abs(ref[k][ok] - mine[k][ok]).max() <= 1e-15 * scale, k
+    ok = np.isfinite(ref["FT"])
+    assert np.abs(ref["FT"][ok] - mine["FT"][ok]).max() <= 1e-13 * max(1.0, np.abs(mine["FT"][ok]).max())
     return off
 
 
