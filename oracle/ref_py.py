@@ -140,3 +140,42 @@ class Reference:
         out["pairs"] = int(rc)
         out["timing_ms"] = float(ms.value)
         return out
+
+
+def plugin_dict_text(entry) -> str:
+    """solidDict entries of one motion / forcer from a Python dict (type=..., keys as the reference's constructors read them)."""
+    if not entry:
+        return ""
+    s = ""
+    for key, v in entry.items():
+        if isinstance(v, (tuple, list, np.ndarray)):
+            s += f"{key} ({' '.join(repr(float(x)) for x in v)});\n"
+        elif isinstance(v, str):
+            s += f"{key} {v};\n"
+        else:
+            s += f"{key} {float(v)!r};\n"
+    return s
+
+
+def ref_evolve(shape_texts, motions, forcers, rho, pos, quat, vel, omega, times, dt, n_subiter, gravity, rhof, fluid_ft=None,
+               bounds=None, delta=-2.0):
+    """SolidCloud::evolve over len(times) steps with the reference's own Solid / motions / forcers (and libcollision when bounds is
+    given).  Returns dict(pos, quat, vel, omega, FT, traj[n_steps, n, 13])."""
+    lib = C.CDLL(LIB_PATH)
+    lib.ref_evolve.restype = C.c_int
+    n = len(shape_texts)
+    arr = lambda a, shape: np.array(a, dtype=np.float64).reshape(shape).copy()
+    enc = lambda texts: (C.c_char_p * n)(*[t.encode() for t in texts])
+    pos, quat, vel, omega = arr(pos, (n, 3)), arr(quat, (n, 4)), arr(vel, (n, 3)), arr(omega, (n, 3))
+    rho, times, g = arr(rho, (n,)), arr(times, (-1,)), arr(gravity, (3,))
+    ft, traj = np.zeros((n, 6)), np.zeros((len(times), n, 13))
+    P = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    fl = None if fluid_ft is None else arr(fluid_ft, (len(times), n, 6))
+    bmin = None if bounds is None else arr(bounds[0], (3,))
+    bmax = None if bounds is None else arr(bounds[1], (3,))
+    rc = lib.ref_evolve(n, enc(shape_texts), enc([plugin_dict_text(m) for m in motions]), enc([plugin_dict_text(f) for f in forcers]),
+                        P(rho), P(pos), P(quat), P(vel), P(omega), P(fl), P(g), C.c_double(rhof), len(times), P(times), C.c_double(dt),
+                        int(n_subiter), P(bmin), P(bmax), C.c_double(delta), P(ft), P(traj))
+    if rc != 0:
+        raise RuntimeError(f"ref_evolve failed ({rc})")
+    return dict(pos=pos, quat=quat, vel=vel, omega=omega, FT=ft, traj=traj)

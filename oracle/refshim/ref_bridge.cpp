@@ -18,6 +18,8 @@
 #include "solid.h"
 #include "libcollision/ugrid.h"
 #include "libcollision/collision.h"
+#include "libmotion/motionfactory.h"
+#include "libforcer/forcerfactory.h"
 
 using namespace sdfibm;
 
@@ -262,6 +264,123 @@ int64_t ref_interact_full(void *h, int n_solids, const char *const *dict_text, c
         return n_out;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "ref_interact_full: %s\n", e.what());
+        return -2;
+    }
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SolidCloud::evolve (reference src/solidcloud.cpp:466-475,521-562) around the reference's own Solid (src/solid.h: applyForcer,
+// addMidFluidForceAndTorque, addAcceleration, move, storeOldForce), MotionFactory / the seven motions (src/libmotion) and
+// ForcerFactory / the three forcers (src/libforcer), all compiled unmodified.  The sub-iteration loop below is the caller's,
+// restated line for line; collisions as in ref_collide when delta > 0 (HEAD's grid yields no pairs).
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+// motion_text[s] / forcer_text[s]: the solidDict entries of the plugin ("type MotionRotor; period 4; ...") or "" for none.
+// fluid_ft: n_steps x n x 6 fluid (force, torque) set before each step (Solid::setFluidForceAndTorque, solidcloud.cpp:424), or
+// null.  State arrays are updated in place; ft_out[6n] = total force / torque of the LAST sub-iteration; traj (optional,
+// n_steps x n x 13) = pos, quat, vel, omega after every step.
+int ref_evolve(int n, const char *const *shape_text, const char *const *motion_text, const char *const *forcer_text, const double *rho,
+               double *pos, double *quat, double *vel, double *omega, const double *fluid_ft, const double *gravity, double rhof,
+               int n_steps, const double *times, double dt, int n_subiter, const double *bmin, const double *bmax, double delta,
+               double *ft_out, double *traj) {
+    try {
+        static bool table = false;
+        if (!table) { InitCollisionFuncTable(); table = true; }
+        std::vector<std::unique_ptr<IShape>> shapes;
+        std::vector<std::unique_ptr<IMotion>> motions(n);
+        std::vector<std::unique_ptr<forcer::IForcer>> forcers(n);
+        std::vector<IMaterial> materials;
+        materials.reserve(n);
+        std::vector<Solid> solids;
+        solids.reserve(n);
+        for (int s = 0; s < n; ++s) {
+            Foam::dictionary d = dict_of(shape_text[s]);
+            shapes.push_back(ShapeFactory::create(std::string(d.lookup("type")), d));
+            materials.emplace_back(rho[s]);
+            solids.emplace_back(s, Foam::vector(pos[3 * s], pos[3 * s + 1], pos[3 * s + 2]),
+                                Foam::quaternion(quat[4 * s], Foam::vector(quat[4 * s + 1], quat[4 * s + 2], quat[4 * s + 3])));
+            Solid &S = solids.back();
+            S.setVelocity(Foam::vector(vel[3 * s], vel[3 * s + 1], vel[3 * s + 2]));
+            S.setOmega(Foam::vector(omega[3 * s], omega[3 * s + 1], omega[3 * s + 2]));
+            S.setShape(shapes.back().get());                                          // order of solidcloud.cpp:171-189
+            S.setMaterial(&materials.back());
+            if (motion_text[s] && motion_text[s][0]) {
+                Foam::dictionary md = dict_of(motion_text[s]);
+                motions[s].reset(MotionFactory::create(std::string(md.lookup("type")), md));
+                if (!motions[s]) return -4;
+                S.setMotion(motions[s].get());
+            }
+            if (forcer_text[s] && forcer_text[s][0]) {
+                Foam::dictionary fd = dict_of(forcer_text[s]);
+                forcers[s] = forcer::ForcerFactory::create(std::string(fd.lookup("type")), fd);
+                S.setForcer(forcers[s].get());
+            }
+        }
+        const Foam::vector g(gravity[0], gravity[1], gravity[2]);
+        std::unique_ptr<UGrid> grid;
+        if (bmin && bmax) { BBox bbox(bmin, bmax); grid.reset(new UGrid(bbox, delta)); }
+        std::vector<CollisionPair> cps;
+        for (int step = 0; step < n_steps; ++step) {
+            scalar time = times[step];
+            if (fluid_ft)
+                for (int s = 0; s < n; ++s) {
+                    const double *f = fluid_ft + ((size_t)step * n + s) * 6;
+                    solids[s].setFluidForceAndTorque(Foam::vector(f[0], f[1], f[2]), Foam::vector(f[3], f[4], f[5]));
+                }
+            const scalar dt_sub = dt / n_subiter;                                     // evolve, :521-562
+            for (int i = 0; i < n_subiter; ++i) {
+                for (Solid &S : solids) S.clearForceAndTorque();
+                for (Solid &S : solids) S.applyForcer(time);
+                for (Solid &S : solids) S.addMidFluidForceAndTorque();
+                for (Solid &S : solids) {                                             // addMidEnvironment, :466-475
+                    const scalar rhos = S.getMaterial()->getRho();
+                    const Foam::vector gprime = ((rhos - rhof) / rhos) * g;
+                    S.addAcceleration(gprime);
+                }
+                if (grid) {                                                           // solidSolidInteract, :477-519
+                    grid->clear();
+                    for (const Solid &S : solids) { const vector c = S.getCenter(); grid->insert(c.x(), c.y(), c.z(), S.getID()); }
+                    cps.clear();
+                    grid->generateCollisionPairs(cps);
+                    for (CollisionPair &cp : cps) {
+                        Solid &s1 = solids[cp.first], &s2 = solids[cp.second];
+                        collisionFunc cfunc = getCollisionFunc(s1.getShape()->getTypeName(), s2.getShape()->getTypeName());
+                        if (!cfunc) continue;
+                        vector cP, cN;
+                        const scalar cd = cfunc(s1, s2, cP, cN);
+                        if (cd < 0) continue;
+                        const vector force = 1e4 * cd * cN, torque = vector::zero;
+                        s1.addForceAndTorque(-force, -torque);
+                        s2.addForceAndTorque(force, torque);
+                    }
+                }
+                for (Solid &S : solids) S.move(time, dt_sub);
+            }
+            for (Solid &S : solids) S.storeOldForce();
+            if (traj)
+                for (int s = 0; s < n; ++s) {
+                    double *o = traj + ((size_t)step * n + s) * 13;
+                    const Solid &S = solids[s];
+                    for (int k = 0; k < 3; ++k) { o[k] = S.getCenter()[k]; o[7 + k] = S.getVelocity()[k]; o[10 + k] = S.getOmega()[k]; }
+                    o[3] = S.getOrientation().w();
+                    for (int k = 0; k < 3; ++k) o[4 + k] = S.getOrientation().v()[k];
+                }
+        }
+        for (int s = 0; s < n; ++s) {
+            const Solid &S = solids[s];
+            for (int k = 0; k < 3; ++k) {
+                pos[3 * s + k] = S.getCenter()[k]; vel[3 * s + k] = S.getVelocity()[k]; omega[3 * s + k] = S.getOmega()[k];
+                quat[4 * s + 1 + k] = S.getOrientation().v()[k];
+                if (ft_out) { ft_out[6 * s + k] = S.getForce()[k]; ft_out[6 * s + 3 + k] = S.getTorque()[k]; }
+            }
+            quat[4 * s] = S.getOrientation().w();
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "ref_evolve: %s\n", e.what());
         return -2;
     }
 }

@@ -128,3 +128,146 @@ def test_collision_step_against_libcollision():
             assert len(pairs) > 20 and np.abs(ft).max() > 0
         else:
             assert len(pairs) == 0
+
+
+def _evolve_case():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import host_cases as hc
+
+    solids = [
+        dict(shp_name="sph", mot_name="free", mat_name="heavy", pos=(0.2, 1.5, 0.1), vel=(0.1, 0.0, -0.1), euler=(10, 20, 30), omega=(0.3, -0.2, 0.5)),
+        dict(shp_name="elo", mot_name="free", mat_name="light", for_name="spring", pos=(1.0, 0.7, -0.3), euler=(0, 45, 10), omega=(0, 0.4, 0.1)),
+        dict(shp_name="box", mot_name="mask", mat_name="heavy", for_name="push", pos=(-0.5, 0.2, 0.4), vel=(0.2, 0.1, 0.3), omega=(0.1, 0.2, 0.3)),
+        dict(shp_name="sph", mot_name="rotor", mat_name="light", pos=(0.7, 0.0, 0.0)),
+        dict(shp_name="elo", mot_name="sine", mat_name="heavy", for_name="mag", pos=(0.0, -1.0, 0.5), euler=(30, 0, 0)),
+        dict(shp_name="box", mot_name="const", mat_name="light", pos=(2.0, 2.0, 2.0)),
+        dict(shp_name="sph", mot_name="spin", mat_name="light", pos=(-2.0, 0.0, 1.0), vel=(1, 1, 1)),
+        dict(shp_name="sph", mot_name="spinfree", mat_name="heavy", for_name="mag", pos=(-2.0, 1.0, 1.0), vel=(0.3, -0.1, 0.2), euler=(0, 0, 15)),
+        dict(shp_name="box", mot_name="gate", mat_name="light", pos=(3.0, 0.0, 0.0)),
+        dict(shp_name="circ", mot_name="free", mat_name="heavy", pos=(0.5, 0.5, 0.0), omega=(0, 0, 0.7)),
+        dict(shp_name="tail", mot_name="free", mat_name="light", for_name="push", pos=(1.5, -0.5, 0.0), euler=(0, 0, 40)),
+    ]
+    return hc, solids
+
+
+def test_evolve_against_the_reference_solid_motions_and_forcers():
+    """Row f1: SolidCloud::evolve.  The reference's own Solid::move / applyForcer / addMidFluidForceAndTorque / storeOldForce, its
+    seven motions and three forcers (compiled unmodified) inside the sub-iteration loop of src/solidcloud.cpp:521-562, against the
+    restatement in oracle/host_oracle.py that pins the host façade: 20 sub-iterations, gravity with buoyancy, a fluid force that
+    changes every step (the AB2 blend 1.5 F_n - 0.5 F_{n-1})."""
+    from oracle import host_oracle as ho
+
+    hc, solids = _evolve_case()
+    ref = hc.oracle_solids(solids)
+    n = len(solids)
+
+    def sdict(name):
+        d = dict(hc.SHAPES[name])
+        return ref_py.shape_dict_text(d.pop("type"), com=d.pop("com", (0.0, 0.0, 0.0)), **d)
+
+    texts = [sdict(s["shp_name"]) for s in solids]
+    motions = [None if s["mot_name"] == "free" else hc.MOTIONS[s["mot_name"]] for s in solids]
+    forcers = [hc.FORCES[s["for_name"]] if "for_name" in s else None for s in solids]
+    rho = [hc.MATERIALS[s["mat_name"]]["rho"] for s in solids]
+    x, q, v, om = hc.state_arrays(ref)
+    assert np.allclose([r.mass for r in ref], [hc.mass_props(s["shp_name"])[0] * r_ for s, r_ in zip(solids, rho)])
+    n_steps, dt, g, rhof = 8, 0.01, (0.0, -9.81, 0.5), 1.1
+    times = 0.5 + dt * np.arange(1, n_steps + 1)
+    rng = np.random.RandomState(11)
+    fluid = 0.05 * rng.standard_normal((n_steps, n, 6))
+    out = ref_py.ref_evolve(texts, motions, forcers, rho, x, q, v, om, times, dt, 20, g, rhof, fluid_ft=fluid)
+    for step in range(n_steps):
+        for i, s in enumerate(ref):
+            s.ff, s.ft = tuple(fluid[step, i, :3]), tuple(fluid[step, i, 3:])
+        ho.evolve(ref, float(times[step]), dt, 20, g, rhof)
+        x, q, v, om = hc.state_arrays(ref)
+        mine = np.concatenate([x, q, v, om], axis=1)
+        err = np.abs(mine - out["traj"][step]).max()
+        assert err <= 2e-14 * max(1.0, np.abs(mine).max()), (step, err)
+    ft = np.array([s.force + s.torque for s in ref])
+    assert np.abs(ft - out["FT"]).max() <= 1e-13 * max(1.0, np.abs(ft).max())
+    # something happened: free bodies fell, constrained ones followed their law
+    assert out["pos"][0][1] < 1.5 - 0.01 and abs(out["vel"][5][0] - 0.1) < 1e-15 and abs(out["omega"][3][2] - 1.1) < 1e-15
+
+
+def test_evolve_with_collisions_against_the_reference():
+    """The same loop with the collision step active (a grid spacing that does build cells, SURVEY Q7 'intended' mode): spheres
+    dropped on a floor plane and on each other; trajectories of the oracle (host_oracle.evolve + Oracle.collide) against the
+    reference's Solid + UGrid + contact functions."""
+    from oracle import host_oracle as ho
+    import host_cases as hc
+
+    rng = np.random.RandomState(2)
+    n = 14
+    shapes_named = dict(hc.SHAPES, ball=dict(type="Sphere", radius=0.3))
+    solids = [dict(shp_name="ball", mot_name="free", mat_name="heavy", pos=tuple(p), vel=(0.0, -1.0, 0.0))
+              for p in rng.uniform((0.5, 0.35, 0.5), (2.5, 1.6, 2.5), size=(n - 1, 3))]
+    solids.append(dict(shp_name="plane", mot_name="frozen", mat_name="heavy", pos=(1.5, 0.1, 1.5)))
+    motions = dict(hc.MOTIONS, frozen=dict(type="Motion01Mask", mask="b000000"))
+    vol = 4.0 / 3.0 * np.pi * 0.3 ** 3
+    ref = []
+    for s in solids:
+        if s["shp_name"] == "ball":
+            ref.append(ho.SolidState(s["pos"], (1.0, 0.0, 0.0, 0.0), s["vel"], (0, 0, 0), vol, 1.0 / vol, [1.0 / (0.4 * vol * 0.09)] * 3, 3.0, None, None))
+        else:
+            ref.append(ho.SolidState(s["pos"], (1.0, 0.0, 0.0, 0.0), (0, 0, 0), (0, 0, 0), 0.0, 0.0, [1.0, 1.0, 1.0], 3.0, motions["frozen"], None))
+    table = np.array([make_shape("Sphere", radius=0.3), make_shape("Plane")])
+    index = [0] * (n - 1) + [1]
+    mesh = Mesh.hex_block((6, 6, 6), x0=(0.0, 0.0, 0.0), dx=(0.5, 0.5, 0.5))
+    o = Oracle(mesh, False)
+    delta = 0.7
+
+    def collide(states):
+        pairs, ft = o.collide(table, ho.records(states, index), delta)
+        return ft
+
+    texts = [ref_py.shape_dict_text("Sphere", radius=0.3)] * (n - 1) + [ref_py.shape_dict_text("Plane")]
+    x, q, v, om = hc.state_arrays(ref)
+    n_steps, dt, g = 12, 0.004, (0.0, -9.81, 0.0)
+    times = dt * np.arange(1, n_steps + 1)
+    out = ref_py.ref_evolve(texts, [None] * (n - 1) + [motions["frozen"]], [None] * n, [3.0] * n, x, q, v, om, times, dt, 20, g, 0.0,
+                            bounds=(mesh.bounds_min, mesh.bounds_max), delta=delta)
+    hit = False
+    for step in range(n_steps):
+        ho.evolve(ref, float(times[step]), dt, 20, g, 0.0, collide=collide)
+        x, q, v, om = hc.state_arrays(ref)
+        mine = np.concatenate([x, q, v, om], axis=1)
+        err = np.abs(mine - out["traj"][step]).max()
+        assert err <= 1e-12 * max(1.0, np.abs(mine).max()), (step, err)
+        hit = hit or np.abs(v[: n - 1, [0, 2]]).max() > 1e-6 or v[: n - 1, 1].max() > -1.0
+    assert hit, "no contact happened: the case does not exercise the collision step"
+
+
+def test_host_facade_evolve_against_the_reference(tmp_path):
+    """The shipped C++ façade (sdfibm::SolidCloud::evolve over solidDict, sdfibm_b200/host) against the reference's classes, no
+    oracle in between: DEM mode (on_fluid 0) restarted at t > 0 so no device call is needed."""
+    from sdfibm_b200 import hostapi
+
+    hc, solids = _evolve_case()
+    solids = solids[:9]                      # the 3-D ones (on_twod 0)
+    meta = dict(on_fluid=0, on_twod=0, gravity=(0.0, -9.81, 0.5))
+    path = hc.write_case(tmp_path, meta, solids)
+    hostapi.load().sdfibm_host_reset_subiterations()
+    mesh = Mesh.hex_block((4, 4, 4), (-2, -2, -2), (1.0, 1.0, 1.0))
+    cloud = hostapi.HostCloud(path, str(tmp_path), mesh, rho_fluid=1.0, start_time=0.5)
+
+    def sdict(name):
+        d = dict(hc.SHAPES[name])
+        return ref_py.shape_dict_text(d.pop("type"), com=d.pop("com", (0.0, 0.0, 0.0)), **d)
+
+    st = cloud.solids()
+    n_steps, dt = 6, 0.01
+    times = 0.5 + dt * np.arange(1, n_steps + 1)
+    out = ref_py.ref_evolve([sdict(s["shp_name"]) for s in solids],
+                            [None if s["mot_name"] == "free" else hc.MOTIONS[s["mot_name"]] for s in solids],
+                            [hc.FORCES[s["for_name"]] if "for_name" in s else None for s in solids],
+                            [hc.MATERIALS[s["mat_name"]]["rho"] for s in solids], st["pos"], st["quat"], st["vel"], st["omega"],
+                            times, dt, 20, meta["gravity"], 0.0)
+    for step in range(n_steps):
+        cloud.evolve(float(times[step]), dt)
+        got = cloud.solids()
+        mine = np.concatenate([got["pos"], got["quat"], got["vel"], got["omega"]], axis=1)
+        err = np.abs(mine - out["traj"][step]).max()
+        assert err <= 2e-14 * max(1.0, np.abs(mine).max()), (step, err)
+    ft, _ = cloud.forces()
+    assert np.abs(ft - out["FT"]).max() <= 1e-13 * max(1.0, np.abs(ft).max())
