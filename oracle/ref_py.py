@@ -179,3 +179,16 @@ def ref_evolve(shape_texts, motions, forcers, rho, pos, quat, vel, omega, times,
     if rc != 0:
         raise RuntimeError(f"ref_evolve failed ({rc})")
     return dict(pos=pos, quat=quat, vel=vel, omega=omega, FT=ft, traj=traj)
+
+
+def ref_fix_internal(mesh, solids, Ct, U):
+    """SolidCloud::fixInternal with the reference's Solid::evalPointVelocity; returns the corrected copy of U."""
+    lib = C.CDLL(LIB_PATH)
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    cc, pos, vel, om, Ct = arr(mesh.cc), arr(solids["pos"]), arr(solids["vel"]), arr(solids["omega"]), arr(Ct)
+    U = np.array(U, dtype=np.float64, order="C", copy=True)
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    rc = lib.ref_fix_internal(int(mesh.n_cells), P(cc), len(solids), P(pos), P(vel), P(om), P(Ct), P(U))
+    if rc != 0:
+        raise RuntimeError(f"ref_fix_internal failed ({rc})")
+    return U

@@ -386,3 +386,23 @@ int ref_evolve(int n, const char *const *shape_text, const char *const *motion_t
 }
 
 } // extern "C"
+
+// SolidCloud::fixInternal (reference src/solidcloud.cpp:288-301) around the reference's Solid::evalPointVelocity.
+extern "C" int ref_fix_internal(int n_cells, const double *cc, int n_solids, const double *pos, const double *vel, const double *omega,
+                                const double *Ct, double *U) {
+    std::vector<Solid> solids;
+    for (int s = 0; s < n_solids; ++s) {
+        solids.emplace_back(s, Foam::vector(pos[3 * s], pos[3 * s + 1], pos[3 * s + 2]), Foam::quaternion(1.0, Foam::vector::zero));
+        solids.back().setVelocity(Foam::vector(vel[3 * s], vel[3 * s + 1], vel[3 * s + 2]));
+        solids.back().setOmega(Foam::vector(omega[3 * s], omega[3 * s + 1], omega[3 * s + 2]));
+    }
+    for (int icell = 0; icell < n_cells; ++icell) {
+        if (Ct[icell] >= 4) {
+            const label id = (label)(Ct[icell] - 4);
+            if (id >= n_solids) return -1;
+            const Foam::vector u = solids[id].evalPointVelocity(Foam::vector(cc[3 * icell], cc[3 * icell + 1], cc[3 * icell + 2]));
+            U[3 * icell] = u.x(); U[3 * icell + 1] = u.y(); U[3 * icell + 2] = u.z();
+        }
+    }
+    return 0;
+}

@@ -62,6 +62,10 @@ def _compare(mesh, two_d, specs, pos, euler):
         assert np.abs(ref[k][ok] - mine[k][ok]).max() <= 1e-15 * scale, k
     ok = np.isfinite(ref["FT"])
     assert np.abs(ref["FT"][ok] - mine["FT"][ok]).max() <= 1e-13 * max(1.0, np.abs(mine["FT"][ok]).max())
+    # fixInternal (src/solidcloud.cpp:288-301) on the Ct just produced: bit-identical
+    fixed = o.fix_internal(shapes, S, mine["Ct"], U)
+    assert np.array_equal(fixed, ref_py.ref_fix_internal(mesh, S, ref["Ct"], U))
+    assert (mine["Ct"] >= 4).any() and not np.array_equal(fixed, U)
     return off
 
 
