@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "c4", "c5"])
     ap.add_argument("--cells-per-side", dest="n", type=int, default=0, help="cells per side (scaled-down runs)")
     ap.add_argument("--solids", type=int, default=0)
-    ap.add_argument("--cpu-solids", type=int, default=48, help="solids per CPU-baseline sample")
+    ap.add_argument("--cpu-solids", type=int, default=256, help="solids per CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
