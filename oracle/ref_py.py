@@ -119,6 +119,16 @@ class Reference:
         except Exception:
             pass
 
+    def mean_field(self, dict_text, pos, quat, seed, field, two_d):
+        """SolidCloud::calcMeanField over one substitute shape: (mean[3], volume)."""
+        arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        pos, quat, field, out = arr(pos), arr(quat), arr(field), np.zeros(4)
+        P = lambda a: C.c_void_p(a.ctypes.data)
+        rc = self._lib.ref_mean_field(self._h, dict_text.encode(), P(pos), P(quat), int(seed), P(field), int(bool(two_d)), P(out))
+        if rc != 0:
+            raise RuntimeError(f"ref_mean_field failed ({rc})")
+        return out[:3].copy(), float(out[3])
+
     def interact(self, dict_texts, solids, seeds, U, dt, rhof, two_d, solid_range=None, want_lists=True):
         n, nC = len(solids), self.mesh.n_cells
         b, e = (0, n) if solid_range is None else solid_range

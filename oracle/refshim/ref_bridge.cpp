@@ -406,3 +406,37 @@ extern "C" int ref_fix_internal(int n_cells, const double *cc, int n_solids, con
     }
     return 0;
 }
+
+// SolidCloud::calcMeanField<vector> (reference src/solidcloud.cpp:315-359): the volume-weighted mean of a vector field over a
+// substitute shape, with the enumerator driven cell by cell (Empty / GetCurCellInd / GetCurCellType / Next) as the reference does.
+// out[4] = mean.xyz, volume.
+extern "C" int ref_mean_field(void *h, const char *shape_text, const double *pos, const double *quat, int seed, const double *field,
+                              int two_d, double *out) {
+    try {
+        RefCtx &R = *static_cast<RefCtx *>(h);
+        Foam::dictionary d = dict_of(shape_text);
+        std::unique_ptr<IShape> shape = ShapeFactory::create(std::string(d.lookup("type")), d);
+        Solid tmpSolid(0, Foam::vector(pos[0], pos[1], pos[2]), Foam::quaternion(quat[0], Foam::vector(quat[1], quat[2], quat[3])));
+        tmpSolid.setShape(shape.get());
+        R.geo->clearCache();
+        Foam::vector meanField = Foam::vector::zero;
+        scalar volume = 0.0;
+        CellEnumerator ce(R.mesh, [&](const vector &v) { return tmpSolid.phi01(v); }, seed);
+        scalar alpha = 0.0;
+        while (!ce.Empty()) {
+            const int icur = ce.GetCurCellInd();
+            if (ce.GetCurCellType() == CellEnumerator::CELL_TYPE::ALL_INSIDE) alpha = 1.0;
+            else alpha = R.geo->calcCellVolume(icur, tmpSolid, two_d != 0) / R.mesh.cv[icur];
+            const scalar dV = alpha * R.mesh.cv[icur];
+            volume += dV;
+            meanField += dV * Foam::vector(field[3 * icur], field[3 * icur + 1], field[3 * icur + 2]);
+            ce.Next();
+        }
+        const Foam::vector m = meanField / volume;
+        out[0] = m.x(); out[1] = m.y(); out[2] = m.z(); out[3] = volume;
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "ref_mean_field: %s\n", e.what());
+        return -2;
+    }
+}

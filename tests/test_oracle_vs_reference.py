@@ -62,6 +62,18 @@ def _compare(mesh, two_d, specs, pos, euler):
         assert np.abs(ref[k][ok] - mine[k][ok]).max() <= 1e-15 * scale, k
     ok = np.isfinite(ref["FT"])
     assert np.abs(ref["FT"][ok] - mine["FT"][ok]).max() <= 1e-13 * max(1.0, np.abs(mine["FT"][ok]).max())
+    # calcMeanField (src/solidcloud.cpp:315-359): sum(alpha V U) / sum(alpha V) from the oracle's per-solid alpha, as the GPU test
+    # of sdfibm_mean_field forms it, against the reference's enumerator-driven loop
+    R = ref_py.Reference(mesh)
+    for i in range(n):
+        one = S[i:i + 1].copy()
+        one["shape"] = 0
+        a = o.interact(shapes[i:i + 1], one, U, 1.0, 1.0)["Ts"]
+        if not np.isfinite(a).all() or a.sum() == 0:
+            continue
+        den = float((a * mesh.V).sum())
+        m, vol = R.mean_field(ref_py.dict_text_from_record(shapes[i]), S[i]["pos"], S[i]["quat"], seeds[i], U, two_d)
+        assert abs(vol - den) <= 1e-13 * den and np.abs(m - (a * mesh.V) @ U / den).max() <= 1e-12
     # fixInternal (src/solidcloud.cpp:288-301) on the Ct just produced: bit-identical
     fixed = o.fix_internal(shapes, S, mine["Ct"], U)
     assert np.array_equal(fixed, ref_py.ref_fix_internal(mesh, S, ref["Ct"], U))
