@@ -1,0 +1,92 @@
+"""The CUDA path against the reference's OWN compiled code (oracle/_ref/libsdfibm_ref.so: src/cellenumerator.cpp,
+src/geometrictools.cpp, src/solid.h, src/libshape — unmodified — inside the loop of src/solidcloud.cpp:361-464), with no
+restatement in between.  The library is built in the build container (where /root/reference exists) and travels with the
+snapshot; where it is absent the tests skip.  Hex meshes only: on mixed polyhedra the reference's ALL_INSIDE test depends on the
+flood fill's visiting order, which test_oracle_vs_reference.py covers on the CPU side.
+
+Bars as in test_gpu_parity.py: lists and Ct exact, As / Ts / Fs 1e-12 relative, force / torque 1e-10 relative to sum |terms|."""
+import numpy as np
+import pytest
+
+from oracle import ref_py
+from oracle.oracle_py import Oracle
+from sdfibm_b200 import cases
+
+CASES = {
+    "c1": cases.case_c1,
+    "c2": cases.case_c2,
+    "c2_walls": lambda: cases.case_c2(with_walls=True),
+    "skewed2d": cases.case_skewed_2d,
+    "c4_small": lambda: cases.case_c4(n=48, n_solids=50, n_side=4),
+    "c5_small": lambda: cases.case_c5_block(0, 1, n=32, n_solids=24, n_side=3),
+}
+
+
+def _reference(case):
+    try:
+        R = ref_py.Reference(case["mesh"])
+    except OSError as ex:          # a library built for another machine
+        pytest.skip(f"oracle/_ref does not load here: {ex}")
+    o = Oracle(case["mesh"], case["two_d"])
+    S = case["solids"]
+    seeds = np.array([o.nearest_cell(S[i]["pos"]) for i in range(len(S))], dtype=np.int32)   # meshSearch::findNearestCell is OpenFOAM's
+    texts = [ref_py.dict_text_from_record(case["shapes"][int(k)]) for k in S["shape"]]
+    return R.interact(texts, S, seeds, case["U"], case["dt"], case["rhof"], case["two_d"])
+
+
+def _check(case, got, off, cells, ref, rel_field, rel_force):
+    assert np.array_equal(off, ref["list_off"]) and np.array_equal(cells, ref["list_cells"])
+    assert np.array_equal(got["Ct"], ref["Ct"])
+    for k in ("As", "Ts", "Fs"):
+        a, b = got[k], ref[k]
+        tol = rel_field * np.maximum(np.abs(b), np.abs(b).max() * 1e-3 + 1e-300)
+        assert (np.abs(a - b) <= tol).all(), (k, np.abs(a - b).max())
+    from test_gpu_parity import _term_scale
+
+    scale = _term_scale(case, ref["list_off"], ref["list_cells"])
+    err = np.abs(got["FT"] - ref["FT"])
+    assert (err <= rel_force * np.maximum(scale, np.abs(ref["FT"])) + 1e-300).all(), err.max()
+
+
+def _moved(case):
+    """fixInternal runs after evolve: solid state moved on, Ct of the last interact."""
+    S2 = case["solids"].copy()
+    S2["vel"] += 0.05
+    S2["omega"] *= 1.1
+    S2["pos"] += 0.01
+    return S2, case["U"] * 0.9
+
+
+needs_ref = pytest.mark.skipif(not ref_py.available(), reason="oracle/_ref/libsdfibm_ref.so not built (needs the reference tree)")
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_against_compiled_reference_on_the_parity_cases(name):
+    """CPU side of the same comparison: the oracle the GPU tests use, on the very cases they use."""
+    case = CASES[name]()
+    ref = _reference(case)
+    mine = Oracle(case["mesh"], case["two_d"]).interact(case["shapes"], case["solids"], case["U"], case["dt"], case["rhof"])
+    _check(case, mine, mine["list_off"], mine["list_cells"], ref, 1e-14, 1e-12)
+    assert ref["pairs"] > 0
+    S2, U2 = _moved(case)
+    o = Oracle(case["mesh"], case["two_d"])
+    assert np.array_equal(o.fix_internal(case["shapes"], S2, mine["Ct"], U2), ref_py.ref_fix_internal(case["mesh"], S2, ref["Ct"], U2))
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_gpu_against_compiled_reference(name):
+    from sdfibm_b200.context import Context
+
+    case = CASES[name]()
+    ref = _reference(case)
+    ctx = Context(0)
+    ctx.set_mesh(case["mesh"], case["two_d"])
+    ctx.set_shapes(case["shapes"])
+    got = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
+    off, cells = ctx.candidate_lists()
+    _check(case, got, off, cells, ref, 1e-12, 1e-10)
+    S2, U2 = _moved(case)
+    assert np.array_equal(ctx.fix_internal(S2, U2), ref_py.ref_fix_internal(case["mesh"], S2, ref["Ct"], U2))
