@@ -455,7 +455,11 @@ __device__ __forceinline__ void eval_staged_vertex(HeavySmem &sm, const DevShape
 }
 
 #define HEAVY_CTAS_PER_SM 5
-template <int CTAS>
+// SYNTH (experimental, opt-in: SDFIBM_SYNTH_FACES=1, uniform box meshes only; NOT measured yet): the face centre and area vector
+// are formed from the staged vertices — Sf = (p2 - p0) x (p3 - p1) / 2 (the vector area of any quadrilateral), apex - Cf = the mean
+// of apex - p_i (the centroid of a parallelogram) — instead of being fetched: no cellFaces / face_rec traffic (24 + up to 384 bytes
+// per item).  Results then differ from the mesh's own Cf / Sf by rounding (1e-16 relative), not bit for bit.
+template <int CTAS, bool SYNTH>
 __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     __shared__ HeavySmem sm;
     const DevMesh &m = P.m;
@@ -495,7 +499,8 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             tw0 = __ldg(m.hex_topo + 3 * (long long)c);
             tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1);
             tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
-            if (m.is_hex) {
+            if (SYNTH) {
+            } else if (m.is_hex) {
                 const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
                 f01 = __ldg(cf2); f23 = __ldg(cf2 + 1); f45 = __ldg(cf2 + 2);
             } else {
@@ -583,10 +588,18 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
                     const double ph[4] = {PH(l[0]), PH(l[1]), PH(l[2]), PH(l[3])};
                     const int npos = (ph[0] > 0) + (ph[1] > 0) + (ph[2] > 0) + (ph[3] > 0);
                     if (npos == 4) continue;                                        // eps_f = 0: adds +0.0 (:107-108)
-                    const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
-                    // face record: Cf.xyz, Sf.xyz, |Sf|, pad — four 16-byte loads issued before the area math
-                    const double2 *fr = m.face_rec + 4 * (long long)face;
-                    const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2), r3 = __ldg(fr + 3);
+                    double2 r0 = {0.0, 0.0}, r1 = {0.0, 0.0}, r2 = {0.0, 0.0}, r3 = {0.0, 0.0};
+                    D3 Sf_s = {0.0, 0.0, 0.0}, dCf_s = {0.0, 0.0, 0.0};
+                    if (SYNTH) {
+                        const D3 p0 = PT(l[0]), p1 = PT(l[1]), p2 = PT(l[2]), p3 = PT(l[3]);
+                        Sf_s = 0.5 * cross3(p2 - p0, p3 - p1);
+                        dCf_s = 0.25 * (((apex - p0) + (apex - p1)) + ((apex - p2) + (apex - p3)));   // apex - Cf
+                    } else {
+                        const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
+                        // face record: Cf.xyz, Sf.xyz, |Sf|, pad — four 16-byte loads issued before the area math
+                        const double2 *fr = m.face_rec + 4 * (long long)face;
+                        r0 = __ldg(fr); r1 = __ldg(fr + 1); r2 = __ldg(fr + 2); r3 = __ldg(fr + 3);
+                    }
                     double eps_f = 1.0;                                             // all phi <= 0 (:109-110)
                     if (npos != 0) {
                         const D3 A = PT(l[0]);                                      // calcFaceArea (:74-96)
@@ -605,10 +618,14 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
                             const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
                             area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
                         }
-                        eps_f = area / r3.x;
+                        eps_f = area / (SYNTH ? mag3(Sf_s) : r3.x);
                     }
-                    const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
-                    volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
+                    if (SYNTH) {
+                        volume += (1.0 / 3.0) * eps_f * fabs(dot3(dCf_s, Sf_s));
+                    } else {
+                        const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
+                        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
+                    }
                 }
             }
             P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));   // type 0: no vertex inside -> not a member
