@@ -742,7 +742,7 @@ struct sdfibm_context {
     GraphKey graph_key = {0};
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
-    bool synth_faces = false;   // experimental (SDFIBM_SYNTH_FACES=1): k_heavy_hex<., true> on uniform box meshes
+    int synth_faces = 0;        // experimental (SDFIBM_SYNTH_FACES=1 | 2): k_heavy_hex<5 | 6, true> on uniform box meshes
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
     const sdfibm_solid_t *ext_solids = nullptr;   // device-resident solid records supplied by the caller for the current call
@@ -814,7 +814,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaMallocHost(&ctx->h_scal, 2 * sizeof(double)));
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
-    if (const char *e = getenv("SDFIBM_SYNTH_FACES")) ctx->synth_faces = atoi(e) != 0;
+    if (const char *e = getenv("SDFIBM_SYNTH_FACES")) ctx->synth_faces = atoi(e);
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -1325,7 +1325,8 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         else k_classify<256, 8, false, false><<<grid, 256, 0, st>>>(I);
     };
     auto launch_heavy = [&]() {
-        if (ctx->synth_faces && ctx->dm.is_hex && ctx->dm.box_uniform) k_heavy_hex<HEAVY_CTAS_PER_SM, true><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+        if (ctx->synth_faces == 2 && ctx->dm.is_hex && ctx->dm.box_uniform) k_heavy_hex<6, true><<<ctx->n_sm * 6, TPB, 0, st>>>(I);
+        else if (ctx->synth_faces && ctx->dm.is_hex && ctx->dm.box_uniform) k_heavy_hex<HEAVY_CTAS_PER_SM, true><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
         else if (ctx->dm.is_hex || ctx->dm.mixed) k_heavy_hex<HEAVY_CTAS_PER_SM, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
         if (!ctx->dm.is_hex) k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     };

@@ -14,13 +14,14 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.xfail(reason="experimental variant, never run on a GPU yet", strict=False)
+@pytest.mark.parametrize("variant", ["1", "2"])       # 1: 5 CTAs / SM (90 registers), 2: 6 CTAs / SM (80 registers)
 @pytest.mark.parametrize("name", ["c4_small", "c1"])
-def test_synthesised_faces_variant_meets_the_parity_bars(name):
+def test_synthesised_faces_variant_meets_the_parity_bars(name, variant):
     from test_gpu_parity import check_parity, run_both
 
     case = cases.case_c4(n=48, n_solids=50, n_side=4) if name == "c4_small" else cases.case_c1()
     old = os.environ.get("SDFIBM_SYNTH_FACES")
-    os.environ["SDFIBM_SYNTH_FACES"] = "1"        # read by sdfibm_create
+    os.environ["SDFIBM_SYNTH_FACES"] = variant    # read by sdfibm_create
     try:
         o, ref, ctx, got = run_both(case)
     finally:
