@@ -1,10 +1,6 @@
-"""Randomised oracle-vs-reference comparison: small hex blocks (2-D and 3-D, several spacings / origins), every shape type with
-random, integer and half-integer sizes, solids placed at random points, exactly on vertices, on cell-centre planes and partly or
-wholly outside the mesh, aligned and arbitrary orientations.  The oracle (both its faithful and its fast list builder) against the
-reference's own compiled classes (oracle/_ref): lists and Ct identical, As / Ts / Fs to 1e-13, force / torque to 1e-11.
-8000 such cases were run when this was written (no discrepancy); the test keeps 400.  A second generator covers non-box cells:
-jittered + rotated hex blocks in 2-D and 3-D, prism meshes, and the mixed hex / prism / polyhedron mesh (1200 run, 160 kept)."""
-import math
+"""Randomised oracle-vs-reference comparison on the cases of tests/fuzz_cases.py.  The oracle (both its faithful and its fast list
+builder) against the reference's own compiled classes (oracle/_ref): lists and Ct identical, As / Ts / Fs to 1e-13, force / torque
+to 1e-11.  8000 box-cell and 1200 general-cell cases were run when this was written (no discrepancy); the test keeps 400 + 160."""
 import os
 import sys
 
@@ -13,15 +9,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+import fuzz_cases  # noqa: E402
 from oracle import ref_py  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
-from sdfibm_b200.mesh import Mesh  # noqa: E402
-from sdfibm_b200.shapes import make_shape, make_solids, quat_from_euler_xyz_deg  # noqa: E402
-from sdfibm_b200 import cases  # noqa: E402
-
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-from mixed_mesh import mixed_hex_prism_mesh  # noqa: E402
 
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
 
@@ -33,147 +25,54 @@ def _built():
     assert build.build_reference_oracle() is not None and ref_py.available()
 
 
-def _rand_shape3(rng, h):
-    t = rng.choice(["Sphere", "Ellipsoid", "Box"])
-    r = lambda: float(rng.choice([rng.uniform(0.2, 4.0) * h, rng.randint(1, 4) * h, rng.randint(1, 8) * 0.5 * h]))
-    if t == "Sphere": return t, dict(radius=r())
-    return t, dict(radiusa=r(), radiusb=r(), radiusc=r())
-def _rand_shape2(rng, h):
-    t = rng.choice(["Circle", "Ellipse", "Rectangle", "Circle_Tail", "Circle_TwoTail", "Plane"])
-    r = lambda: float(rng.choice([rng.uniform(0.2, 5.0) * h, rng.randint(1, 5) * h, rng.randint(1, 8) * 0.5 * h]))
-    if t == "Circle": return t, dict(radius=r())
-    if t in ("Ellipse", "Rectangle"): return t, dict(radiusa=r(), radiusb=r())
-    if t == "Plane": return t, dict()
-    return t, dict(radius=r(), ratio=float(rng.uniform(0.5, 3)), thickness=float(rng.uniform(0.1, 1.0) * h))
-
-def _one(seed, two_d):
-    rng = np.random.RandomState(seed)
-    if two_d:
-        n = (int(rng.randint(6, 24)), int(rng.randint(6, 24)), 1); h = float(rng.choice([0.1, 0.25, 1.0, 0.3]))
-        mesh = Mesh.hex_block(n, x0=(float(rng.choice([0.0, -1.0, -n[0]*h/2])), float(rng.choice([0.0, -n[1]*h/2])), -0.5), dx=(h, h * float(rng.choice([1.0, 1.0, 0.7])), 1.0))
-    else:
-        n = tuple(int(x) for x in rng.randint(5, 12, size=3)); h = float(rng.choice([0.1, 0.25, 1.0, 0.3]))
-        mesh = Mesh.hex_block(n, x0=tuple(float(x) for x in rng.choice([0.0, -1.0, 0.37], size=3)), dx=(h, h * float(rng.choice([1.0, 0.8])), h * float(rng.choice([1.0, 1.3]))))
-    k = int(rng.randint(1, 5))
-    specs = [_rand_shape2(rng, h) if two_d else _rand_shape3(rng, h) for _ in range(k)]
-    shapes = np.array([make_shape(t, **kw) for t, kw in specs])
-    S = make_solids(k)
-    lo, hi = mesh.bounds_min, mesh.bounds_max
-    for i in range(k):
-        mode = rng.randint(0, 4)
-        p = rng.uniform(lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo))
-        if mode == 1:   # on a vertex
-            p = lo + np.round((p - lo) / h) * h
-        elif mode == 2: # on a cell centre along x
-            p[0] = lo[0] + (np.floor((p[0] - lo[0]) / h) + 0.5) * h
-        if two_d: p[2] = 0.0
-        S[i]["pos"] = p
-        e = (0, 0, float(rng.choice([0, 0, 45, 90, rng.uniform(-180, 180)]))) if two_d else tuple(float(x) for x in rng.choice([0, 0, 30, 90, rng.uniform(-180, 180)], size=3))
-        S[i]["quat"] = quat_from_euler_xyz_deg(e)
-        S[i]["vel"] = rng.standard_normal(3) * 0.3; S[i]["omega"] = rng.standard_normal(3) * 0.2
-    S["shape"] = np.arange(k)
-    U = rng.standard_normal((mesh.n_cells, 3))
+def _compare(case):
+    mesh, two_d, shapes, S, U = case["mesh"], case["two_d"], case["shapes"], case["solids"], case["U"]
     o = Oracle(mesh, two_d)
-    mine = o.interact(shapes, S, U, 2.5e-3, 1.7, faithful=True)
-    mine2 = o.interact(shapes, S, U, 2.5e-3, 1.7, faithful=False)
-    seeds = np.array([o.nearest_cell(S[i]["pos"]) for i in range(k)], dtype=np.int32)
-    ref = ref_py.Reference(mesh).interact([ref_py.dict_text_from_record(r) for r in shapes], S, seeds, U, 2.5e-3, 1.7, two_d)
+    mine = o.interact(shapes, S, U, case["dt"], case["rhof"], faithful=True)
+    fast = o.interact(shapes, S, U, case["dt"], case["rhof"], faithful=False)
+    seeds = np.array([o.nearest_cell(S[i]["pos"]) for i in range(len(S))], dtype=np.int32)
+    ref = ref_py.Reference(mesh).interact([ref_py.dict_text_from_record(r) for r in shapes], S, seeds, U, case["dt"], case["rhof"], two_d)
     bad = []
-    if not (np.array_equal(ref["list_off"], mine["list_off"]) and np.array_equal(ref["list_cells"], mine["list_cells"])): bad.append("lists")
-    if not (np.array_equal(mine2["list_off"], mine["list_off"]) and np.array_equal(mine2["list_cells"], mine["list_cells"])): bad.append("lists-fast")
-    if not np.array_equal(ref["Ct"], mine["Ct"]): bad.append("Ct")
+    if not (np.array_equal(ref["list_off"], mine["list_off"]) and np.array_equal(ref["list_cells"], mine["list_cells"])):
+        bad.append("lists")
+    if not np.array_equal(ref["Ct"], mine["Ct"]):
+        bad.append("Ct")
+    if not mesh_is_mixed(case) and not (np.array_equal(fast["list_off"], mine["list_off"]) and np.array_equal(fast["list_cells"], mine["list_cells"])):
+        bad.append("lists of the fast builder")
     for kf in ("As", "Ts", "Fs"):
         a, b = ref[kf], mine[kf]
         okm = np.isfinite(a)
-        if not np.array_equal(okm, np.isfinite(b)): bad.append(kf + "-nan"); continue
-        if okm.any() and np.abs(a[okm] - b[okm]).max() > 1e-13 * max(1.0, np.abs(b[okm]).max()): bad.append((kf, float(np.abs(a[okm] - b[okm]).max())))
+        if not np.array_equal(okm, np.isfinite(b)):
+            bad.append(kf + " finiteness")
+        elif okm.any() and np.abs(a[okm] - b[okm]).max() > 1e-13 * max(1.0, np.abs(b[okm]).max()):
+            bad.append((kf, float(np.abs(a[okm] - b[okm]).max())))
     okm = np.isfinite(ref["FT"]) & np.isfinite(mine["FT"])
-    if okm.any() and np.abs(ref["FT"][okm] - mine["FT"][okm]).max() > 1e-11 * max(1.0, np.abs(mine["FT"][okm]).max()): bad.append("FT")
-    return bad, int(ref["pairs"]), specs
+    if okm.any() and np.abs(ref["FT"][okm] - mine["FT"][okm]).max() > 1e-11 * max(1.0, np.abs(mine["FT"][okm]).max()):
+        bad.append("FT")
+    return bad, int(ref["pairs"])
 
+
+def mesh_is_mixed(case):
+    return case["name"].startswith("mixed3d")      # there the fast (order-free) builder may differ by design
 
 
 @pytest.mark.parametrize("two_d", [False, True])
 def test_random_cases(two_d):
     pairs = 0
     for seed in range(200):
-        bad, p, specs = _one(seed, two_d)
-        assert not bad, (seed, two_d, bad, specs)
+        case = fuzz_cases.box_case(seed, two_d)
+        bad, p = _compare(case)
+        assert not bad, (case["name"], bad, case["specs"])
         pairs += p
     assert pairs > 5000
-
-
-# ---- non-box cells: jittered / rotated hex blocks, prisms, mixed polyhedra -----------------------------------------------------
-def _jittered_block(rng, n, two_d):
-    h = 1.0 / max(n)
-    t = Mesh.hex_block(n, (0.0, 0.0, -0.5 if two_d else 0.0), (h, h, 1.0 if two_d else h))
-    P = t.points.copy()
-    nx, ny, nz = n
-    idx = np.arange(len(P))
-    ix = idx % (nx + 1); iy = (idx // (nx + 1)) % (ny + 1); iz = idx // ((nx + 1) * (ny + 1))
-    interior = (ix > 0) & (ix < nx) & (iy > 0) & (iy < ny)
-    if two_d:
-        layer = (nx + 1) * (ny + 1)
-        jit = (rng.rand(layer, 2) - 0.5) * 0.5 * h
-        J = np.zeros((len(P), 3)); J[:layer, :2] = jit; J[layer:, :2] = jit
-    else:
-        interior &= (iz > 0) & (iz < nz)
-        J = (rng.rand(len(P), 3) - 0.5) * 0.4 * h
-    J[~interior] = 0.0
-    P += J
-    th = float(rng.choice([0.0, 0.3]))
-    c, s = math.cos(th), math.sin(th)
-    x, y = P[:, 0].copy(), P[:, 1].copy()
-    P[:, 0] = c * x - s * y; P[:, 1] = s * x + c * y
-    return Mesh.hex_block_with_points(n, P), h
-
-def _one_general(seed, kind):
-    rng = np.random.RandomState(seed)
-    two_d = kind in ("skew2d", "prism2d")
-    if kind == "skew2d":
-        mesh, h = _jittered_block(rng, (int(rng.randint(8, 20)), int(rng.randint(8, 20)), 1), True)
-    elif kind == "skew3d":
-        mesh, h = _jittered_block(rng, tuple(int(x) for x in rng.randint(5, 10, size=3)), False)
-    elif kind == "prism2d":
-        n = int(rng.randint(6, 16)); h = 0.25
-        mesh = cases.prism_mesh(n, n, (0.0, 0.0, -0.5), (h, h, 1.0))
-    else:
-        mesh = mixed_hex_prism_mesh(int(rng.randint(6, 10))); h = 1.0
-    k = int(rng.randint(1, 4))
-    specs = [_rand_shape2(rng, h) if two_d else _rand_shape3(rng, h) for _ in range(k)]
-    shapes = np.array([make_shape(t, **kw) for t, kw in specs])
-    S = make_solids(k)
-    lo, hi = mesh.bounds_min, mesh.bounds_max
-    for i in range(k):
-        p = rng.uniform(lo - 0.05 * (hi - lo), hi + 0.05 * (hi - lo))
-        if two_d: p[2] = 0.0
-        S[i]["pos"] = p
-        e = (0, 0, float(rng.uniform(-180, 180))) if two_d else tuple(float(x) for x in rng.uniform(-180, 180, size=3))
-        S[i]["quat"] = quat_from_euler_xyz_deg(e)
-        S[i]["vel"] = rng.standard_normal(3) * 0.3; S[i]["omega"] = rng.standard_normal(3) * 0.2
-    S["shape"] = np.arange(k)
-    U = rng.standard_normal((mesh.n_cells, 3))
-    o = Oracle(mesh, two_d)
-    mine = o.interact(shapes, S, U, 2.5e-3, 1.7, faithful=True)
-    seeds = np.array([o.nearest_cell(S[i]["pos"]) for i in range(k)], dtype=np.int32)
-    ref = ref_py.Reference(mesh).interact([ref_py.dict_text_from_record(r) for r in shapes], S, seeds, U, 2.5e-3, 1.7, two_d)
-    bad = []
-    if not (np.array_equal(ref["list_off"], mine["list_off"]) and np.array_equal(ref["list_cells"], mine["list_cells"])): bad.append("lists")
-    if not np.array_equal(ref["Ct"], mine["Ct"]): bad.append("Ct")
-    for kf in ("As", "Ts", "Fs"):
-        a, b = ref[kf], mine[kf]
-        okm = np.isfinite(a)
-        if not np.array_equal(okm, np.isfinite(b)): bad.append(kf + "-nan"); continue
-        if okm.any() and np.abs(a[okm] - b[okm]).max() > 1e-13 * max(1.0, np.abs(b[okm]).max()): bad.append((kf, float(np.abs(a[okm] - b[okm]).max())))
-    return bad, int(ref["pairs"]), specs
-
 
 
 @pytest.mark.parametrize("kind", ["skew2d", "skew3d", "prism2d", "mixed3d"])
 def test_random_cases_on_general_cells(kind):
     pairs = 0
     for seed in range(40):
-        bad, p, specs = _one_general(seed, kind)
-        assert not bad, (seed, kind, bad, specs)
+        case = fuzz_cases.general_case(seed, kind)
+        bad, p = _compare(case)
+        assert not bad, (case["name"], bad, case["specs"])
         pairs += p
     assert pairs > 1000
