@@ -43,8 +43,11 @@ using pointField = UList<vector>;
 using vectorField = UList<vector>;
 using scalarField = UList<scalar>;
 
-// VectorSpaceI.H: vs / mag(vs), zero for a vanishing vector
-inline vector normalised(const vector &v) { const scalar m = mag(v); return m > 1e-300 ? v / m : vector::zero; }
+// VectorSpaceI.H of the openfoam.org line (README.md:9 pins OpenFOAM 12): `return vs/mag(vs);` — no guard, so a vanishing vector
+// (two solids with the same centre, src/libcollision/collision.cpp:10) gives NaN, as in the oracle and the device code.  The
+// openfoam.com line returns Zero below ROOTVSMALL instead; the header cannot be checked here (OpenFOAM is not installed), and the
+// case is degenerate either way (no contact normal exists).
+inline vector normalised(const vector &v) { return v / mag(v); }
 
 class fvMesh {
 public:

@@ -12,6 +12,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import fuzz_cases  # noqa: E402
+from sdfibm_b200.mesh import Mesh  # noqa: E402
+from sdfibm_b200.shapes import make_shape, make_solids, quat_from_euler_xyz_deg  # noqa: E402
 from oracle import ref_py  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
 
@@ -76,3 +78,44 @@ def test_random_cases_on_general_cells(kind):
         assert not bad, (case["name"], bad, case["specs"])
         pairs += p
     assert pairs > 1000
+
+
+def test_random_collision_steps():
+    """UGrid pair order and contact forces: round solids, planes and shapes without a contact function, random and lattice
+    positions (exact ties in the cell hash, coincident centres -> NaN normals in both), three grid spacings per case including
+    HEAD's delta = -2.  9000 comparisons were run when this was written; 600 are kept."""
+    nbad, npairs = 0, 0
+    for seed in range(200):
+        rng = np.random.RandomState(seed)
+        two_d = bool(rng.randint(0,2))
+        n = (int(rng.randint(4,12)), int(rng.randint(4,12)), 1 if two_d else int(rng.randint(4,12)))
+        h = float(rng.choice([0.5, 1.0, 0.3]))
+        mesh = Mesh.hex_block(n, x0=(float(rng.choice([0.0,-1.0])), 0.0, -0.5 if two_d else 0.0), dx=(h,h,1.0 if two_d else h))
+        k = int(rng.randint(2, 40))
+        r = float(rng.uniform(0.2, 0.8))*h
+        round_t = "Circle" if two_d else "Sphere"
+        specs=[]
+        for i in range(k):
+            u = rng.rand()
+            if u < 0.75: specs.append((round_t, dict(radius=float(r*rng.choice([1.0,1.0,0.7])))))
+            elif u < 0.9: specs.append(("Plane", dict()))
+            else: specs.append(("Rectangle", dict(radiusa=r, radiusb=r)) if two_d else ("Ellipsoid", dict(radiusa=r, radiusb=r, radiusc=r*0.8)))
+        shapes = np.array([make_shape(t, **kw) for t, kw in specs])
+        S = make_solids(k)
+        lo, hi = mesh.bounds_min, mesh.bounds_max
+        P = rng.uniform(lo - 0.05*(hi-lo), hi + 0.05*(hi-lo), size=(k,3))
+        if rng.rand() < 0.3: P = lo + np.round((P-lo)/ (0.5*h)) * 0.5*h   # lattice positions: exact ties in the hash
+        if two_d: P[:,2] = 0.0
+        S["pos"] = P
+        for i in range(k):
+            S[i]["quat"] = quat_from_euler_xyz_deg((0,0,float(rng.choice([0,90,180,-90,rng.uniform(-180,180)]))) if two_d else tuple(float(x) for x in rng.choice([0,90,rng.uniform(-180,180)], size=3)))
+        S["shape"] = np.arange(k)
+        texts = [ref_py.shape_dict_text(t, **kw) for t, kw in specs]
+        o = Oracle(mesh, two_d)
+        for delta in (float(rng.uniform(0.5, 3.0))*r*2, -2.0, 2.0*r):
+            pairs, ft = o.collide(shapes, S, delta)
+            rp, rft = ref_py.ref_collide(mesh.bounds_min, mesh.bounds_max, delta, texts, S["pos"], S["quat"])
+            npairs += len(rp)
+            if not np.array_equal(pairs, rp) or not np.array_equal(ft, rft, equal_nan=True):
+                nbad += 1
+    assert nbad == 0 and npairs > 5000
