@@ -119,3 +119,86 @@ def test_random_collision_steps():
             if not np.array_equal(pairs, rp) or not np.array_equal(ft, rft, equal_nan=True):
                 nbad += 1
     assert nbad == 0 and npairs > 5000
+
+
+def _rnd_evolve_case(seed):
+    rng = np.random.RandomState(seed)
+    f = lambda lo, hi: float(rng.uniform(lo, hi))
+    v3 = lambda s=1.0: tuple(float(x) for x in s * rng.standard_normal(3))
+    unit = lambda: (lambda v: tuple(float(x) for x in v / np.linalg.norm(v)))(rng.standard_normal(3))
+    motions = {
+        "mask": dict(type="Motion01Mask", mask="b" + "".join(rng.choice(["0", "1"], size=6))),
+        "spin": dict(type="Motion000002", period=f(0.5, 5)),
+        "spinfree": dict(type="Motion110002", period=f(0.5, 5)),
+        "const": dict(type="Motion222000", u=f(-1, 1), v=f(-1, 1), w=f(-1, 1)),
+        "sine": dict(type="MotionSineDirectional", amplitude=f(0.1, 1), period=f(0.5, 3), direction=unit()),
+        "rotor": dict(type="MotionRotor", period=f(1, 5), radius=f(0.2, 1), theta0=f(0, 3), selfom=f(-2, 2)),
+        "gate": dict(type="MotionOpenClose"),
+    }
+    forces = {
+        "push": dict(type="Constant", force=v3(0.3), torque=v3(0.05)),
+        "spring": dict(type="Spring", pivot=v3(1.0), k=f(1, 10), l=f(0.1, 1.0)),
+        "mag": dict(type="Magnetic", direction=unit(), A=f(0.1, 1), w=f(0.5, 4)),
+    }
+    materials = {"heavy": dict(type="General", rho=f(2, 5)), "light": dict(type="General", rho=f(0.5, 1.5))}
+    n = int(rng.randint(2, 9))
+    solids = []
+    for i in range(n):
+        s = dict(shp_name=str(rng.choice(["sph", "elo", "box"])), mot_name=str(rng.choice(["free"] + list(motions))),
+                 mat_name=str(rng.choice(list(materials))), pos=v3(2.0), vel=v3(0.3), euler=tuple(float(x) for x in rng.uniform(-180, 180, 3)), omega=v3(0.5))
+        if rng.rand() < 0.5: s["for_name"] = str(rng.choice(list(forces)))
+        solids.append(s)
+    g = v3(5.0)
+    t0 = f(0.1, 6.0); dt = f(1e-3, 2e-2); steps = int(rng.randint(2, 7))
+    return solids, motions, forces, materials, g, t0, dt, steps
+
+
+def test_random_evolve_cases(tmp_path):
+    """SolidCloud::evolve with random plugin parameters (all seven motions, all three forcers, random masks / periods / pivots),
+    random states, gravity, step sizes and start times (MotionOpenClose's windows), a fluid force that changes every step:
+    oracle/host_oracle.py within 1e-15 of the reference's compiled Solid / libmotion / libforcer, and the shipped C++ façade
+    (through a solidDict it parses itself) BIT-IDENTICAL to it.  300 cases were run when this was written; 60 are kept."""
+    import shutil
+    import tempfile
+
+    import host_cases as hc
+    from oracle import host_oracle as ho
+    from sdfibm_b200 import hostapi
+
+    hostapi.load()
+    worst_o = worst_f = 0.0
+    for seed in range(60):
+        solids, motions, forces, materials, g, t0, dt, steps = _rnd_evolve_case(seed)
+        n = len(solids)
+        ref = hc.oracle_solids(solids, motions, forces, materials)
+        def sdict(name):
+            d = dict(hc.SHAPES[name]); return ref_py.shape_dict_text(d.pop("type"), com=d.pop("com", (0.0, 0.0, 0.0)), **d)
+        x, q, v, om = hc.state_arrays(ref)
+        times = t0 + dt * np.arange(1, steps + 1)
+        rng = np.random.RandomState(seed + 10000)
+        fluid = 0.05 * rng.standard_normal((steps, n, 6))
+        args = ([sdict(s["shp_name"]) for s in solids], [None if s["mot_name"] == "free" else motions[s["mot_name"]] for s in solids],
+                [forces[s["for_name"]] if "for_name" in s else None for s in solids], [materials[s["mat_name"]]["rho"] for s in solids], x, q, v, om, times, dt, 20, g)
+        out = ref_py.ref_evolve(*args, 1.1, fluid_ft=fluid)
+        for step in range(steps):
+            for i, s in enumerate(ref): s.ff, s.ft = tuple(fluid[step, i, :3]), tuple(fluid[step, i, 3:])
+            ho.evolve(ref, float(times[step]), dt, 20, g, 1.1)
+            mine = np.concatenate(hc.state_arrays(ref), axis=1)
+            worst_o = max(worst_o, np.abs(mine - out["traj"][step]).max() / max(1.0, np.abs(mine).max()))
+        # the façade (DEM mode: rho_f = 0, no fluid force)
+        d = tempfile.mkdtemp()
+        try:
+            path = hc.write_case(d, dict(on_fluid=0, on_twod=0, gravity=g), solids, motions=motions, forces=forces, materials=materials)
+            hostapi.load().sdfibm_host_reset_subiterations()
+            cloud = hostapi.HostCloud(path, d, Mesh.hex_block((2, 2, 2)), rho_fluid=1.0, start_time=t0)
+            st = cloud.solids()
+            out2 = ref_py.ref_evolve(args[0], args[1], args[2], args[3], st["pos"], st["quat"], st["vel"], st["omega"], times, dt, 20, g, 0.0)
+            for step in range(steps):
+                cloud.evolve(float(times[step]), dt)
+                got = cloud.solids()
+                mine = np.concatenate([got["pos"], got["quat"], got["vel"], got["omega"]], axis=1)
+                worst_f = max(worst_f, np.abs(mine - out2["traj"][step]).max() / max(1.0, np.abs(mine).max()))
+            cloud.close()
+        finally:
+            shutil.rmtree(d)
+    assert worst_o <= 1e-15 and worst_f == 0.0, (worst_o, worst_f)
