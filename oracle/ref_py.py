@@ -202,3 +202,17 @@ def ref_fix_internal(mesh, solids, Ct, U):
     if rc != 0:
         raise RuntimeError(f"ref_fix_internal failed ({rc})")
     return U
+
+
+def ref_state_rows(pos, quat, vel, omega, ft, time, two_d) -> str:
+    """The cloud.out rows the reference's operator<< / write2D (src/solid.cpp) print for these solids."""
+    lib = C.CDLL(LIB_PATH)
+    lib.ref_state_rows.restype = C.c_int64
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    pos, quat, vel, omega, ft = arr(pos), arr(quat), arr(vel), arr(omega), arr(ft)
+    buf = C.create_string_buffer(512 * len(pos) + 64)
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    rc = lib.ref_state_rows(len(pos), P(pos), P(quat), P(vel), P(omega), P(ft), C.c_double(time), int(bool(two_d)), buf, C.c_int64(len(buf)))
+    if rc < 0:
+        raise RuntimeError("ref_state_rows failed")
+    return buf.value.decode()

@@ -440,3 +440,26 @@ extern "C" int ref_mean_field(void *h, const char *shape_text, const double *pos
         return -2;
     }
 }
+
+// cloud.out rows (reference src/solidcloud.cpp:595-614 around operator<< / write2D of src/solid.cpp:5-29, compiled unmodified):
+// one row per solid, "time " + 18 (3-D) or 9 (2-D) columns, std::scientific at the default precision.
+namespace sdfibm { void write2D(std::ostream &os, const Solid &s); }
+extern "C" int64_t ref_state_rows(int n, const double *pos, const double *quat, const double *vel, const double *omega, const double *ft,
+                                  double time, int two_d, char *buf, int64_t cap) {
+    std::ostringstream os;
+    os << std::scientific;                                                           // statefile, solidcloud.cpp:235-236
+    for (int s = 0; s < n; ++s) {
+        Solid S(s, Foam::vector(pos[3 * s], pos[3 * s + 1], pos[3 * s + 2]),
+                Foam::quaternion(quat[4 * s], Foam::vector(quat[4 * s + 1], quat[4 * s + 2], quat[4 * s + 3])));
+        S.setVelocity(Foam::vector(vel[3 * s], vel[3 * s + 1], vel[3 * s + 2]));
+        S.setOmega(Foam::vector(omega[3 * s], omega[3 * s + 1], omega[3 * s + 2]));
+        S.setForce(Foam::vector(ft[6 * s], ft[6 * s + 1], ft[6 * s + 2]));
+        S.setTorque(Foam::vector(ft[6 * s + 3], ft[6 * s + 4], ft[6 * s + 5]));
+        if (two_d) { os << time << ' '; write2D(os, S); os << '\n'; }
+        else os << time << ' ' << S << '\n';
+    }
+    const std::string t = os.str();
+    if ((int64_t)t.size() + 1 > cap) return -1;
+    std::memcpy(buf, t.c_str(), t.size() + 1);
+    return (int64_t)t.size();
+}

@@ -279,11 +279,38 @@ def test_host_facade_evolve_against_the_reference(tmp_path):
                             [hc.FORCES[s["for_name"]] if "for_name" in s else None for s in solids],
                             [hc.MATERIALS[s["mat_name"]]["rho"] for s in solids], st["pos"], st["quat"], st["vel"], st["omega"],
                             times, dt, 20, meta["gravity"], 0.0)
+    rows = ""
     for step in range(n_steps):
         cloud.evolve(float(times[step]), dt)
         got = cloud.solids()
         mine = np.concatenate([got["pos"], got["quat"], got["vel"], got["omega"]], axis=1)
         err = np.abs(mine - out["traj"][step]).max()
         assert err <= 2e-14 * max(1.0, np.abs(mine).max()), (step, err)
+        # cloud.out: the rows the reference's own operator<< (src/solid.cpp:5-18, compiled unmodified) prints for this state
+        cloud.save_state()
+        rows += ref_py.ref_state_rows(got["pos"], got["quat"], got["vel"], got["omega"], cloud.forces()[0], float(times[step]), False)
     ft, _ = cloud.forces()
     assert np.abs(ft - out["FT"]).max() <= 1e-13 * max(1.0, np.abs(ft).max())
+    assert open(os.path.join(str(tmp_path), "cloud.out")).read() == rows and rows.count("\n") == n_steps * len(solids)
+
+
+def test_cloud_out_rows_in_two_d(tmp_path):
+    """The 1 + 9 column rows of a 2-D run against the reference's write2D (src/solid.cpp:20-29)."""
+    from sdfibm_b200 import hostapi
+
+    hc, solids = _evolve_case()
+    solids = [dict(s, pos=(s["pos"][0], s["pos"][1], 0.0), vel=(0.1, -0.2, 0.0), omega=(0.0, 0.0, 0.7), euler=(0.0, 0.0, 33.0 * (i + 1)))
+              for i, s in enumerate(solids[-2:])]                                  # the Circle and the Circle_Tail
+    path = hc.write_case(tmp_path, dict(on_fluid=0, on_twod=1, gravity=(0.0, -9.81, 0.0)), solids)
+    hostapi.load().sdfibm_host_reset_subiterations()
+    cloud = hostapi.HostCloud(path, str(tmp_path), Mesh.hex_block((4, 4, 1), (-2, -2, -0.5), (1.0, 1.0, 1.0)), rho_fluid=1.0, start_time=0.25)
+    rows = ""
+    for step in range(3):
+        t = 0.25 + 0.01 * (step + 1)
+        cloud.evolve(t, 0.01)
+        cloud.save_state()
+        got = cloud.solids()
+        rows += ref_py.ref_state_rows(got["pos"], got["quat"], got["vel"], got["omega"], cloud.forces()[0], t, True)
+    text = open(os.path.join(str(tmp_path), "cloud.out")).read()
+    assert text == rows and all(len(r.split()) == 10 for r in text.strip().split("\n"))
+    hostapi.load().sdfibm_host_reset_subiterations()
