@@ -216,3 +216,22 @@ def ref_state_rows(pos, quat, vel, omega, ft, time, two_d) -> str:
     if rc < 0:
         raise RuntimeError("ref_state_rows failed")
     return buf.value.decode()
+
+
+def ref_shape_props(dict_text, pos=None, quat=None, points=None):
+    """Mass properties of a shape from the reference's own constructor and, optionally, Solid::phi01 / Solid::phi at world points."""
+    lib = C.CDLL(LIB_PATH)
+    props = np.zeros(12)
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    n = 0 if points is None else len(points)
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    pos, quat, pts = arr(pos if n else np.zeros(3)), arr(quat if n else [1.0, 0, 0, 0]), arr(points if n else np.zeros((1, 3)))
+    inside, phi = np.zeros(max(n, 1), dtype=np.uint8), np.zeros(max(n, 1))
+    rc = lib.ref_shape_props(dict_text.encode(), P(props), P(pos), P(quat), n, P(pts), P(inside), P(phi))
+    if rc < 0:
+        raise RuntimeError(f"ref_shape_props failed ({rc})")
+    out = dict(volume=props[0], volumeINV=props[1], radiusB=props[2], moi=props[3:6].copy(), moiINV=props[6:9].copy(), com=props[9:12].copy(),
+               finite=bool(rc))
+    if n:
+        out["inside"], out["phi"] = inside[:n].astype(bool), phi[:n]
+    return out

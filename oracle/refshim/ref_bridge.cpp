@@ -463,3 +463,31 @@ extern "C" int64_t ref_state_rows(int n, const double *pos, const double *quat, 
     std::memcpy(buf, t.c_str(), t.size() + 1);
     return (int64_t)t.size();
 }
+
+// Mass properties and point evaluation of ONE shape as the reference's own constructor / members give them (src/libshape/*.h):
+// props[12] = volume, volumeINV, radiusB, moi diag (3), moiINV diag (3), com (3); returns finite (1 / 0) or < 0.
+// phi01 / phi at n_pts world points for a solid at (pos, quat) go through Solid::phi01 / Solid::phi (src/solid.h:110-119).
+extern "C" int ref_shape_props(const char *shape_text, double *props, const double *pos, const double *quat, int n_pts, const double *pts,
+                               unsigned char *inside, double *phi) {
+    try {
+        Foam::dictionary d = dict_of(shape_text);
+        std::unique_ptr<IShape> sh = ShapeFactory::create(std::string(d.lookup("type")), d);
+        props[0] = sh->m_volume; props[1] = sh->m_volumeINV; props[2] = sh->getRadiusB();
+        props[3] = sh->m_moi[0]; props[4] = sh->m_moi[4]; props[5] = sh->m_moi[8];
+        props[6] = sh->m_moiINV[0]; props[7] = sh->m_moiINV[4]; props[8] = sh->m_moiINV[8];
+        props[9] = sh->m_com.x(); props[10] = sh->m_com.y(); props[11] = sh->m_com.z();
+        if (n_pts > 0) {
+            Solid S(0, Foam::vector(pos[0], pos[1], pos[2]), Foam::quaternion(quat[0], Foam::vector(quat[1], quat[2], quat[3])));
+            S.setShape(sh.get());
+            for (int i = 0; i < n_pts; ++i) {
+                const Foam::vector p(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+                inside[i] = S.phi01(p) ? 1 : 0;
+                phi[i] = S.phi(p);
+            }
+        }
+        return sh->finite ? 1 : 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "ref_shape_props: %s\n", e.what());
+        return -2;
+    }
+}

@@ -202,3 +202,56 @@ def test_random_evolve_cases(tmp_path):
         finally:
             shutil.rmtree(d)
     assert worst_o <= 1e-15 and worst_f == 0.0, (worst_o, worst_f)
+
+
+def test_random_shapes_mass_properties_and_point_evaluation(tmp_path):
+    """The nine shapes with random parameters and com offsets: volume, volumeINV, radiusB, moments (the façade's shape plugins, read
+    from a solidDict) and phi01 / phi at random world points for a random pose (the ONE device / host evaluation switch,
+    csrc/device_math.cuh, through the façade and through the oracle) against the reference's own shape constructors and
+    Solid::phi01 / Solid::phi — bit for bit."""
+    import host_cases as hc
+    from oracle.oracle_py import eval_points
+    from sdfibm_b200 import hostapi
+
+    rng = np.random.RandomState(4)
+    f = lambda lo, hi: float(rng.uniform(lo, hi))
+    com = lambda two_d: (f(-0.1, 0.1), f(-0.1, 0.1), 0.0 if two_d else f(-0.1, 0.1))
+    n_checked = 0
+    for rep in range(12):
+        shapes = {
+            "circ": dict(type="Circle", radius=f(0.1, 1), com=com(True)),
+            "sph": dict(type="Sphere", radius=f(0.1, 1), com=com(False)),
+            "ell": dict(type="Ellipse", radiusa=f(0.1, 1), radiusb=f(0.1, 1), com=com(True)),
+            "elo": dict(type="Ellipsoid", radiusa=f(0.1, 1), radiusb=f(0.1, 1), radiusc=f(0.1, 1)),
+            "rect": dict(type="Rectangle", radiusa=f(0.1, 1), radiusb=f(0.1, 1), com=com(True)),
+            "box": dict(type="Box", radiusa=f(0.1, 1), radiusb=f(0.1, 1), radiusc=f(0.1, 1), com=com(False)),
+            "tail": dict(type="Circle_Tail", radius=f(0.1, 0.6), ratio=f(0.5, 3), thickness=f(0.02, 0.2), com=com(True)),
+            "twotail": dict(type="Circle_TwoTail", radius=f(0.1, 0.6), ratio=f(0.5, 3), thickness=f(0.02, 0.2), com=com(True)),
+            "plane": dict(type="Plane"),
+        }
+        d = tmp_path / f"r{rep}"
+        d.mkdir()
+        path = hc.write_case(d, dict(on_fluid=0, on_twod=0, gravity=(0.0, 0.0, 0.0)), [], shapes=shapes)
+        pos = rng.uniform(-0.3, 0.3, 3)
+        q = rng.standard_normal(4)
+        q /= np.linalg.norm(q)
+        pts = rng.uniform(-1.5, 1.5, size=(500, 3))
+        pts[:50] = pos                                        # the centre itself (ellipse / ellipsoid: -1/0)
+        for name, spec in shapes.items():
+            k = dict(spec)
+            text = ref_py.shape_dict_text(k.pop("type"), com=k.pop("com", (0.0, 0.0, 0.0)), **k)
+            ref = ref_py.ref_shape_props(text, pos, q, pts)
+            rec, props = hostapi.shape_record(path, name)
+            assert props["volume"] == ref["volume"] and props["volumeINV"] == ref["volumeINV"] and props["radiusB"] == ref["radiusB"], name
+            assert bool(rec["finite"]) == ref["finite"] and np.array_equal(rec["com"], ref["com"]), name
+            assert np.array_equal(np.asarray(props["moi"]), ref["moi"]), name
+            inside, phi = hostapi.shape_eval(path, name, pos, q, pts)
+            assert np.array_equal(inside, ref["inside"]) and np.array_equal(phi, ref["phi"], equal_nan=True), name
+            from sdfibm_b200.shapes import make_solids
+
+            S = make_solids(1)
+            S[0]["pos"], S[0]["quat"] = pos, q
+            oi, op = eval_points(np.array([rec]), S[0], pts)
+            assert np.array_equal(oi, ref["inside"]) and np.array_equal(op, ref["phi"], equal_nan=True), name
+            n_checked += 1
+    assert n_checked == 108
