@@ -97,7 +97,7 @@ def build_reference_oracle(force: bool = False, reference: str = "/root/referenc
         return None
     d = os.path.join(ROOT, "oracle")
     lib = os.path.join(d, "_ref", "libsdfibm_ref.so")
-    deps = [os.path.join(d, "refshim", f) for f in ("ref_bridge.cpp", "foam_shim.h")] + [os.path.join(HERE, "host", "foamlite.h")]
+    deps = [os.path.join(d, "refshim", f) for f in ("ref_bridge.cpp", "foam_shim.h")] + [os.path.join(HERE, "host", "foamlite.h"), os.path.join(d, "Makefile")]
     if force or not os.path.exists(lib) or max(os.path.getmtime(x) for x in deps) > os.path.getmtime(lib):
         r = subprocess.run(["make", "-C", d, "-B", "ref", f"REFERENCE={reference}"], capture_output=True, text=True)
         if r.returncode != 0:
