@@ -72,3 +72,71 @@ def read_polymesh(case_dir: str):
         owner=read_labels(os.path.join(d, "owner")),
         neighbour=read_labels(os.path.join(d, "neighbour")),
     )
+
+
+# ---- writers (binary, the layout the readers above take) and the decomposed-case layout -----------------------------------------
+def _header(cls: str, obj: str, location: str) -> bytes:
+    return (f"FoamFile\n{{\n    version     2.0;\n    format      binary;\n    class       {cls};\n"
+            f"    location    \"{location}\";\n    object      {obj};\n}}\n\n").encode()
+
+
+def _write_list(path: str, cls: str, obj: str, location: str, payloads) -> None:
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(_header(cls, obj, location))
+        for count, raw in payloads:
+            f.write(f"\n{count}\n(".encode() + raw + b")\n")
+
+
+def write_polymesh(case_dir: str, points, face_off, face_pts, owner, neighbour, location: str = "constant/polyMesh") -> None:
+    """``case_dir/constant/polyMesh/{points,faces,owner,neighbour}`` in OpenFOAM's binary format (faces as a faceCompactList)."""
+    d = os.path.join(case_dir, "constant", "polyMesh")
+    points = np.ascontiguousarray(points, dtype="<f8")
+    face_off, face_pts = np.ascontiguousarray(face_off, dtype="<i4"), np.ascontiguousarray(face_pts, dtype="<i4")
+    owner, neighbour = np.ascontiguousarray(owner, dtype="<i4"), np.ascontiguousarray(neighbour, dtype="<i4")
+    _write_list(os.path.join(d, "points"), "vectorField", "points", location, [(len(points), points.tobytes())])
+    _write_list(os.path.join(d, "faces"), "faceCompactList", "faces", location,
+                [(len(face_off), face_off.tobytes()), (len(face_pts), face_pts.tobytes())])
+    _write_list(os.path.join(d, "owner"), "labelList", "owner", location, [(len(owner), owner.tobytes())])
+    _write_list(os.path.join(d, "neighbour"), "labelList", "neighbour", location, [(len(neighbour), neighbour.tobytes())])
+
+
+def write_labels(path: str, obj: str, labels, location: str = "constant/polyMesh") -> None:
+    labels = np.ascontiguousarray(labels, dtype="<i4")
+    _write_list(path, "labelIOList", obj, location, [(len(labels), labels.tobytes())])
+
+
+def write_scalar_field(path: str, obj: str, values) -> None:
+    """A volScalarField with a nonuniform binary internalField and no boundary entries (what read_scalar_field takes)."""
+    values = np.ascontiguousarray(values, dtype="<f8")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(_header("volScalarField", obj, os.path.basename(os.path.dirname(path))))
+        f.write(b"dimensions      [0 0 0 0 0 0 0];\n\ninternalField   nonuniform List<scalar> ")
+        f.write(f"\n{len(values)}\n(".encode() + values.tobytes() + b");\n\nboundaryField\n{\n}\n")
+
+
+def read_decomposed(case_dir: str):
+    """A `decomposePar` case: one entry per ``processorK`` directory, in rank order, with the subdomain's polyMesh in
+    LOCAL numbering and its ``cellProcAddressing`` (local cell -> global cell), which is all the multi-GPU path needs: cells are
+    partitioned, solids replicated, no halo (every per-cell result depends only on that cell's geometry and U)."""
+    ranks = []
+    k = 0
+    while os.path.isdir(os.path.join(case_dir, f"processor{k}")):
+        d = os.path.join(case_dir, f"processor{k}")
+        pm = read_polymesh(d)
+        pm["cell_addressing"] = read_labels(os.path.join(d, "constant", "polyMesh", "cellProcAddressing"))
+        ranks.append(pm)
+        k += 1
+    if not ranks:
+        raise FileNotFoundError(f"no processor0 directory under {case_dir}")
+    return ranks
+
+
+def reconstruct_cells(ranks, fields, n_cells_total: int) -> np.ndarray:
+    """reconstructPar for cell data: scatter each rank's field through its cellProcAddressing into the global numbering."""
+    first = np.asarray(fields[0])
+    out = np.zeros((n_cells_total,) + first.shape[1:], dtype=first.dtype)
+    for pm, f in zip(ranks, fields):
+        out[pm["cell_addressing"]] = f
+    return out
