@@ -116,7 +116,24 @@ def build_case(args, rank, world):
     wl = args.workload
     if wl == "auto":
         wl = "c4" if world == 1 else "c5"
-    if wl == "c4":
+    if wl in ("c1", "c2", "c3", "c3b"):
+        # BASELINE configs 1-3 (latency-bound; ms/step is the figure of interest): the reference's own example set-ups
+        if world != 1:
+            raise SystemExit(f"workload {wl} is single-GPU")
+        if wl == "c1":
+            case = cases.case_c1()
+            desc = {"workload": "C1: flow_past_cylinder central block 120x120x1 (dx 0.1), 1 fixed Circle r=1 (2-D)"}
+        elif wl == "c2":
+            case = cases.case_c2(with_walls=True)
+            desc = {"workload": "C2: sedimentation 400x400x1 (dx 0.02), 100 Circle r=0.15 + 4 wall planes (2-D)"}
+        elif wl == "c3":
+            pts = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "m2_points.npz"))["points"]
+            case = cases.case_c3(pts)
+            desc = {"workload": "C3: falling_ellipse on the shipped 100x200x1 mesh, Ellipse 0.3/0.15 at -45 deg (2-D)"}
+        else:
+            case = cases.case_skewed_2d()
+            desc = {"workload": "C3b: rotated + jittered 60x60x1 quad block (stand-in for the taylor_couette O-grid), Circle r=0.3 + Circle_TwoTail"}
+    elif wl == "c4":
         n = args.n or 256
         scale = n / 256.0
         n_side = max(1, int(round(22 * scale)))
@@ -251,7 +268,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c4", "c5"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c3b", "c4", "c5"],
+                    help="auto = the contract's line (C4 at N=1, C5 at N>1); c1..c3b = the reference's small example set-ups (ms/step)")
     ap.add_argument("--cells-per-side", dest="n", type=int, default=0, help="cells per side (scaled-down runs)")
     ap.add_argument("--solids", type=int, default=0)
     ap.add_argument("--cpu-solids", type=int, default=256, help="solids per CPU-baseline sample")
