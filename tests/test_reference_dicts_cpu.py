@@ -62,3 +62,30 @@ def test_taylor_couette_dict(tmp_path):
     c.evolve(1.0, 1e-3)                                                            # no gravity, no fluid torque yet: at rest
     s = c.solids()
     assert np.array_equal(s["pos"][0], (0.0, 0.0, 0.0)) and np.array_equal(s["omega"][0], (0.0, 0.0, 0.0))
+
+
+def test_g1_case_data_equal_the_reference_tool_vof_dict():
+    """cases.g1_solids() — the 14 solids behind the hard golden G1 (tests/test_oracle_golden.py, test_gpu_parity.py) — were typed in
+    from tool_vof/example/solidDict; here they are checked against that file itself: shape records through the façade's own shape
+    plugins, positions and Euler angles through a minimal reading of the `solids` block."""
+    import re
+
+    from sdfibm_b200 import cases
+    from sdfibm_b200.shapes import quat_from_euler_xyz_deg
+
+    path = os.path.join(REF, "tool_vof/example/solidDict")
+    text = re.sub(r"//.*", "", open(path).read())
+    shapes, S = cases.g1_solids()
+    names = ["circle1", "circle_tail1", "ellipse1", "rectangle1", "plane1"]          # the order of g1_solids()' shape table
+    for i, name in enumerate(names):
+        rec, _ = hostapi.shape_record(path, name)
+        for f in ("tag", "finite", "radiusB"):
+            assert rec[f] == shapes[i][f], (name, f)
+        assert np.array_equal(rec["p"], shapes[i]["p"]) and np.array_equal(rec["com"], shapes[i]["com"]), name
+    block = text[text.index("solids"):]
+    entries = re.findall(r"shp_name\s+(\w+)\s*;\s*pos\s*\(([^)]*)\)\s*;\s*euler\s*\(([^)]*)\)\s*;", block)
+    assert len(entries) == len(S) == 14
+    for i, (shp, pos, euler) in enumerate(entries):
+        assert names.index(shp) == S[i]["shape"], i
+        assert np.array_equal(np.array(pos.split(), dtype=float), S[i]["pos"]), i
+        assert np.allclose(quat_from_euler_xyz_deg(tuple(float(x) for x in euler.split())), S[i]["quat"], rtol=0, atol=0), i
