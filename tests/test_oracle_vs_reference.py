@@ -314,3 +314,20 @@ def test_cloud_out_rows_in_two_d(tmp_path):
     text = open(os.path.join(str(tmp_path), "cloud.out")).read()
     assert text == rows and all(len(r.split()) == 10 for r in text.strip().split("\n"))
     hostapi.load().sdfibm_host_reset_subiterations()
+
+
+def test_compiled_reference_reproduces_its_own_shipped_golden(m1_points, g1_alpha):
+    """The checker of the checker, checked: the reference's compiled classes behind the OpenFOAM stand-in (oracle/refshim +
+    foamlite vector / quaternion / dictionary) on the shipped mesh M1 with the 14 solids of tool_vof/example/solidDict reproduce the
+    field G1 that the REAL OpenFOAM build of the reference wrote (tool_vof/example/0/alpha.water) to 1e-15 — so the stand-in's
+    arithmetic (quaternion sandwich, Euler angles, mesh geometry) is the one OpenFOAM used."""
+    from sdfibm_b200 import cases
+
+    case = cases.case_g1(m1_points)
+    mesh, S, shapes = case["mesh"], case["solids"], case["shapes"]
+    o = Oracle(mesh, True)
+    seeds = [o.nearest_cell(S[i]["pos"]) for i in range(len(S))]
+    texts = [ref_py.dict_text_from_record(shapes[int(k)]) for k in S["shape"]]
+    off, cells, As = ref_py.ref_interact(mesh, texts, S["pos"], S["quat"], seeds, True)
+    assert np.abs(As - g1_alpha).max() <= 1e-15
+    assert np.array_equal(As > 0, g1_alpha > 0) and (g1_alpha > 0).sum() == 13862
