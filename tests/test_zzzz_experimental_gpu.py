@@ -1,4 +1,4 @@
-"""Opt-in experimental kernel variants (not on the default path; this file sorts last on purpose).
+"""Opt-in experimental kernel variants (not on the default path; this file sorts last on purpose: a faulting experimental kernel must not poison the CUDA context of any other test).
 
 SDFIBM_SYNTH_FACES=1: k_heavy_hex<., true> forms the face centre / area vector of box cells from the staged vertices instead of
 fetching face records.  Written at the end of round 1 with no GPU time left: compiled, never run.  The test is
