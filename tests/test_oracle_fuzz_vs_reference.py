@@ -1,6 +1,6 @@
 """Randomised oracle-vs-reference comparison on the cases of tests/fuzz_cases.py.  The oracle (both its faithful and its fast list
 builder) against the reference's own compiled classes (oracle/_ref): lists and Ct identical, As / Ts / Fs to 1e-13, force / torque
-to 1e-11.  8000 box-cell and 1200 general-cell cases were run when this was written (no discrepancy); the test keeps 400 + 160."""
+to 1e-11.  68 000 box-cell and 7 200 general-cell cases were run when this was written (no discrepancy); the test keeps 400 + 160."""
 import os
 import sys
 
