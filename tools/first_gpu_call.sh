@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a round (one B200):  gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
 # Everything lands in gpurun_out/; nothing here is a bench value if it ran under ncu.
-#   1. GPU test suite (incl. test_gpu_vs_reference, test_zzz_gpu_fuzz, the experimental variants as xfail / XPASS)
+#   1. GPU test suite (incl. test_zy_gpu_vs_reference, test_zzz_gpu_fuzz, the experimental variants as xfail / XPASS)
 #   2. the contract bench line (C4) + the reference arm
 #   3. the experimental k_heavy_hex variants (SDFIBM_SYNTH_FACES=1 | 2): device-resident step only
 #   4. the small BASELINE configurations C1..C3b (ms/step)
