@@ -9,7 +9,7 @@
 set -u
 mkdir -p gpurun_out
 R=${ROUND_TAG:-r02}
-timeout 900 python -m pytest tests -m gpu -q -rxX -x > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${R}_pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q -rxX > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${R}_pytest_gpu.log
 tail -15 gpurun_out/${R}_pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench_c4.json 2> gpurun_out/${R}_bench_c4.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference_arm.json 2>> gpurun_out/${R}_bench_c4.err
