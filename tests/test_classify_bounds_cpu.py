@@ -1,0 +1,76 @@
+"""Host-side check of the bound behind k_classify's fp32 three-way test (csrc/interact_kernels.cuh `test32`, the record layout of
+`k_bin_sort_entries`, `k_cell_radius`, `k_cell_box`, `k_cc32`): the same float32 operations in numpy (the device code is built with
+-fmad=false, so separate multiplies and adds round the same way) on box-cell meshes with several spacings / origins (one ~100 cell
+sizes away from the origin) and spheres at random, vertex-aligned and centre-aligned positions with random / integer / half-integer
+radii.  "Certainly outside" must mean no vertex is inside, "certainly ALL_INSIDE" that all eight are — by the exact fp64 predicate
+the oracle uses — and the test should stay sharp (few undecided cells that are in fact uniform).  18 000 sphere placements were run
+when this was written (no violation; 1 % of the near-surface cells undecided-but-uniform); the test keeps 360."""
+import numpy as np
+
+from oracle.oracle_py import eval_points
+from sdfibm_b200.mesh import Mesh
+from sdfibm_b200.shapes import make_shape, make_solids
+
+f32 = np.float32
+def _ru(x):
+    y = f32(x)
+    return np.nextafter(y, f32(np.inf)) if float(y) < x else y
+def _rd(x):
+    y = f32(x)
+    return np.nextafter(y, f32(-np.inf)) if float(y) > x else y
+REL = 1e-6
+def _run(seed):
+    rng = np.random.RandomState(seed)
+    n = tuple(int(x) for x in rng.randint(5, 14, size=3)); h = float(rng.choice([0.1, 0.25, 1.0, 0.3]))
+    x0 = tuple(float(x) for x in rng.choice([0.0, -1.0, 0.37, 100.3], size=3))
+    dx = (h, h * float(rng.choice([1.0, 0.8])), h * float(rng.choice([1.0, 1.3])))
+    mesh = Mesh.hex_block(n, x0=x0, dx=dx)
+    lo, hi = mesh.bounds_min, mesh.bounds_max
+    o = 0.5 * (lo + hi)
+    half_ext = float(np.max(0.5 * (hi - lo)))
+    cp = mesh.cp.reshape(-1, 8)
+    dcell = mesh.points[cp] - mesh.cc[:, None, :]
+    r3 = np.sqrt((dcell ** 2).sum(axis=2).max(axis=1))
+    r3f = np.array([np.nextafter(_ru(v * (1.0 + REL)), f32(np.inf)) for v in r3], dtype=f32)
+    rxy = np.sqrt((dcell[:, :, :2] ** 2).sum(axis=2).max(axis=1))
+    rxyf = np.array([np.nextafter(_ru(v * (1.0 + REL)), f32(np.inf)) for v in rxy], dtype=f32)
+    rad_max = float(max(r3f.max(), rxyf.max()))
+    hbox = np.abs(dcell).max(axis=1)                         # half extents per cell
+    hb = np.array([[_ru(v * (1.0 + REL)) for v in row] for row in hbox], dtype=f32)
+    p = (mesh.cc - o).astype(f32)
+    viol = 0; decided = 0; total = 0
+    for k in range(6):
+        r = float(rng.choice([rng.uniform(0.3, 4.0) * h, rng.randint(1, 4) * h, rng.randint(1, 8) * 0.5 * h]))
+        pos = rng.uniform(lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo))
+        mode = rng.randint(0, 3)
+        if mode == 1: pos = lo + np.round((pos - lo) / np.array(dx)) * np.array(dx)
+        if mode == 2: pos = lo + (np.floor((pos - lo) / np.array(dx)) + 0.5) * np.array(dx)
+        shapes = np.array([make_shape("Sphere", radius=r)])
+        S = make_solids(1); S[0]["pos"] = pos
+        inside, _ = eval_points(shapes, S[0], mesh.points)
+        n_in = inside[cp].sum(axis=1)
+        r_out = (r + 0.0) * (1.0 + REL) + 1e-300
+        r_in = max(0.0, r * (1.0 - REL))
+        slack = 4e-6 * (half_ext + r_out + rad_max)
+        ro, ri = _ru(r_out + slack), _rd(r_in - slack)
+        e = (pos - o).astype(f32)
+        a = np.abs(p - e)                                     # float32 ops
+        fx = a + hb
+        nx = a - hb
+        N2 = nx[:, 0] * nx[:, 0] + nx[:, 1] * nx[:, 1] + nx[:, 2] * nx[:, 2]
+        F2 = fx[:, 0] * fx[:, 0] + fx[:, 1] * fx[:, 1] + fx[:, 2] * fx[:, 2]
+        cls = np.where(N2 > ro * ro, 0, np.where((ri > 0) & (F2 < ri * ri), 1, 2))
+        viol += int(((cls == 0) & (n_in > 0)).sum() + ((cls == 1) & (n_in < 8)).sum())
+        # how sharp is it: undecided cells that are in fact all-out or all-in
+        near = (np.sqrt(((mesh.cc - pos) ** 2).sum(axis=1)) < r + 2 * r3.max())
+        decided += int(((cls == 2) & ((n_in == 0) | (n_in == 8)) & near).sum()); total += int(near.sum())
+    return viol, decided, total
+
+
+def test_fp32_three_way_test_is_conservative_and_sharp():
+    V = D = T = 0
+    for seed in range(60):
+        v, d, t = _run(seed)
+        V, D, T = V + v, D + d, T + t
+    assert V == 0
+    assert T > 20000 and D < 0.03 * T
