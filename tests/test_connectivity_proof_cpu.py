@@ -1,0 +1,46 @@
+"""The geometric claim behind `conn_proven` (csrc/sdfibm_cuda.cu, k_solid_prepare): on a complete lattice of identical boxes, a ball
+(disc) whose radius exceeds the cell diagonal by a factor 1 + 1e-5 and that lies r + one cell inside the mesh has a FACE-CONNECTED
+set of vertex-inside cells — so the reference's flood fill returns all of them and the connectivity certificate can be skipped.
+Checked against the oracle's real flood fill on anisotropic lattices (aspect 0.3 .. 2), radii from 1e-7 above the bound upwards,
+random and exactly vertex- / centre-aligned centres, 2-D and 3-D.  3 000 cases were run when this was written; 300 are kept."""
+import numpy as np
+
+from oracle.oracle_py import Oracle, eval_points
+from sdfibm_b200.mesh import Mesh
+from sdfibm_b200.shapes import make_shape, make_solids
+
+
+def test_ball_cell_sets_on_box_lattices_are_face_connected():
+    bad = n_cases = tight = 0
+    for seed in range(300):
+        rng = np.random.RandomState(seed)
+        two_d = bool(rng.randint(0, 2))
+        dx = np.array([1.0, float(rng.uniform(0.3, 2.0)), 1.0 if two_d else float(rng.uniform(0.3, 2.0))]) * float(rng.choice([0.1, 1.0, 0.37]))
+        hh = 0.5 * dx
+        diag = 2.0 * np.sqrt(hh[0] ** 2 + hh[1] ** 2 + (0.0 if two_d else hh[2] ** 2))
+        r = diag * (1.0 + 1e-5) * float(rng.choice([1.0000001, 1.001, rng.uniform(1.0, 1.6)]))
+        nd = 2 if two_d else 3
+        need = [int(np.ceil(2 * (r + 2.0 * hh[d] * (1.0 + 1e-5)) / dx[d])) + 2 for d in range(nd)]
+        n = tuple(need[d] + int(rng.randint(0, 3)) for d in range(nd)) + ((1,) if two_d else ())
+        x0 = (float(rng.choice([0.0, -3.0, 17.3])), 0.0, -0.5 * dx[2] if two_d else 0.0)
+        mesh = Mesh.hex_block(n, x0=x0, dx=tuple(dx))
+        lo, hi = mesh.bounds_min, mesh.bounds_max
+        marg = r + 2.0 * hh * (1.0 + 1e-5)
+        pos = np.array([rng.uniform(lo[d] + marg[d] * (1 + 1e-9), hi[d] - marg[d] * (1 + 1e-9)) if d < nd else 0.0 for d in range(3)])
+        if rng.rand() < 0.4:   # vertex- or centre-aligned along some axes (exact ties)
+            for d in range(nd):
+                if rng.rand() < 0.6:
+                    cand = lo[d] + np.round((pos[d] - lo[d]) / (0.5 * dx[d])) * 0.5 * dx[d]
+                    if lo[d] + marg[d] < cand < hi[d] - marg[d]: pos[d] = cand
+        shapes = np.array([make_shape("Circle" if two_d else "Sphere", radius=r)])
+        S = make_solids(1); S[0]["pos"] = pos
+        inside, _ = eval_points(shapes, S[0], mesh.points)
+        cp = mesh.cp.reshape(-1, 8)
+        members = np.nonzero(inside[cp].any(axis=1))[0]
+        res = Oracle(mesh, two_d).interact(shapes, S, np.zeros((mesh.n_cells, 3)), 1.0, 1.0, faithful=True)
+        got = np.sort(res["list_cells"])
+        n_cases += 1
+        tight += r < diag * 1.002
+        if not np.array_equal(got, members):
+            bad += 1
+    assert bad == 0 and n_cases == 300 and tight > 100
