@@ -29,11 +29,15 @@ def _finish(name, mesh, two_d, specs, S, rng):
 
 
 def _rand_shape3(rng, h):
+    if rng.rand() < 0.2:   # a thin slab: its vertex-inside cell set is usually NOT face connected (flood-fill component only)
+        return "Box", dict(radiusa=float(rng.uniform(0.08, 0.4) * h), radiusb=float(rng.uniform(2, 5) * h), radiusc=float(rng.uniform(0.5, 3) * h))
     t = rng.choice(["Sphere", "Ellipsoid", "Box"])
     r = lambda: float(rng.choice([rng.uniform(0.2, 4.0) * h, rng.randint(1, 4) * h, rng.randint(1, 8) * 0.5 * h]))
     if t == "Sphere": return t, dict(radius=r())
     return t, dict(radiusa=r(), radiusb=r(), radiusc=r())
 def _rand_shape2(rng, h):
+    if rng.rand() < 0.2:   # a needle
+        return "Rectangle", dict(radiusa=float(rng.uniform(2, 6) * h), radiusb=float(rng.uniform(0.08, 0.4) * h))
     t = rng.choice(["Circle", "Ellipse", "Rectangle", "Circle_Tail", "Circle_TwoTail", "Plane"])
     r = lambda: float(rng.choice([rng.uniform(0.2, 5.0) * h, rng.randint(1, 5) * h, rng.randint(1, 8) * 0.5 * h]))
     if t == "Circle": return t, dict(radius=r())
