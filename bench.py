@@ -110,6 +110,14 @@ def algorithmic_bytes(n_cells, counts, n_solids):
     return 48 * n_cells + 112 * P + 216 * Pb + 176 * n_solids
 
 
+L2_NOTE = "inputs larger than L2 (fields + mesh arrays of one step >> 126 MB); no explicit flush"
+
+
+def make_config(desc):
+    """`config` of the JSON line: the same keys and values in both arms (ours and --impl reference)."""
+    return dict(desc, l2=L2_NOTE)
+
+
 def build_case(args, rank, world):
     from sdfibm_b200 import cases
 
@@ -219,14 +227,17 @@ def cpu_baseline_sample(case, n_sample, faithful=True, repeats=1, indices=None, 
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm (oracle port; the reference cannot be compiled here,
-    DESIGN.md) on the host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of interact() (its compiled classes, oracle/_ref; the oracle
+    port where that library is absent) on the host cores, a bounded sample of the workload per step."""
     if rank != 0:
         return
     wl, case, desc = build_case(args, 0, 1 if args.workload != "c5" and world == 1 else world)
-    # bounded sample: the per-solid cost of the faithful algorithm is O(nCells) (a fresh CELL_TYPE array per solid, a whole-mesh
-    # scan for every solid that has no vertex-inside cell on this rank), i.e. seconds per solid on a C5 block: probe two solids,
-    # then take as many per step as fit ~100 s for the whole run (at most --cpu-solids)
+    # Bounded sample: the per-solid cost of the faithful algorithm is O(nCells) (a fresh CELL_TYPE array per solid, a whole-mesh
+    # scan for every solid that has no vertex-inside cell on this rank), i.e. seconds per solid on a C5 block.  Two solids are
+    # probed; the run's time box (--cpu-budget seconds, default 150) then fixes how many solid evaluations fit.  At least
+    # MIN_DISTINCT distinct solids are timed over the run: when a step cannot hold that many, every step takes a DIFFERENT
+    # slice of one evenly spaced sample, and the line's value is total pairs / total time over the timed steps.
+    MIN_DISTINCT = 32
     n_total = args.warmup + args.steps
     prefer = True
     try:
@@ -236,19 +247,34 @@ def run_reference(args, rank, world):
         prefer = False
         _, probe_ms, kind = cpu_baseline_sample(case, 2, faithful=True, indices=representative_solids(case, 2), prefer_reference=False)
     per_solid_s = max(probe_ms * 1e-3 / 2.0, 1e-4)
-    n_sample = int(max(1, min(args.cpu_solids, (100.0 / max(n_total, 1)) / per_solid_s)))
-    idx = representative_solids(case, n_sample)
-    n_sample = len(idx)
-    vals = []
+    evals = max(1.0, args.cpu_budget / per_solid_s)                 # solid evaluations the time box holds
+    per_step = int(max(1, min(args.cpu_solids, evals // max(n_total, 1))))
+    rotate = per_step < MIN_DISTINCT
+    pool = representative_solids(case, max(per_step, min(MIN_DISTINCT, len(case["solids"]))) if rotate else per_step)
+    if rotate:   # a step cannot hold MIN_DISTINCT solids: warm-up = 1 solid, the timed steps share the pool between them
+        per_step = max(1, int(np.ceil(len(pool) / max(args.steps, 1))))
+        per_step = int(min(per_step, max(1, (evals - args.warmup) // max(args.steps, 1))))
+    vals, used = [], set()
     for i in range(n_total):
-        pairs, ms, kind = cpu_baseline_sample(case, n_sample, faithful=True, indices=idx, prefer_reference=prefer)
+        if not rotate:
+            idx = pool
+        elif i < args.warmup:
+            idx = pool[:1]
+        else:
+            j = (i - args.warmup) * per_step
+            idx = pool[[(j + t) % len(pool) for t in range(per_step)]]
+        pairs, ms, kind = cpu_baseline_sample(case, len(idx), faithful=True, indices=idx, prefer_reference=prefer)
         if i >= args.warmup:
             vals.append((pairs, ms))
+            used.update(int(x) for x in idx)
     pairs = sum(p for p, _ in vals)
     ms = sum(m for _, m in vals)
     value = pairs / (ms * 1e-3)
-    sample = (f"{n_sample} of {len(case['solids'])} solids per step (evenly spaced over the solids that touch rank 0's block and those that do "
-              f"not, in their proportion; sized by a 2-solid probe to ~100 s per run) on the full mesh of rank 0 of {world}, timed region = solid loop + "
+    n_distinct = len(used)
+    sample = (f"{per_step} of {len(case['solids'])} solids per step"
+              + (f", a different slice of one evenly spaced {len(pool)}-solid sample every step ({n_distinct} distinct solids over the {args.steps} timed steps)" if rotate else "")
+              + f" (evenly spaced over the solids that touch rank 0's block and those that do not, in their proportion; sized by a 2-solid probe "
+              f"of {per_solid_s:.2f} s per solid to a {args.cpu_budget:.0f} s run) on the full mesh of rank 0 of {world}, timed region = solid loop + "
               f"checkAlpha (reference src/solidcloud.cpp:442-451), "
               + ("the reference's own compiled CellEnumerator / GeometricTools / Solid / shape classes (oracle/_ref) inside the loop of "
                  "src/solidcloud.cpp:361-464; " if kind == "reference" else "oracle port, faithful per-solid O(nCells) CELL_TYPE array; ")
@@ -256,10 +282,67 @@ def run_reference(args, rank, world):
               f"(the reference is single-threaded per MPI rank; see DESIGN.md for why an MPI split is slower on this path)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": desc,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(desc),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "distinct_solids": n_distinct},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if n_distinct < MIN_DISTINCT and n_distinct < len(case["solids"]):
+        line["ratio"] = None
+        line["ratio_reason"] = (f"only {n_distinct} distinct solids fit the {args.cpu_budget:.0f} s time box at {per_solid_s:.1f} s per solid: "
+                                f"too few for a meaningful updates/s figure; use the N=1 line's ratio")
     print(json.dumps(line), flush=True)
+
+
+def parity_check(case, ctx, got, partial_ft, n_check, use_reference=True):
+    """What the timed kernels produced (fields and per-solid sums of the last step, host copies) against the CPU checker on
+    `n_check` evenly spaced solids that touch this rank's block: the reference's own compiled classes (oracle/_ref) when
+    available and the mesh is small enough for their O(nCells)-per-solid cost, else the oracle port (same results).
+    Candidate lists must be equal; As / Fs are compared on the sample's cells that no other solid touches; force / torque
+    relative to the largest component of the sample."""
+    from oracle.oracle_py import Oracle
+
+    S = case["solids"]
+    idx = representative_solids(case, n_check)
+    rb = np.array([float(sh["radiusB"]) for sh in case["shapes"]])
+    m = case["mesh"]
+    r = np.where(rb[S["shape"][idx]] > 0, rb[S["shape"][idx]], 0.0) + 1.0
+    idx = idx[np.all((S["pos"][idx] + r[:, None] >= m.bounds_min) & (S["pos"][idx] - r[:, None] <= m.bounds_max), axis=1)]
+    sub = np.ascontiguousarray(S[idx])
+    o = Oracle(m, case["two_d"])
+    kind = "port"
+    if use_reference and reference_available() and m.n_cells <= 20_000_000:
+        from oracle import ref_py
+        key = id(m)
+        if key not in _REF_CACHE:
+            _REF_CACHE.clear()
+            _REF_CACHE[key] = ref_py.Reference(m)
+        texts = [ref_py.dict_text_from_record(case["shapes"][int(sh)]) for sh in sub["shape"]]
+        seeds = np.array([o.nearest_cell(x) for x in sub["pos"]], dtype=np.int32)
+        ref = _REF_CACHE[key].interact(texts, sub, seeds, case["U"], case["dt"], case["rhof"], case["two_d"])
+        kind = "reference"
+    else:
+        ref = o.interact(case["shapes"], sub, case["U"], case["dt"], case["rhof"])
+    off, cells = ctx.candidate_lists()
+    lists_equal = True
+    for j, s_ in enumerate(idx):
+        for t in range(3):
+            a = cells[off[3 * s_ + t]: off[3 * s_ + t + 1]]
+            b = ref["list_cells"][ref["list_off"][3 * j + t]: ref["list_off"][3 * j + t + 1]]
+            lists_equal = lists_equal and np.array_equal(a, b)
+    owners = np.bincount(cells, minlength=m.n_cells)
+    mine = np.unique(ref["list_cells"])
+    mine = mine[owners[mine] == 1]
+    def rel(a, b):
+        d = np.abs(a - b)
+        nz = np.abs(b) > 0
+        return float(np.max(d[nz] / np.abs(b[nz]))) if nz.any() else 0.0
+    ft_scale = max(float(np.abs(ref["FT"]).max()), 1e-300)
+    return {"checker": kind, "solids_checked": int(len(idx)), "pairs_checked": int(ref["list_off"][-1]), "lists_equal": bool(lists_equal),
+            "single_owner_cells": int(len(mine)),
+            "max_rel_As": rel(got["As"][mine], ref["As"][mine]), "max_rel_Ts": rel(got["Ts"][mine], ref["Ts"][mine]),
+            "max_rel_Fs": float(np.abs(got["Fs"][mine] - ref["Fs"][mine]).max() / max(np.abs(ref["Fs"][mine]).max(), 1e-300)) if len(mine) else 0.0,
+            "Ct_equal": bool(np.array_equal(got["Ct"][mine], ref["Ct"][mine])),
+            "max_rel_FT": float(np.abs(partial_ft[idx] - ref["FT"]).max() / ft_scale),
+            "FT_note": "this rank's partial sums (before the all-reduce) vs the checker on this rank's block; relative to the sample's largest component"}
 
 
 def main():
@@ -273,6 +356,9 @@ def main():
     ap.add_argument("--cells-per-side", dest="n", type=int, default=0, help="cells per side (scaled-down runs)")
     ap.add_argument("--solids", type=int, default=0)
     ap.add_argument("--cpu-solids", type=int, default=256, help="solids per CPU-baseline sample")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run")
+    ap.add_argument("--no-base", action="store_true", help="N>1: skip the same-workload 1-GPU base run (scaling_base)")
+    ap.add_argument("--no-check", action="store_true", help="skip the in-bench parity check against the CPU checker")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -455,11 +455,7 @@ __device__ __forceinline__ void eval_staged_vertex(HeavySmem &sm, const DevShape
 }
 
 #define HEAVY_CTAS_PER_SM 5
-// SYNTH (experimental, opt-in: SDFIBM_SYNTH_FACES=1, uniform box meshes only; NOT measured yet): the face centre and area vector
-// are formed from the staged vertices — Sf = (p2 - p0) x (p3 - p1) / 2 (the vector area of any quadrilateral), apex - Cf = the mean
-// of apex - p_i (the centroid of a parallelogram) — instead of being fetched: no cellFaces / face_rec traffic (24 + up to 384 bytes
-// per item).  Results then differ from the mesh's own Cf / Sf by rounding (1e-16 relative), not bit for bit.
-template <int CTAS, bool SYNTH>
+template <int CTAS>
 __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     __shared__ HeavySmem sm;
     const DevMesh &m = P.m;
@@ -499,8 +495,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             tw0 = __ldg(m.hex_topo + 3 * (long long)c);
             tw1 = __ldg(m.hex_topo + 3 * (long long)c + 1);
             tw2 = __ldg(m.hex_topo + 3 * (long long)c + 2);
-            if (SYNTH) {
-            } else if (m.is_hex) {
+            if (m.is_hex) {
                 const int2 *cf2 = reinterpret_cast<const int2 *>(m.cf + 6 * (long long)c);
                 f01 = __ldg(cf2); f23 = __ldg(cf2 + 1); f45 = __ldg(cf2 + 2);
             } else {
@@ -588,18 +583,10 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
                     const double ph[4] = {PH(l[0]), PH(l[1]), PH(l[2]), PH(l[3])};
                     const int npos = (ph[0] > 0) + (ph[1] > 0) + (ph[2] > 0) + (ph[3] > 0);
                     if (npos == 4) continue;                                        // eps_f = 0: adds +0.0 (:107-108)
-                    double2 r0 = {0.0, 0.0}, r1 = {0.0, 0.0}, r2 = {0.0, 0.0}, r3 = {0.0, 0.0};
-                    D3 Sf_s = {0.0, 0.0, 0.0}, dCf_s = {0.0, 0.0, 0.0};
-                    if (SYNTH) {
-                        const D3 p0 = PT(l[0]), p1 = PT(l[1]), p2 = PT(l[2]), p3 = PT(l[3]);
-                        Sf_s = 0.5 * cross3(p2 - p0, p3 - p1);
-                        dCf_s = 0.25 * (((apex - p0) + (apex - p1)) + ((apex - p2) + (apex - p3)));   // apex - Cf
-                    } else {
-                        const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
-                        // face record: Cf.xyz, Sf.xyz, |Sf|, pad — four 16-byte loads issued before the area math
-                        const double2 *fr = m.face_rec + 4 * (long long)face;
-                        r0 = __ldg(fr); r1 = __ldg(fr + 1); r2 = __ldg(fr + 2); r3 = __ldg(fr + 3);
-                    }
+                    const int face = (f == 0) ? f01.x : (f == 1) ? f01.y : (f == 2) ? f23.x : (f == 3) ? f23.y : (f == 4) ? f45.x : f45.y;
+                    // face record: Cf.xyz, Sf.xyz, |Sf|, pad — four 16-byte loads issued before the area math
+                    const double2 *fr = m.face_rec + 4 * (long long)face;
+                    const double2 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2), r3 = __ldg(fr + 3);
                     double eps_f = 1.0;                                             // all phi <= 0 (:109-110)
                     if (npos != 0) {
                         const D3 A = PT(l[0]);                                      // calcFaceArea (:74-96)
@@ -618,19 +605,169 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
                             const D3 O = PT(l[e]), A2 = PT(l[(e + 1) & 3]);
                             area += fabs(0.5 * mag3(cross3(A2 - O, fap - O))) * lf;   // a zero fraction adds +0.0
                         }
-                        eps_f = area / (SYNTH ? mag3(Sf_s) : r3.x);
+                        eps_f = area / r3.x;
                     }
-                    if (SYNTH) {
-                        volume += (1.0 / 3.0) * eps_f * fabs(dot3(dCf_s, Sf_s));
-                    } else {
-                        const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
-                        volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
-                    }
+                    const D3 Cf = {r0.x, r0.y, r1.x}, Sf = {r1.y, r2.x, r2.y};
+                    volume += (1.0 / 3.0) * eps_f * fabs(dot3(apex - Cf, Sf));
                 }
             }
             P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));   // type 0: no vertex inside -> not a member
         }
         __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_heavy_box: the exact evaluation on exact-box meshes (DevMesh::box_exact).  Lane = one (cell, solid) item.  The cell is six
+// coordinates; its corners are addressed by a 3-bit code (bit0 x-hi, bit1 y-hi, bit2 z-hi).  The vertex predicates / signed
+// distances, the two apexes and every difference that can cancel (apex - face plane, face apex - edge) run the reference's own
+// operation sequence un-contracted, so the lists are bit-exact and the fractions keep their RELATIVE accuracy on sliver cells.
+// What the box buys (geometrictools.cpp:74-116 on an axis-aligned rectangle): the triangle (O, A, face apex) of calcFaceArea
+// has the area 0.5 * |edge| * |offset of the apex perpendicular to the edge| — its cross product has ONE non-zero component,
+// whose square root is exact — and eps_f * |(apex - Cf) . Sf| = area * |apex_a - Cf_a| because Sf is exactly (0, 0, +-|Sf|):
+// no cross products, no square roots, no face records; the four edge fractions are quotients of positive numbers (no
+// cancellation) and use a Newton-refined reciprocal instead of the IEEE division sequence.
+// ------------------------------------------------------------------------------------------------
+#define BOX_CTAS_PER_SM 6
+
+// x / y for y > 0 to within 1 ulp: MUFU seed (2^-20), two Newton steps, one residual correction
+__device__ __forceinline__ double div_pos(double x, double y) {
+    if (y < 1e-290 || y > 1e290) return x / y;   // seed under / overflows: IEEE sequence (planes with a vertex within 1e-290 of the surface)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    r = fma(r, fma(-y, r, 1.0), r);
+    r = fma(r, fma(-y, r, 1.0), r);
+    const double q = x * r;
+    return fma(fma(-y, q, x), r, q);
+}
+// calcLineFraction (:13-23) with the quotient of two non-negative numbers taken by div_pos
+__device__ __forceinline__ double line_fraction_fast(double a, double b) {
+    const bool ap = a > 0, bp = b > 0;
+    const double in = ap ? b : a, out = ap ? a : b;
+    const double q = div_pos(-in, out - in);
+    return (ap && bp) ? 0.0 : ((ap || bp) ? q : 1.0);
+}
+
+// pyramid term of face (axis A, side S) of a box cell: 1/3 eps_f |(apex - Cf) . Sf|  (geometrictools.cpp:61-70,98-116)
+template <int A, int S, bool PLANE_FROM_MESH>
+__device__ __forceinline__ double box_face_term(const double *ph /* smem column: ph[code * TPB] */, const double (&lo)[3], const double (&hi)[3],
+                                                const double (&apex)[3], unsigned w1, const double *cfa) {
+    constexpr int U = (A + 1) % 3, V = (A + 2) % 3;
+    constexpr int c00 = (S << A), c10 = c00 | (1 << U), c01 = c00 | (1 << V), c11 = c10 | c01;
+    const double p00 = ph[c00 * TPB], p10 = ph[c10 * TPB], p01 = ph[c01 * TPB], p11 = ph[c11 * TPB];
+    const int npos = (p00 > 0) + (p10 > 0) + (p01 > 0) + (p11 > 0);
+    if (npos == 4) return 0.0;                                                   // eps_f = 0 (:107-108)
+    const double plane = PLANE_FROM_MESH ? __ldg(cfa + 2 * A + S) : (S ? hi[A] : lo[A]);
+    const double height = fabs(apex[A] - plane);                                 // |(apex - Cf) . Sf| / |Sf|
+    const double Lu = hi[U] - lo[U], Lv = hi[V] - lo[V];
+    double area = Lu * Lv;                                                       // eps_f = 1 (:109-110)
+    if (npos != 0) {
+        // calcFaceArea (:74-96): the face apex from the loop's first vertex A0 and the first vertex across the surface
+        const unsigned t = (w1 >> (3 * (2 * A + S))) & 7u;
+        const int iu0 = t & 1, iv0 = (t >> 1) & 1, dir = (t >> 2) & 1;
+        auto sel = [&](int iu, int iv) { return iv ? (iu ? p11 : p01) : (iu ? p10 : p00); };
+        const int iu1 = iu0 ^ (dir ^ 1), iv1 = iv0 ^ dir, iu3 = iu0 ^ dir, iv3 = iv0 ^ (dir ^ 1);
+        const double phA = sel(iu0, iv0), ph1 = sel(iu1, iv1), ph2 = sel(iu0 ^ 1, iv0 ^ 1), ph3 = sel(iu3, iv3);
+        int iuB = iu1, ivB = iv1;
+        double phB = ph1;
+        if (!(phA * ph1 <= 0)) {
+            iuB = iu0 ^ 1; ivB = iv0 ^ 1; phB = ph2;
+            if (!(phA * ph2 <= 0)) { iuB = iu3; ivB = iv3; phB = ph3; }
+        }
+        const double w = fabs(phA) / (SDF_SMALL + fabs(phA) + fabs(phB));
+        const double Au = iu0 ? hi[U] : lo[U], Av = iv0 ? hi[V] : lo[V];
+        const double Bu = iuB ? hi[U] : lo[U], Bv = ivB ? hi[V] : lo[V];
+        const double fu = Au - w * (Au - Bu), fv = Av - w * (Av - Bv);
+        // four triangles: edge length x perpendicular offset of the face apex, weighted by the edge's wet fraction
+        const double a = fabs(fu - lo[U]), b = fabs(fu - hi[U]), c = fabs(fv - lo[V]), d = fabs(fv - hi[V]);
+        area = 0.5 * fma(Lu, fma(c, line_fraction_fast(p00, p10), d * line_fraction_fast(p01, p11)),
+                         Lv * fma(a, line_fraction_fast(p00, p01), b * line_fraction_fast(p10, p11)));
+    }
+    return (1.0 / 3.0) * area * height;
+}
+
+template <int CTAS, bool PLANE_FROM_MESH>
+__global__ void __launch_bounds__(TPB, CTAS) k_heavy_box(InteractParams P) {
+    __shared__ double s_phi[8 * TPB];
+    const DevMesh &m = P.m;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
+    double *ph = s_phi + tid;
+    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
+    const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
+    for (long long k0 = q0 + (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
+        const long long k = k0 + lane;
+        const bool valid = k < n;
+        int c = 0, s = 0;
+        if (valid) { const int2 it = __ldg(P.heavy + k); c = it.x; s = it.y; }
+        DQ q = {1.0, {0.0, 0.0, 0.0}};
+        D3 t = {0.0, 0.0, 0.0};
+        int shape_idx = 0;
+        double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+        uint2 tw = {0u, 0u};
+        D3 cc = {0, 0, 0};
+        if (valid) {
+            const double2 *b2 = reinterpret_cast<const double2 *>(m.box6 + 6 * (long long)c);
+            const double2 b0 = __ldg(b2), b1 = __ldg(b2 + 1), b3 = __ldg(b2 + 2);
+            lo[0] = b0.x; lo[1] = b0.y; lo[2] = b1.x; hi[0] = b1.y; hi[1] = b3.x; hi[2] = b3.y;
+            tw = __ldg(reinterpret_cast<const uint2 *>(m.btopo) + c);
+            cc = ld3(m.cc, c);
+            const DevSolid &S = P.solids[s];
+            q = {S.q[0], {S.q[1], S.q[2], S.q[3]}};
+            t = {S.pos[0], S.pos[1], S.pos[2]};
+            shape_idx = S.shape;
+        }
+        const DevShape &sh = P.shapes[shape_idx];
+        const bool ident = __all_sync(FULL, !valid || quat_is_identity(q));
+        int n_in = 0;
+        if (valid) {
+#pragma unroll 2
+            for (int code = 0; code < 8; ++code) {
+                const D3 p = {(code & 1) ? hi[0] : lo[0], (code & 2) ? hi[1] : lo[1], (code & 4) ? hi[2] : lo[2]};
+                double phv;
+                n_in += shape_eval<true>(sh.s, world2local_sel(q, t, p, ident), phv) ? 1 : 0;
+                ph[code * TPB] = phv;
+            }
+        }
+        if (valid) {
+            int type = 0;
+            double volume = 0.0;
+            if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
+            else if (n_in != 0) {
+                double dummy;
+                type = shape_eval<false>(sh.s, world2local_sel(q, t, cc, ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                // cell apex over cellPoints() order (geometrictools.cpp:25-45,56-58)
+                double apex[3];
+                {
+                    const int cA = tw.x & 7;
+                    const double phiA = ph[cA * TPB];
+                    int cB = cA;
+                    double phiB = 0.0;
+#pragma unroll 1
+                    for (int i = 1; i < 8; ++i) {
+                        cB = (tw.x >> (3 * i)) & 7;
+                        phiB = ph[cB * TPB];
+                        if (phiA * phiB <= 0) break;
+                    }
+                    const double w = fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB));
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const double A = ((cA >> d) & 1) ? hi[d] : lo[d], B = ((cB >> d) & 1) ? hi[d] : lo[d];
+                        apex[d] = A - w * (A - B);
+                    }
+                    if (m.two_d) apex[2] = 0.0;
+                }
+                const double *cfa = PLANE_FROM_MESH ? m.cfa6 + 6 * (long long)c : nullptr;
+                volume = box_face_term<0, 0, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
+                volume += box_face_term<0, 1, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
+                volume += box_face_term<1, 0, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
+                volume += box_face_term<1, 1, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
+                volume += box_face_term<2, 0, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
+                volume += box_face_term<2, 1, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
+            }
+            P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));
+        }
     }
 }
 

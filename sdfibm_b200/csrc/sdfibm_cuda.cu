@@ -116,6 +116,16 @@ struct DevMesh {
     int mixed;              // some cells are such hexahedra and some are not: hex_topo[3c] == HEX_NONE marks the others, which go
                             // through the general-polyhedron kernel from a queue of their own
     int two_d;
+    // Exact-box meshes (checked cell by cell at upload, k_box_topo): every cell's 8 vertices sit bit for bit on the corners of
+    // an axis-aligned box, and every face record agrees bit for bit with its vertices (Cf on the face plane, Sf along its
+    // normal).  The exact evaluation then needs 6 coordinates and two topology words per cell instead of 8 gathered vertices
+    // and 6 face records, and its face areas need no cross products or square roots (k_heavy_box).
+    int box_exact;            // 0: no; 1: yes, face-plane coordinates from cfa6; 2: yes, and every Cf lies bit for bit on its plane
+    const double *box6;       // per position: lo.xyz, hi.xyz of the cell
+    const double *cfa6;       // per position (box_exact == 1): normal coordinate of the mesh's Cf of face (axis a, side s) at [2a+s]
+    const unsigned *btopo;    // per position: [0] corner code (bit0 x-hi, bit1 y-hi, bit2 z-hi) of cellPoints() slot m at bits 3m;
+                              // [1] for face (axis a, side s) at bits 3(2a+s): in-plane corner (iu, iv) of the face loop's
+                              // first vertex + loop direction (0: second vertex differs along u = (a+1)%3, 1: along v = (a+2)%3)
 };
 
 // the tile grid: static per mesh; solids are binned on it every step
@@ -195,6 +205,86 @@ __global__ void k_hex_topo(DevMesh m, unsigned *topo, int *bad) {
     topo[3 * (long long)c] = w[0];
     topo[3 * (long long)c + 1] = w[1];
     topo[3 * (long long)c + 2] = w[2];
+}
+
+
+// Exact-box topology of a cell (see DevMesh::box_exact).  Any deviation clears *ok for the whole mesh.
+__global__ void k_box_topo(DevMesh m, double *box6, unsigned *btopo, double *cfa6, int *ok) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.n_cells) return;
+    const int pb = m.cp_off[c], fb = m.cf_off[c];
+    if (m.cp_off[c + 1] - pb != 8 || m.cf_off[c + 1] - fb != 6) { atomicExch(ok, 0); return; }
+    int vid[8];
+    D3 p[8];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int k = 0; k < 8; ++k) {
+        vid[k] = m.cp[pb + k];
+        p[k] = ld3(m.points, vid[k]);
+        lo[0] = fmin(lo[0], p[k].x); lo[1] = fmin(lo[1], p[k].y); lo[2] = fmin(lo[2], p[k].z);
+        hi[0] = fmax(hi[0], p[k].x); hi[1] = fmax(hi[1], p[k].y); hi[2] = fmax(hi[2], p[k].z);
+    }
+    bool good = lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2];
+    int code[8];
+    unsigned seen = 0, w0 = 0, w1 = 0;
+    for (int k = 0; k < 8; ++k) {
+        const double q[3] = {p[k].x, p[k].y, p[k].z};
+        int cd = 0;
+        for (int a = 0; a < 3; ++a) {
+            if (q[a] == hi[a]) cd |= 1 << a;
+            else if (q[a] != lo[a]) good = false;
+        }
+        code[k] = cd;
+        seen |= 1u << cd;
+        w0 |= (unsigned)cd << (3 * k);
+    }
+    good = good && seen == 0xffu;
+    unsigned fseen = 0;
+    bool cf_exact = true;
+    double cfa[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 6 && good; ++k) {
+        const int f = m.cf[fb + k];
+        const int q0 = m.fp_off[f];
+        if (m.fp_off[f + 1] - q0 != 4) { good = false; break; }
+        int fc[4];
+        for (int j = 0; j < 4; ++j) {
+            const int g = m.fp[q0 + j];
+            int l = -1;
+            for (int t = 0; t < 8; ++t) if (vid[t] == g) l = t;
+            if (l < 0) { good = false; l = 0; }
+            fc[j] = code[l];
+        }
+        const int andc = fc[0] & fc[1] & fc[2] & fc[3], orc = fc[0] | fc[1] | fc[2] | fc[3];
+        const int cm = ~(andc ^ orc) & 7;   // the axes along which the four corners agree
+        if (__popc(cm) != 1) { good = false; break; }
+        const int a = __ffs(cm) - 1, s = (fc[0] >> a) & 1, u = (a + 1) % 3, v = (a + 2) % 3;
+        const int d1 = fc[0] ^ fc[1];
+        int dir;
+        if (d1 == (1 << u)) dir = 0;
+        else if (d1 == (1 << v)) dir = 1;
+        else { good = false; break; }
+        if (fc[2] != (fc[0] ^ (1 << u) ^ (1 << v)) || fc[3] != (fc[0] ^ (dir ? (1 << u) : (1 << v)))) { good = false; break; }
+        const int fi = 2 * a + s;
+        fseen |= 1u << fi;
+        w1 |= (unsigned)(((fc[0] >> u) & 1) | (((fc[0] >> v) & 1) << 1) | (dir << 2)) << (3 * fi);
+        // the face record agrees bit for bit with the vertices: centre on the face plane, area vector along the normal
+        const double Cf[3] = {m.Cf[3 * (long long)f], m.Cf[3 * (long long)f + 1], m.Cf[3 * (long long)f + 2]};
+        const double Sf[3] = {m.Sf[3 * (long long)f], m.Sf[3 * (long long)f + 1], m.Sf[3 * (long long)f + 2]};
+        const double A = (hi[u] - lo[u]) * (hi[v] - lo[v]);
+        if (Sf[u] != 0.0 || Sf[v] != 0.0 || !(fabs(fabs(Sf[a]) - A) <= 1e-14 * A)) good = false;
+        // ... and the centre lies within rounding of the face plane; where it is not bit for bit ON the plane the kernel takes
+        // the plane coordinate of the pyramid height from the mesh's own Cf (cfa6) instead of from the vertices
+        const double plane = s ? hi[a] : lo[a];
+        if (!(fabs(Cf[a] - plane) <= 1e-12 * (hi[a] - lo[a]))) good = false;
+        if (Cf[a] != plane) cf_exact = false;
+        cfa[fi] = Cf[a];
+    }
+    good = good && fseen == 0x3fu;
+    if (!good) { atomicExch(ok, 0); return; }
+    if (!cf_exact) atomicExch(ok + 1, 0);
+    for (int k = 0; k < 6; ++k) cfa6[6 * (long long)c + k] = cfa[k];
+    for (int a = 0; a < 3; ++a) { box6[6 * (long long)c + a] = lo[a]; box6[6 * (long long)c + 3 + a] = hi[a]; }
+    btopo[2 * (long long)c] = w0;
+    btopo[2 * (long long)c + 1] = w1;
 }
 
 // direction table for the connectivity certificate: which face neighbour lies towards -x, +x, -y, ...
@@ -680,7 +770,9 @@ struct sdfibm_context {
     DevBuf<unsigned char> tile_proven;   // per tile and step: all its candidate solids are provably connected
     DevBuf<double> magSf;
     DevBuf<double2> face_rec;
-    DevBuf<unsigned> hex_topo, tile_key;
+    DevBuf<unsigned> hex_topo, tile_key, btopo;
+    DevBuf<double> box6, cfa6;
+    bool allow_box = true;      // SDFIBM_BOX=0: keep exact-box meshes on the general hexahedron kernel
     DevBuf<int> nb6;
     DevBuf<int> orig, inv;      // tile-order renumbering: position -> caller's label and back
     DevBuf<double> cc_orig;     // cell centres in the caller's order (fixInternal)
@@ -742,7 +834,6 @@ struct sdfibm_context {
     GraphKey graph_key = {0};
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
-    int synth_faces = 0;        // experimental (SDFIBM_SYNTH_FACES=1 | 2): k_heavy_hex<5 | 6, true> on uniform box meshes
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
     const sdfibm_solid_t *ext_solids = nullptr;   // device-resident solid records supplied by the caller for the current call
@@ -814,7 +905,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaMallocHost(&ctx->h_scal, 2 * sizeof(double)));
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
-    if (const char *e = getenv("SDFIBM_SYNTH_FACES")) ctx->synth_faces = atoi(e);
+    if (const char *e = getenv("SDFIBM_BOX")) ctx->allow_box = atoi(e) != 0;
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -837,7 +928,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
-    ctx->tile_proven.release(); ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    ctx->tile_proven.release(); ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->btopo.release(); ctx->box6.release(); ctx->cfa6.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release(); ctx->slab_start.release();
     ctx->global_list.release(); ctx->slots.release();
@@ -1059,6 +1150,28 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         CUDA_TRY(ctx->hex_topo.ensure(3 * nC));
         d.hex_topo = ctx->hex_topo.p;
         k_hex_topo<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->hex_topo.p, bad.p);
+    }
+    // exact-box fast path of the exact evaluation (k_heavy_box)?
+    d.box_exact = 0; d.box6 = nullptr; d.btopo = nullptr; d.cfa6 = nullptr;
+    if (is_hex && ctx->allow_box) {
+        DevBuf<int> okf;
+        CUDA_TRY(okf.ensure(2));
+        const int one[2] = {1, 1};
+        CUDA_TRY(cudaMemcpyAsync(okf.p, one, sizeof(one), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx->box6.ensure(6 * nC));
+        CUDA_TRY(ctx->btopo.ensure(2 * nC));
+        CUDA_TRY(ctx->cfa6.ensure(6 * nC));
+        k_box_topo<<<grid_for(nC, 128), 128, 0, st>>>(d, ctx->box6.p, ctx->btopo.p, ctx->cfa6.p, okf.p);
+        int h_ok[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(h_ok, okf.p, sizeof(h_ok), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        okf.release();
+        if (h_ok[0]) {
+            d.box_exact = h_ok[1] ? 2 : 1;
+            d.box6 = ctx->box6.p; d.btopo = ctx->btopo.p;
+            if (h_ok[1]) ctx->cfa6.release();
+            d.cfa6 = ctx->cfa6.p;
+        } else { ctx->box6.release(); ctx->btopo.release(); ctx->cfa6.release(); }
     }
     CUDA_TRY(ctx->nb6.ensure(6 * nC));
     d.nb6 = ctx->nb6.p;
@@ -1325,9 +1438,9 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         else k_classify<256, 8, false, false><<<grid, 256, 0, st>>>(I);
     };
     auto launch_heavy = [&]() {
-        if (ctx->synth_faces == 2 && ctx->dm.is_hex && ctx->dm.box_uniform) k_heavy_hex<6, true><<<ctx->n_sm * 6, TPB, 0, st>>>(I);
-        else if (ctx->synth_faces && ctx->dm.is_hex && ctx->dm.box_uniform) k_heavy_hex<HEAVY_CTAS_PER_SM, true><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-        else if (ctx->dm.is_hex || ctx->dm.mixed) k_heavy_hex<HEAVY_CTAS_PER_SM, false><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+        if (ctx->dm.box_exact == 2) k_heavy_box<BOX_CTAS_PER_SM, false><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
+        else if (ctx->dm.box_exact == 1) k_heavy_box<BOX_CTAS_PER_SM, true><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
+        else if (ctx->dm.is_hex || ctx->dm.mixed) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
         if (!ctx->dm.is_hex) k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     };
     I.heavy_start = nullptr;
