@@ -505,6 +505,32 @@ def main():
                "note": "sdfibm_interact (host-buffer C ABI): pinned U H2D, kernels, As/Fs/Ts/Ct/forceTorque D2H every step; "
                        "the copies stream in cell chunks on two copy streams, overlapped with the kernels and with each other"}
 
+    # ---- what the timed kernels produced, checked against the CPU checker (rank 0's block) ----
+    check = None
+    if world > 1:
+        # one extra untimed step WITHOUT the all-reduce: this rank's partial sums; their NCCL sum must reproduce the timed step's dFT
+        total_timed = dFT.clone()
+        ctx.interact_device(solids_pinned, dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(), dFs.data_ptr(),
+                            dTs.data_ptr(), dCt.data_ptr(), dFT.data_ptr())
+        partial = dFT.clone()
+        total_again = partial.clone()
+        dist.all_reduce(total_again)
+        allreduce_dev = float((total_again - total_timed).abs().max().item() / max(float(total_timed.abs().max().item()), 1e-300))
+    else:
+        partial = dFT
+        allreduce_dev = None
+    if rank == 0 and not args.no_check:
+        got = {"As": dAs.cpu().numpy(), "Fs": dFs.cpu().numpy(), "Ts": dTs.cpu().numpy(), "Ct": dCt.cpu().numpy()}
+        try:
+            check = parity_check(case, ctx, got, partial.cpu().numpy(), 64 if world == 1 else 32)
+            check["counts_equal_device_and_lists"] = bool(sum(counts) == int(ctx.candidate_lists()[0][-1]))
+            if allreduce_dev is not None:
+                check["allreduce_vs_sum_of_partials_rel"] = allreduce_dev
+        except Exception as ex:   # the checker must never take the bench line down
+            check = {"error": repr(ex)}
+        del got
+
+    line = None
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         alg = algorithmic_bytes(nC, counts, nS)            # rank 0's kernel launch
@@ -512,13 +538,14 @@ def main():
         # k_finalize), timed live by the library's CUDA events on its stream
         achieved = alg / (pipe_ms * 1e-3) / 1e9
         traffic, traffic_src = measured_traffic(wl if world == 1 and not args.n else "-")
+        heavy_share = split_mean[1] / max(pipe_ms, 1e-30)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(desc, cells_total=int(tot[3].item()), solids=nS, pairs_per_step=pairs_all,
-                           pairs_by_type={"ALL_INSIDE": counts_all[0], "CENTER_INSIDE": counts_all[1], "CENTER_OUTSIDE": counts_all[2]},
-                           l2="inputs larger than L2 (fields + mesh arrays of one step >> 126 MB); no explicit flush"),
+            "config": make_config(desc),
+            "workload_stats": dict(cells_total=int(tot[3].item()), solids=nS, pairs_per_step=pairs_all,
+                                   pairs_by_type={"ALL_INSIDE": counts_all[0], "CENTER_INSIDE": counts_all[1], "CENTER_OUTSIDE": counts_all[2]}),
             "clocks": clocks,
             "gpu_launches": int(launches_per_step * args.steps),
             "kernel_ms": {"k_classify": split_mean[0], "k_heavy": split_mean[1], "k_final": split_mean[2],
@@ -526,7 +553,7 @@ def main():
                           "interact_kernels": kern_ms, "pipeline_device": pipe_ms, "step_wall_on_stream": ms_per_step,
                           "heavy_items": stats["heavy_items"],
                           "host_us": dict(zip(("stage_solids", "enqueue", "wait_gpu", "call"), host_mean))},
-            "roofline": {"bound": "hbm", "kernel": "one graph launch of the interact pipeline: binning + k_classify + k_heavy_hex + k_final + k_connectivity (k_heavy_hex is 57% of it)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": f"one graph launch of the interact pipeline: binning + k_classify + k_heavy + k_final + k_connectivity (k_heavy is {100 * heavy_share:.0f}% of it)", "achieved": achieved,
                          "achieved_interact_kernels_only": alg / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src["source"] if traffic_src else None,
@@ -534,6 +561,7 @@ def main():
                          "algorithmic_bytes_per_launch": int(alg),
                          "formula": "48*nCells + 112*P + 216*P_b + 176*N (SURVEY.md 8d), rank 0"},
             "e2e": e2e,
+            "parity_check": check,
         }
         if not args.no_cpu and world == 1:
             t0 = time.time()
@@ -554,16 +582,90 @@ def main():
                 "optimised_port_note": "same oracle without the per-solid O(nCells) allocation (not what the reference does)",
                 "wall_s": time.time() - t0,
             }
-        print(json.dumps(line), flush=True)
+            line["ratios_vs_optimised_port"] = {
+                "device_resident": value / line["cpu_baseline"]["optimised_port_value"],
+                "e2e": (e2e["value"] / line["cpu_baseline"]["optimised_port_value"]) if e2e else None,
+                "note": "the faithful CPU path pays a 67 MB CELL_TYPE allocation per solid (src/cellenumerator.cpp:49); these are the ratios against "
+                        "the same algorithm without it, to be quoted beside the driver's headline ratio"}
     # orderly teardown: our context (own CUDA stream / events) before torch's NCCL communicator and allocator
     torch.cuda.synchronize()
-    del ext
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+    # ---- N > 1: the SAME workload on ONE GPU, in the same run (rank 0, after the other ranks have left): the base of the scaling figure
+    if rank == 0 and world > 1 and not args.no_base:
+        try:
+            del dU, dAs, dFs, dTs, dCt, dFT, partial, total_timed, total_again, rep, case, mesh
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            if wl != "c5":
+                raise RuntimeError("no single-GPU base for this workload")
+            case1, desc1 = _c5_single(args)
+            base = device_resident_base(case1, local_rank, steps=max(2, min(args.steps, 5)), warmup=3)
+            line["scaling_base"] = {"workload": desc1["workload"], "n_gpus": 1, "ms_per_step": base["ms_per_step"],
+                                    "pairs_per_step": base["pairs"], "value": base["value"],
+                                    "note": "the SAME mesh and solids on one GPU of this box, timed in this run by rank 0 after the N-rank measurement"}
+            line["speedup_same_workload"] = base["ms_per_step"] / ms_per_step
+            line["pairs_match_base"] = bool(base["pairs"] == pairs_all)
+        except Exception as ex:
+            line["scaling_base"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    del ext
     sys.stdout.flush()
-    os._exit(0)  # skip interpreter-exit destructors of two CUDA runtimes (torch's and the library's static cudart)
+
+
+def _c5_single(args):
+    """The whole C5 mesh as ONE block (the 1-GPU base of the N>1 lines)."""
+    from sdfibm_b200 import cases
+    n = args.n or 512
+    scale = n / 512.0
+    n_side = max(1, int(round(47 * scale)))
+    n_solids = args.solids or min(n_side ** 3, int(round(100000 * scale ** 3)))
+    case = cases.case_c5_block(0, 1, n=n, n_solids=n_solids, n_side=n_side)
+    desc = {"workload": f"C5: {n}^3 hex cells, {n_solids} Sphere r=4.5 / Ellipsoid (5,4.5,4) mixed, jittered {n_side}^3 lattice, seed 12345; one block"}
+    return case, desc
+
+
+def device_resident_base(case, local_rank, steps, warmup):
+    """Device-resident ms/step of one case on one GPU (CUDA events on the library's stream)."""
+    import torch
+    from sdfibm_b200 import capi
+    from sdfibm_b200.context import Context
+
+    dev = torch.device("cuda", local_rank)
+    mesh = case["mesh"]
+    nC, nS = mesh.n_cells, len(case["solids"])
+    ctx = Context(local_rank)
+    ctx.set_mesh(mesh, case["two_d"])
+    ctx.set_shapes(case["shapes"])
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+    dU = torch.from_numpy(case["U"]).to(dev)
+    f = [torch.empty(n, dtype=torch.float64, device=dev) for n in (nC, 3 * nC, nC, nC, 6 * nS)]
+    solids = capi.pinned_like(np.ascontiguousarray(case["solids"], dtype=capi.SOLID_DTYPE))
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.interact_device(solids, dU.data_ptr(), case["dt"], case["rhof"], *[x.data_ptr() for x in f])
+
+    with torch.cuda.stream(ext):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            step()
+        e1.record(ext)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    pairs = sum(ctx.candidate_counts())
+    ctx.close()
+    del ext
+    return {"ms_per_step": ms, "pairs": int(pairs), "value": pairs / (ms * 1e-3)}
 
 
 if __name__ == "__main__":

@@ -169,6 +169,11 @@ int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids
  * (the reference's sampler overwrites Ct as a side effect, SURVEY Q11 — not reproduced). */
 int sdfibm_mean_field(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field,
                       double *mean, double *sum_alpha_v);
+/* The raw sums of the same sampler: sum_alpha_v_field[3*s..] = sum(alpha V field), sum_alpha_v[s] = sum(alpha V) over THIS
+ * rank's cells.  A parallel host reduces both across ranks and divides afterwards (solidcloud.cpp:353-357) — a rank whose
+ * block does not touch the solid contributes zeros, not 0/0. */
+int sdfibm_mean_field_sums(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field,
+                           double *sum_alpha_v_field, double *sum_alpha_v);
 
 /* ---- candidate lists of the last interact (CellEnumerator::intersect result) --------
  * counts[3] = total ALL_INSIDE, CENTER_INSIDE, CENTER_OUTSIDE pairs. */

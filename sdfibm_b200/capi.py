@@ -68,6 +68,7 @@ SYMBOLS = {
     "sdfibm_fix_internal": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "sdfibm_fix_internal_device": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "sdfibm_mean_field": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
+    "sdfibm_mean_field_sums": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
     "sdfibm_candidate_counts": (C.c_int, [_VP, c_int64_p]),
     "sdfibm_candidate_lists": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "sdfibm_last_stats": (C.c_int, [_VP, c_int64_p]),

@@ -99,6 +99,15 @@ class Context:
         capi.check(self._lib.sdfibm_mean_field(self._h, capi.ptr(solids), n, capi.ptr(field), capi.ptr(mean), capi.ptr(den)))
         return mean, den
 
+    def mean_field_sums(self, solids: np.ndarray, field: np.ndarray):
+        """The sampler's raw sums on this rank: (sum(alpha V field)[N,3], sum(alpha V)[N]) — reduce across ranks, then divide."""
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        field = np.ascontiguousarray(field, dtype=np.float64)
+        n = len(solids)
+        num, den = np.empty((n, 3)), np.empty(n)
+        capi.check(self._lib.sdfibm_mean_field_sums(self._h, capi.ptr(solids), n, capi.ptr(field), capi.ptr(num), capi.ptr(den)))
+        return num, den
+
     # ---- candidate lists / diagnostics of the last interact ----
     def candidate_counts(self):
         c = (C.c_int64 * 3)()

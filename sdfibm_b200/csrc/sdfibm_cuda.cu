@@ -959,6 +959,8 @@ int sdfibm_free_pinned(void *p) {
     return SDFIBM_OK;
 }
 
+static void drop_graph(sdfibm_context *ctx);
+
 int sdfibm_set_cell_slots(sdfibm_context *ctx, int slots) {
     if (!ctx || slots < 1 || slots > 64) return fail(SDFIBM_ERR_ARG, "sdfibm_set_cell_slots: slots must be in 1..64");
     if (ctx->has_mesh) return fail(SDFIBM_ERR_STATE, "sdfibm_set_cell_slots: call before sdfibm_set_mesh");
@@ -986,6 +988,8 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         return fail(SDFIBM_ERR_ARG, "sdfibm_set_mesh: missing mesh array");
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    drop_graph(ctx);   // a captured step holds the old mesh's pointers and constants by value
+    ctx->has_mesh = false;
     const size_t nC = m->n_cells, nP = m->n_points, nF = m->n_faces;
     int rc;
     // ---- the tile grid: ~256 cells per tile (8x8x4 mean cell sizes; 16x16 columns for one-cell-thick 2-D meshes) ----
@@ -1236,6 +1240,7 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
 int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) {
     if (!ctx || !shapes || n <= 0) return fail(SDFIBM_ERR_ARG, "sdfibm_set_shapes: bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    drop_graph(ctx);   // the captured step holds n_shapes and the table pointer by value
     ctx->h_shapes.resize(n);
     for (int i = 0; i < n; ++i) {
         if (shapes[i].tag < 0 || shapes[i].tag >= SDFIBM_SHAPE_NTAGS)
@@ -1754,9 +1759,9 @@ __global__ void k_fill_unit_x(double *U, long long n_cells) {
     U[3 * c] = 1.0; U[3 * c + 1] = 0.0; U[3 * c + 2] = 0.0;
 }
 
-int sdfibm_mean_field(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field, double *mean,
-                      double *sum_alpha_v) {
-    if (!ctx || !solids || n_solids <= 0 || !field || !mean) return fail(SDFIBM_ERR_ARG, "sdfibm_mean_field: null argument");
+int sdfibm_mean_field_sums(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field, double *sum_alpha_v_field,
+                           double *sum_alpha_v) {
+    if (!ctx || !solids || n_solids <= 0 || !field || !sum_alpha_v_field || !sum_alpha_v) return fail(SDFIBM_ERR_ARG, "sdfibm_mean_field: null argument");
     if (!ctx->has_mesh || ctx->h_shapes.empty()) return fail(SDFIBM_ERR_STATE, "sdfibm_mean_field: set mesh and shapes first");
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t nC = ctx->dm.n_cells;
@@ -1784,9 +1789,21 @@ int sdfibm_mean_field(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_s
     CUDA_TRY(cudaMemcpyAsync(ft.data(), ctx->sFT.p, sizeof(double) * ft.size(), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int s = 0; s < n_solids; ++s) {
-        const double den = ft[6 * ((size_t)n_solids + s)];
-        for (int d = 0; d < 3; ++d) mean[3 * s + d] = ft[6 * (size_t)s + d] / den;
-        if (sum_alpha_v) sum_alpha_v[s] = den;
+        for (int d = 0; d < 3; ++d) sum_alpha_v_field[3 * s + d] = ft[6 * (size_t)s + d];
+        sum_alpha_v[s] = ft[6 * ((size_t)n_solids + s)];
+    }
+    return SDFIBM_OK;
+}
+
+int sdfibm_mean_field(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field, double *mean,
+                      double *sum_alpha_v) {
+    if (!mean || n_solids <= 0) return fail(SDFIBM_ERR_ARG, "sdfibm_mean_field: null argument");
+    std::vector<double> den((size_t)n_solids);
+    const int rc = sdfibm_mean_field_sums(ctx, solids, n_solids, field, mean, den.data());
+    if (rc) return rc;
+    for (int s = 0; s < n_solids; ++s) {
+        for (int d = 0; d < 3; ++d) mean[3 * s + d] /= den[s];   // single rank: 0/0 = NaN for a solid that touches no cell, as in the reference
+        if (sum_alpha_v) sum_alpha_v[s] = den[s];
     }
     return SDFIBM_OK;
 }

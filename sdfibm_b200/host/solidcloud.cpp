@@ -34,7 +34,6 @@ inline const sdfibm_mesh_t &meshView(const Foam::fvMesh &m) { return m.view(); }
 inline scalar transportRho(const Foam::fvMesh &m) { return m.transportRho(); }
 inline scalar meshTime(const Foam::fvMesh &m) { return m.timeValue(); }
 inline std::string casePath(const Foam::fvMesh &m, const std::string &f) { return m.caseDir() + "/" + f; }
-inline bool isMaster() { return true; }
 inline dictionary readDictionaryFile(const std::string &path) {
     dictionary d = dictionary::fromFile(path);
     d.remove("FoamFile");   // OpenFOAM drops the header entry when reading a dictionary file
@@ -47,6 +46,12 @@ inline dictionary readDictionaryFile(const std::string &path) {
 }
 #endif
 } // namespace
+
+#ifndef SDFIBM_WITH_OPENFOAM
+bool SolidCloud::isMaster() const { return m_rank == 0; }
+#else
+bool SolidCloud::isMaster() const { return Foam::Pstream::master(); }
+#endif
 
 void SolidCloud::log(const std::string &msg) {
     if (isMaster() && logfile) logfile << msg << std::endl;
@@ -306,8 +311,9 @@ scalar SolidCloud::totalSolidVolume() const {   // :572-576
 }
 
 void SolidCloud::saveState() {   // :578-593
-    if (!isMaster()) return;
-    if (m_timeStepCounter % m_writeFrequency == 0) {
+    // Only the master writes files, but the sampler's cross-rank reduction is a collective: every rank takes part in it
+    // (the reference calls it from its master-only branch, :580-590, which cannot work in parallel — SURVEY §2).
+    if (isMaster() && m_timeStepCounter % m_writeFrequency == 0) {
         statefile << (*this);
         statefile.flush();
     }
@@ -338,18 +344,17 @@ void SolidCloud::calcMeanField(std::vector<double> &out) {
     const size_t n = m_solids.size();
     std::vector<sdfibm_solid_t> recs(n);
     for (size_t i = 0; i < n; ++i) m_solids[i].toRecord(recs[i], sampler_index);
-    std::vector<double> den(n);
-    check(sdfibm_mean_field(m_ctx, recs.data(), (int)n, cellData(m_Uf), out.data(), den.data()), "sdfibm_mean_field");
-    if (m_reduce) {   // :353-357 — reduce numerator and denominator, then divide
-        std::vector<double> nd(4 * n);
-        for (size_t i = 0; i < n; ++i) {
-            for (int d = 0; d < 3; ++d) nd[4 * i + d] = out[3 * i + d] * den[i];
-            nd[4 * i + 3] = den[i];
-        }
-        m_reduce(nd.data(), (int)nd.size());
-        for (size_t i = 0; i < n; ++i)
-            for (int d = 0; d < 3; ++d) out[3 * i + d] = nd[4 * i + d] / nd[4 * i + 3];
+    // this rank's raw sums; numerator and denominator are reduced across ranks BEFORE the division (:353-357): a rank whose
+    // block does not touch the solid contributes zeros
+    std::vector<double> nd(4 * n), den(n);
+    check(sdfibm_mean_field_sums(m_ctx, recs.data(), (int)n, cellData(m_Uf), out.data(), den.data()), "sdfibm_mean_field_sums");
+    for (size_t i = 0; i < n; ++i) {
+        for (int d = 0; d < 3; ++d) nd[4 * i + d] = out[3 * i + d];
+        nd[4 * i + 3] = den[i];
     }
+    if (m_reduce) m_reduce(nd.data(), (int)nd.size());
+    for (size_t i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) out[3 * i + d] = nd[4 * i + d] / nd[4 * i + 3];
 }
 
 void SolidCloud::writeMeanField() {   // :303-313

@@ -64,6 +64,7 @@ private:
     std::vector<int> m_shapeIndex;             // per solid: row of the shape table
     std::vector<sdfibm_solid_t> m_records;     // staging of the rigid-body records
     std::vector<double> m_forceTorque;         // [6 N] per-solid (F, T) of the last interact
+    int m_rank = 0;
     std::function<void(double *, int)> m_reduce; // cross-rank sum of m_forceTorque (Foam::reduce / NCCL); none = serial
     double m_lastInteractMs{0};
 
@@ -103,6 +104,10 @@ public:
     // ---- additions of this implementation ----
     // cross-rank sum of the per-solid (F, T) array, replacing the 2N Foam::reduce calls (src/solidcloud.cpp:427-431)
     void setForceTorqueReducer(std::function<void(double *, int)> r) { m_reduce = std::move(r); }
+    // Foam-free parallel hosts: this process's rank (0 = master: the only one that writes cloud.out / meanfield.out).  With
+    // OpenFOAM the answer comes from Pstream::master().
+    void setRank(int rank) { m_rank = rank; }
+    bool isMaster() const;
     // UGrid cell size of the collision broad phase; the reference's HEAD value is 2*m_radiusB = -2 (no pairs, ever).
     // Also read from the optional `meta { collision_delta ...; }` key of solidDict.
     void setCollisionDelta(scalar delta) { m_collisionDelta = delta; }
