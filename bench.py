@@ -335,12 +335,16 @@ def parity_check(case, ctx, got, partial_ft, n_check, use_reference=True):
         d = np.abs(a - b)
         nz = np.abs(b) > 0
         return float(np.max(d[nz] / np.abs(b[nz]))) if nz.any() else 0.0
+    # the checker numbered the sampled solids 0..k-1: ALL_INSIDE cells carry (solid id + 4) (solidcloud.cpp:376-382)
+    ct_ref = ref["Ct"].copy()
+    ai = ct_ref >= 4
+    ct_ref[ai] = idx[(ct_ref[ai] - 4).astype(np.int64)] + 4.0
     ft_scale = max(float(np.abs(ref["FT"]).max()), 1e-300)
     return {"checker": kind, "solids_checked": int(len(idx)), "pairs_checked": int(ref["list_off"][-1]), "lists_equal": bool(lists_equal),
             "single_owner_cells": int(len(mine)),
             "max_rel_As": rel(got["As"][mine], ref["As"][mine]), "max_rel_Ts": rel(got["Ts"][mine], ref["Ts"][mine]),
             "max_rel_Fs": float(np.abs(got["Fs"][mine] - ref["Fs"][mine]).max() / max(np.abs(ref["Fs"][mine]).max(), 1e-300)) if len(mine) else 0.0,
-            "Ct_equal": bool(np.array_equal(got["Ct"][mine], ref["Ct"][mine])),
+            "Ct_equal": bool(np.array_equal(got["Ct"][mine], ct_ref[mine])),
             "max_rel_FT": float(np.abs(partial_ft[idx] - ref["FT"]).max() / ft_scale),
             "FT_note": "this rank's partial sums (before the all-reduce) vs the checker on this rank's block; relative to the sample's largest component"}
 

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsdfibm_b200.so")
+LIB_PATH = os.environ.get("SDFIBM_B200_LIB") or os.path.join(HERE, "libsdfibm_b200.so")   # the override is for kernel-variant experiments
 
 SHAPE_TAGS = {
     "Plane": 0, "Circle": 1, "Sphere": 2, "Ellipse": 3, "Ellipsoid": 4,

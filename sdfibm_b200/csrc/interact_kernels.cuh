@@ -621,79 +621,70 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
 // ------------------------------------------------------------------------------------------------
 // k_heavy_box: the exact evaluation on exact-box meshes (DevMesh::box_exact).  Lane = one (cell, solid) item.  The cell is six
 // coordinates; its corners are addressed by a 3-bit code (bit0 x-hi, bit1 y-hi, bit2 z-hi).  The vertex predicates / signed
-// distances, the two apexes and every difference that can cancel (apex - face plane, face apex - edge) run the reference's own
-// operation sequence un-contracted, so the lists are bit-exact and the fractions keep their RELATIVE accuracy on sliver cells.
+// distances, the two kinds of apex and every difference that can cancel (apex - face plane, face apex - edge) run the reference's
+// own operation sequence un-contracted — the apex weights |phiA| / (SMALL + |phiA| + |phiB|) keep the IEEE division — so the lists
+// are bit-exact and the fractions keep their RELATIVE accuracy on sliver cells.
 // What the box buys (geometrictools.cpp:74-116 on an axis-aligned rectangle): the triangle (O, A, face apex) of calcFaceArea
 // has the area 0.5 * |edge| * |offset of the apex perpendicular to the edge| — its cross product has ONE non-zero component,
 // whose square root is exact — and eps_f * |(apex - Cf) . Sf| = area * |apex_a - Cf_a| because Sf is exactly (0, 0, +-|Sf|):
-// no cross products, no square roots, no face records; the four edge fractions are quotients of positive numbers (no
-// cancellation) and use a Newton-refined reciprocal instead of the IEEE division sequence.
+// no cross products, no square roots, no face records.
+// Every lane runs ONE instruction stream.  The 12 edge fractions of the box are taken once (each edge belongs to two faces;
+// calcLineFraction is symmetric in its arguments, and out - in == |a| + |b| bit for bit when the signs differ; they only scale
+// positive terms, so a 1-ulp reciprocal sequence serves them), the six face terms are computed unconditionally and selected at
+// the end (a boundary cell has 3-5 cut faces, and a warp executes the union of its lanes' branches anyway).
 // ------------------------------------------------------------------------------------------------
+#ifndef BOX_CTAS_PER_SM
 #define BOX_CTAS_PER_SM 6
+#endif
+#ifndef BOX_VUNROLL
+#define BOX_VUNROLL 2
+#endif
+#ifndef BOX_EUNROLL
+#define BOX_EUNROLL 4
+#endif
+#ifndef BOX_FUNROLL
+#define BOX_FUNROLL 2
+#endif
+#define PRAGMA_UNROLL_(n) _Pragma(#n)
+#define PRAGMA_UNROLL(n) PRAGMA_UNROLL_(unroll n)
 
-// x / y for y > 0 to within 1 ulp: MUFU seed (2^-20), two Newton steps, one residual correction
-__device__ __forceinline__ double div_pos(double x, double y) {
-    if (y < 1e-290 || y > 1e290) return x / y;   // seed under / overflows: IEEE sequence (planes with a vertex within 1e-290 of the surface)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
-    r = fma(r, fma(-y, r, 1.0), r);
-    r = fma(r, fma(-y, r, 1.0), r);
-    const double q = x * r;
-    return fma(fma(-y, q, x), r, q);
-}
-// calcLineFraction (:13-23) with the quotient of two non-negative numbers taken by div_pos
-__device__ __forceinline__ double line_fraction_fast(double a, double b) {
-    const bool ap = a > 0, bp = b > 0;
-    const double in = ap ? b : a, out = ap ? a : b;
-    const double q = div_pos(-in, out - in);
-    return (ap && bp) ? 0.0 : ((ap || bp) ? q : 1.0);
-}
-
-// pyramid term of face (axis A, side S) of a box cell: 1/3 eps_f |(apex - Cf) . Sf|  (geometrictools.cpp:61-70,98-116)
-template <int A, int S, bool PLANE_FROM_MESH>
-__device__ __forceinline__ double box_face_term(const double *ph /* smem column: ph[code * TPB] */, const double (&lo)[3], const double (&hi)[3],
-                                                const double (&apex)[3], unsigned w1, const double *cfa) {
-    constexpr int U = (A + 1) % 3, V = (A + 2) % 3;
-    constexpr int c00 = (S << A), c10 = c00 | (1 << U), c01 = c00 | (1 << V), c11 = c10 | c01;
-    const double p00 = ph[c00 * TPB], p10 = ph[c10 * TPB], p01 = ph[c01 * TPB], p11 = ph[c11 * TPB];
-    const int npos = (p00 > 0) + (p10 > 0) + (p01 > 0) + (p11 > 0);
-    if (npos == 4) return 0.0;                                                   // eps_f = 0 (:107-108)
-    const double plane = PLANE_FROM_MESH ? __ldg(cfa + 2 * A + S) : (S ? hi[A] : lo[A]);
-    const double height = fabs(apex[A] - plane);                                 // |(apex - Cf) . Sf| / |Sf|
-    const double Lu = hi[U] - lo[U], Lv = hi[V] - lo[V];
-    double area = Lu * Lv;                                                       // eps_f = 1 (:109-110)
-    if (npos != 0) {
-        // calcFaceArea (:74-96): the face apex from the loop's first vertex A0 and the first vertex across the surface
-        const unsigned t = (w1 >> (3 * (2 * A + S))) & 7u;
-        const int iu0 = t & 1, iv0 = (t >> 1) & 1, dir = (t >> 2) & 1;
-        auto sel = [&](int iu, int iv) { return iv ? (iu ? p11 : p01) : (iu ? p10 : p00); };
-        const int iu1 = iu0 ^ (dir ^ 1), iv1 = iv0 ^ dir, iu3 = iu0 ^ dir, iv3 = iv0 ^ (dir ^ 1);
-        const double phA = sel(iu0, iv0), ph1 = sel(iu1, iv1), ph2 = sel(iu0 ^ 1, iv0 ^ 1), ph3 = sel(iu3, iv3);
-        int iuB = iu1, ivB = iv1;
-        double phB = ph1;
-        if (!(phA * ph1 <= 0)) {
-            iuB = iu0 ^ 1; ivB = iv0 ^ 1; phB = ph2;
-            if (!(phA * ph2 <= 0)) { iuB = iu3; ivB = iv3; phB = ph3; }
-        }
-        const double w = fabs(phA) / (SDF_SMALL + fabs(phA) + fabs(phB));
-        const double Au = iu0 ? hi[U] : lo[U], Av = iv0 ? hi[V] : lo[V];
-        const double Bu = iuB ? hi[U] : lo[U], Bv = ivB ? hi[V] : lo[V];
-        const double fu = Au - w * (Au - Bu), fv = Av - w * (Av - Bv);
-        // four triangles: edge length x perpendicular offset of the face apex, weighted by the edge's wet fraction
-        const double a = fabs(fu - lo[U]), b = fabs(fu - hi[U]), c = fabs(fv - lo[V]), d = fabs(fv - hi[V]);
-        area = 0.5 * fma(Lu, fma(c, line_fraction_fast(p00, p10), d * line_fraction_fast(p01, p11)),
-                         Lv * fma(a, line_fraction_fast(p00, p01), b * line_fraction_fast(p10, p11)));
+// calcLineFraction (:13-23), branch-free
+__device__ __forceinline__ double edge_fraction(double pa, double pb) {
+    const bool ta = pa > 0, tb = pb > 0;
+    const double den = fabs(pa) + fabs(pb);      // == out - in
+    const double num = ta ? fabs(pb) : fabs(pa);  // == -in
+    double q;
+    if (den < 1e-290) q = num / den;   // (planes only: both ends within 1e-290 of the surface; the seed below would flush)
+    else {
+        // num / den to within 1 ulp: MUFU seed (2^-20), two Newton steps, one residual correction
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+        r = fma(r, fma(-den, r, 1.0), r);
+        r = fma(r, fma(-den, r, 1.0), r);
+        q = num * r;
+        q = fma(fma(-den, q, num), r, q);
     }
-    return (1.0 / 3.0) * area * height;
+    return (ta && tb) ? 0.0 : ((ta || tb) ? q : 1.0);
 }
 
-template <int CTAS, bool PLANE_FROM_MESH>
-__global__ void __launch_bounds__(TPB, CTAS) k_heavy_box(InteractParams P) {
-    __shared__ double s_phi[8 * TPB];
+// Per-lane scratch in shared memory, column = the lane's thread (bank = thread: conflict-free whatever the row).  The mesh's
+// own vertex / face-loop order (btopo) makes every corner, edge and axis index of the volume phase a run-time value; rows
+// addressed by a computed index cost one LDS where a register file would cost a chain of selects — and the face / edge / vertex
+// loops stay rolled, so the whole kernel is ~1k instructions and lives in the instruction cache.
+struct BoxSmem {
+    double phi[8 * TPB];    // row = corner code
+    double lohi[6 * TPB];   // row = 2 * axis + side
+    double ef[12 * TPB];    // row = 4 * axis + (bit of axis+1) + 2 * (bit of axis+2): edge along `axis` from the corner with those bits
+    double apex[3 * TPB];
+};
+
+template <bool PLANE_FROM_MESH>
+__global__ void __launch_bounds__(TPB, BOX_CTAS_PER_SM) k_heavy_box(InteractParams P) {
+    __shared__ BoxSmem sm;
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
-    double *ph = s_phi + tid;
+    double *phi = sm.phi + tid, *lohi = sm.lohi + tid, *ef = sm.ef + tid, *apx = sm.apex + tid;
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
     const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
     for (long long k0 = q0 + (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
@@ -704,13 +695,13 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_box(InteractParams P) {
         DQ q = {1.0, {0.0, 0.0, 0.0}};
         D3 t = {0.0, 0.0, 0.0};
         int shape_idx = 0;
-        double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
         uint2 tw = {0u, 0u};
         D3 cc = {0, 0, 0};
         if (valid) {
             const double2 *b2 = reinterpret_cast<const double2 *>(m.box6 + 6 * (long long)c);
             const double2 b0 = __ldg(b2), b1 = __ldg(b2 + 1), b3 = __ldg(b2 + 2);
-            lo[0] = b0.x; lo[1] = b0.y; lo[2] = b1.x; hi[0] = b1.y; hi[1] = b3.x; hi[2] = b3.y;
+            lohi[0 * TPB] = b0.x; lohi[2 * TPB] = b0.y; lohi[4 * TPB] = b1.x;      // lo.xyz
+            lohi[1 * TPB] = b1.y; lohi[3 * TPB] = b3.x; lohi[5 * TPB] = b3.y;      // hi.xyz
             tw = __ldg(reinterpret_cast<const uint2 *>(m.btopo) + c);
             cc = ld3(m.cc, c);
             const DevSolid &S = P.solids[s];
@@ -721,13 +712,39 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_box(InteractParams P) {
         const DevShape &sh = P.shapes[shape_idx];
         const bool ident = __all_sync(FULL, !valid || quat_is_identity(q));
         int n_in = 0;
-        if (valid) {
-#pragma unroll 2
+        unsigned pm = 0;   // bit `code`: phi of that corner > 0
+        // un-rotated balls (every solid before it turns; C4): the corner coordinates are separable, so the body-frame components
+        // com + (p - t) and their squares are taken once per lattice plane (6 + 6 + 6 operations instead of 8 x 9) — the same
+        // expressions, in the same association, as the generic path evaluates per vertex (device_math.cuh SPHERE: bit-identical)
+        const bool ball_fast = ident && __all_sync(FULL, !valid || sh.s.tag == SDFIBM_SHAPE_SPHERE);
+        if (ball_fast) {
+            if (valid) {
+                double sq[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const int d = r >> 1;
+                    const double td = d == 0 ? t.x : (d == 1 ? t.y : t.z);
+                    const double b = sh.s.com[d] + (lohi[r * TPB] - td);
+                    sq[r] = b * b;
+                }
+                const double rad = sh.s.p[0], rad2 = sh.s.p[1];
+#pragma unroll
+                for (int code = 0; code < 8; ++code) {
+                    const double m2 = sq[code & 1] + sq[2 + ((code >> 1) & 1)] + sq[4 + ((code >> 2) & 1)];
+                    const double phv = sdf_filter(sqrt(m2) - rad);
+                    n_in += (m2 < rad2) ? 1 : 0;
+                    pm |= (phv > 0 ? 1u : 0u) << code;
+                    phi[code * TPB] = phv;
+                }
+            }
+        } else if (valid) {
+PRAGMA_UNROLL(BOX_VUNROLL)
             for (int code = 0; code < 8; ++code) {
-                const D3 p = {(code & 1) ? hi[0] : lo[0], (code & 2) ? hi[1] : lo[1], (code & 4) ? hi[2] : lo[2]};
+                const D3 p = {lohi[(code & 1) * TPB], lohi[(2 + ((code >> 1) & 1)) * TPB], lohi[(4 + ((code >> 2) & 1)) * TPB]};
                 double phv;
                 n_in += shape_eval<true>(sh.s, world2local_sel(q, t, p, ident), phv) ? 1 : 0;
-                ph[code * TPB] = phv;
+                pm |= (phv > 0 ? 1u : 0u) << code;
+                phi[code * TPB] = phv;
             }
         }
         if (valid) {
@@ -738,33 +755,66 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_box(InteractParams P) {
                 double dummy;
                 type = shape_eval<false>(sh.s, world2local_sel(q, t, cc, ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
                 // cell apex over cellPoints() order (geometrictools.cpp:25-45,56-58)
-                double apex[3];
                 {
                     const int cA = tw.x & 7;
-                    const double phiA = ph[cA * TPB];
+                    const double phiA = phi[cA * TPB];
                     int cB = cA;
                     double phiB = 0.0;
 #pragma unroll 1
                     for (int i = 1; i < 8; ++i) {
                         cB = (tw.x >> (3 * i)) & 7;
-                        phiB = ph[cB * TPB];
+                        phiB = phi[cB * TPB];
                         if (phiA * phiB <= 0) break;
                     }
                     const double w = fabs(phiA) / (SDF_SMALL + fabs(phiA) + fabs(phiB));
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        const double A = ((cA >> d) & 1) ? hi[d] : lo[d], B = ((cB >> d) & 1) ? hi[d] : lo[d];
-                        apex[d] = A - w * (A - B);
+                        const double A = lohi[(2 * d + ((cA >> d) & 1)) * TPB], B = lohi[(2 * d + ((cB >> d) & 1)) * TPB];
+                        apx[d * TPB] = A - w * (A - B);
                     }
-                    if (m.two_d) apex[2] = 0.0;
+                    if (m.two_d) apx[2 * TPB] = 0.0;
                 }
+                // the 12 edge fractions, each taken once (every edge belongs to two faces)
+PRAGMA_UNROLL(BOX_EUNROLL)
+                for (int e = 0; e < 12; ++e) {
+                    const int d = e >> 2, u = (d == 2) ? 0 : d + 1, v = (d == 0) ? 2 : d - 1;   // u = (d+1)%3, v = (d+2)%3
+                    const int base = ((e & 1) << u) | (((e >> 1) & 1) << v);
+                    ef[e * TPB] = edge_fraction(phi[base * TPB], phi[(base | (1 << d)) * TPB]);
+                }
+                // six pyramid terms 1/3 eps_f |(apex - Cf) . Sf| (geometrictools.cpp:61-70,98-116), face = (axis a, side sd)
                 const double *cfa = PLANE_FROM_MESH ? m.cfa6 + 6 * (long long)c : nullptr;
-                volume = box_face_term<0, 0, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
-                volume += box_face_term<0, 1, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
-                volume += box_face_term<1, 0, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
-                volume += box_face_term<1, 1, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
-                volume += box_face_term<2, 0, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
-                volume += box_face_term<2, 1, PLANE_FROM_MESH>(ph, lo, hi, apex, tw.y, cfa);
+PRAGMA_UNROLL(BOX_FUNROLL)
+                for (int f = 0; f < 6; ++f) {
+                    const int a = f >> 1, sd = f & 1, u = (a == 2) ? 0 : a + 1, v = (a == 0) ? 2 : a - 1;
+                    // the face loop of the mesh: first vertex at in-plane corner (iu0, iv0), second vertex along u (dir 0) or v (dir 1)
+                    const unsigned tq = (tw.y >> (3 * f)) & 7u;
+                    const int iu0 = tq & 1, iv0 = (tq >> 1) & 1, dir = (tq >> 2) & 1;
+                    const int k0 = (sd << a) | (iu0 << u) | (iv0 << v);
+                    const int su = 1 << u, sv = 1 << v;
+                    const int k1 = k0 ^ (dir ? sv : su), k2 = k0 ^ su ^ sv, k3 = k0 ^ (dir ? su : sv);
+                    const double phA = phi[k0 * TPB], ph1 = phi[k1 * TPB], ph2 = phi[k2 * TPB], ph3 = phi[k3 * TPB];
+                    const int npos = __popc(pm & (unsigned)((0xF00FCC33AA55ull >> (8 * f)) & 0xffu));   // corners of face f with phi > 0
+                    const double lu = lohi[(2 * u) * TPB], hu = lohi[(2 * u + 1) * TPB], lv = lohi[(2 * v) * TPB], hv = lohi[(2 * v + 1) * TPB];
+                    const double plane = PLANE_FROM_MESH ? __ldg(cfa + f) : lohi[f * TPB];
+                    const double height = fabs(apx[a * TPB] - plane);                 // |(apex - Cf) . Sf| / |Sf|
+                    const double Lu = hu - lu, Lv = hv - lv;
+                    // calcFaceArea (:74-96): the face apex from the loop's first vertex and the first vertex across the surface
+                    const bool x1 = phA * ph1 <= 0, x2 = phA * ph2 <= 0;
+                    const int kB = x1 ? k1 : (x2 ? k2 : k3);
+                    const double phB = x1 ? ph1 : (x2 ? ph2 : ph3);
+                    const double w = fabs(phA) / (SDF_SMALL + fabs(phA) + fabs(phB));
+                    const double Au = iu0 ? hu : lu, Av = iv0 ? hv : lv;
+                    const double Bu = ((kB >> u) & 1) ? hu : lu, Bv = ((kB >> v) & 1) ? hv : lv;
+                    const double fu = Au - w * (Au - Bu), fv = Av - w * (Av - Bv);
+                    // four triangles: edge length x perpendicular offset of the face apex, weighted by the edge's wet fraction
+                    const double da = fabs(fu - lu), db = fabs(fu - hu), dc = fabs(fv - lv), dd = fabs(fv - hv);
+                    const double eu0 = ef[(4 * u + 2 * sd) * TPB], eu1 = ef[(4 * u + 1 + 2 * sd) * TPB];   // along u at v = lo / hi
+                    const double ev0 = ef[(4 * v + sd) * TPB], ev1 = ef[(4 * v + sd + 2) * TPB];           // along v at u = lo / hi
+                    const double cut = 0.5 * fma(Lu, fma(dc, eu0, dd * eu1), Lv * fma(da, ev0, db * ev1));
+                    const double area = (npos == 0) ? Lu * Lv : cut;                      // eps_f = 1 (:109-110)
+                    const double term = (1.0 / 3.0) * area * height;
+                    volume += (npos == 4) ? 0.0 : term;                                   // eps_f = 0 (:107-108)
+                }
             }
             P.heavy_res[k] = make_double2(volume, __longlong_as_double((long long)(type | (s << 2))));
         }
@@ -885,11 +935,8 @@ __device__ __forceinline__ int find_member(const unsigned char *n_item, const in
     return -1;
 }
 
-__global__ void k_connectivity(ConnParams P) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.m.n_cells) return;
-    // every candidate of the cell's tile is connected by construction and no plane / tilted 2-D solid is about: nothing to certify
-    if (P.tile_proven[__ldg(P.m.tile_key + c)] && P.status->n_global == 0) return;
+// certificate of one cell: every member pair without a smaller-keyed member neighbour is a root of its solid
+__device__ __forceinline__ void conn_cell(const ConnParams &P, int c) {
     const int n = P.n_item[c];
     if (n == 0) return;
     const long long nC = P.m.n_cells;
@@ -927,6 +974,20 @@ __global__ void k_connectivity(ConnParams P) {
             }
         }
         if (!has_parent) atomicAdd(P.root_count + s, 1);
+    }
+}
+
+
+__global__ void __launch_bounds__(256) k_connectivity(ConnParams P) {
+    // nothing to certify: every binned solid is connected by construction and no plane / tilted 2-D solid is about
+    if (!P.status->need_cert && P.status->n_global == 0) return;
+    const long long nC = P.m.n_cells;
+    for (long long c0 = (long long)blockIdx.x * blockDim.x; c0 < nC; c0 += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(c0 + threadIdx.x);
+        if (c >= nC) continue;
+        // every candidate of the cell's tile is connected by construction
+        if (P.tile_proven[__ldg(P.m.tile_key + c)] && P.status->n_global == 0) continue;
+        conn_cell(P, c);
     }
 }
 

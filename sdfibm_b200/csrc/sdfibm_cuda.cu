@@ -147,6 +147,8 @@ struct StepStatus {
     int n_global;
     unsigned long long heavy_total; // (cell, solid) items that needed exact evaluation (mixed meshes: those of hexahedral cells)
     unsigned long long heavy_gen;   // mixed meshes: items of non-hexahedral cells, queued from the back of the same buffer
+    int need_cert;                  // some binned solid's cell set is not connected by construction: the certificate pass has work
+    int pad_;
 };
 
 __device__ __forceinline__ D3 ld3(const double *__restrict__ p, long long i) {
@@ -520,24 +522,18 @@ __global__ void k_solid_prepare(PrepParams P) {
     S.axis_is_z = (fabs(ax.x) <= 1e-12 && fabs(ax.y) <= 1e-12) ? 1 : 0;
     S.global = (S.kind == KIND_PLANE || (S.kind == KIND_2D && !S.axis_is_z)) ? 1 : 0;
     {
-        // A ball (disc) of radius r > the cell diagonal, lying with one cell of margin inside a complete lattice of identical boxes:
-        // every inside vertex v has, along an axis with |d_i| > h_i, a lattice neighbour strictly closer to the centre (hence
-        // inside); the walk ends at a corner of the cell that holds the centre, all of whose corners are inside (distance <= the
-        // cell diagonal < r).  So the inside vertices are lattice connected, and the member cells — the union of the 2x2x2
-        // stars of the inside vertices — are face connected: the flood fill returns all of them and the
-        // certificate pass can skip this solid.  A vertex within rounding of the surface is extremal: flipping it cannot cut the set.
+        // A ball (disc) on a complete lattice of boxes — any radius, clipped by the mesh or not, centre inside or outside it.  Let c* be
+        // the point of the mesh box nearest the centre c.  From an inside vertex v, along any axis with |v_i - c*_i| > h_i, the lattice
+        // neighbour towards c*_i stays in the mesh and is strictly closer to c (c*_i lies between v_i and c_i), hence inside; the walk
+        // ends among the <= 3x3x3 vertices around c*.  Two inside vertices u, w of that block both reach, by changing one coordinate
+        // at a time to whichever of u_i, w_i is nearer c_i, the same vertex without ever increasing a |d_i| (the computed |p - c|^2 is
+        // monotone in every |d_i|: rounding is monotone).  So the inside vertices are lattice connected, and the member cells — the
+        // union of the (clipped) 2x2x2 stars of the inside vertices, stars of lattice neighbours sharing a cell — are face connected:
+        // the flood fill returns all of them from any seed and the certificate pass can skip this solid
+        // (tests/test_connectivity_proof_cpu.py holds the claim to the oracle's real flood fill).
         const sdfibm_shape_t &sp = sh.s;
         const bool ball = sp.tag == SDFIBM_SHAPE_SPHERE, disc = sp.tag == SDFIBM_SHAPE_CIRCLE && S.axis_is_z;
-        bool ok = P.lattice_full && (ball || disc) && sp.com[0] == 0.0 && sp.com[1] == 0.0 && sp.com[2] == 0.0;
-        if (ok) {
-            const double hz = ball ? P.box_h[2] : 0.0;
-            const double diag = 2.0 * sqrt(P.box_h[0] * P.box_h[0] + P.box_h[1] * P.box_h[1] + hz * hz);
-            ok = sp.p[0] > diag * (1.0 + 1e-5);
-            for (int d = 0; d < (ball ? 3 : 2); ++d) {
-                const double marg = sp.p[0] + 2.0 * P.box_h[d] * (1.0 + 1e-5);
-                ok = ok && in.pos[d] - marg > P.mesh_lo[d] && in.pos[d] + marg < P.mesh_hi[d];
-            }
-        }
+        const bool ok = P.lattice_full && (ball || disc) && sp.com[0] == 0.0 && sp.com[1] == 0.0 && sp.com[2] == 0.0;
         S.conn_proven = ok ? 1 : 0;
     }
     if (sub == 0) P.out[s] = S;
@@ -616,6 +612,7 @@ __global__ void k_bin_sort_entries(const int *bin_off, int *bin_list, int n_bins
         const int s = bin_list[pos];
         const DevSolid &S = solids[s];
         proven &= S.conn_proven;
+        if (!S.conn_proven) status->need_cert = 1;
         const double slack = 4e-6 * (half_ext + S.r_out + rad_max);
         BinEntry e;
         e.x = (float)(S.pos[0] - ox); e.y = (float)(S.pos[1] - oy); e.z = (float)(S.pos[2] - oz);
@@ -1003,6 +1000,13 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         } else {
             const double h = std::cbrt(ext[0] * ext[1] * ext[2] / (double)nC);
             T[0] = T[1] = 8.0 * h; T[2] = 4.0 * h;
+        }
+        if (const char *e = getenv("SDFIBM_TILE")) {   // experiments: tile extents in mean cell sizes, "tx,ty,tz"
+            double t3[3];
+            if (sscanf(e, "%lf,%lf,%lf", &t3[0], &t3[1], &t3[2]) == 3 && t3[0] > 0 && t3[1] > 0 && t3[2] > 0) {
+                const double h = two_d ? std::sqrt(ext[0] * ext[1] / (double)nC) : std::cbrt(ext[0] * ext[1] * ext[2] / (double)nC);
+                T[0] = t3[0] * h; T[1] = t3[1] * h; if (!two_d) T[2] = t3[2] * h;
+            }
         }
         for (;;) {
             double nt = 1;
@@ -1443,8 +1447,8 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         else k_classify<256, 8, false, false><<<grid, 256, 0, st>>>(I);
     };
     auto launch_heavy = [&]() {
-        if (ctx->dm.box_exact == 2) k_heavy_box<BOX_CTAS_PER_SM, false><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
-        else if (ctx->dm.box_exact == 1) k_heavy_box<BOX_CTAS_PER_SM, true><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
+        if (ctx->dm.box_exact == 2) k_heavy_box<false><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
+        else if (ctx->dm.box_exact == 1) k_heavy_box<true><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
         else if (ctx->dm.is_hex || ctx->dm.mixed) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
         if (!ctx->dm.is_hex) k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
     };
@@ -1523,7 +1527,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     if (!replay) {
         ConnParams C;
         C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count; C.tile_proven = ctx->tile_proven.p; C.status = ctx->status;
-        k_connectivity<<<grid_for(nC, 256), 256, 0, st>>>(C);
+        k_connectivity<<<std::min(grid_for(nC, 256), ctx->n_sm * 8), 256, 0, st>>>(C);
         ++ctx->launches;
     }
     k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts, ctx->root_count, n_solids, ctx->status, dFT, ctx->scal.p);

@@ -25,25 +25,34 @@ for i, h in enumerate(hdr):
             continue
         if v > 3:
             print(f"  stall {h.replace('smsp__warp_issue_stalled_','').replace('_per_warp_active.pct',''):40s} {v:.1f}")
-src = subprocess.run(["ncu", "-i", rep] + kfilt + ["--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
-if len(rows) > 2:
-    h = rows[0]
-    def col(name):
-        for i, x in enumerate(h):
-            if x == name:
-                return i
-        return None
-    ci, cs, cl = col("# Samples") or col("Warp Stall Sampling (All Samples)"), col("Source"), col("#")
-    cinst = col("Instructions Executed")
-    agg = []
-    for r in rows[1:]:
+stall = {}
+for i, h in enumerate(hdr):
+    if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
         try:
-            agg.append((int(r[ci]), int(r[cinst]) if cinst is not None and r[cinst] else 0, r[cl] if cl is not None else "", r[cs][:110]))
+            stall[h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]] = float(vals[i])
+        except ValueError:
+            pass
+tot = sum(stall.values()) or 1.0
+print("   stalls (share of warp-cycles): " + ", ".join(f"{k} {100 * v / tot:.0f}%" for k, v in sorted(stall.items(), key=lambda kv: -kv[1])[:7]))
+# per-source-line view (cuda,sass): rows with a line number carry the aggregate of the line's SASS
+src = subprocess.run(["ncu", "-i", rep] + kfilt + ["--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+agg = []
+fname, cols = "", None
+for r in csv.reader(io.StringIO(src)):
+    if not r:
+        continue
+    if r[0] == "File Path":
+        fname = r[1].split("/")[-1]
+    elif r[0] == "Line No":
+        cols = {x: i for i, x in enumerate(r)}
+    elif cols and r[0] not in ("", "Function Name", "Kernel Name"):
+        try:
+            agg.append((int(r[cols["# Samples"]]), int(r[cols["Instructions Executed"]]), f"{fname}:{r[0]}", r[1].strip()[:110]))
         except Exception:
             pass
+if agg:
     tot = sum(a[0] for a in agg) or 1
     toti = sum(a[1] for a in agg) or 1
-    print(f"total samples {tot}, total inst {toti}")
+    print(f"total samples {tot}, total warp-inst {toti}")
     for smp, ins, ln, txt in sorted(agg, reverse=True)[:topn]:
-        print(f"{100*smp/tot:5.1f}% smp {100*ins/toti:5.1f}% inst  L{ln}: {txt}")
+        print(f"{100*smp/tot:5.1f}% smp {100*ins/toti:5.1f}% inst  {ln}: {txt}")
