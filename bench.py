@@ -159,7 +159,7 @@ def build_case(args, rank, world):
         case = cases.case_c5_block(rank, world, n=n, n_solids=n_solids, n_side=n_side)
         desc = {"workload": f"C5: {n}^3 hex cells, {n_solids} Sphere r=4.5 / Ellipsoid (5,4.5,4) mixed, jittered {n_side}^3 lattice, "
                             f"seed 12345; block split {cases.decompose_simple(world)}",
-                "parallelism": f"decomposePar-simple x{world}, solids replicated, 1 NCCL allreduce(6N fp64)/step"}
+                "parallelism": f"decomposePar-simple x{world}, solids replicated, 1 NCCL allreduce(6N fp64)/step inside the library (sdfibm_comm_init)"}
     return wl, case, desc
 
 
@@ -408,24 +408,20 @@ def main():
     from sdfibm_b200 import capi
     solids_pinned = capi.pinned_like(np.ascontiguousarray(case["solids"], dtype=capi.SOLID_DTYPE))   # the host side's own solid array
 
-    rep = None
     if world > 1:
+        # the library's own NCCL communicator (C ABI: sdfibm_comm_init): from here on every interact uploads this rank's 1/N slice
+        # of the replicated solid array, all-gathers the slices over NVLink, and all-reduces the per-solid force/torque on the
+        # context stream right behind the kernels (replaces the 2N Foam::reduce calls of solidcloud.cpp:427-431)
         from sdfibm_b200 import parallel
-        rep = parallel.ReplicatedSolids(nS, solids_pinned.dtype.itemsize, dev)
+        parallel.init_library_comm(ctx)
 
-    def step_device_gathered():
-        # the replicated solid states reach the GPUs as one 1/N PCIe upload per rank + an NCCL all-gather over NVLink
-        ctx.interact_device_solids(rep.refresh(solids_pinned), nS, dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(),
-                                   dFs.data_ptr(), dTs.data_ptr(), dCt.data_ptr(), dFT.data_ptr(), may_be_global=False)
-        dist.all_reduce(dFT)  # replaces the 2N Foam::reduce calls of solidcloud.cpp:427-431
+    comm_ms = []
 
     def step_device():
-        if rep is not None and not os.environ.get("SDFIBM_BENCH_FULL_UPLOAD"):
-            return step_device_gathered()
         ctx.interact_device(solids_pinned, dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(), dFs.data_ptr(),
                             dTs.data_ptr(), dCt.data_ptr(), dFT.data_ptr())
         if world > 1:
-            dist.all_reduce(dFT)  # replaces the 2N Foam::reduce calls of solidcloud.cpp:427-431
+            comm_ms.append(ctx.comm_last_ms())
 
     def barrier():
         if world > 1:
@@ -492,12 +488,8 @@ def main():
         hUn = hU.numpy()
 
         def step_host():
+            # (N > 1: force/torque comes back summed over the ranks — the library's all-reduce, solidcloud.cpp:427-431)
             ctx.interact(solids_pinned, hUn, case["dt"], case["rhof"], out=out)
-            if world > 1:
-                # host façade semantics: force/torque reduced across ranks (solidcloud.cpp:427-431)
-                dFT.copy_(hFT, non_blocking=True)
-                dist.all_reduce(dFT)
-                hFT.copy_(dFT, non_blocking=True)
 
         e_steps = max(2, min(args.steps, 5))
         ms_e, _, _ = timed(step_host, e_steps, max(1, min(args.warmup, 3)))
@@ -514,11 +506,13 @@ def main():
     if world > 1:
         # one extra untimed step WITHOUT the all-reduce: this rank's partial sums; their NCCL sum must reproduce the timed step's dFT
         total_timed = dFT.clone()
+        ctx.comm_options(auto_reduce=False, gather_solids=True)
         ctx.interact_device(solids_pinned, dU.data_ptr(), case["dt"], case["rhof"], dAs.data_ptr(), dFs.data_ptr(),
                             dTs.data_ptr(), dCt.data_ptr(), dFT.data_ptr())
+        ctx.comm_options(auto_reduce=True, gather_solids=True)
         partial = dFT.clone()
         total_again = partial.clone()
-        dist.all_reduce(total_again)
+        dist.all_reduce(total_again)   # torch's own NCCL as the independent check of the library's all-reduce
         allreduce_dev = float((total_again - total_timed).abs().max().item() / max(float(total_timed.abs().max().item()), 1e-300))
     else:
         partial = dFT
@@ -556,6 +550,7 @@ def main():
                           "k_connectivity+finalise": split_mean[3], "solid_binning": split_mean[4],
                           "interact_kernels": kern_ms, "pipeline_device": pipe_ms, "step_wall_on_stream": ms_per_step,
                           "heavy_items": stats["heavy_items"],
+                          "comm_device_ms": (float(np.mean(comm_ms[-args.steps:])) if comm_ms else None),
                           "host_us": dict(zip(("stage_solids", "enqueue", "wait_gpu", "call"), host_mean))},
             "roofline": {"bound": "hbm", "kernel": f"one graph launch of the interact pipeline: binning + k_classify + k_heavy + k_final + k_connectivity (k_heavy is {100 * heavy_share:.0f}% of it)", "achieved": achieved,
                          "achieved_interact_kernels_only": alg / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -601,7 +596,7 @@ def main():
     # ---- N > 1: the SAME workload on ONE GPU, in the same run (rank 0, after the other ranks have left): the base of the scaling figure
     if rank == 0 and world > 1 and not args.no_base:
         try:
-            del dU, dAs, dFs, dTs, dCt, dFT, partial, total_timed, total_again, rep, case, mesh
+            del dU, dAs, dFs, dTs, dCt, dFT, partial, total_timed, total_again, case, mesh
             import gc
             gc.collect()
             torch.cuda.empty_cache()

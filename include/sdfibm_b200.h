@@ -200,9 +200,30 @@ int sdfibm_last_host_timings(sdfibm_context *ctx, double us[4]);
 int sdfibm_collide(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double delta,
                    int32_t *pairs, int64_t pair_capacity, int64_t *n_pairs, double *force_torque);
 
-/* ---- device-resident access for the multi-GPU host (allreduce by the caller's NCCL) -- */
+/* ---- device-resident access for the multi-GPU host --------------------------------- */
 int sdfibm_stream(sdfibm_context *ctx, void **cuda_stream);
 int sdfibm_synchronize(sdfibm_context *ctx);
+
+/* ---- cross-rank exchange: one process per GPU, cells partitioned (decomposePar), solids replicated ----
+ * Replaces the 2N Foam::reduce calls of src/solidcloud.cpp:427-431 by ONE ncclAllReduce(sum) of 6N fp64 on the context
+ * stream.  NCCL is bound at run time (dlopen of libnccl.so.2): a serial host never needs it.
+ *   rank 0:      sdfibm_comm_unique_id(id)  ->  the host broadcasts the 128 bytes (MPI_Bcast / Pstream::scatter / a file)
+ *   every rank:  sdfibm_comm_init(ctx, id, rank, n_ranks)      (collective)
+ * After sdfibm_comm_init every sdfibm_interact / sdfibm_interact_device on the context
+ *   - uploads only this rank's 1/N slice of the (replicated) solid array and all-gathers the slices over NVLink, and
+ *   - returns force_torque already summed over the ranks (the all-reduce is enqueued right behind the kernels; a rank that
+ *     has to re-run its step — queue growth, flood-fill replay — tells the others through a flag that rides the same launch).
+ * Both calls are COLLECTIVE from then on: every rank must make them with the same solid array.  sdfibm_comm_options switches
+ * either behaviour off (e.g. to reduce by MPI instead); sdfibm_allreduce_force_torque is the bare collective on a device
+ * array, in place, stream-ordered (no host synchronisation). */
+#define SDFIBM_COMM_ID_BYTES 128
+int sdfibm_comm_unique_id(void *id /* [SDFIBM_COMM_ID_BYTES] */);
+int sdfibm_comm_init(sdfibm_context *ctx, const void *id, int rank, int n_ranks);
+int sdfibm_comm_options(sdfibm_context *ctx, int auto_reduce, int gather_solids);
+int sdfibm_comm_destroy(sdfibm_context *ctx);
+int sdfibm_allreduce_force_torque(sdfibm_context *ctx, double *d_force_torque, int n_solids);
+/* device time (ms) of the collectives of the last interact on this context */
+int sdfibm_comm_last_ms(sdfibm_context *ctx, double *ms);
 
 /* ---- Foam-free mesh helpers (stand-alone harness; OpenFOAM supplies these in the drop-in) */
 /* derived geometry + connectivity from polyMesh primitives (points/faces/owner/neighbour) */

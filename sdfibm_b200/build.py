@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     "-fmad=false",               # strict predicates: no FMA contraction
     "-Xcompiler", "-fPIC,-ffp-contract=off",
     "-shared",
+    "-ldl",
 ]
 
 

@@ -69,6 +69,12 @@ SYMBOLS = {
     "sdfibm_fix_internal_device": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "sdfibm_mean_field": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
     "sdfibm_mean_field_sums": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
+    "sdfibm_comm_unique_id": (C.c_int, [_VP]),
+    "sdfibm_comm_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "sdfibm_comm_options": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "sdfibm_comm_destroy": (C.c_int, [_VP]),
+    "sdfibm_allreduce_force_torque": (C.c_int, [_VP, _VP, C.c_int]),
+    "sdfibm_comm_last_ms": (C.c_int, [_VP, c_double_p]),
     "sdfibm_candidate_counts": (C.c_int, [_VP, c_int64_p]),
     "sdfibm_candidate_lists": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "sdfibm_last_stats": (C.c_int, [_VP, c_int64_p]),

@@ -77,6 +77,35 @@ class Context:
                                                            capi.ptr(dTs), capi.ptr(dCt), capi.ptr(dFT)))
         self.n_solids = int(n_solids)
 
+    # ---- cross-rank exchange (NCCL inside the library) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0: the 128-byte NCCL id every rank passes to comm_init (broadcast it with whatever the host has)."""
+        buf = C.create_string_buffer(128)
+        capi.check(capi.load().sdfibm_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        """Collective.  From here on interact / interact_device return force/torque summed over the ranks (one ncclAllReduce on
+        the context stream, src/solidcloud.cpp:427-431) and upload only this rank's slice of the replicated solid array."""
+        assert len(uid) == 128
+        capi.check(self._lib.sdfibm_comm_init(self._h, C.c_char_p(uid), int(rank), int(n_ranks)))
+
+    def comm_options(self, auto_reduce: bool = True, gather_solids: bool = True):
+        capi.check(self._lib.sdfibm_comm_options(self._h, int(bool(auto_reduce)), int(bool(gather_solids))))
+
+    def comm_destroy(self):
+        capi.check(self._lib.sdfibm_comm_destroy(self._h))
+
+    def allreduce_force_torque(self, dFT: int, n_solids: int):
+        """In-place sum over the ranks of a device array [6 n_solids], stream-ordered on the context stream."""
+        capi.check(self._lib.sdfibm_allreduce_force_torque(self._h, capi.ptr(dFT), int(n_solids)))
+
+    def comm_last_ms(self) -> float:
+        ms = C.c_double()
+        capi.check(self._lib.sdfibm_comm_last_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     # ---- SolidCloud::fixInternal ----
     def fix_internal(self, solids: np.ndarray, U: np.ndarray) -> np.ndarray:
         solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)

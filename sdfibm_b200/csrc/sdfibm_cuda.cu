@@ -12,6 +12,8 @@
 //
 // Compiled with -fmad=false: predicates are strict `<` on un-contracted fp64.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound at run time (sdfibm_comm_*), a host that never calls them needs no NCCL
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -593,6 +595,9 @@ __device__ __forceinline__ void bin_insertion_sort(int *lst, int beg, int end) {
     }
 }
 
+#ifndef FINAL_CTAS
+#define FINAL_CTAS 4
+#endif
 #include "interact_kernels.cuh"
 
 // Thread per bin: sort the bin's solids by id, then write the inline fp32 candidate records k_classify reads.  The radii carry
@@ -835,6 +840,19 @@ struct sdfibm_context {
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
     const sdfibm_solid_t *ext_solids = nullptr;   // device-resident solid records supplied by the caller for the current call
     int n_global_hint = 0;   // host-side: some solid may be on the global list (selects the k_classify variant)
+    // cross-rank exchange (sdfibm_comm_*): one NCCL communicator over the ranks that share the replicated solid cloud
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_n = 1;
+    bool comm_auto_reduce = false;       // every interact all-reduces the per-solid (F, T) sums before it returns
+    bool comm_gather_solids = false;     // the replicated solid states arrive as one 1/N PCIe upload per rank + an all-gather
+    DevBuf<double> ft_partial;           // this rank's sums (the all-reduce is out of place: a local retry keeps them)
+    DevBuf<double> retry_flag;           // [0] this rank must re-run the step (overflow / replay), [1] sum over ranks
+    double *h_retry_sum = nullptr;       // pinned
+    DevBuf<sdfibm_solid_t> solids_slice, solids_gathered;
+    double t_comm_ms = 0;                // device time of the last step's collectives
+    bool gathered_now = false;           // the current call's solid records are in solids_gathered
+    double *reduce_out = nullptr;        // run_pipeline: all-reduce the sums into this buffer right behind the first pass
+    cudaEvent_t ev_comm[2] = {nullptr, nullptr};
     int64_t flagged_last = 0;
 };
 
@@ -876,6 +894,76 @@ static void shape_bounds(const sdfibm_shape_t &s, DevShape &d) {
     d.pad = 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time: the soname every NCCL 2.x ships (a process that already holds one — torch's bundled copy —
+// gets that one back, so there are never two NCCL instances in one process)
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    if (api.handle || !api.error.empty()) return &api;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.error = std::string("NCCL is not loadable: ") + dlerror(); return &api; }
+    auto sym = [&](const char *n) { void *f = dlsym(h, n); if (!f && api.error.empty()) api.error = std::string("NCCL symbol missing: ") + n; return f; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    if (api.error.empty()) api.handle = h;
+    return &api;
+}
+#define NCCL_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        ncclResult_t r__ = (expr);                                                                       \
+        if (r__ != ncclSuccess)                                                                          \
+            return fail(SDFIBM_ERR_CUDA, std::string(#expr) + ": " + nccl_api()->GetErrorString(r__));   \
+    } while (0)
+
+// this rank has to run the step again (a capacity grew, or a solid needs the flood-fill replay): the other ranks must learn it,
+// because the all-reduce that follows is collective
+__global__ void k_retry_flag(const StepStatus *st, long long heavy_cap, double *flag) {
+    const bool again = st->bin_overflow || st->heavy_total + st->heavy_gen > (unsigned long long)heavy_cap || st->n_flagged > 0;
+    flag[0] = again ? 1.0 : 0.0;
+}
+
+// per-solid (F, T): sum over ranks of `partial` into `out` (one ncclAllReduce of 6N fp64 instead of the reference's 2N
+// Foam::reduce calls, src/solidcloud.cpp:427-431) and, grouped into the same launch, the sum of the ranks' retry flags
+static int enqueue_comm_reduce(sdfibm_context *ctx, const double *partial, double *out, int n_solids, bool with_flag) {
+    NcclApi *a = nccl_api();
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(cudaEventRecord(ctx->ev_comm[0], st));
+    if (with_flag) {
+        k_retry_flag<<<1, 1, 0, st>>>(ctx->status, (long long)ctx->heavy.n, ctx->retry_flag.p);
+        NCCL_TRY(a->GroupStart());
+    }
+    NCCL_TRY(a->AllReduce(partial, out, 6 * (size_t)n_solids, ncclDouble, ncclSum, ctx->comm, st));
+    if (with_flag) {
+        NCCL_TRY(a->AllReduce(ctx->retry_flag.p, ctx->retry_flag.p + 1, 1, ncclDouble, ncclSum, ctx->comm, st));
+        NCCL_TRY(a->GroupEnd());
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_retry_sum, ctx->retry_flag.p + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_comm[1], st));
+    return SDFIBM_OK;
+}
+
 extern "C" {
 
 int sdfibm_version(void) { return 100; }
@@ -900,6 +988,9 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(StepStatus)));
     CUDA_TRY(cudaMallocHost(&ctx->h_scal, 2 * sizeof(double)));
+    CUDA_TRY(cudaMallocHost(&ctx->h_retry_sum, sizeof(double)));
+    *ctx->h_retry_sum = 0.0;
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev_comm[i]));
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_BOX")) ctx->allow_box = atoi(e) != 0;
@@ -927,6 +1018,10 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
     ctx->tile_proven.release(); ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->btopo.release(); ctx->box6.release(); ctx->cfa6.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->comm && nccl_api()->handle) nccl_api()->CommDestroy(ctx->comm);
+    ctx->ft_partial.release(); ctx->retry_flag.release(); ctx->solids_slice.release(); ctx->solids_gathered.release();
+    if (ctx->h_retry_sum) cudaFreeHost(ctx->h_retry_sum);
+    for (int i = 0; i < 2; ++i) if (ctx->ev_comm[i]) cudaEventDestroy(ctx->ev_comm[i]);
     ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release(); ctx->slab_start.release();
     ctx->global_list.release(); ctx->slots.release();
     ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
@@ -1101,7 +1196,8 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     CUDA_TRY(ctx->slots.ensure(nC * ctx->K));
     CUDA_TRY(ctx->n_item.ensure(nC));
     {
-        const size_t cap = std::max<size_t>(1 << 20, nC / 2);
+        size_t cap = std::max<size_t>(1 << 20, nC / 2);
+        if (const char *e = getenv("SDFIBM_HEAVY_CAP0")) cap = std::max<size_t>(16, (size_t)atoll(e));   // tests: force the growth path
         CUDA_TRY(ctx->heavy.ensure(cap));
         CUDA_TRY(ctx->heavy_res.ensure(cap));
     }
@@ -1267,7 +1363,7 @@ int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) 
 static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, double dt, double rhof, double *dAs,
                         double *dFs, double *dTs, double *dCt, double *dFT, bool replay);
 
-static int stage_solids(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n) {
+static int stage_solids(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n, bool may_gather = false) {
     if ((size_t)n > ctx->h_solids_cap) {
         if (ctx->h_solids) cudaFreeHost(ctx->h_solids);
         ctx->h_solids = nullptr;
@@ -1288,6 +1384,26 @@ static int stage_solids(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
         }
     }
     ctx->n_global_hint = hint;
+    ctx->gathered_now = false;
+    if (may_gather && ctx->comm && ctx->comm_gather_solids && ctx->comm_n > 1 && n >= 8 * ctx->comm_n) {
+        // the solid cloud is replicated (every rank's host holds the same array): each rank uploads one 1/N slice over PCIe and
+        // the slices are all-gathered over NVLink instead of N identical full uploads
+        const size_t per = ((size_t)n + ctx->comm_n - 1) / ctx->comm_n;
+        CUDA_TRY(ctx->solids_slice.ensure(per));
+        CUDA_TRY(ctx->solids_gathered.ensure(per * ctx->comm_n));
+        const size_t b = std::min((size_t)n, per * ctx->comm_rank), e = std::min((size_t)n, b + per);
+        const void *src = solids + b;
+        cudaPointerAttributes attr;
+        if (e > b && (cudaPointerGetAttributes(&attr, solids) != cudaSuccess || attr.type != cudaMemoryTypeHost)) {
+            cudaGetLastError();
+            memcpy(ctx->h_solids, solids + b, sizeof(sdfibm_solid_t) * (e - b));
+            src = ctx->h_solids;
+        }
+        if (e > b) CUDA_TRY(cudaMemcpyAsync(ctx->solids_slice.p, src, sizeof(sdfibm_solid_t) * (e - b), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(nccl_api()->AllGather(ctx->solids_slice.p, ctx->solids_gathered.p, per * sizeof(sdfibm_solid_t), ncclChar, ctx->comm, ctx->stream));
+        ctx->gathered_now = true;
+        return SDFIBM_OK;
+    }
     CUDA_TRY(ctx->solids_in.ensure(n));
     // page-locked caller memory (sdfibm_alloc_pinned, cudaHostRegister, ...) is copied from directly; anything else is staged
     const void *src = solids;
@@ -1324,12 +1440,26 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     if (n_solids > (1 << 28) - 4) return fail(SDFIBM_ERR_ARG, "too many solids");
     int rc = SDFIBM_OK;
     const auto h0 = std::chrono::steady_clock::now();
-    if (!ctx->pipe.active && !ctx->ext_solids) rc = stage_solids(ctx, solids, n_solids);   // the host-buffer entry stages them ahead of its U copies
+    if (!ctx->pipe.active && !ctx->ext_solids) rc = stage_solids(ctx, solids, n_solids, true);   // the host-buffer entry stages them ahead of its U copies
     if (rc) return rc;
     const auto h1 = std::chrono::steady_clock::now();
     ctx->t_host_us[0] = std::chrono::duration<double, std::micro>(h1 - h0).count();
     ctx->launches = 0;
+    // cross-rank sum of the per-solid (F, T) (src/solidcloud.cpp:427-431) on the context stream, right behind the kernels: the
+    // step's sums go to a buffer of their own and the all-reduce writes the caller's array, so a rank that has to re-run the
+    // step (queue growth, flood-fill replay) still holds its partial sums; the ranks' "again" flags ride the same NCCL launch
+    const bool reduce = ctx->comm && ctx->comm_auto_reduce && ctx->comm_n > 1;
+    double *const dFT_out = dFT;
+    if (reduce) {
+        CUDA_TRY(ctx->ft_partial.ensure(6 * (size_t)n_solids));
+        CUDA_TRY(ctx->retry_flag.ensure(2));
+        dFT = ctx->ft_partial.p;
+        ctx->reduce_out = dFT_out;
+        *ctx->h_retry_sum = 0.0;
+    }
+    ctx->t_comm_ms = 0;
     rc = run_pipeline(ctx, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT, false);
+    ctx->reduce_out = nullptr;
     ctx->t_host_us[3] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
     if (rc) return rc;
     ctx->flagged_last = ctx->last.n_flagged;
@@ -1378,6 +1508,12 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         if (rc) return rc;
         ctx->last_used_replay = true;
     }
+    if (reduce && *ctx->h_retry_sum > 0.0) {
+        // some rank ran its step again: every rank reduces again (the flag sum is the same number everywhere)
+        rc = enqueue_comm_reduce(ctx, ctx->ft_partial.p, dFT_out, n_solids, false);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     ctx->last_Ct = dCt;
     ctx->n_solids_last = n_solids;
     return SDFIBM_OK;
@@ -1398,7 +1534,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         // status word, root / pair counters, bin counters and cursors live in one block: one memset
         CUDA_TRY(cudaMemsetAsync(ctx->zero_block.p, 0, ctx->zero_block.n, st));
         PrepParams P;
-        P.solids = ctx->ext_solids ? ctx->ext_solids : ctx->solids_in.p; P.shapes = ctx->shapes.p; P.n_solids = n_solids; P.n_shapes = (int)ctx->h_shapes.size();
+        P.solids = ctx->ext_solids ? ctx->ext_solids : (ctx->gathered_now ? ctx->solids_gathered.p : ctx->solids_in.p); P.shapes = ctx->shapes.p; P.n_solids = n_solids; P.n_shapes = (int)ctx->h_shapes.size();
         P.out = ctx->solids.p; P.grid = g; P.rad3_max = ctx->rad3_max; P.radxy_max = ctx->radxy_max;
         for (int d = 0; d < 3; ++d) { P.mesh_lo[d] = ctx->bmin[d]; P.mesh_hi[d] = ctx->bmax[d]; P.origin[d] = ctx->dm.origin[d]; }
         P.half_ext = ctx->half_ext; P.rad_max = (double)std::max(ctx->rad3_max, ctx->radxy_max);
@@ -1502,7 +1638,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
             if (p1 > p0) {
                 I.c_begin = (int)p0; I.c_end = (int)p1;
                 CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
-                k_final<4><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
+                k_final<FINAL_CTAS><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
             }
             CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
             for (int j = 0; j < NCH; ++j) {
@@ -1520,7 +1656,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         ctx->launches += ctx->n_chunk - 3;
     } else {
         I.c_begin = 0; I.c_end = nC;
-        k_final<4><<<grid_for(nC, 256), 256, 0, st>>>(I);
+        k_final<FINAL_CTAS><<<grid_for(nC, 256), 256, 0, st>>>(I);
     }
     CUDA_TRY(rec(ctx->ev[4]));
     ctx->launches += 3;
@@ -1584,7 +1720,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         const auto q0 = std::chrono::steady_clock::now();
         if (use_graph) {
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
-                                      (uint64_t)(ctx->ext_solids ? ctx->ext_solids : ctx->solids_in.p), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
+                                      (uint64_t)(ctx->ext_solids ? ctx->ext_solids : (ctx->gathered_now ? ctx->solids_gathered.p : ctx->solids_in.p)), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
                                       (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p ^ ((uint64_t)ctx->tile_proven.p << 1), (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
                                       (uint64_t)ctx->n_global_hint};
@@ -1610,8 +1746,14 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             const int rc = enqueue_pipeline(ctx, n_solids, dU, dAs, dFs, dTs, dCt, dFT, replay, chunked, false);
             if (rc) return rc;
         }
+        const bool reduced_here = ctx->reduce_out && attempt == 0 && !replay;
+        if (reduced_here) {
+            const int rc = enqueue_comm_reduce(ctx, dFT, ctx->reduce_out, n_solids, true);
+            if (rc) return rc;
+        }
         const auto w0 = std::chrono::steady_clock::now();
         CUDA_TRY(cudaStreamSynchronize(st));
+        if (reduced_here) { float x = 0; cudaEventElapsedTime(&x, ctx->ev_comm[0], ctx->ev_comm[1]); ctx->t_comm_ms = x; }
         ctx->t_host_us[2] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
         ctx->t_host_us[1] = std::chrono::duration<double, std::micro>(w0 - q0).count();
         {
@@ -1680,7 +1822,7 @@ int sdfibm_interact(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_sol
         return SDFIBM_OK;
     }
     // the copy engines are FIFO across streams: the small solid upload the kernels depend on goes first
-    rc = stage_solids(ctx, solids, n_solids);
+    rc = stage_solids(ctx, solids, n_solids, true);
     if (rc) return rc;
     // U is not needed before k_final: its chunks stream in on s_in while binning / k_classify / k_heavy run; each chunk of the
     // fields leaves on s_out as soon as its k_final launch is done (PCIe is full duplex: copy-in and copy-out overlap too).
@@ -1709,6 +1851,68 @@ int sdfibm_interact_device_solids(sdfibm_context *ctx, const sdfibm_solid_t *d_s
     const int rc = sdfibm_interact_device(ctx, nullptr, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT);
     ctx->ext_solids = nullptr;
     return rc;
+}
+
+// ---- cross-rank exchange (NCCL over NVLink) ----
+int sdfibm_comm_unique_id(void *id) {
+    if (!id) return fail(SDFIBM_ERR_ARG, "sdfibm_comm_unique_id: null argument");
+    NcclApi *a = nccl_api();
+    if (!a->handle) return fail(SDFIBM_ERR_UNSUPPORTED, a->error);
+    static_assert(sizeof(ncclUniqueId) == SDFIBM_COMM_ID_BYTES, "ncclUniqueId size");
+    NCCL_TRY(a->GetUniqueId(reinterpret_cast<ncclUniqueId *>(id)));
+    return SDFIBM_OK;
+}
+
+int sdfibm_comm_init(sdfibm_context *ctx, const void *id, int rank, int n_ranks) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SDFIBM_ERR_ARG, "sdfibm_comm_init: bad argument");
+    if (ctx->comm) return fail(SDFIBM_ERR_STATE, "sdfibm_comm_init: the context already has a communicator");
+    NcclApi *a = nccl_api();
+    if (!a->handle) return fail(SDFIBM_ERR_UNSUPPORTED, a->error);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NCCL_TRY(a->CommInitRank(&ctx->comm, n_ranks, uid, rank));
+    ctx->comm_rank = rank;
+    ctx->comm_n = n_ranks;
+    ctx->comm_auto_reduce = true;
+    ctx->comm_gather_solids = true;
+    drop_graph(ctx);
+    return SDFIBM_OK;
+}
+
+int sdfibm_comm_options(sdfibm_context *ctx, int auto_reduce, int gather_solids) {
+    if (!ctx) return fail(SDFIBM_ERR_ARG, "sdfibm_comm_options: null context");
+    ctx->comm_auto_reduce = auto_reduce != 0;
+    ctx->comm_gather_solids = gather_solids != 0;
+    drop_graph(ctx);
+    return SDFIBM_OK;
+}
+
+int sdfibm_comm_destroy(sdfibm_context *ctx) {
+    if (!ctx) return fail(SDFIBM_ERR_ARG, "sdfibm_comm_destroy: null context");
+    if (ctx->comm) {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        NCCL_TRY(nccl_api()->CommDestroy(ctx->comm));
+    }
+    ctx->comm = nullptr;
+    ctx->comm_n = 1;
+    ctx->comm_rank = 0;
+    return SDFIBM_OK;
+}
+
+int sdfibm_allreduce_force_torque(sdfibm_context *ctx, double *d_force_torque, int n_solids) {
+    if (!ctx || !d_force_torque || n_solids < 0) return fail(SDFIBM_ERR_ARG, "sdfibm_allreduce_force_torque: bad argument");
+    if (!ctx->comm) return fail(SDFIBM_ERR_STATE, "sdfibm_allreduce_force_torque: call sdfibm_comm_init first");
+    if (n_solids == 0) return SDFIBM_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return enqueue_comm_reduce(ctx, d_force_torque, d_force_torque, n_solids, false);
+}
+
+int sdfibm_comm_last_ms(sdfibm_context *ctx, double *ms) {
+    if (!ctx || !ms) return fail(SDFIBM_ERR_ARG, "null argument");
+    *ms = ctx->t_comm_ms;
+    return SDFIBM_OK;
 }
 
 int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *dU, const double *dCt) {
@@ -1781,11 +1985,14 @@ int sdfibm_mean_field_sums(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     const double *keep_Ct = ctx->last_Ct;
     const int keep_n = ctx->n_solids_last;
     CUDA_TRY(cudaMemcpyAsync(ctx->sU.p, field, sizeof(double) * 3 * nC, cudaMemcpyHostToDevice, st));
+    const bool keep_reduce = ctx->comm_auto_reduce, keep_gather = ctx->comm_gather_solids;
+    ctx->comm_auto_reduce = false; ctx->comm_gather_solids = false;   // this rank's sums: the caller reduces numerator and denominator
     int rc = sdfibm_interact_device(ctx, rest.data(), n_solids, ctx->sU.p, 1.0, 1.0, tAs, tFs, tTs, tCt, ctx->sFT.p);
     if (!rc) {
         k_fill_unit_x<<<grid_for((long long)nC, 256), 256, 0, st>>>(ctx->sU.p, (long long)nC);
         rc = sdfibm_interact_device(ctx, rest.data(), n_solids, ctx->sU.p, 1.0, 1.0, tAs, tFs, tTs, tCt, ctx->sFT.p + 6 * (size_t)n_solids);
     }
+    ctx->comm_auto_reduce = keep_reduce; ctx->comm_gather_solids = keep_gather;
     ctx->last_Ct = keep_Ct;   // the sampler leaves the coupling state of the last interact alone (its candidate lists are replaced)
     ctx->n_solids_last = keep_n;
     if (rc) return rc;

@@ -29,6 +29,21 @@ def local_to_global_cells(rank: int, world: int, n) -> np.ndarray:
     return (i + n[0] * (j + n[1] * k)).reshape(-1)
 
 
+def init_library_comm(ctx):
+    """Give `ctx` (a Context) the library's own NCCL communicator over the ranks of the initialised torch.distributed group:
+    rank 0 draws the id, the group broadcasts the 128 bytes (this is the only use of torch.distributed on the data path — the
+    per-step all-gather of the solid slices and the all-reduce of the force/torque sums then run inside libsdfibm_b200.so on the
+    context stream).  A C++/OpenFOAM host does the same with Pstream / MPI_Bcast."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    return world, rank
+
+
 def allreduce_force_torque(ft):
     """Sum the per-rank partial (F, T)[n_solids, 6] over all ranks, in place.  `ft` is a torch tensor on the
     rank's device (NCCL) or on the CPU (gloo)."""

@@ -1,6 +1,7 @@
 """The geometric claim behind `conn_proven` (csrc/sdfibm_cuda.cu, k_solid_prepare): on a complete lattice of identical boxes, a ball
-(disc) whose radius exceeds the cell diagonal by a factor 1 + 1e-5 and that lies r + one cell inside the mesh has a FACE-CONNECTED
-set of vertex-inside cells — so the reference's flood fill returns all of them and the connectivity certificate can be skipped.
+(disc) has a FACE-CONNECTED set of vertex-inside cells — so the reference's flood fill returns all of them and the connectivity
+certificate can be skipped.  First test: radii just above the cell diagonal, the ball r + one cell inside the mesh (round 1's
+narrower claim); second test: ANY radius (down to a fraction of a cell), balls clipped by the mesh, centres outside it.
 Checked against the oracle's real flood fill on anisotropic lattices (aspect 0.3 .. 2), radii from 1e-7 above the bound upwards,
 random and exactly vertex- / centre-aligned centres, 2-D and 3-D.  3 000 cases were run when this was written; 300 are kept."""
 import numpy as np
@@ -44,3 +45,35 @@ def test_ball_cell_sets_on_box_lattices_are_face_connected():
         if not np.array_equal(got, members):
             bad += 1
     assert bad == 0 and n_cases == 300 and tight > 100
+
+
+def test_any_ball_clipped_or_not_has_a_face_connected_cell_set():
+    """The general claim (k_solid_prepare's comment): walk every inside vertex towards the point of the mesh box nearest the centre."""
+    bad = n_cases = nonempty = outside = small = 0
+    for seed in range(400):
+        rng = np.random.RandomState(10_000 + seed)
+        two_d = bool(rng.randint(0, 2))
+        dx = np.array([1.0, float(rng.uniform(0.3, 2.0)), 1.0 if two_d else float(rng.uniform(0.3, 2.0))]) * float(rng.choice([0.1, 1.0, 0.37]))
+        nd = 2 if two_d else 3
+        diag = np.sqrt((dx[:nd] ** 2).sum())
+        r = diag * float(rng.choice([0.3, 0.6, 1.0, rng.uniform(0.2, 3.0)]))
+        n = tuple(int(rng.randint(3, 9)) for _ in range(nd)) + ((1,) if two_d else ())
+        x0 = (float(rng.choice([0.0, -3.0, 17.3])), 0.0, -0.5 * dx[2] if two_d else 0.0)
+        mesh = Mesh.hex_block(n, x0=x0, dx=tuple(dx))
+        lo, hi = mesh.bounds_min, mesh.bounds_max
+        pos = np.array([rng.uniform(lo[d] - 0.8 * r, hi[d] + 0.8 * r) if d < nd else 0.0 for d in range(3)])
+        if rng.rand() < 0.4:   # exact ties: centres on vertices / cell-centre planes
+            for d in range(nd):
+                if rng.rand() < 0.6:
+                    pos[d] = lo[d] + np.round((pos[d] - lo[d]) / (0.5 * dx[d])) * 0.5 * dx[d]
+        shapes = np.array([make_shape("Circle" if two_d else "Sphere", radius=r)])
+        S = make_solids(1); S[0]["pos"] = pos
+        inside, _ = eval_points(shapes, S[0], mesh.points)
+        members = np.nonzero(inside[mesh.cp.reshape(-1, 8)].any(axis=1))[0]
+        res = Oracle(mesh, two_d).interact(shapes, S, np.zeros((mesh.n_cells, 3)), 1.0, 1.0, faithful=True)
+        n_cases += 1
+        nonempty += len(members) > 0
+        small += r < diag
+        outside += bool(np.any(pos[:nd] < lo[:nd]) or np.any(pos[:nd] > hi[:nd]))
+        bad += not np.array_equal(np.sort(res["list_cells"]), members)
+    assert bad == 0 and n_cases == 400 and nonempty > 300 and outside > 150 and small > 150
