@@ -126,6 +126,14 @@ int sdfibm_free_pinned(void *p);
 /* max solids that may touch one mesh cell (default 3); call before sdfibm_set_mesh */
 int sdfibm_set_cell_slots(sdfibm_context *ctx, int slots);
 
+/* Meshes whose cells differ in vertex count (hanging-node refinement, hex / prism / polyhedron mixes): the reference's
+ * ALL_INSIDE test compares a cell's inside-vertex count with the vertex count of the cell that discovered it in the flood fill
+ * (src/cellenumerator.cpp:25), i.e. it depends on the fill's visiting order.  That order is not reproduced: sdfibm_set_mesh
+ * refuses such a mesh (SDFIBM_ERR_UNSUPPORTED) unless the caller accepts the order-free rule — ALL_INSIDE when all of the cell's
+ * OWN vertices are inside — here (or with SDFIBM_ALLOW_ORDER_FREE=1).  Member cells, fractions of cut cells and forces are
+ * unaffected; only the type (and hence alpha = 1 vs the computed fraction) of a few cells next to a cell of another kind is. */
+int sdfibm_allow_order_free(sdfibm_context *ctx, int on);
+
 /* ---- one-time uploads ------------------------------------------------------------- */
 /* replaces GeometricTools(mesh)/MeshInfo(mesh) binding (solidcloud.cpp:216, meshinfo.h:20-29) */
 int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *mesh, int two_d);
@@ -160,6 +168,25 @@ int sdfibm_interact_device_solids(sdfibm_context *ctx, const sdfibm_solid_t *d_s
 int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *U);
 int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids,
                                double *dU, const double *dCt);
+
+/* ---- the step either side of interact, on the device (src/main.cpp:70-77) ---------------
+ * With the flow fields resident in HBM (sdfibm_interact_device), the forcing is applied where it was computed:
+ *   U = U - Fs dt   (main.cpp:70)      T = (1 - As) T + Ts   (main.cpp:76)
+ * using As / Fs / Ts of the LAST interact on this context (their device arrays must still be alive).  Only cells that hold a
+ * candidate record are touched — everywhere else both updates are the identity bit for bit — so the pass moves 100-odd bytes
+ * per touched cell instead of 120 bytes per mesh cell.  Either pointer may be NULL.  Stream-ordered (no host synchronisation).
+ * Per step the host then sends the solid states (112 B each) and reads back force_torque (48 B per solid): the 1.2 GB of
+ * PCIe traffic of the host-buffer entry at C4 becomes 1.6 MB. */
+int sdfibm_apply_forcing_device(sdfibm_context *ctx, double *dU, double *dT, double dt);
+/* Copy `bytes` from a device array to host memory behind everything enqueued on the context stream, and wait for it (the one
+ * host synchronisation of a device-resident step: e.g. force_torque after sdfibm_interact_device + sdfibm_apply_forcing_device). */
+int sdfibm_download(sdfibm_context *ctx, void *host_dst, const void *device_src, size_t bytes);
+/* Compact records of the cells the last interact touched (a solid's bounding volume reached them; every other cell of the four
+ * fields is zero): cells[n] = cell labels, As[n], Fs[3n], Ts[n], Ct[n] (host arrays).  cells == NULL: only *n_touched is
+ * returned (size the arrays with it).  For a host that keeps its own copy of the fields and wants the D2H traffic of a step to
+ * scale with the solids, not with the mesh. */
+int sdfibm_touched_cells(sdfibm_context *ctx, int64_t capacity, int64_t *n_touched,
+                         int32_t *cells, double *As, double *Fs, double *Ts, double *Ct);
 
 /* ---- mean-field sampler: SolidCloud::calcMeanField (solidcloud.cpp:315-359) ------------
  * For every solid (placed with the SUBSTITUTE shape its record names) the volume-weighted mean of a cell field over

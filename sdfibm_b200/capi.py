@@ -69,6 +69,10 @@ SYMBOLS = {
     "sdfibm_fix_internal_device": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "sdfibm_mean_field": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
     "sdfibm_mean_field_sums": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
+    "sdfibm_allow_order_free": (C.c_int, [_VP, C.c_int]),
+    "sdfibm_apply_forcing_device": (C.c_int, [_VP, _VP, _VP, C.c_double]),
+    "sdfibm_download": (C.c_int, [_VP, _VP, _VP, C.c_size_t]),
+    "sdfibm_touched_cells": (C.c_int, [_VP, C.c_int64, c_int64_p, _VP, _VP, _VP, _VP, _VP]),
     "sdfibm_comm_unique_id": (C.c_int, [_VP]),
     "sdfibm_comm_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
     "sdfibm_comm_options": (C.c_int, [_VP, C.c_int, C.c_int]),

@@ -14,12 +14,14 @@ from . import capi
 
 
 class Context:
-    def __init__(self, device: int = 0, cell_slots: int | None = None):
+    def __init__(self, device: int = 0, cell_slots: int | None = None, allow_order_free: bool = False):
         self._lib = capi.load()
         self._h = C.c_void_p()
         capi.check(self._lib.sdfibm_create(int(device), C.byref(self._h)))
         if cell_slots is not None:
             capi.check(self._lib.sdfibm_set_cell_slots(self._h, int(cell_slots)))
+        if allow_order_free:   # meshes whose cells differ in vertex count: accept the order-free ALL_INSIDE rule
+            capi.check(self._lib.sdfibm_allow_order_free(self._h, 1))
         self.mesh = None
         self.n_cells = 0
         self.n_solids = 0
@@ -76,6 +78,26 @@ class Context:
                                                            capi.ptr(dU), float(dt), float(rhof), capi.ptr(dAs), capi.ptr(dFs),
                                                            capi.ptr(dTs), capi.ptr(dCt), capi.ptr(dFT)))
         self.n_solids = int(n_solids)
+
+    # ---- the step either side of interact, on the device (main.cpp:70-77) ----
+    def apply_forcing_device(self, dU: int | None, dT: int | None, dt: float):
+        """U -= Fs dt, T = (1 - As) T + Ts on the device arrays (pointers as ints; None skips one), from the last interact_device."""
+        capi.check(self._lib.sdfibm_apply_forcing_device(self._h, capi.ptr(dU) if dU else None, capi.ptr(dT) if dT else None, float(dt)))
+
+    def download(self, host: np.ndarray, device_ptr: int):
+        """Stream-ordered device -> host copy into `host` (ideally page-locked), then wait: the step's one synchronisation."""
+        capi.check(self._lib.sdfibm_download(self._h, capi.ptr(host), capi.ptr(device_ptr), host.nbytes))
+
+    def touched_cells(self):
+        """Compact host records of the cells the last interact touched: dict(cells, As, Fs, Ts, Ct)."""
+        n = C.c_int64()
+        capi.check(self._lib.sdfibm_touched_cells(self._h, 0, C.byref(n), None, None, None, None, None))
+        k = int(n.value)
+        out = dict(cells=np.empty(k, np.int32), As=np.empty(k), Fs=np.empty((k, 3)), Ts=np.empty(k), Ct=np.empty(k))
+        if k:
+            capi.check(self._lib.sdfibm_touched_cells(self._h, k, C.byref(n), capi.ptr(out["cells"]), capi.ptr(out["As"]), capi.ptr(out["Fs"]),
+                                                      capi.ptr(out["Ts"]), capi.ptr(out["Ct"])))
+        return out
 
     # ---- cross-rank exchange (NCCL inside the library) ----
     @staticmethod
@@ -173,12 +195,12 @@ class Context:
         return int(p.value or 0)
 
     # ---- collision step ----
-    def collide(self, solids: np.ndarray, delta: float, force_torque: np.ndarray | None = None):
+    def collide(self, solids: np.ndarray, delta: float, force_torque: np.ndarray | None = None, capacity: int = 1 << 16):
         solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
         n = len(solids)
         ft = np.zeros((n, 6)) if force_torque is None else np.array(force_torque, dtype=np.float64, order="C")
         npairs = C.c_int64(0)
-        cap = 1 << 16
+        cap = int(capacity)
         while True:
             pairs = np.empty((cap, 2), dtype=np.int32)
             ft_try = ft.copy()

@@ -251,13 +251,14 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
         const int be = __ldg(P.bin_off + t + 1);
         const float4 *E = reinterpret_cast<const float4 *>(P.bin_entries);
         // one pre-classified candidate -> slot record
+        int n_over = 0;
         auto emit = [&](int s, int qc) {
             if (qc == 0) return;
             if (n_item < P.K) {
                 P.slots[(long long)n_item * nC + c] = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
                 n_heavy += (qc == 2);
                 ++n_item;
-            } else P.status->slot_overflow = 1;
+            } else ++n_over;
         };
         // fp32 three-way test of a binned candidate (two 16-byte records) against the cell's vertex-cloud box: N2 bounds the
         // nearest vertex from below (for box cells it IS the nearest corner), F2 the farthest vertex from above; r_out / r_in
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
             }
         }
         P.n_item[c] = (unsigned char)n_item;
+        if (n_over) { P.status->slot_overflow = 1; atomicMax(&P.status->slot_need, n_item + n_over); }   // the host widens the records and runs again
     }
     // ---- block-aggregated append of the queued pairs to the global queue: ONE atomic on the queue counter per CTA
     //      (a per-warp atomic serialises ~3e5 same-address operations at C4 and bounds the whole kernel).  Mixed meshes keep two
@@ -1144,6 +1146,49 @@ __global__ void k_fix_internal(const double *cc, const sdfibm_solid_t *solids, i
             U[3 * (long long)c + 2] = u.z;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step either side of interact (src/main.cpp:70-77), on the device: U = U - Fs dt, T = (1 - As) T + Ts.  Only cells that hold a
+// slot record can have non-zero Fs / As / Ts; everywhere else both updates are the identity (U - 0 dt, 1 T + 0), bit for bit.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_apply_forcing(const unsigned char *__restrict__ n_item, const int *__restrict__ orig, int n_cells, const double *__restrict__ As,
+                                const double *__restrict__ Fs, const double *__restrict__ Ts, double dt, double *__restrict__ U, double *__restrict__ T) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells || n_item[c] == 0) return;
+    const long long oc = __ldg(orig + c);
+    // every load first (one memory latency, not one per component), then the stores
+    double u0 = 0, u1 = 0, u2 = 0, f0 = 0, f1 = 0, f2 = 0, t = 0, as = 0, ts = 0;
+    if (U) {
+        f0 = __ldg(Fs + 3 * oc); f1 = __ldg(Fs + 3 * oc + 1); f2 = __ldg(Fs + 3 * oc + 2);
+        u0 = U[3 * oc]; u1 = U[3 * oc + 1]; u2 = U[3 * oc + 2];
+    }
+    if (T) { as = __ldg(As + oc); ts = __ldg(Ts + oc); t = T[oc]; }
+    if (U) {
+        U[3 * oc] = u0 - f0 * dt;
+        U[3 * oc + 1] = u1 - f1 * dt;
+        U[3 * oc + 2] = u2 - f2 * dt;
+    }
+    if (T) T[oc] = (1.0 - as) * t + ts;
+}
+
+// compact records of the touched cells (cells that hold a slot record): flags -> exclusive scan -> gather
+__global__ void k_touched_flags(const unsigned char *n_item, int n_cells, int *flag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= n_cells) flag[c] = (c < n_cells && n_item[c] != 0) ? 1 : 0;
+}
+__global__ void k_touched_gather(const unsigned char *n_item, const int *orig, const int *off, int n_cells, long long cap, const double *As,
+                                 const double *Fs, const double *Ts, const double *Ct, int *cells, double *oAs, double *oFs, double *oTs, double *oCt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells || n_item[c] == 0) return;
+    const long long o = off[c];
+    if (o >= cap) return;
+    const long long oc = __ldg(orig + c);
+    cells[o] = (int)oc;
+    oAs[o] = As[oc];
+    oFs[3 * o] = Fs[3 * oc]; oFs[3 * o + 1] = Fs[3 * oc + 1]; oFs[3 * o + 2] = Fs[3 * oc + 2];
+    oTs[o] = Ts[oc];
+    oCt[o] = Ct[oc];
 }
 
 // ------------------------------------------------------------------------------------------------

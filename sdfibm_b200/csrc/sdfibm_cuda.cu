@@ -150,7 +150,7 @@ struct StepStatus {
     unsigned long long heavy_total; // (cell, solid) items that needed exact evaluation (mixed meshes: those of hexahedral cells)
     unsigned long long heavy_gen;   // mixed meshes: items of non-hexahedral cells, queued from the back of the same buffer
     int need_cert;                  // some binned solid's cell set is not connected by construction: the certificate pass has work
-    int pad_;
+    int slot_need;                  // slot_overflow: the largest number of solids that touch one cell
 };
 
 __device__ __forceinline__ D3 ld3(const double *__restrict__ p, long long i) {
@@ -775,6 +775,7 @@ struct sdfibm_context {
     DevBuf<unsigned> hex_topo, tile_key, btopo;
     DevBuf<double> box6, cfa6;
     bool allow_box = true;      // SDFIBM_BOX=0: keep exact-box meshes on the general hexahedron kernel
+    bool allow_order_free = false;   // meshes whose cells differ in vertex count: accept the order-free ALL_INSIDE rule (sdfibm_allow_order_free)
     DevBuf<int> nb6;
     DevBuf<int> orig, inv;      // tile-order renumbering: position -> caller's label and back
     DevBuf<double> cc_orig;     // cell centres in the caller's order (fixInternal)
@@ -815,6 +816,9 @@ struct sdfibm_context {
     DevBuf<double> dU, dAs, dFs, dTs, dCt, dFT;
     DevBuf<double> sU, sOut, sFT; // mean-field sampler scratch
     const double *last_Ct = nullptr;
+    const double *last_As = nullptr, *last_Fs = nullptr, *last_Ts = nullptr;   // device outputs of the last interact (apply_forcing / touched download)
+    DevBuf<int> t_flag, t_off, t_cells;      // touched-cell compaction
+    DevBuf<double> t_vals;
     // replay
     DevBuf<int> labels, seed_cell, min_label, chosen, changed;
     DevBuf<unsigned long long> seed_key;
@@ -940,7 +944,7 @@ static NcclApi *nccl_api() {
 // this rank has to run the step again (a capacity grew, or a solid needs the flood-fill replay): the other ranks must learn it,
 // because the all-reduce that follows is collective
 __global__ void k_retry_flag(const StepStatus *st, long long heavy_cap, double *flag) {
-    const bool again = st->bin_overflow || st->heavy_total + st->heavy_gen > (unsigned long long)heavy_cap || st->n_flagged > 0;
+    const bool again = st->bin_overflow || st->slot_overflow || st->heavy_total + st->heavy_gen > (unsigned long long)heavy_cap || st->n_flagged > 0;
     flag[0] = again ? 1.0 : 0.0;
 }
 
@@ -994,6 +998,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_BOX")) ctx->allow_box = atoi(e) != 0;
+    if (const char *e = getenv("SDFIBM_ALLOW_ORDER_FREE")) ctx->allow_order_free = atoi(e) != 0;
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -1025,7 +1030,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release(); ctx->slab_start.release();
     ctx->global_list.release(); ctx->slots.release();
     ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
-    ctx->ft_internal.release(); ctx->scan_tmp.release();
+    ctx->ft_internal.release(); ctx->scan_tmp.release(); ctx->t_flag.release(); ctx->t_off.release(); ctx->t_cells.release(); ctx->t_vals.release();
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release(); ctx->sU.release(); ctx->sOut.release(); ctx->sFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
@@ -1060,6 +1065,12 @@ int sdfibm_set_cell_slots(sdfibm_context *ctx, int slots) {
     return SDFIBM_OK;
 }
 
+int sdfibm_allow_order_free(sdfibm_context *ctx, int on) {
+    if (!ctx) return fail(SDFIBM_ERR_ARG, "sdfibm_allow_order_free: null context");
+    ctx->allow_order_free = on != 0;
+    return SDFIBM_OK;
+}
+
 int sdfibm_stream(sdfibm_context *ctx, void **s) {
     if (!ctx || !s) return fail(SDFIBM_ERR_ARG, "sdfibm_stream: null argument");
     *s = (void *)ctx->stream;
@@ -1078,6 +1089,21 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
         !m->cell_points_off || !m->cell_points || !m->cell_faces_off || !m->cell_faces || !m->face_points_off ||
         !m->face_points || !m->cell_cells_off || !m->cell_cells)
         return fail(SDFIBM_ERR_ARG, "sdfibm_set_mesh: missing mesh array");
+    {
+        // the reference calls a cell ALL_INSIDE when its inside-vertex count equals the vertex count of the cell that
+        // DISCOVERED it in the flood fill (src/cellenumerator.cpp:25 compares with m_c2p[icur], the current cell) — on a mesh whose
+        // cells differ in vertex count (hanging-node refinement, hex / prism / polyhedron mixes) the outcome depends on the
+        // fill's visiting order.  This library uses the cell's own vertex count: the same thing when all cells have equally
+        // many vertices, an order-free rule otherwise — which the caller has to accept explicitly.
+        const int nv0 = m->cell_points_off[1] - m->cell_points_off[0];
+        bool same = true;
+        for (int c = 1; c < m->n_cells && same; ++c) same = (m->cell_points_off[c + 1] - m->cell_points_off[c]) == nv0;
+        if (!same && !ctx->allow_order_free)
+            return fail(SDFIBM_ERR_UNSUPPORTED,
+                        "sdfibm_set_mesh: the cells differ in vertex count: the reference's ALL_INSIDE test then depends on its flood fill's "
+                        "visiting order (cellenumerator.cpp:25), which is not reproduced; call sdfibm_allow_order_free(ctx, 1) "
+                        "(or set SDFIBM_ALLOW_ORDER_FREE=1) to accept the order-free rule (a cell is ALL_INSIDE when all of ITS vertices are inside)");
+    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     drop_graph(ctx);   // a captured step holds the old mesh's pointers and constants by value
@@ -1197,6 +1223,7 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     CUDA_TRY(ctx->n_item.ensure(nC));
     {
         size_t cap = std::max<size_t>(1 << 20, nC / 2);
+        cap = std::min<size_t>(cap, (1u << 28) - 1);   // a slot record holds the queue index in 28 bits
         if (const char *e = getenv("SDFIBM_HEAVY_CAP0")) cap = std::max<size_t>(16, (size_t)atoll(e));   // tests: force the growth path
         CUDA_TRY(ctx->heavy.ensure(cap));
         CUDA_TRY(ctx->heavy_res.ensure(cap));
@@ -1432,7 +1459,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         CUDA_TRY(cudaMemsetAsync(ctx->n_item.p, 0, nC0, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->last = StepStatus{};
-        ctx->last_Ct = dCt;
+        ctx->last_Ct = dCt; ctx->last_As = dAs; ctx->last_Fs = dFs; ctx->last_Ts = dTs;
         ctx->n_solids_last = 0;
         return SDFIBM_OK;
     }
@@ -1514,7 +1541,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(st));
     }
-    ctx->last_Ct = dCt;
+    ctx->last_Ct = dCt; ctx->last_As = dAs; ctx->last_Fs = dFs; ctx->last_Ts = dTs;
     ctx->n_solids_last = n_solids;
     return SDFIBM_OK;
 }
@@ -1708,7 +1735,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
     }
     ctx->h_scal[0] = 1.0 / dt;
     ctx->h_scal[1] = rhof;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {   // a pass that finds a capacity too small grows it and runs again
         if (!replay) CUDA_TRY(ctx->bin_entries.ensure(ctx->bin_list.n));
         const bool chunked = ctx->pipe.active && !replay && attempt == 0;
         if (ctx->pipe.active && !chunked) {   // a retry / replay pass rewrites the fields: copy them out again at the end
@@ -1771,24 +1798,34 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             ctx->last = *ctx->h_status;
             if (replay) ctx->last.n_flagged = (int)ctx->flagged_last;
         }
-        if (ctx->last.heavy_total + ctx->last.heavy_gen > (unsigned long long)ctx->heavy.n && attempt == 0) {
+        bool again = false;
+        if (ctx->last.slot_overflow && !replay && ctx->K < 64) {
+            // more solids touch one cell than there are slot records (dense packs against a wall plane): widen and run again
+            const int K = std::min(64, std::max(ctx->last.slot_need, ctx->K + 1));
+            drop_graph(ctx);
+            CUDA_TRY(ctx->slots.ensure((size_t)ctx->dm.n_cells * K));
+            ctx->K = K;
+            again = true;
+        }
+        if (ctx->last.heavy_total + ctx->last.heavy_gen > (unsigned long long)ctx->heavy.n) {
             const unsigned long long need = ctx->last.heavy_total + ctx->last.heavy_gen;
+            if (need + need / 4 + 1024 >= (1ull << 28)) return fail(SDFIBM_ERR_CAPACITY, "exact-evaluation queue would exceed 2^28 items (slot records hold the queue index in 28 bits): split the mesh");
             const size_t cap = (size_t)(need + need / 4 + 1024);
             CUDA_TRY(ctx->heavy.ensure(cap));
             CUDA_TRY(ctx->heavy_res.ensure(cap));
-            continue;
+            again = true;
         }
-        if (ctx->last.bin_overflow && !replay && attempt == 0) {
+        if (ctx->last.bin_overflow && !replay) {
             CUDA_TRY(ctx->bin_list.ensure((size_t)ctx->last.bin_total + (size_t)ctx->last.bin_total / 4 + 1024));
-            continue;
+            again = true;
         }
-        break;
+        if (!again || attempt == 3) break;
     }
     if (ctx->last.bin_overflow) return fail(SDFIBM_ERR_CAPACITY, "solid bin list overflow");
     if (ctx->last.bad_cell) return fail(SDFIBM_ERR_UNSUPPORTED, "cell with more than 32 vertices");
     if (ctx->last.bad_shape) return fail(SDFIBM_ERR_ARG, "solid refers to an unknown shape index");
     if (ctx->last.slot_overflow)
-        return fail(SDFIBM_ERR_CAPACITY, "more solids touch one cell than the slot count; raise it with sdfibm_set_cell_slots");
+        return fail(SDFIBM_ERR_CAPACITY, "more than 64 solids touch one cell (slot records)");
     if (ctx->last.heavy_total + ctx->last.heavy_gen > (unsigned long long)ctx->heavy.n) return fail(SDFIBM_ERR_CAPACITY, "exact-evaluation queue overflow");
     return SDFIBM_OK;
 }
@@ -1851,6 +1888,62 @@ int sdfibm_interact_device_solids(sdfibm_context *ctx, const sdfibm_solid_t *d_s
     const int rc = sdfibm_interact_device(ctx, nullptr, n_solids, dU, dt, rhof, dAs, dFs, dTs, dCt, dFT);
     ctx->ext_solids = nullptr;
     return rc;
+}
+
+// ---- the step either side of interact, on the device (src/main.cpp:70-77) ----
+int sdfibm_apply_forcing_device(sdfibm_context *ctx, double *dU, double *dT, double dt) {
+    if (!ctx || (!dU && !dT)) return fail(SDFIBM_ERR_ARG, "sdfibm_apply_forcing_device: null argument");
+    if (!ctx->has_mesh || !ctx->last_Fs) return fail(SDFIBM_ERR_STATE, "sdfibm_apply_forcing_device: no interact has run on this context");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int nC = ctx->dm.n_cells;
+    k_apply_forcing<<<grid_for(nC, 256), 256, 0, ctx->stream>>>(ctx->n_item.p, ctx->orig.p, nC, ctx->last_As, ctx->last_Fs, ctx->last_Ts, dt, dU, dT);
+    CUDA_TRY(cudaGetLastError());
+    return SDFIBM_OK;   // stream-ordered: the next call on this context (or sdfibm_synchronize) sees the result
+}
+
+int sdfibm_download(sdfibm_context *ctx, void *host_dst, const void *device_src, size_t bytes) {
+    if (!ctx || (bytes && (!host_dst || !device_src))) return fail(SDFIBM_ERR_ARG, "sdfibm_download: null argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SDFIBM_OK;
+}
+
+int sdfibm_touched_cells(sdfibm_context *ctx, int64_t capacity, int64_t *n_touched, int32_t *cells, double *As, double *Fs, double *Ts, double *Ct) {
+    if (!ctx || !n_touched) return fail(SDFIBM_ERR_ARG, "sdfibm_touched_cells: null argument");
+    if (!ctx->has_mesh || !ctx->last_Fs) return fail(SDFIBM_ERR_STATE, "sdfibm_touched_cells: no interact has run on this context");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int nC = ctx->dm.n_cells;
+    CUDA_TRY(ctx->t_flag.ensure((size_t)nC + 1));
+    CUDA_TRY(ctx->t_off.ensure((size_t)nC + 1));
+    k_touched_flags<<<grid_for((long long)nC + 1, 256), 256, 0, st>>>(ctx->n_item.p, nC, ctx->t_flag.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->t_flag.p, ctx->t_off.p, nC + 1, st);
+    CUDA_TRY(ctx->scan_tmp.ensure(tb));
+    cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tb, ctx->t_flag.p, ctx->t_off.p, nC + 1, st);
+    int total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, ctx->t_off.p + nC, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *n_touched = total;
+    if (!cells) return SDFIBM_OK;   // count only
+    if (!As || !Fs || !Ts || !Ct) return fail(SDFIBM_ERR_ARG, "sdfibm_touched_cells: null output array");
+    if (total > capacity) return fail(SDFIBM_ERR_CAPACITY, "sdfibm_touched_cells: capacity too small");
+    if (total == 0) return SDFIBM_OK;
+    const size_t n = (size_t)total;
+    CUDA_TRY(ctx->t_cells.ensure(n));
+    CUDA_TRY(ctx->t_vals.ensure(6 * n));
+    double *oAs = ctx->t_vals.p, *oFs = oAs + n, *oTs = oFs + 3 * n, *oCt = oTs + n;
+    k_touched_gather<<<grid_for(nC, 256), 256, 0, st>>>(ctx->n_item.p, ctx->orig.p, ctx->t_off.p, nC, (long long)n, ctx->last_As, ctx->last_Fs,
+                                                       ctx->last_Ts, ctx->last_Ct, ctx->t_cells.p, oAs, oFs, oTs, oCt);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(cells, ctx->t_cells.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(As, oAs, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(Fs, oFs, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(Ts, oTs, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(Ct, oCt, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SDFIBM_OK;
 }
 
 // ---- cross-rank exchange (NCCL over NVLink) ----

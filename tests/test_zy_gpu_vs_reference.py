@@ -6,6 +6,7 @@ flood fill's visiting order, which test_oracle_vs_reference.py cover
 
 Bars as in test_gpu_parity.py: lists and Ct exact, As / Ts / Fs 1e-12 relative, force / torque 1e-10 relative to sum |terms|."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -39,11 +40,9 @@ def _reference(case):
 def _check(case, got, off, cells, ref, rel_field, rel_force):
     assert np.array_equal(off, ref["list_off"]) and np.array_equal(cells, ref["list_cells"])
     assert np.array_equal(got["Ct"], ref["Ct"])
-    for k in ("As", "Ts", "Fs"):
-        a, b = got[k], ref[k]
-        tol = rel_field * np.maximum(np.abs(b), np.abs(b).max() * 1e-3 + 1e-300)
-        assert (np.abs(a - b) <= tol).all(), (k, np.abs(a - b).max())
-    from test_gpu_parity import _term_scale
+    from test_gpu_parity import _term_scale, assert_fields_close
+
+    assert_fields_close(got, ref, rel_field)
 
     scale = _term_scale(case, ref["list_off"], ref["list_cells"])
     err = np.abs(got["FT"] - ref["FT"])
@@ -101,3 +100,57 @@ def test_gpu_against_compiled_reference(name):
     _check(case, got, off, cells, ref, 1e-12, 1e-10)
     S2, U2 = _moved(case)
     assert np.array_equal(ctx.fix_internal(S2, U2), ref_py.ref_fix_internal(case["mesh"], S2, ref["Ct"], U2))
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_gpu_against_compiled_reference_on_a_mesh_of_mixed_cell_types():
+    """SURVEY Q3, against the reference's own compiled CellEnumerator (no oracle variant in between): on a mesh of hexahedra, prisms
+    and 7-faced polyhedra the library is refused by default; with the order-free rule accepted it returns the SAME member cells
+    as the reference for every solid, and the two differ only where the quirk bites — cells whose type the reference takes from
+    the vertex count of the neighbour that discovered them."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from mixed_mesh import mixed_hex_prism_mesh
+    from sdfibm_b200.capi import SdfibmError
+    from sdfibm_b200.context import Context
+    from sdfibm_b200.shapes import make_shape, make_solids, quat_from_euler_xyz_deg
+
+    mesh = mixed_hex_prism_mesh(14)
+    rng = np.random.RandomState(3)
+    shapes = np.array([make_shape("Sphere", radius=3.2), make_shape("Ellipsoid", radiusa=3.5, radiusb=2.5, radiusc=2.0),
+                       make_shape("Box", radiusa=2.2, radiusb=1.6, radiusc=2.7)])
+    S = make_solids(6)
+    S["pos"] = [(5.3, 6.1, 5.7), (9.9, 4.2, 8.7), (4.1, 10.2, 9.6), (10.4, 10.1, 4.3), (7.0, 7.0, 7.0), (12.5, 2.0, 12.0)]
+    S["shape"] = [0, 1, 2, 0, 1, 2]
+    for i, e in enumerate([(0, 0, 0), (20, 40, -15), (35, -10, 60), (0, 0, 0), (-70, 15, 5), (10, 20, 30)]):
+        S[i]["quat"] = quat_from_euler_xyz_deg(e)
+    S["vel"] = 0.1 * rng.standard_normal((6, 3))
+    U = rng.standard_normal((mesh.n_cells, 3))
+    case = dict(name="mixed_cells", mesh=mesh, two_d=False, shapes=shapes, solids=S, U=U, dt=1e-3, rhof=1.3)
+    ref = _reference(case)
+    with pytest.raises(SdfibmError, match="visiting order"):
+        Context(0, cell_slots=8).set_mesh(mesh, False)
+    ctx = Context(0, cell_slots=8, allow_order_free=True)
+    ctx.set_mesh(mesh, False)
+    ctx.set_shapes(shapes)
+    got = ctx.interact(S, U, 1e-3, 1.3)
+    off, cells = ctx.candidate_lists()
+    nv = np.diff(mesh.cp_off)
+    n_diff = 0
+    for s in range(len(S)):
+        mine = {t: cells[off[3 * s + t]: off[3 * s + t + 1]] for t in range(3)}
+        theirs = {t: ref["list_cells"][ref["list_off"][3 * s + t]: ref["list_off"][3 * s + t + 1]] for t in range(3)}
+        assert np.array_equal(np.sort(np.concatenate(list(mine.values()))), np.sort(np.concatenate(list(theirs.values()))))   # same member cells
+        # typed differently only in the ALL_INSIDE decision, and only next to a cell with another vertex count
+        moved = np.setxor1d(mine[0], theirs[0])
+        n_diff += len(moved)
+        for c in moved:
+            nb = mesh.nb[mesh.nb_off[c]: mesh.nb_off[c + 1]]
+            assert (nv[nb] != nv[c]).any(), c
+        assert np.array_equal(np.setdiff1d(mine[1], moved), np.setdiff1d(theirs[1], moved))
+        assert np.array_equal(np.setdiff1d(mine[2], moved), np.setdiff1d(theirs[2], moved))
+    assert 0 < n_diff < 0.05 * ref["list_off"][-1]
+    same = np.ones(mesh.n_cells, bool)
+    same[np.nonzero(got["Ct"] != ref["Ct"])[0]] = False
+    from test_gpu_parity import assert_fields_close
+    assert_fields_close({k: got[k][same] for k in ("As", "Ts", "Fs")}, {k: ref[k][same] for k in ("As", "Ts", "Fs")})
