@@ -46,8 +46,40 @@ enum sdfibm_shape_tag {
     SDFIBM_SHAPE_BOX = 6,            /* src/libshape/box.h:14-57 */
     SDFIBM_SHAPE_CIRCLE_TAIL = 7,    /* src/libshape/circle_tail.h:18-61 */
     SDFIBM_SHAPE_CIRCLE_TWOTAIL = 8, /* src/libshape/circle_twotail.h:18-66 */
-    SDFIBM_SHAPE_NTAGS = 9
+    SDFIBM_SHAPE_PROGRAM = 9,        /* a composed shape: a post-fix program over src/libshape/sdf/sdf.h (see sdfibm_sdf_op_t) */
+    SDFIBM_SHAPE_NTAGS = 10
 };
+
+/* Composable signed-distance programs: the primitives, point transformations and Boolean operations of the reference's
+ * sdf:: namespace (src/libshape/sdf/sdf.h:13-155) — what a plugin written from src/libshape/template.h combines in its
+ * isInside / signedDistance pair — as a post-fix program the device evaluates, so a NEW composed shape needs no change to the
+ * CUDA switch.  Two stacks: points and values (a value = the bool of isInside and the scalar of signedDistance, computed
+ * side by side with the reference's own expressions: `<` predicates un-contracted).
+ *   POINT / POINT_2D          push  com + p   (POINT_2D: z = 0, the 2-D shapes' p2d)
+ *   OFFSET a0 a1 a2           top point -= (a0, a1, a2)                                      sdf::offset      :123-126
+ *   ROT30/45/60/90, ROTTH a0  rotate the top point (the literals of sdf.h, not exact cosines)  sdf::rot*       :91-113
+ *   FLIPX / FLIPY             mirror the top point                                           sdf::flipx/y     :115-122
+ *   CIRCLE a0=r a1=r^2        pop point, push (|P|^2 < a1, |P| - a0)   (a sphere when the point is 3-D)       :15-26
+ *   RECTANGLE a0=ra a1=rb     sdf::rectangle_bool / rectangle                                                :29-40
+ *   BOX a0 a1 a2              sdf::box_bool / box                                                            :43-56
+ *   ELLIPSE a0=1/a^2 a1=1/b^2, ELLIPSOID a0 a1 a2 = 1/a^2 1/b^2 1/c^2                                         :59-83
+ *   HALFSPACE                 (P.y < 0, P.y)                                                 plane.h:21-28
+ *   UNION / INTERSECT / DIFF  pop two values, push sdf::U / I / D of them (n-ary U({..}) = repeated UNION)   :131-142
+ * The program must leave exactly one value; the shape's signedDistance is sdf::filter of it (:147-150). */
+enum sdfibm_sdf_opcode {
+    SDFIBM_OP_POINT = 0, SDFIBM_OP_POINT_2D = 1, SDFIBM_OP_OFFSET = 2,
+    SDFIBM_OP_ROT30 = 3, SDFIBM_OP_ROT45 = 4, SDFIBM_OP_ROT60 = 5, SDFIBM_OP_ROT90 = 6, SDFIBM_OP_ROTTH = 7,
+    SDFIBM_OP_FLIPX = 8, SDFIBM_OP_FLIPY = 9,
+    SDFIBM_OP_CIRCLE = 16, SDFIBM_OP_RECTANGLE = 17, SDFIBM_OP_BOX = 18, SDFIBM_OP_ELLIPSE = 19, SDFIBM_OP_ELLIPSOID = 20,
+    SDFIBM_OP_HALFSPACE = 21,
+    SDFIBM_OP_UNION = 32, SDFIBM_OP_INTERSECT = 33, SDFIBM_OP_DIFF = 34
+};
+#define SDFIBM_SDF_STACK 6   /* depth of either stack */
+typedef struct sdfibm_sdf_op {
+    int32_t op;
+    int32_t pad_;
+    double a[4];
+} sdfibm_sdf_op_t;
 
 /* Cell classification, same numbering as CellEnumerator::CELL_TYPE (src/cellenumerator.h:23). */
 enum sdfibm_cell_type {
@@ -139,6 +171,11 @@ int sdfibm_allow_order_free(sdfibm_context *ctx, int on);
 int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *mesh, int two_d);
 /* replaces EntityLibrary<IShape> lookup by pointer (solidcloud.cpp:59, solid.h:47-50) */
 int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n_shapes);
+/* The op table the SDFIBM_SHAPE_PROGRAM records of the shape table point into; call BEFORE sdfibm_set_shapes.  A PROGRAM record:
+ * p[0] = index of its first op, p[1] = number of ops, p[2] = certified outer radius about the body origin (no point farther is
+ * inside; in-plane for 2-D), p[3] = certified inner radius (every point closer is inside; 0 if unknown), p[4] = 1 for a 2-D shape
+ * (unbounded along the body z axis), else 0.  Programs are checked (stack discipline, opcodes) when the shapes are set. */
+int sdfibm_set_shape_programs(sdfibm_context *ctx, const sdfibm_sdf_op_t *ops, int n_ops);
 
 /* ---- SolidCloud::interact (solidcloud.cpp:435-464), host buffers --------------------
  * U[3*n_cells] in;  As[n_cells], Fs[3*n_cells], Ts[n_cells], Ct[n_cells] out (cell values of
@@ -201,6 +238,13 @@ int sdfibm_mean_field(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_s
  * block does not touch the solid contributes zeros, not 0/0. */
 int sdfibm_mean_field_sums(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, const double *field,
                            double *sum_alpha_v_field, double *sum_alpha_v);
+
+/* ---- tool_vof: SolidCloud::writeVOF (tool_vof/solidcloud.cpp:116-173) ----------------------------------------
+ * alpha[n_cells] (host) = the volume fraction every cell has inside the union of the solids: the per-solid fractions added
+ * in solid order and clamped at 1 (:131-133) — interact's As, computed by the same kernels on scratch outputs (the coupling
+ * state of the last interact on this context stays valid).  The reference lists its `planes{}` block after `solids{}`; pass
+ * them in that order.  total_volume (may be NULL) = sum(alpha V) (:169). */
+int sdfibm_volume_fraction(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *alpha, double *total_volume);
 
 /* ---- candidate lists of the last interact (CellEnumerator::intersect result) --------
  * counts[3] = total ALL_INSIDE, CENTER_INSIDE, CENTER_OUTSIDE pairs. */

@@ -38,6 +38,12 @@ int sdfibm_host_save_state(sdfibm_host_cloud *h);                            /* 
 int sdfibm_host_fix_internal(sdfibm_host_cloud *h, double dt);               /* src/main.cpp:87  */
 int sdfibm_host_save_restart(sdfibm_host_cloud *h, const char *filename);    /* src/main.cpp:101 */
 
+/* tool_vof (tool_vof/main.cpp, tool_vof/solidcloud.cpp:141-173): VofCloud(dictfile, mesh).writeVOF(field_name) — the volume
+ * fraction of the union of the `solids{}` then `planes{}` bodies of a tool_vof-flavoured solidDict; writes
+ * <case_dir>/0_<field_name>; alpha[n_cells], total_volume, n_solids, n_planes may be NULL. */
+int sdfibm_host_write_vof(const char *dictfile, const char *case_dir, const sdfibm_mesh_t *mesh, const char *field_name,
+                          double *alpha, double *total_volume, int *n_solids, int *n_planes);
+
 /* solid states: rigid-body records, total (force, torque) of the last evolve sub-iteration [6N], and the fluid
  * (force, torque) of the last interact [6N] */
 int sdfibm_host_n_solids(sdfibm_host_cloud *h, int *n);

@@ -121,10 +121,60 @@ inline V3 rot30(V3 p) {                                                         
 inline V3 flipy(V3 p) { return {p.x, -p.y, p.z}; }                                             // sdf.h:115-118
 inline V3 offset(V3 p, V3 o) { return p - o; }                                                 // sdf.h:123-126
 
+inline V3 rot45(V3 p) { return 0.707106781 * V3{p.x + p.y, -p.x + p.y, 0.0}; }                 // sdf.h:95-98
+inline V3 rot60(V3 p) { return {0.866025404 * p.y + 0.5 * p.x, -0.866025404 * p.x + 0.5 * p.y, 0.0}; }   // sdf.h:99-102
+inline V3 rot90(V3 p) { return {p.y, -p.x, 0.0}; }                                              // sdf.h:103-106
+inline V3 rotth(V3 p, double th) {                                                              // sdf.h:107-112
+    double s = std::sin(th);
+    double c = std::cos(th);
+    return {p.x * c + p.y * s, -p.x * s + p.y * c, 0.0};
+}
+inline V3 flipx(V3 p) { return {-p.x, p.y, p.z}; }                                             // sdf.h:119-122
+
+// Composed shapes (SDFIBM_SHAPE_PROGRAM): what a plugin written from src/libshape/template.h does in its isInside /
+// signedDistance pair — sdf.h's primitives on transformed points combined by sdf::U / I / D (:131-142) — restated as an
+// evaluation of the same post-fix op list the product takes (include/sdfibm_b200.h, sdfibm_sdf_op_t), with the functions above.
+static const sdfibm_sdf_op_t *g_ops = nullptr;   // set by oracle_set_programs (test infrastructure: one table per process)
+
+struct SdfValue { bool b; double d; };
+static SdfValue program_value(const sdfibm_shape_t &s, V3 p) {
+    const V3 com = {s.com[0], s.com[1], s.com[2]};
+    std::vector<V3> pts;
+    std::vector<SdfValue> vals;
+    const sdfibm_sdf_op_t *ops = g_ops + (int)s.p[0];
+    for (int i = 0; i < (int)s.p[1]; ++i) {
+        const sdfibm_sdf_op_t &o = ops[i];
+        auto pop = [&]() { V3 q = pts.back(); pts.pop_back(); return q; };
+        switch (o.op) {
+        case SDFIBM_OP_POINT: pts.push_back(com + p); break;
+        case SDFIBM_OP_POINT_2D: { V3 q = com + p; q.z = 0.0; pts.push_back(q); break; }
+        case SDFIBM_OP_OFFSET: pts.back() = offset(pts.back(), V3{o.a[0], o.a[1], o.a[2]}); break;
+        case SDFIBM_OP_ROT30: pts.back() = rot30(pts.back()); break;
+        case SDFIBM_OP_ROT45: pts.back() = rot45(pts.back()); break;
+        case SDFIBM_OP_ROT60: pts.back() = rot60(pts.back()); break;
+        case SDFIBM_OP_ROT90: pts.back() = rot90(pts.back()); break;
+        case SDFIBM_OP_ROTTH: pts.back() = rotth(pts.back(), o.a[0]); break;
+        case SDFIBM_OP_FLIPX: pts.back() = flipx(pts.back()); break;
+        case SDFIBM_OP_FLIPY: pts.back() = flipy(pts.back()); break;
+        case SDFIBM_OP_CIRCLE: { V3 q = pop(); vals.push_back({circle_bool_fast(q, o.a[1]), circle_sd(q, o.a[0])}); break; }
+        case SDFIBM_OP_RECTANGLE: { V3 q = pop(); vals.push_back({rectangle_bool(q, o.a[0], o.a[1]), rectangle_sd(q, o.a[0], o.a[1])}); break; }
+        case SDFIBM_OP_BOX: { V3 q = pop(); vals.push_back({box_bool(q, o.a[0], o.a[1], o.a[2]), box_sd(q, o.a[0], o.a[1], o.a[2])}); break; }
+        case SDFIBM_OP_ELLIPSE: { V3 q = pop(); vals.push_back({ellipse_bool_fast(q, o.a[0], o.a[1]), ellipse_sd(q, o.a[0], o.a[1])}); break; }
+        case SDFIBM_OP_ELLIPSOID: { V3 q = pop(); vals.push_back({ellipsoid_bool_fast(q, o.a[0], o.a[1], o.a[2]), ellipsoid_sd(q, o.a[0], o.a[1], o.a[2])}); break; }
+        case SDFIBM_OP_HALFSPACE: { V3 q = pop(); vals.push_back({q.y < 0, q.y}); break; }
+        case SDFIBM_OP_UNION: { SdfValue b = vals.back(); vals.pop_back(); SdfValue &a = vals.back(); a = {std::max(a.b, b.b), std::min(a.d, b.d)}; break; }        // sdf::U
+        case SDFIBM_OP_INTERSECT: { SdfValue b = vals.back(); vals.pop_back(); SdfValue &a = vals.back(); a = {std::min(a.b, b.b), std::max(a.d, b.d)}; break; }    // sdf::I
+        case SDFIBM_OP_DIFF: { SdfValue b = vals.back(); vals.pop_back(); SdfValue &a = vals.back(); a = {a.b && (!b.b), std::max(a.d, -b.d)}; break; }             // sdf::D
+        }
+    }
+    return vals.empty() ? SdfValue{false, 0.0} : vals[0];
+}
+
 // isInside in the body frame (private virtual of each IShape subclass)
 bool shape_is_inside(const sdfibm_shape_t &s, V3 p) {
     const V3 com = {s.com[0], s.com[1], s.com[2]};
     switch (s.tag) {
+    case SDFIBM_SHAPE_PROGRAM: return program_value(s, p).b;
     case SDFIBM_SHAPE_PLANE: return p.y < 0;                                                   // plane.h:21-24
     case SDFIBM_SHAPE_CIRCLE: return circle_bool_fast(com + V3{p.x, p.y, 0.0}, s.p[1]);        // circle.h:38-41
     case SDFIBM_SHAPE_SPHERE: return circle_bool_fast(com + p, s.p[1]);                        // sphere.h:37-40
@@ -159,6 +209,7 @@ bool shape_is_inside(const sdfibm_shape_t &s, V3 p) {
 double shape_signed_distance(const sdfibm_shape_t &s, V3 p) {
     const V3 com = {s.com[0], s.com[1], s.com[2]};
     switch (s.tag) {
+    case SDFIBM_SHAPE_PROGRAM: return sdf_filter(program_value(s, p).d);                       // sdf::filter, sdf.h:147-150
     case SDFIBM_SHAPE_PLANE: return p.y;                                                       // plane.h:25-28 (unfiltered)
     case SDFIBM_SHAPE_CIRCLE: return sdf_filter(circle_sd(com + V3{p.x, p.y, 0.0}, s.p[0]));   // circle.h:42-45
     case SDFIBM_SHAPE_SPHERE: return sdf_filter(circle_sd(com + p, s.p[0]));                   // sphere.h:41-44
@@ -481,6 +532,8 @@ void *oracle_create(const sdfibm_mesh_t *mesh, int twoD) {
     return o;
 }
 void oracle_destroy(void *h) { delete (Oracle *)h; }
+// the op table of the composed shapes (kept by the caller)
+void oracle_set_programs(const sdfibm_sdf_op_t *ops) { g_ops = ops; }
 
 int oracle_nearest_cell(void *h, const double p[3]) { return ((Oracle *)h)->nearest_cell({p[0], p[1], p[2]}); }
 

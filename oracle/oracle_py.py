@@ -123,6 +123,16 @@ class Oracle:
         return pairs[: npairs.value].copy(), ft
 
 
+_programs_keepalive = None
+
+
+def set_programs(ops):
+    """The op table the SDFIBM_SHAPE_PROGRAM records of later calls point into (process-wide; kept alive here)."""
+    global _programs_keepalive
+    _programs_keepalive = None if ops is None else np.ascontiguousarray(ops)
+    load().oracle_set_programs(None if ops is None else _p(_programs_keepalive))
+
+
 def eval_points(shapes, solid, pts):
     shapes = np.ascontiguousarray(shapes)
     solid = np.ascontiguousarray(solid)

@@ -53,6 +53,7 @@ HOST_LIB = os.path.join(HERE, "libsdfibm_host.so")
 HOST_DIR = os.path.join(HERE, "host")
 HOST_SOURCES = [os.path.join(HOST_DIR, "solidcloud.cpp"), os.path.join(HOST_DIR, "capi_host.cpp")]
 RUNNER = os.path.join(HERE, "sdfibm_b200_run")
+VOF_RUNNER = os.path.join(HERE, "sdfibm_b200_vof")
 
 
 def _host_deps():
@@ -65,7 +66,7 @@ def _host_deps():
 
 def build_host(force: bool = False) -> str:
     """Host façade (C++17, g++): libsdfibm_host.so + the stand-alone runner, linked against the CUDA library."""
-    outs = [HOST_LIB, RUNNER]
+    outs = [HOST_LIB, RUNNER, VOF_RUNNER]
     if not force and all(os.path.exists(o) for o in outs):
         t = min(os.path.getmtime(o) for o in outs)
         if all(os.path.getmtime(d) <= t for d in _host_deps()):
@@ -73,7 +74,8 @@ def build_host(force: bool = False) -> str:
     common = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-Wall"]
     link = ["-L" + HERE, "-lsdfibm_b200", "-Wl,-rpath,$ORIGIN"]
     for cmd in (common + ["-shared", "-o", HOST_LIB] + HOST_SOURCES + link,
-                common + ["-o", RUNNER, os.path.join(HOST_DIR, "standalone_main.cpp")] + HOST_SOURCES + link):
+                common + ["-o", RUNNER, os.path.join(HOST_DIR, "standalone_main.cpp")] + HOST_SOURCES + link,
+                common + ["-o", VOF_RUNNER, os.path.join(HOST_DIR, "tool_vof", "vof_main.cpp"), os.path.join(HOST_DIR, "solidcloud.cpp")] + link):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("host build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -18,6 +18,12 @@ SHAPE_TAGS = {
     "Plane": 0, "Circle": 1, "Sphere": 2, "Ellipse": 3, "Ellipsoid": 4,
     "Rectangle": 5, "Box": 6, "Circle_Tail": 7, "Circle_TwoTail": 8,
 }
+SHAPE_PROGRAM_TAG = 9
+# sdfibm_sdf_op_t and its opcodes (include/sdfibm_b200.h)
+SDF_OP_DTYPE = np.dtype([("op", "<i4"), ("pad_", "<i4"), ("a", "<f8", 4)], align=True)
+SDF_OPS = {"POINT": 0, "POINT_2D": 1, "OFFSET": 2, "ROT30": 3, "ROT45": 4, "ROT60": 5, "ROT90": 6, "ROTTH": 7, "FLIPX": 8, "FLIPY": 9,
+           "CIRCLE": 16, "RECTANGLE": 17, "BOX": 18, "ELLIPSE": 19, "ELLIPSOID": 20, "HALFSPACE": 21,
+           "UNION": 32, "INTERSECT": 33, "DIFF": 34}
 
 # numpy dtypes that mirror the POD records (sdfibm_shape_t, sdfibm_solid_t)
 SHAPE_DTYPE = np.dtype(
@@ -27,7 +33,7 @@ SOLID_DTYPE = np.dtype(
     [("pos", "<f8", 3), ("quat", "<f8", 4), ("vel", "<f8", 3), ("omega", "<f8", 3), ("shape", "<i4"), ("pad_", "<i4")],
     align=True,
 )
-assert SHAPE_DTYPE.itemsize == 104 and SOLID_DTYPE.itemsize == 112
+assert SHAPE_DTYPE.itemsize == 104 and SOLID_DTYPE.itemsize == 112 and SDF_OP_DTYPE.itemsize == 40
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -62,11 +68,13 @@ SYMBOLS = {
     "sdfibm_set_cell_slots": (C.c_int, [_VP, C.c_int]),
     "sdfibm_set_mesh": (C.c_int, [_VP, C.POINTER(MeshT), C.c_int]),
     "sdfibm_set_shapes": (C.c_int, [_VP, _VP, C.c_int]),
+    "sdfibm_set_shape_programs": (C.c_int, [_VP, _VP, C.c_int]),
     "sdfibm_interact": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "sdfibm_interact_device": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "sdfibm_interact_device_solids": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "sdfibm_fix_internal": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "sdfibm_fix_internal_device": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
+    "sdfibm_volume_fraction": (C.c_int, [_VP, _VP, C.c_int, _VP, c_double_p]),
     "sdfibm_mean_field": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
     "sdfibm_mean_field_sums": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
     "sdfibm_allow_order_free": (C.c_int, [_VP, C.c_int]),

@@ -43,6 +43,11 @@ class Context:
         self.mesh = mesh
         self.n_cells = mesh.n_cells
 
+    def set_shape_programs(self, ops: np.ndarray):
+        """Op table of the composed shapes (SDFIBM_SHAPE_PROGRAM records point into it); call before set_shapes."""
+        ops = np.ascontiguousarray(ops, dtype=capi.SDF_OP_DTYPE)
+        capi.check(self._lib.sdfibm_set_shape_programs(self._h, capi.ptr(ops), len(ops)))
+
     def set_shapes(self, shapes: np.ndarray):
         shapes = np.ascontiguousarray(shapes, dtype=capi.SHAPE_DTYPE)
         capi.check(self._lib.sdfibm_set_shapes(self._h, capi.ptr(shapes), len(shapes)))
@@ -139,6 +144,15 @@ class Context:
         solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
         capi.check(self._lib.sdfibm_fix_internal_device(self._h, capi.ptr(solids), len(solids), capi.ptr(dU),
                                                         capi.ptr(dCt) if dCt else None))
+
+    # ---- tool_vof: SolidCloud::writeVOF ----
+    def volume_fraction(self, solids: np.ndarray):
+        """(alpha[n_cells], sum(alpha V)) of the union of the solids (tool_vof/solidcloud.cpp:116-173)."""
+        solids = np.ascontiguousarray(solids, dtype=capi.SOLID_DTYPE)
+        alpha = np.empty(self.n_cells)
+        tot = C.c_double()
+        capi.check(self._lib.sdfibm_volume_fraction(self._h, capi.ptr(solids), len(solids), capi.ptr(alpha), C.byref(tot)))
+        return alpha, float(tot.value)
 
     # ---- SolidCloud::calcMeanField ----
     def mean_field(self, solids: np.ndarray, field: np.ndarray):

@@ -65,12 +65,124 @@ __host__ __device__ __forceinline__ double rect_sd(D3 p, double ra, double rb) {
 }
 __host__ __device__ __forceinline__ D3 rot30(D3 p) { return {0.866025404 * p.x + 0.5 * p.y, 0.866025404 * p.y - 0.5 * p.x, 0.0}; }
 
+// the other point transformations of sdf.h:95-122 (literals as in the reference)
+__host__ __device__ __forceinline__ D3 rot45(D3 p) { return 0.707106781 * D3{p.x + p.y, -p.x + p.y, 0.0}; }
+__host__ __device__ __forceinline__ D3 rot60(D3 p) { return {0.866025404 * p.y + 0.5 * p.x, -0.866025404 * p.x + 0.5 * p.y, 0.0}; }
+__host__ __device__ __forceinline__ D3 rot90(D3 p) { return {p.y, -p.x, 0.0}; }
+__host__ __device__ __forceinline__ D3 rotth(D3 p, double th) {
+    const double s = sin(th), c = cos(th);
+    return {p.x * c + p.y * s, -p.x * s + p.y * c, 0.0};
+}
+
+// A composed shape (SDFIBM_SHAPE_PROGRAM): post-fix evaluation of sdf.h's primitives / transformations / Boolean operations
+// (see sdfibm_sdf_op_t).  The bool and the scalar of a value are the reference's two separate expressions, side by side.
+// Programs are validated on the host (sdfibm_set_shapes): the stacks cannot over- or underflow here.
+#ifdef __CUDACC__
+#define SDF_NOINLINE __noinline__   // a real call, taken only by composed shapes: the interpreter's local stacks stay out of the hot kernels' frames
+#else
+#define SDF_NOINLINE
+#endif
+template <bool WANT_PHI>
+__host__ __device__ SDF_NOINLINE bool sdf_program_eval(const sdfibm_sdf_op_t *ops, int n_ops, D3 com, D3 p, double &phi) {
+    D3 pt[SDFIBM_SDF_STACK];
+    bool vb[SDFIBM_SDF_STACK];
+    double vd[SDFIBM_SDF_STACK];
+    int np = 0, nv = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const sdfibm_sdf_op_t &o = ops[i];
+        const double a0 = o.a[0], a1 = o.a[1], a2 = o.a[2];
+        switch (o.op) {
+        case SDFIBM_OP_POINT: pt[np++] = com + p; break;
+        case SDFIBM_OP_POINT_2D: { D3 q = com + p; q.z = 0.0; pt[np++] = q; break; }
+        case SDFIBM_OP_OFFSET: pt[np - 1] = pt[np - 1] - D3{a0, a1, a2}; break;
+        case SDFIBM_OP_ROT30: pt[np - 1] = rot30(pt[np - 1]); break;
+        case SDFIBM_OP_ROT45: pt[np - 1] = rot45(pt[np - 1]); break;
+        case SDFIBM_OP_ROT60: pt[np - 1] = rot60(pt[np - 1]); break;
+        case SDFIBM_OP_ROT90: pt[np - 1] = rot90(pt[np - 1]); break;
+        case SDFIBM_OP_ROTTH: pt[np - 1] = rotth(pt[np - 1], a0); break;
+        case SDFIBM_OP_FLIPX: pt[np - 1].x = -pt[np - 1].x; break;
+        case SDFIBM_OP_FLIPY: pt[np - 1].y = -pt[np - 1].y; break;
+        case SDFIBM_OP_CIRCLE: {
+            const double m2 = magSqr3(pt[--np]);
+            vb[nv] = m2 < a1;
+            if (WANT_PHI) vd[nv] = sqrt(m2) - a0;
+            ++nv;
+            break;
+        }
+        case SDFIBM_OP_RECTANGLE: {
+            const D3 P = pt[--np];
+            vb[nv] = rect_bool(P, a0, a1);
+            if (WANT_PHI) vd[nv] = rect_sd(P, a0, a1);
+            ++nv;
+            break;
+        }
+        case SDFIBM_OP_BOX: {
+            const D3 P = pt[--np];
+            const double dx = fabs(P.x) - a0, dy = fabs(P.y) - a1, dz = fabs(P.z) - a2;
+            vb[nv] = fabs(P.x) < a0 && fabs(P.y) < a1 && fabs(P.z) < a2;
+            if (WANT_PHI) {
+                const double dxp = smax(0.0, dx), dyp = smax(0.0, dy), dzp = smax(0.0, dz);
+                vd[nv] = sqrt(dxp * dxp + dyp * dyp + dzp * dzp) + smin(0.0, smax(dz, smax(dx, dy)));
+            }
+            ++nv;
+            break;
+        }
+        case SDFIBM_OP_ELLIPSE: {
+            const D3 P = pt[--np];
+            const double X = P.x * P.x * a0, Y = P.y * P.y * a1;
+            vb[nv] = X + Y < 1.0;
+            if (WANT_PHI) vd[nv] = 0.5 * (X + Y - 1.0) / (sqrt(X * a0 + Y * a1));
+            ++nv;
+            break;
+        }
+        case SDFIBM_OP_ELLIPSOID: {
+            const D3 P = pt[--np];
+            const double X = P.x * P.x * a0, Y = P.y * P.y * a1, Z = P.z * P.z * a2;
+            vb[nv] = X + Y + Z < 1.0;
+            if (WANT_PHI) vd[nv] = 0.5 * (X + Y + Z - 1.0) / (sqrt(X * a0 + Y * a1 + Z * a2));
+            ++nv;
+            break;
+        }
+        case SDFIBM_OP_HALFSPACE: {
+            const D3 P = pt[--np];
+            vb[nv] = P.y < 0;
+            if (WANT_PHI) vd[nv] = P.y;
+            ++nv;
+            break;
+        }
+        case SDFIBM_OP_UNION:       // sdf::U: std::min of the distances, std::max of the bools (:135-138)
+            --nv;
+            vb[nv - 1] = vb[nv - 1] || vb[nv];
+            if (WANT_PHI) vd[nv - 1] = smin(vd[nv - 1], vd[nv]);
+            break;
+        case SDFIBM_OP_INTERSECT:   // sdf::I (:139-142)
+            --nv;
+            vb[nv - 1] = vb[nv - 1] && vb[nv];
+            if (WANT_PHI) vd[nv - 1] = smax(vd[nv - 1], vd[nv]);
+            break;
+        case SDFIBM_OP_DIFF:        // sdf::D (:131-133)
+            --nv;
+            vb[nv - 1] = vb[nv - 1] && !vb[nv];
+            if (WANT_PHI) vd[nv - 1] = smax(vd[nv - 1], -vd[nv]);
+            break;
+        default: break;
+        }
+    }
+    if (WANT_PHI) phi = (nv > 0) ? sdf_filter(vd[0]) : 0.0;
+    return nv > 0 && vb[0];
+}
+
 // Evaluate isInside and (optionally) signedDistance for a body-frame point.  Shape parameters are
 // passed by pointer to the POD record so both host and device can call it.
-template <bool WANT_PHI>
-__host__ __device__ __forceinline__ bool shape_eval(const sdfibm_shape_t &s, D3 p, double &phi) {
+// `ops`: the op table SDFIBM_SHAPE_PROGRAM records point into (may be null when the table holds no such record).
+// HAS_PROG = false compiles the interpreter call out (the kernels of shape tables without composed shapes).
+template <bool WANT_PHI, bool HAS_PROG = true>
+__host__ __device__ __forceinline__ bool shape_eval(const sdfibm_shape_t &s, D3 p, double &phi, const sdfibm_sdf_op_t *ops = nullptr) {
     const D3 com = {s.com[0], s.com[1], s.com[2]};
     switch (s.tag) {
+    case SDFIBM_SHAPE_PROGRAM:
+        if (!HAS_PROG || !ops) break;
+        return sdf_program_eval<WANT_PHI>(ops + (int)s.p[0], (int)s.p[1], com, p, phi);
     case SDFIBM_SHAPE_PLANE:
         if (WANT_PHI) phi = p.y;
         return p.y < 0;

@@ -138,6 +138,7 @@ struct InteractParams {
     DevMesh m;
     const DevSolid *solids;
     const DevShape *shapes;
+    const sdfibm_sdf_op_t *ops;   // op table of the SDFIBM_SHAPE_PROGRAM records (null: none)
     int n_solids;
     BinGrid grid;
     const int *bin_off;
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
 // k_heavy: exact evaluation of one (cell, solid) item
 // ------------------------------------------------------------------------------------------------
 // General polyhedra: cell-local arrays in local memory, CSR connectivity.
+template <bool PROG>
 __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, int s, int &type_out, double &vol_out) {
     const DevMesh &m = P.m;
     const DevSolid &S = P.solids[s];
@@ -401,7 +403,7 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
         vid[k] = __ldg(m.cp + pb + k);
         pts[k] = ld3(m.points, vid[k]);
         double ph;
-        n_in += shape_eval<true>(sh.s, world2local_sel(q, t, pts[k], ident), ph) ? 1 : 0;
+        n_in += shape_eval<true, PROG>(sh.s, world2local_sel(q, t, pts[k], ident), ph, P.ops) ? 1 : 0;
         phi[k] = ph;
     }
     type_out = 0;
@@ -409,7 +411,7 @@ __device__ __noinline__ void heavy_eval_general(const InteractParams &P, int c, 
     if (n_in == 0) return;
     if (n_in == nv) { type_out = SDFIBM_CELL_ALL_INSIDE; return; }
     double dummy;
-    type_out = shape_eval<false>(sh.s, world2local_sel(q, t, ld3(m.cc, c), ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+    type_out = shape_eval<false, PROG>(sh.s, world2local_sel(q, t, ld3(m.cc, c), ident), dummy, P.ops) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
     vol_out = cell_solid_volume(m, c, vid, pts, phi, nv);
 }
 
@@ -443,11 +445,12 @@ __device__ __forceinline__ void stage_point(HeavySmem &sm, const double *__restr
 }
 
 // evaluate the staged vertex (slot_a, col_a); dup: the same vertex is slot_b of the neighbouring lane's cell
-__device__ __forceinline__ void eval_staged_vertex(HeavySmem &sm, const DevShape &sh, DQ q, D3 t, bool ident,
+template <bool PROG>
+__device__ __forceinline__ void eval_staged_vertex(HeavySmem &sm, const DevShape &sh, const sdfibm_sdf_op_t *ops, DQ q, D3 t, bool ident,
                                                    int slot_a, int col_a, bool dup, int slot_b, int col_b) {
     const D3 p = {sm.px[slot_a * TPB + col_a], sm.py[slot_a * TPB + col_a], sm.pz[slot_a * TPB + col_a]};
     double ph;
-    const bool in = shape_eval<true>(sh.s, world2local_sel(q, t, p, ident), ph);
+    const bool in = shape_eval<true, PROG>(sh.s, world2local_sel(q, t, p, ident), ph, ops);
     sm.phi[slot_a * TPB + col_a] = ph;
     sm.in[slot_a * TPB + col_a] = in ? 1 : 0;
     if (dup) {
@@ -457,7 +460,7 @@ __device__ __forceinline__ void eval_staged_vertex(HeavySmem &sm, const DevShape
 }
 
 #define HEAVY_CTAS_PER_SM 5
-template <int CTAS>
+template <int CTAS, bool PROG>
 __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
     __shared__ HeavySmem sm;
     const DevMesh &m = P.m;
@@ -531,7 +534,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
         if (valid) {
 #pragma unroll
             for (int v = 0; v < 4; ++v)
-                eval_staged_vertex(sm, sh, q, t, ident, 2 * v + 1, tid, right_shares, 2 * v, tid + 1);
+                eval_staged_vertex<PROG>(sm, sh, P.ops, q, t, ident, 2 * v + 1, tid, right_shares, 2 * v, tid + 1);
         }
         // extra rounds: low quads of the run starts, 4 vertices each, spread over all lanes
         const int nwork = 4 * __popc(startmask);
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
                 const DevSolid &S2 = P.solids[s_src];
                 const DQ q2 = {S2.q[0], {S2.q[1], S2.q[2], S2.q[3]}};
                 const D3 t2 = {S2.pos[0], S2.pos[1], S2.pos[2]};
-                eval_staged_vertex(sm, P.shapes[S2.shape], q2, t2, ident, kk, col, false, 0, 0);
+                eval_staged_vertex<PROG>(sm, P.shapes[S2.shape], P.ops, q2, t2, ident, kk, col, false, 0, 0);
             }
         }
         __syncwarp();
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
             if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
             else if (n_in != 0) {
                 double dummy;
-                type = shape_eval<false>(sh.s, world2local_sel(q, t, D3{sm.cx[tid], sm.cy[tid], sm.cz[tid]}, ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                type = shape_eval<false, PROG>(sh.s, world2local_sel(q, t, D3{sm.cx[tid], sm.cy[tid], sm.cz[tid]}, ident), dummy, P.ops) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
                 auto PT = [&](int l) { return D3{sm.px[l * TPB + tid], sm.py[l * TPB + tid], sm.pz[l * TPB + tid]}; };
                 auto PH = [&](int l) { return sm.phi[l * TPB + tid]; };
                 // cell apex over the cell's vertex list (geometrictools.cpp:25-45,56-58)
@@ -680,7 +683,7 @@ struct BoxSmem {
     double apex[3 * TPB];
 };
 
-template <bool PLANE_FROM_MESH>
+template <bool PLANE_FROM_MESH, bool PROG>
 __global__ void __launch_bounds__(TPB, BOX_CTAS_PER_SM) k_heavy_box(InteractParams P) {
     __shared__ BoxSmem sm;
     const DevMesh &m = P.m;
@@ -744,7 +747,7 @@ PRAGMA_UNROLL(BOX_VUNROLL)
             for (int code = 0; code < 8; ++code) {
                 const D3 p = {lohi[(code & 1) * TPB], lohi[(2 + ((code >> 1) & 1)) * TPB], lohi[(4 + ((code >> 2) & 1)) * TPB]};
                 double phv;
-                n_in += shape_eval<true>(sh.s, world2local_sel(q, t, p, ident), phv) ? 1 : 0;
+                n_in += shape_eval<true, PROG>(sh.s, world2local_sel(q, t, p, ident), phv, P.ops) ? 1 : 0;
                 pm |= (phv > 0 ? 1u : 0u) << code;
                 phi[code * TPB] = phv;
             }
@@ -755,7 +758,7 @@ PRAGMA_UNROLL(BOX_VUNROLL)
             if (n_in == 8) type = SDFIBM_CELL_ALL_INSIDE;
             else if (n_in != 0) {
                 double dummy;
-                type = shape_eval<false>(sh.s, world2local_sel(q, t, cc, ident), dummy) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
+                type = shape_eval<false, PROG>(sh.s, world2local_sel(q, t, cc, ident), dummy, P.ops) ? SDFIBM_CELL_CENTER_INSIDE : SDFIBM_CELL_CENTER_OUTSIDE;
                 // cell apex over cellPoints() order (geometrictools.cpp:25-45,56-58)
                 {
                     const int cA = tw.x & 7;
@@ -823,6 +826,7 @@ PRAGMA_UNROLL(BOX_FUNROLL)
     }
 }
 
+template <bool PROG>
 __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
     // all-polyhedral meshes: the front queue; mixed meshes: the back queue (item i at heavy_cap - 1 - i)
     const bool back = P.m.mixed != 0;
@@ -835,7 +839,7 @@ __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
         const int2 it = __ldg(P.heavy + k); // (cell, solid)
         int type;
         double v;
-        heavy_eval_general(P, it.x, it.y, type, v);
+        heavy_eval_general<PROG>(P, it.x, it.y, type, v);
         P.heavy_res[k] = make_double2(v, __longlong_as_double((long long)(type | (it.y << 2))));
     }
 }

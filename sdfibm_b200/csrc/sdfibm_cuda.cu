@@ -790,6 +790,8 @@ struct sdfibm_context {
     // shapes
     std::vector<DevShape> h_shapes;
     DevBuf<DevShape> shapes;
+    std::vector<sdfibm_sdf_op_t> h_ops;   // op table of the composed shapes (SDFIBM_SHAPE_PROGRAM)
+    DevBuf<sdfibm_sdf_op_t> sdf_ops;
     // per step
     DevBuf<sdfibm_solid_t> solids_in;
     DevBuf<DevSolid> solids;
@@ -883,6 +885,11 @@ static void shape_bounds(const sdfibm_shape_t &s, DevShape &d) {
     case SDFIBM_SHAPE_ELLIPSOID: ro = std::max(p[0], std::max(p[1], p[2])); ri = std::min(p[0], std::min(p[1], p[2])); comv = 0; break;
     case SDFIBM_SHAPE_RECTANGLE: kind = KIND_2D; ro = std::sqrt(p[0] * p[0] + p[1] * p[1]); ri = std::min(p[0], p[1]); break;
     case SDFIBM_SHAPE_BOX: ro = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]); ri = std::min(p[0], std::min(p[1], p[2])); break;
+    case SDFIBM_SHAPE_PROGRAM:   // the record carries its certified radii (include/sdfibm_b200.h)
+        kind = p[4] != 0.0 ? KIND_2D : KIND_3D;
+        ro = p[2];
+        ri = p[3];
+        break;
     case SDFIBM_SHAPE_CIRCLE_TAIL:
     case SDFIBM_SHAPE_CIRCLE_TWOTAIL:
         kind = KIND_2D;
@@ -1021,7 +1028,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->cp_off.release(); ctx->cp.release(); ctx->cf_off.release(); ctx->cf.release();
     ctx->fp_off.release(); ctx->fp.release(); ctx->nb_off.release(); ctx->nb.release();
     ctx->tile_key.release(); ctx->orig.release(); ctx->inv.release(); ctx->cc_orig.release(); ctx->cc32.release();
-    ctx->tile_proven.release(); ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->btopo.release(); ctx->box6.release(); ctx->cfa6.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->solids_in.release(); ctx->solids.release();
+    ctx->tile_proven.release(); ctx->cell_box.release(); ctx->cell_rad.release(); ctx->magSf.release(); ctx->face_rec.release(); ctx->hex_topo.release(); ctx->btopo.release(); ctx->box6.release(); ctx->cfa6.release(); ctx->nb6.release(); ctx->shapes.release(); ctx->sdf_ops.release(); ctx->solids_in.release(); ctx->solids.release();
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->comm && nccl_api()->handle) nccl_api()->CommDestroy(ctx->comm);
     ctx->ft_partial.release(); ctx->retry_flag.release(); ctx->solids_slice.release(); ctx->solids_gathered.release();
@@ -1364,6 +1371,38 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     return SDFIBM_OK;
 }
 
+// stack discipline of a composed shape's program: every op finds its operands, depths stay within SDFIBM_SDF_STACK, exactly
+// one value is left
+static std::string check_sdf_program(const std::vector<sdfibm_sdf_op_t> &ops, const sdfibm_shape_t &rec) {
+    const double first = rec.p[0], count = rec.p[1];
+    if (!(first >= 0) || !(count >= 1) || first != std::floor(first) || count != std::floor(count) || first + count > (double)ops.size())
+        return "program range outside the op table (call sdfibm_set_shape_programs first)";
+    if (!(rec.p[2] > 0) || !(rec.p[3] >= 0) || rec.p[3] > rec.p[2]) return "a composed shape needs certified radii: p[2] = outer > 0, 0 <= p[3] = inner <= outer";
+    int np = 0, nv = 0;
+    for (int i = (int)first; i < (int)(first + count); ++i) {
+        const int op = ops[i].op;
+        if (op == SDFIBM_OP_POINT || op == SDFIBM_OP_POINT_2D) ++np;
+        else if (op >= SDFIBM_OP_OFFSET && op <= SDFIBM_OP_FLIPY) { if (np < 1) return "a point transformation without a point"; }
+        else if (op >= SDFIBM_OP_CIRCLE && op <= SDFIBM_OP_HALFSPACE) { if (np < 1) return "a primitive without a point"; --np; ++nv; }
+        else if (op >= SDFIBM_OP_UNION && op <= SDFIBM_OP_DIFF) { if (nv < 2) return "a Boolean operation without two values"; --nv; }
+        else return "unknown opcode " + std::to_string(op);
+        if (np > SDFIBM_SDF_STACK || nv > SDFIBM_SDF_STACK) return "stack deeper than SDFIBM_SDF_STACK";
+    }
+    if (nv != 1 || np != 0) return "the program must consume its points and leave exactly one value";
+    return "";
+}
+
+int sdfibm_set_shape_programs(sdfibm_context *ctx, const sdfibm_sdf_op_t *ops, int n_ops) {
+    if (!ctx || n_ops < 0 || (n_ops > 0 && !ops)) return fail(SDFIBM_ERR_ARG, "sdfibm_set_shape_programs: bad argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    drop_graph(ctx);
+    ctx->h_ops.assign(ops, ops + n_ops);
+    const int rc = upload(ctx->sdf_ops, ctx->h_ops.data(), (size_t)n_ops, ctx->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SDFIBM_OK;
+}
+
 int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) {
     if (!ctx || !shapes || n <= 0) return fail(SDFIBM_ERR_ARG, "sdfibm_set_shapes: bad argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1372,6 +1411,10 @@ int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) 
     for (int i = 0; i < n; ++i) {
         if (shapes[i].tag < 0 || shapes[i].tag >= SDFIBM_SHAPE_NTAGS)
             return fail(SDFIBM_ERR_UNSUPPORTED, "sdfibm_set_shapes: shape type has no device tag (no CPU fallback)");
+        if (shapes[i].tag == SDFIBM_SHAPE_PROGRAM) {
+            const std::string err = check_sdf_program(ctx->h_ops, shapes[i]);
+            if (!err.empty()) return fail(SDFIBM_ERR_ARG, "sdfibm_set_shapes: shape " + std::to_string(i) + ": " + err);
+        }
         shape_bounds(shapes[i], ctx->h_shapes[i]);
     }
     ctx->shapes_may_be_global = false;
@@ -1593,7 +1636,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     InteractParams I;
-    I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.n_solids = n_solids; I.grid = g;
+    I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.ops = ctx->h_ops.empty() ? nullptr : ctx->sdf_ops.p; I.n_solids = n_solids; I.grid = g;
     I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.bin_entries = ctx->bin_entries.p; I.global_list = ctx->global_list.p; I.U = dU;
     I.scal = ctx->scal.p; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
     I.pair_counts = ctx->pair_counts; I.slots = ctx->slots.p; I.K = ctx->K;
@@ -1610,10 +1653,13 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         else k_classify<256, 8, false, false><<<grid, 256, 0, st>>>(I);
     };
     auto launch_heavy = [&]() {
-        if (ctx->dm.box_exact == 2) k_heavy_box<false><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
-        else if (ctx->dm.box_exact == 1) k_heavy_box<true><<<ctx->n_sm * BOX_CTAS_PER_SM, TPB, 0, st>>>(I);
-        else if (ctx->dm.is_hex || ctx->dm.mixed) k_heavy_hex<HEAVY_CTAS_PER_SM><<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
-        if (!ctx->dm.is_hex) k_heavy_general<<<ctx->n_sm * HEAVY_CTAS_PER_SM, TPB, 0, st>>>(I);
+        // (PROG: the shape table holds a composed shape — only then do the kernels carry the op interpreter)
+        const bool prog = !ctx->h_ops.empty();
+        const int gb = ctx->n_sm * BOX_CTAS_PER_SM, gh = ctx->n_sm * HEAVY_CTAS_PER_SM;
+        if (ctx->dm.box_exact == 2) { if (prog) k_heavy_box<false, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<false, false><<<gb, TPB, 0, st>>>(I); }
+        else if (ctx->dm.box_exact == 1) { if (prog) k_heavy_box<true, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<true, false><<<gb, TPB, 0, st>>>(I); }
+        else if (ctx->dm.is_hex || ctx->dm.mixed) { if (prog) k_heavy_hex<HEAVY_CTAS_PER_SM, true><<<gh, TPB, 0, st>>>(I); else k_heavy_hex<HEAVY_CTAS_PER_SM, false><<<gh, TPB, 0, st>>>(I); }
+        if (!ctx->dm.is_hex) { if (prog) k_heavy_general<true><<<gh, TPB, 0, st>>>(I); else k_heavy_general<false><<<gh, TPB, 0, st>>>(I); }
     };
     I.heavy_start = nullptr;
     CUDA_TRY(rec(ctx->ev[1]));
@@ -1749,7 +1795,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
                                       (uint64_t)(ctx->ext_solids ? ctx->ext_solids : (ctx->gathered_now ? ctx->solids_gathered.p : ctx->solids_in.p)), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
-                                      (uint64_t)ctx->shapes.p, (uint64_t)ctx->scan_tmp.p ^ ((uint64_t)ctx->tile_proven.p << 1), (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
+                                      (uint64_t)ctx->shapes.p ^ ((uint64_t)ctx->sdf_ops.p << 2), (uint64_t)ctx->scan_tmp.p ^ ((uint64_t)ctx->tile_proven.p << 1), (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
                                       (uint64_t)ctx->n_global_hint};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
@@ -2095,6 +2141,48 @@ int sdfibm_mean_field_sums(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     for (int s = 0; s < n_solids; ++s) {
         for (int d = 0; d < 3; ++d) sum_alpha_v_field[3 * s + d] = ft[6 * (size_t)s + d];
         sum_alpha_v[s] = ft[6 * ((size_t)n_solids + s)];
+    }
+    return SDFIBM_OK;
+}
+
+// tool_vof (tool_vof/solidcloud.cpp:116-173): the solid volume fraction of every cell — interact's As kernel on scratch outputs
+int sdfibm_volume_fraction(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n_solids, double *alpha, double *total_volume) {
+    if (!ctx || n_solids < 0 || (n_solids > 0 && !solids) || !alpha) return fail(SDFIBM_ERR_ARG, "sdfibm_volume_fraction: null argument");
+    if (!ctx->has_mesh || (n_solids > 0 && ctx->h_shapes.empty())) return fail(SDFIBM_ERR_STATE, "sdfibm_volume_fraction: set mesh and shapes first");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t nC = ctx->dm.n_cells;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx->sU.ensure(3 * nC));
+    CUDA_TRY(ctx->sOut.ensure(6 * nC));
+    CUDA_TRY(ctx->sFT.ensure(12 * (size_t)std::max(n_solids, 1)));
+    // solids at rest in a fluid at rest, dt = 1: only As is of interest (the per-solid += and the clamp at 1 of
+    // tool_vof/solidcloud.cpp:131-133 are interact's own accumulation order and checkAlpha)
+    std::vector<sdfibm_solid_t> rest(solids, solids + n_solids);
+    for (auto &r : rest)
+        for (int d = 0; d < 3; ++d) r.vel[d] = r.omega[d] = 0.0;
+    double *tAs = ctx->sOut.p, *tFs = tAs + nC, *tTs = tFs + 3 * nC, *tCt = tTs + nC;
+    const double *keep_Ct = ctx->last_Ct, *keep_As = ctx->last_As, *keep_Fs = ctx->last_Fs, *keep_Ts = ctx->last_Ts;
+    const int keep_n = ctx->n_solids_last;
+    const bool keep_reduce = ctx->comm_auto_reduce, keep_gather = ctx->comm_gather_solids;
+    ctx->comm_auto_reduce = false; ctx->comm_gather_solids = false;
+    CUDA_TRY(cudaMemsetAsync(ctx->sU.p, 0, sizeof(double) * 3 * nC, st));
+    const int rc = sdfibm_interact_device(ctx, rest.data(), n_solids, ctx->sU.p, 1.0, 1.0, tAs, tFs, tTs, tCt, ctx->sFT.p);
+    ctx->comm_auto_reduce = keep_reduce; ctx->comm_gather_solids = keep_gather;
+    ctx->last_Ct = keep_Ct; ctx->last_As = keep_As; ctx->last_Fs = keep_Fs; ctx->last_Ts = keep_Ts;
+    ctx->n_solids_last = keep_n;
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(alpha, tAs, sizeof(double) * nC, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (total_volume) {   // gSum(tmp * V) (:169)
+        std::vector<double> V(nC);
+        std::vector<int> orig(nC);
+        CUDA_TRY(cudaMemcpy(V.data(), ctx->V.p, sizeof(double) * nC, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(orig.data(), ctx->orig.p, sizeof(int) * nC, cudaMemcpyDeviceToHost));
+        double sum = 0.0;
+        std::vector<double> Vc(nC);
+        for (size_t i = 0; i < nC; ++i) Vc[orig[i]] = V[i];
+        for (size_t c = 0; c < nC; ++c) sum += alpha[c] * Vc[c];
+        *total_volume = sum;
     }
     return SDFIBM_OK;
 }

@@ -3,12 +3,14 @@
 
 #include <cstring>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <vector>
 
 #include "libmotion/motions.h"
 #include "libshape/shapefactory.h"
 #include "solidcloud.h"
+#include "tool_vof/vofcloud.h"
 
 using namespace sdfibm;
 
@@ -98,6 +100,25 @@ int sdfibm_host_evolve(sdfibm_host_cloud *h, double time, double dt) { HOST_TRY(
 int sdfibm_host_save_state(sdfibm_host_cloud *h) { HOST_TRY(h->cloud->saveState()) }
 int sdfibm_host_fix_internal(sdfibm_host_cloud *h, double dt) { HOST_TRY(h->cloud->fixInternal(dt)) }
 int sdfibm_host_save_restart(sdfibm_host_cloud *h, const char *filename) { HOST_TRY(h->cloud->saveRestart(filename)) }
+
+// tool_vof: VofCloud(dictfile, mesh).writeVOF(name) on a Foam-free mesh
+int sdfibm_host_write_vof(const char *dictfile, const char *case_dir, const sdfibm_mesh_t *mesh, const char *field_name, double *alpha,
+                          double *total_volume, int *n_solids, int *n_planes) {
+    HOST_TRY({
+        if (!dictfile || !case_dir || !mesh || !field_name) throw std::runtime_error("sdfibm_host_write_vof: null argument");
+        Foam::fvMesh m(*mesh);
+        m.setTime(0.0);
+        m.setCaseDir(case_dir);
+        Foam::volScalarField field(field_name, m, 0.0);
+        VofCloud cloud(Foam::word(dictfile), m);
+        std::ostringstream info;
+        cloud.writeVOF(field, info);
+        if (alpha) std::memcpy(alpha, cloud.alpha().data(), sizeof(double) * cloud.alpha().size());
+        if (total_volume) *total_volume = cloud.totalVolume();
+        if (n_solids) *n_solids = cloud.nSolids();
+        if (n_planes) *n_planes = cloud.nPlanes();
+    })
+}
 
 int sdfibm_host_n_solids(sdfibm_host_cloud *h, int *n) { HOST_TRY(*n = h->cloud->size()) }
 int sdfibm_host_get_solids(sdfibm_host_cloud *h, sdfibm_solid_t *out) {

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "../types.h"
 
@@ -58,6 +59,14 @@ public:
     // Fill `out` with this shape's device record and return true.  Default: no device tag.
     virtual bool lower(sdfibm_shape_t &out) const {
         (void)out;
+        return false;
+    }
+
+    // Composed shapes (libshape/sdfshape.h): append this shape's post-fix SDF program to `table` and fill `out` with the
+    // SDFIBM_SHAPE_PROGRAM record that points at it.  Default: not a composed shape.  The cloud asks this first, then lower().
+    virtual bool lowerProgram(sdfibm_shape_t &out, std::vector<sdfibm_sdf_op_t> &table) const {
+        (void)out;
+        (void)table;
         return false;
     }
 

@@ -15,6 +15,7 @@
 #endif
 #include "../../csrc/device_math.cuh"
 #include "ishape.h"
+#include "sdfshape.h"
 
 namespace sdfibm {
 
@@ -204,16 +205,18 @@ public:
     SDFIBM_SHAPE_EVAL_VIA_RECORD()
 };
 
-// circle + one rectangular tail: `thickness` is the tail's HALF width (circle_tail.h:18-61)
-class Circle_Tail : public IShape, public _shapecreator<Circle_Tail> {
+// circle + one rectangular tail: `thickness` is the tail's HALF width (circle_tail.h:18-61).  A composed shape: the reference's
+// U({rectangle(offset(p2d, (ra,0,0)), ra, rb), circle(p2d, r)}) stated as a program (bit for bit the hard-coded tag 7 record,
+// tests/test_sdf_programs_cpu.py)
+class Circle_Tail : public SdfShape, public _shapecreator<Circle_Tail> {
 protected:
     scalar m_radius, m_ratio, m_radiusb, m_radiusSQR, m_radiusa;
 
 public:
-    Circle_Tail(const dictionary &para, scalar thickness_factor = 1.0) {
+    Circle_Tail(const dictionary &para) {
         m_radius = Foam::readScalar(para.lookup("radius"));
         m_ratio = Foam::readScalar(para.lookup("ratio"));
-        m_radiusb = Foam::readScalar(para.lookup("thickness")) * thickness_factor;
+        m_radiusb = Foam::readScalar(para.lookup("thickness"));
         m_com = para.lookupOrDefault("com", vector::zero);
         m_radiusSQR = m_radius * m_radius;
         m_radiusa = (m_ratio + 1) * 0.5 * m_radius;
@@ -222,19 +225,22 @@ public:
         const scalar tmp = 0.5 * m_volume * m_radiusSQR;
         detail::diag_moi(*this, tmp, tmp, tmp);
         m_radiusB = 2 * m_radiusa;
+        m_program.point2d().circle(m_radius)                                                        // circle_tail.h:47,55
+            .point2d().offset(vector(m_radiusa, 0.0, 0.0)).rectangle(m_radiusa, m_radiusb).unite();   // :46,56-57 and U (:50,59)
+        // tail box [0, 2 ra] x [-rb, rb]
+        setBounds(std::max(m_radius, std::sqrt(4 * m_radiusa * m_radiusa + m_radiusb * m_radiusb)) * 1.001, m_radius, true);
     }
     SHAPETYPENAME("Circle_Tail")
     virtual std::string description() const override { return "Circle_Tail (x-y plane), r = " + std::to_string(m_radius); }
-    virtual bool lower(sdfibm_shape_t &o) const override {
+    virtual bool lower(sdfibm_shape_t &o) const override {   // the hard-coded record (C-ABI tag 7), kept for hosts that fill records themselves
         lowerCommon(o, SDFIBM_SHAPE_CIRCLE_TAIL);
         o.p[0] = m_radius; o.p[1] = m_radiusSQR; o.p[2] = m_radiusa; o.p[3] = m_radiusb;
         return true;
     }
-    SDFIBM_SHAPE_EVAL_VIA_RECORD()
 };
 
-// circle + two tails at +-30 degrees: the dictionary `thickness` is halved here (circle_twotail.h:18-66)
-class Circle_TwoTail : public IShape, public _shapecreator<Circle_TwoTail> {
+// circle + two tails at +-30 degrees: the dictionary `thickness` is halved here (circle_twotail.h:18-66); composed like Circle_Tail
+class Circle_TwoTail : public SdfShape, public _shapecreator<Circle_TwoTail> {
     scalar m_radius, m_ratio, m_radiusb, m_radiusSQR, m_radiusa;
 
 public:
@@ -250,6 +256,11 @@ public:
         const scalar tmp = 0.5 * m_volume * m_radiusSQR;
         detail::diag_moi(*this, tmp, tmp, tmp);
         m_radiusB = 2 * m_radiusa;
+        const vector shift(m_radiusa, 0, 0);
+        m_program.point2d().circle(m_radius)                                                 // dc  (circle_twotail.h:47,57)
+            .point2d().rot30().offset(shift).rectangle(m_radiusa, m_radiusb).unite()             // d1  (:48-49,58-59)
+            .point2d().flipy().rot30().offset(shift).rectangle(m_radiusa, m_radiusb).unite();    // d2  (:50-51,60-61); U({dc,d1,d2}) (:53,63)
+        setBounds(std::max(m_radius, std::sqrt(4 * m_radiusa * m_radiusa + m_radiusb * m_radiusb) * 1.001), m_radius, true);   // rot30's literal is not unitary
     }
     SHAPETYPENAME("Circle_TwoTail")
     virtual std::string description() const override { return "Circle_TwoTail (x-y plane), r = " + std::to_string(m_radius); }
@@ -258,7 +269,6 @@ public:
         o.p[0] = m_radius; o.p[1] = m_radiusSQR; o.p[2] = m_radiusa; o.p[3] = m_radiusb;
         return true;
     }
-    SDFIBM_SHAPE_EVAL_VIA_RECORD()
 };
 
 // half space local y < 0; not finite: zero volume, so mass_inv = 0 and moi_inv = I / rho (plane.h:13-28, solid.h:95-103)

@@ -148,13 +148,14 @@ void SolidCloud::buildShapeTable() {
     const dictionary &shapes = m_solidDict.subDict("shapes");
     std::vector<sdfibm_shape_t> &table = m_shapeTable;
     table.clear();
+    m_sdfOps.clear();
     std::map<const IShape *, int> index;
     for (const auto &key : shapes.toc()) {
         const std::string name = Foam::word(shapes.subDict(key).lookup("name"));
         const IShape *sh = m_libshape.at(name).get();
         if (index.count(sh)) continue;
         sdfibm_shape_t rec;
-        if (!sh->lower(rec))
+        if (!sh->lowerProgram(rec, m_sdfOps) && !sh->lower(rec))   // a composed shape brings its op program, a primitive its tag record
             throw std::runtime_error("shape type '" + sh->getTypeName() + "' has no device tag: implement IShape::lower() "
                                      "(the coupling path has no CPU fallback)");
         index[sh] = (int)table.size();
@@ -176,6 +177,7 @@ void SolidCloud::ensureDevice() {
     m_ctx = ctx;
     if (const char *k = std::getenv("SDFIBM_CELL_SLOTS")) check(sdfibm_set_cell_slots(m_ctx, std::atoi(k)), "sdfibm_set_cell_slots");
     check(sdfibm_set_mesh(m_ctx, &meshView(m_mesh), m_ON_TWOD ? 1 : 0), "sdfibm_set_mesh");
+    if (!m_sdfOps.empty()) check(sdfibm_set_shape_programs(m_ctx, m_sdfOps.data(), (int)m_sdfOps.size()), "sdfibm_set_shape_programs");
     check(sdfibm_set_shapes(m_ctx, m_shapeTable.data(), (int)m_shapeTable.size()), "sdfibm_set_shapes");
 }
 

@@ -61,6 +61,7 @@ private:
     // device side
     sdfibm_context *m_ctx{nullptr};
     std::vector<sdfibm_shape_t> m_shapeTable;  // lowered shape records, solidDict order
+    std::vector<sdfibm_sdf_op_t> m_sdfOps;     // op programs of the composed shapes (SDFIBM_SHAPE_PROGRAM records point into it)
     std::vector<int> m_shapeIndex;             // per solid: row of the shape table
     std::vector<sdfibm_solid_t> m_records;     // staging of the rigid-body records
     std::vector<double> m_forceTorque;         // [6 N] per-solid (F, T) of the last interact

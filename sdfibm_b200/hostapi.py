@@ -34,6 +34,7 @@ SYMBOLS = {
     "sdfibm_host_get_forces": (C.c_int, [_VP, _VP, _VP]),
     "sdfibm_host_get_masses": (C.c_int, [_VP, _VP]),
     "sdfibm_host_mean_field": (C.c_int, [_VP, _VP]),
+    "sdfibm_host_write_vof": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(capi.MeshT), C.c_char_p, _VP, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdfibm_host_set_collision_delta": (C.c_int, [_VP, C.c_double]),
     "sdfibm_host_reset_subiterations": (C.c_int, []),
     "sdfibm_host_factory_has": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]),
@@ -93,6 +94,45 @@ def shape_eval(dictfile: str, shape_name: str, pos, quat, points):
     check(load().sdfibm_host_shape_eval(dictfile.encode(), shape_name.encode(), capi.ptr(pos), capi.ptr(quat), capi.ptr(points), n,
                                         capi.ptr(inside), capi.ptr(phi)))
     return inside.astype(bool), phi
+
+
+def write_vof(dictfile: str, case_dir: str, mesh, field_name: str = "alpha.water"):
+    """tool_vof: VofCloud(dictfile, mesh).writeVOF(field_name).  Returns (alpha[n_cells], total volume, n_solids, n_planes);
+    the field is also written to <case_dir>/0_<field_name>."""
+    alpha = np.empty(mesh.n_cells)
+    tot = C.c_double()
+    ns, npl = C.c_int(), C.c_int()
+    check(load().sdfibm_host_write_vof(dictfile.encode(), case_dir.encode(), C.byref(mesh.view), field_name.encode(), capi.ptr(alpha),
+                                       C.byref(tot), C.byref(ns), C.byref(npl)))
+    return alpha, float(tot.value), int(ns.value), int(npl.value)
+
+
+def write_vof_dict(path, on_twod, shapes, solids, planes=()):
+    """A solidDict of tool_vof's flavour (tool_vof/example/solidDict): meta.on_twod, shapes{}, solids{ shp_name pos euler }, planes{}."""
+    def body(title, items, prefix):
+        out = [f"{title}\n{{"]
+        for i, b in enumerate(items):
+            out.append(f"    {prefix}{i}\n    {{")
+            out.append(f"        shp_name {b['shp_name']};")
+            out.append(f"        pos {_fmt(tuple(b['pos']))};")
+            out.append(f"        euler {_fmt(tuple(b.get('euler', (0, 0, 0))))};")
+            out.append("    }")
+        out.append("}")
+        return "\n".join(out)
+    lines = ["meta\n{", f"    on_twod {1 if on_twod else 0};", "}", "shapes\n{"]
+    for name, d in shapes.items():
+        lines.append(f"    {name}\n    {{")
+        lines.append(f"        name {name};")
+        for k, v in d.items():
+            lines.append(f"        {k} {_fmt(v)};")
+        lines.append("    }")
+    lines.append("}")
+    lines.append(body("solids", solids, "solid"))
+    if planes:
+        lines.append(body("planes", planes, "plane"))
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return path
 
 
 class HostCloud:

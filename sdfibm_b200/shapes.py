@@ -6,7 +6,7 @@ import math
 
 import numpy as np
 
-from .capi import SHAPE_DTYPE, SHAPE_TAGS, SOLID_DTYPE
+from .capi import SDF_OP_DTYPE, SDF_OPS, SHAPE_DTYPE, SHAPE_PROGRAM_TAG, SHAPE_TAGS, SOLID_DTYPE
 
 
 def make_shape(type_name: str, com=(0.0, 0.0, 0.0), **k) -> np.ndarray:
@@ -80,3 +80,62 @@ def make_solids(n: int) -> np.ndarray:
     s = np.zeros(n, dtype=SOLID_DTYPE)
     s["quat"][:, 0] = 1.0
     return s
+
+
+class SdfProgram:
+    """Builder of a composed shape's post-fix program over the reference's sdf:: namespace (src/libshape/sdf/sdf.h; the op set is
+    documented at sdfibm_sdf_op_t in include/sdfibm_b200.h).  Each method appends one op and returns self:
+
+        tail = (SdfProgram().point2d().circle(r)                                   # d1 = sdf::circle(p2d, r)
+                .point2d().offset((ra, 0, 0)).rectangle(ra, rb)                    # d2 = sdf::rectangle(sdf::offset(p2d, ..), ra, rb)
+                .union())                                                          # sdf::U({d1, d2})
+    """
+
+    def __init__(self):
+        self.ops = []
+
+    def _add(self, name, *a):
+        o = np.zeros((), dtype=SDF_OP_DTYPE)
+        o["op"] = SDF_OPS[name]
+        o["a"][: len(a)] = a
+        self.ops.append(o)
+        return self
+
+    def point(self): return self._add("POINT")
+    def point2d(self): return self._add("POINT_2D")
+    def offset(self, v): return self._add("OFFSET", *[float(x) for x in v])
+    def rot30(self): return self._add("ROT30")
+    def rot45(self): return self._add("ROT45")
+    def rot60(self): return self._add("ROT60")
+    def rot90(self): return self._add("ROT90")
+    def rotth(self, th): return self._add("ROTTH", float(th))
+    def flipx(self): return self._add("FLIPX")
+    def flipy(self): return self._add("FLIPY")
+    def circle(self, r): return self._add("CIRCLE", float(r), float(r) * float(r))
+    sphere = circle
+    def rectangle(self, ra, rb): return self._add("RECTANGLE", float(ra), float(rb))
+    def box(self, ra, rb, rc): return self._add("BOX", float(ra), float(rb), float(rc))
+    def ellipse(self, a, b): return self._add("ELLIPSE", 1.0 / (a * a), 1.0 / (b * b))
+    def ellipsoid(self, a, b, c): return self._add("ELLIPSOID", 1.0 / (a * a), 1.0 / (b * b), 1.0 / (c * c))
+    def halfspace(self): return self._add("HALFSPACE")
+    def union(self): return self._add("UNION")
+    def intersect(self): return self._add("INTERSECT")
+    def diff(self): return self._add("DIFF")
+
+
+def make_program_shapes(programs):
+    """(shape records, op table) of composed shapes: `programs` = list of dict(program=SdfProgram, r_out=, r_in=0.0, two_d=False,
+    com=(0, 0, 0), radiusB=None).  r_out / r_in are the certified radii about the body origin the binning needs."""
+    ops, recs = [], []
+    for d in programs:
+        s = np.zeros((), dtype=SHAPE_DTYPE)
+        s["tag"] = SHAPE_PROGRAM_TAG
+        s["finite"] = 1
+        s["com"] = d.get("com", (0.0, 0.0, 0.0))
+        s["radiusB"] = d.get("radiusB") or d["r_out"]
+        p = np.zeros(8)
+        p[0], p[1], p[2], p[3], p[4] = len(ops), len(d["program"].ops), d["r_out"], d.get("r_in", 0.0), 1.0 if d.get("two_d") else 0.0
+        s["p"] = p
+        recs.append(s)
+        ops.extend(d["program"].ops)
+    return np.array(recs, dtype=SHAPE_DTYPE), np.array(ops, dtype=SDF_OP_DTYPE)
