@@ -7,7 +7,10 @@
 #include <string>
 #include <vector>
 
+#include "libforcer/forcerfactory.h"
+#ifndef SDFIBM_EXTERNAL_PLUGINS
 #include "libmotion/motions.h"
+#endif
 #include "libshape/shapefactory.h"
 #include "solidcloud.h"
 #include "tool_vof/vofcloud.h"
@@ -155,18 +158,10 @@ int sdfibm_host_reset_subiterations(void) { HOST_TRY(SolidCloud::resetSubIterati
 int sdfibm_host_factory_has(const char *kind, const char *type_name, int *found) {
     HOST_TRY({
         const std::string k(kind);
-        dictionary empty;
-        *found = 0;
-        // probing a factory = trying to create: unknown names throw / return null before any dictionary access
-        if (k == "shape") {
-            try { ShapeFactory::create(type_name, empty); *found = 1; }
-            catch (const std::runtime_error &e) { *found = std::string(e.what()).find("unrecognized") == std::string::npos; }
-        } else if (k == "forcer") {
-            try { forcer::ForcerFactory::create(type_name, empty); *found = 1; }
-            catch (const std::runtime_error &e) { *found = std::string(e.what()).find("unrecognized") == std::string::npos; }
-        } else if (k == "motion") {
-            try { IMotion *m = MotionFactory::create(type_name, empty); *found = m != nullptr; delete m; }
-            catch (const std::runtime_error &) { *found = 1; }
+        // (no trial construction: a plugin written for the reference may std::exit() on a dictionary it does not like)
+        if (k == "shape") *found = ShapeFactory::has(type_name);
+        else if (k == "forcer") *found = forcer::ForcerFactory::has(type_name);
+        else if (k == "motion") { *found = MotionFactory::has(type_name);
         } else throw std::runtime_error("unknown factory kind " + k);
     })
 }

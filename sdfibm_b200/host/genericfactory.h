@@ -26,6 +26,9 @@ public:
         return it->second(para);
     }
 
+    // (an addition: is a creator registered under this name?  A plugin's constructor need not run to find out.)
+    static bool has(const std::string &name) { return registry().count(name) != 0; }
+
     static void report(std::ostream &os = std::cout) {
         os << "Objects the factory can \"produce\":\n";
         int i = 1;

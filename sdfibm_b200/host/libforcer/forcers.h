@@ -1,39 +1,11 @@
-// forcers.h — external force/torque generators (reference src/libforcer/{iforcer,forcerfactory,constant,spring,
-// magnetic}.h): generate(t, x, v, q, omega) -> (F, T), blended 1.5 new - 0.5 old by Solid::applyForcer.
+// forcers.h — the three built-in forcers (reference src/libforcer/{constant,spring,magnetic}.h).
 #pragma once
 #include <cmath>
-#include <memory>
-#include <utility>
 
-#include "../genericfactory.h"
-#include "../types.h"
+#include "forcerfactory.h"
 
 namespace sdfibm {
 namespace forcer {
-
-#define FORCERTYPENAME(name)                       \
-    static std::string typeName() { return name; } \
-    static bool added;
-
-class IForcer;
-template <typename T>
-class _creator {
-public:
-    static std::unique_ptr<IForcer> create(const dictionary &para) { return std::make_unique<T>(para); }
-};
-
-class IForcer {
-public:
-    using Force = std::pair<vector, vector>;
-    IForcer() = default;
-    virtual ~IForcer() = default;
-    virtual Force generate(const scalar &time, const vector &position, const vector &velocity, const quaternion &orientation,
-                           const vector &omega) = 0;
-    virtual std::string description() const = 0;
-};
-
-MAKESPECIALFACTORY(Forcer, IForcer, dictionary);
-#define REGISTERFORCE(m) bool sdfibm::m::added = sdfibm::forcer::ForcerFactory::add(sdfibm::m::typeName(), sdfibm::m::create);
 
 class Constant : public IForcer, public _creator<Constant> {   // constant.h:14-33
     vector force, torque;

@@ -39,6 +39,7 @@ public:
         const auto it = methods().find(name);
         return it == methods().end() ? nullptr : it->second(node);
     }
+    static bool has(const std::string &name) { return methods().count(name) != 0; }
     static void report(std::ostream &os = std::cout) {
         int i = 1;
         for (const auto &kv : methods()) os << '[' << i++ << "] " << kv.first << std::endl;

@@ -4,7 +4,9 @@
 #include "../genericfactory.h"
 #include "../types.h"
 #include "ishape.h"
-#include "shapes.h"
+#ifndef SDFIBM_EXTERNAL_PLUGINS
+#include "shapes.h"   // the nine built-in shapes (a build that brings its own plugin set defines SDFIBM_EXTERNAL_PLUGINS)
+#endif
 
 namespace sdfibm {
 MAKESPECIALFACTORY(Shape, IShape, dictionary);
@@ -12,7 +14,7 @@ MAKESPECIALFACTORY(Shape, IShape, dictionary);
 #define REGISTERSHAPE(m) bool sdfibm::m::added = sdfibm::ShapeFactory::add(sdfibm::m::typeName(), sdfibm::m::create);
 } // namespace sdfibm
 
-#ifdef SDFIBM_REGISTER_BUILTINS
+#if defined(SDFIBM_REGISTER_BUILTINS) && !defined(SDFIBM_EXTERNAL_PLUGINS)
 REGISTERSHAPE(Circle)
 REGISTERSHAPE(Sphere)
 REGISTERSHAPE(Ellipse)

