@@ -62,6 +62,14 @@ bool SolidCloud::isMaster() const { return m_rank == 0; }
 bool SolidCloud::isMaster() const { return Foam::Pstream::master(); }
 #endif
 
+void SolidCloud::deviceCommId(void *id128) { check(sdfibm_comm_unique_id(id128), "sdfibm_comm_unique_id"); }
+void SolidCloud::initDeviceComm(const void *id128, int rank, int n_ranks) {
+    ensureDevice();
+    check(sdfibm_comm_init(m_ctx, id128, rank, n_ranks), "sdfibm_comm_init");
+    m_rank = rank;
+    m_reduce = nullptr;   // the sums come back reduced
+}
+
 void SolidCloud::log(const std::string &msg) {
     if (isMaster() && logfile) logfile << msg << std::endl;
 }

@@ -105,6 +105,20 @@ public:
     // ---- additions of this implementation ----
     // cross-rank sum of the per-solid (F, T) array, replacing the 2N Foam::reduce calls (src/solidcloud.cpp:427-431)
     void setForceTorqueReducer(std::function<void(double *, int)> r) { m_reduce = std::move(r); }
+    // The same exchange INSIDE the library (NCCL over NVLink, one ncclAllReduce of 6N fp64 on the context stream right behind the
+    // kernels): rank 0 draws the 128-byte id (deviceCommId), the host broadcasts it (Pstream / MPI / a file), every rank calls
+    // initDeviceComm.  interact() then returns force / torque already summed; no reducer is needed.
+    static void deviceCommId(void *id128);
+    void initDeviceComm(const void *id128, int rank, int n_ranks);
+    // Which solidDict main.cpp reads and where it writes the restart file (src/main.cpp:25-36,93-100): the case root at time 0,
+    // `<time>/solidDict` on a serial restart, `processor0/<time>/solidDict` in a parallel run.
+    static std::string startDictName(const std::string &time_name, scalar time_value, bool par_run) {
+        if (!(time_value > 0)) return "solidDict";
+        return (par_run ? "processor0/" : "") + time_name + "/solidDict";
+    }
+    static std::string restartDictName(const std::string &time_name, bool par_run) {
+        return (par_run ? "./processor0/" : "./") + time_name + "/solidDict";
+    }
     // Foam-free parallel hosts: this process's rank (0 = master: the only one that writes cloud.out / meanfield.out).  With
     // OpenFOAM the answer comes from Pstream::master().
     void setRank(int rank) { m_rank = rank; }

@@ -6,9 +6,13 @@
 //   solidDict      the reference's schema
 //   runDict        mesh { cells (nx ny nz); origin (x y z); spacing (dx dy dz); }   single blockMesh-numbered hex block
 //                  fluid { rho 1; U (ux uy uz); }                                   uniform initial velocity
-//                  time { deltaT 1e-3; nSteps 10; startTime 0; }
-// Outputs: cloud.out, cloud.log, 0_As (initialCorrect), <endTime>/solidDict-style restart file `solidDict.restart`.
+//                  time { deltaT 1e-3; nSteps 10; startTime 0; parallel 0; }
+// Which solidDict is read follows src/main.cpp:25-36: the case root at time 0, `<startTime>/solidDict` on a restart
+// (`processor0/<startTime>/solidDict` with `parallel 1`) when that file exists.
+// Outputs: cloud.out, cloud.log, 0_As (initialCorrect), the restart dictionary `solidDict.restart` and, as main.cpp:93-100 does,
+// `<endTime>/solidDict` (`processor0/<endTime>/solidDict` with `parallel 1`).
 #include <cstdio>
+#include <filesystem>
 #include <iostream>
 #include <memory>
 
@@ -47,7 +51,14 @@ int main(int argc, char **argv) {
         Foam::volScalarField As("As", mesh, 0.0), Ct("Ct", mesh, 0.0), Ts("Ts", mesh, 0.0);
         Foam::volVectorField Fs("Fs", mesh, vector::zero);
 
-        SolidCloud solidcloud(dir + "/solidDict", U, t0);   // main.cpp:38
+        const bool par = td.lookupOrDefault("parallel", (label)0) != 0;
+        auto time_name = [](scalar t) { char b[64]; std::snprintf(b, sizeof b, "%g", t); return std::string(b); };
+        std::string dictfile = dir + "/solidDict";                                  // main.cpp:25-36
+        if (t0 > 0) {
+            const std::string at_time = dir + "/" + SolidCloud::startDictName(time_name(t0), t0, par);
+            if (std::filesystem::exists(at_time)) dictfile = at_time;
+        }
+        SolidCloud solidcloud(dictfile, U, t0);             // main.cpp:38
         solidcloud.saveState();                             // :39
         scalar t = t0;
         for (label step = 0; step < n_steps; ++step) {
@@ -65,6 +76,11 @@ int main(int argc, char **argv) {
             if (solidcloud.isOnFluid()) solidcloud.fixInternal(dt);   // :85-88
         }
         solidcloud.saveRestart(dir + "/solidDict.restart"); // :101
+        {
+            const std::string at_time = dir + "/" + SolidCloud::restartDictName(time_name(t), par);   // :93-100
+            std::filesystem::create_directories(std::filesystem::path(at_time).parent_path());
+            solidcloud.saveRestart(at_time);
+        }
         std::printf("ran %d steps, %d solids, last interact %.3f ms, solid volume %.9g\n", (int)n_steps, (int)solidcloud.size(),
                     solidcloud.lastInteractMs(), solidcloud.totalSolidVolume());
         sdfibm_mesh_free(st);

@@ -105,6 +105,17 @@ def test_standalone_runner_3d(tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "solidDict.restart"))
     log = open(os.path.join(str(tmp_path), "cloud.log")).read()
     assert "FSI took" in log
+    # the restart layout of src/main.cpp:25-36,93-100: <endTime>/solidDict is written and, on a restart from that time, read
+    assert os.path.exists(os.path.join(str(tmp_path), "0.003", "solidDict"))
+    with open(os.path.join(str(tmp_path), "runDict"), "w") as f:
+        f.write("mesh { cells (48 48 48); origin (0 0 0); spacing (0.1 0.1 0.1); }\n"
+                "fluid { rho 1.0; U (0.1 0 0); }\ntime { deltaT 1e-3; nSteps 2; startTime 0.003; parallel 1; }\n")
+    os.makedirs(os.path.join(str(tmp_path), "processor0", "0.003"))
+    os.replace(os.path.join(str(tmp_path), "0.003", "solidDict"), os.path.join(str(tmp_path), "processor0", "0.003", "solidDict"))
+    os.remove(os.path.join(str(tmp_path), "solidDict"))          # only the time-directory copy is left: it must be the one read
+    r2 = subprocess.run([hostapi.RUNNER_PATH, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stderr
+    assert "ran 2 steps, 2 solids" in r2.stdout and os.path.exists(os.path.join(str(tmp_path), "processor0", "0.005", "solidDict"))
 
 
 def test_mean_field_output(tmp_path):
