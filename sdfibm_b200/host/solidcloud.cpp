@@ -129,10 +129,9 @@ void SolidCloud::initFromDictionary(const Foam::word &dictfile) {   // :14-206
         const vector pos = solid.lookup("pos");
         if (m_ON_TWOD && pos.z() != 0)
             throw std::runtime_error("Solid must has z=0 in 2D simulation, violated by solid # " + std::to_string(i));
-        Solid s((label)i, pos, quaternion::I);
-        s.setVelocity(solid.lookupOrDefault("vel", vector::zero));
-        s.setOrientation(solid.lookupOrDefault("euler", vector::zero) * M_PI / 180.0);
-        s.setOmega(solid.lookupOrDefault("omega", vector::zero));
+        const size_t row = m_solids.add(pos, solid.lookupOrDefault("euler", vector::zero) * M_PI / 180.0);
+        m_solids.v[row] = solid.lookupOrDefault("vel", vector::zero);
+        m_solids.w[row] = solid.lookupOrDefault("omega", vector::zero);
 
         const std::string mot_name = Foam::word(solid.lookup("mot_name"));
         const std::string mat_name = Foam::word(solid.lookup("mat_name"));
@@ -141,21 +140,19 @@ void SolidCloud::initFromDictionary(const Foam::word &dictfile) {   // :14-206
             // the reference's operator[] silently inserts a null motion for an unknown name (:186); report it instead
             const auto it = m_libmotion.find(mot_name);
             if (it == m_libmotion.end()) throw std::runtime_error("Unrecognized motion name " + mot_name);
-            s.setMotion(it->second);
+            m_solids.motion[row] = it->second;
         }
         const auto shp = m_libshape.find(shp_name);
         if (shp == m_libshape.end()) throw std::runtime_error("Unrecognized shape name " + shp_name);
-        s.setShape(shp->second.get());
         if (solid.found("for_name")) {
             const std::string for_name = Foam::word(solid.lookup("for_name"));
             const auto f = m_libforcer.find(for_name);
             if (f == m_libforcer.end()) throw std::runtime_error("Unrecognized force name " + for_name);
-            s.setForcer(f->second.get());
+            m_solids.forcer[row] = f->second.get();
         }
         const auto mat = m_libmat.find(mat_name);
         if (mat == m_libmat.end()) throw std::runtime_error("Unrecognized material name " + mat_name);   // null deref in the reference (:198)
-        s.setMaterial(mat->second);
-        this->addSolid(std::move(s));
+        m_solids.setShapeAndMaterial(row, shp->second.get(), mat->second);
     }
     m_solidDict = root;
 }
@@ -180,7 +177,7 @@ void SolidCloud::buildShapeTable() {
     }
     if (table.empty()) throw std::runtime_error("solidDict defines no shapes");
     m_shapeIndex.resize(m_solids.size());
-    for (size_t i = 0; i < m_solids.size(); ++i) m_shapeIndex[i] = index.at(m_solids[i].getShape());
+    for (size_t i = 0; i < m_solids.size(); ++i) m_shapeIndex[i] = index.at(m_solids.shape[i]);
 }
 
 // device context: one per rank, on the GPU given by SDFIBM_DEVICE (default 0).  Created at the first device call; the
@@ -199,8 +196,7 @@ void SolidCloud::ensureDevice() {
 }
 
 void SolidCloud::stageRecords() {
-    m_records.resize(m_solids.size());
-    for (size_t i = 0; i < m_solids.size(); ++i) m_solids[i].toRecord(m_records[i], m_shapeIndex[i]);
+    m_solids.pack(m_records, m_shapeIndex);
 }
 
 SolidCloud::SolidCloud(const Foam::word &dictfile, Foam::volVectorField &U, scalar time)   // :209-274
@@ -244,7 +240,7 @@ void SolidCloud::initialCorrect() {   // :276-286
     this->interact(0, 1);
     m_As.write();
     log("Initial As written to 0 directory");
-    for (Solid &solid : m_solids) solid.clearForceAndTorque();
+    m_solids.clearLoads();
 }
 
 void SolidCloud::fixInternal(scalar) {   // :288-301 — Ct of the last interact, solid state AFTER evolve
@@ -265,10 +261,7 @@ void SolidCloud::interact(scalar time, scalar dt) {   // :435-464
                               cellData(m_Ts), cellData(m_ct), m_forceTorque.data()),
               "sdfibm_interact");
         if (m_reduce) m_reduce(m_forceTorque.data(), (int)m_forceTorque.size());   // :427-431, one sum instead of 2N
-        for (size_t i = 0; i < m_solids.size(); ++i) {
-            const double *ft = &m_forceTorque[6 * i];
-            m_solids[i].setFluidForceAndTorque(vector(ft[0], ft[1], ft[2]), vector(ft[3], ft[4], ft[5]));   // :432
-        }
+        m_solids.setFluidLoads(m_forceTorque.data());   // :432
     } else {
         m_ct = 0.0; m_As = 0.0; m_Fs = vector::zero; m_Ts = 0.0;
     }
@@ -284,13 +277,7 @@ void SolidCloud::interact(scalar time, scalar dt) {   // :435-464
     m_Ts.correctBoundaryConditions();
 }
 
-void SolidCloud::addMidEnvironment() {   // :466-475
-    for (Solid &solid : m_solids) {
-        const scalar rhos = solid.getMaterial()->getRho();
-        const vector gprime = ((rhos - m_rhof) / rhos) * m_gravity;
-        solid.addAcceleration(gprime);
-    }
-}
+void SolidCloud::addMidEnvironment() { m_solids.addBuoyantWeight(m_gravity, m_rhof); }   // :466-475
 
 void SolidCloud::solidSolidInteract() {   // :477-519 — broad phase, narrow phase and force law on the device
     // HEAD constructs its UGrid with cell size 2*m_radiusB = -2, which has no cells and never yields a pair
@@ -302,23 +289,22 @@ void SolidCloud::solidSolidInteract() {   // :477-519 — broad phase, narrow ph
     int64_t n_pairs = 0;
     check(sdfibm_collide(m_ctx, m_records.data(), (int)m_records.size(), m_collisionDelta, nullptr, 0, &n_pairs, ft.data()), "sdfibm_collide");
     if (n_pairs == 0) return;
-    for (size_t i = 0; i < m_solids.size(); ++i)
-        m_solids[i].addForceAndTorque(vector(ft[6 * i], ft[6 * i + 1], ft[6 * i + 2]), vector(ft[6 * i + 3], ft[6 * i + 4], ft[6 * i + 5]));
+    m_solids.addLoads(ft.data());
 }
 
 void SolidCloud::evolve(scalar time, scalar dt) {   // :521-562
     m_time = time;
     if (m_solids.size() == 1) N_SUBITER = 1;   // sticky, like the reference's function-static
     const scalar dt_sub = dt / N_SUBITER;
-    for (int i = 0; i < N_SUBITER; ++i) {
-        for (Solid &solid : m_solids) solid.clearForceAndTorque();
-        for (Solid &solid : m_solids) solid.applyForcer(time);
-        for (Solid &solid : m_solids) solid.addMidFluidForceAndTorque();
+    for (int i = 0; i < N_SUBITER; ++i) {   // five batched passes over the state arrays per sub-iteration
+        m_solids.clearLoads();
+        m_solids.applyForcers(time);
+        m_solids.blendFluidLoads();
         this->addMidEnvironment();
         this->solidSolidInteract();
-        for (Solid &solid : m_solids) solid.move(time, dt_sub);   // `time` is not advanced across sub-iterations (Q8)
+        m_solids.advance(time, dt_sub);   // `time` is not advanced across sub-iterations (Q8)
     }
-    for (Solid &solid : m_solids) solid.storeOldForce();
+    m_solids.rememberLoads();
 }
 
 scalar SolidCloud::totalSolidVolume() const {   // :572-576
@@ -362,7 +348,7 @@ void SolidCloud::calcMeanField(std::vector<double> &out) {
     ensureDevice();
     const size_t n = m_solids.size();
     std::vector<sdfibm_solid_t> recs(n);
-    for (size_t i = 0; i < n; ++i) m_solids[i].toRecord(recs[i], sampler_index);
+    m_solids.pack(recs, {}, sampler_index);
     // this rank's raw sums; numerator and denominator are reduced across ranks BEFORE the division (:353-357): a rank whose
     // block does not touch the solid contributes zeros
     std::vector<double> nd(4 * n), den(n);
@@ -387,14 +373,10 @@ void SolidCloud::writeMeanField() {   // :303-313
 }
 
 std::ostream &operator<<(std::ostream &os, const SolidCloud &sc) {   // :595-614
-    if (sc.m_ON_TWOD) {
-        for (const Solid &solid : sc.m_solids) {
-            os << sc.m_time << ' ';
-            write2D(os, solid);
-            os << '\n';
-        }
-    } else {
-        for (const Solid &solid : sc.m_solids) os << sc.m_time << ' ' << solid << '\n';
+    for (size_t i = 0; i < sc.m_solids.size(); ++i) {
+        os << sc.m_time << ' ';
+        sc.m_solids.writeRow(os, i, sc.m_ON_TWOD);
+        os << '\n';
     }
     return os;
 }
@@ -403,7 +385,7 @@ void SolidCloud::saveRestart(const std::string &filename) {   // :616-665
     dictionary &solids = m_solidDict.subDict("solids");
     const auto names = solids.toc();
     for (size_t i = 0; i < names.size(); ++i) {
-        const Solid &s = m_solids[i];
+        const Solid s(m_solids, i);
         dictionary &solid = solids.subDict(names[i]);
         vector tmp = s.getCenter();
         if (m_ON_TWOD) tmp.z() = 0.0;

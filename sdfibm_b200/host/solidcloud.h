@@ -36,7 +36,7 @@ private:
     unsigned int m_timeStepCounter{0};
     unsigned int m_writeFrequency{1};
     scalar m_time{0};
-    std::vector<Solid> m_solids;
+    SolidStates m_solids;            // struct of arrays: one row per solid (solid.h)
     dictionary m_solidDict;
     scalar m_radiusB{-1.0};          // reference src/solidcloud.cpp:74-75: never computed, so the UGrid cell is 2*(-1)
     scalar m_collisionDelta{-2.0};   // UGrid cell size handed to the collision step (HEAD value: no pairs)
@@ -81,11 +81,10 @@ public:
     SolidCloud(const Foam::word &dictfile, Foam::volVectorField &U, scalar time = 0.0);
     ~SolidCloud();
 
-    inline void addSolid(Solid &&solid) { m_solids.emplace_back(solid); }
     void saveState();
     void initFromDictionary(const Foam::word &dictname);
     void saveRestart(const std::string &filename);
-    const Solid &operator[](label i) const { return m_solids[i]; }
+    Solid operator[](label i) const { return Solid(m_solids, (size_t)i); }   // a read-only view of row i
     label size() const { return (label)m_solids.size(); }
 
     void checkAlpha() const {}   // As <= 1 is applied inside the interact kernel (src/solidcloud.cpp:564-570)

@@ -23,7 +23,7 @@ class VofCloud {
     const Foam::fvMesh &m_mesh;
     bool m_ON_TWOD{false};
     EntityLibrary<IShape> m_libshape;
-    std::vector<Solid> m_solids, m_planes;            // tool_vof/solidcloud.h: two lists, planes applied after the solids
+    SolidStates m_solids, m_planes;                   // tool_vof/solidcloud.h: two lists, planes applied after the solids
     std::vector<sdfibm_shape_t> m_shapeTable;
     std::vector<sdfibm_sdf_op_t> m_sdfOps;
     std::vector<sdfibm_solid_t> m_records;
@@ -34,19 +34,17 @@ class VofCloud {
     static void check(int rc, const char *what) {
         if (rc) throw std::runtime_error(std::string(what) + ": " + sdfibm_last_error());
     }
-    void readBodies(const dictionary &block, std::vector<Solid> &into) {   // tool_vof/solidcloud.cpp:82-105 (and the planes loop)
+    void readBodies(const dictionary &block, SolidStates &into) {   // tool_vof/solidcloud.cpp:82-105 (and the planes loop)
         const auto names = block.toc();
         for (size_t i = 0; i < names.size(); ++i) {
             const dictionary &d = block.subDict(names[i]);
             const vector pos = d.lookup("pos");
             if (m_ON_TWOD && pos.z() != 0) throw std::runtime_error("Solid must has z=0 in 2D simulation, violated by solid # " + std::to_string(i));
-            Solid s((label)i, pos, quaternion::I);
-            s.setOrientation(d.lookupOrDefault("euler", vector::zero) * M_PI / 180.0);
+            const size_t row = into.add(pos, d.lookupOrDefault("euler", vector::zero) * M_PI / 180.0);
             const std::string shp_name = Foam::word(d.lookup("shp_name"));
             const auto shp = m_libshape.find(shp_name);
             if (shp == m_libshape.end()) throw std::runtime_error("Unrecognized shape name " + shp_name);
-            s.setShape(shp->second.get());
-            into.emplace_back(std::move(s));
+            into.shape[row] = shp->second.get();
         }
     }
 
@@ -69,10 +67,10 @@ public:
             index[sh] = (int)m_shapeTable.size();
             m_shapeTable.push_back(rec);
         }
-        for (const std::vector<Solid> *list : {&m_solids, &m_planes})
-            for (const Solid &s : *list) {
+        for (const SolidStates *list : {&m_solids, &m_planes})
+            for (size_t i = 0; i < list->size(); ++i) {
                 sdfibm_solid_t r;
-                s.toRecord(r, index.at(s.getShape()));
+                list->packOne(i, r, index.at(list->shape[i]));
                 m_records.push_back(r);
             }
     }
