@@ -287,6 +287,10 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(desc),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "distinct_solids": n_distinct},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:   # the product's CUDA library takes no part in this arm: only the mesh helper (libsdfibm_mesh.so) and the checker are mapped
+        line["product_cuda_library_mapped"] = "libsdfibm_b200.so" in open("/proc/self/maps").read()
+    except OSError:
+        pass
     if n_distinct < MIN_DISTINCT and n_distinct < len(case["solids"]):
         line["ratio"] = None
         line["ratio_reason"] = (f"only {n_distinct} distinct solids fit the {args.cpu_budget:.0f} s time box at {per_solid_s:.1f} s per solid: "

@@ -49,6 +49,22 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     return LIB
 
 
+MESH_LIB = os.path.join(HERE, "libsdfibm_mesh.so")
+
+
+def build_mesh(force: bool = False) -> str:
+    """The Foam-free mesh helpers alone (g++, no CUDA): what sdfibm_b200.mesh loads, so that building a mesh never maps the
+    CUDA library (the CPU reference arm of bench.py times the reference's code with only this helper loaded)."""
+    src = os.path.join(HERE, "csrc", "mesh_host.cpp")
+    hdr = os.path.join(ROOT, "include", "sdfibm_b200.h")
+    if force or not os.path.exists(MESH_LIB) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(MESH_LIB):
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-DSDFIBM_MESH_STANDALONE", "-o", MESH_LIB, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("mesh helper build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return MESH_LIB
+
+
 HOST_LIB = os.path.join(HERE, "libsdfibm_host.so")
 HOST_DIR = os.path.join(HERE, "host")
 HOST_SOURCES = [os.path.join(HOST_DIR, "solidcloud.cpp"), os.path.join(HOST_DIR, "capi_host.cpp")]
@@ -111,6 +127,7 @@ def build_reference_oracle(force: bool = False, reference: str = "/root/referenc
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_mesh(force="--force" in sys.argv))
     print(build_host(force="--force" in sys.argv))
     print(build_oracle(force="--force" in sys.argv))
     print(build_reference_oracle(force="--force" in sys.argv))

@@ -17,7 +17,15 @@
 #include <string>
 #include <vector>
 
-void sdfibm_set_error(const std::string &msg); // capi.cu
+#ifdef SDFIBM_MESH_STANDALONE
+// libsdfibm_mesh.so: the same helpers without the CUDA library around them (hosts that only need a mesh — the CPU reference arm of
+// bench.py, the oracle tests — never map libsdfibm_b200.so)
+static thread_local std::string g_mesh_error;
+void sdfibm_set_error(const std::string &msg) { g_mesh_error = msg; }
+extern "C" const char *sdfibm_mesh_last_error(void) { return g_mesh_error.c_str(); }
+#else
+void sdfibm_set_error(const std::string &msg); // sdfibm_cuda.cu
+#endif
 
 struct sdfibm_mesh_storage {
     int32_t n_cells = 0, n_points = 0, n_faces = 0, n_internal = 0;

@@ -21,6 +21,7 @@ def _built():
     from sdfibm_b200 import build
 
     build.build()
+    build.build_mesh()
     build.build_host()
     build.build_oracle()
 
