@@ -1083,17 +1083,23 @@ __global__ void k_replay_propagate(ReplayParams P) {
     }
 }
 
-// nearest cell centre to each flagged solid's centre, restricted to the cells that list the solid as
-// a candidate (sufficient: any member cell is within the binned bounding volume).
-__global__ void k_replay_seed(ReplayParams P, int pass) {
+// the solids that failed the certificate, as a compact list
+__global__ void k_replay_flagged(ReplayParams P, int *flagged, int *n_flagged) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n_solids && P.root_count[s] > 1) flagged[atomicAdd(n_flagged, 1)] = s;
+}
+
+// The reference seeds its flood fill at meshSearch::findNearestCell(centre) (src/solidcloud.cpp:363-365): the cell whose CENTRE is
+// nearest the solid's centre over the WHOLE mesh — also when the solid's centre lies outside the (sub)mesh, where the nearest
+// cell need not be a candidate of the solid at all (the fill then starts from the first member cell in index order,
+// src/cellenumerator.cpp:52-63).  So every cell is compared with every flagged solid: a full pass, on the rare path only.
+__global__ void k_replay_seed(ReplayParams P, const int *flagged, const int *n_flagged, int pass) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.m.n_cells) return;
     const D3 cc = ld3(P.m.cc, c);
-    const int b = (int)__ldg(P.m.tile_key + c);
-    const int b0 = P.bin_off[b], b1 = P.bin_off[b + 1];
-    for (int t = 0; t < (b1 - b0) + P.n_global; ++t) {
-        const int s = (t < b1 - b0) ? P.bin_list[b0 + t] : P.global_list[t - (b1 - b0)];
-        if (P.root_count[s] <= 1) continue;
+    const int nf = *n_flagged;
+    for (int t = 0; t < nf; ++t) {
+        const int s = flagged[t];
         const D3 x = {P.solids[s].pos[0], P.solids[s].pos[1], P.solids[s].pos[2]};
         const unsigned long long key = (unsigned long long)__double_as_longlong(magSqr3(cc - x));
         if (pass == 0) atomicMin(P.seed_key + s, key);
@@ -1101,7 +1107,7 @@ __global__ void k_replay_seed(ReplayParams P, int pass) {
     }
     if (pass == 1) {
         const int n = P.n_item[c];
-                for (int j = 0; j < n; ++j) {
+        for (int j = 0; j < n; ++j) {
             const int lab = P.labels[(long long)c * P.K + j];
             if (lab >= 0) atomicMin(P.min_label + (P.slots[(long long)j * P.m.n_cells + c] >> 3), lab);
         }

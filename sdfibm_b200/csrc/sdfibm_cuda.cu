@@ -822,7 +822,7 @@ struct sdfibm_context {
     DevBuf<int> t_flag, t_off, t_cells;      // touched-cell compaction
     DevBuf<double> t_vals;
     // replay
-    DevBuf<int> labels, seed_cell, min_label, chosen, changed;
+    DevBuf<int> labels, seed_cell, min_label, chosen, changed, flagged_list;
     DevBuf<unsigned long long> seed_key;
     DevBuf<unsigned char> excluded;
     bool last_used_replay = false;
@@ -950,8 +950,8 @@ static NcclApi *nccl_api() {
 
 // this rank has to run the step again (a capacity grew, or a solid needs the flood-fill replay): the other ranks must learn it,
 // because the all-reduce that follows is collective
-__global__ void k_retry_flag(const StepStatus *st, long long heavy_cap, double *flag) {
-    const bool again = st->bin_overflow || st->slot_overflow || st->heavy_total + st->heavy_gen > (unsigned long long)heavy_cap || st->n_flagged > 0;
+__global__ void k_retry_flag(const StepStatus *st, long long heavy_cap, int global_hint, double *flag) {
+    const bool again = (st->n_global > 0 && !global_hint) || st->bin_overflow || st->slot_overflow || st->heavy_total + st->heavy_gen > (unsigned long long)heavy_cap || st->n_flagged > 0;
     flag[0] = again ? 1.0 : 0.0;
 }
 
@@ -962,7 +962,7 @@ static int enqueue_comm_reduce(sdfibm_context *ctx, const double *partial, doubl
     cudaStream_t st = ctx->stream;
     CUDA_TRY(cudaEventRecord(ctx->ev_comm[0], st));
     if (with_flag) {
-        k_retry_flag<<<1, 1, 0, st>>>(ctx->status, (long long)ctx->heavy.n, ctx->retry_flag.p);
+        k_retry_flag<<<1, 1, 0, st>>>(ctx->status, (long long)ctx->heavy.n, ctx->n_global_hint, ctx->retry_flag.p);
         NCCL_TRY(a->GroupStart());
     }
     NCCL_TRY(a->AllReduce(partial, out, 6 * (size_t)n_solids, ncclDouble, ncclSum, ctx->comm, st));
@@ -1040,7 +1040,7 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->ft_internal.release(); ctx->scan_tmp.release(); ctx->t_flag.release(); ctx->t_off.release(); ctx->t_cells.release(); ctx->t_vals.release();
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release(); ctx->sU.release(); ctx->sOut.release(); ctx->sFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
-    ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release();
+    ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release(); ctx->flagged_list.release();
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < sdfibm_context::MAX_CHUNK; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_fin[i]) cudaEventDestroy(ctx->ev_fin[i]); }
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -1567,8 +1567,11 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
             ctx->launches += 8;
             if (!h_changed) break;
         }
-        k_replay_seed<<<g, 256, 0, st>>>(R, 0);
-        k_replay_seed<<<g, 256, 0, st>>>(R, 1);
+        CUDA_TRY(ctx->flagged_list.ensure((size_t)n_solids + 1));
+        CUDA_TRY(cudaMemsetAsync(ctx->flagged_list.p + n_solids, 0, sizeof(int), st));
+        k_replay_flagged<<<grid_for(n_solids, 256), 256, 0, st>>>(R, ctx->flagged_list.p, ctx->flagged_list.p + n_solids);
+        k_replay_seed<<<g, 256, 0, st>>>(R, ctx->flagged_list.p, ctx->flagged_list.p + n_solids, 0);
+        k_replay_seed<<<g, 256, 0, st>>>(R, ctx->flagged_list.p, ctx->flagged_list.p + n_solids, 1);
         k_replay_choose<<<grid_for(n_solids, 256), 256, 0, st>>>(R);
         k_replay_mark<<<g, 256, 0, st>>>(R);
         CUDA_TRY(cudaGetLastError());
@@ -1845,6 +1848,12 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             if (replay) ctx->last.n_flagged = (int)ctx->flagged_last;
         }
         bool again = false;
+        if (ctx->last.n_global > 0 && !ctx->n_global_hint && !replay) {
+            // the caller of sdfibm_interact_device_solids promised "no plane / tilted 2-D solid" and was wrong: the classify variant
+            // that was run never looked at the global list.  Run again with the variant that does.
+            ctx->n_global_hint = 1;
+            again = true;
+        }
         if (ctx->last.slot_overflow && !replay && ctx->K < 64) {
             // more solids touch one cell than there are slot records (dense packs against a wall plane): widen and run again
             const int K = std::min(64, std::max(ctx->last.slot_need, ctx->K + 1));

@@ -292,6 +292,49 @@ def test_parity_disconnected_component_replay():
     check_parity(case, o, ref, ctx, got)
 
 
+def test_replay_seed_is_the_globally_nearest_cell_also_for_centres_outside_the_mesh():
+    """the reference seeds the fill at findNearestCell(centre) over the WHOLE mesh (src/solidcloud.cpp:363-365).  Thin
+    rectangles whose centres lie outside this (sub)mesh: the nearest cell is then often not a candidate of the solid, and the
+    fill starts from the first member in index order (src/cellenumerator.cpp:52-63) — the kept component must be the oracle's."""
+    kept_fewer = 0
+    for pos0, e0, pos3, e3 in [((-2.2, 9.1, 0), 31, (12.0, 26.0, 0), 75), ((24.7, 12.3, 0), 143, (3.1, -1.2, 0), 62)]:
+        case = cases.case_disconnected()
+        S = case["solids"]
+        S[0]["pos"] = pos0; S[0]["quat"] = cases.quat_from_euler_xyz_deg((0, 0, e0))     # needle centres outside the mesh,
+        S[3]["pos"] = pos3; S[3]["quat"] = cases.quat_from_euler_xyz_deg((0, 0, e3))     # the needles reach in
+        o, ref, ctx, got = run_both(case)
+        assert ctx.last_stats()["flagged_solids"] >= 1
+        check_parity(case, o, ref, ctx, got)
+        from oracle.oracle_py import eval_points
+        for s_ in (0, 3):                                                              # the fill really dropped a component
+            inside, _ = eval_points(case["shapes"], S[s_], case["mesh"].points)
+            n_members = int(inside[case["mesh"].cp.reshape(-1, 8)].any(axis=1).sum())
+            kept_fewer += int(ref["list_off"][3 * s_ + 3] - ref["list_off"][3 * s_]) < n_members
+    assert kept_fewer >= 3
+    case = cases.case_disconnected()
+    o, ref, ctx, got = run_both(case)
+    assert ctx.last_stats()["flagged_solids"] >= 1
+    check_parity(case, o, ref, ctx, got)
+    assert ref["list_off"][-1] > 20
+
+
+def test_wrong_no_global_promise_is_caught_and_the_step_run_again():
+    """sdfibm_interact_device_solids(may_be_global = 0) with a plane present used to drop the plane silently."""
+    import torch
+
+    case = cases.case_c2(with_walls=True)        # 100 circles + 4 wall planes
+    o, ref, ctx, got = run_both(case)
+    dev = torch.device("cuda", 0)
+    nC, nS = case["mesh"].n_cells, len(case["solids"])
+    dS = torch.from_numpy(np.ascontiguousarray(case["solids"]).view(np.uint8)).to(dev)
+    dU = torch.from_numpy(case["U"]).to(dev)
+    f = [torch.zeros(k, dtype=torch.float64, device=dev) for k in (nC, 3 * nC, nC, nC, 6 * nS)]
+    ctx.interact_device_solids(dS.data_ptr(), nS, dU.data_ptr(), case["dt"], case["rhof"], *[x.data_ptr() for x in f], may_be_global=False)
+    assert np.array_equal(f[3].cpu().numpy(), got["Ct"]) and np.array_equal(f[0].cpu().numpy(), got["As"])
+    check_parity(case, o, ref, ctx, {"As": f[0].cpu().numpy(), "Fs": f[1].cpu().numpy().reshape(nC, 3), "Ts": f[2].cpu().numpy(),
+                                     "Ct": f[3].cpu().numpy(), "FT": f[4].cpu().numpy().reshape(nS, 6)})
+
+
 def test_empty_and_outside_solids():
     """Solids that touch no cell of this (sub)mesh yield empty lists and zero force (cellenumerator.cpp:52-65)."""
     case = cases.case_c4(n=32, n_solids=6, n_side=2)
