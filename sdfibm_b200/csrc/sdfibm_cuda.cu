@@ -535,7 +535,26 @@ __global__ void k_solid_prepare(PrepParams P) {
         // (tests/test_connectivity_proof_cpu.py holds the claim to the oracle's real flood fill).
         const sdfibm_shape_t &sp = sh.s;
         const bool ball = sp.tag == SDFIBM_SHAPE_SPHERE, disc = sp.tag == SDFIBM_SHAPE_CIRCLE && S.axis_is_z;
-        const bool ok = P.lattice_full && (ball || disc) && sp.com[0] == 0.0 && sp.com[1] == 0.0 && sp.com[2] == 0.0;
+        bool ok = P.lattice_full && (ball || disc) && sp.com[0] == 0.0 && sp.com[1] == 0.0 && sp.com[2] == 0.0;
+        // A well-resolved ellipsoid (ellipse) of ANY orientation, lying inside the lattice.  With f(v) = |A v|^2 (inside: f < 1) and
+        // M = A^T A, a lattice step of length h_i along axis i changes f by -+2 h_i (M v)_i + h_i^2 M_ii; some axis has
+        // |(M v)_i| >= |M v| / sqrt 3 >= sqrt(lambda_min) sqrt(f) / sqrt 3, so f strictly decreases — by a margin far above rounding —
+        // as long as sqrt(f) > rho := (sqrt 3 / 2) h lambda_max / sqrt(lambda_min) = (sqrt 3 / 2) h a_max / a_min^2.  Every inside vertex
+        // therefore walks, inside, into the small ellipsoid f <= rho^2; the lattice box around that one lies within f <= 3 rho^2 < 1,
+        // so its vertices are all inside and mutually connected.  Required with a 1.5x margin on rho, and the body two cells inside
+        // the mesh (the walk must not leave it).
+        const bool ellipsoid = sp.tag == SDFIBM_SHAPE_ELLIPSOID, ellipse = sp.tag == SDFIBM_SHAPE_ELLIPSE && S.axis_is_z && sp.com[0] == 0.0 && sp.com[1] == 0.0;
+        if (!ok && P.lattice_full && (ellipsoid || ellipse)) {
+            const int nd = ellipsoid ? 3 : 2;
+            double a_max = 0.0, a_min = 1e300, h = 0.0;
+            for (int d = 0; d < nd; ++d) { a_max = fmax(a_max, sp.p[d]); a_min = fmin(a_min, sp.p[d]); h = fmax(h, 2.0 * P.box_h[d]); }
+            const double rho = 1.5 * 0.8660254037844386 * h * a_max / (a_min * a_min);
+            ok = 3.0 * rho * rho < 0.9;
+            for (int d = 0; d < nd; ++d) {
+                const double marg = a_max + 4.0 * P.box_h[d] * (1.0 + 1e-5);
+                ok = ok && in.pos[d] - marg > P.mesh_lo[d] && in.pos[d] + marg < P.mesh_hi[d];
+            }
+        }
         S.conn_proven = ok ? 1 : 0;
     }
     if (sub == 0) P.out[s] = S;

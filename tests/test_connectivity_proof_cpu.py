@@ -77,3 +77,43 @@ def test_any_ball_clipped_or_not_has_a_face_connected_cell_set():
         outside += bool(np.any(pos[:nd] < lo[:nd]) or np.any(pos[:nd] > hi[:nd]))
         bad += not np.array_equal(np.sort(res["list_cells"]), members)
     assert bad == 0 and n_cases == 400 and nonempty > 300 and outside > 150 and small > 150
+
+
+def test_well_resolved_ellipsoids_of_any_orientation_have_a_face_connected_cell_set():
+    """The second rule of k_solid_prepare: rho = 1.5 (sqrt 3 / 2) h a_max / a_min^2 with 3 rho^2 < 0.9, body two cells inside the mesh."""
+    from sdfibm_b200.shapes import quat_from_euler_xyz_deg
+    bad = n_cases = tight = 0
+    for seed in range(250):
+        rng = np.random.RandomState(20_000 + seed)
+        two_d = bool(rng.randint(0, 2))
+        nd = 2 if two_d else 3
+        dx = np.array([1.0, float(rng.uniform(0.5, 1.0)), 1.0 if two_d else float(rng.uniform(0.5, 1.0))])
+        h = float(dx[:nd].max())
+        a_min = float(rng.uniform(2.2, 4.0))
+        # the largest a_max the rule admits for this a_min: 3 rho^2 < 0.9
+        a_cap = np.sqrt(0.3) * a_min * a_min / (1.5 * 0.8660254037844386 * h)
+        a_max = float(min(a_cap * rng.choice([0.999, 0.9, 0.7]), 3.0 * a_min))
+        if a_max < a_min:
+            continue
+        semi = [a_max, a_min, float(rng.uniform(a_min, a_max))]
+        rng.shuffle(semi)
+        need = [int(np.ceil(2 * (a_max + 2.0 * dx[d] * (1 + 1e-5)) / dx[d])) + 2 for d in range(nd)]
+        n = tuple(need) + ((1,) if two_d else ())
+        mesh = Mesh.hex_block(n, x0=(0.0, 0.0, -0.5 * dx[2] if two_d else 0.0), dx=tuple(dx))
+        lo, hi = mesh.bounds_min, mesh.bounds_max
+        marg = a_max + 2.0 * dx * (1 + 1e-5)
+        pos = np.array([rng.uniform(lo[d] + marg[d] * (1 + 1e-9), hi[d] - marg[d] * (1 + 1e-9)) if d < nd else 0.0 for d in range(3)])
+        if two_d:
+            shapes = np.array([make_shape("Ellipse", radiusa=semi[0], radiusb=semi[1])])
+            euler = (0.0, 0.0, float(rng.uniform(-180, 180)))
+        else:
+            shapes = np.array([make_shape("Ellipsoid", radiusa=semi[0], radiusb=semi[1], radiusc=semi[2])])
+            euler = tuple(rng.uniform(-180, 180, size=3))
+        S = make_solids(1); S[0]["pos"] = pos; S[0]["quat"] = quat_from_euler_xyz_deg(euler)
+        inside, _ = eval_points(shapes, S[0], mesh.points)
+        members = np.nonzero(inside[mesh.cp.reshape(-1, 8)].any(axis=1))[0]
+        res = Oracle(mesh, two_d).interact(shapes, S, np.zeros((mesh.n_cells, 3)), 1.0, 1.0, faithful=True)
+        n_cases += 1
+        tight += a_max > 0.95 * a_cap
+        bad += not np.array_equal(np.sort(res["list_cells"]), members)
+    assert bad == 0 and n_cases > 150 and tight > 20

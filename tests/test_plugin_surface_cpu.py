@@ -101,6 +101,11 @@ def test_reference_plugins_interact_on_the_gpu_like_the_builtin_ones(tmp_path):
             cloud.close()
     finally:
         hostapi.use_library(None)
-    for k in ("As", "Fs", "Ts", "Ct", "U"):
+    for k in ("As", "Fs", "Ts", "Ct"):
         assert np.array_equal(res[0][k], res[1][k]), k
-    assert res[0]["As"].max() == 1.0 and np.array_equal(res[0]["solids"], res[1]["solids"])
+    # the per-solid force sums are atomic accumulations (not bit-reproducible run to run): the solid states after evolve, and
+    # the velocities fixInternal writes from them, agree to rounding
+    assert np.abs(res[0]["U"] - res[1]["U"]).max() <= 1e-12
+    for k in ("pos", "quat", "vel", "omega"):
+        assert np.abs(res[0]["solids"][k] - res[1]["solids"][k]).max() <= 1e-12, k
+    assert res[0]["As"].max() == 1.0
