@@ -93,9 +93,9 @@ class ClockSampler:
 
 
 def measured_traffic(workload):
-    """DRAM bytes per launch of the interact kernels from the committed ncu capture (profiles/r01_traffic.json); None when the
-    capture is of another workload."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of the interact kernels from the committed ncu capture of the current kernels
+    (profiles/r02_traffic.json); None when the capture is of another workload."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         d = json.load(open(p))
         if d.get("workload", "").lower() == workload:
