@@ -155,6 +155,48 @@ def case_skewed_2d(n=60, seed=3):
     return _case("skewed2d", mesh, True, shapes, S, U, 1e-3)
 
 
+def case_taylor_couette(n=50):
+    """BASELINE config 3, the reference's own set-up: examples/taylor_couette — the five-block O-grid of its blockMeshDict
+    (sdfibm_b200.meshgen.ogrid_taylor_couette: curved, non-orthogonal hexahedra, three blocks meeting at the core corners) with the
+    solidDict's one Circle r = 0.3 at the origin (:24-29,57-65), free to spin about z; a second, offset tailed shape crosses the
+    block junctions so that the unstructured corners are exercised too."""
+    from .meshgen import ogrid_taylor_couette
+
+    mesh = ogrid_taylor_couette(n)
+    shapes = np.array([make_shape("Circle", radius=0.3), make_shape("Circle_Tail", radius=0.12, ratio=1.6, thickness=0.05)])
+    S = make_solids(2)
+    S[0]["pos"] = (0.0, 0.0, 0.0)
+    S[0]["omega"] = (0, 0, 6.28)
+    S[1]["pos"] = (0.33, -0.36, 0.0)
+    S[1]["quat"] = quat_from_euler_xyz_deg((0, 0, 35))
+    S[1]["shape"] = 1
+    S[1]["vel"] = (-0.2, 0.15, 0)
+    S[1]["omega"] = (0, 0, -2.0)
+    U = taylor_green(mesh.cc, 2.0)
+    return _case("taylor_couette", mesh, True, shapes, S, U, 1e-3)
+
+
+def case_sedimentation_refined(n=40, n_circles=9, seed=4):
+    """BASELINE config 2 on the mesh refineMesh leaves behind (examples/sedimentation/system/refineMeshDict + topoSetDict): a
+    one-cell-thick block whose central band is split 2 x 2 in the plane, hanging nodes kept — the coarse cells along the band
+    have 10 vertices / 7 faces.  Circles of the example's radius-to-cell ratio sit inside the band, across its edge and outside."""
+    from .meshgen import refine_2d
+
+    L = 8.0
+    h = L / n
+    mesh = refine_2d(n, n, (-4.0, 0.0), (h, h), (-2.0, 2.0, 2.0, 6.0))
+    shapes = np.array([make_shape("Circle", radius=0.45)])
+    rng = np.random.RandomState(seed)
+    S = make_solids(n_circles)
+    k = int(math.ceil(math.sqrt(n_circles)))
+    for i in range(n_circles):
+        S[i]["pos"] = (-3.0 + 6.0 * ((i % k) + 0.5) / k + 0.1 * rng.randn(), 1.0 + 6.0 * ((i // k) + 0.5) / k + 0.1 * rng.randn(), 0.0)
+        S[i]["vel"] = (0.05 * rng.randn(), -0.3, 0.0)
+        S[i]["omega"] = (0, 0, rng.randn())
+    U = taylor_green(mesh.cc, 4.0)
+    return _case("sedimentation_refined", mesh, True, shapes, S, U, 2e-3)
+
+
 # ---- random 3-D packs ---------------------------------------------------------------------------
 def random_quaternions(rng, n):
     q = rng.standard_normal((n, 4))

@@ -17,6 +17,15 @@
 #pragma once
 
 #define TPB 128
+#ifndef CLS4_NT
+#define CLS4_NT 64      // k_classify4: threads per CTA (x 4 positions)
+#endif
+#ifndef CLS4_PREFETCH
+#define CLS4_PREFETCH 1
+#endif
+#ifndef CLS4_MINB
+#define CLS4_MINB 16
+#endif
 #define SLOT_HEAVY 4
 
 // ------------------------------------------------------------------------------------------------
@@ -377,6 +386,171 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
             }
             pos += step;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_classify4: the plain classification (no global list, no corner refinement — the C4 variant), FOUR consecutive positions per
+// thread.  The candidate records of a tile are fetched once per four cells (the next record is requested while the current one
+// is tested), the four tests are independent instruction streams, slot 0 of the four cells is held in registers and leaves as
+// one 16-byte store (every sector of slots[0][.] written in full: no partial-sector fills), n_item as one 4-byte store, and the
+// scan / queue append run once per four cells.  Queue order is unchanged (position order).  A thread whose four positions do
+// not share one tile (tile runs need not be multiples of four on general meshes) walks them one by one.  Measured at C4:
+// 0.225 -> 0.18 ms; with the refinement / global-list code in the loop the register count halves the occupancy and the
+// one-position kernel stays faster, so those variants keep it.
+// ------------------------------------------------------------------------------------------------
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
+    const DevMesh &m = P.m;
+    const unsigned FULL = 0xffffffffu;
+    const long long nC = m.n_cells;
+    const int lane = threadIdx.x & 31;
+    const int c0 = P.cls_begin + (blockIdx.x * NT + threadIdx.x) * 4;
+    const bool vec = ((P.cls_begin | (int)(nC & 3)) & 3) == 0;   // 16-byte accesses are aligned (uniform over the grid)
+    const bool full = c0 + 3 < P.cls_end;
+    int n_item[4] = {0, 0, 0, 0}, n_heavy[4] = {0, 0, 0, 0}, slot0[4] = {0, 0, 0, 0};
+    int n_over[4] = {0, 0, 0, 0};
+    const float4 *E = reinterpret_cast<const float4 *>(P.bin_entries);
+    if (c0 < P.cls_end) {
+        float4 p[4], hb[4];
+        unsigned t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = min(c0 + q, P.cls_end - 1);
+            p[q] = __ldg(m.cc32 + c);
+            hb[q] = m.box_uniform ? m.box_const : __ldg(m.cell_box + c);
+        }
+        if (vec && full) {
+            const uint4 tk = __ldg(reinterpret_cast<const uint4 *>(m.tile_key + c0));
+            t[0] = tk.x; t[1] = tk.y; t[2] = tk.z; t[3] = tk.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] = __ldg(m.tile_key + min(c0 + q, P.cls_end - 1));
+        }
+        // one pre-classified candidate of cell q -> slot record (slot 0 stays in a register)
+        auto emit = [&](int q, int s, int qc) {
+            if (qc == 0) return;
+            if (n_item[q] < P.K) {
+                const int rec = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
+                if (n_item[q] == 0) slot0[q] = rec;
+                else P.slots[(long long)n_item[q] * nC + (c0 + q)] = rec;
+                n_heavy[q] += (qc == 2);
+                ++n_item[q];
+            } else ++n_over[q];
+        };
+        auto test32 = [&](int q, float4 e0, float4 e1) {     // see k_classify
+            const bool k3 = __float_as_int(e1.z) == KIND_3D;
+            const float ax = fabsf(p[q].x - e0.x), ay = fabsf(p[q].y - e0.y), az = k3 ? fabsf(p[q].z - e0.z) : 0.f;
+            const float hz = k3 ? hb[q].z : 0.f;
+            const float fx = ax + hb[q].x, fy = ay + hb[q].y, fz = az + hz;
+            float nx = ax - hb[q].x, ny = ay - hb[q].y, nz = az - hz;
+            if (hb[q].w == 0.f) { nx = fmaxf(nx, 0.f); ny = fmaxf(ny, 0.f); nz = fmaxf(nz, 0.f); }
+            const float N2 = nx * nx + ny * ny + nz * nz, F2 = fx * fx + fy * fy + fz * fz;
+            const float ro = e0.w, ri = e1.x;
+            return (N2 > ro * ro) ? 0 : ((ri > 0.f && F2 < ri * ri) ? 1 : 2);
+        };
+        if (t[1] == t[0] && t[2] == t[0] && t[3] == t[0]) {
+            int bi = __ldg(P.bin_off + t[0]);
+            const int be = __ldg(P.bin_off + t[0] + 1);
+#if CLS4_PREFETCH
+            float4 e0 = {0.f, 0.f, 0.f, 0.f}, e1 = e0;
+            if (bi < be) { e0 = __ldg(E + 2 * (long long)bi); e1 = __ldg(E + 2 * (long long)bi + 1); }
+#endif
+            for (; bi < be; ++bi) {
+#if CLS4_PREFETCH
+                float4 f0 = e0, f1 = e1;
+                if (bi + 1 < be) { f0 = __ldg(E + 2 * (long long)bi + 2); f1 = __ldg(E + 2 * (long long)bi + 3); }   // next record in flight
+#else
+                const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
+#endif
+                const int s = __float_as_int(e1.y);
+                int qc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) qc[q] = test32(q, e0, e1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q]);
+#if CLS4_PREFETCH
+                e0 = f0; e1 = f1;
+#endif
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c0 + q >= P.cls_end) continue;
+                int bi = __ldg(P.bin_off + t[q]);
+                const int be = __ldg(P.bin_off + t[q] + 1);
+                for (; bi < be; ++bi) {
+                    const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
+                    emit(q, __float_as_int(e1.y), test32(q, e0, e1));
+                }
+            }
+        }
+        if (vec && full) *reinterpret_cast<uchar4 *>(P.n_item + c0) = make_uchar4((unsigned char)n_item[0], (unsigned char)n_item[1], (unsigned char)n_item[2], (unsigned char)n_item[3]);
+        else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (c0 + q < P.cls_end) P.n_item[c0 + q] = (unsigned char)n_item[q];
+        }
+        if (n_over[0] | n_over[1] | n_over[2] | n_over[3]) {   // the host widens the records and runs again
+            P.status->slot_overflow = 1;
+            atomicMax(&P.status->slot_need, max(max(n_item[0] + n_over[0], n_item[1] + n_over[1]), max(n_item[2] + n_over[2], n_item[3] + n_over[3])));
+        }
+    }
+    // ---- block-aggregated append to the queue (see k_classify): hex count in the low, general-cell count in the high 16 bits
+    int mine = 0;
+    bool gen[4] = {false, false, false, false};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        gen[q] = m.mixed && n_heavy[q] > 0 && __ldg(m.hex_topo + 3 * (long long)(c0 + q)) == HEX_NONE;
+        mine += gen[q] ? (n_heavy[q] << 16) : n_heavy[q];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    __shared__ int s_wtot[NT / 32];
+    __shared__ unsigned long long s_base, s_base_gen;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) { const int tw = s_wtot[w]; s_wtot[w] = tot; tot += tw; }
+        const int tot_hex = tot & 0xffff, tot_gen = tot >> 16;
+        s_base = tot_hex ? atomicAdd(P.heavy_count, (unsigned long long)tot_hex) : 0ull;
+        s_base_gen = tot_gen ? atomicAdd(P.heavy_gen, (unsigned long long)tot_gen) : 0ull;
+    }
+    __syncthreads();
+    if (c0 >= P.cls_end) return;
+    if (mine != 0) {
+        const int excl = s_wtot[warp] + incl - mine;
+        long long pos_hex = (long long)s_base + (excl & 0xffff);
+        long long pos_gen = P.heavy_cap - 1 - ((long long)s_base_gen + (excl >> 16));   // back queue: item i lives at heavy_cap - 1 - i
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (n_heavy[q] == 0) continue;
+            const int c = c0 + q;
+            for (int j = 0; j < n_item[q]; ++j) {
+                const int e = (j == 0) ? slot0[q] : P.slots[(long long)j * nC + c];
+                if (e & SLOT_HEAVY) {
+                    const long long pos = gen[q] ? pos_gen : pos_hex;
+                    if (pos >= 0 && pos < P.heavy_cap) {
+                        P.heavy[pos] = make_int2(c, e >> 3);
+                        const int rec = ((int)pos << 3) | SLOT_HEAVY;     // the slot now points at its queue item
+                        if (j == 0) slot0[q] = rec;
+                        else P.slots[(long long)j * nC + c] = rec;
+                    }
+                    if (gen[q]) --pos_gen; else ++pos_hex;
+                }
+            }
+        }
+    }
+    if (vec && full) *reinterpret_cast<int4 *>(P.slots + c0) = make_int4(slot0[0], slot0[1], slot0[2], slot0[3]);
+    else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (c0 + q < P.cls_end && n_item[q] > 0) P.slots[c0 + q] = slot0[q];
     }
 }
 
@@ -905,6 +1079,158 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
         }
     }
     if (live) store_cell(P, oc, as, fs, ts, ct);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_final2: the same pass, TWO consecutive positions per thread: index / record / coordinate loads as 16-byte accesses, twice the
+// loads in flight per warp, and one warp butterfly per 64 cells — two pairs of the same solid (the rule inside a tile) are added
+// before they enter it.  Per-cell sums keep the reference's += order (ascending solid id within the cell).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_accumulate2(bool have, int s, int n1, int n2, int n3, const double v[6], double *force_torque,
+                                                 unsigned *pair_counts) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned pending = __ballot_sync(FULL, have);
+    const int lane = threadIdx.x & 31;
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int s0 = __shfl_sync(FULL, s, leader);
+        const bool mine = have && (s == s0);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        double w[8];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = mine ? v[k] : 0.0;
+        w[6] = mine ? (double)n1 : 0.0;
+        w[7] = mine ? (double)n2 : 0.0;
+        const unsigned c3 = __reduce_add_sync(FULL, mine ? (unsigned)n3 : 0u);
+        double a[4], b[2], c;
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = (h16 ? w[i + 4] : w[i]) + __shfl_xor_sync(FULL, h16 ? w[i] : w[i + 4], 16);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(FULL, h8 ? a[i] : a[i + 2], 8);
+        c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(FULL, h4 ? b[0] : b[1], 4);
+        c += __shfl_xor_sync(FULL, c, 2);
+        c += __shfl_xor_sync(FULL, c, 1);
+        if ((lane & 3) == 0) {
+            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if (idx < 6) atomicAdd(force_torque + 6 * (long long)s0 + idx, c);
+            else if (c != 0.0) atomicAdd(pair_counts + 3 * (long long)s0 + (idx - 6), (unsigned)c);
+        }
+        if (lane == leader && c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
+        pending &= ~grp;
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_final2(InteractParams P) {
+    const DevMesh &m = P.m;
+    const unsigned FULL = 0xffffffffu;
+    const long long nC = m.n_cells;
+    const int c0 = P.c_begin + (blockIdx.x * 128 + threadIdx.x) * 2;
+    const bool live0 = c0 < P.c_end, live1 = c0 + 1 < P.c_end;
+    const bool vec = live1 && (((P.c_begin | (int)(nC & 1)) & 1) == 0);     // 8 / 16-byte accesses on position pairs are aligned
+    int oc[2] = {0, 0}, n[2] = {0, 0}, e0[2] = {0, 0};
+    if (vec) {
+        const int2 o2 = __ldg(reinterpret_cast<const int2 *>(m.orig + c0));
+        const unsigned short n2 = *reinterpret_cast<const unsigned short *>(P.n_item + c0);
+        const int2 s2 = *reinterpret_cast<const int2 *>(P.slots + c0);
+        oc[0] = o2.x; oc[1] = o2.y; n[0] = n2 & 0xff; n[1] = n2 >> 8; e0[0] = s2.x; e0[1] = s2.y;
+    } else {
+        if (live0) { oc[0] = __ldg(m.orig + c0); n[0] = P.n_item[c0]; e0[0] = P.slots[c0]; }
+        if (live1) { oc[1] = __ldg(m.orig + c0 + 1); n[1] = P.n_item[c0 + 1]; e0[1] = P.slots[c0 + 1]; }
+    }
+    int nmax = max(n[0], n[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+    const bool adj = vec && oc[1] == oc[0] + 1 && (oc[0] & 1) == 0;       // the two cells are neighbours in the caller's numbering too
+
+    double as[2] = {0.0, 0.0}, ts[2] = {0.0, 0.0}, ct[2] = {0.0, 0.0};
+    D3 fs[2] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    if (nmax > 0) {
+        const double dtINV = __ldg(P.scal);
+        D3 cc[2] = {{0, 0, 0}, {0, 0, 0}}, uf[2] = {{0, 0, 0}, {0, 0, 0}};
+        double vol[2] = {1.0, 1.0};
+        if (n[0] | n[1]) {
+            if (vec) {
+                const double2 *g = reinterpret_cast<const double2 *>(m.cc + 3 * (long long)c0);
+                const double2 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2);
+                cc[0] = {a.x, a.y, b.x}; cc[1] = {b.y, c.x, c.y};
+                const double2 v2 = __ldg(reinterpret_cast<const double2 *>(m.V + c0));
+                vol[0] = v2.x; vol[1] = v2.y;
+            } else {
+                if (n[0]) { cc[0] = ld3(m.cc, c0); vol[0] = __ldg(m.V + c0); }
+                if (n[1]) { cc[1] = ld3(m.cc, c0 + 1); vol[1] = __ldg(m.V + c0 + 1); }
+            }
+            if (adj) {
+                const double2 *g = reinterpret_cast<const double2 *>(P.U + 3 * (long long)oc[0]);
+                const double2 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2);
+                uf[0] = {a.x, a.y, b.x}; uf[1] = {b.y, c.x, c.y};
+            } else {
+                if (n[0]) uf[0] = ld3(P.U, oc[0]);
+                if (n[1]) uf[1] = ld3(P.U, oc[1]);
+            }
+        }
+        for (int j = 0; j < nmax; ++j) {
+            bool have[2] = {false, false};
+            int s[2] = {-1, -1}, type[2] = {0, 0};
+            double contrib[2][6];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) contrib[q][k] = 0.0;
+                if (j < n[q]) {
+                    const int c = c0 + q;
+                    const int e = (j == 0) ? e0[q] : P.slots[(long long)j * nC + c];
+                    s[q] = e >> 3;
+                    type[q] = e & 3;
+                    double v = 0.0;
+                    if (e & SLOT_HEAVY) {                                           // the slot points at its queue item
+                        const double2 r = P.heavy_res[e >> 3];
+                        const int bits = (int)__double_as_longlong(r.y);
+                        type[q] = bits & 3;
+                        s[q] = bits >> 2;
+                        v = r.x;
+                        P.slots[(long long)j * nC + c] = (s[q] << 3) | SLOT_HEAVY | type[q];   // final record
+                    }
+                    const bool skip = P.excluded && P.excluded[(long long)c * P.K + j]; // replay: outside the seed's component
+                    if (type[q] != 0 && !skip) {
+                        const double alpha = (type[q] == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol[q];   // solidcloud.cpp:408-410
+                        D3 fi;
+                        pair_terms(P.solids[s[q]], cc[q], uf[q], vol[q], alpha, dtINV, fi, contrib[q]);   // :384-390,411-421
+                        as[q] += alpha;
+                        fs[q] = fs[q] + fi;
+                        ts[q] += alpha;
+                        ct[q] = (type[q] == SDFIBM_CELL_ALL_INSIDE) ? (double)(s[q] + 4) : (double)type[q];   // :376-382, last writer wins
+                        have[q] = true;
+                    }
+                }
+            }
+            if (__any_sync(FULL, have[0] || have[1])) {
+                // pair A: cell 0's, or cell 1's when cell 0 has none, or both when they belong to the same solid; pair B: the rest
+                const bool both = have[0] && have[1], same = both && s[0] == s[1];
+                const bool haveA = have[0] || have[1], haveB = both && !same;
+                const int qa = have[0] ? 0 : 1;
+                double vA[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) vA[k] = (qa == 0 ? contrib[0][k] : contrib[1][k]) + (same ? contrib[1][k] : 0.0);
+                const int tA = qa == 0 ? type[0] : type[1], tB = type[1];
+                warp_accumulate2(haveA, qa == 0 ? s[0] : s[1], (tA == 1) + (same && tB == 1), (tA == 2) + (same && tB == 2), (tA == 3) + (same && tB == 3),
+                                 vA, P.force_torque, P.pair_counts);
+                if (__any_sync(FULL, haveB)) warp_accumulate2(haveB, s[1], tB == 1, tB == 2, tB == 3, contrib[1], P.force_torque, P.pair_counts);
+            }
+        }
+    }
+    if (adj) {
+        const double a0 = (as[0] < 1.0) ? as[0] : 1.0, a1 = (as[1] < 1.0) ? as[1] : 1.0;   // checkAlpha, :564-570
+        *reinterpret_cast<double2 *>(P.As + oc[0]) = make_double2(a0, a1);
+        double2 *f = reinterpret_cast<double2 *>(P.Fs + 3 * (long long)oc[0]);
+        f[0] = make_double2(fs[0].x, fs[0].y); f[1] = make_double2(fs[0].z, fs[1].x); f[2] = make_double2(fs[1].y, fs[1].z);
+        *reinterpret_cast<double2 *>(P.Ts + oc[0]) = make_double2(ts[0], ts[1]);
+        *reinterpret_cast<double2 *>(P.Ct + oc[0]) = make_double2(ct[0], ct[1]);
+    } else {
+        if (live0) store_cell(P, oc[0], as[0], fs[0], ts[0], ct[0]);
+        if (live1) store_cell(P, oc[1], as[1], fs[1], ts[1], ct[1]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

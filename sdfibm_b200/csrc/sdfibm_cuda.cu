@@ -614,6 +614,9 @@ __device__ __forceinline__ void bin_insertion_sort(int *lst, int beg, int end) {
     }
 }
 
+#ifndef FINAL2_CTAS
+#define FINAL2_CTAS 4
+#endif
 #ifndef FINAL_CTAS
 #define FINAL_CTAS 4
 #endif
@@ -861,6 +864,8 @@ struct sdfibm_context {
     GraphKey graph_key = {0};
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
+    bool final2 = false;                 // k_final2 (two positions per thread); SDFIBM_FINAL2=1
+    bool classify4 = true;               // k_classify4 (four positions per thread); SDFIBM_CLASSIFY4=0: the one-position kernel
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
     const sdfibm_solid_t *ext_solids = nullptr;   // device-resident solid records supplied by the caller for the current call
@@ -1023,6 +1028,8 @@ int sdfibm_create(int device, sdfibm_context **out) {
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev_comm[i]));
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
+    if (const char *e = getenv("SDFIBM_CLASSIFY4")) ctx->classify4 = atoi(e) != 0;
+    if (const char *e = getenv("SDFIBM_FINAL2")) ctx->final2 = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_BOX")) ctx->allow_box = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_ALLOW_ORDER_FREE")) ctx->allow_order_free = atoi(e) != 0;
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
@@ -1670,6 +1677,10 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         const int grid = grid_for(p1 - p0, 256);
         // variants: with / without the global-list merge (planes, tilted 2-D solids) and the fp32 corner refinement (shape tables
         // holding ellipsoids, boxes, ellipses, rectangles); the plain one runs at 32 registers / full occupancy
+        if (ctx->classify4 && !ctx->n_global_hint && !ctx->shapes_refinable) {   // the plain variant: four consecutive positions per thread
+            k_classify4<CLS4_NT, CLS4_MINB><<<grid_for(p1 - p0, 4 * CLS4_NT), CLS4_NT, 0, st>>>(I);
+            return;
+        }
         if (ctx->n_global_hint) k_classify<256, 4, true, true><<<grid, 256, 0, st>>>(I);
         else if (ctx->shapes_refinable) k_classify<256, 6, false, true><<<grid, 256, 0, st>>>(I);
         else k_classify<256, 8, false, false><<<grid, 256, 0, st>>>(I);
@@ -1733,7 +1744,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
             if (p1 > p0) {
                 I.c_begin = (int)p0; I.c_end = (int)p1;
                 CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
-                k_final<FINAL_CTAS><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
+                if (ctx->final2) k_final2<FINAL2_CTAS><<<grid_for(p1 - p0, 256), 128, 0, st>>>(I); else k_final<FINAL_CTAS><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
             }
             CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
             for (int j = 0; j < NCH; ++j) {
@@ -1751,7 +1762,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         ctx->launches += ctx->n_chunk - 3;
     } else {
         I.c_begin = 0; I.c_end = nC;
-        k_final<FINAL_CTAS><<<grid_for(nC, 256), 256, 0, st>>>(I);
+        if (ctx->final2) k_final2<FINAL2_CTAS><<<grid_for(nC, 256), 128, 0, st>>>(I); else k_final<FINAL_CTAS><<<grid_for(nC, 256), 256, 0, st>>>(I);
     }
     CUDA_TRY(rec(ctx->ev[4]));
     ctx->launches += 3;

@@ -20,6 +20,7 @@ CASES = {
     "c2": cases.case_c2,
     "c2_walls": lambda: cases.case_c2(with_walls=True),
     "skewed2d": cases.case_skewed_2d,
+    "taylor_couette": cases.case_taylor_couette,       # the reference's five-block O-grid (examples/taylor_couette/system/blockMeshDict)
     "c4_small": lambda: cases.case_c4(n=48, n_solids=50, n_side=4),
     "c5_small": lambda: cases.case_c5_block(0, 1, n=32, n_solids=24, n_side=3),
 }
@@ -102,17 +103,9 @@ def test_gpu_against_compiled_reference(name):
     assert np.array_equal(ctx.fix_internal(S2, U2), ref_py.ref_fix_internal(case["mesh"], S2, ref["Ct"], U2))
 
 
-@needs_ref
-@pytest.mark.gpu
-def test_gpu_against_compiled_reference_on_a_mesh_of_mixed_cell_types():
-    """SURVEY Q3, against the reference's own compiled CellEnumerator (no oracle variant in between): on a mesh of hexahedra, prisms
-    and 7-faced polyhedra the library is refused by default; with the order-free rule accepted it returns the SAME member cells
-    as the reference for every solid, and the two differ only where the quirk bites — cells whose type the reference takes from
-    the vertex count of the neighbour that discovered them."""
+def _mixed_cells_case():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from mixed_mesh import mixed_hex_prism_mesh
-    from sdfibm_b200.capi import SdfibmError
-    from sdfibm_b200.context import Context
     from sdfibm_b200.shapes import make_shape, make_solids, quat_from_euler_xyz_deg
 
     mesh = mixed_hex_prism_mesh(14)
@@ -126,14 +119,47 @@ def test_gpu_against_compiled_reference_on_a_mesh_of_mixed_cell_types():
         S[i]["quat"] = quat_from_euler_xyz_deg(e)
     S["vel"] = 0.1 * rng.standard_normal((6, 3))
     U = rng.standard_normal((mesh.n_cells, 3))
-    case = dict(name="mixed_cells", mesh=mesh, two_d=False, shapes=shapes, solids=S, U=U, dt=1e-3, rhof=1.3)
+    return dict(name="mixed_cells", mesh=mesh, two_d=False, shapes=shapes, solids=S, U=U, dt=1e-3, rhof=1.3)
+
+
+MIXED = {
+    "hex_prism_polyhedron": _mixed_cells_case,
+    # what refineMesh leaves behind (examples/sedimentation/system/refineMeshDict): hanging nodes, 10-vertex / 7-face cells
+    "hanging_nodes": cases.case_sedimentation_refined,
+}
+
+
+@needs_ref
+def test_oracle_reproduces_the_reference_on_the_hanging_node_mesh(name="hanging_nodes"):
+    """CPU side: the oracle (which follows the flood fill's visiting order) against the reference's compiled
+    CellEnumerator on the refined mesh the GPU test below uses (the hex / prism / polyhedron mesh: test_oracle_vs_reference.py)."""
+    case = MIXED[name]()
+    ref = _reference(case)
+    mine = Oracle(case["mesh"], case["two_d"]).interact(case["shapes"], case["solids"], case["U"], case["dt"], case["rhof"])
+    _check(case, mine, mine["list_off"], mine["list_cells"], ref, 1e-14, 1e-12)
+    assert len(set(np.diff(case["mesh"].cp_off))) > 1 and ref["pairs"] > 0
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(MIXED))
+def test_gpu_against_compiled_reference_on_a_mesh_of_mixed_cell_types(name):
+    """SURVEY Q3, against the reference's own compiled CellEnumerator (no oracle variant in between): on a mesh whose cells differ
+    in vertex count (hexahedra / prisms / 7-faced polyhedra; hanging-node refinement) the library is refused by default; with the
+    order-free rule accepted it returns the SAME member cells as the reference for every solid, and the two differ only where the
+    quirk bites — cells whose type the reference takes from the vertex count of the neighbour that discovered them."""
+    from sdfibm_b200.capi import SdfibmError
+    from sdfibm_b200.context import Context
+
+    case = MIXED[name]()
+    mesh, shapes, S, U = case["mesh"], case["shapes"], case["solids"], case["U"]
     ref = _reference(case)
     with pytest.raises(SdfibmError, match="visiting order"):
-        Context(0, cell_slots=8).set_mesh(mesh, False)
+        Context(0, cell_slots=8).set_mesh(mesh, case["two_d"])
     ctx = Context(0, cell_slots=8, allow_order_free=True)
-    ctx.set_mesh(mesh, False)
+    ctx.set_mesh(mesh, case["two_d"])
     ctx.set_shapes(shapes)
-    got = ctx.interact(S, U, 1e-3, 1.3)
+    got = ctx.interact(S, U, case["dt"], case["rhof"])
     off, cells = ctx.candidate_lists()
     nv = np.diff(mesh.cp_off)
     n_diff = 0
@@ -149,7 +175,7 @@ def test_gpu_against_compiled_reference_on_a_mesh_of_mixed_cell_types():
             assert (nv[nb] != nv[c]).any(), c
         assert np.array_equal(np.setdiff1d(mine[1], moved), np.setdiff1d(theirs[1], moved))
         assert np.array_equal(np.setdiff1d(mine[2], moved), np.setdiff1d(theirs[2], moved))
-    assert 0 < n_diff < 0.05 * ref["list_off"][-1]
+    assert n_diff < 0.05 * ref["list_off"][-1] and (n_diff > 0 or name != "hex_prism_polyhedron")
     same = np.ones(mesh.n_cells, bool)
     same[np.nonzero(got["Ct"] != ref["Ct"])[0]] = False
     from test_gpu_parity import assert_fields_close
