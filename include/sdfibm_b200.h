@@ -263,6 +263,9 @@ int sdfibm_last_timings(sdfibm_context *ctx, double ms[6]);
 /* host wall time of the last interact, in microseconds: [0] staging the solid states, [1] enqueue / graph launch,
  * [2] waiting for the GPU, [3] the whole call */
 int sdfibm_last_host_timings(sdfibm_context *ctx, double us[4]);
+/* device time (CUDA events on the context stream, ms) of the kernels of [0] the last sdfibm_fix_internal_device and [1] the last
+ * sdfibm_collide (key build, sort, pair enumeration, narrow phase; the pair-count read-back in the middle included) */
+int sdfibm_last_aux_timings(sdfibm_context *ctx, double ms[2]);
 
 /* ---- collision step (solidcloud.cpp:477-519, libcollision/) -------------------------
  * delta = UGrid cell size.  HEAD passes 2*m_radiusB = -2 (solidcloud.cpp:74-75,245) which yields

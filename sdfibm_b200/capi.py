@@ -94,6 +94,7 @@ SYMBOLS = {
     "sdfibm_free_pinned": (C.c_int, [_VP]),
     "sdfibm_last_timings": (C.c_int, [_VP, c_double_p]),
     "sdfibm_last_host_timings": (C.c_int, [_VP, c_double_p]),
+    "sdfibm_last_aux_timings": (C.c_int, [_VP, c_double_p]),
     "sdfibm_collide": (C.c_int, [_VP, _VP, C.c_int, C.c_double, _VP, C.c_int64, c_int64_p, _VP]),
     "sdfibm_stream": (C.c_int, [_VP, C.POINTER(_VP)]),
     "sdfibm_synchronize": (C.c_int, [_VP]),

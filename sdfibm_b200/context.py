@@ -197,6 +197,11 @@ class Context:
         capi.check(self._lib.sdfibm_last_host_timings(self._h, t))
         return {"stage_us": t[0], "enqueue_us": t[1], "wait_us": t[2], "call_us": t[3]}
 
+    def last_aux_timings(self):
+        t = (C.c_double * 2)()
+        capi.check(self._lib.sdfibm_last_aux_timings(self._h, t))
+        return {"fix_internal_ms": t[0], "collide_ms": t[1]}
+
     def last_timings(self):
         t = (C.c_double * 6)()
         capi.check(self._lib.sdfibm_last_timings(self._h, t))

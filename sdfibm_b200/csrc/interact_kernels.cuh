@@ -21,7 +21,7 @@
 #define CLS4_NT 64      // k_classify4: threads per CTA (x 4 positions)
 #endif
 #ifndef CLS4_PREFETCH
-#define CLS4_PREFETCH 1
+#define CLS4_PREFETCH 0   // requesting the next candidate record while the current one is tested: measured slower (spills at 64 registers)
 #endif
 #ifndef CLS4_MINB
 #define CLS4_MINB 16
@@ -391,8 +391,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
 
 // ------------------------------------------------------------------------------------------------
 // k_classify4: the plain classification (no global list, no corner refinement — the C4 variant), FOUR consecutive positions per
-// thread.  The candidate records of a tile are fetched once per four cells (the next record is requested while the current one
-// is tested), the four tests are independent instruction streams, slot 0 of the four cells is held in registers and leaves as
+// thread.  The candidate records of a tile are fetched once per four cells, the four tests are independent instruction streams, slot 0 of the four cells is held in registers and leaves as
 // one 16-byte store (every sector of slots[0][.] written in full: no partial-sector fills), n_item as one 4-byte store, and the
 // scan / queue append run once per four cells.  Queue order is unchanged (position order).  A thread whose four positions do
 // not share one tile (tile runs need not be multiples of four on general meshes) walks them one by one.  Measured at C4:
@@ -1082,158 +1081,6 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_final2: the same pass, TWO consecutive positions per thread: index / record / coordinate loads as 16-byte accesses, twice the
-// loads in flight per warp, and one warp butterfly per 64 cells — two pairs of the same solid (the rule inside a tile) are added
-// before they enter it.  Per-cell sums keep the reference's += order (ascending solid id within the cell).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_accumulate2(bool have, int s, int n1, int n2, int n3, const double v[6], double *force_torque,
-                                                 unsigned *pair_counts) {
-    const unsigned FULL = 0xffffffffu;
-    unsigned pending = __ballot_sync(FULL, have);
-    const int lane = threadIdx.x & 31;
-    while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const int s0 = __shfl_sync(FULL, s, leader);
-        const bool mine = have && (s == s0);
-        const unsigned grp = __ballot_sync(FULL, mine);
-        double w[8];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) w[k] = mine ? v[k] : 0.0;
-        w[6] = mine ? (double)n1 : 0.0;
-        w[7] = mine ? (double)n2 : 0.0;
-        const unsigned c3 = __reduce_add_sync(FULL, mine ? (unsigned)n3 : 0u);
-        double a[4], b[2], c;
-        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = (h16 ? w[i + 4] : w[i]) + __shfl_xor_sync(FULL, h16 ? w[i] : w[i + 4], 16);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) b[i] = (h8 ? a[i + 2] : a[i]) + __shfl_xor_sync(FULL, h8 ? a[i] : a[i + 2], 8);
-        c = (h4 ? b[1] : b[0]) + __shfl_xor_sync(FULL, h4 ? b[0] : b[1], 4);
-        c += __shfl_xor_sync(FULL, c, 2);
-        c += __shfl_xor_sync(FULL, c, 1);
-        if ((lane & 3) == 0) {
-            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            if (idx < 6) atomicAdd(force_torque + 6 * (long long)s0 + idx, c);
-            else if (c != 0.0) atomicAdd(pair_counts + 3 * (long long)s0 + (idx - 6), (unsigned)c);
-        }
-        if (lane == leader && c3) atomicAdd(pair_counts + 3 * (long long)s0 + 2, c3);
-        pending &= ~grp;
-    }
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_final2(InteractParams P) {
-    const DevMesh &m = P.m;
-    const unsigned FULL = 0xffffffffu;
-    const long long nC = m.n_cells;
-    const int c0 = P.c_begin + (blockIdx.x * 128 + threadIdx.x) * 2;
-    const bool live0 = c0 < P.c_end, live1 = c0 + 1 < P.c_end;
-    const bool vec = live1 && (((P.c_begin | (int)(nC & 1)) & 1) == 0);     // 8 / 16-byte accesses on position pairs are aligned
-    int oc[2] = {0, 0}, n[2] = {0, 0}, e0[2] = {0, 0};
-    if (vec) {
-        const int2 o2 = __ldg(reinterpret_cast<const int2 *>(m.orig + c0));
-        const unsigned short n2 = *reinterpret_cast<const unsigned short *>(P.n_item + c0);
-        const int2 s2 = *reinterpret_cast<const int2 *>(P.slots + c0);
-        oc[0] = o2.x; oc[1] = o2.y; n[0] = n2 & 0xff; n[1] = n2 >> 8; e0[0] = s2.x; e0[1] = s2.y;
-    } else {
-        if (live0) { oc[0] = __ldg(m.orig + c0); n[0] = P.n_item[c0]; e0[0] = P.slots[c0]; }
-        if (live1) { oc[1] = __ldg(m.orig + c0 + 1); n[1] = P.n_item[c0 + 1]; e0[1] = P.slots[c0 + 1]; }
-    }
-    int nmax = max(n[0], n[1]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-    const bool adj = vec && oc[1] == oc[0] + 1 && (oc[0] & 1) == 0;       // the two cells are neighbours in the caller's numbering too
-
-    double as[2] = {0.0, 0.0}, ts[2] = {0.0, 0.0}, ct[2] = {0.0, 0.0};
-    D3 fs[2] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-    if (nmax > 0) {
-        const double dtINV = __ldg(P.scal);
-        D3 cc[2] = {{0, 0, 0}, {0, 0, 0}}, uf[2] = {{0, 0, 0}, {0, 0, 0}};
-        double vol[2] = {1.0, 1.0};
-        if (n[0] | n[1]) {
-            if (vec) {
-                const double2 *g = reinterpret_cast<const double2 *>(m.cc + 3 * (long long)c0);
-                const double2 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2);
-                cc[0] = {a.x, a.y, b.x}; cc[1] = {b.y, c.x, c.y};
-                const double2 v2 = __ldg(reinterpret_cast<const double2 *>(m.V + c0));
-                vol[0] = v2.x; vol[1] = v2.y;
-            } else {
-                if (n[0]) { cc[0] = ld3(m.cc, c0); vol[0] = __ldg(m.V + c0); }
-                if (n[1]) { cc[1] = ld3(m.cc, c0 + 1); vol[1] = __ldg(m.V + c0 + 1); }
-            }
-            if (adj) {
-                const double2 *g = reinterpret_cast<const double2 *>(P.U + 3 * (long long)oc[0]);
-                const double2 a = __ldg(g), b = __ldg(g + 1), c = __ldg(g + 2);
-                uf[0] = {a.x, a.y, b.x}; uf[1] = {b.y, c.x, c.y};
-            } else {
-                if (n[0]) uf[0] = ld3(P.U, oc[0]);
-                if (n[1]) uf[1] = ld3(P.U, oc[1]);
-            }
-        }
-        for (int j = 0; j < nmax; ++j) {
-            bool have[2] = {false, false};
-            int s[2] = {-1, -1}, type[2] = {0, 0};
-            double contrib[2][6];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) contrib[q][k] = 0.0;
-                if (j < n[q]) {
-                    const int c = c0 + q;
-                    const int e = (j == 0) ? e0[q] : P.slots[(long long)j * nC + c];
-                    s[q] = e >> 3;
-                    type[q] = e & 3;
-                    double v = 0.0;
-                    if (e & SLOT_HEAVY) {                                           // the slot points at its queue item
-                        const double2 r = P.heavy_res[e >> 3];
-                        const int bits = (int)__double_as_longlong(r.y);
-                        type[q] = bits & 3;
-                        s[q] = bits >> 2;
-                        v = r.x;
-                        P.slots[(long long)j * nC + c] = (s[q] << 3) | SLOT_HEAVY | type[q];   // final record
-                    }
-                    const bool skip = P.excluded && P.excluded[(long long)c * P.K + j]; // replay: outside the seed's component
-                    if (type[q] != 0 && !skip) {
-                        const double alpha = (type[q] == SDFIBM_CELL_ALL_INSIDE) ? 1.0 : v / vol[q];   // solidcloud.cpp:408-410
-                        D3 fi;
-                        pair_terms(P.solids[s[q]], cc[q], uf[q], vol[q], alpha, dtINV, fi, contrib[q]);   // :384-390,411-421
-                        as[q] += alpha;
-                        fs[q] = fs[q] + fi;
-                        ts[q] += alpha;
-                        ct[q] = (type[q] == SDFIBM_CELL_ALL_INSIDE) ? (double)(s[q] + 4) : (double)type[q];   // :376-382, last writer wins
-                        have[q] = true;
-                    }
-                }
-            }
-            if (__any_sync(FULL, have[0] || have[1])) {
-                // pair A: cell 0's, or cell 1's when cell 0 has none, or both when they belong to the same solid; pair B: the rest
-                const bool both = have[0] && have[1], same = both && s[0] == s[1];
-                const bool haveA = have[0] || have[1], haveB = both && !same;
-                const int qa = have[0] ? 0 : 1;
-                double vA[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) vA[k] = (qa == 0 ? contrib[0][k] : contrib[1][k]) + (same ? contrib[1][k] : 0.0);
-                const int tA = qa == 0 ? type[0] : type[1], tB = type[1];
-                warp_accumulate2(haveA, qa == 0 ? s[0] : s[1], (tA == 1) + (same && tB == 1), (tA == 2) + (same && tB == 2), (tA == 3) + (same && tB == 3),
-                                 vA, P.force_torque, P.pair_counts);
-                if (__any_sync(FULL, haveB)) warp_accumulate2(haveB, s[1], tB == 1, tB == 2, tB == 3, contrib[1], P.force_torque, P.pair_counts);
-            }
-        }
-    }
-    if (adj) {
-        const double a0 = (as[0] < 1.0) ? as[0] : 1.0, a1 = (as[1] < 1.0) ? as[1] : 1.0;   // checkAlpha, :564-570
-        *reinterpret_cast<double2 *>(P.As + oc[0]) = make_double2(a0, a1);
-        double2 *f = reinterpret_cast<double2 *>(P.Fs + 3 * (long long)oc[0]);
-        f[0] = make_double2(fs[0].x, fs[0].y); f[1] = make_double2(fs[0].z, fs[1].x); f[2] = make_double2(fs[1].y, fs[1].z);
-        *reinterpret_cast<double2 *>(P.Ts + oc[0]) = make_double2(ts[0], ts[1]);
-        *reinterpret_cast<double2 *>(P.Ct + oc[0]) = make_double2(ct[0], ct[1]);
-    } else {
-        if (live0) store_cell(P, oc[0], as[0], fs[0], ts[0], ct[0]);
-        if (live1) store_cell(P, oc[1], as[1], fs[1], ts[1], ct[1]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_connectivity: a member pair is a "root" when no face neighbour that is a member of the same solid has a smaller key.  Exactly one
 // root  =>  the solid's vertex-inside cell set is face connected.
 // ------------------------------------------------------------------------------------------------
@@ -1386,7 +1233,12 @@ __global__ void k_replay_init(ReplayParams P) {
     }
 }
 
-__global__ void k_replay_propagate(ReplayParams P) {
+// One sweep of the min-label propagation.  The host enqueues REPLAY_BATCH sweeps per round trip; `changed[sweep]` records whether
+// sweep `sweep` of the batch lowered a label, and a sweep whose predecessor changed nothing returns at once (converged), so the
+// convergence test runs on the device and the host reads ONE flag per batch.
+#define REPLAY_BATCH 32
+__global__ void k_replay_propagate(ReplayParams P, int sweep) {
+    if (sweep > 0 && ((volatile int *)P.changed)[sweep - 1] == 0) return;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.m.n_cells) return;
     const int n = P.n_item[c];
@@ -1405,7 +1257,7 @@ __global__ void k_replay_propagate(ReplayParams P) {
                 if (l2 >= 0 && l2 < best) best = l2;
             }
         }
-        if (best < lab) { P.labels[(long long)c * P.K + j] = best; *P.changed = 1; }
+        if (best < lab) { P.labels[(long long)c * P.K + j] = best; P.changed[sweep] = 1; }
     }
 }
 
@@ -1467,10 +1319,8 @@ __global__ void k_replay_mark(ReplayParams P) {
 // ------------------------------------------------------------------------------------------------
 // fixInternal (solidcloud.cpp:288-301)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_fix_internal(const double *cc, const sdfibm_solid_t *solids, int n_solids, const double *Ct, double *U, int c_begin, int c_end) {
-    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_end) return;
-    const double ct = Ct[c];
+// Two consecutive cells per thread: Ct streams in as 16-byte loads (8 nC of the pass's 8 nC + 48 #(Ct >= 4) bytes).
+__device__ __forceinline__ void fix_internal_cell(const double *cc, const sdfibm_solid_t *solids, int n_solids, double ct, double *U, int c) {
     if (ct >= 4) {
         const int id = (int)(ct - 4);
         if (id < n_solids) {
@@ -1481,6 +1331,19 @@ __global__ void k_fix_internal(const double *cc, const sdfibm_solid_t *solids, i
             U[3 * (long long)c + 1] = u.y;
             U[3 * (long long)c + 2] = u.z;
         }
+    }
+}
+__global__ void __launch_bounds__(256) k_fix_internal(const double *__restrict__ cc, const sdfibm_solid_t *__restrict__ solids, int n_solids,
+                                                      const double *__restrict__ Ct, double *__restrict__ U, int c_begin, int c_end) {
+    const int c = c_begin + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= c_end) return;
+    if ((c_begin & 1) == 0 && c + 1 < c_end) {
+        const double2 ct = __ldg(reinterpret_cast<const double2 *>(Ct + c));
+        fix_internal_cell(cc, solids, n_solids, ct.x, U, c);
+        fix_internal_cell(cc, solids, n_solids, ct.y, U, c + 1);
+    } else {
+        fix_internal_cell(cc, solids, n_solids, Ct[c], U, c);
+        if (c + 1 < c_end) fix_internal_cell(cc, solids, n_solids, Ct[c + 1], U, c + 1);
     }
 }
 

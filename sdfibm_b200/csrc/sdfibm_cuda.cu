@@ -614,9 +614,6 @@ __device__ __forceinline__ void bin_insertion_sort(int *lst, int beg, int end) {
     }
 }
 
-#ifndef FINAL2_CTAS
-#define FINAL2_CTAS 4
-#endif
 #ifndef FINAL_CTAS
 #define FINAL_CTAS 4
 #endif
@@ -847,6 +844,13 @@ struct sdfibm_context {
     DevBuf<int> labels, seed_cell, min_label, chosen, changed, flagged_list;
     DevBuf<unsigned long long> seed_key;
     DevBuf<unsigned char> excluded;
+    // collision step: buffers kept between calls (evolve runs it 20 times per step; cudaMalloc / cudaFree per call cost more than the kernels)
+    DevBuf<int> col_ids, col_sids, col_pcnt, col_poff, col_pairs;
+    DevBuf<unsigned> col_keys, col_skeys;
+    DevBuf<unsigned char> col_tmp;
+    DevBuf<double> col_ft;
+    cudaEvent_t ev_aux[2] = {nullptr, nullptr};   // device time of the last fixInternal / collision kernels
+    double t_fix_ms = 0, t_col_ms = 0;
     bool last_used_replay = false;
     // stats
     StepStatus last{};
@@ -864,7 +868,6 @@ struct sdfibm_context {
     GraphKey graph_key = {0};
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
-    bool final2 = false;                 // k_final2 (two positions per thread); SDFIBM_FINAL2=1
     bool classify4 = true;               // k_classify4 (four positions per thread); SDFIBM_CLASSIFY4=0: the one-position kernel
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
@@ -1022,14 +1025,13 @@ int sdfibm_create(int device, sdfibm_context **out) {
     ctx->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMallocHost(&ctx->h_status, sizeof(StepStatus)));
-    CUDA_TRY(cudaMallocHost(&ctx->h_scal, 2 * sizeof(double)));
+    CUDA_TRY(cudaMallocHost(&ctx->h_scal, 4 * sizeof(double)));   // [0..1] per-step scalars, [2..3] small read-back scratch
     CUDA_TRY(cudaMallocHost(&ctx->h_retry_sum, sizeof(double)));
     *ctx->h_retry_sum = 0.0;
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev_comm[i]));
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_CLASSIFY4")) ctx->classify4 = atoi(e) != 0;
-    if (const char *e = getenv("SDFIBM_FINAL2")) ctx->final2 = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_BOX")) ctx->allow_box = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_ALLOW_ORDER_FREE")) ctx->allow_order_free = atoi(e) != 0;
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
@@ -1067,6 +1069,9 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->dU.release(); ctx->dAs.release(); ctx->dFs.release(); ctx->dTs.release(); ctx->dCt.release(); ctx->dFT.release(); ctx->sU.release(); ctx->sOut.release(); ctx->sFT.release();
     ctx->labels.release(); ctx->seed_cell.release(); ctx->min_label.release(); ctx->chosen.release();
     ctx->changed.release(); ctx->seed_key.release(); ctx->excluded.release(); ctx->flagged_list.release();
+    ctx->col_ids.release(); ctx->col_sids.release(); ctx->col_pcnt.release(); ctx->col_poff.release(); ctx->col_pairs.release();
+    ctx->col_keys.release(); ctx->col_skeys.release(); ctx->col_tmp.release(); ctx->col_ft.release();
+    for (int i = 0; i < 2; ++i) if (ctx->ev_aux[i]) cudaEventDestroy(ctx->ev_aux[i]);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < sdfibm_context::MAX_CHUNK; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_fin[i]) cudaEventDestroy(ctx->ev_fin[i]); }
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -1571,7 +1576,7 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         CUDA_TRY(ctx->seed_cell.ensure(n_solids));
         CUDA_TRY(ctx->min_label.ensure(n_solids));
         CUDA_TRY(ctx->chosen.ensure(n_solids));
-        CUDA_TRY(ctx->changed.ensure(1));
+        CUDA_TRY(ctx->changed.ensure(REPLAY_BATCH));
         ReplayParams R;
         R.m = ctx->dm; R.solids = ctx->solids.p; R.n_item = ctx->n_item.p; R.slots = ctx->slots.p; R.K = ctx->K;
         R.root_count = ctx->root_count; R.labels = ctx->labels.p; R.changed = ctx->changed.p;
@@ -1584,14 +1589,14 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
         CUDA_TRY(cudaMemsetAsync(ctx->seed_key.p, 0xff, sizeof(unsigned long long) * n_solids, st));
         CUDA_TRY(cudaMemsetAsync(ctx->seed_cell.p, 0x7f, sizeof(int) * n_solids, st));
         CUDA_TRY(cudaMemsetAsync(ctx->min_label.p, 0x7f, sizeof(int) * n_solids, st));
+        int *h_changed = reinterpret_cast<int *>(ctx->h_scal + 2);   // page-locked read-back scratch
         for (int it = 0; it < 1000000; ++it) {
-            int h_changed = 0;
-            CUDA_TRY(cudaMemsetAsync(ctx->changed.p, 0, sizeof(int), st));
-            for (int rep = 0; rep < 8; ++rep) k_replay_propagate<<<g, 256, 0, st>>>(R);
-            CUDA_TRY(cudaMemcpyAsync(&h_changed, ctx->changed.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemsetAsync(ctx->changed.p, 0, sizeof(int) * REPLAY_BATCH, st));
+            for (int rep = 0; rep < REPLAY_BATCH; ++rep) k_replay_propagate<<<g, 256, 0, st>>>(R, rep);
+            CUDA_TRY(cudaMemcpyAsync(h_changed, ctx->changed.p + (REPLAY_BATCH - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            ctx->launches += 8;
-            if (!h_changed) break;
+            ctx->launches += REPLAY_BATCH;
+            if (!*h_changed) break;     // the last sweep of the batch changed nothing (or never ran: an earlier one converged)
         }
         CUDA_TRY(ctx->flagged_list.ensure((size_t)n_solids + 1));
         CUDA_TRY(cudaMemsetAsync(ctx->flagged_list.p + n_solids, 0, sizeof(int), st));
@@ -1744,7 +1749,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
             if (p1 > p0) {
                 I.c_begin = (int)p0; I.c_end = (int)p1;
                 CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
-                if (ctx->final2) k_final2<FINAL2_CTAS><<<grid_for(p1 - p0, 256), 128, 0, st>>>(I); else k_final<FINAL_CTAS><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
+                k_final<FINAL_CTAS><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
             }
             CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
             for (int j = 0; j < NCH; ++j) {
@@ -1762,7 +1767,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         ctx->launches += ctx->n_chunk - 3;
     } else {
         I.c_begin = 0; I.c_end = nC;
-        if (ctx->final2) k_final2<FINAL2_CTAS><<<grid_for(nC, 256), 128, 0, st>>>(I); else k_final<FINAL_CTAS><<<grid_for(nC, 256), 256, 0, st>>>(I);
+        k_final<FINAL_CTAS><<<grid_for(nC, 256), 256, 0, st>>>(I);
     }
     CUDA_TRY(rec(ctx->ev[4]));
     ctx->launches += 3;
@@ -2102,9 +2107,13 @@ int sdfibm_fix_internal_device(sdfibm_context *ctx, const sdfibm_solid_t *solids
     CUDA_TRY(cudaSetDevice(ctx->device));
     int rc = stage_solids(ctx, solids, n_solids);
     if (rc) return rc;
-    k_fix_internal<<<grid_for(ctx->dm.n_cells, 256), 256, 0, ctx->stream>>>(ctx->cc_orig.p, ctx->solids_in.p, n_solids, dCt, dU, 0, ctx->dm.n_cells);
+    for (int i = 0; i < 2; ++i) if (!ctx->ev_aux[i]) CUDA_TRY(cudaEventCreate(&ctx->ev_aux[i]));
+    CUDA_TRY(cudaEventRecord(ctx->ev_aux[0], ctx->stream));
+    k_fix_internal<<<grid_for(((long long)ctx->dm.n_cells + 1) / 2, 256), 256, 0, ctx->stream>>>(ctx->cc_orig.p, ctx->solids_in.p, n_solids, dCt, dU, 0, ctx->dm.n_cells);
+    CUDA_TRY(cudaEventRecord(ctx->ev_aux[1], ctx->stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    { float x = 0; cudaEventElapsedTime(&x, ctx->ev_aux[0], ctx->ev_aux[1]); ctx->t_fix_ms = x; }
     return SDFIBM_OK;
 }
 
@@ -2128,7 +2137,7 @@ int sdfibm_fix_internal(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n
         const size_t c0 = nC * i / ctx->n_chunk, c1 = nC * (i + 1) / ctx->n_chunk;
         if (c1 <= c0) continue;
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[i], 0));
-        k_fix_internal<<<grid_for((long long)(c1 - c0), 256), 256, 0, st>>>(ctx->cc_orig.p, ctx->solids_in.p, n_solids, ctx->dCt.p, ctx->dU.p, (int)c0, (int)c1);
+        k_fix_internal<<<grid_for(((long long)(c1 - c0) + 1) / 2, 256), 256, 0, st>>>(ctx->cc_orig.p, ctx->solids_in.p, n_solids, ctx->dCt.p, ctx->dU.p, (int)c0, (int)c1);
         CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_out, ctx->ev_fin[i], 0));
         CUDA_TRY(cudaMemcpyAsync(U + 3 * c0, ctx->dU.p + 3 * c0, sizeof(double) * 3 * (c1 - c0), cudaMemcpyDeviceToHost, ctx->s_out));
@@ -2260,6 +2269,13 @@ int sdfibm_last_timings(sdfibm_context *ctx, double ms[6]) {
     return SDFIBM_OK;
 }
 
+int sdfibm_last_aux_timings(sdfibm_context *ctx, double ms[2]) {
+    if (!ctx || !ms) return fail(SDFIBM_ERR_ARG, "sdfibm_last_aux_timings: null argument");
+    ms[0] = ctx->t_fix_ms;
+    ms[1] = ctx->t_col_ms;
+    return SDFIBM_OK;
+}
+
 int sdfibm_last_host_timings(sdfibm_context *ctx, double us[4]) {
     if (!ctx || !us) return fail(SDFIBM_ERR_ARG, "null argument");
     for (int k = 0; k < 4; ++k) us[k] = ctx->t_host_us[k];
@@ -2327,26 +2343,27 @@ int sdfibm_collide(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n, dou
     if (g.nx <= 0 || g.ny <= 0 || g.nz <= 0) return SDFIBM_OK;                 // HEAD: delta = -2 -> no pairs
     int rc = stage_solids(ctx, solids, n);
     if (rc) return rc;
-    DevBuf<int> ids, sids, pcnt, poff, dpairs;
-    DevBuf<unsigned> keys, skeys;
-    DevBuf<unsigned char> tmp;
-    DevBuf<double> dft;
+    DevBuf<int> &ids = ctx->col_ids, &sids = ctx->col_sids, &pcnt = ctx->col_pcnt, &poff = ctx->col_poff, &dpairs = ctx->col_pairs;
+    DevBuf<unsigned> &keys = ctx->col_keys, &skeys = ctx->col_skeys;
+    DevBuf<unsigned char> &tmp = ctx->col_tmp;
+    DevBuf<double> &dft = ctx->col_ft;
+    for (int i = 0; i < 2; ++i) if (!ctx->ev_aux[i]) CUDA_TRY(cudaEventCreate(&ctx->ev_aux[i]));
+    size_t sb = 0, tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, keys.p, skeys.p, ids.p, sids.p, n, 0, 32, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, pcnt.p, poff.p, n + 1, st);
+    CUDA_TRY(tmp.ensure(std::max(sb, tb)));
+    CUDA_TRY(cudaEventRecord(ctx->ev_aux[0], st));
     CUDA_TRY(keys.ensure(n)); CUDA_TRY(ids.ensure(n)); CUDA_TRY(skeys.ensure(n)); CUDA_TRY(sids.ensure(n));
     CUDA_TRY(pcnt.ensure((size_t)n + 1)); CUDA_TRY(poff.ensure((size_t)n + 1));
     k_col_keys<<<grid_for(n, 256), 256, 0, st>>>(ctx->solids_in.p, n, g, keys.p, ids.p);
-    size_t sb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sb, keys.p, skeys.p, ids.p, sids.p, n, 0, 32, st);
-    CUDA_TRY(tmp.ensure(sb));
     cub::DeviceRadixSort::SortPairs(tmp.p, sb, keys.p, skeys.p, ids.p, sids.p, n, 0, 32, st); // stable; keys are signed but compared as bits:
     CUDA_TRY(cudaMemsetAsync(pcnt.p, 0, sizeof(int) * ((size_t)n + 1), st));
     k_col_pairs<<<grid_for(n, 128), 128, 0, st>>>(skeys.p, sids.p, n, g, pcnt.p, nullptr, nullptr, 0, 0);
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, pcnt.p, poff.p, n + 1, st);
-    CUDA_TRY(tmp.ensure(tb));
     cub::DeviceScan::ExclusiveSum(tmp.p, tb, pcnt.p, poff.p, n + 1, st);
-    int total = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, poff.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int *h_total = reinterpret_cast<int *>(ctx->h_scal + 2);   // page-locked scratch next to the per-step scalars
+    CUDA_TRY(cudaMemcpyAsync(h_total, poff.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    const int total = *h_total;
     *n_pairs = total;
     if (total > 0) {
         CUDA_TRY(dpairs.ensure(2 * (size_t)total));
@@ -2362,9 +2379,10 @@ int sdfibm_collide(sdfibm_context *ctx, const sdfibm_solid_t *solids, int n, dou
             CUDA_TRY(cudaMemcpyAsync(pairs, dpairs.p, sizeof(int) * 2 * (size_t)total, cudaMemcpyDeviceToHost, st));
         }
     }
+    CUDA_TRY(cudaEventRecord(ctx->ev_aux[1], st));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(st));
-    keys.release(); ids.release(); skeys.release(); sids.release(); pcnt.release(); poff.release(); dpairs.release(); tmp.release(); dft.release();
+    { float x = 0; cudaEventElapsedTime(&x, ctx->ev_aux[0], ctx->ev_aux[1]); ctx->t_col_ms = x; }
     return SDFIBM_OK;
 }
 
