@@ -115,9 +115,14 @@ def algorithmic_bytes(n_cells, counts, n_solids):
 L2_NOTE = "inputs larger than L2 (fields + mesh arrays of one step >> 126 MB); no explicit flush"
 
 
+L2_NOTE_SMALL = ("the reference's small example set-up: one step's data fits the 126 MB L2 and is not flushed; the figure of interest is "
+                 "latency (ms/step of one graph launch), no roofline claim is made on it")
+
+
 def make_config(desc):
     """`config` of the JSON line: the same keys and values in both arms (ours and --impl reference)."""
-    return dict(desc, l2=L2_NOTE)
+    small = desc.get("workload", "").startswith(("C1", "C2", "C3"))
+    return dict(desc, l2=L2_NOTE_SMALL if small else L2_NOTE)
 
 
 def build_case(args, rank, world):
@@ -126,7 +131,7 @@ def build_case(args, rank, world):
     wl = args.workload
     if wl == "auto":
         wl = "c4" if world == 1 else "c5"
-    if wl in ("c1", "c2", "c3", "c3b"):
+    if wl in ("c1", "c2", "c3", "c3b", "c3tc"):
         # BASELINE configs 1-3 (latency-bound; ms/step is the figure of interest): the reference's own example set-ups
         if world != 1:
             raise SystemExit(f"workload {wl} is single-GPU")
@@ -140,9 +145,13 @@ def build_case(args, rank, world):
             pts = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "m2_points.npz"))["points"]
             case = cases.case_c3(pts)
             desc = {"workload": "C3: falling_ellipse on the shipped 100x200x1 mesh, Ellipse 0.3/0.15 at -45 deg (2-D)"}
+        elif wl == "c3tc":
+            case = cases.case_taylor_couette()
+            desc = {"workload": "C3 taylor_couette: the five-block O-grid of examples/taylor_couette/system/blockMeshDict (5 x 50x50x1 curved hexahedra), "
+                                "Circle r=0.3 spinning at the origin + a Circle_Tail across a block junction (2-D)"}
         else:
             case = cases.case_skewed_2d()
-            desc = {"workload": "C3b: rotated + jittered 60x60x1 quad block (stand-in for the taylor_couette O-grid), Circle r=0.3 + Circle_TwoTail"}
+            desc = {"workload": "C3b: rotated + jittered 60x60x1 quad block, Circle r=0.3 + Circle_TwoTail"}
     elif wl == "c4":
         n = args.n or 256
         scale = n / 256.0
@@ -361,7 +370,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c3b", "c4", "c5"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c3b", "c3tc", "c4", "c5"],
                     help="auto = the contract's line (C4 at N=1, C5 at N>1); c1..c3b = the reference's small example set-ups (ms/step)")
     ap.add_argument("--cells-per-side", dest="n", type=int, default=0, help="cells per side (scaled-down runs)")
     ap.add_argument("--solids", type=int, default=0)

@@ -430,13 +430,24 @@ __global__ void k_cc32(const double *cc_p, const float2 *rad, int n_cells, doubl
 // [cmin, cmax] of the caller's cell labels over each chunk of positions (host-buffer pipeline)
 __global__ void k_chunk_ranges(const int *orig, int n_cells, int n_chunk, int *cmin, int *cmax) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cells) return;
     // chunk k covers positions [n*k/n_chunk, n*(k+1)/n_chunk)
-    int k = (int)(((long long)i * n_chunk) / n_cells);
-    while ((long long)n_cells * k / n_chunk > i) --k;
-    while ((long long)n_cells * (k + 1) / n_chunk <= i) ++k;
-    atomicMin(cmin + k, orig[i]);
-    atomicMax(cmax + k, orig[i]);
+    int k = -1, v = 0;
+    if (i < n_cells) {
+        k = (int)(((long long)i * n_chunk) / n_cells);
+        while ((long long)n_cells * k / n_chunk > i) --k;
+        while ((long long)n_cells * (k + 1) / n_chunk <= i) ++k;
+        v = orig[i];
+    }
+    // a warp lies inside one chunk except at the few chunk boundaries: reduce in the warp, one atomic pair per warp
+    const unsigned FULL = 0xffffffffu;
+    const int k0 = __shfl_sync(FULL, k, 0);
+    if (__all_sync(FULL, k == k0) && k0 >= 0) {
+        const int lo = __reduce_min_sync(FULL, v), hi = __reduce_max_sync(FULL, v);
+        if ((threadIdx.x & 31) == 0) { atomicMin(cmin + k0, lo); atomicMax(cmax + k0, hi); }
+    } else if (k >= 0) {
+        atomicMin(cmin + k, v);
+        atomicMax(cmax + k, v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
