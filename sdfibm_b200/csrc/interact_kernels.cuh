@@ -814,6 +814,9 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
 #ifndef BOX_CTAS_PER_SM
 #define BOX_CTAS_PER_SM 6
 #endif
+#ifndef BOX_PREFETCH
+#define BOX_PREFETCH 2   // C4 k_heavy_box: 0.387 ms without, 0.390 with the register prefetch, 0.378 with the cp.async one
+#endif
 #ifndef BOX_VUNROLL
 #define BOX_VUNROLL 2
 #endif
@@ -865,11 +868,42 @@ __global__ void __launch_bounds__(TPB, BOX_CTAS_PER_SM) k_heavy_box(InteractPara
     double *phi = sm.phi + tid, *lohi = sm.lohi + tid, *ef = sm.ef + tid, *apx = sm.apex + tid;
     const long long n = min((long long)*P.heavy_count, P.heavy_cap);
     const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
+    // the queue item of the NEXT batch is requested while this one is evaluated — BOX_PREFETCH 1: 8 bytes in two registers,
+    // 2: an 8-byte cp.async into the lane's shared-memory slot (no registers) — so the cell / solid records of a batch are one
+    // dependent level away instead of two
+#if BOX_PREFETCH == 1
+    int2 it_next = make_int2(0, 0);
+    {
+        const long long kf = q0 + (long long)blockIdx.x * TPB + wbase + lane;
+        if (kf < n) it_next = __ldg(P.heavy + kf);
+    }
+#elif BOX_PREFETCH == 2
+    __shared__ double s_item[TPB];
+    {
+        const long long kf = q0 + (long long)blockIdx.x * TPB + wbase + lane;
+        if (kf < n) cp_async8(&s_item[tid], reinterpret_cast<const double *>(P.heavy + kf));
+    }
+#endif
     for (long long k0 = q0 + (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
         const long long k = k0 + lane;
         const bool valid = k < n;
         int c = 0, s = 0;
+#if BOX_PREFETCH == 1
+        c = it_next.x; s = it_next.y;
+        {
+            const long long kn = k + (long long)gridDim.x * TPB;
+            if (kn < n) it_next = __ldg(P.heavy + kn);
+        }
+#elif BOX_PREFETCH == 2
+        cp_async_wait_all();
+        if (valid) { const long long it = __double_as_longlong(s_item[tid]); c = (int)(it & 0xffffffffll); s = (int)(it >> 32); }
+        {
+            const long long kn = k + (long long)gridDim.x * TPB;
+            if (kn < n) cp_async8(&s_item[tid], reinterpret_cast<const double *>(P.heavy + kn));
+        }
+#else
         if (valid) { const int2 it = __ldg(P.heavy + k); c = it.x; s = it.y; }
+#endif
         DQ q = {1.0, {0.0, 0.0, 0.0}};
         D3 t = {0.0, 0.0, 0.0};
         int shape_idx = 0;
@@ -1020,15 +1054,13 @@ __global__ void __launch_bounds__(TPB) k_heavy_general(InteractParams P) {
 // ------------------------------------------------------------------------------------------------
 // k_final: thread per cell, every output sector written exactly once and in full.
 // ------------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
+#ifndef FINAL_NT
+#define FINAL_NT 64     // 2-warp CTAs: a CTA's slot frees as soon as its slowest warp is done (256-thread CTAs: 0.440 ms, 64: 0.403 ms at C4)
+#endif
+// one cell of the pass, given its first-level records: caller label oc, slot count n, slot 0
+__device__ __forceinline__ void final_cell(const InteractParams &P, int c, bool live, int oc, int n, int e0) {
     const DevMesh &m = P.m;
-    const int c = P.c_begin + blockIdx.x * blockDim.x + threadIdx.x;   // [c_begin, c_end): one chunk of the cell range
-    const bool live = c < P.c_end;
     const long long nC = m.n_cells;
-    const int oc = live ? __ldg(m.orig + c) : 0;   // caller's cell label: U is read and the fields are written there
-    const int n = live ? (int)P.n_item[c] : 0;
-    const int e0 = live ? P.slots[c] : 0;       // slot 0, fetched together with n_item (meaningless when n == 0)
     const unsigned FULL = 0xffffffffu;
     int nmax = n;
 #pragma unroll
@@ -1078,6 +1110,16 @@ __global__ void __launch_bounds__(256, MINB) k_final(InteractParams P) {
         }
     }
     if (live) store_cell(P, oc, as, fs, ts, ct);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(FINAL_NT, MINB) k_final(InteractParams P) {
+    const int c = P.c_begin + blockIdx.x * blockDim.x + threadIdx.x;   // [c_begin, c_end): one chunk of the cell range
+    const bool live = c < P.c_end;
+    const int oc = live ? __ldg(P.m.orig + c) : 0;   // caller's cell label: U is read and the fields are written there
+    const int n = live ? (int)P.n_item[c] : 0;
+    const int e0 = live ? P.slots[c] : 0;       // slot 0, fetched together with n_item (meaningless when n == 0)
+    final_cell(P, c, live, oc, n, e0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1161,12 +1203,24 @@ __global__ void __launch_bounds__(256) k_connectivity(ConnParams P) {
     // nothing to certify: every binned solid is connected by construction and no plane / tilted 2-D solid is about
     if (!P.status->need_cert && P.status->n_global == 0) return;
     const long long nC = P.m.n_cells;
-    for (long long c0 = (long long)blockIdx.x * blockDim.x; c0 < nC; c0 += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(c0 + threadIdx.x);
-        if (c >= nC) continue;
-        // every candidate of the cell's tile is connected by construction
-        if (P.tile_proven[__ldg(P.m.tile_key + c)] && P.status->n_global == 0) continue;
-        conn_cell(P, c);
+    const bool global = P.status->n_global != 0;
+    // persistent; FOUR position blocks per iteration: the tile_key -> tile_proven chain of the four is in flight at once (with one
+    // block per iteration the pass was a serial chain of ~55 two-level round trips per thread at 256^3 cells)
+    for (long long c0 = (long long)blockIdx.x * 1024; c0 < nC; c0 += (long long)gridDim.x * 1024) {
+        int c[4];
+        bool skip[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long cq = c0 + q * 256 + threadIdx.x;
+            c[q] = cq < nC ? (int)cq : -1;
+        }
+        unsigned t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = c[q] >= 0 ? __ldg(P.m.tile_key + c[q]) : 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) skip[q] = c[q] < 0 || (!global && P.tile_proven[t[q]]);   // every candidate of the cell's tile is connected by construction
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (!skip[q]) conn_cell(P, c[q]);
     }
 }
 

@@ -625,8 +625,11 @@ __device__ __forceinline__ void bin_insertion_sort(int *lst, int beg, int end) {
     }
 }
 
+#ifndef CLS_NT
+#define CLS_NT 128   // k_classify (one position per thread): threads per CTA (C5 at 256^3: 0.373 ms at 256, 0.352 at 128, 0.355 at 64)
+#endif
 #ifndef FINAL_CTAS
-#define FINAL_CTAS 4
+#define FINAL_CTAS (1024 / FINAL_NT)   // 1024 resident threads per SM at 64 registers
 #endif
 #include "interact_kernels.cuh"
 
@@ -1697,9 +1700,11 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
             k_classify4<CLS4_NT, CLS4_MINB><<<grid_for(p1 - p0, 4 * CLS4_NT), CLS4_NT, 0, st>>>(I);
             return;
         }
-        if (ctx->n_global_hint) k_classify<256, 4, true, true><<<grid, 256, 0, st>>>(I);
-        else if (ctx->shapes_refinable) k_classify<256, 6, false, true><<<grid, 256, 0, st>>>(I);
-        else k_classify<256, 8, false, false><<<grid, 256, 0, st>>>(I);
+        constexpr int CM = 256 / CLS_NT;   // resident CTAs scale with the CTA size: the same threads per SM
+        const int gridc = grid_for(p1 - p0, CLS_NT);
+        if (ctx->n_global_hint) k_classify<CLS_NT, 4 * CM, true, true><<<gridc, CLS_NT, 0, st>>>(I);
+        else if (ctx->shapes_refinable) k_classify<CLS_NT, 6 * CM, false, true><<<gridc, CLS_NT, 0, st>>>(I);
+        else k_classify<CLS_NT, 8 * CM, false, false><<<gridc, CLS_NT, 0, st>>>(I);
     };
     auto launch_heavy = [&]() {
         // (PROG: the shape table holds a composed shape — only then do the kernels carry the op interpreter)
@@ -1760,7 +1765,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
             if (p1 > p0) {
                 I.c_begin = (int)p0; I.c_end = (int)p1;
                 CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[range_of(ctx->chunk_cmax[i])], 0));
-                k_final<FINAL_CTAS><<<grid_for(p1 - p0, 256), 256, 0, st>>>(I);
+                k_final<FINAL_CTAS><<<grid_for(p1 - p0, FINAL_NT), FINAL_NT, 0, st>>>(I);
             }
             CUDA_TRY(cudaEventRecord(ctx->ev_fin[i], st));
             for (int j = 0; j < NCH; ++j) {
@@ -1778,7 +1783,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         ctx->launches += ctx->n_chunk - 3;
     } else {
         I.c_begin = 0; I.c_end = nC;
-        k_final<FINAL_CTAS><<<grid_for(nC, 256), 256, 0, st>>>(I);
+        k_final<FINAL_CTAS><<<grid_for(nC, FINAL_NT), FINAL_NT, 0, st>>>(I);
     }
     CUDA_TRY(rec(ctx->ev[4]));
     ctx->launches += 3;
