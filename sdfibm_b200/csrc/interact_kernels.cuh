@@ -817,6 +817,9 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
 #ifndef BOX_PREFETCH
 #define BOX_PREFETCH 2   // C4 k_heavy_box: 0.387 ms without, 0.390 with the register prefetch, 0.378 with the cp.async one
 #endif
+#ifndef BOX_EDGE_COMPACT
+#define BOX_EDGE_COMPACT 1
+#endif
 #ifndef BOX_VUNROLL
 #define BOX_VUNROLL 2
 #endif
@@ -986,13 +989,38 @@ PRAGMA_UNROLL(BOX_VUNROLL)
                     }
                     if (m.two_d) apx[2 * TPB] = 0.0;
                 }
-                // the 12 edge fractions, each taken once (every edge belongs to two faces)
+                // the 12 edge fractions, each taken once (every edge belongs to two faces).  Row e = 4 * axis + ... starts at the corner
+                // EDGE_BASE[e] = {0,2,4,6 | 0,4,1,5 | 0,1,2,3}.
+#if BOX_EDGE_COMPACT
+                // An edge whose ends lie on one side has the fraction 0 (both phi > 0) or 1 by definition (:14-17): stored straight from
+                // the sign mask.  Only CUT edges need the quotient, and a cell has 3-6 of them (a warp: the maximum over its lanes), so
+                // each lane walks the set bits of its own 12-bit cut mask instead of all 12 rows.
+                {
+                    const unsigned x = pm ^ (pm >> 1), y = pm ^ (pm >> 2), z = pm ^ (pm >> 4);
+                    unsigned cm = (x & 1u) | ((x >> 1) & 2u) | ((x >> 2) & 4u) | ((x >> 3) & 8u)            // axis 0: corners 0,2,4,6
+                                  | ((y & 1u) << 4) | (((y >> 4) & 1u) << 5) | (((y >> 1) & 1u) << 6) | (((y >> 5) & 1u) << 7)   // axis 1: 0,4,1,5
+                                  | ((z & 15u) << 8);                                                                         // axis 2: 0,1,2,3
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) {
+                        const int base = e < 4 ? 2 * e : (e < 8 ? ((e & 1) << 2) | ((e >> 1) & 1) : e - 8);
+                        ef[e * TPB] = ((pm >> base) & 1u) ? 0.0 : 1.0;
+                    }
+                    while (cm) {
+                        const int e = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        const int d = e >> 2;
+                        const int base = e >= 8 ? e - 8 : (int)((0x51406420u >> (4 * e)) & 7u);
+                        ef[e * TPB] = edge_fraction(phi[base * TPB], phi[(base | (1 << d)) * TPB]);
+                    }
+                }
+#else
 PRAGMA_UNROLL(BOX_EUNROLL)
                 for (int e = 0; e < 12; ++e) {
                     const int d = e >> 2, u = (d == 2) ? 0 : d + 1, v = (d == 0) ? 2 : d - 1;   // u = (d+1)%3, v = (d+2)%3
                     const int base = ((e & 1) << u) | (((e >> 1) & 1) << v);
                     ef[e * TPB] = edge_fraction(phi[base * TPB], phi[(base | (1 << d)) * TPB]);
                 }
+#endif
                 // six pyramid terms 1/3 eps_f |(apex - Cf) . Sf| (geometrictools.cpp:61-70,98-116), face = (axis a, side sd)
                 const double *cfa = PLANE_FROM_MESH ? m.cfa6 + 6 * (long long)c : nullptr;
 PRAGMA_UNROLL(BOX_FUNROLL)
