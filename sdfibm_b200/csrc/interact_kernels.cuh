@@ -398,7 +398,10 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
 // 0.225 -> 0.18 ms; with the refinement / global-list code in the loop the register count halves the occupancy and the
 // one-position kernel stays faster, so those variants keep it.
 // ------------------------------------------------------------------------------------------------
-template <int NT, int MINB>
+// SPEC: every shape of the table is 3-D and every cell is the same axis-aligned box (C4, C5): the 2-D / 3-D selects and the clamp of
+// the near-corner offsets drop out of the test.  The two sums of squares use explicit fmaf (one rounding less per term; the 4e-6
+// relative slack of the radii covers either rounding sequence — tests/test_classify_bounds_cpu.py runs both).
+template <int NT, int MINB, bool SPEC>
 __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
         for (int q = 0; q < 4; ++q) {
             const int c = min(c0 + q, P.cls_end - 1);
             p[q] = __ldg(m.cc32 + c);
-            hb[q] = m.box_uniform ? m.box_const : __ldg(m.cell_box + c);
+            hb[q] = (SPEC || m.box_uniform) ? m.box_const : __ldg(m.cell_box + c);
         }
         if (vec && full) {
             const uint4 tk = __ldg(reinterpret_cast<const uint4 *>(m.tile_key + c0));
@@ -438,13 +441,13 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
             } else ++n_over[q];
         };
         auto test32 = [&](int q, float4 e0, float4 e1) {     // see k_classify
-            const bool k3 = __float_as_int(e1.z) == KIND_3D;
+            const bool k3 = SPEC || __float_as_int(e1.z) == KIND_3D;
             const float ax = fabsf(p[q].x - e0.x), ay = fabsf(p[q].y - e0.y), az = k3 ? fabsf(p[q].z - e0.z) : 0.f;
             const float hz = k3 ? hb[q].z : 0.f;
             const float fx = ax + hb[q].x, fy = ay + hb[q].y, fz = az + hz;
             float nx = ax - hb[q].x, ny = ay - hb[q].y, nz = az - hz;
-            if (hb[q].w == 0.f) { nx = fmaxf(nx, 0.f); ny = fmaxf(ny, 0.f); nz = fmaxf(nz, 0.f); }
-            const float N2 = nx * nx + ny * ny + nz * nz, F2 = fx * fx + fy * fy + fz * fz;
+            if (!SPEC && hb[q].w == 0.f) { nx = fmaxf(nx, 0.f); ny = fmaxf(ny, 0.f); nz = fmaxf(nz, 0.f); }
+            const float N2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx)), F2 = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
             const float ro = e0.w, ri = e1.x;
             return (N2 > ro * ro) ? 0 : ((ri > 0.f && F2 < ri * ri) ? 1 : 2);
         };

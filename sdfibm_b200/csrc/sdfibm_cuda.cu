@@ -1697,7 +1697,9 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         // variants: with / without the global-list merge (planes, tilted 2-D solids) and the fp32 corner refinement (shape tables
         // holding ellipsoids, boxes, ellipses, rectangles); the plain one runs at 32 registers / full occupancy
         if (ctx->classify4 && !ctx->n_global_hint && !ctx->shapes_refinable) {   // the plain variant: four consecutive positions per thread
-            k_classify4<CLS4_NT, CLS4_MINB><<<grid_for(p1 - p0, 4 * CLS4_NT), CLS4_NT, 0, st>>>(I);
+            const bool spec = !ctx->shapes_may_be_global && ctx->dm.box_uniform && ctx->dm.box_const.w != 0.f;   // 3-D shapes on identical box cells
+            if (spec) k_classify4<CLS4_NT, CLS4_MINB, true><<<grid_for(p1 - p0, 4 * CLS4_NT), CLS4_NT, 0, st>>>(I);
+            else k_classify4<CLS4_NT, CLS4_MINB, false><<<grid_for(p1 - p0, 4 * CLS4_NT), CLS4_NT, 0, st>>>(I);
             return;
         }
         constexpr int CM = 256 / CLS_NT;   // resident CTAs scale with the CTA size: the same threads per SM

@@ -24,7 +24,10 @@ def _rd(x):
     y = f32(x)
     return np.nextafter(y, f32(-np.inf)) if float(y) > x else y
 REL = 1e-6
-def _run(seed):
+def _fma(a, b, c):
+    """fmaf: the product is exact in float64, the sum rounds once more than the device's (a difference far below the slack)"""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+def _run(seed, fma=False):
     rng = np.random.RandomState(seed)
     n = tuple(int(x) for x in rng.randint(5, 14, size=3)); h = float(rng.choice([0.1, 0.25, 1.0, 0.3]))
     x0 = tuple(float(x) for x in rng.choice([0.0, -1.0, 0.37, 100.3], size=3))
@@ -62,8 +65,12 @@ def _run(seed):
         a = np.abs(p - e)                                     # float32 ops
         fx = a + hb
         nx = a - hb
-        N2 = nx[:, 0] * nx[:, 0] + nx[:, 1] * nx[:, 1] + nx[:, 2] * nx[:, 2]
-        F2 = fx[:, 0] * fx[:, 0] + fx[:, 1] * fx[:, 1] + fx[:, 2] * fx[:, 2]
+        if fma:     # k_classify4<., ., SPEC>: fmaf(nz, nz, fmaf(ny, ny, nx * nx))
+            N2 = _fma(nx[:, 2], nx[:, 2], _fma(nx[:, 1], nx[:, 1], nx[:, 0] * nx[:, 0]))
+            F2 = _fma(fx[:, 2], fx[:, 2], _fma(fx[:, 1], fx[:, 1], fx[:, 0] * fx[:, 0]))
+        else:
+            N2 = nx[:, 0] * nx[:, 0] + nx[:, 1] * nx[:, 1] + nx[:, 2] * nx[:, 2]
+            F2 = fx[:, 0] * fx[:, 0] + fx[:, 1] * fx[:, 1] + fx[:, 2] * fx[:, 2]
         cls = np.where(N2 > ro * ro, 0, np.where((ri > 0) & (F2 < ri * ri), 1, 2))
         viol += int(((cls == 0) & (n_in > 0)).sum() + ((cls == 1) & (n_in < 8)).sum())
         # how sharp is it: undecided cells that are in fact all-out or all-in
@@ -73,12 +80,13 @@ def _run(seed):
 
 
 def test_fp32_three_way_test_is_conservative_and_sharp():
-    V = D = T = 0
-    for seed in range(60):
-        v, d, t = _run(seed)
-        V, D, T = V + v, D + d, T + t
-    assert V == 0
-    assert T > 20000 and D < 0.03 * T
+    for fma in (False, True):      # k_classify's separate multiplies and adds; k_classify4's fmaf chain
+        V = D = T = 0
+        for seed in range(60):
+            v, d, t = _run(seed, fma)
+            V, D, T = V + v, D + d, T + t
+        assert V == 0
+        assert T > 20000 and D < 0.03 * T
 
 
 # ---- refine32: boxes and ellipsoids --------------------------------------------------------------------------------------------
