@@ -451,7 +451,33 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
             const float ro = e0.w, ri = e1.x;
             return (N2 > ro * ro) ? 0 : ((ri > 0.f && F2 < ri * ri) ? 1 : 2);
         };
-        if (t[1] == t[0] && t[2] == t[0] && t[3] == t[0]) {
+        // SPEC: the four positions of a thread are normally four consecutive cells of one mesh line (tiles keep the caller's order
+        // inside, x fastest): their y and z offsets to a candidate — and the partial sums of squares they feed — are taken once
+        const bool line = SPEC && p[1].y == p[0].y && p[2].y == p[0].y && p[3].y == p[0].y && p[1].z == p[0].z && p[2].z == p[0].z && p[3].z == p[0].z;
+        if (line && t[1] == t[0] && t[2] == t[0] && t[3] == t[0]) {
+            int bi = __ldg(P.bin_off + t[0]);
+            const int be = __ldg(P.bin_off + t[0] + 1);
+            const float4 h = m.box_const;
+            for (; bi < be; ++bi) {
+                const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
+                const int s = __float_as_int(e1.y);
+                const float ay = fabsf(p[0].y - e0.y), az = fabsf(p[0].z - e0.z);
+                const float fy = ay + h.y, fz = az + h.z, ny = ay - h.y, nz = az - h.z;
+                const float Nyz = fmaf(nz, nz, ny * ny), Fyz = fmaf(fz, fz, fy * fy);
+                const float ro2 = e0.w * e0.w, ri2 = e1.x * e1.x;
+                const bool has_in = e1.x > 0.f;
+                int qc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float ax = fabsf(p[q].x - e0.x);
+                    const float fx = ax + h.x, nx = ax - h.x;
+                    const float N2 = fmaf(nx, nx, Nyz), F2 = fmaf(fx, fx, Fyz);
+                    qc[q] = (N2 > ro2) ? 0 : ((has_in && F2 < ri2) ? 1 : 2);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q]);
+            }
+        } else if (t[1] == t[0] && t[2] == t[0] && t[3] == t[0]) {
             int bi = __ldg(P.bin_off + t[0]);
             const int be = __ldg(P.bin_off + t[0] + 1);
 #if CLS4_PREFETCH
@@ -830,7 +856,7 @@ __global__ void __launch_bounds__(TPB, CTAS) k_heavy_hex(InteractParams P) {
 #define BOX_EUNROLL 4
 #endif
 #ifndef BOX_FUNROLL
-#define BOX_FUNROLL 2
+#define BOX_FUNROLL 2   // C4 k_heavy_box after the edge compaction: 0.378 (1) / 0.352 (2) / 0.372 (3) / 0.347 ms (6); C5 at 256^3 (mixed shapes): 0.597 (2) / 0.638 (6)
 #endif
 #define PRAGMA_UNROLL_(n) _Pragma(#n)
 #define PRAGMA_UNROLL(n) PRAGMA_UNROLL_(unroll n)
@@ -1106,7 +1132,7 @@ __device__ __forceinline__ void final_cell(const InteractParams &P, int c, bool 
         if (n > 0) {
             cc = ld3(m.cc, c);
             uf = ld3(P.U, oc);
-            vol = __ldg(m.V + c);
+            vol = m.V_uniform ? m.V_const : __ldg(m.V + c);
         }
         for (int j = 0; j < nmax; ++j) {
             bool have = false;

@@ -108,6 +108,8 @@ struct DevMesh {
     const float4 *cell_box;   // per position (nullptr when box_uniform)
     float4 box_const;         // the one box of a uniform mesh
     int box_uniform;
+    int V_uniform;            // every cell has bit for bit the same volume: k_final takes V_const instead of 8 bytes per touched cell
+    double V_const;
     // the mesh is a complete nx x ny x nz lattice of identical boxes whose lattice neighbours are all face neighbours: for such a
     // mesh the vertex-inside cell set of a ball that lies inside the mesh is provably face connected (see k_solid_prepare)
     int lattice_full;
@@ -360,6 +362,11 @@ __global__ void k_cell_radius(DevMesh m, float2 *rad, int *bad, float *rmax) {
 
 // per-cell half extents of the vertex cloud + "is an axis-aligned box" flag; ext[0..2] = max, ext[3..5] = min over the mesh
 // (as int bits of non-negative floats), ext[6] = number of non-box cells
+__global__ void k_v_uniform(const double *V, int n_cells, int *differs) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cells && __double_as_longlong(V[c]) != __double_as_longlong(V[0])) *differs = 1;
+}
+
 __global__ void k_cell_box(DevMesh m, float4 *box, int *ext) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m.n_cells) return;
@@ -1359,6 +1366,21 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
     CUDA_TRY(ctx->nb6.ensure(6 * nC));
     d.nb6 = ctx->nb6.p;
     k_nb6<<<grid_for(nC, 256), 256, 0, st>>>(d, ctx->nb6.p);
+    {
+        // identical cell volumes (uniform lattices): one constant
+        DevBuf<int> differs;
+        CUDA_TRY(differs.ensure(1));
+        CUDA_TRY(cudaMemsetAsync(differs.p, 0, sizeof(int), st));
+        k_v_uniform<<<grid_for(nC, 256), 256, 0, st>>>(d.V, (int)nC, differs.p);
+        int h_differs = 1;
+        double h_v0 = 0.0;
+        CUDA_TRY(cudaMemcpyAsync(&h_differs, differs.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&h_v0, d.V, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        differs.release();
+        d.V_uniform = h_differs ? 0 : 1;
+        d.V_const = h_v0;
+    }
     {
         // cell boxes; a mesh of identical boxes keeps one constant instead of 16 bytes per cell
         DevBuf<int> ext;

@@ -65,7 +65,10 @@ def _run(seed, fma=False):
         a = np.abs(p - e)                                     # float32 ops
         fx = a + hb
         nx = a - hb
-        if fma:     # k_classify4<., ., SPEC>: fmaf(nz, nz, fmaf(ny, ny, nx * nx))
+        if fma == 2:   # k_classify4<., ., SPEC>, four cells of one mesh line: fmaf(nx, nx, fmaf(nz, nz, ny * ny))
+            N2 = _fma(nx[:, 0], nx[:, 0], _fma(nx[:, 2], nx[:, 2], nx[:, 1] * nx[:, 1]))
+            F2 = _fma(fx[:, 0], fx[:, 0], _fma(fx[:, 2], fx[:, 2], fx[:, 1] * fx[:, 1]))
+        elif fma:     # k_classify4<., ., SPEC>, general: fmaf(nz, nz, fmaf(ny, ny, nx * nx))
             N2 = _fma(nx[:, 2], nx[:, 2], _fma(nx[:, 1], nx[:, 1], nx[:, 0] * nx[:, 0]))
             F2 = _fma(fx[:, 2], fx[:, 2], _fma(fx[:, 1], fx[:, 1], fx[:, 0] * fx[:, 0]))
         else:
@@ -80,7 +83,7 @@ def _run(seed, fma=False):
 
 
 def test_fp32_three_way_test_is_conservative_and_sharp():
-    for fma in (False, True):      # k_classify's separate multiplies and adds; k_classify4's fmaf chain
+    for fma in (0, 1, 2):      # k_classify's separate multiplies and adds; k_classify4's two fmaf chains
         V = D = T = 0
         for seed in range(60):
             v, d, t = _run(seed, fma)
