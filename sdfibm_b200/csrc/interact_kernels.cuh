@@ -398,10 +398,41 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
 // 0.225 -> 0.18 ms; with the refinement / global-list code in the loop the register count halves the occupancy and the
 // one-position kernel stays faster, so those variants keep it.
 // ------------------------------------------------------------------------------------------------
+// k_classify's fp32 corner refinement (the same operation sequence) as a function of its own: k_classify4 calls it out of line, once
+// per undecided (cell, refinable solid) pair, so that its registers are not paid four times over in the candidate loop.
+__device__ __noinline__ int refine32_pair(const DevSolid &S, float4 p, float4 hb, int mode) {
+    const bool k3 = S.kind == KIND_3D;
+    const float dx = p.x - S.pos32[0], dy = p.y - S.pos32[1], dz = p.z - S.pos32[2];
+    const float hz = k3 ? hb.z : 0.f;
+    float gmax = -3.0e38f, gmin = 3.0e38f;
+    float bc[3], ex[3], ey[3], ez[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        bc[i] = S.M[3 * i] * dx + S.M[3 * i + 1] * dy + S.M[3 * i + 2] * dz + S.com32[i];
+        ex[i] = S.M[3 * i] * hb.x; ey[i] = S.M[3 * i + 1] * hb.y; ez[i] = S.M[3 * i + 2] * hz;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float g = (mode == 1) ? -1.f : -3.0e38f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float b = bc[i] + ((k & 1) ? ex[i] : -ex[i]) + ((k & 2) ? ey[i] : -ey[i]) + ((k & 4) ? ez[i] : -ez[i]);
+            if (mode == 1) { const float t = b * S.rp[i]; g += t * t; }
+            else g = fmaxf(g, fabsf(b) - S.rp[i]);
+        }
+        gmax = fmaxf(gmax, g);
+        gmin = fminf(gmin, g);
+    }
+    const float eps = S.eps_ref;
+    if (gmax < -eps) return 1;
+    if (hb.w != 0.f && gmin > ((mode == 1) ? 4.f * eps : eps)) return 0;
+    return 2;
+}
+
 // SPEC: every shape of the table is 3-D and every cell is the same axis-aligned box (C4, C5): the 2-D / 3-D selects and the clamp of
 // the near-corner offsets drop out of the test.  The two sums of squares use explicit fmaf (one rounding less per term; the 4e-6
 // relative slack of the radii covers either rounding sequence — tests/test_classify_bounds_cpu.py runs both).
-template <int NT, int MINB, bool SPEC>
+template <int NT, int MINB, bool SPEC, bool REFINE>
 __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
@@ -474,6 +505,10 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
                     const float N2 = fmaf(nx, nx, Nyz), F2 = fmaf(fx, fx, Fyz);
                     qc[q] = (N2 > ro2) ? 0 : ((has_in && F2 < ri2) ? 1 : 2);
                 }
+                if (REFINE && __float_as_int(e1.w) != 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (qc[q] == 2) qc[q] = refine32_pair(P.solids[s], p[q], hb[q], __float_as_int(e1.w));
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q]);
             }
@@ -495,6 +530,10 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
                 int qc[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) qc[q] = test32(q, e0, e1);
+                if (REFINE && __float_as_int(e1.w) != 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (qc[q] == 2) qc[q] = refine32_pair(P.solids[s], p[q], hb[q], __float_as_int(e1.w));
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q]);
 #if CLS4_PREFETCH
@@ -509,7 +548,9 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
                 const int be = __ldg(P.bin_off + t[q] + 1);
                 for (; bi < be; ++bi) {
                     const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
-                    emit(q, __float_as_int(e1.y), test32(q, e0, e1));
+                    int qc1 = test32(q, e0, e1);
+                    if (REFINE && qc1 == 2 && __float_as_int(e1.w) != 0) qc1 = refine32_pair(P.solids[__float_as_int(e1.y)], p[q], hb[q], __float_as_int(e1.w));
+                    emit(q, __float_as_int(e1.y), qc1);
                 }
             }
         }

@@ -891,6 +891,7 @@ struct sdfibm_context {
     GraphKey graph_key = {0};
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
+    int classify4_refine = 1;            // SDFIBM_CLASSIFY4_REFINE=0: refinable shape tables keep the one-position kernel
     bool classify4 = true;               // k_classify4 (four positions per thread); SDFIBM_CLASSIFY4=0: the one-position kernel
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
@@ -1720,10 +1721,16 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         const int grid = grid_for(p1 - p0, 256);
         // variants: with / without the global-list merge (planes, tilted 2-D solids) and the fp32 corner refinement (shape tables
         // holding ellipsoids, boxes, ellipses, rectangles); the plain one runs at 32 registers / full occupancy
-        if (ctx->classify4 && !ctx->n_global_hint && !ctx->shapes_refinable) {   // the plain variant: four consecutive positions per thread
+        if (ctx->classify4 && !ctx->n_global_hint) {   // no plane / tilted 2-D solid about: four consecutive positions per thread
             const bool spec = !ctx->shapes_may_be_global && ctx->dm.box_uniform && ctx->dm.box_const.w != 0.f;   // 3-D shapes on identical box cells
-            if (spec) k_classify4<CLS4_NT, CLS4_MINB, true><<<grid_for(p1 - p0, 4 * CLS4_NT), CLS4_NT, 0, st>>>(I);
-            else k_classify4<CLS4_NT, CLS4_MINB, false><<<grid_for(p1 - p0, 4 * CLS4_NT), CLS4_NT, 0, st>>>(I);
+            const int g4 = grid_for(p1 - p0, 4 * CLS4_NT);
+            if (ctx->shapes_refinable) {
+                if (spec) k_classify4<CLS4_NT, CLS4_MINB, true, true><<<g4, CLS4_NT, 0, st>>>(I);
+                else k_classify4<CLS4_NT, CLS4_MINB, false, true><<<g4, CLS4_NT, 0, st>>>(I);
+            } else {
+                if (spec) k_classify4<CLS4_NT, CLS4_MINB, true, false><<<g4, CLS4_NT, 0, st>>>(I);
+                else k_classify4<CLS4_NT, CLS4_MINB, false, false><<<g4, CLS4_NT, 0, st>>>(I);
+            }
             return;
         }
         constexpr int CM = 256 / CLS_NT;   // resident CTAs scale with the CTA size: the same threads per SM
