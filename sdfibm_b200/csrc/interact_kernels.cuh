@@ -27,6 +27,7 @@
 #define CLS4_MINB 16
 #endif
 #define SLOT_HEAVY 4
+#define BIN_FIXED_CAP 8   // list slots per tile in the fixed-capacity binning mode (a tile with more candidates switches the context to scan + fill)
 
 // ------------------------------------------------------------------------------------------------
 // geometry: apex / pyramid volume fraction (reference src/geometrictools.cpp:13-116)
@@ -150,6 +151,8 @@ struct InteractParams {
     const sdfibm_sdf_op_t *ops;   // op table of the SDFIBM_SHAPE_PROGRAM records (null: none)
     int n_solids;
     BinGrid grid;
+    int bin_fixed;               // 1: tile t owns the slots [t * BIN_FIXED_CAP, +min(bin_count[t], BIN_FIXED_CAP)); 0: CSR (bin_off)
+    const int *bin_count;
     const int *bin_off;
     const int *bin_list;
     const BinEntry *bin_entries; // bin_list materialised after the per-bin sort
@@ -173,6 +176,17 @@ struct InteractParams {
     int cls_begin, cls_end; // k_classify: position range of this launch (the host-buffer path works slab by slab)
     const unsigned long long *heavy_start;   // k_heavy: [0] first front-queue index, [1] first back-queue item of this launch (nullptr: 0)
 };
+
+// candidate records of tile t: [bi, be) in bin_entries
+__device__ __forceinline__ void bin_range(const InteractParams &P, unsigned t, int &bi, int &be) {
+    if (P.bin_fixed) {
+        bi = (int)t * BIN_FIXED_CAP;
+        be = bi + min(__ldg(P.bin_count + t), BIN_FIXED_CAP);
+    } else {
+        bi = __ldg(P.bin_off + t);
+        be = __ldg(P.bin_off + t + 1);
+    }
+}
 
 __device__ __forceinline__ float2 cell_radius(const DevMesh &m, int c) { return m.rad_uniform ? m.rad_const : __ldg(m.cell_rad + c); }
 
@@ -257,8 +271,8 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
     if (live) {
         const float4 p = __ldg(m.cc32 + c);
         const unsigned t = __ldg(m.tile_key + c);
-        int bi = __ldg(P.bin_off + t);
-        const int be = __ldg(P.bin_off + t + 1);
+        int bi, be;
+        bin_range(P, t, bi, be);
         const float4 *E = reinterpret_cast<const float4 *>(P.bin_entries);
         // one pre-classified candidate -> slot record
         int n_over = 0;
@@ -486,8 +500,8 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
         // inside, x fastest): their y and z offsets to a candidate — and the partial sums of squares they feed — are taken once
         const bool line = SPEC && p[1].y == p[0].y && p[2].y == p[0].y && p[3].y == p[0].y && p[1].z == p[0].z && p[2].z == p[0].z && p[3].z == p[0].z;
         if (line && t[1] == t[0] && t[2] == t[0] && t[3] == t[0]) {
-            int bi = __ldg(P.bin_off + t[0]);
-            const int be = __ldg(P.bin_off + t[0] + 1);
+            int bi, be;
+            bin_range(P, t[0], bi, be);
             const float4 h = m.box_const;
             for (; bi < be; ++bi) {
                 const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
@@ -513,8 +527,8 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
                 for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q]);
             }
         } else if (t[1] == t[0] && t[2] == t[0] && t[3] == t[0]) {
-            int bi = __ldg(P.bin_off + t[0]);
-            const int be = __ldg(P.bin_off + t[0] + 1);
+            int bi, be;
+            bin_range(P, t[0], bi, be);
 #if CLS4_PREFETCH
             float4 e0 = {0.f, 0.f, 0.f, 0.f}, e1 = e0;
             if (bi < be) { e0 = __ldg(E + 2 * (long long)bi); e1 = __ldg(E + 2 * (long long)bi + 1); }
@@ -544,8 +558,8 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (c0 + q >= P.cls_end) continue;
-                int bi = __ldg(P.bin_off + t[q]);
-                const int be = __ldg(P.bin_off + t[q] + 1);
+                int bi, be;
+                bin_range(P, t[q], bi, be);
                 for (; bi < be; ++bi) {
                     const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
                     int qc1 = test32(q, e0, e1);

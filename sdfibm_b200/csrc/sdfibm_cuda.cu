@@ -493,6 +493,8 @@ struct PrepParams {
     int *bin_count;   // [n_bins+1]
     int *global_list; // [n_solids]
     StepStatus *status;
+    int fixed_cap;    // > 0: every tile owns fixed_cap list slots (no scan, no separate fill pass): the solid is appended right here
+    int *bin_list;    // [n_bins * fixed_cap] in that mode
 };
 
 // SUB threads per solid share the loop over the bins its bounding box covers
@@ -588,7 +590,12 @@ __global__ void k_solid_prepare(PrepParams P) {
     const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
     for (int t = sub; t < nx * ny * nz; t += BIN_SUB) {
         const int i = lo[0] + t % nx, j = lo[1] + (t / nx) % ny, k = lo[2] + t / (nx * ny);
-        atomicAdd(&P.bin_count[(k * P.grid.n[1] + j) * P.grid.n[0] + i], 1);
+        const int b = (k * P.grid.n[1] + j) * P.grid.n[0] + i;
+        const int pos = atomicAdd(&P.bin_count[b], 1);
+        if (P.fixed_cap) {
+            if (pos < P.fixed_cap) P.bin_list[(long long)b * P.fixed_cap + pos] = s;
+            else P.status->bin_overflow = 2;   // a tile with more candidates than slots: the host falls back to the scan + fill path
+        }
     }
 }
 
@@ -643,10 +650,58 @@ __device__ __forceinline__ void bin_insertion_sort(int *lst, int beg, int end) {
 // Thread per bin: sort the bin's solids by id, then write the inline fp32 candidate records k_classify reads.  The radii carry
 // the fp32 slack: coordinates relative to the mesh origin are bounded by M = half extent + r_out + rad, so the fp32 distance is
 // off by < 1e-6 M; slack = 4e-6 M keeps the three-way test conservative (the exact fp64 predicates decide everything it does not).
+__device__ __forceinline__ BinEntry make_bin_entry(const DevSolid &S, int s, double ox, double oy, double oz, double half_ext, double rad_max) {
+    const double slack = 4e-6 * (half_ext + S.r_out + rad_max);
+    BinEntry e;
+    e.x = (float)(S.pos[0] - ox); e.y = (float)(S.pos[1] - oy); e.z = (float)(S.pos[2] - oz);
+    e.r_out = __double2float_ru(S.r_out + slack);
+    e.r_in = __double2float_rd(S.r_in - slack);
+    e.s = s;
+    e.kind = S.kind;
+    e.refine = S.refine;
+    return e;
+}
+
 __global__ void k_bin_sort_entries(const int *bin_off, int *bin_list, int n_bins, int bin_cap, int *global_list, StepStatus *status,
                                    const DevSolid *solids, BinEntry *out, double ox, double oy, double oz, double half_ext, double rad_max,
-                                   unsigned char *tile_proven) {
+                                   unsigned char *tile_proven, int fixed_cap, const int *bin_count) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fixed_cap) {
+        // every tile owns BIN_FIXED_CAP slots: ids to registers, sorted there, records written behind the tile's first slot
+        int cnt = 0;
+        if (b < n_bins) {
+            cnt = bin_count[b];
+            const int n = min(cnt, BIN_FIXED_CAP);
+            int ids[BIN_FIXED_CAP];
+#pragma unroll
+            for (int i = 0; i < BIN_FIXED_CAP; ++i) ids[i] = i < n ? bin_list[(long long)b * BIN_FIXED_CAP + i] : 0x7fffffff;
+#pragma unroll
+            for (int i = 1; i < BIN_FIXED_CAP; ++i) {
+#pragma unroll
+                for (int j = i; j > 0; --j) {
+                    const int lo = min(ids[j - 1], ids[j]), hi = max(ids[j - 1], ids[j]);
+                    ids[j - 1] = lo; ids[j] = hi;
+                }
+            }
+            int proven = 1;
+#pragma unroll
+            for (int i = 0; i < BIN_FIXED_CAP; ++i) {
+                if (i < n) {
+                    const DevSolid &S = solids[ids[i]];
+                    proven &= S.conn_proven;
+                    out[(long long)b * BIN_FIXED_CAP + i] = make_bin_entry(S, ids[i], ox, oy, oz, half_ext, rad_max);
+                }
+            }
+            if (!proven) status->need_cert = 1;
+            tile_proven[b] = (unsigned char)proven;
+        } else if (b == n_bins) bin_insertion_sort(global_list, 0, status->n_global);
+        // the true total (also of the entries that found no slot): sizes the scan + fill path if it has to take over
+        unsigned tot = (unsigned)cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&status->bin_total, (int)tot);
+        return;
+    }
     if (b == n_bins) { bin_insertion_sort(global_list, 0, status->n_global); status->bin_total = bin_off[n_bins]; return; }
     if (b > n_bins) return;
     const int beg = bin_off[b], end = bin_off[b + 1];
@@ -658,15 +713,7 @@ __global__ void k_bin_sort_entries(const int *bin_off, int *bin_list, int n_bins
         const DevSolid &S = solids[s];
         proven &= S.conn_proven;
         if (!S.conn_proven) status->need_cert = 1;
-        const double slack = 4e-6 * (half_ext + S.r_out + rad_max);
-        BinEntry e;
-        e.x = (float)(S.pos[0] - ox); e.y = (float)(S.pos[1] - oy); e.z = (float)(S.pos[2] - oz);
-        e.r_out = __double2float_ru(S.r_out + slack);
-        e.r_in = __double2float_rd(S.r_in - slack);
-        e.s = s;
-        e.kind = S.kind;
-        e.refine = S.refine;
-        out[pos] = e;
+        out[pos] = make_bin_entry(S, s, ox, oy, oz, half_ext, rad_max);
     }
     tile_proven[b] = (unsigned char)proven;
 }
@@ -892,6 +939,8 @@ struct sdfibm_context {
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
     int classify4_refine = 1;            // SDFIBM_CLASSIFY4_REFINE=0: refinable shape tables keep the one-position kernel
+    bool bin_fixed = false;              // tile bins with BIN_FIXED_CAP slots each (set per mesh; a tile that overflows switches the context to scan + fill)
+    bool bin_fixed_allowed = true;       // SDFIBM_BIN_FIXED=0
     bool classify4 = true;               // k_classify4 (four positions per thread); SDFIBM_CLASSIFY4=0: the one-position kernel
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
@@ -1056,6 +1105,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_CLASSIFY4")) ctx->classify4 = atoi(e) != 0;
+    if (const char *e = getenv("SDFIBM_BIN_FIXED")) ctx->bin_fixed_allowed = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_BOX")) ctx->allow_box = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_ALLOW_ORDER_FREE")) ctx->allow_order_free = atoi(e) != 0;
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
@@ -1206,6 +1256,8 @@ int sdfibm_set_mesh(sdfibm_context *ctx, const sdfibm_mesh_t *m, int two_d) {
             g.n_bins *= g.n[k];
             ctx->half_ext = std::max(ctx->half_ext, 0.5 * ext[k]);
         }
+        // fixed-capacity tile bins (40 bytes per slot: id + record) as long as they stay below 1 GiB
+        ctx->bin_fixed = ctx->bin_fixed_allowed && (double)g.n_bins * BIN_FIXED_CAP * 40.0 <= 1073741824.0;
     }
     DevMesh &d = ctx->dm;
     for (int k = 0; k < 3; ++k) d.origin[k] = 0.5 * (m->bounds_min[k] + m->bounds_max[k]);
@@ -1684,20 +1736,26 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         P.lattice_full = ctx->dm.lattice_full;
         P.box_h[0] = ctx->dm.box_const.x; P.box_h[1] = ctx->dm.box_const.y; P.box_h[2] = ctx->dm.box_const.z;
         P.bin_count = ctx->bin_count; P.global_list = ctx->global_list.p; P.status = ctx->status;
+        P.fixed_cap = ctx->bin_fixed ? BIN_FIXED_CAP : 0; P.bin_list = ctx->bin_list.p;
         k_solid_prepare<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(P);
-        size_t tmp_bytes = ctx->scan_tmp.n;
-        cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, ctx->bin_count, ctx->bin_off.p, g.n_bins + 1, st);
-        FillParams F;
-        F.solids = ctx->solids.p; F.n_solids = n_solids; F.grid = g; F.rad3_max = ctx->rad3_max; F.radxy_max = ctx->radxy_max;
-        for (int d = 0; d < 3; ++d) { F.mesh_lo[d] = ctx->bmin[d]; F.mesh_hi[d] = ctx->bmax[d]; }
-        F.bin_off = ctx->bin_off.p; F.bin_cursor = ctx->bin_cursor; F.bin_list = ctx->bin_list.p;
-        F.bin_cap = (int)std::min<size_t>(ctx->bin_list.n, 0x7fffffff); F.status = ctx->status;
-        k_bin_fill<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(F);
+        const int bin_cap_i = (int)std::min<size_t>(ctx->bin_list.n, 0x7fffffff);
+        if (!ctx->bin_fixed) {
+            // scan + fill: a CSR list of exactly the size the step needs (the fallback when some tile has more candidates than slots)
+            size_t tmp_bytes = ctx->scan_tmp.n;
+            cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, ctx->bin_count, ctx->bin_off.p, g.n_bins + 1, st);
+            FillParams F;
+            F.solids = ctx->solids.p; F.n_solids = n_solids; F.grid = g; F.rad3_max = ctx->rad3_max; F.radxy_max = ctx->radxy_max;
+            for (int d = 0; d < 3; ++d) { F.mesh_lo[d] = ctx->bmin[d]; F.mesh_hi[d] = ctx->bmax[d]; }
+            F.bin_off = ctx->bin_off.p; F.bin_cursor = ctx->bin_cursor; F.bin_list = ctx->bin_list.p;
+            F.bin_cap = bin_cap_i; F.status = ctx->status;
+            k_bin_fill<<<grid_for((long long)n_solids * BIN_SUB, 128), 128, 0, st>>>(F);
+            ctx->launches += 2;
+        }
         k_bin_sort_entries<<<grid_for((long long)g.n_bins + 1, 128), 128, 0, st>>>(
-            ctx->bin_off.p, ctx->bin_list.p, g.n_bins, F.bin_cap, ctx->global_list.p, ctx->status, ctx->solids.p, ctx->bin_entries.p,
+            ctx->bin_off.p, ctx->bin_list.p, g.n_bins, bin_cap_i, ctx->global_list.p, ctx->status, ctx->solids.p, ctx->bin_entries.p,
             ctx->dm.origin[0], ctx->dm.origin[1], ctx->dm.origin[2], ctx->half_ext, (double)std::max(ctx->rad3_max, ctx->radxy_max),
-            ctx->tile_proven.p);
-        ctx->launches += 4;
+            ctx->tile_proven.p, ctx->bin_fixed ? BIN_FIXED_CAP : 0, ctx->bin_count);
+        ctx->launches += 2;
     } else {
         // keep the binning of the first pass; restore the counters the status word carries
         CUDA_TRY(cudaMemsetAsync(ctx->root_count, 0, sizeof(int) * n_solids, st));
@@ -1710,6 +1768,7 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     }
     InteractParams I;
     I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.ops = ctx->h_ops.empty() ? nullptr : ctx->sdf_ops.p; I.n_solids = n_solids; I.grid = g;
+    I.bin_fixed = ctx->bin_fixed ? 1 : 0; I.bin_count = ctx->bin_count;
     I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.bin_entries = ctx->bin_entries.p; I.global_list = ctx->global_list.p; I.U = dU;
     I.scal = ctx->scal.p; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
     I.pair_counts = ctx->pair_counts; I.slots = ctx->slots.p; I.K = ctx->K;
@@ -1861,7 +1920,8 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
         CUDA_TRY(ctx->bin_off.ensure((size_t)g.n_bins + 1));
         CUDA_TRY(ctx->tile_proven.ensure((size_t)g.n_bins + 1));
         CUDA_TRY(ctx->global_list.ensure(n_solids));
-        if (ctx->bin_list.n == 0) CUDA_TRY(ctx->bin_list.ensure(std::max<size_t>(1 << 20, 128 * (size_t)n_solids)));
+        if (ctx->bin_fixed) CUDA_TRY(ctx->bin_list.ensure((size_t)g.n_bins * BIN_FIXED_CAP));
+        else if (ctx->bin_list.n == 0) CUDA_TRY(ctx->bin_list.ensure(std::max<size_t>(1 << 20, 128 * (size_t)n_solids)));
         // one zero-initialised block: [StepStatus | root_count n | pair_counts 3n | bin_count n_bins+1 | bin_cursor n_bins]
         const size_t o_root = (sizeof(StepStatus) + 15) & ~size_t(15);
         const size_t o_pair = o_root + ((sizeof(int) * (size_t)n_solids + 15) & ~size_t(15));
@@ -1897,7 +1957,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
                                       (uint64_t)(ctx->ext_solids ? ctx->ext_solids : (ctx->gathered_now ? ctx->solids_gathered.p : ctx->solids_in.p)), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
                                       (uint64_t)ctx->shapes.p ^ ((uint64_t)ctx->sdf_ops.p << 2), (uint64_t)ctx->scan_tmp.p ^ ((uint64_t)ctx->tile_proven.p << 1), (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
-                                      (uint64_t)ctx->n_global_hint};
+                                      (uint64_t)ctx->n_global_hint ^ ((uint64_t)ctx->bin_fixed << 8)};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
                 cudaGraph_t graph = nullptr;
@@ -1962,6 +2022,7 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             again = true;
         }
         if (ctx->last.bin_overflow && !replay) {
+            if (ctx->bin_fixed) { ctx->bin_fixed = false; drop_graph(ctx); }   // a tile with more candidates than slots: scan + fill from now on
             CUDA_TRY(ctx->bin_list.ensure((size_t)ctx->last.bin_total + (size_t)ctx->last.bin_total / 4 + 1024));
             again = true;
         }

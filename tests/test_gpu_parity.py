@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): candidate lists and collision pair sets bit-exact; As / Fs (and Ts, Ct)
 within 1e-12 relative; per-solid force / torque within 1e-10 relative to the sum of |terms|.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -357,6 +359,27 @@ def test_slot_overflow_widens_the_records_and_runs_again():
     check_parity(case, o, ref, ctx, got)
     again = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])   # the widened records stay
     assert np.array_equal(again["As"], got["As"]) and np.array_equal(again["Ct"], got["Ct"])
+
+
+def test_more_candidates_than_tile_slots_switches_to_scan_and_fill():
+    """The default binning gives every tile a fixed number of list slots (BIN_FIXED_CAP = 8: no scan, no fill pass).  A tile that 14
+    solids reach does not fit: the step is run again with the scan + fill lists (sized exactly), and stays on them."""
+    case = cases.case_c4(n=24, n_solids=14, n_side=3)
+    rng = np.random.RandomState(11)
+    case["solids"]["pos"][:] = (9.0, 10.0, 11.0) + rng.uniform(-2.5, 2.5, size=(14, 3))     # all within one 8 x 8 x 4 tile's reach
+    o, ref, ctx, got = run_both(case, cell_slots=16)
+    check_parity(case, o, ref, ctx, got)
+    assert ctx.last_stats()["bin_entries"] >= 14 * 8       # every solid reaches several tiles; the count is the true total
+    again = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
+    assert np.array_equal(again["As"], got["As"]) and np.array_equal(again["Ct"], got["Ct"])
+    # the same step on a context that never used the fixed slots
+    os.environ["SDFIBM_BIN_FIXED"] = "0"
+    try:
+        _, _, ctx2, got2 = run_both(case, cell_slots=16)
+    finally:
+        del os.environ["SDFIBM_BIN_FIXED"]
+    assert np.array_equal(got2["As"], got["As"]) and np.array_equal(got2["Ct"], got["Ct"]) and np.array_equal(got2["Fs"], got["Fs"])
+    assert ctx2.last_stats()["bin_entries"] == ctx.last_stats()["bin_entries"]
 
 
 def test_collision_parity():
