@@ -2,7 +2,7 @@
 # round 2, evidence call: GPU suite, the contract bench line (C4, with the CPU baseline), the small configurations, C5 at 256^3, the aux
 # kernels, the ncu launch list and the ncu --set full capture of the three interact kernels — all on the committed tree
 set -u
-R=r02f
+R=r02g
 mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -m gpu -q -rxX > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${R}_pytest_gpu.log
 tail -6 gpurun_out/${R}_pytest_gpu.log
@@ -17,7 +17,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
 NCU_SKIP=3 NCU_COUNT=3 bash tools/gpu/ncu_full.sh ${R} "^(k_classify4|k_heavy_box|k_final)$"
 python - <<'PY'
 import glob, json
-for f in sorted(glob.glob("gpurun_out/r02f_bench_*.json")):
+for f in sorted(glob.glob("gpurun_out/r02g_bench_*.json")):
     try:
         d = json.loads([l for l in open(f) if l.startswith("{")][-1])
     except Exception as ex:
