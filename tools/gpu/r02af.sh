@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, call af: smoke(), C5 (512^3) on ONE GPU with the final kernels (the same-workload base of the 8-GPU line), extended randomised parity
+set -u
+R=r02af
+mkdir -p gpurun_out
+timeout 600 python __graft_entry__.py --smoke > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${R}_smoke.log
+timeout 1500 python bench.py --workload c5 --gpus 1 --steps 5 --warmup 3 --no-cpu --no-e2e --no-check > gpurun_out/${R}_bench_c5_n1.json 2> gpurun_out/${R}_bench_c5_n1.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d = json.loads([l for l in open("gpurun_out/r02af_bench_c5_n1.json") if l.startswith("{")][-1])
+k = d.get("kernel_ms", {})
+print("c5 n1 ms/step %.4g" % d["ms_per_step"], "value %.4g" % d["value"], {a[:12]: round(b, 4) for a, b in k.items() if isinstance(b, float)})
+PY
+timeout 1500 python tools/gpu_fuzz.py 700 120 1000 > gpurun_out/${R}_fuzz.json 2> gpurun_out/${R}_fuzz.err; echo "fuzz rc=$?"
+cut -c1-1500 gpurun_out/${R}_fuzz.json; tail -3 gpurun_out/${R}_fuzz.err | cut -c1-300
