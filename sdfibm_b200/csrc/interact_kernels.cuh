@@ -1339,7 +1339,14 @@ __global__ void __launch_bounds__(256) k_connectivity(ConnParams P) {
 __global__ void k_snapshot(const unsigned long long *a, const unsigned long long *b, unsigned long long *dst) { dst[0] = *a; dst[1] = *b; }
 
 // per-step totals for the status word + rhof scaling of the per-solid sums (solidcloud.cpp:424-425)
-__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status, double *ft, const double *scal) {
+// rhof scaling alone (solidcloud.cpp:424-425): the split multi-GPU step scales right behind k_final, so that the all-reduce of the
+// per-solid sums can run on its own stream while the certificate pass and the status totals follow on the context stream
+__global__ void k_scale_ft(double *ft, long long n, const double *scal) {
+    const double rhof = __ldg(scal + 1);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) ft[i] = ft[i] * rhof;
+}
+
+__global__ void k_finalize(const unsigned *pair_counts, const int *root_count, int n_solids, StepStatus *status, double *ft, const double *scal, int scale) {
     unsigned long long c0 = 0, c1 = 0, c2 = 0;
     int nf = 0;
     const double rhof = __ldg(scal + 1);
@@ -1348,8 +1355,10 @@ __global__ void k_finalize(const unsigned *pair_counts, const int *root_count, i
         c1 += pair_counts[3 * s + 1];
         c2 += pair_counts[3 * s + 2];
         nf += root_count[s] > 1;
+        if (scale) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) ft[6 * (long long)s + k] = ft[6 * (long long)s + k] * rhof;
+            for (int k = 0; k < 6; ++k) ft[6 * (long long)s + k] = ft[6 * (long long)s + k] * rhof;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         c0 += __shfl_xor_sync(0xffffffffu, c0, o);

@@ -959,6 +959,9 @@ struct sdfibm_context {
     bool gathered_now = false;           // the current call's solid records are in solids_gathered
     double *reduce_out = nullptr;        // run_pipeline: all-reduce the sums into this buffer right behind the first pass
     cudaEvent_t ev_comm[2] = {nullptr, nullptr};
+    cudaStream_t s_comm = nullptr;       // high-priority stream of the split step's all-reduce
+    cudaEvent_t ev_ft = nullptr;
+    bool comm_split = true;              // SDFIBM_COMM_SPLIT=0: the all-reduce behind the whole step, on the context stream
     int64_t flagged_last = 0;
 };
 
@@ -1102,6 +1105,13 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(cudaMallocHost(&ctx->h_retry_sum, sizeof(double)));
     *ctx->h_retry_sum = 0.0;
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreate(&ctx->ev_comm[i]));
+    if (!ctx->s_comm) {
+        int lo_p = 0, hi_p = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ctx->s_comm, cudaStreamNonBlocking, hi_p));   // its kernels are dispatched ahead of the certificate pass
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_ft, cudaEventDisableTiming));
+    }
+    if (const char *e = getenv("SDFIBM_COMM_SPLIT")) ctx->comm_split = atoi(e) != 0;
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_CLASSIFY4")) ctx->classify4 = atoi(e) != 0;
@@ -1136,6 +1146,8 @@ int sdfibm_destroy(sdfibm_context *ctx) {
     ctx->ft_partial.release(); ctx->retry_flag.release(); ctx->solids_slice.release(); ctx->solids_gathered.release();
     if (ctx->h_retry_sum) cudaFreeHost(ctx->h_retry_sum);
     for (int i = 0; i < 2; ++i) if (ctx->ev_comm[i]) cudaEventDestroy(ctx->ev_comm[i]);
+    if (ctx->ev_ft) cudaEventDestroy(ctx->ev_ft);
+    if (ctx->s_comm) cudaStreamDestroy(ctx->s_comm);
     ctx->bin_off.release(); ctx->bin_list.release(); ctx->zero_block.release(); ctx->scal.release(); ctx->slab_start.release();
     ctx->global_list.release(); ctx->slots.release();
     ctx->bin_entries.release(); ctx->heavy_res.release(); ctx->n_item.release(); ctx->heavy.release();
@@ -1714,10 +1726,28 @@ int sdfibm_interact_device(sdfibm_context *ctx, const sdfibm_solid_t *solids, in
     return SDFIBM_OK;
 }
 
+// The tail of a pass: connectivity certificate, status totals (+ the rhof scaling unless the head did it), status read-back.
+static int enqueue_tail(sdfibm_context *ctx, int n_solids, double *dFT, bool replay, bool capturing, int scale) {
+    cudaStream_t st = ctx->stream;
+    const int nC = ctx->dm.n_cells;
+    if (!replay) {
+        ConnParams C;
+        C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count; C.tile_proven = ctx->tile_proven.p; C.status = ctx->status;
+        k_connectivity<<<std::min(grid_for(nC, 256), ctx->n_sm * 8), 256, 0, st>>>(C);
+        ++ctx->launches;
+    }
+    k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts, ctx->root_count, n_solids, ctx->status, dFT, ctx->scal.p, scale);
+    ++ctx->launches;
+    CUDA_TRY(capturing ? cudaEventRecordWithFlags(ctx->ev[5], st, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[5], st));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
+    return SDFIBM_OK;
+}
+
 // Everything one pass of the pipeline enqueues on the context stream (directly, or once into a CUDA graph that later steps
 // re-launch: ~20 dependent launches / memsets become one submission, which matters because every step starts on an idle GPU).
 static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, double *dAs, double *dFs, double *dTs, double *dCt,
-                            double *dFT, bool replay, bool chunked, bool capturing) {
+                            double *dFT, bool replay, bool chunked, bool capturing, int part = 0) {
     cudaStream_t st = ctx->stream;
     const int nC = ctx->dm.n_cells;
     const BinGrid &g = ctx->grid;
@@ -1879,18 +1909,13 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     }
     CUDA_TRY(rec(ctx->ev[4]));
     ctx->launches += 3;
-    if (!replay) {
-        ConnParams C;
-        C.m = ctx->dm; C.solids = ctx->solids.p; C.n_item = ctx->n_item.p; C.slots = ctx->slots.p; C.K = ctx->K; C.root_count = ctx->root_count; C.tile_proven = ctx->tile_proven.p; C.status = ctx->status;
-        k_connectivity<<<std::min(grid_for(nC, 256), ctx->n_sm * 8), 256, 0, st>>>(C);
+    if (part == 1) {   // the head of a split step: the sums are final once scaled; the tail follows outside the graph
+        k_scale_ft<<<std::min(grid_for(6 * (long long)n_solids, 256), 296), 256, 0, st>>>(dFT, 6 * (long long)n_solids, ctx->scal.p);
         ++ctx->launches;
+        CUDA_TRY(cudaGetLastError());
+        return SDFIBM_OK;
     }
-    k_finalize<<<std::min(grid_for(n_solids, 256), 296), 256, 0, st>>>(ctx->pair_counts, ctx->root_count, n_solids, ctx->status, dFT, ctx->scal.p);
-    ++ctx->launches;
-    CUDA_TRY(rec(ctx->ev[5]));
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->status, sizeof(StepStatus), cudaMemcpyDeviceToHost, st));
-    return SDFIBM_OK;
+    return enqueue_tail(ctx, n_solids, dFT, replay, capturing, /*scale*/ 1);
 }
 
 static void fold_timings(sdfibm_context *ctx) {
@@ -1951,19 +1976,23 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             CUDA_TRY(cudaStreamSynchronize(ctx->s_out));
         }
         const bool use_graph = ctx->use_graph && !replay && !ctx->pipe.active;
+        const bool reduced_here = ctx->reduce_out && attempt == 0 && !replay;
+        // split step (multi-GPU): the graph ends behind k_final + the rhof scaling; the all-reduce of the sums then runs on the
+        // communication stream WHILE the certificate pass and the status totals follow on the context stream
+        const bool split = use_graph && reduced_here && ctx->comm_split && ctx->s_comm;
         const auto q0 = std::chrono::steady_clock::now();
         if (use_graph) {
             const uint64_t key[20] = {(uint64_t)n_solids, (uint64_t)dU, (uint64_t)dAs, (uint64_t)dFs, (uint64_t)dTs, (uint64_t)dCt, (uint64_t)dFT,
                                       (uint64_t)(ctx->ext_solids ? ctx->ext_solids : (ctx->gathered_now ? ctx->solids_gathered.p : ctx->solids_in.p)), (uint64_t)ctx->solids.p, (uint64_t)ctx->heavy.p, (uint64_t)ctx->heavy.n,
                                       (uint64_t)ctx->bin_list.p, (uint64_t)ctx->bin_list.n, (uint64_t)ctx->bin_entries.p, (uint64_t)ctx->zero_block.p,
                                       (uint64_t)ctx->shapes.p ^ ((uint64_t)ctx->sdf_ops.p << 2), (uint64_t)ctx->scan_tmp.p ^ ((uint64_t)ctx->tile_proven.p << 1), (uint64_t)ctx->global_list.p, (uint64_t)ctx->shapes_refinable,
-                                      (uint64_t)ctx->n_global_hint ^ ((uint64_t)ctx->bin_fixed << 8)};
+                                      (uint64_t)ctx->n_global_hint ^ ((uint64_t)ctx->bin_fixed << 8) ^ ((uint64_t)split << 9)};
             if (!ctx->graph_exec || memcmp(key, ctx->graph_key, sizeof(key)) != 0) {
                 drop_graph(ctx);
                 cudaGraph_t graph = nullptr;
                 CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
                 const int64_t keep_launches = ctx->launches;
-                const int rc = enqueue_pipeline(ctx, n_solids, dU, dAs, dFs, dTs, dCt, dFT, false, false, true);
+                const int rc = enqueue_pipeline(ctx, n_solids, dU, dAs, dFs, dTs, dCt, dFT, false, false, true, split ? 1 : 0);
                 ctx->graph_launches = ctx->launches - keep_launches;
                 ctx->launches = keep_launches;
                 const cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -1976,12 +2005,26 @@ static int run_pipeline(sdfibm_context *ctx, int n_solids, const double *dU, dou
             }
             CUDA_TRY(cudaGraphLaunch(ctx->graph_exec, st));
             ctx->launches += ctx->graph_launches;
+            if (split) {
+                NcclApi *a = nccl_api();
+                CUDA_TRY(cudaEventRecord(ctx->ev_ft, st));                        // the scaled sums are final
+                CUDA_TRY(cudaStreamWaitEvent(ctx->s_comm, ctx->ev_ft, 0));
+                CUDA_TRY(cudaEventRecord(ctx->ev_comm[0], ctx->s_comm));
+                NCCL_TRY(a->AllReduce(dFT, ctx->reduce_out, 6 * (size_t)n_solids, ncclDouble, ncclSum, ctx->comm, ctx->s_comm));
+                CUDA_TRY(cudaEventRecord(ctx->ev_comm[1], ctx->s_comm));
+                const int rc = enqueue_tail(ctx, n_solids, dFT, false, false, /*scale*/ 0);   // certificate + totals, alongside the all-reduce
+                if (rc) return rc;
+                // the ranks' "again" flags need the certificate's result: a second, 8-byte all-reduce behind the tail
+                k_retry_flag<<<1, 1, 0, st>>>(ctx->status, (long long)ctx->heavy.n, ctx->n_global_hint, ctx->retry_flag.p);
+                NCCL_TRY(a->AllReduce(ctx->retry_flag.p, ctx->retry_flag.p + 1, 1, ncclDouble, ncclSum, ctx->comm, st));
+                CUDA_TRY(cudaMemcpyAsync(ctx->h_retry_sum, ctx->retry_flag.p + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_comm[1], 0));             // the host's one synchronisation covers both streams
+            }
         } else {
             const int rc = enqueue_pipeline(ctx, n_solids, dU, dAs, dFs, dTs, dCt, dFT, replay, chunked, false);
             if (rc) return rc;
         }
-        const bool reduced_here = ctx->reduce_out && attempt == 0 && !replay;
-        if (reduced_here) {
+        if (reduced_here && !split) {
             const int rc = enqueue_comm_reduce(ctx, dFT, ctx->reduce_out, n_solids, true);
             if (rc) return rc;
         }
@@ -2193,6 +2236,7 @@ int sdfibm_comm_destroy(sdfibm_context *ctx) {
     if (ctx->comm) {
         CUDA_TRY(cudaSetDevice(ctx->device));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->s_comm) CUDA_TRY(cudaStreamSynchronize(ctx->s_comm));
         NCCL_TRY(nccl_api()->CommDestroy(ctx->comm));
     }
     ctx->comm = nullptr;

@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world, out_dir = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    import torch   # device memory for the device-resident step only — imported BEFORE the library binds libnccl.so.2, so that both use torch's copy
     from sdfibm_b200 import cases
     from sdfibm_b200.context import Context
 
@@ -36,6 +37,20 @@ def main():
             time.sleep(0.05)
         uid = open(id_file, "rb").read()
     ctx.comm_init(uid, rank, world)
+    # 0. the device-resident entry (one CUDA-graph launch per step): the SPLIT step — the all-reduce of the sums on the library's
+    #    communication stream alongside the certificate pass, the ranks' retry flags in a second, 8-byte all-reduce.  Rank 1's queue
+    #    overflows in this very step, so the flag protocol and the second reduction run in split mode.
+    dev = torch.device("cuda", rank)
+    nC, nS = case["mesh"].n_cells, len(case["solids"])
+    dU = torch.from_numpy(case["U"]).to(dev)
+    f = [torch.zeros(k, dtype=torch.float64, device=dev) for k in (nC, 3 * nC, nC, nC, 6 * nS)]
+    from sdfibm_b200 import capi
+    solids_pinned = capi.pinned_like(np.ascontiguousarray(case["solids"], dtype=capi.SOLID_DTYPE))
+    dev_ft = []
+    for _ in range(3):     # the first step carries the retry; the next two replay the captured graph
+        ctx.interact_device(solids_pinned, dU.data_ptr(), case["dt"], case["rhof"], *[x.data_ptr() for x in f])
+        dev_ft.append(f[4].cpu().numpy().reshape(nS, 6).copy())
+    dev_As = f[0].cpu().numpy().copy()
     # 1. the default: slice upload + all-gather of the replicated solids, force/torque summed over the ranks
     total = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
     lists = ctx.candidate_lists()
@@ -46,7 +61,8 @@ def main():
     ctx.comm_options(auto_reduce=True, gather_solids=True)
     again = ctx.interact(case["solids"], case["U"], case["dt"], case["rhof"])
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), FT=total["FT"], FT_partial=part["FT"], FT_again=again["FT"], As=total["As"],
-             As_partial=part["As"], Ct=total["Ct"], off=lists[0], cells=lists[1], comm_ms=ctx.comm_last_ms())
+             As_partial=part["As"], Ct=total["Ct"], off=lists[0], cells=lists[1], comm_ms=ctx.comm_last_ms(),
+             FT_dev0=dev_ft[0], FT_dev1=dev_ft[1], FT_dev2=dev_ft[2], As_dev=dev_As)
     ctx.close()
 
 
