@@ -285,8 +285,9 @@ int sdfibm_synchronize(sdfibm_context *ctx);
  *   every rank:  sdfibm_comm_init(ctx, id, rank, n_ranks)      (collective)
  * After sdfibm_comm_init every sdfibm_interact / sdfibm_interact_device on the context
  *   - uploads only this rank's 1/N slice of the (replicated) solid array and all-gathers the slices over NVLink, and
- *   - returns force_torque already summed over the ranks (the all-reduce is enqueued right behind the kernels; a rank that
- *     has to re-run its step — queue growth, flood-fill replay — tells the others through a flag that rides the same launch).
+ *   - returns force_torque already summed over the ranks (on the device-resident entries the all-reduce runs on a communication
+ *     stream of the library alongside the last kernels of the step; a rank that has to re-run its step — queue growth,
+ *     flood-fill replay — tells the others through a flag that is reduced with it, and every rank then reduces again).
  * Both calls are COLLECTIVE from then on: every rank must make them with the same solid array.  sdfibm_comm_options switches
  * either behaviour off (e.g. to reduce by MPI instead); sdfibm_allreduce_force_torque is the bare collective on a device
  * array, in place, stream-ordered (no host synchronisation). */
