@@ -206,13 +206,26 @@ __device__ __forceinline__ void pair_terms(const DevSolid &S, D3 cc, D3 uf, doub
 }
 
 // c = the caller's cell label (orig[position])
+#ifndef FINAL_STREAM_STORES
+#define FINAL_STREAM_STORES 0
+#endif
 __device__ __forceinline__ void store_cell(const InteractParams &P, int c, double as, D3 fs, double ts, double ct) {
+#if FINAL_STREAM_STORES
+    // the four fields are written once per step and not read again by this pipeline: streaming (evict-first) stores
+    __stcs(P.As + c, (as < 1.0) ? as : 1.0);
+    __stcs(P.Fs + 3 * (long long)c, fs.x);
+    __stcs(P.Fs + 3 * (long long)c + 1, fs.y);
+    __stcs(P.Fs + 3 * (long long)c + 2, fs.z);
+    __stcs(P.Ts + c, ts);
+    __stcs(P.Ct + c, ct);
+#else
     P.As[c] = (as < 1.0) ? as : 1.0;                                               // checkAlpha, :564-570 (std::min(As,1))
     P.Fs[3 * (long long)c] = fs.x;
     P.Fs[3 * (long long)c + 1] = fs.y;
     P.Fs[3 * (long long)c + 2] = fs.z;
     P.Ts[c] = ts;
     P.Ct[c] = ct;
+#endif
 }
 
 // warp-level aggregation of one member pair per lane: lanes with the same solid are reduced together and
