@@ -151,6 +151,8 @@ struct InteractParams {
     const sdfibm_sdf_op_t *ops;   // op table of the SDFIBM_SHAPE_PROGRAM records (null: none)
     int n_solids;
     BinGrid grid;
+    int part_shapes;             // exact-box meshes: queued pairs of un-rotated spheres go to the FRONT queue, all others to the BACK queue
+                                 // (item i at heavy_cap - 1 - i), so that the warps of k_heavy_box are uniform in their corner path
     int bin_fixed;               // 1: tile t owns the slots [t * BIN_FIXED_CAP, +min(bin_count[t], BIN_FIXED_CAP)); 0: CSR (bin_off)
     const int *bin_count;
     const int *bin_off;
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
             for (; bi < be; ++bi) {
                 const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
                 const int s = __float_as_int(e1.y);
-                emit(s, refine32(s, test32(e0, e1), __float_as_int(e1.w)));
+                emit(s, refine32(s, test32(e0, e1), __float_as_int(e1.w) & 0xff));
             }
         } else {
             // planes / tilted 2-D solids are tested by every cell: merge the tile list and the global list in ascending solid id
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify(InteractParams P) {
                     sb = __float_as_int(e1.y);
                 }
                 const int sg = (gi < ge) ? __ldg(P.global_list + gi) : 0x7fffffff;
-                if (sb <= sg) { ++bi; emit(sb, refine32(sb, test32(e0, e1), __float_as_int(e1.w))); }
+                if (sb <= sg) { ++bi; emit(sb, refine32(sb, test32(e0, e1), __float_as_int(e1.w) & 0xff)); }
                 else { ++gi; emit(sg, quick_class(P.solids[sg], cc, rad)); }
             }
         }
@@ -459,7 +461,7 @@ __device__ __noinline__ int refine32_pair(const DevSolid &S, float4 p, float4 hb
 // SPEC: every shape of the table is 3-D and every cell is the same axis-aligned box (C4, C5): the 2-D / 3-D selects and the clamp of
 // the near-corner offsets drop out of the test.  The two sums of squares use explicit fmaf (one rounding less per term; the 4e-6
 // relative slack of the radii covers either rounding sequence — tests/test_classify_bounds_cpu.py runs both).
-template <int NT, int MINB, bool SPEC, bool REFINE>
+template <int NT, int MINB, bool SPEC, bool REFINE, bool PART>
 __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
@@ -470,6 +472,7 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
     const bool full = c0 + 3 < P.cls_end;
     int n_item[4] = {0, 0, 0, 0}, n_heavy[4] = {0, 0, 0, 0}, slot0[4] = {0, 0, 0, 0};
     int n_over[4] = {0, 0, 0, 0};
+    unsigned ballmask[4] = {0u, 0u, 0u, 0u};   // bit j: slot j of the cell is a queued pair of an un-rotated sphere (front queue)
     const float4 *E = reinterpret_cast<const float4 *>(P.bin_entries);
     if (c0 < P.cls_end) {
         float4 p[4], hb[4];
@@ -488,13 +491,14 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
             for (int q = 0; q < 4; ++q) t[q] = __ldg(m.tile_key + min(c0 + q, P.cls_end - 1));
         }
         // one pre-classified candidate of cell q -> slot record (slot 0 stays in a register)
-        auto emit = [&](int q, int s, int qc) {
+        auto emit = [&](int q, int s, int qc, int ball) {
             if (qc == 0) return;
             if (n_item[q] < P.K) {
                 const int rec = (s << 3) | (qc == 2 ? SLOT_HEAVY : SDFIBM_CELL_ALL_INSIDE);
                 if (n_item[q] == 0) slot0[q] = rec;
                 else P.slots[(long long)n_item[q] * nC + (c0 + q)] = rec;
                 n_heavy[q] += (qc == 2);
+                if (PART && qc == 2 && ball && n_item[q] < 32) ballmask[q] |= 1u << n_item[q];
                 ++n_item[q];
             } else ++n_over[q];
         };
@@ -532,12 +536,13 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
                     const float N2 = fmaf(nx, nx, Nyz), F2 = fmaf(fx, fx, Fyz);
                     qc[q] = (N2 > ro2) ? 0 : ((has_in && F2 < ri2) ? 1 : 2);
                 }
-                if (REFINE && __float_as_int(e1.w) != 0) {
+                const int flags = __float_as_int(e1.w), mode = flags & 0xff, ball = (flags >> 8) & 1;
+                if (REFINE && mode != 0) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) if (qc[q] == 2) qc[q] = refine32_pair(P.solids[s], p[q], hb[q], __float_as_int(e1.w));
+                    for (int q = 0; q < 4; ++q) if (qc[q] == 2) qc[q] = refine32_pair(P.solids[s], p[q], hb[q], mode);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q]);
+                for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q], ball);
             }
         } else if (t[1] == t[0] && t[2] == t[0] && t[3] == t[0]) {
             int bi, be;
@@ -557,12 +562,13 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
                 int qc[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) qc[q] = test32(q, e0, e1);
-                if (REFINE && __float_as_int(e1.w) != 0) {
+                const int flags = __float_as_int(e1.w), mode = flags & 0xff, ball = (flags >> 8) & 1;
+                if (REFINE && mode != 0) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) if (qc[q] == 2) qc[q] = refine32_pair(P.solids[s], p[q], hb[q], __float_as_int(e1.w));
+                    for (int q = 0; q < 4; ++q) if (qc[q] == 2) qc[q] = refine32_pair(P.solids[s], p[q], hb[q], mode);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q]);
+                for (int q = 0; q < 4; ++q) if (full || c0 + q < P.cls_end) emit(q, s, qc[q], ball);
 #if CLS4_PREFETCH
                 e0 = f0; e1 = f1;
 #endif
@@ -576,8 +582,9 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
                 for (; bi < be; ++bi) {
                     const float4 e0 = __ldg(E + 2 * (long long)bi), e1 = __ldg(E + 2 * (long long)bi + 1);
                     int qc1 = test32(q, e0, e1);
-                    if (REFINE && qc1 == 2 && __float_as_int(e1.w) != 0) qc1 = refine32_pair(P.solids[__float_as_int(e1.y)], p[q], hb[q], __float_as_int(e1.w));
-                    emit(q, __float_as_int(e1.y), qc1);
+                    const int flags = __float_as_int(e1.w), mode = flags & 0xff;
+                    if (REFINE && qc1 == 2 && mode != 0) qc1 = refine32_pair(P.solids[__float_as_int(e1.y)], p[q], hb[q], mode);
+                    emit(q, __float_as_int(e1.y), qc1, (flags >> 8) & 1);
                 }
             }
         }
@@ -592,12 +599,18 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
         }
     }
     // ---- block-aggregated append to the queue (see k_classify): hex count in the low, general-cell count in the high 16 bits
+    // (part_shapes, exact-box meshes: the low count = pairs of un-rotated spheres, front queue; the high count = all other pairs, back queue)
     int mine = 0;
     bool gen[4] = {false, false, false, false};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        gen[q] = m.mixed && n_heavy[q] > 0 && __ldg(m.hex_topo + 3 * (long long)(c0 + q)) == HEX_NONE;
-        mine += gen[q] ? (n_heavy[q] << 16) : n_heavy[q];
+        if (PART) {
+            const int nb = __popc(ballmask[q]);
+            mine += nb | ((n_heavy[q] - nb) << 16);
+        } else {
+            gen[q] = m.mixed && n_heavy[q] > 0 && __ldg(m.hex_topo + 3 * (long long)(c0 + q)) == HEX_NONE;
+            mine += gen[q] ? (n_heavy[q] << 16) : n_heavy[q];
+        }
     }
     int incl = mine;
 #pragma unroll
@@ -631,14 +644,15 @@ __global__ void __launch_bounds__(NT, MINB) k_classify4(InteractParams P) {
             for (int j = 0; j < n_item[q]; ++j) {
                 const int e = (j == 0) ? slot0[q] : P.slots[(long long)j * nC + c];
                 if (e & SLOT_HEAVY) {
-                    const long long pos = gen[q] ? pos_gen : pos_hex;
+                    const bool back = PART ? !(j < 32 && ((ballmask[q] >> j) & 1u)) : gen[q];
+                    const long long pos = back ? pos_gen : pos_hex;
                     if (pos >= 0 && pos < P.heavy_cap) {
                         P.heavy[pos] = make_int2(c, e >> 3);
                         const int rec = ((int)pos << 3) | SLOT_HEAVY;     // the slot now points at its queue item
                         if (j == 0) slot0[q] = rec;
                         else P.slots[(long long)j * nC + c] = rec;
                     }
-                    if (gen[q]) --pos_gen; else ++pos_hex;
+                    if (back) --pos_gen; else ++pos_hex;
                 }
             }
         }
@@ -959,47 +973,53 @@ struct BoxSmem {
     double apex[3 * TPB];
 };
 
-template <bool PLANE_FROM_MESH, bool PROG>
+template <bool PLANE_FROM_MESH, bool PROG, bool PART>
 __global__ void __launch_bounds__(TPB, BOX_CTAS_PER_SM) k_heavy_box(InteractParams P) {
     __shared__ BoxSmem sm;
     const DevMesh &m = P.m;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
     double *phi = sm.phi + tid, *lohi = sm.lohi + tid, *ef = sm.ef + tid, *apx = sm.apex + tid;
-    const long long n = min((long long)*P.heavy_count, P.heavy_cap);
-    const long long q0 = P.heavy_start ? (long long)*P.heavy_start : 0;
+    // The items of this launch as ONE index range: first the front queue (ascending positions; with part_shapes the pairs of
+    // un-rotated spheres), then the back queue (item i at heavy_cap - 1 - i; every other pair) — so all warps but the one that
+    // straddles the seam are uniform in the corner path they take below.
+    const long long qf = P.heavy_start ? (long long)P.heavy_start[0] : 0, qb = (PART && P.heavy_start) ? (long long)P.heavy_start[1] : 0;
+    const long long n_front = max(min((long long)*P.heavy_count, P.heavy_cap) - qf, 0ll);
+    const long long n_tot = n_front + (PART ? max(min((long long)*P.heavy_gen, P.heavy_cap) - qb, 0ll) : 0ll);
+    auto pos_of = [&](long long i) { return (!PART || i < n_front) ? qf + i : P.heavy_cap - 1 - (qb + (i - n_front)); };
     // the queue item of the NEXT batch is requested while this one is evaluated — BOX_PREFETCH 1: 8 bytes in two registers,
     // 2: an 8-byte cp.async into the lane's shared-memory slot (no registers) — so the cell / solid records of a batch are one
     // dependent level away instead of two
 #if BOX_PREFETCH == 1
     int2 it_next = make_int2(0, 0);
     {
-        const long long kf = q0 + (long long)blockIdx.x * TPB + wbase + lane;
-        if (kf < n) it_next = __ldg(P.heavy + kf);
+        const long long jf = (long long)blockIdx.x * TPB + wbase + lane;
+        if (jf < n_tot) it_next = __ldg(P.heavy + pos_of(jf));
     }
 #elif BOX_PREFETCH == 2
     __shared__ double s_item[TPB];
     {
-        const long long kf = q0 + (long long)blockIdx.x * TPB + wbase + lane;
-        if (kf < n) cp_async8(&s_item[tid], reinterpret_cast<const double *>(P.heavy + kf));
+        const long long jf = (long long)blockIdx.x * TPB + wbase + lane;
+        if (jf < n_tot) cp_async8(&s_item[tid], reinterpret_cast<const double *>(P.heavy + pos_of(jf)));
     }
 #endif
-    for (long long k0 = q0 + (long long)blockIdx.x * TPB + wbase; k0 < n; k0 += (long long)gridDim.x * TPB) {
-        const long long k = k0 + lane;
-        const bool valid = k < n;
+    for (long long i0 = (long long)blockIdx.x * TPB + wbase; i0 < n_tot; i0 += (long long)gridDim.x * TPB) {
+        const long long i = i0 + lane;
+        const bool valid = i < n_tot;
+        const long long k = valid ? pos_of(i) : 0;       // the item's queue position: its result goes to heavy_res[k]
         int c = 0, s = 0;
 #if BOX_PREFETCH == 1
         c = it_next.x; s = it_next.y;
         {
-            const long long kn = k + (long long)gridDim.x * TPB;
-            if (kn < n) it_next = __ldg(P.heavy + kn);
+            const long long jn = i + (long long)gridDim.x * TPB;
+            if (jn < n_tot) it_next = __ldg(P.heavy + pos_of(jn));
         }
 #elif BOX_PREFETCH == 2
         cp_async_wait_all();
         if (valid) { const long long it = __double_as_longlong(s_item[tid]); c = (int)(it & 0xffffffffll); s = (int)(it >> 32); }
         {
-            const long long kn = k + (long long)gridDim.x * TPB;
-            if (kn < n) cp_async8(&s_item[tid], reinterpret_cast<const double *>(P.heavy + kn));
+            const long long jn = i + (long long)gridDim.x * TPB;
+            if (jn < n_tot) cp_async8(&s_item[tid], reinterpret_cast<const double *>(P.heavy + pos_of(jn)));
         }
 #else
         if (valid) { const int2 it = __ldg(P.heavy + k); c = it.x; s = it.y; }

@@ -73,6 +73,7 @@ struct DevSolid {
     double r_out, r_in;
     float pos32[3]; // centre relative to the mesh origin (keys of the connectivity certificate)
     int conn_proven; // the vertex-inside cell set of this solid is provably face connected: no certificate needed
+    int ball_fast;   // an un-rotated sphere: k_heavy_box's separable corner path applies (the queue keeps such pairs apart from the rest)
     float ri32;     // KIND_3D: certified inner radius minus the fp32 slack, rounded down (<= 0: none): the same test as k_classify
     // fp32 refinement of the pre-classification for convex analytic shapes (k_classify): body coordinates b = M (p - pos) + com;
     // refine 1: inside <=> sum (b_i rp_i)^2 < 1 (ellipsoid, ellipse: rp = 1/radius, 0 for an ignored axis);
@@ -576,6 +577,7 @@ __global__ void k_solid_prepare(PrepParams P) {
             }
         }
         S.conn_proven = ok ? 1 : 0;
+        S.ball_fast = (sp.tag == SDFIBM_SHAPE_SPHERE && quat_is_identity(q)) ? 1 : 0;
     }
     if (sub == 0) P.out[s] = S;
     if (S.global) {
@@ -658,7 +660,7 @@ __device__ __forceinline__ BinEntry make_bin_entry(const DevSolid &S, int s, dou
     e.r_in = __double2float_rd(S.r_in - slack);
     e.s = s;
     e.kind = S.kind;
-    e.refine = S.refine;
+    e.refine = S.refine | (S.ball_fast << 8);   // bits 0-7: corner-refinement mode; bit 8: un-rotated sphere
     return e;
 }
 
@@ -941,6 +943,8 @@ struct sdfibm_context {
     int classify4_refine = 1;            // SDFIBM_CLASSIFY4_REFINE=0: refinable shape tables keep the one-position kernel
     bool bin_fixed = false;              // tile bins with BIN_FIXED_CAP slots each (set per mesh; a tile that overflows switches the context to scan + fill)
     bool bin_fixed_allowed = true;       // SDFIBM_BIN_FIXED=0
+    bool part_shapes = true;             // SDFIBM_PART_SHAPES=0: one queue order for all shapes
+    bool shapes_sphere_and_other = false; // the shape table holds spheres AND other shapes: only then does the partition pay
     bool classify4 = true;               // k_classify4 (four positions per thread); SDFIBM_CLASSIFY4=0: the one-position kernel
     bool shapes_may_be_global = false;   // the shape table holds a plane or a 2-D shape
     bool shapes_refinable = false;       // ... or a convex analytic shape the fp32 corner refinement of k_classify handles
@@ -1115,6 +1119,7 @@ int sdfibm_create(int device, sdfibm_context **out) {
     CUDA_TRY(ctx->scal.ensure(2));
     if (const char *e = getenv("SDFIBM_GRAPH")) ctx->use_graph = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_CLASSIFY4")) ctx->classify4 = atoi(e) != 0;
+    if (const char *e = getenv("SDFIBM_PART_SHAPES")) ctx->part_shapes = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_BIN_FIXED")) ctx->bin_fixed_allowed = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_BOX")) ctx->allow_box = atoi(e) != 0;
     if (const char *e = getenv("SDFIBM_ALLOW_ORDER_FREE")) ctx->allow_order_free = atoi(e) != 0;
@@ -1553,10 +1558,13 @@ int sdfibm_set_shapes(sdfibm_context *ctx, const sdfibm_shape_t *shapes, int n) 
     }
     ctx->shapes_may_be_global = false;
     ctx->shapes_refinable = false;
+    bool any_sphere = false, any_other = false;
     for (auto &sh : ctx->h_shapes) {
+        (sh.s.tag == SDFIBM_SHAPE_SPHERE ? any_sphere : any_other) = true;
         ctx->shapes_may_be_global |= (sh.kind != KIND_3D);
         ctx->shapes_refinable |= (sh.s.tag == SDFIBM_SHAPE_ELLIPSOID || sh.s.tag == SDFIBM_SHAPE_ELLIPSE || sh.s.tag == SDFIBM_SHAPE_BOX || sh.s.tag == SDFIBM_SHAPE_RECTANGLE);
     }
+    ctx->shapes_sphere_and_other = any_sphere && any_other;
     if (const char *e = getenv("SDFIBM_REFINE")) ctx->shapes_refinable = ctx->shapes_refinable && atoi(e) != 0;
     int rc = upload(ctx->shapes, ctx->h_shapes.data(), (size_t)n, ctx->stream);
     if (rc) return rc;
@@ -1799,6 +1807,8 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
     InteractParams I;
     I.m = ctx->dm; I.solids = ctx->solids.p; I.shapes = ctx->shapes.p; I.ops = ctx->h_ops.empty() ? nullptr : ctx->sdf_ops.p; I.n_solids = n_solids; I.grid = g;
     I.bin_fixed = ctx->bin_fixed ? 1 : 0; I.bin_count = ctx->bin_count;
+    // (the one-position kernel of the global-list variant queues everything in front: no partition then)
+    I.part_shapes = (ctx->part_shapes && ctx->shapes_sphere_and_other && ctx->classify4 && ctx->dm.box_exact && !ctx->dm.mixed && !ctx->n_global_hint) ? 1 : 0;
     I.bin_off = ctx->bin_off.p; I.bin_list = ctx->bin_list.p; I.bin_entries = ctx->bin_entries.p; I.global_list = ctx->global_list.p; I.U = dU;
     I.scal = ctx->scal.p; I.As = dAs; I.Fs = dFs; I.Ts = dTs; I.Ct = dCt; I.force_torque = dFT;
     I.pair_counts = ctx->pair_counts; I.slots = ctx->slots.p; I.K = ctx->K;
@@ -1813,12 +1823,16 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         if (ctx->classify4 && !ctx->n_global_hint) {   // no plane / tilted 2-D solid about: four consecutive positions per thread
             const bool spec = !ctx->shapes_may_be_global && ctx->dm.box_uniform && ctx->dm.box_const.w != 0.f;   // 3-D shapes on identical box cells
             const int g4 = grid_for(p1 - p0, 4 * CLS4_NT);
-            if (ctx->shapes_refinable) {
-                if (spec) k_classify4<CLS4_NT, CLS4_MINB, true, true><<<g4, CLS4_NT, 0, st>>>(I);
-                else k_classify4<CLS4_NT, CLS4_MINB, false, true><<<g4, CLS4_NT, 0, st>>>(I);
-            } else {
-                if (spec) k_classify4<CLS4_NT, CLS4_MINB, true, false><<<g4, CLS4_NT, 0, st>>>(I);
-                else k_classify4<CLS4_NT, CLS4_MINB, false, false><<<g4, CLS4_NT, 0, st>>>(I);
+            const int variant = (spec ? 4 : 0) | (ctx->shapes_refinable ? 2 : 0) | (I.part_shapes ? 1 : 0);
+            switch (variant) {
+                case 0: k_classify4<CLS4_NT, CLS4_MINB, false, false, false><<<g4, CLS4_NT, 0, st>>>(I); break;
+                case 1: k_classify4<CLS4_NT, CLS4_MINB, false, false, true><<<g4, CLS4_NT, 0, st>>>(I); break;
+                case 2: k_classify4<CLS4_NT, CLS4_MINB, false, true, false><<<g4, CLS4_NT, 0, st>>>(I); break;
+                case 3: k_classify4<CLS4_NT, CLS4_MINB, false, true, true><<<g4, CLS4_NT, 0, st>>>(I); break;
+                case 4: k_classify4<CLS4_NT, CLS4_MINB, true, false, false><<<g4, CLS4_NT, 0, st>>>(I); break;
+                case 5: k_classify4<CLS4_NT, CLS4_MINB, true, false, true><<<g4, CLS4_NT, 0, st>>>(I); break;
+                case 6: k_classify4<CLS4_NT, CLS4_MINB, true, true, false><<<g4, CLS4_NT, 0, st>>>(I); break;
+                default: k_classify4<CLS4_NT, CLS4_MINB, true, true, true><<<g4, CLS4_NT, 0, st>>>(I); break;
             }
             return;
         }
@@ -1832,8 +1846,14 @@ static int enqueue_pipeline(sdfibm_context *ctx, int n_solids, const double *dU,
         // (PROG: the shape table holds a composed shape — only then do the kernels carry the op interpreter)
         const bool prog = !ctx->h_ops.empty();
         const int gb = ctx->n_sm * BOX_CTAS_PER_SM, gh = ctx->n_sm * HEAVY_CTAS_PER_SM;
-        if (ctx->dm.box_exact == 2) { if (prog) k_heavy_box<false, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<false, false><<<gb, TPB, 0, st>>>(I); }
-        else if (ctx->dm.box_exact == 1) { if (prog) k_heavy_box<true, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<true, false><<<gb, TPB, 0, st>>>(I); }
+        const bool part = I.part_shapes != 0;
+        if (ctx->dm.box_exact == 2) {
+            if (prog) { if (part) k_heavy_box<false, true, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<false, true, false><<<gb, TPB, 0, st>>>(I); }
+            else { if (part) k_heavy_box<false, false, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<false, false, false><<<gb, TPB, 0, st>>>(I); }
+        } else if (ctx->dm.box_exact == 1) {
+            if (prog) { if (part) k_heavy_box<true, true, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<true, true, false><<<gb, TPB, 0, st>>>(I); }
+            else { if (part) k_heavy_box<true, false, true><<<gb, TPB, 0, st>>>(I); else k_heavy_box<true, false, false><<<gb, TPB, 0, st>>>(I); }
+        }
         else if (ctx->dm.is_hex || ctx->dm.mixed) { if (prog) k_heavy_hex<HEAVY_CTAS_PER_SM, true><<<gh, TPB, 0, st>>>(I); else k_heavy_hex<HEAVY_CTAS_PER_SM, false><<<gh, TPB, 0, st>>>(I); }
         if (!ctx->dm.is_hex) { if (prog) k_heavy_general<true><<<gh, TPB, 0, st>>>(I); else k_heavy_general<false><<<gh, TPB, 0, st>>>(I); }
     };
