@@ -940,7 +940,6 @@ struct sdfibm_context {
     GraphKey graph_key = {0};
     cudaGraphExec_t graph_exec = nullptr;
     bool use_graph = true;
-    int classify4_refine = 1;            // SDFIBM_CLASSIFY4_REFINE=0: refinable shape tables keep the one-position kernel
     bool bin_fixed = false;              // tile bins with BIN_FIXED_CAP slots each (set per mesh; a tile that overflows switches the context to scan + fill)
     bool bin_fixed_allowed = true;       // SDFIBM_BIN_FIXED=0
     bool part_shapes = true;             // SDFIBM_PART_SHAPES=0: one queue order for all shapes
