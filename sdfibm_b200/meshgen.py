@@ -40,9 +40,9 @@ def polymesh_from_faces(points, faces):
         if cb >= 0 and cb < ca:
             ca, cb = cb, ca
         p = pts[loop]
-        nrm = np.zeros(3)
-        for q in range(len(loop)):
-            nrm += np.cross(p[q], p[(q + 1) % len(loop)])
+        pn = np.roll(p, -1, axis=0)
+        nrm = np.array([(p[:, 1] * pn[:, 2] - p[:, 2] * pn[:, 1]).sum(), (p[:, 2] * pn[:, 0] - p[:, 0] * pn[:, 2]).sum(),
+                        (p[:, 0] * pn[:, 1] - p[:, 1] * pn[:, 0]).sum()])        # sum of p_q x p_(q+1): twice the area vector
         ref = (cen[cb] - cen[ca]) if cb >= 0 else (p.mean(axis=0) - cen[ca])
         if np.dot(nrm, ref) < 0:
             loop = loop[::-1]
