@@ -18,6 +18,7 @@ SHAPES = {
     "tail": dict(type="Circle_Tail", radius=0.3, ratio=1.0, thickness=0.1),
     "twotail": dict(type="Circle_TwoTail", radius=0.2, ratio=1.5, thickness=0.1),
     "plane": dict(type="Plane"),
+    "circle_tc": dict(type="Circle", radius=0.3),      # examples/taylor_couette/solidDict: circle1
 }
 MOTIONS = {
     "mask": dict(type="Motion01Mask", mask="b110001"),

@@ -85,6 +85,58 @@ def test_coupled_steps_match_oracle_chain(tmp_path):
     assert np.array_equal(got["pos"][-4:], [s["pos"] for s in solids[-4:]])
 
 
+def test_taylor_couette_example_through_the_facade(tmp_path):
+    """BASELINE config 3 as the reference sets it up — examples/taylor_couette: the five-block O-grid of its blockMeshDict
+    (sdfibm_b200.meshgen), the solidDict's one Circle r = 0.3 at the origin, material rho 2, Motion01Mask b000001 (free to spin about
+    z only: the torque-coupled motion), no gravity — three coupled steps through the C++ SolidCloud against the oracle chain."""
+    from sdfibm_b200.meshgen import ogrid_taylor_couette
+
+    motions = dict(onlyzrot1=dict(type="Motion01Mask", mask="b000001"))
+    materials = dict(mat1=dict(type="General", rho=2.0))
+    solids = [dict(shp_name="circle_tc", mot_name="onlyzrot1", mat_name="mat1", pos=(0.0, 0.0, 0.0), vel=(0.0, 0.0, 0.0), euler=(0.0, 0.0, 0.0))]
+    meta = dict(on_fluid=1, on_twod=1, gravity=(0.0, 0.0, 0.0))
+    path = hc.write_case(tmp_path, meta, solids, motions=motions, materials=materials)
+    mesh = ogrid_taylor_couette(30)
+    # a swirling initial field (the outer cylinder drives the flow in the example): it exerts a torque on the inner circle
+    r2 = mesh.cc[:, 0] ** 2 + mesh.cc[:, 1] ** 2
+    U0 = np.stack([-mesh.cc[:, 1] * (0.5 + r2), mesh.cc[:, 0] * (0.5 + r2), np.zeros(mesh.n_cells)], axis=1)
+    rhof, dt = 1.0, 1e-3
+    hostapi.load().sdfibm_host_reset_subiterations()
+    cloud = hostapi.HostCloud(path, str(tmp_path), mesh, rhof, start_time=0.0, U_init=U0)
+    table, index = hc.shape_table(solids)
+    ref = hc.oracle_solids(solids, motions=motions, materials=materials)
+    o = Oracle(mesh, True)
+    U = U0.copy()
+    t = 0.0
+    for step in range(3):
+        t += dt
+        cloud.interact(t, dt)
+        r = o.interact(table, ho.records(ref, index), U, dt, rhof)
+        assert np.array_equal(cloud.field("Ct"), r["Ct"]), step
+        for k in ("As", "Ts", "Fs"):
+            assert np.abs(cloud.field(k) - r[k]).max() <= 1e-9 * max(1.0, np.abs(r[k]).max()), (step, k)
+        _, fluid = cloud.forces()
+        assert np.abs(fluid - r["FT"]).max() <= 1e-9 * np.abs(r["FT"]).max(), step
+        assert abs(r["FT"][0, 5]) > 1e-3                                        # the swirl turns the circle
+        for i, sd in enumerate(ref):
+            sd.ff, sd.ft = tuple(r["FT"][i, :3]), tuple(r["FT"][i, 3:])
+        cloud.field("U")[:] = cloud.field("U") - cloud.field("Fs") * dt       # main.cpp:70
+        U = U - r["Fs"] * dt
+        cloud.evolve(t, dt)
+        ho.evolve(ref, t, dt, 20, meta["gravity"], rhof)
+        cloud.save_state()
+        cloud.fix_internal(dt)
+        U = o.fix_internal(table, ho.records(ref, index), r["Ct"], U)
+        x, q, v, om = hc.state_arrays(ref)
+        got = cloud.solids()
+        for a_, b_ in ((got["pos"], x), (got["quat"], q), (got["vel"], v), (got["omega"], om)):
+            assert np.abs(a_ - b_).max() <= 1e-8 * max(1.0, np.abs(b_).max()), step
+        assert np.abs(cloud.field("U") - U).max() <= 1e-8 * np.abs(U).max(), step
+    got = cloud.solids()
+    assert np.array_equal(got["pos"][0], (0.0, 0.0, 0.0)) and got["omega"][0, 2] != 0.0 and not got["omega"][0, :2].any()   # only z rotation is free
+    cloud.close()
+
+
 def test_standalone_runner_3d(tmp_path):
     """sdfibm_b200_run: the main.cpp-shaped loop without OpenFOAM on a small 3-D case."""
     solids = [dict(shp_name="sph", mot_name="free", mat_name="heavy", pos=(1.6, 1.7, 1.5), omega=(0.0, 0.0, 0.5)),
